@@ -1,0 +1,122 @@
+/* mantis_b200 -- C ABI of the B200-native (sm_100a) kernels behind the Mantis interleaved multi-image hot path.
+ *
+ * The reference (TIGER-AI-Lab/Mantis) is pure Python over HuggingFace transformers: it has no FFI / plugin
+ * layer, its boundary is the nn.Module API.  This header is therefore the boundary
+ * *beneath* the module shell in mantis_b200/models: every entry point replaces the ATen / cuBLAS / flash-attn
+ * call sequence of the reference code cited next to it.
+ *
+ * Conventions: raw device pointers + explicit sizes/strides; no allocation, no ownership transfer, no implicit
+ * synchronisation; `stream` is a cudaStream_t passed as void*; `dtype` is MB200_DTYPE_{F32,BF16}; every function
+ * returns 0 or a negative errno (-EINVAL bad argument, -ENOTSUP operands not eligible for the fast path, -EIO launch
+ * failure; mb200_last_error() has the detail).  All entry points are re-entrant and thread-safe.
+ */
+#ifndef MANTIS_B200_H
+#define MANTIS_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB200_DTYPE_F32 0
+#define MB200_DTYPE_BF16 1
+
+/* ---- library ---------------------------------------------------------------------------------------------- */
+int mb200_version(void);
+const char* mb200_last_error(void);
+int mb200_check_device(void);
+int mb200_num_sms(void);
+
+/* ---- image-token merge: LlavaForConditionalGeneration._merge_input_ids_with_image_features
+ *      (mantis/models/mllava/modeling_llava.py:293-360), bit-exact integer outputs ------------------------- */
+long long mb200_merge_ws_bytes(int B, int T_len);
+int mb200_merge_plan(const int64_t* ids, const void* embeds, int dtype, int B, int T_len, int D, int P,
+                     int64_t image_token, int64_t pad_token, void* ws, int64_t* header_dev, void* stream);
+int mb200_merge_index(const int64_t* ids, const int64_t* attn, const int64_t* labels, const void* ws, int B,
+                      int T_len, int P, int S, int left_padding, int64_t image_token, int64_t ignore_index,
+                      int32_t* srcmap, int64_t* out_mask, int64_t* out_labels, int64_t* out_pos, void* stream);
+int mb200_merge_rows(const int32_t* srcmap, const void* text, const void* img, void* out, int B, int S, int T_len,
+                     long long row_bytes, long long n_img_rows, void* stream);
+int mb200_merge_rows_bwd(const int32_t* srcmap, const void* gout, void* gtext, void* gimg, int B, int S, int T_len,
+                         long long row_bytes, long long n_img_rows, void* stream);
+
+/* ---- token embedding gather / scatter-add (modeling_llava.py:427 -> nn.Embedding) ------------------------- */
+int mb200_embedding_fwd(const int64_t* ids, const void* table, void* out, long long n, int D, long long V, int dtype,
+                        void* stream);
+int mb200_embedding_bwd(const int64_t* ids, const void* gout, void* gtable, long long n, int D, long long V, int dtype,
+                        void* stream);
+
+/* ---- norms: LlamaRMSNorm (transformers llama/modeling_llama.py:53-68), Idefics2RMSNorm
+ *      (mantis/models/idefics2/modeling_idefics2.py:795-809), nn.LayerNorm (siglip/modeling_siglip.py:334-336) */
+int mb200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, long long n, int D, float eps, int dtype,
+                      void* stream);
+int mb200_norm_bwd_parts(long long n);
+int mb200_rmsnorm_bwd(const void* x, const void* w, const void* dy, const float* rstd, void* dx, float* dw_part,
+                      void* dw, int accumulate_dw, int accumulate_dx, long long n, int D, int dtype, void* stream);
+int mb200_layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, long long n,
+                        int D, float eps, int dtype, void* stream);
+int mb200_layernorm_bwd(const void* x, const void* w, const void* dy, const float* mean, const float* rstd, void* dx,
+                        float* dw_part, float* db_part, void* dw, void* db, int accumulate, long long n, int D,
+                        int dtype, void* stream);
+
+/* ---- RoPE, rotate_half form, in place (transformers llama/modeling_llama.py:146-168) ----------------------- */
+int mb200_rope(void* x, const int64_t* pos, const float* inv_freq, long long n_tok, int H, int hd,
+               long long tok_stride, float attn_scaling, int backward, int dtype, void* stream);
+
+/* ---- SwiGLU (llama/modeling_llama.py:182-184; idefics2 :506-521) and GELU family
+ *      (projector modeling_llava.py:110-118; SigLIP / CLIP MLP).  kind: 0 erf, 1 tanh, 2 quick ------------- */
+int mb200_swiglu_fwd(const void* gate, const void* up, void* out, long long n, int dtype, void* stream);
+int mb200_swiglu_bwd(const void* gate, const void* up, const void* dout, void* dgate, void* dup, long long n,
+                     int dtype, void* stream);
+int mb200_act_fwd(const void* x, void* y, long long n, int kind, int dtype, void* stream);
+int mb200_act_bwd(const void* x, const void* dy, void* dx, long long n, int kind, int dtype, void* stream);
+
+/* ---- residual add, position-embedding add, bias gradient, im2col (patch-embed conv as GEMM:
+ *      siglip/modeling_siglip.py:124-130,175-186), dtype cast ----------------------------------------------- */
+int mb200_add(const void* a, const void* b, void* y, long long n, int dtype, void* stream);
+int mb200_add_rows(const void* x, const void* table, const int64_t* idx, void* y, long long n, int D, long long period,
+                   int dtype, void* stream);
+int mb200_colsum_parts(long long n);
+int mb200_colsum(const void* x, float* part, void* out, int accumulate, long long n, int N, long long ld, int dtype,
+                 void* stream);
+int mb200_im2col(const void* px, int px_dtype, void* out, int out_dtype, int N, int C, int H, int W, int p, int Kpad,
+                 void* stream);
+int mb200_cast(const void* x, int in_dtype, void* y, int out_dtype, long long n, void* stream);
+
+/* ---- shifted masked cross-entropy (modeling_llava.py:523-537; modeling_idefics2.py:1883-1899) and AdamW ---- */
+int mb200_shift_labels(const int64_t* labels, const int64_t* mask, int64_t* out, int B, int S, int64_t ignore_index,
+                       float* count_out, void* stream);
+int mb200_ce_fwd_bwd(const void* logits, const int64_t* labels, float* loss_rows, float* lse_rows, void* dlogits,
+                     long long n, int V, long long ld, const float* gscale_ptr, float gscale_const, int dtype,
+                     void* stream);
+int mb200_ce_reduce(const float* loss_rows, const int64_t* labels, long long n, int V, float* out2, int accumulate,
+                    void* stream);
+int mb200_adamw(void* p, const void* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                float wd, int step, float grad_scale, int dtype, void* stream);
+int mb200_sumsq(const void* g, long long n, float* out, int dtype, void* stream);
+
+/* ---- GEMM: nn.Linear forward / dgrad / wgrad (llama/modeling_llama.py:171-184,238-249,487; siglip :270-273,
+ *      :320-321; projector modeling_llava.py:110-118).  mb200_gemm_bf16 = tcgen05 + TMEM + TMA path;
+ *      mb200_gemm_generic = shape-agnostic SIMT path (tiny configs, fp32 parity, cross-check) ---------------- */
+int mb200_gemm_generic(const void* A, const void* B, void* C, const void* bias, int M, int N, int K, long long lda,
+                       long long ldb, long long ldc, int transA, int transB, float alpha, float beta, int batch,
+                       long long strideA, long long strideB, long long strideC, int dtype_ab, int dtype_c,
+                       void* stream);
+int mb200_gemm_bf16(const void* A, const void* B, void* C, const void* bias, const void* addend, int M, int N, int K,
+                    long long lda, long long ldb, long long ldc, long long ld_add, int transA, int transB, int act,
+                    void* stream);
+
+/* ---- attention: softmax(q k^T * scale + causal/padding mask) v, GQA (llama/modeling_llama.py:199-289;
+ *      siglip/modeling_siglip.py:229-303; idefics2 perceiver :812-910).  q/o [B,Sq,H,hd], k/v [B,Sk,Hkv,hd];
+ *      strides = {q_b,q_s,q_h, k_b,k_s,k_h, v_b,v_s,v_h, o_b,o_s,o_h} in elements -------------------------- */
+int mb200_attn_generic_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Hkv,
+                           int Sq, int Sk, int hd, const long long* strides, float scale, int causal,
+                           const int64_t* kmask, long long kmask_sb, int dtype, void* stream);
+int mb200_attn_generic_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                           const float* lse, float* delta, void* dq, void* dk, void* dv, int B, int H, int Hkv, int Sq,
+                           int Sk, int hd, const long long* strides, float scale, int causal, const int64_t* kmask,
+                           long long kmask_sb, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MANTIS_B200_H */

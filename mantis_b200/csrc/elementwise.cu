@@ -1,0 +1,537 @@
+// HBM-bound row / elementwise kernels of the LLaVA / Idefics2 hot path (sm_100a).
+//   embedding gather + scatter-add backward   (modeling_llava.py:427 -> nn.Embedding)
+//   RMSNorm fwd/bwd                           (transformers llama/modeling_llama.py:53-68; idefics2 :795-809)
+//   LayerNorm fwd/bwd                         (transformers siglip/modeling_siglip.py:334-336, clip)
+//   RoPE (rotate_half form) fwd/bwd in place  (transformers llama/modeling_llama.py:146-168)
+//   SwiGLU silu(gate)*up fwd/bwd              (transformers llama/modeling_llama.py:182-184)
+//   GELU (erf / tanh / quick) fwd/bwd         (projector :110-118, SigLIP MLP, CLIP MLP)
+//   bias add, column-sum (bias grad), add, row-broadcast add (position embeddings), im2col
+// All reductions accumulate in fp32; in bf16 mode intermediate roundings follow the reference's
+// op-by-op bf16 evaluation order so that results track the HF path as closely as possible.
+#include "common.cuh"
+
+namespace {
+
+using mb::Cvt; using mb::Vec8;
+
+// ------------------------------------------------------------------ embedding
+template <typename T>
+__global__ void __launch_bounds__(256)
+embedding_fwd_kernel(const int64_t* __restrict__ ids, const T* __restrict__ table, T* __restrict__ out,
+                     long long n, int D, long long V) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long row_bytes = (long long)D * sizeof(T);
+  for (long long r = warp0; r < n; r += nwarps) {
+    long long id = ids[r];
+    T* dst = out + (size_t)r * D;
+    if (id < 0 || id >= V) { for (int i = lane; i < D; i += 32) dst[i] = Cvt<T>::from_f(0.f); continue; }
+    const T* src = table + (size_t)id * D;
+    if ((row_bytes & 15) == 0) {
+      const int4* s4 = reinterpret_cast<const int4*>(src); int4* d4 = reinterpret_cast<int4*>(dst);
+      const int nv = (int)(row_bytes >> 4);
+      for (int i = lane; i < nv; i += 32) d4[i] = __ldg(s4 + i);
+    } else {
+      for (int i = lane; i < D; i += 32) dst[i] = src[i];
+    }
+  }
+}
+
+__device__ __forceinline__ void atomic_add_T(float* p, float v) { atomicAdd(p, v); }
+__device__ __forceinline__ void atomic_add_T(bf16* p, float v) { atomicAdd(p, __float2bfloat16_rn(v)); }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+embedding_bwd_kernel(const int64_t* __restrict__ ids, const T* __restrict__ gout, T* __restrict__ gtable,
+                     long long n, int D, long long V) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp0; r < n; r += nwarps) {
+    long long id = ids[r];
+    if (id < 0 || id >= V) continue;
+    const T* src = gout + (size_t)r * D;
+    T* dst = gtable + (size_t)id * D;
+    if (sizeof(T) == 2 && (D & 1) == 0) {
+      const bf162* s2 = reinterpret_cast<const bf162*>(src); bf162* d2 = reinterpret_cast<bf162*>(dst);
+      for (int i = lane; i < D / 2; i += 32) atomicAdd(d2 + i, s2[i]);
+    } else {
+      for (int i = lane; i < D; i += 32) atomic_add_T(dst + i, Cvt<T>::to_f(src[i]));
+    }
+  }
+}
+
+// ------------------------------------------------------------------ RMSNorm
+// y = w * T(x_f32 * rsqrt(mean(x^2) + eps))     (LlamaRMSNorm: cast to input dtype, then scale)
+template <typename T>
+__global__ void __launch_bounds__(256)
+rmsnorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w, T* __restrict__ y,
+                   float* __restrict__ rstd_out, long long n, int D, float eps) {
+  __shared__ float red[33];
+  for (long long r = blockIdx.x; r < n; r += gridDim.x) {
+    const T* xr = x + (size_t)r * D; T* yr = y + (size_t)r * D;
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) { float v = Cvt<T>::to_f(xr[i]); ss += v * v; }
+    ss = mb::block_sum(ss, red);
+    const float rstd = rsqrtf(ss / (float)D + eps);
+    if (threadIdx.x == 0 && rstd_out) rstd_out[r] = rstd;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+      float v = mb::rnd<T>(Cvt<T>::to_f(xr[i]) * rstd);
+      yr[i] = Cvt<T>::from_f(Cvt<T>::to_f(w[i]) * v);
+    }
+  }
+}
+
+// dx = rstd * (g - xhat * mean(g*xhat)), g = dy*w ; dw partial sums per CTA into dw_part[gridDim.x, D]
+template <typename T>
+__global__ void __launch_bounds__(256)
+rmsnorm_bwd_kernel(const T* __restrict__ x, const T* __restrict__ w, const T* __restrict__ dy,
+                   const float* __restrict__ rstd_in, T* __restrict__ dx, float* __restrict__ dw_part,
+                   long long n, int D, int accumulate_dx) {
+  extern __shared__ float dw_acc[];   // D floats
+  __shared__ float red[33];
+  for (int i = threadIdx.x; i < D; i += blockDim.x) dw_acc[i] = 0.f;
+  __syncthreads();
+  for (long long r = blockIdx.x; r < n; r += gridDim.x) {
+    const T* xr = x + (size_t)r * D; const T* gr = dy + (size_t)r * D; T* dxr = dx + (size_t)r * D;
+    const float rstd = rstd_in[r];
+    float dot = 0.f;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+      float xh = Cvt<T>::to_f(xr[i]) * rstd, g = Cvt<T>::to_f(gr[i]);
+      dot += g * Cvt<T>::to_f(w[i]) * xh;
+      dw_acc[i] += g * xh;
+    }
+    dot = mb::block_sum(dot, red) / (float)D;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+      float xh = Cvt<T>::to_f(xr[i]) * rstd, g = Cvt<T>::to_f(gr[i]) * Cvt<T>::to_f(w[i]);
+      float v = rstd * (g - xh * dot);
+      if (accumulate_dx) v += Cvt<T>::to_f(dxr[i]);
+      dxr[i] = Cvt<T>::from_f(v);
+    }
+  }
+  __syncthreads();
+  if (dw_part) for (int i = threadIdx.x; i < D; i += blockDim.x) dw_part[(size_t)blockIdx.x * D + i] = dw_acc[i];
+}
+
+// out[i] (+)= sum_p part[p, i]   -> T
+template <typename T>
+__global__ void colsum_partials_kernel(const float* __restrict__ part, int nparts, int D, T* __restrict__ out,
+                                       int accumulate) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += part[(size_t)p * D + i];
+  if (accumulate) s += Cvt<T>::to_f(out[i]);
+  out[i] = Cvt<T>::from_f(s);
+}
+
+// ------------------------------------------------------------------ LayerNorm
+template <typename T>
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w, const T* __restrict__ b,
+                     T* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                     long long n, int D, float eps) {
+  __shared__ float red[33];
+  for (long long r = blockIdx.x; r < n; r += gridDim.x) {
+    const T* xr = x + (size_t)r * D; T* yr = y + (size_t)r * D;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) s += Cvt<T>::to_f(xr[i]);
+    const float mean = mb::block_sum(s, red) / (float)D;
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) { float d = Cvt<T>::to_f(xr[i]) - mean; ss += d * d; }
+    const float rstd = rsqrtf(mb::block_sum(ss, red) / (float)D + eps);
+    if (threadIdx.x == 0) { if (mean_out) mean_out[r] = mean; if (rstd_out) rstd_out[r] = rstd; }
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+      float v = (Cvt<T>::to_f(xr[i]) - mean) * rstd;
+      v = v * Cvt<T>::to_f(w[i]) + (b ? Cvt<T>::to_f(b[i]) : 0.f);
+      yr[i] = Cvt<T>::from_f(v);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const T* __restrict__ x, const T* __restrict__ w, const T* __restrict__ dy,
+                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                     T* __restrict__ dx, float* __restrict__ dw_part, float* __restrict__ db_part,
+                     long long n, int D) {
+  extern __shared__ float acc[];   // 2*D floats: dw, db
+  __shared__ float red[33];
+  float* dw_acc = acc; float* db_acc = acc + D;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) { dw_acc[i] = 0.f; db_acc[i] = 0.f; }
+  __syncthreads();
+  for (long long r = blockIdx.x; r < n; r += gridDim.x) {
+    const T* xr = x + (size_t)r * D; const T* gr = dy + (size_t)r * D; T* dxr = dx + (size_t)r * D;
+    const float mean = mean_in[r], rstd = rstd_in[r];
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+      float xh = (Cvt<T>::to_f(xr[i]) - mean) * rstd, g0 = Cvt<T>::to_f(gr[i]);
+      float g = g0 * Cvt<T>::to_f(w[i]);
+      s1 += g; s2 += g * xh;
+      dw_acc[i] += g0 * xh; db_acc[i] += g0;
+    }
+    s1 = mb::block_sum(s1, red) / (float)D;
+    s2 = mb::block_sum(s2, red) / (float)D;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+      float xh = (Cvt<T>::to_f(xr[i]) - mean) * rstd, g = Cvt<T>::to_f(gr[i]) * Cvt<T>::to_f(w[i]);
+      dxr[i] = Cvt<T>::from_f(rstd * (g - s1 - xh * s2));
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    if (dw_part) dw_part[(size_t)blockIdx.x * D + i] = dw_acc[i];
+    if (db_part) db_part[(size_t)blockIdx.x * D + i] = db_acc[i];
+  }
+}
+
+// ------------------------------------------------------------------ RoPE (in place)
+// x: [n_tok, H, hd] (row stride `tok_stride` elements), pos: [n_tok] int64, inv_freq: [hd/2] fp32
+// sign=+1 forward, -1 backward (rotation by -angle).
+template <typename T>
+__global__ void __launch_bounds__(256)
+rope_kernel(T* __restrict__ x, const int64_t* __restrict__ pos, const float* __restrict__ inv_freq,
+            long long n_tok, int H, int hd, long long tok_stride, float attn_scaling, float sign) {
+  const int half = hd >> 1;
+  const long long total = n_tok * H * half;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % half);
+    const long long th = idx / half;
+    const int h = (int)(th % H);
+    const long long t = th / H;
+    const float ang = (float)pos[t] * inv_freq[i];
+    float sn, cs;
+    sincosf(ang, &sn, &cs);
+    cs = mb::rnd<T>(cs * attn_scaling); sn = mb::rnd<T>(sn * attn_scaling) * sign;
+    T* p = x + (size_t)t * tok_stride + (size_t)h * hd;
+    const float x1 = Cvt<T>::to_f(p[i]), x2 = Cvt<T>::to_f(p[i + half]);
+    // q_embed = (q * cos) + (rotate_half(q) * sin), each product rounded to T like the reference
+    const float y1 = mb::rnd<T>(x1 * cs) + mb::rnd<T>(-x2 * sn);
+    const float y2 = mb::rnd<T>(x2 * cs) + mb::rnd<T>(x1 * sn);
+    p[i] = Cvt<T>::from_f(y1); p[i + half] = Cvt<T>::from_f(y2);
+  }
+}
+
+// ------------------------------------------------------------------ SwiGLU
+__device__ __forceinline__ float silu_f(float g) { return g / (1.f + __expf(-g)); }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+swiglu_fwd_kernel(const T* __restrict__ gate, const T* __restrict__ up, T* __restrict__ out, long long n8) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float g[8], u[8], o[8];
+    Vec8<T>::load(gate + i * 8, g); Vec8<T>::load(up + i * 8, u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = mb::rnd<T>(silu_f(g[j])) * u[j];
+    Vec8<T>::store(out + i * 8, o);
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+swiglu_bwd_kernel(const T* __restrict__ gate, const T* __restrict__ up, const T* __restrict__ dout,
+                  T* __restrict__ dgate, T* __restrict__ dup, long long n8) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float g[8], u[8], d[8], dg[8], du[8];
+    Vec8<T>::load(gate + i * 8, g); Vec8<T>::load(up + i * 8, u); Vec8<T>::load(dout + i * 8, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float sg = 1.f / (1.f + __expf(-g[j]));
+      const float s = g[j] * sg;
+      du[j] = d[j] * s;
+      dg[j] = d[j] * u[j] * (sg * (1.f + g[j] * (1.f - sg)));
+    }
+    Vec8<T>::store(dgate + i * 8, dg); Vec8<T>::store(dup + i * 8, du);
+  }
+}
+
+// ------------------------------------------------------------------ GELU family (kind: 0 erf, 1 tanh, 2 quick)
+__device__ __forceinline__ float act_fwd(float x, int kind) {
+  if (kind == 0) return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+  if (kind == 1) { const float k = 0.79788456080286535588f; return 0.5f * x * (1.f + tanhf(k * (x + 0.044715f * x * x * x))); }
+  return x / (1.f + __expf(-1.702f * x));
+}
+__device__ __forceinline__ float act_bwd(float x, int kind) {
+  if (kind == 0) {
+    const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+    return cdf + x * 0.39894228040143267794f * __expf(-0.5f * x * x);
+  }
+  if (kind == 1) {
+    const float k = 0.79788456080286535588f, c = 0.044715f;
+    const float u = k * (x + c * x * x * x), t = tanhf(u);
+    return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * k * (1.f + 3.f * c * x * x);
+  }
+  const float s = 1.f / (1.f + __expf(-1.702f * x));
+  return s + 1.702f * x * s * (1.f - s);
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long n8, int kind) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float a[8], o[8];
+    Vec8<T>::load(x + i * 8, a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = act_fwd(a[j], kind);
+    Vec8<T>::store(y + i * 8, o);
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+act_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, long long n8, int kind) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float a[8], d[8], o[8];
+    Vec8<T>::load(x + i * 8, a); Vec8<T>::load(dy + i * 8, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = d[j] * act_bwd(a[j], kind);
+    Vec8<T>::store(dx + i * 8, o);
+  }
+}
+
+// ------------------------------------------------------------------ add / bias / row-broadcast add
+template <typename T>
+__global__ void __launch_bounds__(256)
+add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, long long n8) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float p[8], q[8];
+    Vec8<T>::load(a + i * 8, p); Vec8<T>::load(b + i * 8, q);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) p[j] += q[j];
+    Vec8<T>::store(y + i * 8, p);
+  }
+}
+// y[r, :] = x[r, :] + table[idx ? idx[r] : (r % period), :]
+template <typename T>
+__global__ void __launch_bounds__(256)
+add_rows_kernel(const T* __restrict__ x, const T* __restrict__ table, const int64_t* __restrict__ idx,
+                T* __restrict__ y, long long n, int D, long long period) {
+  const long long total = n * D;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / D; const int c = (int)(e % D);
+    const long long tr = idx ? idx[r] : (r % period);
+    y[e] = Cvt<T>::from_f(Cvt<T>::to_f(x[e]) + Cvt<T>::to_f(table[(size_t)tr * D + c]));
+  }
+}
+// column sums of a [n, N] matrix (bias gradient): two stage, fp32 partials
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T* __restrict__ x, float* __restrict__ part, long long n, int N, long long ld) {
+  // grid.x over column tiles of 256, grid.y over row slabs
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long rows_per = (n + gridDim.y - 1) / gridDim.y;
+  const long long r0 = (long long)blockIdx.y * rows_per, r1 = min(n, r0 + rows_per);
+  if (c >= N) return;
+  float s = 0.f;
+  for (long long r = r0; r < r1; ++r) s += Cvt<T>::to_f(x[(size_t)r * ld + c]);
+  part[(size_t)blockIdx.y * N + c] = s;
+}
+
+// ------------------------------------------------------------------ im2col (patch embed as GEMM)
+// pixels [N, C, H, W] (Tin) -> patches [N*gh*gw, Kpad] (Tout), K order (c, ky, kx) == conv weight.flatten(1)
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(256)
+im2col_kernel(const Tin* __restrict__ px, Tout* __restrict__ out, int N, int C, int H, int W, int p,
+              int gh, int gw, int K, int Kpad) {
+  const long long total = (long long)N * gh * gw * Kpad;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(e % Kpad);
+    const long long row = e / Kpad;
+    float v = 0.f;
+    if (k < K) {
+      const int kx = k % p, ky = (k / p) % p, c = k / (p * p);
+      const int gx = (int)(row % gw), gy = (int)((row / gw) % gh);
+      const long long n = row / ((long long)gw * gh);
+      v = Cvt<Tin>::to_f(px[(((size_t)n * C + c) * H + (gy * p + ky)) * W + (gx * p + kx)]);
+    }
+    out[e] = Cvt<Tout>::from_f(v);
+  }
+}
+
+// ------------------------------------------------------------------ cast
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(256)
+cast_kernel(const Tin* __restrict__ x, Tout* __restrict__ y, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = Cvt<Tout>::from_f(Cvt<Tin>::to_f(x[i]));
+}
+
+inline int ew_grid(long long work_items, int threads = 256) {
+  long long g = (work_items + threads - 1) / threads;
+  long long cap = (long long)mb::num_sms() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+#define DISPATCH_T(dtype, ...)                                             \
+  if ((dtype) == MB200_DTYPE_BF16) { typedef bf16 T; __VA_ARGS__; }        \
+  else if ((dtype) == MB200_DTYPE_F32) { typedef float T; __VA_ARGS__; }   \
+  else return -EINVAL;
+
+extern "C" {
+
+int mb200_embedding_fwd(const int64_t* ids, const void* table, void* out, long long n, int D, long long V,
+                        int dtype, void* stream) {
+  if (n <= 0) return MB200_OK;
+  DISPATCH_T(dtype, (embedding_fwd_kernel<T><<<ew_grid(n * 32), 256, 0, (cudaStream_t)stream>>>(
+                        ids, (const T*)table, (T*)out, n, D, V)));
+  MB200_CHECK_LAUNCH(); return MB200_OK;
+}
+int mb200_embedding_bwd(const int64_t* ids, const void* gout, void* gtable, long long n, int D, long long V,
+                        int dtype, void* stream) {
+  if (n <= 0) return MB200_OK;
+  DISPATCH_T(dtype, (embedding_bwd_kernel<T><<<ew_grid(n * 32), 256, 0, (cudaStream_t)stream>>>(
+                        ids, (const T*)gout, (T*)gtable, n, D, V)));
+  MB200_CHECK_LAUNCH(); return MB200_OK;
+}
+
+int mb200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, long long n, int D, float eps,
+                      int dtype, void* stream) {
+  if (n <= 0) return MB200_OK;
+  int grid = (int)(n < (long long)mb::num_sms() * 8 ? n : (long long)mb::num_sms() * 8);
+  DISPATCH_T(dtype, (rmsnorm_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)x, (const T*)w, (T*)y, rstd, n, D, eps)));
+  MB200_CHECK_LAUNCH(); return MB200_OK;
+}
+// number of partial rows the bwd kernels write (= grid size); caller allocates [parts, D] fp32 per output
+int mb200_norm_bwd_parts(long long n) {
+  long long g = (long long)mb::num_sms() * 2; if (n < g) g = n; if (g < 1) g = 1; return (int)g;
+}
+int mb200_rmsnorm_bwd(const void* x, const void* w, const void* dy, const float* rstd, void* dx,
+                      float* dw_part, void* dw, int accumulate_dw, int accumulate_dx, long long n, int D,
+                      int dtype, void* stream) {
+  if (n <= 0) return MB200_OK;
+  const int grid = mb200_norm_bwd_parts(n);
+  const size_t smem = (size_t)D * sizeof(float);
+  DISPATCH_T(dtype, {
+    cudaFuncSetAttribute(rmsnorm_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    rmsnorm_bwd_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>((const T*)x, (const T*)w, (const T*)dy, rstd,
+                                                                   (T*)dx, dw_part, n, D, accumulate_dx);
+    if (dw && dw_part)
+      colsum_partials_kernel<T><<<(D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dw_part, grid, D, (T*)dw, accumulate_dw);
+  });
+  MB200_CHECK_LAUNCH(); return MB200_OK;
+}
+
+int mb200_layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd,
+                        long long n, int D, float eps, int dtype, void* stream) {
+  if (n <= 0) return MB200_OK;
+  int grid = (int)(n < (long long)mb::num_sms() * 8 ? n : (long long)mb::num_sms() * 8);
+  DISPATCH_T(dtype, (layernorm_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)x, (const T*)w, (const T*)b, (T*)y, mean, rstd, n, D, eps)));
+  MB200_CHECK_LAUNCH(); return MB200_OK;
+}
+int mb200_layernorm_bwd(const void* x, const void* w, const void* dy, const float* mean, const float* rstd,
+                        void* dx, float* dw_part, float* db_part, void* dw, void* db, int accumulate,
+                        long long n, int D, int dtype, void* stream) {
+  if (n <= 0) return MB200_OK;
+  const int grid = mb200_norm_bwd_parts(n);
+  const size_t smem = (size_t)2 * D * sizeof(float);
+  DISPATCH_T(dtype, {
+    cudaFuncSetAttribute(layernorm_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    layernorm_bwd_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>((const T*)x, (const T*)w, (const T*)dy, mean, rstd,
+                                                                     (T*)dx, dw_part, db_part, n, D);
+    if (dw && dw_part)
+      colsum_partials_kernel<T><<<(D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dw_part, grid, D, (T*)dw, accumulate);
+    if (db && db_part)
+      colsum_partials_kernel<T><<<(D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(db_part, grid, D, (T*)db, accumulate);
+  });
+  MB200_CHECK_LAUNCH(); return MB200_OK;
+}
+
+int mb200_rope(void* x, const int64_t* pos, const float* inv_freq, long long n_tok, int H, int hd,
+               long long tok_stride, float attn_scaling, int backward, int dtype, void* stream) {
+  if (n_tok <= 0) return MB200_OK;
+  if (hd & 1) return -EINVAL;
+  const long long total = n_tok * H * (hd / 2);
+  DISPATCH_T(dtype, (rope_kernel<T><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(
+                        (T*)x, pos, inv_freq, n_tok, H, hd, tok_stride, attn_scaling, backward ? -1.f : 1.f)));
+  MB200_CHECK_LAUNCH(); return MB200_OK;
+}
+
+int mb200_swiglu_fwd(const void* gate, const void* up, void* out, long long n, int dtype, void* stream) {
+  if (n <= 0) return MB200_OK;
+  if (n & 7) return -EINVAL;
+  DISPATCH_T(dtype, (swiglu_fwd_kernel<T><<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)gate, (const T*)up, (T*)out, n / 8)));
+  MB200_CHECK_LAUNCH(); return MB200_OK;
+}
+int mb200_swiglu_bwd(const void* gate, const void* up, const void* dout, void* dgate, void* dup, long long n,
+                     int dtype, void* stream) {
+  if (n <= 0) return MB200_OK;
+  if (n & 7) return -EINVAL;
+  DISPATCH_T(dtype, (swiglu_bwd_kernel<T><<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)gate, (const T*)up, (const T*)dout, (T*)dgate, (T*)dup, n / 8)));
+  MB200_CHECK_LAUNCH(); return MB200_OK;
+}
+int mb200_act_fwd(const void* x, void* y, long long n, int kind, int dtype, void* stream) {
+  if (n <= 0) return MB200_OK;
+  if ((n & 7) || kind < 0 || kind > 2) return -EINVAL;
+  DISPATCH_T(dtype, (act_fwd_kernel<T><<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, n / 8, kind)));
+  MB200_CHECK_LAUNCH(); return MB200_OK;
+}
+int mb200_act_bwd(const void* x, const void* dy, void* dx, long long n, int kind, int dtype, void* stream) {
+  if (n <= 0) return MB200_OK;
+  if ((n & 7) || kind < 0 || kind > 2) return -EINVAL;
+  DISPATCH_T(dtype, (act_bwd_kernel<T><<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)x, (const T*)dy, (T*)dx, n / 8, kind)));
+  MB200_CHECK_LAUNCH(); return MB200_OK;
+}
+int mb200_add(const void* a, const void* b, void* y, long long n, int dtype, void* stream) {
+  if (n <= 0) return MB200_OK;
+  if (n & 7) return -EINVAL;
+  DISPATCH_T(dtype, (add_kernel<T><<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)b, (T*)y, n / 8)));
+  MB200_CHECK_LAUNCH(); return MB200_OK;
+}
+int mb200_add_rows(const void* x, const void* table, const int64_t* idx, void* y, long long n, int D,
+                   long long period, int dtype, void* stream) {
+  if (n <= 0) return MB200_OK;
+  if (!idx && period <= 0) return -EINVAL;
+  DISPATCH_T(dtype, (add_rows_kernel<T><<<ew_grid(n * D), 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)x, (const T*)table, idx, (T*)y, n, D, period)));
+  MB200_CHECK_LAUNCH(); return MB200_OK;
+}
+int mb200_colsum_parts(long long n) { long long g = (n + 255) / 256; if (g > 64) g = 64; if (g < 1) g = 1; return (int)g; }
+int mb200_colsum(const void* x, float* part, void* out, int accumulate, long long n, int N, long long ld,
+                 int dtype, void* stream) {
+  if (n <= 0 || N <= 0) return MB200_OK;
+  const int parts = mb200_colsum_parts(n);
+  dim3 grid((N + 255) / 256, parts);
+  DISPATCH_T(dtype, {
+    colsum_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, part, n, N, ld);
+    colsum_partials_kernel<T><<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(part, parts, N, (T*)out, accumulate);
+  });
+  MB200_CHECK_LAUNCH(); return MB200_OK;
+}
+int mb200_im2col(const void* px, int px_dtype, void* out, int out_dtype, int N, int C, int H, int W, int p,
+                 int Kpad, void* stream) {
+  if (N <= 0) return MB200_OK;
+  const int gh = H / p, gw = W / p, K = C * p * p;
+  if (Kpad < K) return -EINVAL;
+  const long long total = (long long)N * gh * gw * Kpad;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = ew_grid(total);
+  if (px_dtype == MB200_DTYPE_F32 && out_dtype == MB200_DTYPE_F32)
+    im2col_kernel<float, float><<<g, 256, 0, st>>>((const float*)px, (float*)out, N, C, H, W, p, gh, gw, K, Kpad);
+  else if (px_dtype == MB200_DTYPE_F32 && out_dtype == MB200_DTYPE_BF16)
+    im2col_kernel<float, bf16><<<g, 256, 0, st>>>((const float*)px, (bf16*)out, N, C, H, W, p, gh, gw, K, Kpad);
+  else if (px_dtype == MB200_DTYPE_BF16 && out_dtype == MB200_DTYPE_BF16)
+    im2col_kernel<bf16, bf16><<<g, 256, 0, st>>>((const bf16*)px, (bf16*)out, N, C, H, W, p, gh, gw, K, Kpad);
+  else if (px_dtype == MB200_DTYPE_BF16 && out_dtype == MB200_DTYPE_F32)
+    im2col_kernel<bf16, float><<<g, 256, 0, st>>>((const bf16*)px, (float*)out, N, C, H, W, p, gh, gw, K, Kpad);
+  else return -EINVAL;
+  MB200_CHECK_LAUNCH(); return MB200_OK;
+}
+int mb200_cast(const void* x, int in_dtype, void* y, int out_dtype, long long n, void* stream) {
+  if (n <= 0) return MB200_OK;
+  cudaStream_t st = (cudaStream_t)stream; const int g = ew_grid(n);
+  if (in_dtype == MB200_DTYPE_F32 && out_dtype == MB200_DTYPE_BF16) cast_kernel<float, bf16><<<g, 256, 0, st>>>((const float*)x, (bf16*)y, n);
+  else if (in_dtype == MB200_DTYPE_BF16 && out_dtype == MB200_DTYPE_F32) cast_kernel<bf16, float><<<g, 256, 0, st>>>((const bf16*)x, (float*)y, n);
+  else if (in_dtype == MB200_DTYPE_F32 && out_dtype == MB200_DTYPE_F32) cast_kernel<float, float><<<g, 256, 0, st>>>((const float*)x, (float*)y, n);
+  else if (in_dtype == MB200_DTYPE_BF16 && out_dtype == MB200_DTYPE_BF16) cast_kernel<bf16, bf16><<<g, 256, 0, st>>>((const bf16*)x, (bf16*)y, n);
+  else return -EINVAL;
+  MB200_CHECK_LAUNCH(); return MB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,664 @@
+"""torch-facing wrappers of the C-ABI kernels (mantis_b200/csrc) + autograd Functions.
+
+PyTorch is plumbing here (device memory, streams, autograd graph); every arithmetic op of the hot path is one of
+the hand-written CUDA kernels.  There is no CPU path: tensors must live on an sm_100a device.
+"""
+import ctypes
+import math
+import os
+
+import torch
+
+from . import _lib
+from ._lib import check
+
+F32, BF16 = 0, 1
+ACT_KINDS = {"gelu": 0, "gelu_pytorch_tanh": 1, "gelu_new": 1, "gelu_tanh": 1, "quick_gelu": 2}
+# epilogue codes of the tcgen05 GEMM: 0 none, 1 erf, 2 tanh, 3 quick
+_GEMM_ACT = {None: 0, "gelu": 1, "gelu_pytorch_tanh": 2, "gelu_new": 2, "gelu_tanh": 2, "quick_gelu": 3}
+
+# Minimum M*N*K for the tensor-core GEMM (below this the SIMT kernel is as fast and supports any alignment).
+FAST_GEMM_MIN_WORK = int(os.environ.get("MB200_FAST_GEMM_MIN_WORK", str(128 * 128 * 64)))
+FORCE_GENERIC = os.environ.get("MB200_FORCE_GENERIC", "0") == "1"
+
+launch_count = 0   # kernels (C-ABI calls) issued; bench.py reports it as gpu_launches
+
+
+def _L():
+    return _lib.lib()
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"mantis_b200 kernels support float32 and bfloat16, got {t.dtype}")
+
+
+def _p(t):
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _st():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.MantisB200Error("mantis_b200 ops need CUDA tensors (there is no CPU fallback)")
+
+
+def _call(name, *args):
+    global launch_count
+    launch_count += 1
+    rc = getattr(_L(), name)(*args)
+    check(rc, name)
+
+
+# ---------------------------------------------------------------------------------------------- GEMM / linear
+def _fast_ok(a, b, M, N, K):
+    if FORCE_GENERIC or a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16:
+        return False
+    if M * N * K < FAST_GEMM_MIN_WORK or K < 8:
+        return False
+    return (a.stride(0) % 8 == 0 and b.stride(0) % 8 == 0 and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0)
+
+
+def gemm(a, b, trans_a=False, trans_b=True, bias=None, act=None, addend=None, out=None):
+    """out[M,N] = act(op(a) @ op(b) + bias) + addend.   a: [M,K] (or [K,M] if trans_a);  b: [N,K] if trans_b
+    (nn.Linear weight layout) else [K,N].  2-D tensors with unit inner stride."""
+    _need_cuda(a, b)
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1, "gemm operands must be 2-D, inner-contiguous"
+    M, K = (a.shape[1], a.shape[0]) if trans_a else (a.shape[0], a.shape[1])
+    N, Kb = (b.shape[0], b.shape[1]) if trans_b else (b.shape[1], b.shape[0])
+    assert K == Kb, f"gemm K mismatch {K} vs {Kb}"
+    if out is None:
+        out = torch.empty((M, N), dtype=a.dtype, device=a.device)
+    assert out.stride(1) == 1
+    if M == 0 or N == 0:
+        return out
+    if bias is not None:
+        bias = bias.contiguous()
+    if addend is not None:
+        assert addend.shape == out.shape and addend.stride(1) == 1
+    if _fast_ok(a, b, M, N, K) and out.dtype == torch.bfloat16:
+        _call("mb200_gemm_bf16", _p(a), _p(b), _p(out), _p(bias), _p(addend), M, N, K, a.stride(0), b.stride(0),
+              out.stride(0), addend.stride(0) if addend is not None else 0, int(trans_a), int(trans_b),
+              _GEMM_ACT[act], _st())
+        return out
+    # generic SIMT path
+    beta = 0.0
+    if addend is not None and act is None:
+        if addend.data_ptr() != out.data_ptr():
+            out.copy_(addend)
+        beta = 1.0
+    _call("mb200_gemm_generic", _p(a), _p(b), _p(out), _p(bias), M, N, K, a.stride(0), b.stride(0), out.stride(0),
+          int(trans_a), int(trans_b), 1.0, beta, 1, 0, 0, 0, _dt(a), _dt(out), _st())
+    if act is not None:
+        n = out.numel()
+        assert out.is_contiguous() and n % 8 == 0
+        _call("mb200_act_fwd", _p(out), _p(out), n, ACT_KINDS[act], _dt(out), _st())
+        if addend is not None:
+            _call("mb200_add", _p(out), _p(addend.contiguous()), _p(out), n, _dt(out), _st())
+    return out
+
+
+def colsum(x2d, out=None, accumulate=False):
+    """column sums of [n, N] -> [N] (bias gradients), fp32 accumulation"""
+    n, N = x2d.shape
+    assert x2d.stride(1) == 1
+    parts = _L().mb200_colsum_parts(n)
+    part = torch.empty((parts, N), dtype=torch.float32, device=x2d.device)
+    if out is None:
+        out = torch.empty((N,), dtype=x2d.dtype, device=x2d.device)
+    _call("mb200_colsum", _p(x2d), _p(part), _p(out), int(accumulate), n, N, x2d.stride(0), _dt(x2d), _st())
+    return out
+
+
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, act, residual):
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1])
+        if x2.stride(1) != 1:
+            x2 = x2.contiguous()
+        res2 = residual.reshape(-1, weight.shape[0]) if residual is not None else None
+        need_pre = act is not None and (x.requires_grad or weight.requires_grad)
+        if need_pre:
+            pre = gemm(x2, weight, bias=bias)
+            y = activation_fwd(pre, act)
+            if res2 is not None:
+                y = add(y, res2)
+        else:
+            pre = None
+            y = gemm(x2, weight, bias=bias, act=act, addend=res2)
+        ctx.save_for_backward(x2, weight, pre)
+        ctx.act = act
+        ctx.has_bias = bias is not None
+        ctx.has_res = residual is not None
+        ctx.in_shape = shp
+        return y.reshape(*shp[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, weight, pre = ctx.saved_tensors
+        g2 = gy.reshape(-1, weight.shape[0])
+        if g2.stride(1) != 1:
+            g2 = g2.contiguous()
+        gres = gy if ctx.has_res else None
+        if ctx.act is not None:
+            g2 = activation_bwd(pre, g2, ctx.act)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = gemm(g2, weight, trans_a=False, trans_b=False).reshape(ctx.in_shape)      # dx = dy @ W
+        if ctx.needs_input_grad[1]:
+            gw = gemm(g2, x2, trans_a=True, trans_b=False)                                 # dW = dy^T @ x
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = colsum(g2)
+        return gx, gw, gb, None, gres
+
+
+def linear(x, weight, bias=None, act=None, residual=None):
+    """y = act(x @ weight^T + bias) + residual  (weight in nn.Linear [out, in] layout)"""
+    return _LinearFn.apply(x, weight, bias, act, residual)
+
+
+# ---------------------------------------------------------------------------------------------- elementwise
+def activation_fwd(x, kind):
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    _call("mb200_act_fwd", _p(x), _p(y), x.numel(), ACT_KINDS[kind], _dt(x), _st())
+    return y
+
+
+def activation_bwd(x, dy, kind):
+    dy = dy.contiguous()
+    dx = torch.empty_like(x)
+    _call("mb200_act_bwd", _p(x), _p(dy), _p(dx), x.numel(), ACT_KINDS[kind], _dt(x), _st())
+    return dx
+
+
+class _ActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kind):
+        ctx.save_for_backward(x)
+        ctx.kind = kind
+        return activation_fwd(x, kind)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return activation_bwd(x.contiguous(), dy, ctx.kind), None
+
+
+def activation(x, kind):
+    return _ActFn.apply(x, kind)
+
+
+def add(a, b):
+    a = a.contiguous(); b = b.contiguous()
+    assert a.shape == b.shape and a.numel() % 8 == 0
+    y = torch.empty_like(a)
+    _call("mb200_add", _p(a), _p(b), _p(y), a.numel(), _dt(a), _st())
+    return y
+
+
+class _AddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        return add(a, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+def residual_add(a, b):
+    return _AddFn.apply(a, b)
+
+
+class _SwigluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gate, up):
+        gate = gate.contiguous(); up = up.contiguous()
+        out = torch.empty_like(gate)
+        _call("mb200_swiglu_fwd", _p(gate), _p(up), _p(out), gate.numel(), _dt(gate), _st())
+        ctx.save_for_backward(gate, up)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        gate, up = ctx.saved_tensors
+        dout = dout.contiguous()
+        dg = torch.empty_like(gate); du = torch.empty_like(up)
+        _call("mb200_swiglu_bwd", _p(gate), _p(up), _p(dout), _p(dg), _p(du), gate.numel(), _dt(gate), _st())
+        return dg, du
+
+
+def swiglu(gate, up):
+    """silu(gate) * up"""
+    return _SwigluFn.apply(gate, up)
+
+
+# ---------------------------------------------------------------------------------------------- norms
+class _RMSNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, eps):
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1]).contiguous()
+        n, D = x2.shape
+        y = torch.empty_like(x2)
+        rstd = torch.empty((n,), dtype=torch.float32, device=x.device)
+        w = w.contiguous()
+        _call("mb200_rmsnorm_fwd", _p(x2), _p(w), _p(y), _p(rstd), n, D, float(eps), _dt(x2), _st())
+        ctx.save_for_backward(x2, w, rstd)
+        ctx.shp = shp
+        return y.reshape(shp)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, rstd = ctx.saved_tensors
+        n, D = x2.shape
+        dy2 = dy.reshape(-1, D).contiguous()
+        dx = torch.empty_like(x2)
+        parts = _L().mb200_norm_bwd_parts(n)
+        need_w = ctx.needs_input_grad[1]
+        dw_part = torch.empty((parts, D), dtype=torch.float32, device=x2.device) if need_w else None
+        dw = torch.empty_like(w) if need_w else None
+        _call("mb200_rmsnorm_bwd", _p(x2), _p(w), _p(dy2), _p(rstd), _p(dx), _p(dw_part), _p(dw), 0, 0, n, D,
+              _dt(x2), _st())
+        return dx.reshape(ctx.shp), dw, None
+
+
+def rms_norm(x, weight, eps):
+    return _RMSNormFn.apply(x, weight, eps)
+
+
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1]).contiguous()
+        n, D = x2.shape
+        y = torch.empty_like(x2)
+        need = x.requires_grad or w.requires_grad
+        mean = torch.empty((n,), dtype=torch.float32, device=x.device)
+        rstd = torch.empty((n,), dtype=torch.float32, device=x.device)
+        w = w.contiguous(); b = b.contiguous() if b is not None else None
+        _call("mb200_layernorm_fwd", _p(x2), _p(w), _p(b), _p(y), _p(mean), _p(rstd), n, D, float(eps), _dt(x2), _st())
+        if need:
+            ctx.save_for_backward(x2, w, mean, rstd)
+        ctx.shp = shp
+        ctx.has_b = b is not None
+        return y.reshape(shp)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, mean, rstd = ctx.saved_tensors
+        n, D = x2.shape
+        dy2 = dy.reshape(-1, D).contiguous()
+        dx = torch.empty_like(x2)
+        parts = _L().mb200_norm_bwd_parts(n)
+        dw_part = torch.empty((parts, D), dtype=torch.float32, device=x2.device)
+        db_part = torch.empty((parts, D), dtype=torch.float32, device=x2.device)
+        dw = torch.empty_like(w)
+        db = torch.empty_like(w) if ctx.has_b else None
+        _call("mb200_layernorm_bwd", _p(x2), _p(w), _p(dy2), _p(mean), _p(rstd), _p(dx), _p(dw_part), _p(db_part),
+              _p(dw), _p(db), 0, n, D, _dt(x2), _st())
+        return dx.reshape(ctx.shp), dw, db, None
+
+
+def layer_norm(x, weight, bias, eps):
+    return _LayerNormFn.apply(x, weight, bias, eps)
+
+
+# ---------------------------------------------------------------------------------------------- embedding
+class _EmbeddingFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ids, table):
+        ids_c = ids.contiguous().to(torch.int64)
+        V, D = table.shape
+        out = torch.empty((*ids.shape, D), dtype=table.dtype, device=table.device)
+        _call("mb200_embedding_fwd", _p(ids_c), _p(table), _p(out), ids_c.numel(), D, V, _dt(table), _st())
+        ctx.save_for_backward(ids_c)
+        ctx.V, ctx.D = V, D
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (ids_c,) = ctx.saved_tensors
+        gout = gout.contiguous()
+        gt = torch.zeros((ctx.V, ctx.D), dtype=gout.dtype, device=gout.device)
+        _call("mb200_embedding_bwd", _p(ids_c), _p(gout), _p(gt), ids_c.numel(), ctx.D, ctx.V, _dt(gout), _st())
+        return None, gt
+
+
+def embedding(ids, table):
+    _need_cuda(ids, table)
+    assert table.is_contiguous()
+    return _EmbeddingFn.apply(ids, table)
+
+
+# ---------------------------------------------------------------------------------------------- RoPE
+def rope_inplace(x, pos, inv_freq, attn_scaling=1.0, backward=False):
+    """x: [B, S, H, hd] view (hd contiguous, token stride uniform) ; pos: [B, S] int64"""
+    B, S, H, hd = x.shape
+    assert x.stride(3) == 1 and x.stride(2) == hd and x.stride(0) == S * x.stride(1), "rope needs a [B,S,H,hd] view of a row-major buffer"
+    pos = pos.contiguous().to(torch.int64)
+    _call("mb200_rope", _p(x), _p(pos), _p(inv_freq), B * S, H, hd, x.stride(1), float(attn_scaling),
+          int(backward), _dt(x), _st())
+    return x
+
+
+class _RopeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, pos, inv_freq, attn_scaling):
+        qo = q.contiguous().clone() if q.requires_grad or not q.is_contiguous() else q
+        ko = k.contiguous().clone() if k.requires_grad or not k.is_contiguous() else k
+        rope_inplace(qo, pos, inv_freq, attn_scaling)
+        rope_inplace(ko, pos, inv_freq, attn_scaling)
+        ctx.save_for_backward(pos, inv_freq)
+        ctx.scaling = attn_scaling
+        return qo, ko
+
+    @staticmethod
+    def backward(ctx, dq, dk):
+        pos, inv_freq = ctx.saved_tensors
+        dq = dq.contiguous().clone(); dk = dk.contiguous().clone()
+        rope_inplace(dq, pos, inv_freq, ctx.scaling, backward=True)
+        rope_inplace(dk, pos, inv_freq, ctx.scaling, backward=True)
+        return dq, dk, None, None, None
+
+
+def rope(q, k, pos, inv_freq, attn_scaling=1.0):
+    """q: [B,S,H,hd], k: [B,S,Hkv,hd] -> rotated copies (rotate_half convention)"""
+    return _RopeFn.apply(q, k, pos, inv_freq, attn_scaling)
+
+
+# ---------------------------------------------------------------------------------------------- attention
+def _strides12(q, k, v, o):
+    arr = (ctypes.c_longlong * 12)(q.stride(0), q.stride(1), q.stride(2), k.stride(0), k.stride(1), k.stride(2),
+                                   v.stride(0), v.stride(1), v.stride(2), o.stride(0), o.stride(1), o.stride(2))
+    return arr
+
+
+def attention_fwd(q, k, v, causal, kmask, scale):
+    """q [B,Sq,H,hd], k/v [B,Sk,Hkv,hd] (hd contiguous). Returns (o [B,Sq,H,hd] contiguous, lse [B,H,Sq] fp32)."""
+    _need_cuda(q, k, v)
+    B, Sq, H, hd = q.shape
+    Sk, Hkv = k.shape[1], k.shape[2]
+    assert q.stride(3) == 1 and k.stride(3) == 1 and v.stride(3) == 1
+    o = torch.empty((B, Sq, H, hd), dtype=q.dtype, device=q.device)
+    lse = torch.empty((B, H, Sq), dtype=torch.float32, device=q.device)
+    if kmask is not None:
+        kmask = kmask.contiguous().to(torch.int64)
+        assert kmask.shape == (B, Sk)
+    st = _strides12(q, k, v, o)
+    _call("mb200_attn_generic_fwd", _p(q), _p(k), _p(v), _p(o), _p(lse), B, H, Hkv, Sq, Sk, hd, st, float(scale),
+          int(causal), _p(kmask), Sk if kmask is not None else 0, _dt(q), _st())
+    return o, lse
+
+
+def attention_bwd(q, k, v, o, do, lse, causal, kmask, scale):
+    B, Sq, H, hd = q.shape
+    Sk, Hkv = k.shape[1], k.shape[2]
+    do = do.contiguous()
+    assert o.is_contiguous()
+    qc, kc, vc = q.contiguous(), k.contiguous(), v.contiguous()
+    dq = torch.empty_like(qc); dk = torch.empty_like(kc); dv = torch.empty_like(vc)
+    delta = torch.empty((B, H, Sq), dtype=torch.float32, device=q.device)
+    st = _strides12(qc, kc, vc, o)
+    _call("mb200_attn_generic_bwd", _p(qc), _p(kc), _p(vc), _p(o), _p(do), _p(lse), _p(delta), _p(dq), _p(dk), _p(dv),
+          B, H, Hkv, Sq, Sk, hd, st, float(scale), int(causal), _p(kmask), Sk if kmask is not None else 0,
+          _dt(q), _st())
+    return dq, dk, dv
+
+
+class _AttentionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, causal, kmask, scale):
+        o, lse = attention_fwd(q, k, v, causal, kmask, scale)
+        if kmask is not None:
+            kmask = kmask.contiguous().to(torch.int64)
+        ctx.save_for_backward(q, k, v, o, lse, kmask)
+        ctx.causal, ctx.scale = causal, scale
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, o, lse, kmask = ctx.saved_tensors
+        dq, dk, dv = attention_bwd(q, k, v, o, do, lse, ctx.causal, kmask, ctx.scale)
+        return dq, dk, dv, None, None, None
+
+
+def attention(q, k, v, causal=False, kmask=None, scale=None):
+    """softmax(q k^T * scale + mask) v with GQA.  q [B,Sq,H,hd]; k,v [B,Sk,Hkv,hd]; kmask [B,Sk] (non-zero = attend)"""
+    if scale is None:
+        scale = 1.0 / math.sqrt(q.shape[-1])
+    return _AttentionFn.apply(q, k, v, bool(causal), kmask, float(scale))
+
+
+# ---------------------------------------------------------------------------------------------- merge (scatter)
+_merge_ws_cache = {}
+
+
+def _merge_ws(B, T, device):
+    need = _L().mb200_merge_ws_bytes(B, T)
+    key = (device, )
+    ws = _merge_ws_cache.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros((max(need, 1 << 16),), dtype=torch.uint8, device=device)
+        _merge_ws_cache[key] = ws
+    return ws
+
+
+def merge_plan(input_ids, inputs_embeds, P, image_token, pad_token):
+    """Runs the plan kernel and reads the 8-word header back (the ONE host sync of the merge: the output
+    length is data dependent).  Returns (ws, header list)."""
+    B, T = input_ids.shape
+    D = inputs_embeds.shape[-1]
+    ws = _merge_ws(B, T, input_ids.device)
+    header = torch.empty((8,), dtype=torch.int64, device=input_ids.device)
+    _call("mb200_merge_plan", _p(input_ids), _p(inputs_embeds), _dt(inputs_embeds), B, T, D, P, int(image_token),
+          int(pad_token), _p(ws), _p(header), _st())
+    return ws, header.tolist()
+
+
+class _MergeRowsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, inputs_embeds, image_features, srcmap, S):
+        B, T, D = inputs_embeds.shape
+        img2 = image_features.reshape(-1, D).contiguous()
+        text = inputs_embeds.contiguous()
+        out = torch.empty((B, S, D), dtype=text.dtype, device=text.device)
+        row_bytes = D * text.element_size()
+        _call("mb200_merge_rows", _p(srcmap), _p(text), _p(img2), _p(out), B, S, T, row_bytes, img2.shape[0], _st())
+        ctx.save_for_backward(srcmap)
+        ctx.dims = (B, T, D, S, tuple(image_features.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (srcmap,) = ctx.saved_tensors
+        B, T, D, S, img_shape = ctx.dims
+        gout = gout.contiguous()
+        gtext = gimg = None
+        if ctx.needs_input_grad[0]:
+            gtext = torch.zeros((B, T, D), dtype=gout.dtype, device=gout.device)
+        if ctx.needs_input_grad[1]:
+            gimg = torch.empty(img_shape, dtype=gout.dtype, device=gout.device)
+        n_img_rows = 1
+        for s in img_shape[:-1]:
+            n_img_rows *= s
+        _call("mb200_merge_rows_bwd", _p(srcmap), _p(gout), _p(gtext), _p(gimg), B, S, T,
+              D * gout.element_size(), n_img_rows, _st())
+        return gtext, gimg, None, None
+
+
+def merge_input_ids_with_image_features(image_features, inputs_embeds, input_ids, attention_mask, labels,
+                                        image_token_index, pad_token_id, ignore_index=-100):
+    """CUDA re-implementation of LlavaForConditionalGeneration._merge_input_ids_with_image_features
+    (mantis/models/mllava/modeling_llava.py:293-360).  Same return tuple, same ValueError."""
+    _need_cuda(image_features, inputs_embeds, input_ids)
+    num_images, P, D = image_features.shape
+    B, T = input_ids.shape
+    if (D * inputs_embeds.element_size()) % 16 != 0:
+        raise ValueError("embedding rows must be multiples of 16 bytes")
+    ids = input_ids.contiguous().to(torch.int64)
+    emb = inputs_embeds.contiguous()
+    mask_dtype = attention_mask.dtype
+    am = attention_mask.contiguous().to(torch.int64)
+    lab = labels.contiguous().to(torch.int64) if labels is not None else None
+    ws, hdr = merge_plan(ids, emb, P, image_token_index, pad_token_id)
+    S, left_padding, n_slots = int(hdr[0]), int(hdr[1]), int(hdr[2])
+    if n_slots != num_images * P:
+        raise ValueError(
+            f"The input provided to the model are wrong. The number of image tokens is {int(hdr[4])} while"
+            f" the number of image given to the model is {num_images}. This prevents correct indexing and breaks batch generation.")
+    dev = ids.device
+    srcmap = torch.empty((B, S), dtype=torch.int32, device=dev)
+    out_mask = torch.empty((B, S), dtype=torch.int64, device=dev)
+    out_pos = torch.empty((B, S), dtype=torch.int64, device=dev)
+    out_labels = torch.empty((B, S), dtype=torch.int64, device=dev) if lab is not None else None
+    _call("mb200_merge_index", _p(ids), _p(am), _p(lab), _p(ws), B, T, P, S, left_padding, int(image_token_index),
+          int(ignore_index), _p(srcmap), _p(out_mask), _p(out_labels), _p(out_pos), _st())
+    final = _MergeRowsFn.apply(emb, image_features, srcmap, S)
+    if mask_dtype != torch.int64:
+        out_mask = out_mask.to(mask_dtype)
+    return final, out_mask, out_labels, out_pos
+
+
+# ---------------------------------------------------------------------------------------------- loss
+def shift_labels(labels, attention_mask, ignore_index=-100):
+    """eff[b,s] = labels[b,s+1] if mask[b,s+1] != 0 and != ignore_index else -100 ; count of valid rows (fp32 scalar)"""
+    B, S = labels.shape
+    labels = labels.contiguous().to(torch.int64)
+    am = attention_mask.contiguous().to(torch.int64) if attention_mask is not None else None
+    out = torch.empty_like(labels)
+    count = torch.zeros((1,), dtype=torch.float32, device=labels.device)
+    _call("mb200_shift_labels", _p(labels), _p(am), _p(out), B, S, int(ignore_index), _p(count), _st())
+    return out, count
+
+
+LM_HEAD_CHUNK = int(os.environ.get("MB200_LM_HEAD_CHUNK", "4096"))
+
+
+class _LMHeadCEFn(torch.autograd.Function):
+    """Fused LM head + shifted masked cross-entropy: logits are produced chunk by chunk, consumed by the CE kernel
+    (which overwrites them with dlogits), and immediately folded into d(hidden) and d(W) -- the [B,S,V] logits
+    tensor (8 GB at Mantis-8B scale) is never materialised.  loss = sum_rows(lse - logit[target]) / n_valid."""
+
+    @staticmethod
+    def forward(ctx, hidden, weight, eff_labels, count):
+        h2 = hidden.reshape(-1, hidden.shape[-1])
+        if h2.stride(1) != 1:
+            h2 = h2.contiguous()
+        n, D = h2.shape
+        V = weight.shape[0]
+        lab = eff_labels.reshape(-1)
+        dev = h2.device
+        need_h, need_w = hidden.requires_grad, weight.requires_grad
+        ld = (V + 7) // 8 * 8
+        acc = torch.zeros((2,), dtype=torch.float32, device=dev)
+        inv = (1.0 / count).to(torch.float32)                # device scalar: dlogits scale (mean over valid rows)
+        dh = torch.empty_like(h2) if need_h else None
+        dw = None
+        chunk = min(LM_HEAD_CHUNK, n)
+        buf = torch.empty((chunk, ld), dtype=h2.dtype, device=dev)
+        loss_rows = torch.empty((chunk,), dtype=torch.float32, device=dev)
+        for r0 in range(0, n, chunk):
+            r1 = min(n, r0 + chunk)
+            m = r1 - r0
+            logits = buf[:m, :V]
+            gemm(h2[r0:r1], weight, out=logits)
+            _call("mb200_ce_fwd_bwd", _p(logits), _p(lab[r0:r1]), _p(loss_rows), None,
+                  _p(logits) if (need_h or need_w) else None, m, V, ld, _p(inv), 1.0, _dt(h2), _st())
+            _call("mb200_ce_reduce", _p(loss_rows), _p(lab[r0:r1]), m, V, _p(acc), 1, _st())
+            if need_h:
+                gemm(logits, weight, trans_a=False, trans_b=False, out=dh[r0:r1])
+            if need_w:
+                if dw is None:
+                    dw = gemm(logits, h2[r0:r1], trans_a=True, trans_b=False)
+                else:
+                    gemm(logits, h2[r0:r1], trans_a=True, trans_b=False, addend=dw, out=dw)
+        loss = (acc[0] / acc[1]).to(hidden.dtype if hidden.dtype == torch.float32 else torch.float32)
+        ctx.save_for_backward(dh, dw)
+        ctx.shape = hidden.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        dh, dw = ctx.saved_tensors
+        gh = gw = None
+        if dh is not None:
+            gh = (dh * gloss.to(dh.dtype)).reshape(ctx.shape)
+        if dw is not None:
+            gw = dw * gloss.to(dw.dtype)
+        return gh, gw, None, None
+
+
+def lm_head_ce(hidden, weight, eff_labels, count):
+    return _LMHeadCEFn.apply(hidden, weight, eff_labels, count)
+
+
+class _CEFn(torch.autograd.Function):
+    """cross-entropy over materialised logits [n, V] with labels (-100 = ignore), mean over valid rows"""
+
+    @staticmethod
+    def forward(ctx, logits2, lab, count):
+        n, V = logits2.shape
+        assert logits2.stride(1) == 1
+        dev = logits2.device
+        loss_rows = torch.empty((n,), dtype=torch.float32, device=dev)
+        acc = torch.zeros((2,), dtype=torch.float32, device=dev)
+        dl = torch.empty((n, V), dtype=logits2.dtype, device=dev) if logits2.requires_grad else None
+        inv = (1.0 / count).to(torch.float32)
+        _call("mb200_ce_fwd_bwd", _p(logits2), _p(lab), _p(loss_rows), None, _p(dl), n, V, logits2.stride(0), _p(inv), 1.0,
+              _dt(logits2), _st())
+        _call("mb200_ce_reduce", _p(loss_rows), _p(lab), n, V, _p(acc), 0, _st())
+        ctx.save_for_backward(dl)
+        return acc[0] / acc[1]
+
+    @staticmethod
+    def backward(ctx, g):
+        (dl,) = ctx.saved_tensors
+        return (dl * g.to(dl.dtype)) if dl is not None else None, None, None
+
+
+def cross_entropy(logits2, labels1, count):
+    return _CEFn.apply(logits2, labels1.contiguous(), count)
+
+
+# ---------------------------------------------------------------------------------------------- misc
+def im2col(pixels, patch, k_pad, out_dtype):
+    N, C, H, W = pixels.shape
+    px = pixels.contiguous()
+    gh, gw = H // patch, W // patch
+    out = torch.empty((N * gh * gw, k_pad), dtype=out_dtype, device=px.device)
+    _call("mb200_im2col", _p(px), _dt(px), _p(out), BF16 if out_dtype == torch.bfloat16 else F32, N, C, H, W, patch,
+          k_pad, _st())
+    return out
+
+
+def add_rows(x2, table, idx=None, period=None):
+    """y[r,:] = x[r,:] + table[idx[r] or r % period, :]"""
+    n, D = x2.shape
+    x2 = x2.contiguous(); table = table.contiguous()
+    y = torch.empty_like(x2)
+    if idx is not None:
+        idx = idx.contiguous().to(torch.int64)
+    _call("mb200_add_rows", _p(x2), _p(table), _p(idx), _p(y), n, D, int(period or 0), _dt(x2), _st())
+    return y
+
+
+def adamw_step(p, g, m, v, lr, beta1, beta2, eps, wd, step, grad_scale=1.0):
+    _call("mb200_adamw", _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
+          float(wd), int(step), float(grad_scale), _dt(p), _st())
+
+
+def sumsq(g, out):
+    _call("mb200_sumsq", _p(g), g.numel(), _p(out), _dt(g), _st())

@@ -1,0 +1,94 @@
+"""TEST INFRASTRUCTURE ONLY -- loads the UNMODIFIED reference classes from /root/reference.
+
+Only usable in the build container (the GPU box has no /root/reference).  Used by
+oracle/make_golden.py to generate tests/golden/*.pt fixtures and by `bench.py --impl reference`
+when baseline/_ref or /root/reference is present.
+
+Compat shim: the reference pins transformers<4.46 but the image has 5.5.0.
+ (1) mantis/models/mllava/__init__.py imports processing_llava which imports removed hub helpers
+     -> load configuration_llava.py / modeling_llava.py by file path under a synthetic package.
+ (2) `_supports_sdpa` is a property reading self.language_model -> class attribute.
+ (3) tie_weights() must accept kwargs.
+ (4) shim subclasses must live in a real .py file (this one).
+"""
+import importlib.util
+import os
+import sys
+import types
+
+REF_ROOTS = [os.environ.get("MANTIS_REF_ROOT", ""), "/root/reference",
+             os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "baseline", "_ref")]
+
+
+def find_ref_root():
+    for r in REF_ROOTS:
+        if r and os.path.isfile(os.path.join(r, "mantis", "models", "mllava", "modeling_llava.py")):
+            return os.path.abspath(r)
+    return None
+
+
+def _load(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+_CACHE = {}
+
+
+def load_reference_mllava():
+    """Returns (config_module, modeling_module) of the reference mllava, bypassing its __init__."""
+    if "mllava" in _CACHE:
+        return _CACHE["mllava"]
+    root = find_ref_root()
+    if root is None:
+        raise RuntimeError("reference tree not found (only available in the build container)")
+    base = os.path.join(root, "mantis", "models", "mllava")
+    pkg_name = "_mantis_ref.models.mllava"
+    for p in ("_mantis_ref", "_mantis_ref.models", pkg_name):
+        if p not in sys.modules:
+            m = types.ModuleType(p)
+            m.__path__ = []
+            sys.modules[p] = m
+    cfg = _load(pkg_name + ".configuration_llava", os.path.join(base, "configuration_llava.py"))
+    mod = _load(pkg_name + ".modeling_llava", os.path.join(base, "modeling_llava.py"))
+    _CACHE["mllava"] = (cfg, mod)
+    return cfg, mod
+
+
+def load_reference_idefics2():
+    if "idefics2" in _CACHE:
+        return _CACHE["idefics2"]
+    root = find_ref_root()
+    if root is None:
+        raise RuntimeError("reference tree not found (only available in the build container)")
+    pkg_name = "_mantis_ref.models.idefics2"
+    for p in ("_mantis_ref", "_mantis_ref.models", pkg_name):
+        if p not in sys.modules:
+            m = types.ModuleType(p)
+            m.__path__ = []
+            sys.modules[p] = m
+    mod = _load(pkg_name + ".modeling_idefics2",
+                os.path.join(root, "mantis", "models", "idefics2", "modeling_idefics2.py"))
+    _CACHE["idefics2"] = mod
+    return mod
+
+
+def ref_llava_classes():
+    cfg, modm = load_reference_mllava()
+
+    class RefLlava(modm.LlavaForConditionalGeneration):
+        _supports_sdpa = True
+
+        def tie_weights(self, *a, **k):
+            return None
+
+    class RefMLlava(modm.MLlavaForConditionalGeneration):
+        _supports_sdpa = True
+
+        def tie_weights(self, *a, **k):
+            return None
+
+    return cfg.LlavaConfig, RefLlava, RefMLlava
