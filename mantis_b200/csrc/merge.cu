@@ -264,9 +264,10 @@ extern "C" {
 
 // workspace sizes (bytes) the caller must provide
 long long mb200_merge_ws_bytes(int B, int T_len) {
-  // zflag [B*T] (rounded to 16) + rowinfo int64[4B] + ticket (16 B)
+  // ticket (16 B, fixed offset 0 so that it stays armed across calls with different shapes)
+  // + rowinfo int64[4B] + zflag [B*T] (rounded to 16)
   long long z = ((long long)B * T_len + 15) / 16 * 16;
-  return z + (long long)B * 4 * 8 + 16;
+  return 16 + (long long)B * 4 * 8 + z;
 }
 
 int mb200_merge_plan(const int64_t* ids, const void* embeds, int dtype, int B, int T_len, int D, int P,
@@ -274,10 +275,9 @@ int mb200_merge_plan(const int64_t* ids, const void* embeds, int dtype, int B, i
                      void* stream) {
   if (B <= 0 || T_len <= 0 || D <= 0 || P <= 0) return -EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
-  long long z = ((long long)B * T_len + 15) / 16 * 16;
-  uint8_t* zflag = (uint8_t*)ws;
-  int64_t* rowinfo = (int64_t*)((uint8_t*)ws + z);
-  unsigned int* ticket = (unsigned int*)((uint8_t*)ws + z + (long long)B * 32);
+  unsigned int* ticket = (unsigned int*)ws;
+  int64_t* rowinfo = (int64_t*)((uint8_t*)ws + 16);
+  uint8_t* zflag = (uint8_t*)ws + 16 + (long long)B * 32;
   // ticket must be zero on first use: caller zero-initialises ws once; the kernel re-arms it.
   if (dtype == MB200_DTYPE_BF16)
     merge_plan_kernel<bf16><<<B, kPlanThreads, 0, st>>>(ids, (const bf16*)embeds, B, T_len, D, P, image_token,
@@ -295,9 +295,8 @@ int mb200_merge_index(const int64_t* ids, const int64_t* attn, const int64_t* la
                       int64_t ignore_index, int32_t* srcmap, int64_t* out_mask, int64_t* out_labels,
                       int64_t* out_pos, void* stream) {
   if (B <= 0 || T_len <= 0 || S < T_len) return -EINVAL;
-  long long z = ((long long)B * T_len + 15) / 16 * 16;
-  const uint8_t* zflag = (const uint8_t*)ws;
-  const int64_t* rowinfo = (const int64_t*)((const uint8_t*)ws + z);
+  const int64_t* rowinfo = (const int64_t*)((const uint8_t*)ws + 16);
+  const uint8_t* zflag = (const uint8_t*)ws + 16 + (long long)B * 32;
   merge_index_kernel<<<B, kIndexThreads, 0, (cudaStream_t)stream>>>(
       ids, attn, labels, zflag, rowinfo, B, T_len, P, S, left_padding, image_token, ignore_index,
       srcmap, out_mask, labels ? out_labels : nullptr, out_pos);

@@ -1,0 +1,235 @@
+"""LLaMA / Mistral decoder stack on the mantis_b200 kernels.
+
+Mirrors transformers' LlamaForCausalLM / LlamaModel / MistralModel (llama/modeling_llama.py:53-499,
+mistral/modeling_mistral.py) -- same module tree and parameter names (`model.embed_tokens`, `model.layers.N.
+self_attn.{q,k,v,o}_proj`, `mlp.{gate,up,down}_proj`, `input_layernorm`, `post_attention_layernorm`, `model.norm`,
+`lm_head`) so reference checkpoints load unchanged -- but every op is one of our CUDA kernels:
+RMSNorm -> tcgen05 GEMMs (q,k,v) -> RoPE with caller-supplied position_ids -> causal GQA attention with key
+padding mask (+ KV cache) -> o_proj with fused residual -> RMSNorm -> gate/up GEMMs -> SwiGLU -> down_proj with
+fused residual.
+"""
+import torch
+from torch import nn
+from transformers import PreTrainedModel
+from transformers.modeling_outputs import BaseModelOutputWithPast, CausalLMOutputWithPast
+
+from .. import ops
+from .kv_cache import B200KVCache
+from .layers import B200Embedding, B200Linear, B200RMSNorm, default_inv_freq, llama3_inv_freq
+
+try:
+    from transformers import LlamaConfig, MistralConfig
+except Exception:  # pragma: no cover
+    LlamaConfig = MistralConfig = None
+
+
+def _rope_params(config):
+    theta = getattr(config, "rope_theta", None)
+    rs = getattr(config, "rope_scaling", None)
+    rp = getattr(config, "rope_parameters", None)
+    if isinstance(rp, dict):
+        theta = rp.get("rope_theta", theta)
+        if rp.get("rope_type", "default") != "default":
+            rs = rp
+    if theta is None:
+        theta = 10000.0
+    return float(theta), rs
+
+
+class B200Attention(nn.Module):
+    def __init__(self, config, layer_idx):
+        super().__init__()
+        self.layer_idx = layer_idx
+        self.hidden_size = config.hidden_size
+        self.num_heads = config.num_attention_heads
+        self.num_kv_heads = getattr(config, "num_key_value_heads", None) or self.num_heads
+        self.head_dim = getattr(config, "head_dim", None) or self.hidden_size // self.num_heads
+        bias = bool(getattr(config, "attention_bias", False))
+        self.q_proj = B200Linear(self.hidden_size, self.num_heads * self.head_dim, bias=bias)
+        self.k_proj = B200Linear(self.hidden_size, self.num_kv_heads * self.head_dim, bias=bias)
+        self.v_proj = B200Linear(self.hidden_size, self.num_kv_heads * self.head_dim, bias=bias)
+        self.o_proj = B200Linear(self.num_heads * self.head_dim, self.hidden_size, bias=bias)
+        self.scaling = self.head_dim ** -0.5
+
+    def forward(self, x, residual, position_ids, inv_freq, rope_scale, key_mask, cache):
+        B, S, _ = x.shape
+        q = self.q_proj(x).view(B, S, self.num_heads, self.head_dim)
+        k = self.k_proj(x).view(B, S, self.num_kv_heads, self.head_dim)
+        v = self.v_proj(x).view(B, S, self.num_kv_heads, self.head_dim)
+        q, k = ops.rope(q, k, position_ids, inv_freq, rope_scale)
+        if cache is not None:
+            k, v = cache.append(k, v, self.layer_idx)
+        o = ops.attention(q, k, v, causal=True, kmask=key_mask, scale=self.scaling)
+        return self.o_proj(o.view(B, S, self.num_heads * self.head_dim), residual=residual)
+
+
+class B200MLP(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        bias = bool(getattr(config, "mlp_bias", False))
+        self.gate_proj = B200Linear(config.hidden_size, config.intermediate_size, bias=bias)
+        self.up_proj = B200Linear(config.hidden_size, config.intermediate_size, bias=bias)
+        self.down_proj = B200Linear(config.intermediate_size, config.hidden_size, bias=bias)
+
+    def forward(self, x, residual=None):
+        return self.down_proj(ops.swiglu(self.gate_proj(x), self.up_proj(x)), residual=residual)
+
+
+class B200DecoderLayer(nn.Module):
+    def __init__(self, config, layer_idx):
+        super().__init__()
+        self.self_attn = B200Attention(config, layer_idx)
+        self.mlp = B200MLP(config)
+        self.input_layernorm = B200RMSNorm(config.hidden_size, eps=config.rms_norm_eps)
+        self.post_attention_layernorm = B200RMSNorm(config.hidden_size, eps=config.rms_norm_eps)
+
+    def forward(self, x, position_ids, inv_freq, rope_scale, key_mask, cache):
+        x = self.self_attn(self.input_layernorm(x), x, position_ids, inv_freq, rope_scale, key_mask, cache)
+        x = self.mlp(self.post_attention_layernorm(x), residual=x)
+        return x
+
+
+class B200DecoderPreTrainedModel(PreTrainedModel):
+    base_model_prefix = "model"
+    supports_gradient_checkpointing = True
+    _no_split_modules = ["B200DecoderLayer"]
+    _supports_sdpa = True
+    _supports_flash_attn = True
+    _supports_flash_attn_2 = True
+
+    def _init_weights(self, module):
+        std = getattr(self.config, "initializer_range", 0.02)
+        if isinstance(module, nn.Linear):
+            module.weight.data.normal_(mean=0.0, std=std)
+            if module.bias is not None:
+                module.bias.data.zero_()
+        elif isinstance(module, nn.Embedding):
+            module.weight.data.normal_(mean=0.0, std=std)
+            if module.padding_idx is not None:
+                module.weight.data[module.padding_idx].zero_()
+        elif isinstance(module, B200RMSNorm):
+            module.weight.data.fill_(1.0)
+
+
+class B200DecoderModel(B200DecoderPreTrainedModel):
+    """== LlamaModel / MistralModel (sliding window is not applied: S << sliding_window on this path)."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.padding_idx = getattr(config, "pad_token_id", None)
+        self.vocab_size = config.vocab_size
+        self.embed_tokens = B200Embedding(config.vocab_size, config.hidden_size, self.padding_idx)
+        self.layers = nn.ModuleList([B200DecoderLayer(config, i) for i in range(config.num_hidden_layers)])
+        self.norm = B200RMSNorm(config.hidden_size, eps=config.rms_norm_eps)
+        self.gradient_checkpointing = False
+        self._inv_freq = {}
+        self.post_init()
+
+    def get_input_embeddings(self):
+        return self.embed_tokens
+
+    def set_input_embeddings(self, value):
+        self.embed_tokens = value
+
+    def rope_tables(self, device):
+        key = str(device)
+        if key not in self._inv_freq:
+            hd = self.layers[0].self_attn.head_dim
+            theta, rs = _rope_params(self.config)
+            scale = 1.0
+            if rs and rs.get("rope_type", rs.get("type", "default")) == "llama3":
+                inv = llama3_inv_freq(hd, theta, rs, device)
+            else:
+                inv = default_inv_freq(hd, theta, device)
+            self._inv_freq[key] = (inv.contiguous(), scale)
+        return self._inv_freq[key]
+
+    def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None,
+                inputs_embeds=None, use_cache=None, output_attentions=None, output_hidden_states=None,
+                return_dict=None, cache_position=None, **kwargs):
+        if (input_ids is None) == (inputs_embeds is None):
+            raise ValueError("You must specify exactly one of input_ids or inputs_embeds")
+        if inputs_embeds is None:
+            inputs_embeds = self.embed_tokens(input_ids)
+        B, S, _ = inputs_embeds.shape
+        use_cache = bool(use_cache) if use_cache is not None else False
+        cache = None
+        if use_cache or past_key_values is not None:
+            if past_key_values is None or not isinstance(past_key_values, B200KVCache):
+                if past_key_values is not None and hasattr(past_key_values, "get_seq_length") and past_key_values.get_seq_length() > 0:
+                    raise ValueError("mantis_b200 needs its own B200KVCache for cached decoding")
+                past_key_values = B200KVCache()
+            cache = past_key_values
+        past = cache.get_seq_length() if cache is not None else 0
+        if position_ids is None:
+            position_ids = torch.arange(past, past + S, device=inputs_embeds.device).unsqueeze(0).expand(B, S)
+        key_mask = None
+        if attention_mask is not None:
+            if attention_mask.dim() != 2:
+                raise ValueError("mantis_b200 expects a 2-D [batch, kv_len] attention_mask")
+            key_mask = attention_mask
+            if key_mask.shape[1] != past + S:
+                raise ValueError(f"attention_mask length {key_mask.shape[1]} != past({past}) + seq({S})")
+        inv_freq, rope_scale = self.rope_tables(inputs_embeds.device)
+        x = inputs_embeds
+        all_hidden = () if output_hidden_states else None
+        for layer in self.layers:
+            if output_hidden_states:
+                all_hidden += (x,)
+            if self.gradient_checkpointing and self.training and cache is None:
+                x = torch.utils.checkpoint.checkpoint(layer, x, position_ids, inv_freq, rope_scale, key_mask, None,
+                                                      use_reentrant=False)
+            else:
+                x = layer(x, position_ids, inv_freq, rope_scale, key_mask, cache)
+        x = self.norm(x)
+        if output_hidden_states:
+            all_hidden += (x,)
+        return BaseModelOutputWithPast(last_hidden_state=x, past_key_values=cache, hidden_states=all_hidden,
+                                       attentions=None)
+
+
+class B200CausalLM(B200DecoderPreTrainedModel):
+    """== LlamaForCausalLM: `.model` + `.lm_head` (untied for LLaMA-3)."""
+    _tied_weights_keys = {}
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.model = B200DecoderModel(config)
+        self.vocab_size = config.vocab_size
+        self.lm_head = B200Linear(config.hidden_size, config.vocab_size, bias=False)
+        self.post_init()
+
+    def get_input_embeddings(self):
+        return self.model.embed_tokens
+
+    def set_input_embeddings(self, value):
+        self.model.embed_tokens = value
+
+    def get_output_embeddings(self):
+        return self.lm_head
+
+    def set_output_embeddings(self, new):
+        self.lm_head = new
+
+    def set_decoder(self, decoder):
+        self.model = decoder
+
+    def get_decoder(self):
+        return self.model
+
+    def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None,
+                inputs_embeds=None, labels=None, use_cache=None, output_attentions=None, output_hidden_states=None,
+                return_dict=None, logits_to_keep=0, **kwargs):
+        out = self.model(input_ids=input_ids, attention_mask=attention_mask, position_ids=position_ids,
+                         past_key_values=past_key_values, inputs_embeds=inputs_embeds, use_cache=use_cache,
+                         output_hidden_states=output_hidden_states)
+        h = out.last_hidden_state
+        if isinstance(logits_to_keep, int) and logits_to_keep > 0:
+            h = h[:, -logits_to_keep:, :]
+        logits = self.lm_head(h)
+        loss = None
+        if labels is not None:
+            eff, count = ops.shift_labels(labels, None)
+            loss = ops.cross_entropy(logits.reshape(-1, logits.shape[-1]), eff.reshape(-1), count)
+        return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=out.past_key_values,
+                                      hidden_states=out.hidden_states, attentions=None)

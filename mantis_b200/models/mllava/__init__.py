@@ -1,0 +1,6 @@
+from .configuration_llava import LlavaConfig, mantis_8b_siglip_llama3_config
+from .modeling_llava import (LlavaCausalLMOutputWithPast, LlavaForConditionalGeneration,
+                             MLlavaForConditionalGeneration)
+
+__all__ = ["LlavaConfig", "LlavaForConditionalGeneration", "MLlavaForConditionalGeneration",
+           "LlavaCausalLMOutputWithPast", "mantis_8b_siglip_llama3_config"]

@@ -1,0 +1,267 @@
+"""SigLIP / CLIP vision towers on the mantis_b200 kernels.
+
+Mirror transformers' SiglipVisionModel (siglip/modeling_siglip.py:116-710) and CLIPVisionModel
+(clip/modeling_clip.py) -- same module tree / parameter names (`vision_model.embeddings.patch_embedding`,
+`...position_embedding`, `encoder.layers.N.{layer_norm1,self_attn.{q,k,v,out}_proj,layer_norm2,mlp.fc{1,2}}`,
+`post_layernorm`, SigLIP `head.*`, CLIP `class_embedding` / `pre_layrnorm`) so reference checkpoints load
+unchanged.  Patch embedding is an im2col + tcgen05 GEMM (K padded to a TMA-legal multiple), attention is
+bidirectional.  Only the encoder layers needed for `hidden_states[vision_feature_layer]` are evaluated: the
+reference computes (and discards) the last layer, post_layernorm and the SigLIP MAP head
+(mantis/models/mllava/modeling_llava.py:456-458).
+"""
+import torch
+from torch import nn
+from transformers import PreTrainedModel
+from transformers.modeling_outputs import BaseModelOutputWithPooling
+
+from .. import ops
+from .layers import B200LayerNorm, B200Linear
+
+
+class B200VisionAttention(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.embed_dim = config.hidden_size
+        self.num_heads = config.num_attention_heads
+        self.head_dim = self.embed_dim // self.num_heads
+        self.scale = self.head_dim ** -0.5
+        self.q_proj = B200Linear(self.embed_dim, self.embed_dim)
+        self.k_proj = B200Linear(self.embed_dim, self.embed_dim)
+        self.v_proj = B200Linear(self.embed_dim, self.embed_dim)
+        self.out_proj = B200Linear(self.embed_dim, self.embed_dim)
+
+    def forward(self, x, residual, key_mask=None):
+        B, L, _ = x.shape
+        q = self.q_proj(x).view(B, L, self.num_heads, self.head_dim)
+        k = self.k_proj(x).view(B, L, self.num_heads, self.head_dim)
+        v = self.v_proj(x).view(B, L, self.num_heads, self.head_dim)
+        o = ops.attention(q, k, v, causal=False, kmask=key_mask, scale=self.scale)
+        return self.out_proj(o.view(B, L, self.embed_dim), residual=residual)
+
+
+class B200VisionMLP(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.act = config.hidden_act
+        self.fc1 = B200Linear(config.hidden_size, config.intermediate_size)
+        self.fc2 = B200Linear(config.intermediate_size, config.hidden_size)
+
+    def forward(self, x, residual=None):
+        return self.fc2(self.fc1(x, act=self.act), residual=residual)
+
+
+class B200VisionEncoderLayer(nn.Module):
+    """pre-LN block shared by SigLIP, CLIP and the Idefics2 vision transformer"""
+
+    def __init__(self, config):
+        super().__init__()
+        self.self_attn = B200VisionAttention(config)
+        self.layer_norm1 = B200LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+        self.mlp = B200VisionMLP(config)
+        self.layer_norm2 = B200LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+
+    def forward(self, x, key_mask=None):
+        x = self.self_attn(self.layer_norm1(x), x, key_mask)
+        x = self.mlp(self.layer_norm2(x), residual=x)
+        return x
+
+
+class B200VisionEncoder(nn.Module):
+    """== CLIPEncoder / SiglipEncoder: `.layers`"""
+
+    def __init__(self, config):
+        super().__init__()
+        self.layers = nn.ModuleList([B200VisionEncoderLayer(config) for _ in range(config.num_hidden_layers)])
+        self.gradient_checkpointing = False
+
+    def forward(self, x, num_layers=None, collect=False, key_mask=None):
+        hs = [x] if collect else None
+        n = len(self.layers) if num_layers is None else num_layers
+        for layer in self.layers[:n]:
+            if self.gradient_checkpointing and self.training and x.requires_grad:
+                x = torch.utils.checkpoint.checkpoint(layer, x, key_mask, use_reentrant=False)
+            else:
+                x = layer(x, key_mask)
+            if collect:
+                hs.append(x)
+        return x, hs
+
+
+class PatchEmbedGemm:
+    """conv2d(kernel = stride = patch) as im2col + GEMM. Keeps a K-padded copy of the flattened conv weight."""
+
+    def __init__(self):
+        self._w = None
+        self._key = None
+
+    def weight2d(self, conv_weight, k_pad):
+        key = (conv_weight.data_ptr(), conv_weight._version, conv_weight.dtype, k_pad, conv_weight.device)
+        if self._key != key:
+            out_ch = conv_weight.shape[0]
+            w2 = conv_weight.detach().reshape(out_ch, -1)
+            if w2.shape[1] != k_pad:
+                w = torch.zeros((out_ch, k_pad), dtype=w2.dtype, device=w2.device)
+                w[:, : w2.shape[1]] = w2
+                w2 = w
+            self._w, self._key = w2.contiguous(), key
+        return self._w
+
+    def __call__(self, pixel_values, conv, patch):
+        K = conv.weight.shape[1] * patch * patch
+        k_pad = (K + 63) // 64 * 64 if conv.weight.dtype == torch.bfloat16 else (K + 7) // 8 * 8
+        patches = ops.im2col(pixel_values, patch, k_pad, conv.weight.dtype)
+        return ops.gemm(patches, self.weight2d(conv.weight, k_pad), bias=conv.bias)
+
+
+class B200SiglipVisionEmbeddings(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.embed_dim = config.hidden_size
+        self.patch_size = config.patch_size
+        self.patch_embedding = nn.Conv2d(config.num_channels, self.embed_dim, kernel_size=self.patch_size,
+                                         stride=self.patch_size, padding="valid")
+        self.num_patches = (config.image_size // self.patch_size) ** 2
+        self.num_positions = self.num_patches
+        self.position_embedding = nn.Embedding(self.num_positions, self.embed_dim)
+        self._pe = PatchEmbedGemm()
+
+    def forward(self, pixel_values):
+        N = pixel_values.shape[0]
+        x = self._pe(pixel_values, self.patch_embedding, self.patch_size)            # [N*L, d]
+        L = x.shape[0] // N
+        if L != self.num_positions:
+            raise ValueError(f"image gives {L} patches but position table has {self.num_positions}")
+        x = ops.add_rows(x, self.position_embedding.weight, period=L)
+        return x.view(N, L, self.embed_dim)
+
+
+class B200SiglipHeadParams(nn.Module):
+    """Parameter holder for SiglipMultiheadAttentionPoolingHead so checkpoints round-trip. The MAP head output is
+    computed and discarded by the reference hot path (modeling_llava.py:456-458); it is not evaluated here."""
+
+    def __init__(self, config):
+        super().__init__()
+        d = config.hidden_size
+        self.probe = nn.Parameter(torch.randn(1, 1, d))
+        self.attention = nn.MultiheadAttention(d, config.num_attention_heads, batch_first=True)
+        self.layernorm = nn.LayerNorm(d, eps=config.layer_norm_eps)
+        self.mlp = B200VisionMLP(config)
+
+
+class B200SiglipVisionTransformer(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.embeddings = B200SiglipVisionEmbeddings(config)
+        self.encoder = B200VisionEncoder(config)
+        self.post_layernorm = B200LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+        self.use_head = getattr(config, "vision_use_head", True)
+        if self.use_head:
+            self.head = B200SiglipHeadParams(config)
+
+
+class B200CLIPVisionEmbeddings(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.embed_dim = config.hidden_size
+        self.patch_size = config.patch_size
+        self.class_embedding = nn.Parameter(torch.randn(self.embed_dim))
+        self.patch_embedding = nn.Conv2d(config.num_channels, self.embed_dim, kernel_size=self.patch_size,
+                                         stride=self.patch_size, bias=False)
+        self.num_patches = (config.image_size // self.patch_size) ** 2
+        self.num_positions = self.num_patches + 1
+        self.position_embedding = nn.Embedding(self.num_positions, self.embed_dim)
+        self._pe = PatchEmbedGemm()
+
+    def forward(self, pixel_values):
+        N = pixel_values.shape[0]
+        pe = self._pe(pixel_values, self.patch_embedding, self.patch_size)
+        L = pe.shape[0] // N
+        x = torch.empty((N, L + 1, self.embed_dim), dtype=pe.dtype, device=pe.device)
+        x[:, 0] = self.class_embedding.to(pe.dtype)                                 # layout plumbing (1 row / image)
+        x[:, 1:] = pe.view(N, L, self.embed_dim)
+        x = ops.add_rows(x.view(N * (L + 1), self.embed_dim), self.position_embedding.weight, period=L + 1)
+        return x.view(N, L + 1, self.embed_dim)
+
+
+class B200CLIPVisionTransformer(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.embeddings = B200CLIPVisionEmbeddings(config)
+        self.pre_layrnorm = B200LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+        self.encoder = B200VisionEncoder(config)
+        self.post_layernorm = B200LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+
+
+class B200VisionPreTrainedModel(PreTrainedModel):
+    base_model_prefix = "vision_model"
+    main_input_name = "pixel_values"
+    supports_gradient_checkpointing = True
+    _no_split_modules = ["B200VisionEncoderLayer"]
+    _supports_sdpa = True
+    _supports_flash_attn = True
+    _supports_flash_attn_2 = True
+
+    def _init_weights(self, module):
+        std = getattr(self.config, "initializer_range", 0.02)
+        if isinstance(module, (nn.Linear, nn.Conv2d)):
+            module.weight.data.normal_(mean=0.0, std=std)
+            if module.bias is not None:
+                module.bias.data.zero_()
+        elif isinstance(module, nn.Embedding):
+            module.weight.data.normal_(mean=0.0, std=std)
+        elif isinstance(module, nn.LayerNorm):
+            module.bias.data.zero_(); module.weight.data.fill_(1.0)
+
+    def get_input_embeddings(self):
+        return self.vision_model.embeddings.patch_embedding
+
+    def features(self, pixel_values, feature_layer):
+        """hidden_states[feature_layer] of the HF model (tuple of N+1 entries), evaluating only what is needed."""
+        vm = self.vision_model
+        n_layers = len(vm.encoder.layers)
+        idx = feature_layer if feature_layer >= 0 else n_layers + 1 + feature_layer
+        if not 0 <= idx <= n_layers:
+            raise ValueError(f"vision_feature_layer {feature_layer} out of range")
+        x = vm.embeddings(pixel_values.to(vm.embeddings.patch_embedding.weight.dtype))
+        if hasattr(vm, "pre_layrnorm"):
+            x = vm.pre_layrnorm(x)
+        x, _ = vm.encoder(x, num_layers=idx)
+        return x
+
+    def forward(self, pixel_values=None, output_attentions=None, output_hidden_states=None, return_dict=None, **kw):
+        vm = self.vision_model
+        x = vm.embeddings(pixel_values.to(vm.embeddings.patch_embedding.weight.dtype))
+        if hasattr(vm, "pre_layrnorm"):
+            x = vm.pre_layrnorm(x)
+        x, hs = vm.encoder(x, collect=bool(output_hidden_states))
+        last = vm.post_layernorm(x) if not hasattr(vm, "pre_layrnorm") else x
+        pooled = None
+        if hasattr(vm, "pre_layrnorm"):
+            pooled = vm.post_layernorm(x[:, 0, :])
+        return BaseModelOutputWithPooling(last_hidden_state=last, pooler_output=pooled,
+                                          hidden_states=tuple(hs) if hs is not None else None, attentions=None)
+
+
+class B200SiglipVisionModel(B200VisionPreTrainedModel):
+    def __init__(self, config):
+        super().__init__(config)
+        self.vision_model = B200SiglipVisionTransformer(config)
+        self.post_init()
+
+
+class B200CLIPVisionModel(B200VisionPreTrainedModel):
+    def __init__(self, config):
+        super().__init__(config)
+        self.vision_model = B200CLIPVisionTransformer(config)
+        self.post_init()
+
+
+def build_vision_tower(vision_config):
+    mt = getattr(vision_config, "model_type", "")
+    if mt in ("siglip_vision_model", "siglip"):
+        return B200SiglipVisionModel(vision_config)
+    if mt in ("clip_vision_model", "clip"):
+        return B200CLIPVisionModel(vision_config)
+    raise ValueError(f"mantis_b200 supports SigLIP and CLIP vision towers, got model_type={mt!r}")
