@@ -116,6 +116,13 @@ int mb200_attn_generic_bwd(const void* q, const void* k, const void* v, const vo
                            int Sk, int hd, const long long* strides, float scale, int causal, const int64_t* kmask,
                            long long kmask_sb, int dtype, void* stream);
 
+/* tcgen05 flash attention (bf16, head_dim 128): same semantics as mb200_attn_generic_fwd; -ENOTSUP if ineligible.
+ * kbits_ws: B * mb200_attn_kbits_words(Sk) uint32 of device scratch, needed only when kmask != NULL. */
+long long mb200_attn_kbits_words(int Sk);
+int mb200_attn_fwd_bf16(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Hkv, int Sq,
+                        int Sk, int hd, const long long* strides, float scale, int causal, const int64_t* kmask,
+                        long long kmask_sb, void* kbits_ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,8 +87,35 @@ class B200VisionEncoder(nn.Module):
         return x, hs
 
 
+class _PatchEmbedFn(torch.autograd.Function):
+    """conv2d(kernel = stride = patch) as im2col + GEMM; differentiable w.r.t. the conv weight / bias
+    (pixels never need a gradient on this path)."""
+
+    @staticmethod
+    def forward(ctx, pixel_values, weight, bias, patch, w2d, k_pad):
+        patches = ops.im2col(pixel_values, patch, k_pad, weight.dtype)
+        y = ops.gemm(patches, w2d, bias=bias)
+        ctx.save_for_backward(patches if weight.requires_grad else None)
+        ctx.wshape = weight.shape
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (patches,) = ctx.saved_tensors
+        gw = gb = None
+        gy = gy.contiguous()
+        if ctx.needs_input_grad[1] and patches is not None:
+            K = ctx.wshape[1] * ctx.wshape[2] * ctx.wshape[3]
+            gw2 = ops.gemm(gy, patches, trans_a=True, trans_b=False)            # [out, k_pad]
+            gw = gw2[:, :K].reshape(ctx.wshape)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = ops.colsum(gy)
+        return None, gw, gb, None, None, None
+
+
 class PatchEmbedGemm:
-    """conv2d(kernel = stride = patch) as im2col + GEMM. Keeps a K-padded copy of the flattened conv weight."""
+    """Keeps a K-padded copy of the flattened conv weight (TMA needs 16-byte multiples: 3*14*14 = 588 -> 640)."""
 
     def __init__(self):
         self._w = None
@@ -109,8 +136,7 @@ class PatchEmbedGemm:
     def __call__(self, pixel_values, conv, patch):
         K = conv.weight.shape[1] * patch * patch
         k_pad = (K + 63) // 64 * 64 if conv.weight.dtype == torch.bfloat16 else (K + 7) // 8 * 8
-        patches = ops.im2col(pixel_values, patch, k_pad, conv.weight.dtype)
-        return ops.gemm(patches, self.weight2d(conv.weight, k_pad), bias=conv.bias)
+        return _PatchEmbedFn.apply(pixel_values, conv.weight, conv.bias, patch, self.weight2d(conv.weight, k_pad), k_pad)
 
 
 class B200SiglipVisionEmbeddings(nn.Module):

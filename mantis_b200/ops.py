@@ -386,6 +386,18 @@ def _strides12(q, k, v, o):
     return arr
 
 
+FAST_ATTN_MIN_SQ = int(os.environ.get("MB200_FAST_ATTN_MIN_SQ", "64"))
+
+
+def _attn_fast_ok(q, k, v, hd, Sq, Sk):
+    if FORCE_GENERIC or q.dtype != torch.bfloat16 or hd != 128 or Sq < FAST_ATTN_MIN_SQ:
+        return False
+    for t in (q, k, v):
+        if t.data_ptr() % 16 or any(s % 8 for s in t.stride()[:3]):
+            return False
+    return True
+
+
 def attention_fwd(q, k, v, causal, kmask, scale):
     """q [B,Sq,H,hd], k/v [B,Sk,Hkv,hd] (hd contiguous). Returns (o [B,Sq,H,hd] contiguous, lse [B,H,Sq] fp32)."""
     _need_cuda(q, k, v)
@@ -398,6 +410,13 @@ def attention_fwd(q, k, v, causal, kmask, scale):
         kmask = kmask.contiguous().to(torch.int64)
         assert kmask.shape == (B, Sk)
     st = _strides12(q, k, v, o)
+    if _attn_fast_ok(q, k, v, hd, Sq, Sk):
+        kbits = None
+        if kmask is not None:
+            kbits = torch.empty((B * ((Sk + 31) // 32),), dtype=torch.int32, device=q.device)
+        _call("mb200_attn_fwd_bf16", _p(q), _p(k), _p(v), _p(o), _p(lse), B, H, Hkv, Sq, Sk, hd, st, float(scale),
+              int(causal), _p(kmask), Sk if kmask is not None else 0, _p(kbits), _st())
+        return o, lse
     _call("mb200_attn_generic_fwd", _p(q), _p(k), _p(v), _p(o), _p(lse), B, H, Hkv, Sq, Sk, hd, st, float(scale),
           int(causal), _p(kmask), Sk if kmask is not None else 0, _dt(q), _st())
     return o, lse
@@ -644,15 +663,35 @@ def im2col(pixels, patch, k_pad, out_dtype):
     return out
 
 
+class _AddRowsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x2, table, idx, period):
+        n, D = x2.shape
+        x2 = x2.contiguous(); tab = table.contiguous()
+        y = torch.empty_like(x2)
+        if idx is not None:
+            idx = idx.contiguous().to(torch.int64)
+        _call("mb200_add_rows", _p(x2), _p(tab), _p(idx), _p(y), n, D, int(period or 0), _dt(x2), _st())
+        ctx.save_for_backward(idx)
+        ctx.period, ctx.tshape = period, tuple(table.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        gt = None
+        if ctx.needs_input_grad[1]:
+            g2 = g.contiguous()
+            n, D = g2.shape
+            ids = idx if idx is not None else (torch.arange(n, device=g.device, dtype=torch.int64) % ctx.period)
+            gt = torch.zeros(ctx.tshape, dtype=g.dtype, device=g.device)
+            _call("mb200_embedding_bwd", _p(ids), _p(g2), _p(gt), n, D, ctx.tshape[0], _dt(g2), _st())
+        return g, gt, None, None
+
+
 def add_rows(x2, table, idx=None, period=None):
-    """y[r,:] = x[r,:] + table[idx[r] or r % period, :]"""
-    n, D = x2.shape
-    x2 = x2.contiguous(); table = table.contiguous()
-    y = torch.empty_like(x2)
-    if idx is not None:
-        idx = idx.contiguous().to(torch.int64)
-    _call("mb200_add_rows", _p(x2), _p(table), _p(idx), _p(y), n, D, int(period or 0), _dt(x2), _st())
-    return y
+    """y[r,:] = x[r,:] + table[idx[r] or r % period, :]   (position / type embeddings)"""
+    return _AddRowsFn.apply(x2, table, idx, period)
 
 
 def adamw_step(p, g, m, v, lr, beta1, beta2, eps, wd, step, grad_scale=1.0):

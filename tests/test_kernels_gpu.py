@@ -234,6 +234,43 @@ def test_attention_generic(ops, cuda, dtype, hd, H, Hkv, causal, Sq, Sk):
     assert _rel(q.grad * m, qr.grad * m) < tol and _rel(k.grad, kr.grad) < tol and _rel(v.grad, vr.grad) < tol
 
 
+@pytest.mark.parametrize("B,H,Hkv,Sq,Sk,causal,masked", [(1, 4, 2, 128, 128, True, False), (2, 8, 2, 300, 300, True, True),
+                                                         (1, 4, 4, 257, 257, False, False), (2, 4, 1, 200, 455, True, True),
+                                                         (1, 32, 8, 1000, 1000, True, False), (1, 2, 2, 130, 700, False, True)])
+def test_attention_tcgen05_fwd(ops, cuda, B, H, Hkv, Sq, Sk, causal, masked):
+    torch.manual_seed(12)
+    hd = 128
+    q = torch.randn(B, Sq, H, hd, device=cuda).bfloat16()
+    k = torch.randn(B, Sk, Hkv, hd, device=cuda).bfloat16()
+    v = torch.randn(B, Sk, Hkv, hd, device=cuda).bfloat16()
+    kmask = None
+    if masked:
+        kmask = torch.ones(B, Sk, dtype=torch.int64, device=cuda)
+        kmask[B - 1, :37] = 0                      # left padding
+        kmask[0, Sk - 5:] = 0 if not causal else 1
+    scale = hd ** -0.5
+    o, lse = ops.attention_fwd(q, k, v, causal, kmask, scale)
+    import mantis_b200.ops as om
+    old = om.FORCE_GENERIC; om.FORCE_GENERIC = True
+    try:
+        og, lseg = ops.attention_fwd(q, k, v, causal, kmask, scale)
+    finally:
+        om.FORCE_GENERIC = old
+    ref = _attn_ref(q.float(), k.float(), v.float(), causal, kmask, scale)
+    # rows whose keys are all masked are don't-care
+    off = Sk - Sq
+    vis = torch.ones(B, Sq, Sk, dtype=torch.bool, device=cuda)
+    if causal:
+        vis &= (torch.arange(Sk, device=cuda)[None, :] <= torch.arange(Sq, device=cuda)[:, None] + off)[None]
+    if kmask is not None:
+        vis &= (kmask != 0)[:, None, :]
+    rows = vis.any(-1)[:, :, None, None]
+    assert _rel(o * rows, ref * rows) < 1e-2, _rel(o * rows, ref * rows)
+    assert _rel(o * rows, og * rows) < 1e-2
+    lm = rows[:, :, 0, 0][:, None, :].expand(B, H, Sq)
+    assert (lse[lm] - lseg[lm]).abs().max().item() < 2e-2
+
+
 # ------------------------------------------------------------------------------------------------ merge
 def _merge_case(rng, B, T, P, D, mode, zero_pad_rows):
     ids = rng.integers(1, 12, size=(B, T))
