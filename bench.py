@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- the driver contract.
+
+  python bench.py --gpus N --steps K --warmup W            our arm  (one process per GPU; torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's own CPU forward/backward (rank 0 only)
+
+Workload (BASELINE.json configs[1] / SURVEY.md section 8d config 2): Mantis-8B-SigLIP-LLaMA-3, random init, bf16, one
+data-parallel rank = 4 samples x (8 images 384x384 + 2048 text tokens) per optimizer step (merged S = 7864 per sample,
+31,456 merged tokens per step), processed as 4 micro-batches of one sample with gradient accumulation exactly like the
+reference recipe (per_device_train_batch_size 1, mantis/train/scripts/train_mllava.sh:137), then one gradient
+all-reduce (N > 1) and one fused AdamW step.  A "step" = those 4 forward+backward passes + all-reduce + AdamW.
+metric = merged tokens / s over the whole job.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+IMG_TOKEN, N_IMG, T_TEXT, IMG_RES, SAMPLES_PER_STEP = 128256, 8, 2048, 384, 4
+FLOP_PER_STEP = 1.634e15          # 408.6 TFLOP/sample * 4 (ViT fwd only, rest x3)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--text-layers", type=int, default=32, help="debug only: fewer layers => INVALID as a bench number")
+    ap.add_argument("--vision-layers", type=int, default=27)
+    ap.add_argument("--samples", type=int, default=SAMPLES_PER_STEP)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-gemm", action="store_true", help="only run the per-kernel roofline section")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ synthetic data
+def make_sample(i, torch):
+    g = torch.Generator().manual_seed(1234 + i)
+    ids = torch.randint(0, 128000, (1, T_TEXT), generator=g)
+    for j in range(N_IMG):
+        ids[0, j * 256 + 16] = IMG_TOKEN
+    labels = ids.clone()
+    labels[ids == IMG_TOKEN] = -100
+    gp = torch.Generator().manual_seed(4321 + i)
+    pv = torch.randn(N_IMG, 3, IMG_RES, IMG_RES, generator=gp).to(torch.bfloat16)
+    return dict(input_ids=ids, attention_mask=torch.ones_like(ids), labels=labels, pixel_values=pv)
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True); self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm = sorted(int(float(r[0])) for r in self.rows if r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if r[1].replace(".", "").isdigit()]
+        reasons = []
+        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
+            if any(r[col].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference_baseline(n_timed=1, n_warm=0):
+    """The reference's own forward+backward (mantis/models/mllava/modeling_llava.py:364-549, imported unmodified via
+    oracle/ref_shim.py from baseline/_ref or /root/reference) on the host cores.  Bounded sample: full-width
+    Mantis-8B-SigLIP at reduced depth (1+1 and 2+2 layers), one sample of 1 image + 256 text tokens (S = 983), fp32;
+    per-layer cost from the depth difference, extrapolated linearly to 27 ViT + 32 LLaMA layers."""
+    import torch
+    from oracle.ref_shim import find_ref_root, ref_llava_classes
+    if find_ref_root() is None:
+        return None
+    from transformers import LlamaConfig, SiglipVisionConfig
+    LlavaConfig, RefLlava, _ = ref_llava_classes()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+
+    def build(depth):
+        vc = SiglipVisionConfig(hidden_size=1152, intermediate_size=4304, num_hidden_layers=depth + 1,
+                                num_attention_heads=16, image_size=384, patch_size=14, layer_norm_eps=1e-6,
+                                hidden_act="gelu_pytorch_tanh")   # +1: hidden_states[-2] drops the last layer
+        tc = LlamaConfig(hidden_size=4096, intermediate_size=14336, num_hidden_layers=depth, num_attention_heads=32,
+                         num_key_value_heads=8, vocab_size=128258, rms_norm_eps=1e-5, rope_theta=500000.0)
+        cfg = LlavaConfig(vision_config=vc, text_config=tc, image_token_index=IMG_TOKEN, pad_token_id=128257,
+                          vocab_size=128258)
+        torch.manual_seed(0)
+        m = RefLlava(cfg)
+        for n, p in m.named_parameters():
+            if "vision_tower" in n:
+                p.requires_grad_(False)
+        return m.train()
+
+    g = torch.Generator().manual_seed(7)
+    ids = torch.randint(0, 128000, (1, 256), generator=g); ids[0, 16] = IMG_TOKEN
+    labels = ids.clone(); labels[ids == IMG_TOKEN] = -100
+    pv = torch.randn(1, 3, IMG_RES, IMG_RES, generator=g)
+    times = {}
+    for depth in (1, 2):
+        m = build(depth)
+        ts = []
+        for it in range(n_warm + n_timed):
+            t0 = time.perf_counter()
+            out = m(input_ids=ids, pixel_values=pv, attention_mask=torch.ones_like(ids), labels=labels)
+            out.loss.backward()
+            m.zero_grad(set_to_none=True)
+            if it >= n_warm:
+                ts.append(time.perf_counter() - t0)
+        times[depth] = sum(ts) / len(ts)
+        del m
+    per_layer = max(times[2] - times[1], 1e-9)
+    fixed = max(times[1] - per_layer, 0.0)
+    full = fixed + 32 * per_layer
+    S = 256 + 727
+    return {"value": S / full, "unit": "tokens/s", "cores": cores, "kind": "reference",
+            "sample": (f"reference fwd+bwd fp32 on {cores} host threads, full-width Mantis-8B-SigLIP at depth 1+1 "
+                       f"({times[1]:.2f} s) and 2+2 ({times[2]:.2f} s), 1 image + 256 text tokens (S=983); linear "
+                       f"extrapolation to 27+32 layers = {full:.1f} s/sample (short sequence favours the reference)"),
+            "seconds_per_sample_extrapolated": full}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.time()
+    try:
+        res = cpu_reference_baseline(n_timed=max(1, min(args.steps, 3)), n_warm=min(args.warmup, 1))
+    except Exception as e:  # noqa
+        res = None
+        err = f"{type(e).__name__}: {e}"
+    if res is None:
+        print(json.dumps({"impl": "reference", "unavailable": locals().get("err", "reference tree not found (baseline/_ref)")}))
+        return
+    line = {"impl": "reference", "metric": "training tokens/sec Mantis-8B-SigLIP 8-img/2048-tok", "value": res["value"],
+            "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": res["seconds_per_sample_extrapolated"] * SAMPLES_PER_STEP * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "Mantis-8B-SigLIP-LLaMA-3 fwd+bwd, reference CPU path, bounded sample (see cpu_baseline.sample)"},
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.time() - t0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def gemm_roofline(torch, ops, peaks):
+    """Per-kernel roofline of the dominant kernel (gemm_sm100_kernel): the seven linear-layer shapes of one LLaMA
+    layer at M = 7864 (fwd, dgrad, wgrad), each timed with CUDA events on the launching stream; L2 is flushed by
+    cycling through operand sets larger than L2."""
+    dev = torch.device("cuda")
+    M = 7864
+    shapes = [(4096, 4096), (1024, 4096), (1024, 4096), (4096, 4096), (14336, 4096), (14336, 4096), (4096, 14336)]
+    flops = 0.0; t_ms = 0.0; launches = 0
+    nset = 3
+    for (N, K) in shapes:
+        xs = [torch.randn(M, K, device=dev).bfloat16() for _ in range(nset)]
+        ws = [(torch.randn(N, K, device=dev) * 0.02).bfloat16() for _ in range(nset)]
+        gs = [torch.randn(M, N, device=dev).bfloat16() for _ in range(nset)]
+        for kind in ("fwd", "dgrad", "wgrad"):
+            def run(i):
+                if kind == "fwd":
+                    ops.gemm(xs[i], ws[i])
+                elif kind == "dgrad":
+                    ops.gemm(gs[i], ws[i], trans_a=False, trans_b=False)
+                else:
+                    ops.gemm(gs[i], xs[i], trans_a=True, trans_b=False)
+            for i in range(nset):
+                run(i)
+            torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            reps = 6
+            e0.record()
+            for r in range(reps):
+                run(r % nset)
+            e1.record(); torch.cuda.synchronize()
+            t_ms += e0.elapsed_time(e1); flops += reps * 2.0 * M * N * K; launches += reps
+        del xs, ws, gs
+    ach = flops / (t_ms * 1e-3) / 1e12
+    peak = peaks["bf16_tflops"]
+    return {"bound": "tensor", "kernel": "gemm_sm100_kernel (tcgen05, 128x256x64)", "achieved": ach, "peak": peak,
+            "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "launches_timed": launches,
+            "avg_launch_ms": t_ms / launches}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from mantis_b200 import _lib, ops
+    from mantis_b200.models.mllava import LlavaForConditionalGeneration, mantis_8b_siglip_llama3_config
+    from mantis_b200.train import B200Trainer
+    assert _lib.lib().mb200_check_device() == 0, _lib.lib().mb200_last_error()
+    peaks, peaks_src = measured_peaks()
+
+    if args.profile_gemm:
+        print(json.dumps(gemm_roofline(torch, ops, peaks)))
+        return
+
+    cfg = mantis_8b_siglip_llama3_config(num_vision_layers=args.vision_layers, num_text_layers=args.text_layers)
+    torch.manual_seed(0)
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)
+    with torch.device(dev):
+        model = LlavaForConditionalGeneration(cfg)
+    torch.set_default_dtype(old)
+    model.train()
+    trainer = B200Trainer(model, lr=1e-5, weight_decay=0.0, max_grad_norm=1.0, grad_accum=args.samples)
+    n_train = sum(p.numel() for p in trainer.params)
+
+    host = [make_sample(rank * args.samples + i, torch) for i in range(args.samples)]
+    host = [{k: v.pin_memory() for k, v in s.items()} for s in host]
+    resident = [{k: v.to(dev, non_blocking=True) for k, v in s.items()} for s in host]
+    torch.cuda.synchronize()
+    S_merged = T_TEXT + N_IMG * 727
+    tokens_per_step_rank = args.samples * S_merged
+    h2d = sum(v.numel() * v.element_size() for s in host for v in s.values())
+
+    def step(e2e):
+        if e2e:
+            batches = [{k: v.to(dev, non_blocking=True) for k, v in s.items()} for s in host]
+        else:
+            batches = resident
+        loss = trainer.train_step(batches)
+        return float(loss.item()) if e2e else loss
+
+    def timed(e2e, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        l0 = ops.launch_count
+        e0.record()
+        last = None
+        for _ in range(k):
+            last = step(e2e)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), ops.launch_count - l0, last
+
+    for _ in range(args.warmup):
+        step(False)
+    sampler = ClockSampler(local); sampler.start()
+    ms, launches, last_loss = timed(False, args.steps)
+    clocks = sampler.stop()
+    mem_gb = torch.cuda.max_memory_allocated() / 2 ** 30
+    e2e = None
+    if not args.no_e2e:
+        step(True)
+        ms2, _, _ = timed(True, args.steps)
+        e2e = {"value": world * tokens_per_step_rank * args.steps / (ms2 * 1e-3), "unit": "tokens/s",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = world * tokens_per_step_rank * args.steps / (ms * 1e-3)
+    step_tflops = world * FLOP_PER_STEP * (args.samples / SAMPLES_PER_STEP) * args.steps / (ms * 1e-3) / 1e12
+    roof = gemm_roofline(torch, ops, peaks) if world == 1 else None
+    full = (args.text_layers == 32 and args.vision_layers == 27 and args.samples == SAMPLES_PER_STEP)
+    line = {
+        "metric": "training tokens/sec Mantis-8B-SigLIP 8-img/2048-tok", "value": value, "unit": "tokens/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "Mantis-8B-SigLIP-LLaMA-3 instruction-tuning step, random init (configs[1])",
+                   "samples_per_rank_per_step": args.samples, "images_per_sample": N_IMG, "text_tokens": T_TEXT,
+                   "merged_seq_len": S_merged, "micro_batch": 1, "grad_accum": args.samples,
+                   "parallelism": f"dp{world}", "optimizer": "fused AdamW (fp32 moments) + grad-norm clip",
+                   "trainable_params": n_train, "vision_tower": "frozen (train_mllava.py:239-242)",
+                   "l2": "working set >> L2 (35 GB of activations + 16 GB weights per micro-batch), no flush needed",
+                   "text_layers": args.text_layers, "vision_layers": args.vision_layers, "valid": full},
+        "step_tflops": step_tflops, "step_frac_of_sustained_peak": step_tflops / world / peaks["bf16_tflops_sustained"],
+        "peaks": peaks_src, "gpu_launches": launches, "max_mem_gb": mem_gb, "clocks": clocks, "loss": float(last_loss),
+        "e2e": e2e, "roofline": roof,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            cb = cpu_reference_baseline(1, 0)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")} if cb else None
+        except Exception as e:  # noqa
+            line["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

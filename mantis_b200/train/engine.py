@@ -1,0 +1,89 @@
+"""Minimal data-parallel instruction-tuning engine for the hot path (what HF Trainer + accelerate/DeepSpeed do for
+mantis/train/train_mllava.py:312-329 with per_device_train_batch_size=1 + gradient accumulation,
+mantis/train/scripts/train_mllava.sh:137-168), reduced to what the step needs:
+
+  * micro-batches of one sample: loss/accum -> backward (gradients accumulate in ONE flat bf16 buffer that every
+    trainable parameter's .grad is a view of),
+  * one NCCL all-reduce (sum, then 1/world) of that flat buffer per optimizer step -- the only exchange of the
+    data-parallel path; the vision tower is frozen and excluded,
+  * optional global-norm clipping + fused AdamW (bf16 params, fp32 moments) on our CUDA kernel.
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+from .. import ops
+
+
+def flat_grad_buffer(params):
+    """Allocates one contiguous buffer and makes every param.grad a view into it. Returns (flat, views)."""
+    params = [p for p in params if p.requires_grad]
+    total = sum((p.numel() + 7) // 8 * 8 for p in params)      # keep every view 16-byte aligned
+    dtype = params[0].dtype
+    assert all(p.dtype == dtype for p in params), "trainable parameters must share a dtype"
+    flat = torch.zeros(total, dtype=dtype, device=params[0].device)
+    off = 0
+    for p in params:
+        n = p.numel()
+        p.grad = flat[off:off + n].view_as(p)
+        off += (n + 7) // 8 * 8
+    return flat
+
+
+class B200Trainer:
+    def __init__(self, model, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0,
+                 grad_accum=1, freeze_vision=True):
+        self.model = model
+        if freeze_vision:                                   # mantis/train/train_mllava.py:239-242
+            for n, p in model.named_parameters():
+                if "vision_tower" in n:
+                    p.requires_grad_(False)
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        self.flat_grad = flat_grad_buffer(self.params)
+        self.m = [torch.zeros(p.shape, dtype=torch.float32, device=p.device) for p in self.params]
+        self.v = [torch.zeros(p.shape, dtype=torch.float32, device=p.device) for p in self.params]
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.max_grad_norm = max_grad_norm
+        self.grad_accum = grad_accum
+        self.step_count = 0
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self._norm = torch.zeros(1, dtype=torch.float32, device=self.flat_grad.device)
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+
+    def micro_step(self, batch):
+        """forward + backward of one micro-batch (gradients accumulate). Returns the detached loss."""
+        out = self.model(**batch)
+        (out.loss / self.grad_accum).backward()
+        return out.loss.detach()
+
+    def _restore_grad_views(self):
+        # autograd accumulates in place into existing .grad tensors, so the views stay bound; assert cheaply
+        p = self.params[0]
+        assert p.grad.data_ptr() == self.flat_grad.data_ptr(), "param.grad was rebound away from the flat buffer"
+
+    def optimizer_step(self):
+        self._restore_grad_views()
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)            # the one collective of the DP path
+        scale = 1.0 / self.world
+        if self.max_grad_norm is not None and self.max_grad_norm > 0:
+            self._norm.zero_()
+            ops.sumsq(self.flat_grad, self._norm)
+            # clip factor computed on device; read back lazily (no sync needed: pass through a tiny host value
+            # only when logging).  The fused kernel takes the scale as a host float, so one 4-byte readback here.
+            total = math.sqrt(float(self._norm.item())) * scale
+            if total > self.max_grad_norm:
+                scale *= self.max_grad_norm / (total + 1e-6)
+        self.step_count += 1
+        for p, m, v in zip(self.params, self.m, self.v):
+            ops.adamw_step(p.data, p.grad, m, v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
+                           self.step_count, grad_scale=scale)
+        self.zero_grad()
+
+    def train_step(self, micro_batches):
+        losses = [self.micro_step(b) for b in micro_batches]
+        self.optimizer_step()
+        return torch.stack(losses).mean()
