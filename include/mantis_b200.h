@@ -123,6 +123,13 @@ int mb200_attn_fwd_bf16(const void* q, const void* k, const void* v, void* o, fl
                         int Sk, int hd, const long long* strides, float scale, int causal, const int64_t* kmask,
                         long long kmask_sb, void* kbits_ws, void* stream);
 
+/* tcgen05 flash attention backward (dK/dV kernel + dQ kernel, deterministic, no atomics).  dq/dk/dv/dout contiguous;
+ * kbits = the bitmask scratch filled by mb200_attn_fwd_bf16 for the same kmask (NULL iff kmask == NULL). */
+int mb200_attn_bwd_bf16(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
+                        float* delta, void* dq, void* dk, void* dv, int B, int H, int Hkv, int Sq, int Sk, int hd,
+                        const long long* strides, float scale, int causal, const int64_t* kmask, long long kmask_sb,
+                        const void* kbits, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,553 @@
+// Flash-attention backward on tcgen05 (head_dim 128), as two kernels that share the forward's building blocks
+// (TMA -> 128B-swizzled smem, tcgen05.mma with TMEM accumulators, one softmax thread per TMEM lane):
+//
+//   dKV kernel : CTA owns a 128-key tile of one (batch, kv head); loops over the query heads of the GQA group and
+//                over 64-query sub-tiles.  S^T = K Q^T and dP^T = V dO^T (128x64, double buffered in TMEM),
+//                P^T / dS^T -> swizzled smem, dV += P^T dO, dK += dS^T Q accumulate in TMEM over the whole loop.
+//   dQ kernel  : CTA owns a 128-query tile of one (batch, head); loops over 64-key sub-tiles.
+//                S = Q K^T, dP = dO V^T (double buffered), dS -> smem, dQ += dS K accumulates in TMEM.
+//
+// No atomics, deterministic.  S/dP are recomputed in both kernels (7 GEMMs instead of the fused 5) -- the price of
+// keeping every accumulator resident in the 512 TMEM columns without a global dQ reduction.
+// The same [rows x 64] swizzled tile serves as a K-major operand (rows = M/N) and as an MN-major operand
+// (rows = K) -- only the descriptor differs -- so Q, dO, K, V are each loaded once per use.
+// Backward of LlamaAttention's SDPA/flash call (transformers llama/modeling_llama.py:199-289).
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace {
+using namespace sm100;
+
+constexpr int HD = 128;
+constexpr int FULL_HALF = 128 * 128;     // [128 rows x 64 bf16] swizzled sub-tile (16 KB)
+constexpr int FULL_TILE = 2 * FULL_HALF; // [128 rows x 128 hd]
+constexpr int SUB_HALF = 64 * 128;       // [64 rows x 64 bf16] (8 KB)
+constexpr int SUB_TILE = 2 * SUB_HALF;   // [64 rows x 128 hd] (16 KB)
+constexpr float LOG2E = 1.44269504088896340736f;
+
+struct BwdParams {
+  const float* lse;      // [B,H,Sq] natural log
+  const float* delta;    // [B,H,Sq]
+  bf16* dq; long long dq_sb, dq_ss, dq_sh;
+  bf16* dk; long long dk_sb, dk_ss, dk_sh;
+  bf16* dv; long long dv_sb, dv_ss, dv_sh;
+  const uint32_t* kbits; int kbits_stride;
+  int B, H, Hkv, Sq, Sk;
+  float scale, scale_log2;
+  int causal;
+};
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  bf162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&h);
+}
+// write 64 bf16 (32 packed words) as one 128-byte swizzled row r of a K-major tile
+__device__ __forceinline__ void store_row64(uint8_t* tile, int r, const uint32_t* pk) {
+  uint8_t* rowp = tile + r * 128;
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch)
+    *reinterpret_cast<uint4*>(rowp + ((ch ^ (r & 7)) << 4)) = make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+}
+// store one 128-lane x 128-column fp32 accumulator row as bf16 (256 B) to global
+__device__ __forceinline__ void store_acc_row(uint32_t taddr, bf16* dst, bool ok, float mul) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t ov[32];
+    tmem_ld_32x32b_x32(taddr + c * 32, ov);
+    tmem_ld_wait();
+    if (ok) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 o4;
+        o4.x = pack_bf16(__uint_as_float(ov[g * 8 + 0]) * mul, __uint_as_float(ov[g * 8 + 1]) * mul);
+        o4.y = pack_bf16(__uint_as_float(ov[g * 8 + 2]) * mul, __uint_as_float(ov[g * 8 + 3]) * mul);
+        o4.z = pack_bf16(__uint_as_float(ov[g * 8 + 4]) * mul, __uint_as_float(ov[g * 8 + 5]) * mul);
+        o4.w = pack_bf16(__uint_as_float(ov[g * 8 + 6]) * mul, __uint_as_float(ov[g * 8 + 7]) * mul);
+        *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = o4;
+      }
+    }
+  }
+}
+
+// ============================================================================================ dK / dV
+__global__ void __launch_bounds__(192, 1)
+attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant__ CUtensorMap tmDO64,
+                          const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                          const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;                           // 32 KB resident
+  uint8_t* sV = sK + FULL_TILE;                 // 32 KB resident
+  uint8_t* sQ = sV + FULL_TILE;                 // 2 stages x 16 KB
+  uint8_t* sDO = sQ + 2 * SUB_TILE;             // 2 stages x 16 KB
+  uint8_t* sPT = sDO + 2 * SUB_TILE;            // 16 KB  [128 keys x 64 q]
+  uint8_t* sDST = sPT + FULL_HALF;              // 16 KB
+  float* sLse = reinterpret_cast<float*>(sDST + FULL_HALF);   // [2][64]
+  float* sDelta = sLse + 128;                                  // [2][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 128);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* qdo_full = bars + 1;    // [2]
+  uint64_t* qdo_empty = bars + 3;   // [2]
+  uint64_t* sdp_full = bars + 5;    // [2]
+  uint64_t* sdp_empty = bars + 7;   // [2]
+  uint64_t* pds_full = bars + 9;
+  uint64_t* pds_empty = bars + 10;
+  uint64_t* acc_done = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kt = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
+  const int G = p.H / p.Hkv;
+  const int k0 = kt * 128;
+  const int off = p.Sk - p.Sq;
+  const int n_qs = (p.Sq + 63) / 64;
+  int qs_begin = 0;
+  if (p.causal) { int qb = k0 - off; if (qb < 0) qb = 0; qs_begin = qb / 64; }
+  const int per_head = (n_qs > qs_begin) ? (n_qs - qs_begin) : 0;
+  const int n_it = per_head * G;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmQ64); prefetch_tmap(&tmDO64); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1); mbar_init(&sdp_full[s], 1); mbar_init(&sdp_empty[s], 128);
+    }
+    mbar_init(pds_full, 128); mbar_init(pds_empty, 1); mbar_init(acc_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tDK = tmem_base, tDV = tmem_base + 128;
+  const uint32_t tST[2] = {tmem_base + 256, tmem_base + 384};
+  const uint32_t tDPT[2] = {tmem_base + 320, tmem_base + 448};
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(kv_full, 2 * FULL_TILE);
+      tma_load_4d(sK, &tmK, kv_full, 0, hk, k0, b);
+      tma_load_4d(sK + FULL_HALF, &tmK, kv_full, 64, hk, k0, b);
+      tma_load_4d(sV, &tmV, kv_full, 0, hk, k0, b);
+      tma_load_4d(sV + FULL_HALF, &tmV, kv_full, 64, hk, k0, b);
+      for (int n = 0; n < n_it; ++n) {
+        const int s = n & 1; const uint32_t ph = (n >> 1) & 1;
+        const int h = hk * G + n / per_head, qs = qs_begin + n % per_head;
+        mbar_wait(&qdo_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&qdo_full[s], 2 * SUB_TILE);
+        tma_load_4d(sQ + s * SUB_TILE, &tmQ64, &qdo_full[s], 0, h, qs * 64, b);
+        tma_load_4d(sQ + s * SUB_TILE + SUB_HALF, &tmQ64, &qdo_full[s], 64, h, qs * 64, b);
+        tma_load_4d(sDO + s * SUB_TILE, &tmDO64, &qdo_full[s], 0, h, qs * 64, b);
+        tma_load_4d(sDO + s * SUB_TILE + SUB_HALF, &tmDO64, &qdo_full[s], 64, h, qs * 64, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_it > 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, false, false);
+      constexpr uint32_t idesc_acc = make_idesc_bf16(128, 128, false, true);
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+      const uint32_t pt_addr = smem_u32(sPT), dst_addr = smem_u32(sDST);
+      auto issue_sdp = [&](int n) {
+        const int s = n & 1; const uint32_t ph = (n >> 1) & 1;
+        mbar_wait(&qdo_full[s], ph);
+        mbar_wait(&sdp_empty[s], ph ^ 1);
+        tc_fence_after();
+        const uint32_t q_addr = smem_u32(sQ + s * SUB_TILE), do_addr = smem_u32(sDO + s * SUB_TILE);
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const uint32_t oa = (kk >> 2) * FULL_HALF + (kk & 3) * 32, ob = (kk >> 2) * SUB_HALF + (kk & 3) * 32;
+          umma_bf16_ss(tST[s], make_smem_desc(k_addr + oa, 16, 1024), make_smem_desc(q_addr + ob, 16, 1024), idesc_s, kk != 0);
+        }
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const uint32_t oa = (kk >> 2) * FULL_HALF + (kk & 3) * 32, ob = (kk >> 2) * SUB_HALF + (kk & 3) * 32;
+          umma_bf16_ss(tDPT[s], make_smem_desc(v_addr + oa, 16, 1024), make_smem_desc(do_addr + ob, 16, 1024), idesc_s, kk != 0);
+        }
+        umma_commit(&sdp_full[s]);
+      };
+      mbar_wait(kv_full, 0);
+      issue_sdp(0);
+      for (int n = 0; n < n_it; ++n) {
+        if (n + 1 < n_it) issue_sdp(n + 1);
+        const int s = n & 1;
+        mbar_wait(pds_full, n & 1);
+        tc_fence_after();
+        const uint32_t q_addr = smem_u32(sQ + s * SUB_TILE), do_addr = smem_u32(sDO + s * SUB_TILE);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)     // dV += P^T (K = 64 queries) x dO (MN-major: rows = queries)
+          umma_bf16_ss(tDV, make_smem_desc(pt_addr + kk * 32, 16, 1024),
+                       make_smem_desc(do_addr + kk * 2048, SUB_HALF, 1024), idesc_acc, (n | kk) != 0);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)     // dK += dS^T x Q
+          umma_bf16_ss(tDK, make_smem_desc(dst_addr + kk * 32, 16, 1024),
+                       make_smem_desc(q_addr + kk * 2048, SUB_HALF, 1024), idesc_acc, (n | kk) != 0);
+        umma_commit(&qdo_empty[s]);
+        umma_commit(pds_empty);
+      }
+      umma_commit(acc_done);
+    }
+  } else {
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;                // key row in tile == TMEM lane
+    const int tid = threadIdx.x - 64;            // 0..127 within the softmax group
+    const int kj = k0 + r;
+    const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+    bool key_ok = kj < p.Sk;
+    if (key_ok && p.kbits) key_ok = (__ldg(p.kbits + (size_t)b * p.kbits_stride + (kj >> 5)) >> (kj & 31)) & 1u;
+    for (int n = 0; n < n_it; ++n) {
+      const int s = n & 1; const uint32_t ph = (n >> 1) & 1;
+      const int h = hk * G + n / per_head, qs = qs_begin + n % per_head;
+      const int q0 = qs * 64;
+      // stage lse (log2 domain, +inf for dead / out-of-range rows) and delta for the 64 queries of this sub-tile
+      {
+        const int i = tid & 63, qi = q0 + i;
+        const size_t idx = ((size_t)b * p.H + h) * p.Sq + qi;
+        if (tid < 64) {
+          float L = (qi < p.Sq) ? p.lse[idx] : INFINITY;
+          sLse[s * 64 + i] = (L == -INFINITY) ? INFINITY : L * LOG2E;
+        } else {
+          sDelta[s * 64 + i] = (qi < p.Sq) ? p.delta[idx] : 0.f;
+        }
+      }
+      named_bar_sync(1, 128);
+      mbar_wait(&sdp_full[s], ph);
+      tc_fence_after();
+      float sv[64], dp[64];
+      tmem_ld_32x32b_x32(tST[s] + lane_off, reinterpret_cast<uint32_t*>(sv));
+      tmem_ld_32x32b_x32(tST[s] + lane_off + 32, reinterpret_cast<uint32_t*>(sv) + 32);
+      tmem_ld_32x32b_x32(tDPT[s] + lane_off, reinterpret_cast<uint32_t*>(dp));
+      tmem_ld_32x32b_x32(tDPT[s] + lane_off + 32, reinterpret_cast<uint32_t*>(dp) + 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&sdp_empty[s]);
+      uint32_t pk[32], dk_[32];
+      const int qlim = kj - off;                 // causal: query qi sees key kj iff qi >= kj - off
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float pv[2], dsv[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = 2 * i + e, qi = q0 + c;
+          const bool vis = key_ok && (!p.causal || qi >= qlim);
+          const float pe = vis ? fast_exp2(fmaf(sv[c], p.scale_log2, -sLse[s * 64 + c])) : 0.f;
+          pv[e] = pe;
+          dsv[e] = pe * (dp[c] - sDelta[s * 64 + c]) * p.scale;
+        }
+        pk[i] = pack_bf16(pv[0], pv[1]);
+        dk_[i] = pack_bf16(dsv[0], dsv[1]);
+      }
+      if (n > 0) mbar_wait(pds_empty, (n - 1) & 1);
+      store_row64(sPT, r, pk);
+      store_row64(sDST, r, dk_);
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(pds_full);
+    }
+    // ---- epilogue: dK, dV rows -> global ----
+    const bool row_ok = kj < p.Sk;
+    bf16* dkp = p.dk + (size_t)b * p.dk_sb + (size_t)(row_ok ? kj : 0) * p.dk_ss + (size_t)hk * p.dk_sh;
+    bf16* dvp = p.dv + (size_t)b * p.dv_sb + (size_t)(row_ok ? kj : 0) * p.dv_ss + (size_t)hk * p.dv_sh;
+    if (n_it > 0) {
+      mbar_wait(acc_done, 0);
+      tc_fence_after();
+      store_acc_row(tDK + lane_off, dkp, row_ok, 1.f);
+      store_acc_row(tDV + lane_off, dvp, row_ok, 1.f);
+    } else if (row_ok) {
+      const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) { *reinterpret_cast<uint4*>(dkp + c * 8) = z; *reinterpret_cast<uint4*>(dvp + c * 8) = z; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ============================================================================================ dQ
+__global__ void __launch_bounds__(192, 1)
+attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
+                         const __grid_constant__ CUtensorMap tmK64, const __grid_constant__ CUtensorMap tmV64,
+                         const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                           // 32 KB resident
+  uint8_t* sDO = sQ + FULL_TILE;                // 32 KB resident
+  uint8_t* sK = sDO + FULL_TILE;                // 2 x 16 KB
+  uint8_t* sV = sK + 2 * SUB_TILE;              // 2 x 16 KB
+  uint8_t* sDS = sV + 2 * SUB_TILE;             // 16 KB [128 q x 64 keys]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + FULL_HALF);
+  uint64_t* qdo_full = bars + 0;
+  uint64_t* kv_full = bars + 1;     // [2]
+  uint64_t* kv_empty = bars + 3;    // [2]
+  uint64_t* sdp_full = bars + 5;    // [2]
+  uint64_t* sdp_empty = bars + 7;   // [2]
+  uint64_t* ds_full = bars + 9;
+  uint64_t* ds_empty = bars + 10;
+  uint64_t* acc_done = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = gridDim.x - 1 - blockIdx.x;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int hk = h / (p.H / p.Hkv);
+  const int q0 = qt * 128;
+  const int off = p.Sk - p.Sq;
+  int kv_end = p.Sk;
+  if (p.causal) { kv_end = min(p.Sk, q0 + 128 + off); if (kv_end < 0) kv_end = 0; }
+  const int n_it = (kv_end + 63) / 64;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmQ); prefetch_tmap(&tmDO); prefetch_tmap(&tmK64); prefetch_tmap(&tmV64);
+    mbar_init(qdo_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); mbar_init(&sdp_full[s], 1); mbar_init(&sdp_empty[s], 128);
+    }
+    mbar_init(ds_full, 128); mbar_init(ds_empty, 1); mbar_init(acc_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tDQ = tmem_base;
+  const uint32_t tS[2] = {tmem_base + 128, tmem_base + 256};
+  const uint32_t tDP[2] = {tmem_base + 192, tmem_base + 320};
+
+  if (warp == 0) {
+    if (lane == 0 && n_it > 0) {
+      mbar_arrive_expect_tx(qdo_full, 2 * FULL_TILE);
+      tma_load_4d(sQ, &tmQ, qdo_full, 0, h, q0, b);
+      tma_load_4d(sQ + FULL_HALF, &tmQ, qdo_full, 64, h, q0, b);
+      tma_load_4d(sDO, &tmDO, qdo_full, 0, h, q0, b);
+      tma_load_4d(sDO + FULL_HALF, &tmDO, qdo_full, 64, h, q0, b);
+      for (int n = 0; n < n_it; ++n) {
+        const int s = n & 1; const uint32_t ph = (n >> 1) & 1;
+        mbar_wait(&kv_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&kv_full[s], 2 * SUB_TILE);
+        tma_load_4d(sK + s * SUB_TILE, &tmK64, &kv_full[s], 0, hk, n * 64, b);
+        tma_load_4d(sK + s * SUB_TILE + SUB_HALF, &tmK64, &kv_full[s], 64, hk, n * 64, b);
+        tma_load_4d(sV + s * SUB_TILE, &tmV64, &kv_full[s], 0, hk, n * 64, b);
+        tma_load_4d(sV + s * SUB_TILE + SUB_HALF, &tmV64, &kv_full[s], 64, hk, n * 64, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_it > 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, false, false);
+      constexpr uint32_t idesc_acc = make_idesc_bf16(128, 128, false, true);
+      const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sDO), ds_addr = smem_u32(sDS);
+      auto issue_sdp = [&](int n) {
+        const int s = n & 1; const uint32_t ph = (n >> 1) & 1;
+        mbar_wait(&kv_full[s], ph);
+        mbar_wait(&sdp_empty[s], ph ^ 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sK + s * SUB_TILE), v_addr = smem_u32(sV + s * SUB_TILE);
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const uint32_t oa = (kk >> 2) * FULL_HALF + (kk & 3) * 32, ob = (kk >> 2) * SUB_HALF + (kk & 3) * 32;
+          umma_bf16_ss(tS[s], make_smem_desc(q_addr + oa, 16, 1024), make_smem_desc(k_addr + ob, 16, 1024), idesc_s, kk != 0);
+        }
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const uint32_t oa = (kk >> 2) * FULL_HALF + (kk & 3) * 32, ob = (kk >> 2) * SUB_HALF + (kk & 3) * 32;
+          umma_bf16_ss(tDP[s], make_smem_desc(do_addr + oa, 16, 1024), make_smem_desc(v_addr + ob, 16, 1024), idesc_s, kk != 0);
+        }
+        umma_commit(&sdp_full[s]);
+      };
+      mbar_wait(qdo_full, 0);
+      issue_sdp(0);
+      for (int n = 0; n < n_it; ++n) {
+        if (n + 1 < n_it) issue_sdp(n + 1);
+        const int s = n & 1;
+        mbar_wait(ds_full, n & 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sK + s * SUB_TILE);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)     // dQ += dS (K = 64 keys) x K (MN-major: rows = keys)
+          umma_bf16_ss(tDQ, make_smem_desc(ds_addr + kk * 32, 16, 1024),
+                       make_smem_desc(k_addr + kk * 2048, SUB_HALF, 1024), idesc_acc, (n | kk) != 0);
+        umma_commit(&kv_empty[s]);
+        umma_commit(ds_empty);
+      }
+      umma_commit(acc_done);
+    }
+  } else {
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;
+    const int qi = q0 + r;
+    const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+    const bool row_ok = qi < p.Sq;
+    float L = INFINITY, dl = 0.f;
+    if (row_ok) {
+      const size_t idx = ((size_t)b * p.H + h) * p.Sq + qi;
+      const float l0 = p.lse[idx];
+      L = (l0 == -INFINITY) ? INFINITY : l0 * LOG2E;
+      dl = p.delta[idx];
+    }
+    const int limit = p.causal ? min(qi + off, p.Sk - 1) : (p.Sk - 1);
+    for (int n = 0; n < n_it; ++n) {
+      const int s = n & 1; const uint32_t ph = (n >> 1) & 1;
+      const int k0 = n * 64;
+      mbar_wait(&sdp_full[s], ph);
+      tc_fence_after();
+      float sv[64], dp[64];
+      tmem_ld_32x32b_x32(tS[s] + lane_off, reinterpret_cast<uint32_t*>(sv));
+      tmem_ld_32x32b_x32(tS[s] + lane_off + 32, reinterpret_cast<uint32_t*>(sv) + 32);
+      tmem_ld_32x32b_x32(tDP[s] + lane_off, reinterpret_cast<uint32_t*>(dp));
+      tmem_ld_32x32b_x32(tDP[s] + lane_off + 32, reinterpret_cast<uint32_t*>(dp) + 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&sdp_empty[s]);
+      uint32_t w0 = 0xffffffffu, w1 = 0xffffffffu;
+      if (p.kbits) {
+        const int wi = k0 >> 5;
+        w0 = (wi < p.kbits_stride) ? __ldg(p.kbits + (size_t)b * p.kbits_stride + wi) : 0u;
+        w1 = (wi + 1 < p.kbits_stride) ? __ldg(p.kbits + (size_t)b * p.kbits_stride + wi + 1) : 0u;
+      }
+      uint32_t dsk[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float dsv[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = 2 * i + e, kj = k0 + c;
+          const uint32_t w = (c < 32) ? w0 : w1;
+          const bool vis = (kj <= limit) && ((w >> (c & 31)) & 1u);
+          const float pe = vis ? fast_exp2(fmaf(sv[c], p.scale_log2, -L)) : 0.f;
+          dsv[e] = pe * (dp[c] - dl) * p.scale;
+        }
+        dsk[i] = pack_bf16(dsv[0], dsv[1]);
+      }
+      if (n > 0) mbar_wait(ds_empty, (n - 1) & 1);
+      store_row64(sDS, r, dsk);
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(ds_full);
+    }
+    bf16* dqp = p.dq + (size_t)b * p.dq_sb + (size_t)(row_ok ? qi : 0) * p.dq_ss + (size_t)h * p.dq_sh;
+    if (n_it > 0) {
+      mbar_wait(acc_done, 0);
+      tc_fence_after();
+      store_acc_row(tDQ + lane_off, dqp, row_ok, 1.f);
+    } else if (row_ok) {
+      const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) *reinterpret_cast<uint4*>(dqp + c * 8) = z;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// delta[b,h,q] = sum_d dO * O   (one warp per row of 128)
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, float* __restrict__ delta,
+                  int B, int H, int Sq, long long o_sb, long long o_ss, long long o_sh,
+                  long long g_sb, long long g_ss, long long g_sh) {
+  const int lane = threadIdx.x & 31;
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long total = (long long)B * H * Sq;
+  if (row >= total) return;
+  const int qi = (int)(row % Sq); const int h = (int)((row / Sq) % H); const int b = (int)(row / ((long long)Sq * H));
+  const bf16* op = o + (size_t)b * o_sb + (size_t)qi * o_ss + (size_t)h * o_sh + lane * 4;
+  const bf16* gp = dout + (size_t)b * g_sb + (size_t)qi * g_ss + (size_t)h * g_sh + lane * 4;
+  const uint2 a = *reinterpret_cast<const uint2*>(op), g = *reinterpret_cast<const uint2*>(gp);
+  const bf162* ah = reinterpret_cast<const bf162*>(&a); const bf162* gh = reinterpret_cast<const bf162*>(&g);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) { float2 x = __bfloat1622float2(ah[i]), y = __bfloat1622float2(gh[i]); s += x.x * y.x + x.y * y.y; }
+  s = mb::warp_sum(s);
+  if (lane == 0) delta[row] = s;      // row index == ((b*H + h)*Sq + qi)
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr; cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)ptr;
+  }
+  return fn;
+}
+static int make_tmap_bshd(CUtensorMap* tm, const void* base, int B, int S, int H, int hd, long long sb, long long ss,
+                          long long sh, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { mb200_set_last_error("cuTensorMapEncodeTiled unavailable"); return -ENOSYS; }
+  cuuint64_t dims[4] = {(cuuint64_t)hd, (cuuint64_t)H, (cuuint64_t)S, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)sh * 2, (cuuint64_t)ss * 2, (cuuint64_t)sb * 2};
+  cuuint32_t box[4] = {64, 1, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { mb200_set_last_error("cuTensorMapEncodeTiled (attention bwd) failed"); return -EINVAL; }
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+// strides: 12 entries as in mb200_attn_generic_bwd ({q,k,v,o} x {b,s,h}); dq/dk/dv/dout are contiguous
+// [B,Sq,H,hd] / [B,Sk,Hkv,hd] / [B,Sk,Hkv,hd] / [B,Sq,H,hd].  delta: [B,H,Sq] fp32 scratch (written here).
+int mb200_attn_bwd_bf16(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
+                        float* delta, void* dq, void* dk, void* dv, int B, int H, int Hkv, int Sq, int Sk, int hd,
+                        const long long* strides, float scale, int causal, const int64_t* kmask, long long kmask_sb,
+                        const void* kbits, void* stream) {
+  if (B <= 0 || Sq <= 0) return MB200_OK;
+  if (hd != HD || H % Hkv != 0 || Sk <= 0) return -ENOTSUP;
+  for (int i = 0; i < 12; ++i) if (strides[i] & 7) return -ENOTSUP;
+  if (kmask && !kbits) return -EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long dq_ss = (long long)H * hd, dq_sb = (long long)Sq * H * hd;
+  const long long dk_ss = (long long)Hkv * hd, dk_sb = (long long)Sk * Hkv * hd;
+  {
+    const long long rows = (long long)B * H * Sq;
+    attn_delta_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>((const bf16*)o, (const bf16*)dout, delta, B, H, Sq,
+                                                                         strides[9], strides[10], strides[11], dq_sb, dq_ss, hd);
+  }
+  CUtensorMap tmQ, tmDO, tmK, tmV, tmQ64, tmDO64, tmK64, tmV64;
+  int rc;
+  if ((rc = make_tmap_bshd(&tmQ, q, B, Sq, H, hd, strides[0], strides[1], strides[2], 128))) return rc;
+  if ((rc = make_tmap_bshd(&tmQ64, q, B, Sq, H, hd, strides[0], strides[1], strides[2], 64))) return rc;
+  if ((rc = make_tmap_bshd(&tmDO, dout, B, Sq, H, hd, dq_sb, dq_ss, hd, 128))) return rc;
+  if ((rc = make_tmap_bshd(&tmDO64, dout, B, Sq, H, hd, dq_sb, dq_ss, hd, 64))) return rc;
+  if ((rc = make_tmap_bshd(&tmK, k, B, Sk, Hkv, hd, strides[3], strides[4], strides[5], 128))) return rc;
+  if ((rc = make_tmap_bshd(&tmK64, k, B, Sk, Hkv, hd, strides[3], strides[4], strides[5], 64))) return rc;
+  if ((rc = make_tmap_bshd(&tmV, v, B, Sk, Hkv, hd, strides[6], strides[7], strides[8], 128))) return rc;
+  if ((rc = make_tmap_bshd(&tmV64, v, B, Sk, Hkv, hd, strides[6], strides[7], strides[8], 64))) return rc;
+  BwdParams p;
+  p.lse = lse; p.delta = delta;
+  p.dq = (bf16*)dq; p.dq_sb = dq_sb; p.dq_ss = dq_ss; p.dq_sh = hd;
+  p.dk = (bf16*)dk; p.dk_sb = dk_sb; p.dk_ss = dk_ss; p.dk_sh = hd;
+  p.dv = (bf16*)dv; p.dv_sb = dk_sb; p.dv_ss = dk_ss; p.dv_sh = hd;
+  p.kbits = kmask ? (const uint32_t*)kbits : nullptr; p.kbits_stride = (Sk + 31) / 32;
+  p.B = B; p.H = H; p.Hkv = Hkv; p.Sq = Sq; p.Sk = Sk; p.scale = scale; p.scale_log2 = scale * LOG2E; p.causal = causal;
+  constexpr int smem_dkv = 2 * FULL_TILE + 4 * SUB_TILE + 2 * FULL_HALF + 1024 + 256 + 1024;
+  constexpr int smem_dq = 2 * FULL_TILE + 4 * SUB_TILE + FULL_HALF + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(attn_bwd_dkv_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dkv) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd_dq_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq) != cudaSuccess) {
+      mb200_set_last_error("cudaFuncSetAttribute(attn bwd smem) failed"); return -EIO;
+    }
+    configured = true;
+  }
+  dim3 gkv((Sk + 127) / 128, Hkv, B), gq((Sq + 127) / 128, H, B);
+  attn_bwd_dkv_sm100_kernel<<<gkv, 192, smem_dkv, st>>>(tmQ64, tmDO64, tmK, tmV, p);
+  attn_bwd_dq_sm100_kernel<<<gq, 192, smem_dq, st>>>(tmQ, tmDO, tmK64, tmV64, p);
+  MB200_CHECK_LAUNCH();
+  return MB200_OK;
+}
+
+}  // extern "C"

@@ -398,7 +398,7 @@ def _attn_fast_ok(q, k, v, hd, Sq, Sk):
     return True
 
 
-def attention_fwd(q, k, v, causal, kmask, scale):
+def attention_fwd(q, k, v, causal, kmask, scale, return_kbits=False):
     """q [B,Sq,H,hd], k/v [B,Sk,Hkv,hd] (hd contiguous). Returns (o [B,Sq,H,hd] contiguous, lse [B,H,Sq] fp32)."""
     _need_cuda(q, k, v)
     B, Sq, H, hd = q.shape
@@ -416,17 +416,31 @@ def attention_fwd(q, k, v, causal, kmask, scale):
             kbits = torch.empty((B * ((Sk + 31) // 32),), dtype=torch.int32, device=q.device)
         _call("mb200_attn_fwd_bf16", _p(q), _p(k), _p(v), _p(o), _p(lse), B, H, Hkv, Sq, Sk, hd, st, float(scale),
               int(causal), _p(kmask), Sk if kmask is not None else 0, _p(kbits), _st())
+        if return_kbits:
+            return o, lse, kbits, True
         return o, lse
     _call("mb200_attn_generic_fwd", _p(q), _p(k), _p(v), _p(o), _p(lse), B, H, Hkv, Sq, Sk, hd, st, float(scale),
           int(causal), _p(kmask), Sk if kmask is not None else 0, _dt(q), _st())
+    if return_kbits:
+        return o, lse, None, False
     return o, lse
 
 
-def attention_bwd(q, k, v, o, do, lse, causal, kmask, scale):
+def attention_bwd(q, k, v, o, do, lse, causal, kmask, scale, kbits=None, fast=False):
     B, Sq, H, hd = q.shape
     Sk, Hkv = k.shape[1], k.shape[2]
     do = do.contiguous()
     assert o.is_contiguous()
+    if fast:
+        dq = torch.empty((B, Sq, H, hd), dtype=q.dtype, device=q.device)
+        dk = torch.empty((B, Sk, Hkv, hd), dtype=q.dtype, device=q.device)
+        dv = torch.empty((B, Sk, Hkv, hd), dtype=q.dtype, device=q.device)
+        delta = torch.empty((B, H, Sq), dtype=torch.float32, device=q.device)
+        st = _strides12(q, k, v, o)
+        _call("mb200_attn_bwd_bf16", _p(q), _p(k), _p(v), _p(o), _p(do), _p(lse), _p(delta), _p(dq), _p(dk), _p(dv),
+              B, H, Hkv, Sq, Sk, hd, st, float(scale), int(causal), _p(kmask), Sk if kmask is not None else 0,
+              _p(kbits), _st())
+        return dq, dk, dv
     qc, kc, vc = q.contiguous(), k.contiguous(), v.contiguous()
     dq = torch.empty_like(qc); dk = torch.empty_like(kc); dv = torch.empty_like(vc)
     delta = torch.empty((B, H, Sq), dtype=torch.float32, device=q.device)
@@ -440,17 +454,17 @@ def attention_bwd(q, k, v, o, do, lse, causal, kmask, scale):
 class _AttentionFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, causal, kmask, scale):
-        o, lse = attention_fwd(q, k, v, causal, kmask, scale)
         if kmask is not None:
             kmask = kmask.contiguous().to(torch.int64)
-        ctx.save_for_backward(q, k, v, o, lse, kmask)
-        ctx.causal, ctx.scale = causal, scale
+        o, lse, kbits, fast = attention_fwd(q, k, v, causal, kmask, scale, return_kbits=True)
+        ctx.save_for_backward(q, k, v, o, lse, kmask, kbits)
+        ctx.causal, ctx.scale, ctx.fast = causal, scale, fast
         return o
 
     @staticmethod
     def backward(ctx, do):
-        q, k, v, o, lse, kmask = ctx.saved_tensors
-        dq, dk, dv = attention_bwd(q, k, v, o, do, lse, ctx.causal, kmask, ctx.scale)
+        q, k, v, o, lse, kmask, kbits = ctx.saved_tensors
+        dq, dk, dv = attention_bwd(q, k, v, o, do, lse, ctx.causal, kmask, ctx.scale, kbits=kbits, fast=ctx.fast)
         return dq, dk, dv, None, None, None
 
 

@@ -271,6 +271,38 @@ def test_attention_tcgen05_fwd(ops, cuda, B, H, Hkv, Sq, Sk, causal, masked):
     assert (lse[lm] - lseg[lm]).abs().max().item() < 2e-2
 
 
+@pytest.mark.parametrize("B,H,Hkv,Sq,Sk,causal,masked", [(1, 4, 2, 128, 128, True, False), (2, 8, 2, 300, 300, True, True),
+                                                         (1, 4, 4, 257, 257, False, False), (1, 8, 2, 1000, 1000, True, False),
+                                                         (2, 4, 1, 200, 455, True, True)])
+def test_attention_tcgen05_bwd(ops, cuda, B, H, Hkv, Sq, Sk, causal, masked):
+    torch.manual_seed(13)
+    hd = 128
+    q = torch.randn(B, Sq, H, hd, device=cuda).bfloat16().requires_grad_(True)
+    k = torch.randn(B, Sk, Hkv, hd, device=cuda).bfloat16().requires_grad_(True)
+    v = torch.randn(B, Sk, Hkv, hd, device=cuda).bfloat16().requires_grad_(True)
+    kmask = None
+    if masked:
+        kmask = torch.ones(B, Sk, dtype=torch.int64, device=cuda)
+        kmask[B - 1, :37] = 0
+    scale = hd ** -0.5
+    o = ops.attention(q, k, v, causal=causal, kmask=kmask, scale=scale)
+    off = Sk - Sq
+    vis = torch.ones(B, Sq, Sk, dtype=torch.bool, device=cuda)
+    if causal:
+        vis &= (torch.arange(Sk, device=cuda)[None, :] <= torch.arange(Sq, device=cuda)[:, None] + off)[None]
+    if kmask is not None:
+        vis &= (kmask != 0)[:, None, :]
+    rows = vis.any(-1)[:, :, None, None]
+    go = (torch.randn_like(o) * rows.to(o.dtype))
+    o.backward(go)
+    qr, kr, vr = [t.detach().float().requires_grad_(True) for t in (q, k, v)]
+    orf = _attn_ref(qr, kr, vr, causal, kmask, scale)
+    orf.backward(go.float())
+    assert _rel(q.grad * rows, qr.grad * rows) < 1.5e-2, _rel(q.grad * rows, qr.grad * rows)
+    assert _rel(k.grad, kr.grad) < 1.5e-2, _rel(k.grad, kr.grad)
+    assert _rel(v.grad, vr.grad) < 1.5e-2, _rel(v.grad, vr.grad)
+
+
 # ------------------------------------------------------------------------------------------------ merge
 def _merge_case(rng, B, T, P, D, mode, zero_pad_rows):
     ids = rng.integers(1, 12, size=(B, T))
