@@ -81,6 +81,8 @@ int mb200_colsum(const void* x, float* part, void* out, int accumulate, long lon
 int mb200_im2col(const void* px, int px_dtype, void* out, int out_dtype, int N, int C, int H, int W, int p, int Kpad,
                  void* stream);
 int mb200_cast(const void* x, int in_dtype, void* y, int out_dtype, long long n, void* stream);
+/* flags[r] = 1 iff row r is all zeros: Idefics2 padding-image removal (mantis/models/idefics2/modeling_idefics2.py:1637-1639) */
+int mb200_rows_all_zero(const void* x, long long n_rows, long long row_elems, int* flags, int dtype, void* stream);
 
 /* ---- shifted masked cross-entropy (modeling_llava.py:523-537; modeling_idefics2.py:1883-1899) and AdamW ---- */
 int mb200_shift_labels(const int64_t* labels, const int64_t* mask, int64_t* out, int B, int S, int64_t ignore_index,

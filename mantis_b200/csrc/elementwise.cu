@@ -354,6 +354,29 @@ cast_kernel(const Tin* __restrict__ x, Tout* __restrict__ y, long long n) {
     y[i] = Cvt<Tout>::from_f(Cvt<Tin>::to_f(x[i]));
 }
 
+// flags[r] = 1 iff every element of row r is exactly zero (Idefics2 padding-image detection,
+// mantis/models/idefics2/modeling_idefics2.py:1637-1639); one CTA per row, early exit per chunk
+template <typename T>
+__global__ void __launch_bounds__(256)
+rows_all_zero_kernel(const T* __restrict__ x, long long row_elems, int* __restrict__ flags) {
+  __shared__ int nz;
+  if (threadIdx.x == 0) nz = 0;
+  __syncthreads();
+  const T* row = x + (size_t)blockIdx.x * row_elems;
+  for (long long base = 0; base < row_elems; base += 256 * 16) {
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      long long i = base + (long long)j * 256 + threadIdx.x;
+      if (i < row_elems) any |= !(Cvt<T>::to_f(row[i]) == 0.0f);
+    }
+    if (any) nz = 1;
+    __syncthreads();
+    if (nz) break;
+  }
+  if (threadIdx.x == 0) flags[blockIdx.x] = nz ? 0 : 1;
+}
+
 inline int ew_grid(long long work_items, int threads = 256) {
   long long g = (work_items + threads - 1) / threads;
   long long cap = (long long)mb::num_sms() * 16;
@@ -521,6 +544,11 @@ int mb200_im2col(const void* px, int px_dtype, void* out, int out_dtype, int N, 
   else if (px_dtype == MB200_DTYPE_BF16 && out_dtype == MB200_DTYPE_F32)
     im2col_kernel<bf16, float><<<g, 256, 0, st>>>((const bf16*)px, (float*)out, N, C, H, W, p, gh, gw, K, Kpad);
   else return -EINVAL;
+  MB200_CHECK_LAUNCH(); return MB200_OK;
+}
+int mb200_rows_all_zero(const void* x, long long n_rows, long long row_elems, int* flags, int dtype, void* stream) {
+  if (n_rows <= 0) return MB200_OK;
+  DISPATCH_T(dtype, (rows_all_zero_kernel<T><<<(unsigned)n_rows, 256, 0, (cudaStream_t)stream>>>((const T*)x, row_elems, flags)));
   MB200_CHECK_LAUNCH(); return MB200_OK;
 }
 int mb200_cast(const void* x, int in_dtype, void* y, int out_dtype, long long n, void* stream) {

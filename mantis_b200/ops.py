@@ -708,6 +708,14 @@ def add_rows(x2, table, idx=None, period=None):
     return _AddRowsFn.apply(x2, table, idx, period)
 
 
+def rows_all_zero(x2):
+    """int32 flags[r] = 1 iff row r of the 2-D tensor is entirely zero"""
+    x2 = x2.contiguous()
+    flags = torch.empty((x2.shape[0],), dtype=torch.int32, device=x2.device)
+    _call("mb200_rows_all_zero", _p(x2), x2.shape[0], x2.shape[1], _p(flags), _dt(x2), _st())
+    return flags
+
+
 def adamw_step(p, g, m, v, lr, beta1, beta2, eps, wd, step, grad_scale=1.0):
     _call("mb200_adamw", _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
           float(wd), int(step), float(grad_scale), _dt(p), _st())

@@ -92,3 +92,15 @@ def ref_llava_classes():
             return None
 
     return cfg.LlavaConfig, RefLlava, RefMLlava
+
+
+def ref_idefics2_classes():
+    modm = load_reference_idefics2()
+
+    class RefIdefics2(modm.Idefics2ForConditionalGeneration):
+        _supports_sdpa = True
+
+        def tie_weights(self, *a, **k):
+            return None
+
+    return RefIdefics2
