@@ -64,11 +64,16 @@ class B200Trainer:
         p = self.params[0]
         assert p.grad.data_ptr() == self.flat_grad.data_ptr(), "param.grad was rebound away from the flat buffer"
 
+    def reduce_gradients(self):
+        """the one collective of the data-parallel path: sum the flat gradient buffer over ranks.
+        Returns the scale (1/world) still to be applied (folded into the AdamW kernel)."""
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
+        return 1.0 / self.world
+
     def optimizer_step(self):
         self._restore_grad_views()
-        if self.world > 1:
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)            # the one collective of the DP path
-        scale = 1.0 / self.world
+        scale = self.reduce_gradients()
         if self.max_grad_norm is not None and self.max_grad_norm > 0:
             self._norm.zero_()
             ops.sumsq(self.flat_grad, self._norm)

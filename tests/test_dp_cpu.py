@@ -1,0 +1,59 @@
+"""World-size-2 gloo test (CPU) of the data-parallel plumbing: flat gradient buffer, autograd accumulating into its views
+across micro-batches, and the single all-reduce.  (The AdamW update itself is a CUDA kernel and is tested on the GPU.)"""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mantis_b200.train.engine import B200Trainer
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.GELU(), torch.nn.Linear(32, 4))
+    tr = B200Trainer.__new__(B200Trainer)            # plumbing only: no CUDA kernels on this box
+    from mantis_b200.train.engine import flat_grad_buffer
+    tr.params = [p for p in model.parameters()]
+    tr.flat_grad = flat_grad_buffer(tr.params)
+    tr.world = world; tr.grad_accum = 2
+    g = torch.Generator().manual_seed(100 + rank)
+    xs = [torch.randn(8, 16, generator=g) for _ in range(2)]
+    for x in xs:                                     # two micro-batches accumulate into the flat buffer
+        (model(x).pow(2).mean() / tr.grad_accum).backward()
+    assert tr.params[0].grad.data_ptr() == tr.flat_grad.data_ptr()
+    local = tr.flat_grad.clone()
+    scale = tr.reduce_gradients()
+    q.put((rank, local, tr.flat_grad.clone() * scale))
+    dist.destroy_process_group()
+
+
+def test_flat_buffer_allreduce_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    mean = (res[0][1] + res[1][1]) / 2
+    assert torch.allclose(res[0][2], mean, atol=1e-6) and torch.allclose(res[1][2], mean, atol=1e-6)
+    assert not torch.allclose(res[0][1], res[1][1])          # ranks really saw different data
+
+
+def test_flat_grad_views_are_aligned():
+    from mantis_b200.train.engine import flat_grad_buffer
+    ps = [torch.nn.Parameter(torch.randn(n)) for n in (3, 17, 64, 5)]
+    flat = flat_grad_buffer(ps)
+    for p in ps:
+        assert (p.grad.data_ptr() - flat.data_ptr()) % 16 == 0
+        assert p.grad.shape == p.shape
