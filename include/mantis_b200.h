@@ -107,6 +107,11 @@ int mb200_gemm_bf16(const void* A, const void* B, void* C, const void* bias, con
                     long long lda, long long ldb, long long ldc, long long ld_add, int transA, int transB, int act,
                     void* stream);
 
+/* CTA-pair (cta_group::2, 256x256 tile per SM pair) variant of mb200_gemm_bf16; identical contract. */
+int mb200_gemm_bf16_2cta(const void* A, const void* B, void* C, const void* bias, const void* addend, int M, int N, int K,
+                         long long lda, long long ldb, long long ldc, long long ld_add, int transA, int transB, int act,
+                         void* stream);
+
 /* ---- attention: softmax(q k^T * scale + causal/padding mask) v, GQA (llama/modeling_llama.py:199-289;
  *      siglip/modeling_siglip.py:229-303; idefics2 perceiver :812-910).  q/o [B,Sq,H,hd], k/v [B,Sk,Hkv,hd];
  *      strides = {q_b,q_s,q_h, k_b,k_s,k_h, v_b,v_s,v_h, o_b,o_s,o_h} in elements -------------------------- */

@@ -1,0 +1,267 @@
+// CTA-pair (cta_group::2) variant of the tcgen05 GEMM: two SMs of one TPC cooperate on a 256 x 256 output tile.
+// Each CTA stages its own 128 rows of A and its own 128 columns of B (so the L2->SM operand traffic per FLOP drops by
+// one third versus the single-CTA 128x256 tile), the even CTA's MMA thread issues tcgen05.mma.cta_group::2 (M = 256,
+// N = 256, K = 16) which reads A from each CTA's shared memory and the two halves of B from both, and accumulates rows
+// 0-127 in CTA0's TMEM and rows 128-255 in CTA1's.  Same epilogue / majorness options as gemm_sm100.cu.
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace {
+using namespace sm100;
+
+constexpr int BM = 128, BK = 64, BN_HALF = 128;          // per CTA; the pair covers 256 x 256
+constexpr int A_STAGE = BM * BK * 2;                     // 16 KB
+constexpr int B_STAGE = BN_HALF * BK * 2;                // 16 KB
+constexpr int STAGES = 6;
+constexpr int GROUP_M = 8;                               // in units of 256-row tile rows
+
+struct GemmEpi {
+  bf16* C; long long ldc;
+  const bf16* bias;
+  const bf16* addend; long long ld_add;
+  int act;
+};
+
+__device__ __forceinline__ float epi_act(float x, int kind) {
+  if (kind == 1) return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+  if (kind == 2) { const float k = 0.79788456080286535588f; return 0.5f * x * (1.f + tanhf(k * (x + 0.044715f * x * x * x))); }
+  if (kind == 3) return x / (1.f + __expf(-1.702f * x));
+  return x;
+}
+__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& mb_, int& nb_) {
+  const int per_group = GROUP_M * num_n;
+  const int g = t / per_group, r = t % per_group;
+  const int gm0 = g * GROUP_M;
+  const int gsz = min(GROUP_M, num_m - gm0);
+  mb_ = gm0 + r % gsz;
+  nb_ = r / gsz;
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const GemmEpi epi, const int M, const int N, const int K) {
+  constexpr uint32_t TMEM_COLS = 512;       // 2 accumulator stages x 256 columns
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_STAGE;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();          // 0 = leader
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int num_m = (M + 255) / 256, num_n = (N + 255) / 256;
+  const int num_tiles = num_m * num_n;
+  const int nkb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA); prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2cta(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        int mb_, nb_; tile_coords(t, num_m, num_n, mb_, nb_);
+        const int m0 = mb_ * 256 + (int)rank * BM, n0 = nb_ * 256 + (int)rank * BN_HALF;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * (A_STAGE + B_STAGE));
+          uint8_t* a_dst = sA + s * A_STAGE;
+          uint8_t* b_dst = sB + s * B_STAGE;
+          if (!A_MN) tma_load_2d_2cta(a_dst, &tmA, &full_bar[s], kb * BK, m0);
+          else {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) tma_load_2d_2cta(a_dst + c * 8192, &tmA, &full_bar[s], m0 + c * 64, kb * BK);
+          }
+          if (!B_MN) tma_load_2d_2cta(b_dst, &tmB, &full_bar[s], kb * BK, n0);
+          else {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) tma_load_2d_2cta(b_dst + c * 8192, &tmB, &full_bar[s], n0 + c * 64, kb * BK);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, 256, A_MN, B_MN);
+      int s = 0; uint32_t ph = 0; int it = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+        const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * 256;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + s * A_STAGE);
+          const uint32_t b_addr = smem_u32(sB + s * B_STAGE);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ad = A_MN ? make_smem_desc(a_addr + k * 2048, 8192, 1024) : make_smem_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t bd = B_MN ? make_smem_desc(b_addr + k * 2048, 8192, 1024) : make_smem_desc(b_addr + k * 32, 16, 1024);
+            umma_bf16_ss_2cta(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2cta(&empty_bar[s], 3);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit_2cta(&tfull_bar[as], 3);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    int it = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+      int mb_, nb_; tile_coords(t, num_m, num_n, mb_, nb_);
+      const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+      const int row = mb_ * 256 + (int)rank * BM + q * 32 + lane;
+      const int n0 = nb_ * 256;
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const bool row_ok = row < M;
+      bf16* crow = epi.C + (size_t)(row_ok ? row : 0) * epi.ldc;
+      const bf16* arow = epi.addend ? epi.addend + (size_t)(row_ok ? row : 0) * epi.ld_add : nullptr;
+      const bool vec_ok = ((epi.ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(epi.C) & 15) == 0) &&
+                          (!epi.addend || (((epi.ld_add & 7) == 0) && ((reinterpret_cast<uintptr_t>(epi.addend) & 15) == 0)));
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + c * 32, r);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        if (row_ok && col0 < N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (epi.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (col0 + j < N) v[j] += __bfloat162float(__ldg(epi.bias + col0 + j));
+          }
+          if (epi.act) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = epi_act(v[j], epi.act);
+          }
+          if (vec_ok && col0 + 32 <= N) {
+            if (arow) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                int4 a4 = *reinterpret_cast<const int4*>(arow + col0 + g * 8);
+                const bf162* ah = reinterpret_cast<const bf162*>(&a4);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(ah[j]); v[g * 8 + 2 * j] += f.x; v[g * 8 + 2 * j + 1] += f.y; }
+              }
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              int4 o4; bf162* oh = reinterpret_cast<bf162*>(&o4);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
+              *reinterpret_cast<int4*>(crow + col0 + g * 8) = o4;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j) {
+              if (col0 + j < N) {
+                float x = v[j];
+                if (arow) x += __bfloat162float(arow[col0 + j]);
+                crow[col0 + j] = __float2bfloat16_rn(x);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc_2cta(tmem_base, TMEM_COLS); }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr; cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+static int make_tmap_2d(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld,
+                        int box_cols, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { mb200_set_last_error("cuTensorMapEncodeTiled unavailable"); return -ENOSYS; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { mb200_set_last_error("cuTensorMapEncodeTiled failed"); return -EINVAL; }
+  return 0;
+}
+
+template <bool A_MN, bool B_MN>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpi& epi, int M, int N, int K, cudaStream_t st) {
+  constexpr int smem = STAGES * (A_STAGE + B_STAGE) + 1024 + 256;
+  auto kern = gemm_sm100_2cta_kernel<A_MN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      mb200_set_last_error("cudaFuncSetAttribute(max dynamic smem) failed"); return -EIO;
+    }
+    configured = true;
+  }
+  const int num_tiles = ((M + 255) / 256) * ((N + 255) / 256);
+  int clusters = mb::num_sms() / 2;
+  if (num_tiles < clusters) clusters = num_tiles;
+  kern<<<clusters * 2, 192, smem, st>>>(tmA, tmB, epi, M, N, K);
+  return 0;
+}
+}  // namespace
+
+extern "C" int mb200_gemm_bf16_2cta(const void* A, const void* B, void* C, const void* bias, const void* addend, int M,
+                                    int N, int K, long long lda, long long ldb, long long ldc, long long ld_add,
+                                    int transA, int transB, int act, void* stream) {
+  if (M <= 0 || N <= 0) return MB200_OK;
+  if (K <= 0) return -EINVAL;
+  if ((lda & 7) || (ldb & 7) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
+    return -ENOTSUP;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!transA) rc = make_tmap_2d(&tmA, A, M, K, lda, BK, BM); else rc = make_tmap_2d(&tmA, A, K, M, lda, 64, BK);
+  if (rc) return rc;
+  if (transB) rc = make_tmap_2d(&tmB, B, N, K, ldb, BK, BN_HALF); else rc = make_tmap_2d(&tmB, B, K, N, ldb, 64, BK);
+  if (rc) return rc;
+  GemmEpi epi;
+  epi.C = (bf16*)C; epi.ldc = ldc; epi.bias = (const bf16*)bias; epi.addend = (const bf16*)addend; epi.ld_add = ld_add; epi.act = act;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool a_mn = transA != 0, b_mn = transB == 0;
+  if (!a_mn && !b_mn) rc = launch<false, false>(tmA, tmB, epi, M, N, K, st);
+  else if (!a_mn && b_mn) rc = launch<false, true>(tmA, tmB, epi, M, N, K, st);
+  else if (a_mn && b_mn) rc = launch<true, true>(tmA, tmB, epi, M, N, K, st);
+  else rc = launch<true, false>(tmA, tmB, epi, M, N, K, st);
+  if (rc) return rc;
+  MB200_CHECK_LAUNCH();
+  return MB200_OK;
+}

@@ -19,6 +19,15 @@ from .layers import B200LayerNorm, B200Linear
 
 
 class B200VisionAttention(nn.Module):
+    """Bidirectional MHA of SigLIP / CLIP (hf: siglip/modeling_siglip.py:252-312).
+
+    Frozen bf16 towers take the tensor-core route: head_dim (72 for so400m) is zero-padded to 128 *inside cached fused
+    QKV / out-proj weights*, so q/k/v come out of ONE tcgen05 GEMM already in the [B, L, H, 128] layout the tcgen05
+    flash-attention kernel wants (padded lanes are exactly zero, so q.k and p.v are unchanged; the softmax scale stays
+    head_dim**-0.5).  Trainable / fp32 / tiny towers use the per-projection kernels + SIMT attention."""
+
+    PAD_HD = 128
+
     def __init__(self, config):
         super().__init__()
         self.embed_dim = config.hidden_size
@@ -29,9 +38,42 @@ class B200VisionAttention(nn.Module):
         self.k_proj = B200Linear(self.embed_dim, self.embed_dim)
         self.v_proj = B200Linear(self.embed_dim, self.embed_dim)
         self.out_proj = B200Linear(self.embed_dim, self.embed_dim)
+        self._pad_cache = None
+        self._pad_key = None
+
+    def _padded_weights(self):
+        ws = (self.q_proj.weight, self.k_proj.weight, self.v_proj.weight, self.out_proj.weight)
+        key = tuple((w.data_ptr(), w._version) for w in ws) + (ws[0].dtype, ws[0].device)
+        if self._pad_key != key:
+            H, hd, P, d = self.num_heads, self.head_dim, self.PAD_HD, self.embed_dim
+            with torch.no_grad():
+                wqkv = torch.zeros((3, H, P, d), dtype=ws[0].dtype, device=ws[0].device)
+                bqkv = torch.zeros((3, H, P), dtype=ws[0].dtype, device=ws[0].device)
+                for i, lin in enumerate((self.q_proj, self.k_proj, self.v_proj)):
+                    wqkv[i, :, :hd] = lin.weight.view(H, hd, d)
+                    if lin.bias is not None:
+                        bqkv[i, :, :hd] = lin.bias.view(H, hd)
+                wo = torch.zeros((d, H, P), dtype=ws[0].dtype, device=ws[0].device)
+                wo[:, :, :hd] = self.out_proj.weight.view(d, H, hd)
+            self._pad_cache = (wqkv.view(3 * H * P, d), bqkv.view(3 * H * P), wo.view(d, H * P))
+            self._pad_key = key
+        return self._pad_cache
+
+    def _can_pad(self, x, key_mask):
+        frozen = not (torch.is_grad_enabled() and (self.q_proj.weight.requires_grad or x.requires_grad))
+        return (frozen and x.dtype == torch.bfloat16 and self.head_dim < self.PAD_HD and x.shape[1] >= 64
+                and not ops.FORCE_GENERIC)
 
     def forward(self, x, residual, key_mask=None):
         B, L, _ = x.shape
+        if self._can_pad(x, key_mask):
+            wqkv, bqkv, wo = self._padded_weights()
+            H, P = self.num_heads, self.PAD_HD
+            qkv = ops.gemm(x.reshape(B * L, self.embed_dim), wqkv, bias=bqkv).view(B, L, 3, H, P)
+            o, _ = ops.attention_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], False, key_mask, self.scale)
+            out = ops.gemm(o.view(B * L, H * P), wo, bias=self.out_proj.bias,
+                           addend=residual.reshape(B * L, self.embed_dim) if residual is not None else None)
+            return out.view(B, L, self.embed_dim)
         q = self.q_proj(x).view(B, L, self.num_heads, self.head_dim)
         k = self.k_proj(x).view(B, L, self.num_heads, self.head_dim)
         v = self.v_proj(x).view(B, L, self.num_heads, self.head_dim)

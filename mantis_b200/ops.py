@@ -20,6 +20,7 @@ _GEMM_ACT = {None: 0, "gelu": 1, "gelu_pytorch_tanh": 2, "gelu_new": 2, "gelu_ta
 # Minimum M*N*K for the tensor-core GEMM (below this the SIMT kernel is as fast and supports any alignment).
 FAST_GEMM_MIN_WORK = int(os.environ.get("MB200_FAST_GEMM_MIN_WORK", str(128 * 128 * 64)))
 FORCE_GENERIC = os.environ.get("MB200_FORCE_GENERIC", "0") == "1"
+GEMM_2CTA = os.environ.get("MB200_GEMM_2CTA", "0") == "1"      # CTA-pair tiles for large problems
 
 launch_count = 0   # kernels (C-ABI calls) issued; bench.py reports it as gpu_launches
 
@@ -86,7 +87,8 @@ def gemm(a, b, trans_a=False, trans_b=True, bias=None, act=None, addend=None, ou
     if addend is not None:
         assert addend.shape == out.shape and addend.stride(1) == 1
     if _fast_ok(a, b, M, N, K) and out.dtype == torch.bfloat16:
-        _call("mb200_gemm_bf16", _p(a), _p(b), _p(out), _p(bias), _p(addend), M, N, K, a.stride(0), b.stride(0),
+        fn = "mb200_gemm_bf16_2cta" if (GEMM_2CTA and M >= 512 and N >= 512) else "mb200_gemm_bf16"
+        _call(fn, _p(a), _p(b), _p(out), _p(bias), _p(addend), M, N, K, a.stride(0), b.stride(0),
               out.stride(0), addend.stride(0) if addend is not None else 0, int(trans_a), int(trans_b),
               _GEMM_ACT[act], _st())
         return out
@@ -137,6 +139,7 @@ class _LinearFn(torch.autograd.Function):
             pre = None
             y = gemm(x2, weight, bias=bias, act=act, addend=res2)
         ctx.save_for_backward(x2, weight, pre)
+        ctx.weight_ref = weight if getattr(weight, "_b200_fused_grad", False) else None
         ctx.act = act
         ctx.has_bias = bias is not None
         ctx.has_res = residual is not None
@@ -156,7 +159,12 @@ class _LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = gemm(g2, weight, trans_a=False, trans_b=False).reshape(ctx.in_shape)      # dx = dy @ W
         if ctx.needs_input_grad[1]:
-            gw = gemm(g2, x2, trans_a=True, trans_b=False)                                 # dW = dy^T @ x
+            wref = ctx.weight_ref
+            if wref is not None and wref.grad is not None and wref.grad.is_contiguous():
+                # gradient accumulation fused into the wgrad epilogue: grad += dy^T @ x (no temporary, no extra pass)
+                gemm(g2, x2, trans_a=True, trans_b=False, addend=wref.grad, out=wref.grad)
+            else:
+                gw = gemm(g2, x2, trans_a=True, trans_b=False)                             # dW = dy^T @ x
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = colsum(g2)
         return gx, gw, gb, None, gres

@@ -33,7 +33,7 @@ def flat_grad_buffer(params):
 
 class B200Trainer:
     def __init__(self, model, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0,
-                 grad_accum=1, freeze_vision=True):
+                 grad_accum=1, freeze_vision=True, fused_wgrad_accum=True):
         self.model = model
         if freeze_vision:                                   # mantis/train/train_mllava.py:239-242
             for n, p in model.named_parameters():
@@ -41,6 +41,12 @@ class B200Trainer:
                     p.requires_grad_(False)
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.flat_grad = flat_grad_buffer(self.params)
+        if fused_wgrad_accum:
+            # linear layers accumulate dW straight into the flat buffer from the wgrad GEMM epilogue
+            from ..models.layers import B200Linear
+            for mod in model.modules():
+                if isinstance(mod, B200Linear) and mod.weight.requires_grad and mod.weight.grad is not None:
+                    mod.weight._b200_fused_grad = True
         self.m = [torch.zeros(p.shape, dtype=torch.float32, device=p.device) for p in self.params]
         self.v = [torch.zeros(p.shape, dtype=torch.float32, device=p.device) for p in self.params]
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay

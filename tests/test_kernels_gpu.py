@@ -64,6 +64,24 @@ def test_gemm_tcgen05(ops, cuda, M, N, K, ta, tb):
     assert err <= 2e-2 * ref.abs().max().item() + 1e-3
 
 
+@pytest.mark.parametrize("M,N,K", [(512, 512, 256), (1000, 1152, 4304), (7864, 1024, 4096), (777, 4096, 1000 * 8)])
+@pytest.mark.parametrize("ta,tb", [(False, True), (False, False), (True, False)])
+def test_gemm_tcgen05_2cta(ops, cuda, M, N, K, ta, tb):
+    import mantis_b200.ops as om
+    torch.manual_seed(21)
+    a = (torch.randn((K, M) if ta else (M, K), device=cuda) * 0.5).bfloat16()
+    b = (torch.randn((N, K) if tb else (K, N), device=cuda) * 0.5).bfloat16()
+    bias = torch.randn(N, device=cuda).bfloat16()
+    res = torch.randn(M, N, device=cuda).bfloat16()
+    old = om.GEMM_2CTA; om.GEMM_2CTA = True
+    try:
+        c = ops.gemm(a, b, trans_a=ta, trans_b=tb, bias=bias, addend=res)
+    finally:
+        om.GEMM_2CTA = old
+    ref = (a.float().t() if ta else a.float()) @ (b.float().t() if tb else b.float()) + bias.float() + res.float()
+    assert _rel(c, ref) < 4e-3, _rel(c, ref)
+
+
 def test_gemm_tcgen05_epilogue(ops, cuda):
     torch.manual_seed(2)
     M, N, K = 515, 1152, 1152
