@@ -1,0 +1,64 @@
+"""CPU tests of the caller-side helpers: placeholder balancing / image tags of MLlavaProcessor and the conversation
+templates (expected strings derived from mantis/models/mllava/processing_llava.py:84-155 and conversation.py:43-145)."""
+import torch
+
+from mantis_b200.models.conversation import conv_templates
+from mantis_b200.models.mllava import MLlavaProcessor
+
+
+class _Img:
+    size = (4, 4)
+
+
+class _Tok:
+    model_input_names = ["input_ids", "attention_mask"]
+
+    def convert_tokens_to_ids(self, t):
+        return 7
+
+    def __call__(self, text, return_tensors=None, padding=False, truncation=None, max_length=None):
+        ids = [[7 if w == "<image>" else 1 for w in t.replace("<image>", " <image> ").split()] for t in text]
+        if max_length:
+            ids = [i[:max_length] for i in ids]
+        L = max(len(i) for i in ids)
+        ids = [i + [0] * (L - len(i)) for i in ids]
+        t = torch.tensor(ids)
+        return {"input_ids": t, "attention_mask": (t != 0).long()}
+
+
+class _IP:
+    model_input_names = ["pixel_values"]
+
+    def __call__(self, images, return_tensors=None):
+        return {"pixel_values": torch.zeros(len(images), 3, 4, 4)}
+
+
+def test_placeholder_balancing_and_tags():
+    p = MLlavaProcessor(_IP(), _Tok())
+    texts, images = p.preprocess_interleaved_images_and_text("USER: compare <image> please", [_Img(), _Img()])
+    assert texts == ["USER:(image 1: <Image><image></Image>) compare (image 2: <Image><image></Image>) please"]
+    texts, _ = p.preprocess_interleaved_images_and_text("a <image> b <image> c <image>", [_Img()])
+    assert texts == ["a (image 1: <Image><image></Image>) b  c "]
+    texts, _ = p.preprocess_interleaved_images_and_text("no tag", [_Img()])
+    assert texts == ["(image 1: <Image><image></Image>)no tag"]
+
+
+def test_call_truncation_drops_images_and_collate_contract():
+    p = MLlavaProcessor(_IP(), _Tok())
+    out = p(text="x <image> y <image> z", images=[_Img(), _Img()], truncation=True, max_length=6)
+    assert int((out["input_ids"] == 7).sum()) == out["pixel_values"].shape[0]
+    col = p._right_pad_inputs_with_attention_mask([dict(out)])
+    assert isinstance(col["pixel_values"], list) and col["input_ids"].shape[0] == 1
+
+
+def test_conversation_templates():
+    c = conv_templates["llama_3"].copy(); c.messages = []
+    c.append_message("user", "hi <image>"); c.append_message("assistant", "")
+    assert c.get_prompt().endswith("<|eot_id|><|start_header_id|>user<|end_header_id|>\n\nhi <image><|eot_id|>"
+                                   "<|start_header_id|>assistant<|end_header_id|>\n\n")
+    c = conv_templates["mllava_v1"].copy(); c.messages = []
+    c.append_message("USER", "q"); c.append_message("ASSISTANT", "")
+    assert c.get_prompt().endswith("</s>USER: q</s>ASSISTANT:")
+    c = conv_templates["idefics_2"].copy(); c.messages = []
+    c.append_message("User", "q"); c.append_message("Assistant", "")
+    assert c.get_prompt() == "User:q<end_of_utterance>\nAssistant:"
