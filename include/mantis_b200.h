@@ -126,6 +126,7 @@ int mb200_attn_generic_bwd(const void* q, const void* k, const void* v, const vo
 /* tcgen05 flash attention (bf16, head_dim 128): same semantics as mb200_attn_generic_fwd; -ENOTSUP if ineligible.
  * kbits_ws: B * mb200_attn_kbits_words(Sk) uint32 of device scratch, needed only when kmask != NULL. */
 long long mb200_attn_kbits_words(int Sk);
+int mb200_kmask_bits(const int64_t* kmask, long long kmask_sb, void* bits, int B, int Sk, void* stream);
 int mb200_attn_fwd_bf16(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Hkv, int Sq,
                         int Sk, int hd, const long long* strides, float scale, int causal, const int64_t* kmask,
                         long long kmask_sb, void* kbits_ws, void* stream);
@@ -136,6 +137,18 @@ int mb200_attn_bwd_bf16(const void* q, const void* k, const void* v, const void*
                         float* delta, void* dq, void* dk, void* dv, int B, int H, int Hkv, int Sq, int Sk, int hd,
                         const long long* strides, float scale, int causal, const int64_t* kmask, long long kmask_sb,
                         const void* kbits, void* stream);
+
+/* ---- decode-time kernels of generate() (q_len 1): skinny GEMM (M <= 16 rows, every weight byte read once), KV-cache
+ *      append, split-KV attention + combine (hf: llama/modeling_llama.py:269-270; ref modeling_llava.py:477-519) ---- */
+int mb200_skinny_gemm_bf16(const void* X, const void* W, void* C, const void* bias, const void* addend, int M, int N,
+                           int K, long long ldx, long long ldw, long long ldc, long long ld_add, void* stream);
+int mb200_kv_append(const void* k_new, const void* v_new, void* k_cache, void* v_cache, const int* pos_dev, int pos_const,
+                    int B, int row_elems, long long ld_new, long long capacity, void* stream);
+int mb200_decode_attn_splits(int ctx);
+int mb200_decode_attn_bf16(const void* q, const void* k, const void* v, void* o, float* part, int B, int H, int Hkv,
+                           int ctx, int hd, long long q_sb, long long q_sh, long long kv_sb, long long kv_ss,
+                           long long kv_sh, long long o_sb, long long o_sh, float scale, const void* kbits,
+                           int kbits_stride, void* stream);
 
 #ifdef __cplusplus
 }

@@ -320,6 +320,16 @@ extern "C" {
 
 long long mb200_attn_kbits_words(int Sk) { return (Sk + 31) / 32; }
 
+// bits[b, w] bit i = (kmask[b, 32 w + i] != 0): key-valid bitmask consumed by the attention kernels
+int mb200_kmask_bits(const int64_t* kmask, long long kmask_sb, void* bits, int B, int Sk, void* stream) {
+  if (B <= 0 || Sk <= 0) return MB200_OK;
+  const int words = (Sk + 31) / 32;
+  const long long threads = (long long)B * words * 32;
+  kmask_bits_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kmask, kmask_sb, (uint32_t*)bits, B, Sk, words);
+  MB200_CHECK_LAUNCH();
+  return MB200_OK;
+}
+
 // bf16, head_dim 128 only (returns -ENOTSUP otherwise: caller uses mb200_attn_generic_fwd).
 // kbits_ws: device scratch of B * mb200_attn_kbits_words(Sk) uint32 (only touched when kmask != null).
 int mb200_attn_fwd_bf16(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Hkv,

@@ -1,0 +1,289 @@
+// Decode-time (q_len == 1) kernels of generate(): HBM-bound by construction.
+//   skinny GEMM  : C[M,N] = X[M,K] W[N,K]^T for M <= 16 rows (one row per sequence of the decode batch).
+//                  Every weight byte is read exactly once with 128-bit loads; X is tiny and stays in L1.
+//                  (the tcgen05 tile kernel would light up only N/256 CTAs for these shapes)
+//   split-KV attention : grid (splits, kv_heads, batch); each CTA streams a slice of the cached keys/values once for all
+//                  query heads of its GQA group, then a combine kernel merges the partial (max, sum, out) triples.
+//   KV append    : writes the new token's K/V rows into the token-major cache at a per-sequence position.
+// These replace DynamicCache's torch.cat growth + SDPA at q_len 1 in the reference stack
+// (hf: llama/modeling_llama.py:269-270; mantis/models/mllava/modeling_llava.py:477-519).
+#include "common.cuh"
+
+namespace {
+using mb::Cvt;
+
+// ------------------------------------------------------------------ skinny GEMM
+template <int MT, int RPW>
+__global__ void __launch_bounds__(256)
+skinny_gemm_kernel(const bf16* __restrict__ X, const bf16* __restrict__ W, bf16* __restrict__ C,
+                   const bf16* __restrict__ bias, const bf16* __restrict__ addend, int M, int N, int K,
+                   long long ldx, long long ldw, long long ldc, long long ld_add) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n0 = (blockIdx.x * 8 + warp) * RPW;
+  if (n0 >= N) return;
+  float acc[RPW][MT];
+#pragma unroll
+  for (int r = 0; r < RPW; ++r)
+#pragma unroll
+    for (int m = 0; m < MT; ++m) acc[r][m] = 0.f;
+  for (int k = lane * 8; k < K; k += 256) {
+    float xv[MT][8];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      if (m < M) mb::Vec8<bf16>::load(X + (size_t)m * ldx + k, xv[m]);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xv[m][j] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      if (n0 + r < N) {
+        int4 wv = mb::ld_stream(reinterpret_cast<const int4*>(W + (size_t)(n0 + r) * ldw + k));
+        const bf162* wh = reinterpret_cast<const bf162*>(&wv);
+        float wf[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { float2 t = __bfloat1622float2(wh[j]); wf[2 * j] = t.x; wf[2 * j + 1] = t.y; }
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[r][m] = fmaf(wf[j], xv[m][j], acc[r][m]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RPW; ++r)
+#pragma unroll
+    for (int m = 0; m < MT; ++m) acc[r][m] = mb::warp_sum(acc[r][m]);
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const int n = n0 + r;
+      if (n >= N) continue;
+      const float b = bias ? __bfloat162float(bias[n]) : 0.f;
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        if (m < M) {
+          float v = acc[r][m] + b;
+          if (addend) v += __bfloat162float(addend[(size_t)m * ld_add + n]);
+          C[(size_t)m * ldc + n] = __float2bfloat16_rn(v);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ KV append
+// k_new/v_new: [B, Hkv*hd] rows (row stride ld_new) -> cache[b, pos[b], :, :]  (cache: [B, cap, Hkv*hd])
+__global__ void __launch_bounds__(256)
+kv_append_kernel(const bf16* __restrict__ k_new, const bf16* __restrict__ v_new, bf16* __restrict__ kc,
+                 bf16* __restrict__ vc, const int* __restrict__ pos, int pos_const, int B, int row_elems,
+                 long long ld_new, long long cap) {
+  const int b = blockIdx.y;
+  const int p = pos ? pos[b] : pos_const;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i >= row_elems) return;
+  const size_t dst = ((size_t)b * cap + p) * row_elems + i;
+  *reinterpret_cast<int4*>(kc + dst) = *reinterpret_cast<const int4*>(k_new + (size_t)b * ld_new + i);
+  *reinterpret_cast<int4*>(vc + dst) = *reinterpret_cast<const int4*>(v_new + (size_t)b * ld_new + i);
+}
+
+// ------------------------------------------------------------------ split-KV decode attention (head_dim 128)
+constexpr int DHD = 128;
+constexpr int DKT = 32;             // keys per smem tile
+constexpr int DWARPS = 4;
+
+struct DecP {
+  const bf16* q; long long q_sb, q_sh;          // q [B, H, hd]
+  const bf16* k; const bf16* v; long long kv_sb, kv_ss, kv_sh;   // cache [B, cap, Hkv, hd]
+  const uint32_t* kbits; int kbits_stride;      // key-valid bitmask or null
+  float* part;                                  // [B, H, splits, hd + 2]
+  int B, H, Hkv, ctx, splits, chunk; float scale;
+};
+
+template <int G>
+__global__ void __launch_bounds__(DWARPS * 32)
+decode_attn_kernel(DecP p) {
+  __shared__ __align__(16) bf162 Ks[DWARPS][DKT][DHD / 2 + 1];   // 65-word rows: conflict-free column walks
+  __shared__ float Qs[G][DHD];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int sp = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
+  for (int i = threadIdx.x; i < G * DHD; i += blockDim.x) {
+    const int g = i / DHD, d = i % DHD;
+    Qs[g][d] = __bfloat162float(p.q[(size_t)b * p.q_sb + (size_t)(hk * G + g) * p.q_sh + d]) * p.scale;
+  }
+  __syncthreads();
+  const int k_begin = sp * p.chunk, k_end = min(p.ctx, k_begin + p.chunk);
+  float m[G], l[G], acc[G][4];
+#pragma unroll
+  for (int g = 0; g < G; ++g) { m[g] = -INFINITY; l[g] = 0.f; acc[g][0] = acc[g][1] = acc[g][2] = acc[g][3] = 0.f; }
+  for (int k0 = k_begin + w * DKT; k0 < k_end; k0 += DWARPS * DKT) {
+    // stage 32 keys (each 256 B) coalesced: lane handles 16 B pieces
+    for (int e = lane; e < DKT * 16; e += 32) {
+      const int j = e >> 4, c = e & 15, kj = k0 + j;
+      int4 raw = make_int4(0, 0, 0, 0);
+      if (kj < k_end) raw = *reinterpret_cast<const int4*>(p.k + (size_t)b * p.kv_sb + (size_t)kj * p.kv_ss + (size_t)hk * p.kv_sh + c * 8);
+      const bf162* rh = reinterpret_cast<const bf162*>(&raw);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) Ks[w][j][c * 4 + t] = rh[t];
+    }
+    __syncwarp();
+    const int kj = k0 + lane;
+    bool vis = kj < k_end;
+    if (vis && p.kbits) vis = (p.kbits[(size_t)b * p.kbits_stride + (kj >> 5)] >> (kj & 31)) & 1u;
+    float s[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) s[g] = 0.f;
+    if (vis) {
+      for (int d2 = 0; d2 < DHD / 2; ++d2) {
+        const float2 kv = __bfloat1622float2(Ks[w][lane][d2]);
+#pragma unroll
+        for (int g = 0; g < G; ++g) s[g] = fmaf(Qs[g][2 * d2 + 1], kv.y, fmaf(Qs[g][2 * d2], kv.x, s[g]));
+      }
+    }
+    float pj[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const float sg = vis ? s[g] : -INFINITY;
+      const float mt = mb::warp_max(sg);
+      const float m_new = fmaxf(m[g], mt);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float corr = (m[g] == -INFINITY) ? 0.f : __expf(m[g] - m_use);
+      pj[g] = vis ? __expf(sg - m_use) : 0.f;
+      l[g] = l[g] * corr + mb::warp_sum(pj[g]);
+      m[g] = m_new;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) acc[g][t] *= corr;
+    }
+    __syncwarp();
+    // V: lanes own 4 consecutive dims; rows read straight from global (coalesced 256 B per key)
+    for (int j = 0; j < DKT; ++j) {
+      const int kv_j = k0 + j;
+      if (kv_j >= k_end) break;
+      const uint2 raw = *reinterpret_cast<const uint2*>(p.v + (size_t)b * p.kv_sb + (size_t)kv_j * p.kv_ss + (size_t)hk * p.kv_sh + lane * 4);
+      const bf162* vh = reinterpret_cast<const bf162*>(&raw);
+      const float2 v01 = __bfloat1622float2(vh[0]), v23 = __bfloat1622float2(vh[1]);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const float pb = __shfl_sync(0xffffffffu, pj[g], j);
+        acc[g][0] = fmaf(pb, v01.x, acc[g][0]); acc[g][1] = fmaf(pb, v01.y, acc[g][1]);
+        acc[g][2] = fmaf(pb, v23.x, acc[g][2]); acc[g][3] = fmaf(pb, v23.y, acc[g][3]);
+      }
+    }
+    __syncwarp();
+  }
+  // combine the 4 warps through shared memory (reuse Ks)
+  float* red = reinterpret_cast<float*>(&Ks[0][0][0]);   // [DWARPS][G][DHD + 2] floats (<= 16.6 KB of the 33 KB tile)
+  __syncthreads();
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    float* r = red + ((size_t)w * G + g) * (DHD + 2);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) r[lane * 4 + t] = acc[g][t];
+    if (lane == 0) { r[DHD] = m[g]; r[DHD + 1] = l[g]; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < G * DHD; i += blockDim.x) {
+    const int g = i / DHD, d = i % DHD;
+    float M_ = -INFINITY;
+#pragma unroll
+    for (int ww = 0; ww < DWARPS; ++ww) M_ = fmaxf(M_, red[((size_t)ww * G + g) * (DHD + 2) + DHD]);
+    float o = 0.f, L = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < DWARPS; ++ww) {
+      const float* r = red + ((size_t)ww * G + g) * (DHD + 2);
+      const float sc = (r[DHD] == -INFINITY) ? 0.f : __expf(r[DHD] - M_);
+      o += r[d] * sc; L += r[DHD + 1] * sc;
+    }
+    float* out = p.part + (((size_t)b * p.H + hk * G + g) * p.splits + sp) * (DHD + 2);
+    out[d] = o;
+    if (d == 0) { out[DHD] = M_; out[DHD + 1] = L; }
+  }
+}
+
+__global__ void __launch_bounds__(DHD)
+decode_combine_kernel(const float* __restrict__ part, bf16* __restrict__ o, long long o_sb, long long o_sh, int H,
+                      int splits) {
+  const int h = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
+  const float* base = part + ((size_t)b * H + h) * splits * (DHD + 2);
+  float M_ = -INFINITY;
+  for (int s = 0; s < splits; ++s) M_ = fmaxf(M_, base[(size_t)s * (DHD + 2) + DHD]);
+  float acc = 0.f, L = 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const float* r = base + (size_t)s * (DHD + 2);
+    const float sc = (r[DHD] == -INFINITY) ? 0.f : __expf(r[DHD] - M_);
+    acc += r[d] * sc; L += r[DHD + 1] * sc;
+  }
+  o[(size_t)b * o_sb + (size_t)h * o_sh + d] = __float2bfloat16_rn(L > 0.f ? acc / L : 0.f);
+}
+
+template <int MT>
+int launch_skinny(const void* X, const void* W, void* C, const void* bias, const void* addend, int M, int N, int K,
+                  long long ldx, long long ldw, long long ldc, long long ld_add, cudaStream_t st) {
+  constexpr int RPW = (MT <= 4) ? 2 : 4;
+  const int rows_per_block = 8 * RPW;
+  const int grid = (N + rows_per_block - 1) / rows_per_block;
+  skinny_gemm_kernel<MT, RPW><<<grid, 256, 0, st>>>((const bf16*)X, (const bf16*)W, (bf16*)C, (const bf16*)bias,
+                                                   (const bf16*)addend, M, N, K, ldx, ldw, ldc, ld_add);
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+// C[M,N] = X[M,K] W[N,K]^T (+bias) (+addend), bf16, M <= 16, K % 8 == 0, 16-byte aligned rows.
+int mb200_skinny_gemm_bf16(const void* X, const void* W, void* C, const void* bias, const void* addend, int M, int N,
+                           int K, long long ldx, long long ldw, long long ldc, long long ld_add, void* stream) {
+  if (M <= 0 || N <= 0) return MB200_OK;
+  if (M > 16 || (K & 7) || (ldx & 7) || (ldw & 7)) return -ENOTSUP;
+  if ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(W)) & 15) return -ENOTSUP;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (M == 1) launch_skinny<1>(X, W, C, bias, addend, M, N, K, ldx, ldw, ldc, ld_add, st);
+  else if (M == 2) launch_skinny<2>(X, W, C, bias, addend, M, N, K, ldx, ldw, ldc, ld_add, st);
+  else if (M <= 4) launch_skinny<4>(X, W, C, bias, addend, M, N, K, ldx, ldw, ldc, ld_add, st);
+  else if (M <= 8) launch_skinny<8>(X, W, C, bias, addend, M, N, K, ldx, ldw, ldc, ld_add, st);
+  else launch_skinny<16>(X, W, C, bias, addend, M, N, K, ldx, ldw, ldc, ld_add, st);
+  MB200_CHECK_LAUNCH();
+  return MB200_OK;
+}
+
+int mb200_kv_append(const void* k_new, const void* v_new, void* k_cache, void* v_cache, const int* pos_dev, int pos_const,
+                    int B, int row_elems, long long ld_new, long long capacity, void* stream) {
+  if (B <= 0) return MB200_OK;
+  if (row_elems & 7) return -EINVAL;
+  dim3 grid((row_elems / 8 + 255) / 256, B);
+  kv_append_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)k_new, (const bf16*)v_new, (bf16*)k_cache,
+                                                          (bf16*)v_cache, pos_dev, pos_const, B, row_elems, ld_new, capacity);
+  MB200_CHECK_LAUNCH();
+  return MB200_OK;
+}
+
+int mb200_decode_attn_splits(int ctx) { int s = (ctx + 255) / 256; if (s < 1) s = 1; if (s > 64) s = 64; return s; }
+
+// q [B,H,128] (strides q_sb,q_sh), cache k/v [B,cap,Hkv,128] (strides kv_sb, kv_ss, kv_sh), o [B,H,128].
+// part: fp32 scratch of B*H*splits*(130) floats with splits = mb200_decode_attn_splits(ctx).
+int mb200_decode_attn_bf16(const void* q, const void* k, const void* v, void* o, float* part, int B, int H, int Hkv,
+                           int ctx, int hd, long long q_sb, long long q_sh, long long kv_sb, long long kv_ss,
+                           long long kv_sh, long long o_sb, long long o_sh, float scale, const void* kbits,
+                           int kbits_stride, void* stream) {
+  if (B <= 0 || ctx <= 0) return MB200_OK;
+  if (hd != DHD || H % Hkv != 0) return -ENOTSUP;
+  const int G = H / Hkv;
+  DecP p;
+  p.q = (const bf16*)q; p.q_sb = q_sb; p.q_sh = q_sh; p.k = (const bf16*)k; p.v = (const bf16*)v;
+  p.kv_sb = kv_sb; p.kv_ss = kv_ss; p.kv_sh = kv_sh; p.kbits = (const uint32_t*)kbits; p.kbits_stride = kbits_stride;
+  p.part = part; p.B = B; p.H = H; p.Hkv = Hkv; p.ctx = ctx; p.splits = mb200_decode_attn_splits(ctx);
+  p.chunk = (ctx + p.splits - 1) / p.splits; p.scale = scale;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(p.splits, Hkv, B);
+  if (G == 1) decode_attn_kernel<1><<<grid, DWARPS * 32, 0, st>>>(p);
+  else if (G == 2) decode_attn_kernel<2><<<grid, DWARPS * 32, 0, st>>>(p);
+  else if (G == 4) decode_attn_kernel<4><<<grid, DWARPS * 32, 0, st>>>(p);
+  else if (G == 8) decode_attn_kernel<8><<<grid, DWARPS * 32, 0, st>>>(p);
+  else return -ENOTSUP;
+  decode_combine_kernel<<<dim3(H, B), DHD, 0, st>>>(part, (bf16*)o, o_sb, o_sh, H, p.splits);
+  MB200_CHECK_LAUNCH();
+  return MB200_OK;
+}
+
+}  // extern "C"

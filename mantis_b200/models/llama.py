@@ -51,7 +51,7 @@ class B200Attention(nn.Module):
         self.o_proj = B200Linear(self.num_heads * self.head_dim, self.hidden_size, bias=bias)
         self.scaling = self.head_dim ** -0.5
 
-    def forward(self, x, residual, position_ids, inv_freq, rope_scale, key_mask, cache):
+    def forward(self, x, residual, position_ids, inv_freq, rope_scale, key_mask, cache, kbits=None):
         B, S, _ = x.shape
         q = self.q_proj(x).view(B, S, self.num_heads, self.head_dim)
         k = self.k_proj(x).view(B, S, self.num_kv_heads, self.head_dim)
@@ -59,6 +59,10 @@ class B200Attention(nn.Module):
         q, k = ops.rope(q, k, position_ids, inv_freq, rope_scale)
         if cache is not None:
             k, v = cache.append(k, v, self.layer_idx)
+            if (S == 1 and self.head_dim == 128 and q.dtype == torch.bfloat16 and not torch.is_grad_enabled()
+                    and not ops.FORCE_GENERIC):
+                o = ops.decode_attention(q, k, v, k.shape[1], key_mask, self.scaling, kbits=kbits)   # split-KV decode kernel
+                return self.o_proj(o.view(B, S, self.num_heads * self.head_dim), residual=residual)
         o = ops.attention(q, k, v, causal=True, kmask=key_mask, scale=self.scaling)
         return self.o_proj(o.view(B, S, self.num_heads * self.head_dim), residual=residual)
 
@@ -83,8 +87,8 @@ class B200DecoderLayer(nn.Module):
         self.input_layernorm = B200RMSNorm(config.hidden_size, eps=config.rms_norm_eps)
         self.post_attention_layernorm = B200RMSNorm(config.hidden_size, eps=config.rms_norm_eps)
 
-    def forward(self, x, position_ids, inv_freq, rope_scale, key_mask, cache):
-        x = self.self_attn(self.input_layernorm(x), x, position_ids, inv_freq, rope_scale, key_mask, cache)
+    def forward(self, x, position_ids, inv_freq, rope_scale, key_mask, cache, kbits=None):
+        x = self.self_attn(self.input_layernorm(x), x, position_ids, inv_freq, rope_scale, key_mask, cache, kbits)
         x = self.mlp(self.post_attention_layernorm(x), residual=x)
         return x
 
@@ -172,6 +176,10 @@ class B200DecoderModel(B200DecoderPreTrainedModel):
                 raise ValueError(f"attention_mask length {key_mask.shape[1]} != past({past}) + seq({S})")
         inv_freq, rope_scale = self.rope_tables(inputs_embeds.device)
         x = inputs_embeds
+        kbits = None
+        if (S == 1 and cache is not None and key_mask is not None and x.dtype == torch.bfloat16
+                and not torch.is_grad_enabled()):
+            kbits = ops.kmask_bits(key_mask)                 # one bitmask per decode step, shared by all layers
         all_hidden = () if output_hidden_states else None
         for layer in self.layers:
             if output_hidden_states:
@@ -180,7 +188,7 @@ class B200DecoderModel(B200DecoderPreTrainedModel):
                 x = torch.utils.checkpoint.checkpoint(layer, x, position_ids, inv_freq, rope_scale, key_mask, None,
                                                       use_reentrant=False)
             else:
-                x = layer(x, position_ids, inv_freq, rope_scale, key_mask, cache)
+                x = layer(x, position_ids, inv_freq, rope_scale, key_mask, cache, kbits)
         x = self.norm(x)
         if output_hidden_states:
             all_hidden += (x,)

@@ -86,6 +86,12 @@ def gemm(a, b, trans_a=False, trans_b=True, bias=None, act=None, addend=None, ou
         bias = bias.contiguous()
     if addend is not None:
         assert addend.shape == out.shape and addend.stride(1) == 1
+    if (M <= 16 and not trans_a and trans_b and act is None and not FORCE_GENERIC and a.dtype == torch.bfloat16
+            and b.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and K % 8 == 0 and N * K >= 65536
+            and a.stride(0) % 8 == 0 and b.stride(0) % 8 == 0 and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0):
+        _call("mb200_skinny_gemm_bf16", _p(a), _p(b), _p(out), _p(bias), _p(addend), M, N, K, a.stride(0), b.stride(0),
+              out.stride(0), addend.stride(0) if addend is not None else 0, _st())
+        return out
     if _fast_ok(a, b, M, N, K) and out.dtype == torch.bfloat16:
         fn = "mb200_gemm_bf16_2cta" if (GEMM_2CTA and M >= 512 and N >= 512) else "mb200_gemm_bf16"
         _call(fn, _p(a), _p(b), _p(out), _p(bias), _p(addend), M, N, K, a.stride(0), b.stride(0),
@@ -432,6 +438,34 @@ def attention_fwd(q, k, v, causal, kmask, scale, return_kbits=False):
     if return_kbits:
         return o, lse, None, False
     return o, lse
+
+
+def kmask_bits(kmask):
+    """[B, Sk] int mask -> [B, ceil(Sk/32)] uint32 bitmask (as int32 tensor)"""
+    km = kmask.contiguous().to(torch.int64)
+    B, Sk = km.shape
+    bits = torch.empty((B, (Sk + 31) // 32), dtype=torch.int32, device=km.device)
+    _call("mb200_kmask_bits", _p(km), Sk, _p(bits), B, Sk, _st())
+    return bits
+
+
+def decode_attention(q, k_cache, v_cache, ctx, kmask, scale, kbits=None):
+    """q [B,1,H,128] bf16; k_cache/v_cache [B,cap,Hkv,128] (first ctx tokens valid); kmask [B,ctx] or None
+    (or its precomputed bitmask `kbits`, shared by all layers of a decode step)."""
+    B, _, H, hd = q.shape
+    Hkv = k_cache.shape[2]
+    o = torch.empty((B, 1, H, hd), dtype=q.dtype, device=q.device)
+    splits = _L().mb200_decode_attn_splits(ctx)
+    part = torch.empty((B * H * splits * (hd + 2),), dtype=torch.float32, device=q.device)
+    words = 0
+    if kbits is None and kmask is not None:
+        kbits = kmask_bits(kmask[:, :ctx])
+    if kbits is not None:
+        words = kbits.shape[1]
+    _call("mb200_decode_attn_bf16", _p(q), _p(k_cache), _p(v_cache), _p(o), _p(part), B, H, Hkv, ctx, hd,
+          q.stride(0), q.stride(2), k_cache.stride(0), k_cache.stride(1), k_cache.stride(2), o.stride(0), o.stride(2),
+          float(scale), _p(kbits), words, _st())
+    return o
 
 
 def attention_bwd(q, k, v, o, do, lse, causal, kmask, scale, kbits=None, fast=False):

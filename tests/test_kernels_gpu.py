@@ -321,6 +321,37 @@ def test_attention_tcgen05_bwd(ops, cuda, B, H, Hkv, Sq, Sk, causal, masked):
     assert _rel(v.grad, vr.grad) < 1.5e-2, _rel(v.grad, vr.grad)
 
 
+@pytest.mark.parametrize("M", [1, 2, 3, 8, 16])
+def test_skinny_gemm(ops, cuda, M):
+    torch.manual_seed(30)
+    for (N, K) in [(4096, 4096), (1024, 4096), (14336, 4096), (4096, 14336), (1003, 512)]:
+        x = torch.randn(M, K, device=cuda).bfloat16() * 0.3
+        w = torch.randn(N, K, device=cuda).bfloat16() * 0.05
+        b = torch.randn(N, device=cuda).bfloat16()
+        r = torch.randn(M, N, device=cuda).bfloat16()
+        y = ops.gemm(x, w, bias=b, addend=r)
+        ref = x.float() @ w.float().t() + b.float() + r.float()
+        assert _rel(y, ref) < 5e-3, (M, N, K, _rel(y, ref))
+
+
+@pytest.mark.parametrize("B,H,Hkv,ctx", [(1, 32, 8, 6137), (3, 8, 2, 300), (2, 4, 4, 33), (16, 32, 8, 1000)])
+def test_decode_attention(ops, cuda, B, H, Hkv, ctx):
+    torch.manual_seed(31)
+    hd = 128
+    cap = ctx + 50
+    q = torch.randn(B, 1, H, hd, device=cuda).bfloat16()
+    kc = torch.randn(B, cap, Hkv, hd, device=cuda).bfloat16()
+    vc = torch.randn(B, cap, Hkv, hd, device=cuda).bfloat16()
+    kmask = torch.ones(B, ctx, dtype=torch.int64, device=cuda)
+    kmask[B - 1, :7] = 0
+    o = ops.decode_attention(q, kc[:, :ctx], vc[:, :ctx], ctx, kmask, hd ** -0.5)
+    ref = _attn_ref(q.float(), kc[:, :ctx].float(), vc[:, :ctx].float(), True, kmask, hd ** -0.5)
+    assert _rel(o, ref) < 1e-2, _rel(o, ref)
+    o2 = ops.decode_attention(q, kc[:, :ctx], vc[:, :ctx], ctx, None, hd ** -0.5)
+    ref2 = _attn_ref(q.float(), kc[:, :ctx].float(), vc[:, :ctx].float(), True, None, hd ** -0.5)
+    assert _rel(o2, ref2) < 1e-2
+
+
 # ------------------------------------------------------------------------------------------------ merge
 def _merge_case(rng, B, T, P, D, mode, zero_pad_rows):
     ids = rng.integers(1, 12, size=(B, T))
