@@ -58,9 +58,9 @@ int mb200_layernorm_bwd(const void* x, const void* w, const void* dy, const floa
                         float* dw_part, float* db_part, void* dw, void* db, int accumulate, long long n, int D,
                         int dtype, void* stream);
 
-/* ---- RoPE, rotate_half form, in place (transformers llama/modeling_llama.py:146-168) ----------------------- */
-int mb200_rope(void* x, const int64_t* pos, const float* inv_freq, long long n_tok, int H, int hd,
-               long long tok_stride, float attn_scaling, int backward, int dtype, void* stream);
+/* ---- RoPE, rotate_half form (transformers llama/modeling_llama.py:146-168); y may alias x ------------------- */
+int mb200_rope(const void* x, void* y, const int64_t* pos, const float* inv_freq, long long n_tok, int H, int hd,
+               long long tok_stride, long long out_stride, float attn_scaling, int backward, int dtype, void* stream);
 
 /* ---- SwiGLU (llama/modeling_llama.py:182-184; idefics2 :506-521) and GELU family
  *      (projector modeling_llava.py:110-118; SigLIP / CLIP MLP).  kind: 0 erf, 1 tanh, 2 quick ------------- */
@@ -132,7 +132,9 @@ int mb200_attn_fwd_bf16(const void* q, const void* k, const void* v, void* o, fl
                         long long kmask_sb, void* kbits_ws, void* stream);
 
 /* tcgen05 flash attention backward (dK/dV kernel + dQ kernel, deterministic, no atomics).  dq/dk/dv/dout contiguous;
- * kbits = the bitmask scratch filled by mb200_attn_fwd_bf16 for the same kmask (NULL iff kmask == NULL). */
+ * kbits = the bitmask scratch filled by mb200_attn_fwd_bf16 for the same kmask (NULL iff kmask == NULL);
+ * delta = fp32 scratch of 2 * B * H * mb200_attn_bwd_sq_pad(Sq) floats. */
+long long mb200_attn_bwd_sq_pad(int Sq);
 int mb200_attn_bwd_bf16(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
                         float* delta, void* dq, void* dk, void* dv, int B, int H, int Hkv, int Sq, int Sk, int hd,
                         const long long* strides, float scale, int causal, const int64_t* kmask, long long kmask_sb,

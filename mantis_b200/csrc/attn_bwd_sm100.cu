@@ -25,9 +25,13 @@ constexpr int SUB_HALF = 64 * 128;       // [64 rows x 64 bf16] (8 KB)
 constexpr int SUB_TILE = 2 * SUB_HALF;   // [64 rows x 128 hd] (16 KB)
 constexpr float LOG2E = 1.44269504088896340736f;
 
+constexpr int SM_WARPS = 8;              // softmax warps (two per TMEM lane quarter, each takes half of the columns)
+constexpr int SM_THREADS = SM_WARPS * 32;
+constexpr int NTHREADS = 64 + SM_THREADS;
+
 struct BwdParams {
-  const float* lse;      // [B,H,Sq] natural log
-  const float* delta;    // [B,H,Sq]
+  const float2* ld;      // [B,H,Sq_pad] {lse * log2(e) (+inf for dead / padded rows), delta}
+  int Sq_pad;
   bf16* dq; long long dq_sb, dq_ss, dq_sh;
   bf16* dk; long long dk_sb, dk_ss, dk_sh;
   bf16* dv; long long dv_sb, dv_ss, dv_sh;
@@ -43,15 +47,19 @@ __device__ __forceinline__ float fast_exp2(float x) {
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   bf162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&h);
 }
-// write 64 bf16 (32 packed words) as one 128-byte swizzled row r of a K-major tile
-__device__ __forceinline__ void store_row64(uint8_t* tile, int r, const uint32_t* pk) {
+// write 32 bf16 (16 packed words) = chunks [4*half, 4*half+4) of the 128-byte swizzled row r
+__device__ __forceinline__ void store_row32(uint8_t* tile, int r, int half, const uint32_t* pk) {
   uint8_t* rowp = tile + r * 128;
 #pragma unroll
-  for (int ch = 0; ch < 8; ++ch)
-    *reinterpret_cast<uint4*>(rowp + ((ch ^ (r & 7)) << 4)) = make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+  for (int c = 0; c < 4; ++c) {
+    const int ch = half * 4 + c;
+    *reinterpret_cast<uint4*>(rowp + ((ch ^ (r & 7)) << 4)) = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
+  }
 }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+// 1-D bulk copy global -> shared, completion credited to an mbarrier (bytes % 16 == 0, 16-byte aligned)
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 // store one 128-lane x 128-column fp32 accumulator row as bf16 (256 B) to global
 __device__ __forceinline__ void store_acc_row(uint32_t taddr, bf16* dst, bool ok, float mul) {
@@ -75,7 +83,7 @@ __device__ __forceinline__ void store_acc_row(uint32_t taddr, bf16* dst, bool ok
 }
 
 // ============================================================================================ dK / dV
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant__ CUtensorMap tmDO64,
                           const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                           const BwdParams p) {
@@ -87,9 +95,8 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __gri
   uint8_t* sDO = sQ + 2 * SUB_TILE;             // 2 stages x 16 KB
   uint8_t* sPT = sDO + 2 * SUB_TILE;            // 16 KB  [128 keys x 64 q]
   uint8_t* sDST = sPT + FULL_HALF;              // 16 KB
-  float* sLse = reinterpret_cast<float*>(sDST + FULL_HALF);   // [2][64]
-  float* sDelta = sLse + 128;                                  // [2][64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 128);
+  float2* sLD = reinterpret_cast<float2*>(sDST + FULL_HALF);   // [2][64] {lse2, delta}
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sLD + 128);
   uint64_t* kv_full = bars + 0;
   uint64_t* qdo_full = bars + 1;    // [2]
   uint64_t* qdo_empty = bars + 3;   // [2]
@@ -98,7 +105,8 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __gri
   uint64_t* pds_full = bars + 9;
   uint64_t* pds_empty = bars + 10;
   uint64_t* acc_done = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* ld_empty = bars + 12;   // [2]  softmax finished reading sLD[s]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
@@ -115,9 +123,10 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __gri
     prefetch_tmap(&tmQ64); prefetch_tmap(&tmDO64); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
     mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1); mbar_init(&sdp_full[s], 1); mbar_init(&sdp_empty[s], 128);
+      mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1); mbar_init(&sdp_full[s], 1);
+      mbar_init(&sdp_empty[s], SM_THREADS); mbar_init(&ld_empty[s], SM_THREADS);
     }
-    mbar_init(pds_full, 128); mbar_init(pds_empty, 1); mbar_init(acc_done, 1);
+    mbar_init(pds_full, SM_THREADS); mbar_init(pds_empty, 1); mbar_init(acc_done, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -140,11 +149,13 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __gri
         const int s = n & 1; const uint32_t ph = (n >> 1) & 1;
         const int h = hk * G + n / per_head, qs = qs_begin + n % per_head;
         mbar_wait(&qdo_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&qdo_full[s], 2 * SUB_TILE);
+        mbar_wait(&ld_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&qdo_full[s], 2 * SUB_TILE + 64 * 8);
         tma_load_4d(sQ + s * SUB_TILE, &tmQ64, &qdo_full[s], 0, h, qs * 64, b);
         tma_load_4d(sQ + s * SUB_TILE + SUB_HALF, &tmQ64, &qdo_full[s], 64, h, qs * 64, b);
         tma_load_4d(sDO + s * SUB_TILE, &tmDO64, &qdo_full[s], 0, h, qs * 64, b);
         tma_load_4d(sDO + s * SUB_TILE + SUB_HALF, &tmDO64, &qdo_full[s], 64, h, qs * 64, b);
+        bulk_load_1d(sLD + s * 64, p.ld + ((size_t)b * p.H + h) * p.Sq_pad + qs * 64, 64 * 8, &qdo_full[s]);
       }
     }
   } else if (warp == 1) {
@@ -193,75 +204,73 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __gri
       umma_commit(acc_done);
     }
   } else {
-    const int qd = warp & 3;
+    const int qd = warp & 3;                     // TMEM lane quarter
+    const int half = (warp - 2) >> 2;            // which 32 of the 64 query columns
     const int r = qd * 32 + lane;                // key row in tile == TMEM lane
-    const int tid = threadIdx.x - 64;            // 0..127 within the softmax group
     const int kj = k0 + r;
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
     bool key_ok = kj < p.Sk;
     if (key_ok && p.kbits) key_ok = (__ldg(p.kbits + (size_t)b * p.kbits_stride + (kj >> 5)) >> (kj & 31)) & 1u;
+    const int qlim = kj - off;                   // causal: query qi sees key kj iff qi >= kj - off
     for (int n = 0; n < n_it; ++n) {
       const int s = n & 1; const uint32_t ph = (n >> 1) & 1;
-      const int h = hk * G + n / per_head, qs = qs_begin + n % per_head;
-      const int q0 = qs * 64;
-      // stage lse (log2 domain, +inf for dead / out-of-range rows) and delta for the 64 queries of this sub-tile
-      {
-        const int i = tid & 63, qi = q0 + i;
-        const size_t idx = ((size_t)b * p.H + h) * p.Sq + qi;
-        if (tid < 64) {
-          float L = (qi < p.Sq) ? p.lse[idx] : INFINITY;
-          sLse[s * 64 + i] = (L == -INFINITY) ? INFINITY : L * LOG2E;
-        } else {
-          sDelta[s * 64 + i] = (qi < p.Sq) ? p.delta[idx] : 0.f;
-        }
-      }
-      named_bar_sync(1, 128);
+      const int qs = qs_begin + n % per_head;
+      const int q0 = qs * 64 + half * 32;
+      mbar_wait(&qdo_full[s], ph);               // lse/delta of this sub-tile landed (bulk copy on the same barrier)
       mbar_wait(&sdp_full[s], ph);
       tc_fence_after();
-      float sv[64], dp[64];
-      tmem_ld_32x32b_x32(tST[s] + lane_off, reinterpret_cast<uint32_t*>(sv));
-      tmem_ld_32x32b_x32(tST[s] + lane_off + 32, reinterpret_cast<uint32_t*>(sv) + 32);
-      tmem_ld_32x32b_x32(tDPT[s] + lane_off, reinterpret_cast<uint32_t*>(dp));
-      tmem_ld_32x32b_x32(tDPT[s] + lane_off + 32, reinterpret_cast<uint32_t*>(dp) + 32);
+      float sv[32], dp[32];
+      tmem_ld_32x32b_x32(tST[s] + lane_off + half * 32, reinterpret_cast<uint32_t*>(sv));
+      tmem_ld_32x32b_x32(tDPT[s] + lane_off + half * 32, reinterpret_cast<uint32_t*>(dp));
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&sdp_empty[s]);
-      uint32_t pk[32], dk_[32];
-      const int qlim = kj - off;                 // causal: query qi sees key kj iff qi >= kj - off
+      const float2* ldp = sLD + s * 64 + half * 32;
+      uint32_t pk[16], dk_[16];
+      const bool full_vis = key_ok && (!p.causal || q0 >= qlim);
+      if (full_vis) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float pv[2], dsv[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int c = 2 * i + e, qi = q0 + c;
-          const bool vis = key_ok && (!p.causal || qi >= qlim);
-          const float pe = vis ? fast_exp2(fmaf(sv[c], p.scale_log2, -sLse[s * 64 + c])) : 0.f;
-          pv[e] = pe;
-          dsv[e] = pe * (dp[c] - sDelta[s * 64 + c]) * p.scale;
+        for (int i = 0; i < 16; ++i) {
+          const float2 l0 = ldp[2 * i], l1 = ldp[2 * i + 1];
+          const float p0 = fast_exp2(fmaf(sv[2 * i], p.scale_log2, -l0.x));
+          const float p1 = fast_exp2(fmaf(sv[2 * i + 1], p.scale_log2, -l1.x));
+          pk[i] = pack_bf16(p0, p1);
+          dk_[i] = pack_bf16(p0 * (dp[2 * i] - l0.y), p1 * (dp[2 * i + 1] - l1.y));
         }
-        pk[i] = pack_bf16(pv[0], pv[1]);
-        dk_[i] = pack_bf16(dsv[0], dsv[1]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float2 l0 = ldp[2 * i], l1 = ldp[2 * i + 1];
+          const bool v0 = key_ok && (!p.causal || q0 + 2 * i >= qlim);
+          const bool v1 = key_ok && (!p.causal || q0 + 2 * i + 1 >= qlim);
+          const float p0 = v0 ? fast_exp2(fmaf(sv[2 * i], p.scale_log2, -l0.x)) : 0.f;
+          const float p1 = v1 ? fast_exp2(fmaf(sv[2 * i + 1], p.scale_log2, -l1.x)) : 0.f;
+          pk[i] = pack_bf16(p0, p1);
+          dk_[i] = pack_bf16(p0 * (dp[2 * i] - l0.y), p1 * (dp[2 * i + 1] - l1.y));
+        }
       }
+      mbar_arrive(&ld_empty[s]);
       if (n > 0) mbar_wait(pds_empty, (n - 1) & 1);
-      store_row64(sPT, r, pk);
-      store_row64(sDST, r, dk_);
+      store_row32(sPT, r, half, pk);
+      store_row32(sDST, r, half, dk_);
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(pds_full);
     }
-    // ---- epilogue: dK, dV rows -> global ----
+    // ---- epilogue: dK (x softmax scale), dV rows -> global; the two column halves split the 4 chunks of 32 dims ----
     const bool row_ok = kj < p.Sk;
     bf16* dkp = p.dk + (size_t)b * p.dk_sb + (size_t)(row_ok ? kj : 0) * p.dk_ss + (size_t)hk * p.dk_sh;
     bf16* dvp = p.dv + (size_t)b * p.dv_sb + (size_t)(row_ok ? kj : 0) * p.dv_ss + (size_t)hk * p.dv_sh;
     if (n_it > 0) {
       mbar_wait(acc_done, 0);
       tc_fence_after();
-      store_acc_row(tDK + lane_off, dkp, row_ok, 1.f);
-      store_acc_row(tDV + lane_off, dvp, row_ok, 1.f);
+      if (half == 0) store_acc_row(tDK + lane_off, dkp, row_ok, p.scale);
+      else           store_acc_row(tDV + lane_off, dvp, row_ok, 1.f);
     } else if (row_ok) {
       const uint4 z = make_uint4(0, 0, 0, 0);
+      bf16* dst = half == 0 ? dkp : dvp;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) { *reinterpret_cast<uint4*>(dkp + c * 8) = z; *reinterpret_cast<uint4*>(dvp + c * 8) = z; }
+      for (int c = 0; c < 16; ++c) *reinterpret_cast<uint4*>(dst + c * 8) = z;
     }
   }
   tc_fence_before();
@@ -270,7 +279,7 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __gri
 }
 
 // ============================================================================================ dQ
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                          const __grid_constant__ CUtensorMap tmK64, const __grid_constant__ CUtensorMap tmV64,
                          const BwdParams p) {
@@ -306,9 +315,9 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     prefetch_tmap(&tmQ); prefetch_tmap(&tmDO); prefetch_tmap(&tmK64); prefetch_tmap(&tmV64);
     mbar_init(qdo_full, 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); mbar_init(&sdp_full[s], 1); mbar_init(&sdp_empty[s], 128);
+      mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); mbar_init(&sdp_full[s], 1); mbar_init(&sdp_empty[s], SM_THREADS);
     }
-    mbar_init(ds_full, 128); mbar_init(ds_empty, 1); mbar_init(acc_done, 1);
+    mbar_init(ds_full, SM_THREADS); mbar_init(ds_empty, 1); mbar_init(acc_done, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -379,66 +388,77 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     }
   } else {
     const int qd = warp & 3;
+    const int half = (warp - 2) >> 2;            // which 32 of the 64 key columns
     const int r = qd * 32 + lane;
     const int qi = q0 + r;
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
     const bool row_ok = qi < p.Sq;
-    float L = INFINITY, dl = 0.f;
-    if (row_ok) {
-      const size_t idx = ((size_t)b * p.H + h) * p.Sq + qi;
-      const float l0 = p.lse[idx];
-      L = (l0 == -INFINITY) ? INFINITY : l0 * LOG2E;
-      dl = p.delta[idx];
-    }
+    const float2 ldv = p.ld[((size_t)b * p.H + h) * p.Sq_pad + qi];        // padded rows hold {+inf, 0}
+    const float L = ldv.x, dl = ldv.y;
     const int limit = p.causal ? min(qi + off, p.Sk - 1) : (p.Sk - 1);
     for (int n = 0; n < n_it; ++n) {
       const int s = n & 1; const uint32_t ph = (n >> 1) & 1;
-      const int k0 = n * 64;
+      const int k0 = n * 64 + half * 32;
       mbar_wait(&sdp_full[s], ph);
       tc_fence_after();
-      float sv[64], dp[64];
-      tmem_ld_32x32b_x32(tS[s] + lane_off, reinterpret_cast<uint32_t*>(sv));
-      tmem_ld_32x32b_x32(tS[s] + lane_off + 32, reinterpret_cast<uint32_t*>(sv) + 32);
-      tmem_ld_32x32b_x32(tDP[s] + lane_off, reinterpret_cast<uint32_t*>(dp));
-      tmem_ld_32x32b_x32(tDP[s] + lane_off + 32, reinterpret_cast<uint32_t*>(dp) + 32);
+      float sv[32], dp[32];
+      tmem_ld_32x32b_x32(tS[s] + lane_off + half * 32, reinterpret_cast<uint32_t*>(sv));
+      tmem_ld_32x32b_x32(tDP[s] + lane_off + half * 32, reinterpret_cast<uint32_t*>(dp));
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&sdp_empty[s]);
-      uint32_t w0 = 0xffffffffu, w1 = 0xffffffffu;
-      if (p.kbits) {
-        const int wi = k0 >> 5;
-        w0 = (wi < p.kbits_stride) ? __ldg(p.kbits + (size_t)b * p.kbits_stride + wi) : 0u;
-        w1 = (wi + 1 < p.kbits_stride) ? __ldg(p.kbits + (size_t)b * p.kbits_stride + wi + 1) : 0u;
-      }
-      uint32_t dsk[32];
+      uint32_t w = 0xffffffffu;
+      if (p.kbits) { const int wi = k0 >> 5; w = (wi < p.kbits_stride) ? __ldg(p.kbits + (size_t)b * p.kbits_stride + wi) : 0u; }
+      uint32_t dsk[16];
+      if (w == 0xffffffffu && k0 + 31 <= limit) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float dsv[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int c = 2 * i + e, kj = k0 + c;
-          const uint32_t w = (c < 32) ? w0 : w1;
-          const bool vis = (kj <= limit) && ((w >> (c & 31)) & 1u);
-          const float pe = vis ? fast_exp2(fmaf(sv[c], p.scale_log2, -L)) : 0.f;
-          dsv[e] = pe * (dp[c] - dl) * p.scale;
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = fast_exp2(fmaf(sv[2 * i], p.scale_log2, -L));
+          const float p1 = fast_exp2(fmaf(sv[2 * i + 1], p.scale_log2, -L));
+          dsk[i] = pack_bf16(p0 * (dp[2 * i] - dl), p1 * (dp[2 * i + 1] - dl));
         }
-        dsk[i] = pack_bf16(dsv[0], dsv[1]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const bool v0 = (k0 + 2 * i <= limit) && ((w >> (2 * i)) & 1u);
+          const bool v1 = (k0 + 2 * i + 1 <= limit) && ((w >> (2 * i + 1)) & 1u);
+          const float p0 = v0 ? fast_exp2(fmaf(sv[2 * i], p.scale_log2, -L)) : 0.f;
+          const float p1 = v1 ? fast_exp2(fmaf(sv[2 * i + 1], p.scale_log2, -L)) : 0.f;
+          dsk[i] = pack_bf16(p0 * (dp[2 * i] - dl), p1 * (dp[2 * i + 1] - dl));
+        }
       }
       if (n > 0) mbar_wait(ds_empty, (n - 1) & 1);
-      store_row64(sDS, r, dsk);
+      store_row32(sDS, r, half, dsk);
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(ds_full);
     }
-    bf16* dqp = p.dq + (size_t)b * p.dq_sb + (size_t)(row_ok ? qi : 0) * p.dq_ss + (size_t)h * p.dq_sh;
+    // epilogue: each column-half warp stores 64 of the 128 head dims of its dQ row (x softmax scale)
+    bf16* dqp = p.dq + (size_t)b * p.dq_sb + (size_t)(row_ok ? qi : 0) * p.dq_ss + (size_t)h * p.dq_sh + half * 64;
     if (n_it > 0) {
       mbar_wait(acc_done, 0);
       tc_fence_after();
-      store_acc_row(tDQ + lane_off, dqp, row_ok, 1.f);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t ov[32];
+        tmem_ld_32x32b_x32(tDQ + lane_off + half * 64 + c * 32, ov);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 o4;
+            o4.x = pack_bf16(__uint_as_float(ov[g * 8 + 0]) * p.scale, __uint_as_float(ov[g * 8 + 1]) * p.scale);
+            o4.y = pack_bf16(__uint_as_float(ov[g * 8 + 2]) * p.scale, __uint_as_float(ov[g * 8 + 3]) * p.scale);
+            o4.z = pack_bf16(__uint_as_float(ov[g * 8 + 4]) * p.scale, __uint_as_float(ov[g * 8 + 5]) * p.scale);
+            o4.w = pack_bf16(__uint_as_float(ov[g * 8 + 6]) * p.scale, __uint_as_float(ov[g * 8 + 7]) * p.scale);
+            *reinterpret_cast<uint4*>(dqp + c * 32 + g * 8) = o4;
+          }
+        }
+      }
     } else if (row_ok) {
       const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
-      for (int c = 0; c < 16; ++c) *reinterpret_cast<uint4*>(dqp + c * 8) = z;
+      for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(dqp + c * 8) = z;
     }
   }
   tc_fence_before();
@@ -446,16 +466,17 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-// delta[b,h,q] = sum_d dO * O   (one warp per row of 128)
+// ld[b,h,q] = {lse * log2(e) (+inf if the row is dead or q >= Sq), sum_d dO * O}   (one warp per row of 128, rows padded to Sq_pad)
 __global__ void __launch_bounds__(256)
-attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, float* __restrict__ delta,
-                  int B, int H, int Sq, long long o_sb, long long o_ss, long long o_sh,
+attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, const float* __restrict__ lse,
+                  float2* __restrict__ ld, int B, int H, int Sq, int Sq_pad, long long o_sb, long long o_ss, long long o_sh,
                   long long g_sb, long long g_ss, long long g_sh) {
   const int lane = threadIdx.x & 31;
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long total = (long long)B * H * Sq;
+  const long long total = (long long)B * H * Sq_pad;
   if (row >= total) return;
-  const int qi = (int)(row % Sq); const int h = (int)((row / Sq) % H); const int b = (int)(row / ((long long)Sq * H));
+  const int qi = (int)(row % Sq_pad); const int h = (int)((row / Sq_pad) % H); const int b = (int)(row / ((long long)Sq_pad * H));
+  if (qi >= Sq) { if (lane == 0) ld[row] = make_float2(INFINITY, 0.f); return; }
   const bf16* op = o + (size_t)b * o_sb + (size_t)qi * o_ss + (size_t)h * o_sh + lane * 4;
   const bf16* gp = dout + (size_t)b * g_sb + (size_t)qi * g_ss + (size_t)h * g_sh + lane * 4;
   const uint2 a = *reinterpret_cast<const uint2*>(op), g = *reinterpret_cast<const uint2*>(gp);
@@ -464,7 +485,10 @@ attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, flo
 #pragma unroll
   for (int i = 0; i < 2; ++i) { float2 x = __bfloat1622float2(ah[i]), y = __bfloat1622float2(gh[i]); s += x.x * y.x + x.y * y.y; }
   s = mb::warp_sum(s);
-  if (lane == 0) delta[row] = s;      // row index == ((b*H + h)*Sq + qi)
+  if (lane == 0) {
+    const float L = lse[((size_t)b * H + h) * Sq + qi];
+    ld[row] = make_float2((L == -INFINITY) ? INFINITY : L * LOG2E, s);
+  }
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -499,7 +523,10 @@ static int make_tmap_bshd(CUtensorMap* tm, const void* base, int B, int S, int H
 extern "C" {
 
 // strides: 12 entries as in mb200_attn_generic_bwd ({q,k,v,o} x {b,s,h}); dq/dk/dv/dout are contiguous
-// [B,Sq,H,hd] / [B,Sk,Hkv,hd] / [B,Sk,Hkv,hd] / [B,Sq,H,hd].  delta: [B,H,Sq] fp32 scratch (written here).
+// [B,Sq,H,hd] / [B,Sk,Hkv,hd] / [B,Sk,Hkv,hd] / [B,Sq,H,hd].
+// delta: fp32 scratch of 2 * B * H * mb200_attn_bwd_sq_pad(Sq) floats (written here: {lse*log2e, rowsum(dO*O)} pairs).
+long long mb200_attn_bwd_sq_pad(int Sq) { return (long long)((Sq + 127) / 128) * 128; }
+
 int mb200_attn_bwd_bf16(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
                         float* delta, void* dq, void* dk, void* dv, int B, int H, int Hkv, int Sq, int Sk, int hd,
                         const long long* strides, float scale, int causal, const int64_t* kmask, long long kmask_sb,
@@ -511,10 +538,12 @@ int mb200_attn_bwd_bf16(const void* q, const void* k, const void* v, const void*
   cudaStream_t st = (cudaStream_t)stream;
   const long long dq_ss = (long long)H * hd, dq_sb = (long long)Sq * H * hd;
   const long long dk_ss = (long long)Hkv * hd, dk_sb = (long long)Sk * Hkv * hd;
+  const int Sq_pad = (int)mb200_attn_bwd_sq_pad(Sq);
   {
-    const long long rows = (long long)B * H * Sq;
-    attn_delta_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>((const bf16*)o, (const bf16*)dout, delta, B, H, Sq,
-                                                                         strides[9], strides[10], strides[11], dq_sb, dq_ss, hd);
+    const long long rows = (long long)B * H * Sq_pad;
+    attn_delta_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>((const bf16*)o, (const bf16*)dout, lse, (float2*)delta,
+                                                                         B, H, Sq, Sq_pad, strides[9], strides[10], strides[11],
+                                                                         dq_sb, dq_ss, hd);
   }
   CUtensorMap tmQ, tmDO, tmK, tmV, tmQ64, tmDO64, tmK64, tmV64;
   int rc;
@@ -527,7 +556,7 @@ int mb200_attn_bwd_bf16(const void* q, const void* k, const void* v, const void*
   if ((rc = make_tmap_bshd(&tmV, v, B, Sk, Hkv, hd, strides[6], strides[7], strides[8], 128))) return rc;
   if ((rc = make_tmap_bshd(&tmV64, v, B, Sk, Hkv, hd, strides[6], strides[7], strides[8], 64))) return rc;
   BwdParams p;
-  p.lse = lse; p.delta = delta;
+  p.ld = (const float2*)delta; p.Sq_pad = Sq_pad;
   p.dq = (bf16*)dq; p.dq_sb = dq_sb; p.dq_ss = dq_ss; p.dq_sh = hd;
   p.dk = (bf16*)dk; p.dk_sb = dk_sb; p.dk_ss = dk_ss; p.dk_sh = hd;
   p.dv = (bf16*)dv; p.dv_sb = dk_sb; p.dv_ss = dk_ss; p.dv_sh = hd;
@@ -544,8 +573,8 @@ int mb200_attn_bwd_bf16(const void* q, const void* k, const void* v, const void*
     configured = true;
   }
   dim3 gkv((Sk + 127) / 128, Hkv, B), gq((Sq + 127) / 128, H, B);
-  attn_bwd_dkv_sm100_kernel<<<gkv, 192, smem_dkv, st>>>(tmQ64, tmDO64, tmK, tmV, p);
-  attn_bwd_dq_sm100_kernel<<<gq, 192, smem_dq, st>>>(tmQ, tmDO, tmK64, tmV64, p);
+  attn_bwd_dkv_sm100_kernel<<<gkv, NTHREADS, smem_dkv, st>>>(tmQ64, tmDO64, tmK, tmV, p);
+  attn_bwd_dq_sm100_kernel<<<gq, NTHREADS, smem_dq, st>>>(tmQ, tmDO, tmK64, tmV64, p);
   MB200_CHECK_LAUNCH();
   return MB200_OK;
 }

@@ -114,6 +114,125 @@ rmsnorm_bwd_kernel(const T* __restrict__ x, const T* __restrict__ w, const T* __
   if (dw_part) for (int i = threadIdx.x; i < D; i += blockDim.x) dw_part[(size_t)blockIdx.x * D + i] = dw_acc[i];
 }
 
+// ---- vectorised RMSNorm (bf16, D % 256 == 0, D <= 8192): one warp per row, the row lives in registers,
+//      16-byte loads/stores, no block barriers.  HBM traffic = 1 read + 1 write of the activation.
+template <int NV>   // 16-byte vectors per lane: D = NV * 256
+__global__ void __launch_bounds__(256)
+rmsnorm_fwd_vec_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
+                       float* __restrict__ rstd_out, long long n, float eps) {
+  constexpr int D = NV * 256;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp0; r < n; r += nwarps) {
+    const int4* xr = reinterpret_cast<const int4*>(x + (size_t)r * D);
+    int4 xv[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) xv[v] = mb::ld_stream(xr + v * 32 + lane);
+    float ss = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const bf162* h = reinterpret_cast<const bf162*>(&xv[v]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); ss += f.x * f.x + f.y * f.y; }
+    }
+    ss = mb::warp_sum(ss);
+    const float rstd = rsqrtf(ss / (float)D + eps);
+    if (lane == 0 && rstd_out) rstd_out[r] = rstd;
+    int4* yr = reinterpret_cast<int4*>(y + (size_t)r * D);
+    const int4* wr = reinterpret_cast<const int4*>(w);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int4 wv = __ldg(wr + v * 32 + lane);
+      const bf162* h = reinterpret_cast<const bf162*>(&xv[v]);
+      const bf162* wh = reinterpret_cast<const bf162*>(&wv);
+      int4 o; bf162* oh = reinterpret_cast<bf162*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(h[j]), g = __bfloat1622float2(wh[j]);
+        const bf162 nx = __floats2bfloat162_rn(f.x * rstd, f.y * rstd);        // .to(input_dtype) first, like the reference
+        const float2 nf = __bfloat1622float2(nx);
+        oh[j] = __floats2bfloat162_rn(g.x * nf.x, g.y * nf.y);
+      }
+      mb::st_stream(yr + v * 32 + lane, o);
+    }
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(128)
+rmsnorm_bwd_dx_vec_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ dy,
+                          const float* __restrict__ rstd_in, bf16* __restrict__ dx, long long n) {
+  constexpr int D = NV * 256;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int4* wr = reinterpret_cast<const int4*>(w);
+  for (long long r = warp0; r < n; r += nwarps) {
+    const int4* xr = reinterpret_cast<const int4*>(x + (size_t)r * D);
+    const int4* gr = reinterpret_cast<const int4*>(dy + (size_t)r * D);
+    int4 xv[NV], gv[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) { xv[v] = mb::ld_stream(xr + v * 32 + lane); gv[v] = mb::ld_stream(gr + v * 32 + lane); }
+    const float rstd = rstd_in[r];
+    float dot = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int4 wv = __ldg(wr + v * 32 + lane);
+      const bf162* xh = reinterpret_cast<const bf162*>(&xv[v]);
+      const bf162* gh = reinterpret_cast<const bf162*>(&gv[v]);
+      const bf162* wh = reinterpret_cast<const bf162*>(&wv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 xf = __bfloat1622float2(xh[j]), gf = __bfloat1622float2(gh[j]), wf = __bfloat1622float2(wh[j]);
+        dot += gf.x * wf.x * xf.x + gf.y * wf.y * xf.y;
+      }
+    }
+    dot = mb::warp_sum(dot) * rstd / (float)D;       // mean(g*w*xhat)
+    int4* dxr = reinterpret_cast<int4*>(dx + (size_t)r * D);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int4 wv = __ldg(wr + v * 32 + lane);
+      const bf162* xh = reinterpret_cast<const bf162*>(&xv[v]);
+      const bf162* gh = reinterpret_cast<const bf162*>(&gv[v]);
+      const bf162* wh = reinterpret_cast<const bf162*>(&wv);
+      int4 o; bf162* oh = reinterpret_cast<bf162*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 xf = __bfloat1622float2(xh[j]), gf = __bfloat1622float2(gh[j]), wf = __bfloat1622float2(wh[j]);
+        oh[j] = __floats2bfloat162_rn(rstd * (gf.x * wf.x - xf.x * rstd * dot), rstd * (gf.y * wf.y - xf.y * rstd * dot));
+      }
+      mb::st_stream(dxr + v * 32 + lane, o);
+    }
+  }
+}
+
+// dw partials: part[blockIdx.x, c] = sum over this CTA's row slab of dy[r,c] * x[r,c] * rstd[r]  (thread owns 8-wide column groups)
+__global__ void __launch_bounds__(256)
+rmsnorm_bwd_dw_vec_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, const float* __restrict__ rstd_in,
+                          float* __restrict__ part, long long n, int D) {
+  const long long rows_per = (n + gridDim.x - 1) / gridDim.x;
+  const long long r0 = (long long)blockIdx.x * rows_per, r1 = min(n, r0 + rows_per);
+  for (int c0 = threadIdx.x * 8; c0 < D; c0 += 256 * 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (long long r = r0; r < r1; ++r) {
+      const int4 xv = mb::ld_stream(reinterpret_cast<const int4*>(x + (size_t)r * D + c0));
+      const int4 gv = mb::ld_stream(reinterpret_cast<const int4*>(dy + (size_t)r * D + c0));
+      const float rs = rstd_in[r];
+      const bf162* xh = reinterpret_cast<const bf162*>(&xv); const bf162* gh = reinterpret_cast<const bf162*>(&gv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 xf = __bfloat1622float2(xh[j]), gf = __bfloat1622float2(gh[j]);
+        acc[2 * j] += gf.x * xf.x * rs; acc[2 * j + 1] += gf.y * xf.y * rs;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) part[(size_t)blockIdx.x * D + c0 + j] = acc[j];
+  }
+}
+
 // out[i] (+)= sum_p part[p, i]   -> T
 template <typename T>
 __global__ void colsum_partials_kernel(const float* __restrict__ part, int nparts, int D, T* __restrict__ out,
@@ -190,8 +309,8 @@ layernorm_bwd_kernel(const T* __restrict__ x, const T* __restrict__ w, const T* 
 // sign=+1 forward, -1 backward (rotation by -angle).
 template <typename T>
 __global__ void __launch_bounds__(256)
-rope_kernel(T* __restrict__ x, const int64_t* __restrict__ pos, const float* __restrict__ inv_freq,
-            long long n_tok, int H, int hd, long long tok_stride, float attn_scaling, float sign) {
+rope_kernel(const T* x, T* y, const int64_t* __restrict__ pos, const float* __restrict__ inv_freq,
+            long long n_tok, int H, int hd, long long tok_stride, long long out_stride, float attn_scaling, float sign) {
   const int half = hd >> 1;
   const long long total = n_tok * H * half;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -204,12 +323,13 @@ rope_kernel(T* __restrict__ x, const int64_t* __restrict__ pos, const float* __r
     float sn, cs;
     sincosf(ang, &sn, &cs);
     cs = mb::rnd<T>(cs * attn_scaling); sn = mb::rnd<T>(sn * attn_scaling) * sign;
-    T* p = x + (size_t)t * tok_stride + (size_t)h * hd;
+    const T* p = x + (size_t)t * tok_stride + (size_t)h * hd;
+    T* q = y + (size_t)t * out_stride + (size_t)h * hd;
     const float x1 = Cvt<T>::to_f(p[i]), x2 = Cvt<T>::to_f(p[i + half]);
     // q_embed = (q * cos) + (rotate_half(q) * sin), each product rounded to T like the reference
     const float y1 = mb::rnd<T>(x1 * cs) + mb::rnd<T>(-x2 * sn);
     const float y2 = mb::rnd<T>(x2 * cs) + mb::rnd<T>(x1 * sn);
-    p[i] = Cvt<T>::from_f(y1); p[i + half] = Cvt<T>::from_f(y2);
+    q[i] = Cvt<T>::from_f(y1); q[i + half] = Cvt<T>::from_f(y2);
   }
 }
 
@@ -412,6 +532,15 @@ int mb200_embedding_bwd(const int64_t* ids, const void* gout, void* gtable, long
 int mb200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, long long n, int D, float eps,
                       int dtype, void* stream) {
   if (n <= 0) return MB200_OK;
+  if (dtype == MB200_DTYPE_BF16 && (D == 4096 || D == 2048 || D == 1024) &&
+      !((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(w)) & 15)) {
+    long long g = (n + 7) / 8; const long long cap = (long long)mb::num_sms() * 8; if (g > cap) g = cap;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (D == 4096) rmsnorm_fwd_vec_kernel<16><<<(int)g, 256, 0, st>>>((const bf16*)x, (const bf16*)w, (bf16*)y, rstd, n, eps);
+    else if (D == 2048) rmsnorm_fwd_vec_kernel<8><<<(int)g, 256, 0, st>>>((const bf16*)x, (const bf16*)w, (bf16*)y, rstd, n, eps);
+    else rmsnorm_fwd_vec_kernel<4><<<(int)g, 256, 0, st>>>((const bf16*)x, (const bf16*)w, (bf16*)y, rstd, n, eps);
+    MB200_CHECK_LAUNCH(); return MB200_OK;
+  }
   int grid = (int)(n < (long long)mb::num_sms() * 8 ? n : (long long)mb::num_sms() * 8);
   DISPATCH_T(dtype, (rmsnorm_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
                         (const T*)x, (const T*)w, (T*)y, rstd, n, D, eps)));
@@ -425,6 +554,21 @@ int mb200_rmsnorm_bwd(const void* x, const void* w, const void* dy, const float*
                       float* dw_part, void* dw, int accumulate_dw, int accumulate_dx, long long n, int D,
                       int dtype, void* stream) {
   if (n <= 0) return MB200_OK;
+  if (dtype == MB200_DTYPE_BF16 && (D == 4096 || D == 2048 || D == 1024) && !accumulate_dx &&
+      !((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) |
+         reinterpret_cast<uintptr_t>(w)) & 15)) {
+    cudaStream_t st = (cudaStream_t)stream;
+    long long g = (n + 3) / 4; const long long cap = (long long)mb::num_sms() * 12; if (g > cap) g = cap;
+    if (D == 4096) rmsnorm_bwd_dx_vec_kernel<16><<<(int)g, 128, 0, st>>>((const bf16*)x, (const bf16*)w, (const bf16*)dy, rstd, (bf16*)dx, n);
+    else if (D == 2048) rmsnorm_bwd_dx_vec_kernel<8><<<(int)g, 128, 0, st>>>((const bf16*)x, (const bf16*)w, (const bf16*)dy, rstd, (bf16*)dx, n);
+    else rmsnorm_bwd_dx_vec_kernel<4><<<(int)g, 128, 0, st>>>((const bf16*)x, (const bf16*)w, (const bf16*)dy, rstd, (bf16*)dx, n);
+    if (dw && dw_part) {
+      const int parts = mb200_norm_bwd_parts(n);
+      rmsnorm_bwd_dw_vec_kernel<<<parts, 256, 0, st>>>((const bf16*)x, (const bf16*)dy, rstd, dw_part, n, D);
+      colsum_partials_kernel<bf16><<<(D + 255) / 256, 256, 0, st>>>(dw_part, parts, D, (bf16*)dw, accumulate_dw);
+    }
+    MB200_CHECK_LAUNCH(); return MB200_OK;
+  }
   const int grid = mb200_norm_bwd_parts(n);
   const size_t smem = (size_t)D * sizeof(float);
   DISPATCH_T(dtype, {
@@ -463,13 +607,14 @@ int mb200_layernorm_bwd(const void* x, const void* w, const void* dy, const floa
   MB200_CHECK_LAUNCH(); return MB200_OK;
 }
 
-int mb200_rope(void* x, const int64_t* pos, const float* inv_freq, long long n_tok, int H, int hd,
-               long long tok_stride, float attn_scaling, int backward, int dtype, void* stream) {
+int mb200_rope(const void* x, void* y, const int64_t* pos, const float* inv_freq, long long n_tok, int H, int hd,
+               long long tok_stride, long long out_stride, float attn_scaling, int backward, int dtype, void* stream) {
   if (n_tok <= 0) return MB200_OK;
   if (hd & 1) return -EINVAL;
   const long long total = n_tok * H * (hd / 2);
   DISPATCH_T(dtype, (rope_kernel<T><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(
-                        (T*)x, pos, inv_freq, n_tok, H, hd, tok_stride, attn_scaling, backward ? -1.f : 1.f)));
+                        (const T*)x, (T*)y, pos, inv_freq, n_tok, H, hd, tok_stride, out_stride, attn_scaling,
+                        backward ? -1.f : 1.f)));
   MB200_CHECK_LAUNCH(); return MB200_OK;
 }
 

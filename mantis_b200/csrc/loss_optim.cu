@@ -47,6 +47,77 @@ ce_fwd_bwd_kernel(const T* __restrict__ logits, const int64_t* __restrict__ labe
   }
 }
 
+// bf16 fast path: 16-byte vector loads, online (max, sum-exp) in ONE read pass, then one read + one write pass for dlogits
+// (algorithmic minimum for forward+backward is 1 read + 1 write; the second read mostly hits L2: a row is 256 KB).
+__global__ void __launch_bounds__(512)
+ce_fwd_bwd_vec_kernel(const bf16* __restrict__ logits, const int64_t* __restrict__ labels, float* __restrict__ loss_rows,
+                      float* __restrict__ lse_rows, bf16* __restrict__ dlogits, long long n, int V, long long ld,
+                      const float* __restrict__ gscale_ptr, float gscale_const) {
+  __shared__ float red[33];
+  const long long r = blockIdx.x;
+  const bf16* lr = logits + (size_t)r * ld;
+  const long long y = labels[r];
+  const bool ignored = (y < 0 || y >= V);
+  const int nv = V >> 3;
+  if (ignored && !lse_rows) {
+    if (loss_rows && threadIdx.x == 0) loss_rows[r] = 0.f;
+    if (dlogits) {
+      bf16* dr = dlogits + (size_t)r * ld;
+      const int4 z = make_int4(0, 0, 0, 0);
+      for (int i = threadIdx.x; i < nv; i += blockDim.x) reinterpret_cast<int4*>(dr)[i] = z;
+      for (int i = nv * 8 + threadIdx.x; i < V; i += blockDim.x) dr[i] = __float2bfloat16_rn(0.f);
+    }
+    return;
+  }
+  float m = -INFINITY, sacc = 0.f;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    float f[8];
+    mb::Vec8<bf16>::load(lr + (size_t)i * 8, f);
+    float vm = f[0];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) vm = fmaxf(vm, f[j]);
+    const float mn = fmaxf(m, vm);
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += __expf(f[j] - mn);
+    sacc = sacc * __expf(m - mn) + t;      // exp(-inf) = 0 on the first vector
+    m = mn;
+  }
+  for (int i = nv * 8 + threadIdx.x; i < V; i += blockDim.x) {
+    const float v = __bfloat162float(lr[i]);
+    const float mn = fmaxf(m, v);
+    sacc = sacc * __expf(m - mn) + __expf(v - mn);
+    m = mn;
+  }
+  const float M = mb::block_max(m, red);
+  const float se = mb::block_sum((m == -INFINITY) ? 0.f : sacc * __expf(m - M), red);
+  const float lse = M + logf(se);
+  if (threadIdx.x == 0) {
+    if (lse_rows) lse_rows[r] = lse;
+    if (loss_rows) loss_rows[r] = ignored ? 0.f : (lse - __bfloat162float(lr[y]));
+  }
+  if (dlogits) {
+    const float gs = ignored ? 0.f : (gscale_ptr ? *gscale_ptr : gscale_const);
+    bf16* dr = dlogits + (size_t)r * ld;
+    const int yv = ignored ? -1 : (int)(y >> 3);
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+      float f[8];
+      mb::Vec8<bf16>::load(lr + (size_t)i * 8, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = __expf(f[j] - lse);
+      if (i == yv) f[y & 7] -= 1.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] *= gs;
+      mb::Vec8<bf16>::store(dr + (size_t)i * 8, f);
+    }
+    for (int i = nv * 8 + threadIdx.x; i < V; i += blockDim.x) {
+      float pv = __expf(__bfloat162float(lr[i]) - lse);
+      if (i == y) pv -= 1.f;
+      dr[i] = __float2bfloat16_rn(pv * gs);
+    }
+  }
+}
+
 // sum of loss_rows and count of valid labels -> out[0] = sum, out[1] = count  (single CTA, deterministic)
 __global__ void __launch_bounds__(1024)
 ce_reduce_kernel(const float* __restrict__ loss_rows, const int64_t* __restrict__ labels, long long n, int V,
@@ -134,6 +205,12 @@ int mb200_ce_fwd_bwd(const void* logits, const int64_t* labels, float* loss_rows
                      void* stream) {
   if (n <= 0) return MB200_OK;
   if (n > 2147483647LL) return -EINVAL;
+  if (dtype == MB200_DTYPE_BF16 && (ld & 7) == 0 && !(reinterpret_cast<uintptr_t>(logits) & 15) &&
+      (!dlogits || !(reinterpret_cast<uintptr_t>(dlogits) & 15))) {
+    ce_fwd_bwd_vec_kernel<<<(unsigned)n, 512, 0, (cudaStream_t)stream>>>((const bf16*)logits, labels, loss_rows, lse_rows,
+                                                                        (bf16*)dlogits, n, V, ld, gscale_ptr, gscale_const);
+    MB200_CHECK_LAUNCH(); return MB200_OK;
+  }
   DISPATCH_T(dtype, (ce_fwd_bwd_kernel<T><<<(unsigned)n, 512, 0, (cudaStream_t)stream>>>(
                         (const T*)logits, labels, loss_rows, lse_rows, (T*)dlogits, n, V, ld, gscale_ptr, gscale_const)));
   MB200_CHECK_LAUNCH(); return MB200_OK;

@@ -20,7 +20,7 @@ _GEMM_ACT = {None: 0, "gelu": 1, "gelu_pytorch_tanh": 2, "gelu_new": 2, "gelu_ta
 # Minimum M*N*K for the tensor-core GEMM (below this the SIMT kernel is as fast and supports any alignment).
 FAST_GEMM_MIN_WORK = int(os.environ.get("MB200_FAST_GEMM_MIN_WORK", str(128 * 128 * 64)))
 FORCE_GENERIC = os.environ.get("MB200_FORCE_GENERIC", "0") == "1"
-GEMM_2CTA = os.environ.get("MB200_GEMM_2CTA", "0") == "1"      # CTA-pair tiles for large problems
+GEMM_2CTA = os.environ.get("MB200_GEMM_2CTA", "1") == "1"      # CTA-pair tiles for large problems
 
 launch_count = 0   # kernels (C-ABI calls) issued; bench.py reports it as gpu_launches
 
@@ -358,23 +358,22 @@ def embedding(ids, table):
 
 
 # ---------------------------------------------------------------------------------------------- RoPE
-def rope_inplace(x, pos, inv_freq, attn_scaling=1.0, backward=False):
-    """x: [B, S, H, hd] view (hd contiguous, token stride uniform) ; pos: [B, S] int64"""
+def rope_apply(x, pos, inv_freq, attn_scaling=1.0, backward=False):
+    """x: [B, S, H, hd] view (hd contiguous, uniform token stride) ; pos: [B, S] int64 -> new contiguous tensor"""
     B, S, H, hd = x.shape
     assert x.stride(3) == 1 and x.stride(2) == hd and x.stride(0) == S * x.stride(1), "rope needs a [B,S,H,hd] view of a row-major buffer"
     pos = pos.contiguous().to(torch.int64)
-    _call("mb200_rope", _p(x), _p(pos), _p(inv_freq), B * S, H, hd, x.stride(1), float(attn_scaling),
+    y = torch.empty((B, S, H, hd), dtype=x.dtype, device=x.device)
+    _call("mb200_rope", _p(x), _p(y), _p(pos), _p(inv_freq), B * S, H, hd, x.stride(1), H * hd, float(attn_scaling),
           int(backward), _dt(x), _st())
-    return x
+    return y
 
 
 class _RopeFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, pos, inv_freq, attn_scaling):
-        qo = q.contiguous().clone() if q.requires_grad or not q.is_contiguous() else q
-        ko = k.contiguous().clone() if k.requires_grad or not k.is_contiguous() else k
-        rope_inplace(qo, pos, inv_freq, attn_scaling)
-        rope_inplace(ko, pos, inv_freq, attn_scaling)
+        qo = rope_apply(q, pos, inv_freq, attn_scaling)
+        ko = rope_apply(k, pos, inv_freq, attn_scaling)
         ctx.save_for_backward(pos, inv_freq)
         ctx.scaling = attn_scaling
         return qo, ko
@@ -382,10 +381,8 @@ class _RopeFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dq, dk):
         pos, inv_freq = ctx.saved_tensors
-        dq = dq.contiguous().clone(); dk = dk.contiguous().clone()
-        rope_inplace(dq, pos, inv_freq, ctx.scaling, backward=True)
-        rope_inplace(dk, pos, inv_freq, ctx.scaling, backward=True)
-        return dq, dk, None, None, None
+        return (rope_apply(dq.contiguous(), pos, inv_freq, ctx.scaling, backward=True),
+                rope_apply(dk.contiguous(), pos, inv_freq, ctx.scaling, backward=True), None, None, None)
 
 
 def rope(q, k, pos, inv_freq, attn_scaling=1.0):
@@ -477,7 +474,7 @@ def attention_bwd(q, k, v, o, do, lse, causal, kmask, scale, kbits=None, fast=Fa
         dq = torch.empty((B, Sq, H, hd), dtype=q.dtype, device=q.device)
         dk = torch.empty((B, Sk, Hkv, hd), dtype=q.dtype, device=q.device)
         dv = torch.empty((B, Sk, Hkv, hd), dtype=q.dtype, device=q.device)
-        delta = torch.empty((B, H, Sq), dtype=torch.float32, device=q.device)
+        delta = torch.empty((2 * B * H * _L().mb200_attn_bwd_sq_pad(Sq),), dtype=torch.float32, device=q.device)
         st = _strides12(q, k, v, o)
         _call("mb200_attn_bwd_bf16", _p(q), _p(k), _p(v), _p(o), _p(do), _p(lse), _p(delta), _p(dq), _p(dk), _p(dv),
               B, H, Hkv, Sq, Sk, hd, st, float(scale), int(causal), _p(kmask), Sk if kmask is not None else 0,
