@@ -152,6 +152,13 @@ int mb200_decode_attn_bf16(const void* q, const void* k, const void* v, void* o,
                            long long kv_sh, long long o_sb, long long o_sh, float scale, const void* kbits,
                            int kbits_stride, void* stream);
 
+/* ---- native decode step: the whole single-token LLaMA/Mistral step (all layers, final norm, LM head, greedy argmax)
+ *      enqueued by one call (hf: llama/modeling_llama.py:375-427 at q_len 1).  See decode_engine.cu for the tables. ---- */
+int mb200_argmax_bf16(const void* logits, long long ld, int B, int V, int64_t* out, void* stream);
+long long mb200_decode_ws_bytes(int B, int hidden, int n_heads, int n_kv_heads, int head_dim, int inter, int ctx_max);
+int mb200_llama_decode_step(const int* dims, const float* fparm, const void* const* layers, const void* const* misc,
+                            void* ws, long long ld_logits, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

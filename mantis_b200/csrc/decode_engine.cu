@@ -1,0 +1,115 @@
+// Native decode step: one C call enqueues the whole LLaMA/Mistral single-token step (all layers + final norm + LM head +
+// greedy argmax) on a stream -- ~15 launches per layer issued from C++ instead of ~420 Python/ctypes round trips per
+// token, which is what bounds generate() once the kernels themselves are HBM-bound.
+// Mirrors LlamaModel.forward at q_len == 1 (hf: llama/modeling_llama.py:375-427,225-333) with the KV cache of
+// mantis_b200/models/kv_cache.py (token-major [B, capacity, Hkv, hd]).
+#include "common.cuh"
+#include "../../include/mantis_b200.h"
+
+namespace {
+__global__ void __launch_bounds__(1024)
+argmax_kernel(const bf16* __restrict__ logits, long long ld, int V, int64_t* __restrict__ out) {
+  __shared__ float bv[32]; __shared__ int bi[32];
+  const bf16* row = logits + (size_t)blockIdx.x * ld;
+  float best = -INFINITY; int idx = 0x7fffffff;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    const float v = __bfloat162float(row[i]);
+    if (v > best || (v == best && i < idx)) { best = v; idx = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov > best || (ov == best && oi < idx)) { best = ov; idx = oi; }
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { bv[w] = best; bi[w] = idx; }
+  __syncthreads();
+  if (w == 0) {
+    best = bv[lane]; idx = bi[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (ov > best || (ov == best && oi < idx)) { best = ov; idx = oi; }
+    }
+    if (lane == 0) out[blockIdx.x] = idx;
+  }
+}
+}  // namespace
+
+#define TRY(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
+
+extern "C" {
+
+int mb200_argmax_bf16(const void* logits, long long ld, int B, int V, int64_t* out, void* stream) {
+  if (B <= 0) return MB200_OK;
+  argmax_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>((const bf16*)logits, ld, V, out);
+  MB200_CHECK_LAUNCH();
+  return MB200_OK;
+}
+
+// dims  : {n_layers, hidden, n_heads, n_kv_heads, head_dim, intermediate, vocab, B, ctx, capacity, kbits_stride}
+// fparm : {rms_eps, rope_scaling}
+// layers: n_layers x 11 device pointers {wq, wk, wv, wo, w_gate, w_up, w_down, ln1, ln2, k_cache, v_cache}
+// misc  : {embed, final_norm, lm_head, inv_freq, ids(int64[B]), pos(int64[B]), kbits (or null), logits_out [B, ld_logits] bf16,
+//          next_ids (int64[B]) or null}
+// ws    : device scratch, mb200_decode_ws_bytes(...) bytes.   bf16 only; head_dim 128.
+long long mb200_decode_ws_bytes(int B, int hidden, int n_heads, int n_kv_heads, int head_dim, int inter, int ctx_max) {
+  const long long e = 2;
+  long long b = 0;
+  b += 2LL * B * hidden * e;                                   // x, xn
+  b += (long long)B * (n_heads + 2 * n_kv_heads) * head_dim * e * 2;   // q,k,v + rotated q,k (over-allocated)
+  b += (long long)B * n_heads * head_dim * e;                  // attn out
+  b += 3LL * B * inter * e;                                    // gate, up, act
+  b += (long long)B * n_heads * 64 * (head_dim + 2) * 4;       // split-KV partials (<= 64 splits)
+  return b + 4096;
+}
+
+int mb200_llama_decode_step(const int* dims, const float* fparm, const void* const* layers, const void* const* misc,
+                            void* ws, long long ld_logits, void* stream) {
+  const int L = dims[0], D = dims[1], H = dims[2], Hkv = dims[3], hd = dims[4], I = dims[5], V = dims[6], B = dims[7];
+  const int ctx = dims[8]; const long long cap = dims[9]; const int kbs = dims[10];
+  if (B <= 0 || B > 16 || hd != 128) return -ENOTSUP;
+  if (ctx + 1 > cap) return -EINVAL;
+  const float eps = fparm[0], rope_scale = fparm[1];
+  const void* embed = misc[0]; const void* fnorm = misc[1]; const void* lm_head = misc[2];
+  const float* inv_freq = (const float*)misc[3];
+  const int64_t* ids = (const int64_t*)misc[4]; const int64_t* pos = (const int64_t*)misc[5];
+  const void* kbits = misc[6]; void* logits = const_cast<void*>(misc[7]); int64_t* next_ids = (int64_t*)const_cast<void*>(misc[8]);
+  const int dt = MB200_DTYPE_BF16;
+  char* p = (char*)ws;
+  auto take = [&](long long bytes) { void* r = p; p += (bytes + 255) / 256 * 256; return r; };
+  void* x = take(2LL * B * D); void* xn = take(2LL * B * D);
+  void* q = take(2LL * B * H * hd); void* k = take(2LL * B * Hkv * hd); void* v = take(2LL * B * Hkv * hd);
+  void* qr = take(2LL * B * H * hd); void* kr = take(2LL * B * Hkv * hd);
+  void* ao = take(2LL * B * H * hd);
+  void* g = take(2LL * B * I); void* u = take(2LL * B * I); void* act = take(2LL * B * I);
+  float* part = (float*)take(4LL * B * H * 64 * (hd + 2));
+  const float scale = 1.0f / sqrtf((float)hd);
+  const int HD = H * hd, KD = Hkv * hd;
+
+  TRY(mb200_embedding_fwd(ids, embed, x, B, D, V, dt, stream));
+  for (int l = 0; l < L; ++l) {
+    const void* const* w = layers + (size_t)l * 11;
+    TRY(mb200_rmsnorm_fwd(x, w[7], xn, nullptr, B, D, eps, dt, stream));
+    TRY(mb200_skinny_gemm_bf16(xn, w[0], q, nullptr, nullptr, B, HD, D, D, D, HD, 0, stream));
+    TRY(mb200_skinny_gemm_bf16(xn, w[1], k, nullptr, nullptr, B, KD, D, D, D, KD, 0, stream));
+    TRY(mb200_skinny_gemm_bf16(xn, w[2], v, nullptr, nullptr, B, KD, D, D, D, KD, 0, stream));
+    TRY(mb200_rope(q, qr, pos, inv_freq, B, H, hd, HD, HD, rope_scale, 0, dt, stream));
+    TRY(mb200_rope(k, kr, pos, inv_freq, B, Hkv, hd, KD, KD, rope_scale, 0, dt, stream));
+    TRY(mb200_kv_append(kr, v, const_cast<void*>(w[9]), const_cast<void*>(w[10]), nullptr, ctx, B, KD, KD, cap, stream));
+    TRY(mb200_decode_attn_bf16(qr, w[9], w[10], ao, part, B, H, Hkv, ctx + 1, hd, HD, hd, cap * KD, KD, hd, HD, hd, scale,
+                               kbits, kbs, stream));
+    TRY(mb200_skinny_gemm_bf16(ao, w[3], x, nullptr, x, B, D, HD, HD, HD, D, D, stream));          // x += o_proj(attn)
+    TRY(mb200_rmsnorm_fwd(x, w[8], xn, nullptr, B, D, eps, dt, stream));
+    TRY(mb200_skinny_gemm_bf16(xn, w[4], g, nullptr, nullptr, B, I, D, D, D, I, 0, stream));
+    TRY(mb200_skinny_gemm_bf16(xn, w[5], u, nullptr, nullptr, B, I, D, D, D, I, 0, stream));
+    TRY(mb200_swiglu_fwd(g, u, act, (long long)B * I, dt, stream));
+    TRY(mb200_skinny_gemm_bf16(act, w[6], x, nullptr, x, B, D, I, I, I, D, D, stream));            // x += down(act)
+  }
+  TRY(mb200_rmsnorm_fwd(x, fnorm, xn, nullptr, B, D, eps, dt, stream));
+  TRY(mb200_skinny_gemm_bf16(xn, lm_head, logits, nullptr, nullptr, B, V, D, D, D, ld_logits, 0, stream));
+  if (next_ids) TRY(mb200_argmax_bf16(logits, ld_logits, B, V, next_ids, stream));
+  return MB200_OK;
+}
+
+}  // extern "C"

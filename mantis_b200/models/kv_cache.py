@@ -68,6 +68,22 @@ class B200KVCache:
         self.lengths[layer_idx] = n + S_new
         return self.k[layer_idx][:, :n + S_new], self.v[layer_idx][:, :n + S_new]
 
+    def reserve(self, capacity):
+        """grow every layer to at least `capacity` tokens (one reallocation; afterwards pointers are stable, which the
+        native decode engine relies on)"""
+        for i in range(len(self.k)):
+            cur = self.k[i]
+            if cur is not None and cur.shape[1] < capacity:
+                B, _, Hkv, hd = cur.shape
+                self._ensure(i, B, capacity, Hkv, hd, cur.dtype, cur.device)
+
+    def capacity(self):
+        return min(k.shape[1] for k in self.k) if self.k else 0
+
+    def advance(self, n=1):
+        for i in range(len(self.lengths)):
+            self.lengths[i] += n
+
     def reorder_cache(self, beam_idx):
         for i in range(len(self.k)):
             self.k[i] = self.k[i].index_select(0, beam_idx)
