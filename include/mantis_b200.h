@@ -144,6 +144,13 @@ int mb200_attn_bwd_bf16(const void* q, const void* k, const void* v, const void*
  *      append, split-KV attention + combine (hf: llama/modeling_llama.py:269-270; ref modeling_llava.py:477-519) ---- */
 int mb200_skinny_gemm_bf16(const void* X, const void* W, void* C, const void* bias, const void* addend, int M, int N,
                            int K, long long ldx, long long ldw, long long ldc, long long ld_add, void* stream);
+int mb200_skinny_gemm3_bf16(const void* X, const void* W0, const void* W1, const void* W2, void* C0, void* C1, void* C2,
+                            int M, int N0, int N1, int N2, int K, long long ldx, long long ldw, void* stream);
+int mb200_skinny_swiglu_bf16(const void* X, const void* Wg, const void* Wu, void* C, int M, int N, int K, long long ldx,
+                             long long ldw, long long ldc, void* stream);
+int mb200_rope_append_bf16(const void* q, const void* k, const void* v, void* q_out, void* k_cache, void* v_cache,
+                           const int64_t* pos, const float* inv_freq, int B, int H, int Hkv, int hd, int ctx,
+                           long long capacity, float rope_scale, void* stream);
 int mb200_kv_append(const void* k_new, const void* v_new, void* k_cache, void* v_cache, const int* pos_dev, int pos_const,
                     int B, int row_elems, long long ld_new, long long capacity, void* stream);
 int mb200_decode_attn_splits(int ctx);

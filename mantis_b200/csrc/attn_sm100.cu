@@ -39,12 +39,19 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   bf162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-__global__ void __launch_bounds__(192, 1)
+constexpr int SMW = 8;                    // softmax warps: two per TMEM lane quarter, each owns 64 of the 128 S columns
+constexpr int SMT = SMW * 32;
+constexpr int FWD_THREADS = 64 + SMT;
+
+__global__ void __launch_bounds__(FWD_THREADS, 1)
 attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -64,6 +71,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint64_t* p_full = bars + 13;
   uint64_t* pv_done = bars + 14;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  float* sx = reinterpret_cast<float*>(bars + 18);      // [2][128] row-max / row-sum exchange between the column halves
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = gridDim.x - 1 - blockIdx.x;           // heavy (late) causal tiles first
@@ -80,9 +88,9 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
-      mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 128);
+      mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], SMT);
     }
-    mbar_init(p_full, 128); mbar_init(pv_done, 1);
+    mbar_init(p_full, SMT); mbar_init(pv_done, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -151,29 +159,30 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
   } else {
     const int qd = warp & 3;                        // TMEM lane quarter
+    const int half = (warp - 2) >> 2;               // columns [64*half, 64*half + 64) of every S tile / of O
     const int r = qd * 32 + lane;                   // row in tile == TMEM lane
     const int qi = q0 + r;
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-    float m = -INFINITY, l = 0.f;
+    float m = -INFINITY, l = 0.f;                   // l: partial row sum over this thread's columns
     const int limit = p.causal ? (qi + off) : (p.Sk - 1);    // last visible key index for this row
     for (int j = 0; j < n_kv; ++j) {
       const int s = j & 1; const uint32_t ph = (j >> 1) & 1;
-      const int k0 = j * BKV;
+      const int k0 = j * BKV + half * 64;
       mbar_wait(&s_full[s], ph);
       tc_fence_after();
-      float sv[128];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tS[s] + lane_off + c * 32, reinterpret_cast<uint32_t*>(sv) + c * 32);
+      float sv[64];
+      tmem_ld_32x32b_x32(tS[s] + lane_off + half * 64, reinterpret_cast<uint32_t*>(sv));
+      tmem_ld_32x32b_x32(tS[s] + lane_off + half * 64 + 32, reinterpret_cast<uint32_t*>(sv) + 32);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&s_empty[s]);
       // ---- masking (only on tiles that need it) ----
-      const bool tail = (k0 + BKV > p.Sk) || (p.causal && (k0 + BKV - 1 > q0 + off));
-      uint32_t w[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+      const bool tail = (j * BKV + BKV > p.Sk) || (p.causal && (j * BKV + BKV - 1 > q0 + off));
+      uint32_t w[2] = {0xffffffffu, 0xffffffffu};
       bool need = tail;
       if (p.kbits) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           const int wi = (k0 >> 5) + c;
           w[c] = (wi < p.kbits_stride) ? __ldg(p.kbits + (size_t)b * p.kbits_stride + wi) : 0u;
           need |= (w[c] != 0xffffffffu);
@@ -182,7 +191,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       if (need) {
         const int lim = min(limit, p.Sk - 1);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int kj = k0 + c * 32 + i;
@@ -193,14 +202,18 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
       float mx = sv[0];
 #pragma unroll
-      for (int i = 1; i < 128; ++i) mx = fmaxf(mx, sv[i]);
+      for (int i = 1; i < 64; ++i) mx = fmaxf(mx, sv[i]);
+      // exchange the half-row maxima (the pair of threads that share TMEM lane r)
+      sx[half * 128 + r] = mx;
+      named_bar_sync(1, SMT);
+      mx = fmaxf(mx, sx[(half ^ 1) * 128 + r]);
       const float m_new = fmaxf(m, mx * p.scale_log2);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = (m == -INFINITY) ? 0.f : exp2f(m - m_use);
+      const float alpha = (m == -INFINITY) ? 0.f : fast_exp2(m - m_use);
       float rs = 0.f;
-      uint32_t pk[64];
+      uint32_t pk[32];
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
+      for (int i = 0; i < 32; ++i) {
         const float p0 = fast_exp2(fmaf(sv[2 * i], p.scale_log2, -m_use));
         const float p1 = fast_exp2(fmaf(sv[2 * i + 1], p.scale_log2, -m_use));
         rs += p0 + p1;
@@ -214,40 +227,41 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       if (j > 0 && __any_sync(0xffffffffu, changed)) {
         const float a = changed ? alpha : 1.f;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           uint32_t ov[32];
-          tmem_ld_32x32b_x32(tO + lane_off + c * 32, ov);
+          tmem_ld_32x32b_x32(tO + lane_off + half * 64 + c * 32, ov);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * a);
-          tmem_st_32x32b_x16(tO + lane_off + c * 32, ov);
-          tmem_st_32x32b_x16(tO + lane_off + c * 32 + 16, ov + 16);
+          tmem_st_32x32b_x16(tO + lane_off + half * 64 + c * 32, ov);
+          tmem_st_32x32b_x16(tO + lane_off + half * 64 + c * 32 + 16, ov + 16);
         }
         tmem_st_wait();
       }
-      // write P (bf16) as the K-major, 128B-swizzled A operand: row r, 16-byte chunk ch -> ch ^ (r & 7)
+      // write this thread's 64 P columns = one 128-byte row of half-tile `half` (K-major, 128B swizzle: chunk ^ (r & 7))
+      {
+        uint8_t* rowp = sP + half * HALF_BYTES + r * 128;
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        uint8_t* rowp = sP + hf * HALF_BYTES + r * 128;
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          const int idx = hf * 32 + ch * 4;
-          *reinterpret_cast<uint4*>(rowp + ((ch ^ (r & 7)) << 4)) = make_uint4(pk[idx], pk[idx + 1], pk[idx + 2], pk[idx + 3]);
-        }
+        for (int ch = 0; ch < 8; ++ch)
+          *reinterpret_cast<uint4*>(rowp + ((ch ^ (r & 7)) << 4)) = make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
       }
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(p_full);
+      named_bar_sync(2, SMT);      // sx[] is reused by the next tile
     }
     // ---- epilogue ----
     if (n_kv > 0) { mbar_wait(pv_done, (n_kv - 1) & 1); tc_fence_after(); }
+    sx[half * 128 + r] = l;
+    named_bar_sync(1, SMT);
+    l += sx[(half ^ 1) * 128 + r];
     const float inv = (l > 0.f) ? 1.f / l : 0.f;
     const bool row_ok = qi < p.Sq;
-    bf16* op = p.o + (size_t)b * p.o_sb + (size_t)(row_ok ? qi : 0) * p.o_ss + (size_t)h * p.o_sh;
+    bf16* op = p.o + (size_t)b * p.o_sb + (size_t)(row_ok ? qi : 0) * p.o_ss + (size_t)h * p.o_sh + half * 64;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
       uint32_t ov[32];
-      if (n_kv > 0) { tmem_ld_32x32b_x32(tO + lane_off + c * 32, ov); tmem_ld_wait(); }
+      if (n_kv > 0) { tmem_ld_32x32b_x32(tO + lane_off + half * 64 + c * 32, ov); tmem_ld_wait(); }
       else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) ov[i] = 0u;
@@ -264,7 +278,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         }
       }
     }
-    if (row_ok && p.lse)
+    if (row_ok && p.lse && half == 0)
       p.lse[((size_t)b * p.H + h) * p.Sq + qi] = (l > 0.f) ? (m * 0.69314718055994530942f + logf(l)) : -INFINITY;
   }
   tc_fence_before();
@@ -358,7 +372,7 @@ int mb200_attn_fwd_bf16(const void* q, const void* k, const void* v, void* o, fl
     kmask_bits_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(kmask, kmask_sb, (uint32_t*)kbits_ws, B, Sk, words);
     p.kbits = (const uint32_t*)kbits_ws; p.kbits_stride = words;
   }
-  constexpr int smem = 7 * TILE_BYTES + 1024 + 256;
+  constexpr int smem = 7 * TILE_BYTES + 1024 + 256 + 1024;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(attn_fwd_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
@@ -367,7 +381,7 @@ int mb200_attn_fwd_bf16(const void* q, const void* k, const void* v, void* o, fl
     configured = true;
   }
   dim3 grid((Sq + BQ - 1) / BQ, H, B);
-  attn_fwd_sm100_kernel<<<grid, 192, smem, st>>>(tmQ, tmK, tmV, p);
+  attn_fwd_sm100_kernel<<<grid, FWD_THREADS, smem, st>>>(tmQ, tmK, tmV, p);
   MB200_CHECK_LAUNCH();
   return MB200_OK;
 }

@@ -13,34 +13,62 @@ namespace {
 using mb::Cvt;
 
 // ------------------------------------------------------------------ skinny GEMM
-template <int MT, int RPW>
+// Up to three weight matrices that share the same input X are served by ONE launch (q/k/v, or gate/up): `seg` picks the
+// matrix from the output-row index.  mode 1 (two segments = gate, up): writes silu(gate) * up (SwiGLU fused).
+struct SkinnySeg { const bf16* W[3]; bf16* C[3]; int N[3]; long long ldc[3]; int nseg; int mode; };
+
+template <int MT, int RPW, int KU>
 __global__ void __launch_bounds__(256)
-skinny_gemm_kernel(const bf16* __restrict__ X, const bf16* __restrict__ W, bf16* __restrict__ C,
-                   const bf16* __restrict__ bias, const bf16* __restrict__ addend, int M, int N, int K,
-                   long long ldx, long long ldw, long long ldc, long long ld_add) {
+skinny_gemm_kernel(const bf16* __restrict__ X, SkinnySeg sg, const bf16* __restrict__ bias,
+                   const bf16* __restrict__ addend, int M, int K, long long ldx, long long ldw, long long ld_add) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Ntot = (sg.mode == 1) ? sg.N[0] : (sg.N[0] + sg.N[1] + sg.N[2]);
   const int n0 = (blockIdx.x * 8 + warp) * RPW;
-  if (n0 >= N) return;
-  float acc[RPW][MT];
+  if (n0 >= Ntot) return;
+  constexpr int NR = RPW;            // output rows per warp; in SwiGLU mode each output row reads a gate row and an up row
+  float acc[NR][MT], acc2[NR][MT];
 #pragma unroll
-  for (int r = 0; r < RPW; ++r)
+  for (int r = 0; r < NR; ++r)
 #pragma unroll
-    for (int m = 0; m < MT; ++m) acc[r][m] = 0.f;
-  for (int k = lane * 8; k < K; k += 256) {
-    float xv[MT][8];
+    for (int m = 0; m < MT; ++m) { acc[r][m] = 0.f; acc2[r][m] = 0.f; }
+  const bf16* wrow[NR]; const bf16* wrow2[NR];
 #pragma unroll
-    for (int m = 0; m < MT; ++m) {
-      if (m < M) mb::Vec8<bf16>::load(X + (size_t)m * ldx + k, xv[m]);
-      else {
+  for (int r = 0; r < NR; ++r) {
+    int n = n0 + r; if (n >= Ntot) n = Ntot - 1;
+    if (sg.mode == 1) { wrow[r] = sg.W[0] + (size_t)n * ldw; wrow2[r] = sg.W[1] + (size_t)n * ldw; }
+    else {
+      int seg = 0, nn = n;
+      if (nn >= sg.N[0]) { nn -= sg.N[0]; seg = 1; if (nn >= sg.N[1]) { nn -= sg.N[1]; seg = 2; } }
+      wrow[r] = sg.W[seg] + (size_t)nn * ldw; wrow2[r] = wrow[r];
+    }
+  }
+  for (int k = lane * 8; k < K; k += 256 * KU) {
+    int4 wv[KU][NR], wv2[KU][NR];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) xv[m][j] = 0.f;
+    for (int u = 0; u < KU; ++u) {
+      const int kk = k + u * 256;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        wv[u][r] = (kk < K) ? mb::ld_stream(reinterpret_cast<const int4*>(wrow[r] + kk)) : make_int4(0, 0, 0, 0);
+        if (sg.mode == 1) wv2[u][r] = (kk < K) ? mb::ld_stream(reinterpret_cast<const int4*>(wrow2[r] + kk)) : make_int4(0, 0, 0, 0);
       }
     }
 #pragma unroll
-    for (int r = 0; r < RPW; ++r) {
-      if (n0 + r < N) {
-        int4 wv = mb::ld_stream(reinterpret_cast<const int4*>(W + (size_t)(n0 + r) * ldw + k));
-        const bf162* wh = reinterpret_cast<const bf162*>(&wv);
+    for (int u = 0; u < KU; ++u) {
+      const int kk = k + u * 256;
+      if (kk >= K) break;
+      float xv[MT][8];
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        if (m < M) mb::Vec8<bf16>::load(X + (size_t)m * ldx + kk, xv[m]);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) xv[m][j] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const bf162* wh = reinterpret_cast<const bf162*>(&wv[u][r]);
         float wf[8];
 #pragma unroll
         for (int j = 0; j < 4; ++j) { float2 t = __bfloat1622float2(wh[j]); wf[2 * j] = t.x; wf[2 * j + 1] = t.y; }
@@ -48,25 +76,43 @@ skinny_gemm_kernel(const bf16* __restrict__ X, const bf16* __restrict__ W, bf16*
         for (int m = 0; m < MT; ++m)
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[r][m] = fmaf(wf[j], xv[m][j], acc[r][m]);
+        if (sg.mode == 1) {
+          const bf162* wh2 = reinterpret_cast<const bf162*>(&wv2[u][r]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { float2 t = __bfloat1622float2(wh2[j]); wf[2 * j] = t.x; wf[2 * j + 1] = t.y; }
+#pragma unroll
+          for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc2[r][m] = fmaf(wf[j], xv[m][j], acc2[r][m]);
+        }
       }
     }
   }
 #pragma unroll
-  for (int r = 0; r < RPW; ++r)
+  for (int r = 0; r < NR; ++r)
 #pragma unroll
-    for (int m = 0; m < MT; ++m) acc[r][m] = mb::warp_sum(acc[r][m]);
+    for (int m = 0; m < MT; ++m) { acc[r][m] = mb::warp_sum(acc[r][m]); if (sg.mode == 1) acc2[r][m] = mb::warp_sum(acc2[r][m]); }
   if (lane == 0) {
 #pragma unroll
-    for (int r = 0; r < RPW; ++r) {
+    for (int r = 0; r < NR; ++r) {
       const int n = n0 + r;
-      if (n >= N) continue;
-      const float b = bias ? __bfloat162float(bias[n]) : 0.f;
+      if (n >= Ntot) continue;
+      int seg = 0, nn = n;
+      if (sg.mode != 1 && nn >= sg.N[0]) { nn -= sg.N[0]; seg = 1; if (nn >= sg.N[1]) { nn -= sg.N[1]; seg = 2; } }
+      const float b = (bias && seg == 0) ? __bfloat162float(bias[nn]) : 0.f;
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
         if (m < M) {
           float v = acc[r][m] + b;
-          if (addend) v += __bfloat162float(addend[(size_t)m * ld_add + n]);
-          C[(size_t)m * ldc + n] = __float2bfloat16_rn(v);
+          if (sg.mode == 1) {
+            // reference order: act_fn(gate) rounded to bf16, then * up (hf: llama/modeling_llama.py:182-184)
+            const float gq = __bfloat162float(__float2bfloat16_rn(v));
+            const float uq = __bfloat162float(__float2bfloat16_rn(acc2[r][m]));
+            const float sl = __bfloat162float(__float2bfloat16_rn(gq / (1.f + __expf(-gq))));
+            v = sl * uq;
+          }
+          if (addend && seg == 0) v += __bfloat162float(addend[(size_t)m * ld_add + nn]);
+          sg.C[seg][(size_t)m * sg.ldc[seg] + nn] = __float2bfloat16_rn(v);
         }
       }
     }
@@ -86,6 +132,35 @@ kv_append_kernel(const bf16* __restrict__ k_new, const bf16* __restrict__ v_new,
   const size_t dst = ((size_t)b * cap + p) * row_elems + i;
   *reinterpret_cast<int4*>(kc + dst) = *reinterpret_cast<const int4*>(k_new + (size_t)b * ld_new + i);
   *reinterpret_cast<int4*>(vc + dst) = *reinterpret_cast<const int4*>(v_new + (size_t)b * ld_new + i);
+}
+
+// RoPE(q) -> q_out ; RoPE(k) and v -> cache[b, ctx] : one launch per layer for the decode step
+__global__ void __launch_bounds__(256)
+rope_append_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v, bf16* __restrict__ q_out,
+                   bf16* __restrict__ kc, bf16* __restrict__ vc, const int64_t* __restrict__ pos, const float* __restrict__ inv_freq,
+                   int H, int Hkv, int hd, int ctx, long long cap, float rope_scale) {
+  const int b = blockIdx.y;
+  const int half = hd >> 1;
+  const int n_q = H * half, n_k = Hkv * half, n_v = Hkv * hd / 8;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float ps = (float)pos[b];
+  if (i < n_q + n_k) {
+    const bool isq = i < n_q;
+    const int j = isq ? i : i - n_q;
+    const int h = j / half, d = j % half;
+    float sn, cs; sincosf(ps * inv_freq[d], &sn, &cs);
+    cs = __bfloat162float(__float2bfloat16_rn(cs * rope_scale)); sn = __bfloat162float(__float2bfloat16_rn(sn * rope_scale));
+    const bf16* src = (isq ? q + (size_t)b * H * hd : k + (size_t)b * Hkv * hd) + (size_t)h * hd;
+    bf16* dst = (isq ? q_out + (size_t)b * H * hd : kc + ((size_t)b * cap + ctx) * Hkv * hd) + (size_t)h * hd;
+    const float x1 = __bfloat162float(src[d]), x2 = __bfloat162float(src[d + half]);
+    const float y1 = __bfloat162float(__float2bfloat16_rn(x1 * cs)) + __bfloat162float(__float2bfloat16_rn(-x2 * sn));
+    const float y2 = __bfloat162float(__float2bfloat16_rn(x2 * cs)) + __bfloat162float(__float2bfloat16_rn(x1 * sn));
+    dst[d] = __float2bfloat16_rn(y1); dst[d + half] = __float2bfloat16_rn(y2);
+  } else if (i < n_q + n_k + n_v) {
+    const int j = i - n_q - n_k;
+    *reinterpret_cast<int4*>(vc + ((size_t)b * cap + ctx) * Hkv * hd + j * 8) =
+        *reinterpret_cast<const int4*>(v + (size_t)b * Hkv * hd + j * 8);
+  }
 }
 
 // ------------------------------------------------------------------ split-KV decode attention (head_dim 128)
@@ -218,14 +293,24 @@ decode_combine_kernel(const float* __restrict__ part, bf16* __restrict__ o, long
 }
 
 template <int MT>
-int launch_skinny(const void* X, const void* W, void* C, const void* bias, const void* addend, int M, int N, int K,
-                  long long ldx, long long ldw, long long ldc, long long ld_add, cudaStream_t st) {
-  constexpr int RPW = (MT <= 4) ? 2 : 4;
+int launch_skinny(const void* X, const SkinnySeg& sg, const void* bias, const void* addend, int M, int K, long long ldx,
+                  long long ldw, long long ld_add, cudaStream_t st) {
+  constexpr int RPW = (MT <= 2) ? 2 : (MT <= 4 ? 2 : 4);
+  constexpr int KU = (MT <= 2) ? 4 : (MT <= 4 ? 2 : 1);
+  const int Ntot = (sg.mode == 1) ? sg.N[0] : (sg.N[0] + sg.N[1] + sg.N[2]);
   const int rows_per_block = 8 * RPW;
-  const int grid = (N + rows_per_block - 1) / rows_per_block;
-  skinny_gemm_kernel<MT, RPW><<<grid, 256, 0, st>>>((const bf16*)X, (const bf16*)W, (bf16*)C, (const bf16*)bias,
-                                                   (const bf16*)addend, M, N, K, ldx, ldw, ldc, ld_add);
+  const int grid = (Ntot + rows_per_block - 1) / rows_per_block;
+  skinny_gemm_kernel<MT, RPW, KU><<<grid, 256, 0, st>>>((const bf16*)X, sg, (const bf16*)bias, (const bf16*)addend, M, K,
+                                                       ldx, ldw, ld_add);
   return 0;
+}
+int dispatch_skinny(const void* X, const SkinnySeg& sg, const void* bias, const void* addend, int M, int K, long long ldx,
+                    long long ldw, long long ld_add, cudaStream_t st) {
+  if (M == 1) return launch_skinny<1>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
+  if (M == 2) return launch_skinny<2>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
+  if (M <= 4) return launch_skinny<4>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
+  if (M <= 8) return launch_skinny<8>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
+  return launch_skinny<16>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
 }
 }  // namespace
 
@@ -237,12 +322,38 @@ int mb200_skinny_gemm_bf16(const void* X, const void* W, void* C, const void* bi
   if (M <= 0 || N <= 0) return MB200_OK;
   if (M > 16 || (K & 7) || (ldx & 7) || (ldw & 7)) return -ENOTSUP;
   if ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(W)) & 15) return -ENOTSUP;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (M == 1) launch_skinny<1>(X, W, C, bias, addend, M, N, K, ldx, ldw, ldc, ld_add, st);
-  else if (M == 2) launch_skinny<2>(X, W, C, bias, addend, M, N, K, ldx, ldw, ldc, ld_add, st);
-  else if (M <= 4) launch_skinny<4>(X, W, C, bias, addend, M, N, K, ldx, ldw, ldc, ld_add, st);
-  else if (M <= 8) launch_skinny<8>(X, W, C, bias, addend, M, N, K, ldx, ldw, ldc, ld_add, st);
-  else launch_skinny<16>(X, W, C, bias, addend, M, N, K, ldx, ldw, ldc, ld_add, st);
+  SkinnySeg sg; sg.nseg = 1; sg.mode = 0;
+  sg.W[0] = (const bf16*)W; sg.C[0] = (bf16*)C; sg.N[0] = N; sg.ldc[0] = ldc;
+  sg.W[1] = sg.W[2] = nullptr; sg.C[1] = sg.C[2] = nullptr; sg.N[1] = sg.N[2] = 0; sg.ldc[1] = sg.ldc[2] = 0;
+  dispatch_skinny(X, sg, bias, addend, M, K, ldx, ldw, ld_add, (cudaStream_t)stream);
+  MB200_CHECK_LAUNCH();
+  return MB200_OK;
+}
+
+// Three projections of the same input in one launch: Ci[M,Ni] = X Wi^T (q/k/v).  W rows share ldw.
+int mb200_skinny_gemm3_bf16(const void* X, const void* W0, const void* W1, const void* W2, void* C0, void* C1, void* C2,
+                            int M, int N0, int N1, int N2, int K, long long ldx, long long ldw, void* stream) {
+  if (M <= 0) return MB200_OK;
+  if (M > 16 || (K & 7) || (ldx & 7) || (ldw & 7)) return -ENOTSUP;
+  SkinnySeg sg; sg.nseg = 3; sg.mode = 0;
+  sg.W[0] = (const bf16*)W0; sg.W[1] = (const bf16*)W1; sg.W[2] = (const bf16*)W2;
+  sg.C[0] = (bf16*)C0; sg.C[1] = (bf16*)C1; sg.C[2] = (bf16*)C2;
+  sg.N[0] = N0; sg.N[1] = N1; sg.N[2] = N2; sg.ldc[0] = N0; sg.ldc[1] = N1; sg.ldc[2] = N2;
+  dispatch_skinny(X, sg, nullptr, nullptr, M, K, ldx, ldw, 0, (cudaStream_t)stream);
+  MB200_CHECK_LAUNCH();
+  return MB200_OK;
+}
+
+// C[M,N] = silu(X Wg^T) * (X Wu^T)   (SwiGLU MLP input half, fused)
+int mb200_skinny_swiglu_bf16(const void* X, const void* Wg, const void* Wu, void* C, int M, int N, int K, long long ldx,
+                             long long ldw, long long ldc, void* stream) {
+  if (M <= 0) return MB200_OK;
+  if (M > 16 || (K & 7) || (ldx & 7) || (ldw & 7)) return -ENOTSUP;
+  SkinnySeg sg; sg.nseg = 2; sg.mode = 1;
+  sg.W[0] = (const bf16*)Wg; sg.W[1] = (const bf16*)Wu; sg.W[2] = nullptr;
+  sg.C[0] = (bf16*)C; sg.C[1] = sg.C[2] = nullptr; sg.N[0] = N; sg.N[1] = N; sg.N[2] = 0;
+  sg.ldc[0] = ldc; sg.ldc[1] = sg.ldc[2] = 0;
+  dispatch_skinny(X, sg, nullptr, nullptr, M, K, ldx, ldw, 0, (cudaStream_t)stream);
   MB200_CHECK_LAUNCH();
   return MB200_OK;
 }
@@ -254,6 +365,20 @@ int mb200_kv_append(const void* k_new, const void* v_new, void* k_cache, void* v
   dim3 grid((row_elems / 8 + 255) / 256, B);
   kv_append_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)k_new, (const bf16*)v_new, (bf16*)k_cache,
                                                           (bf16*)v_cache, pos_dev, pos_const, B, row_elems, ld_new, capacity);
+  MB200_CHECK_LAUNCH();
+  return MB200_OK;
+}
+
+int mb200_rope_append_bf16(const void* q, const void* k, const void* v, void* q_out, void* k_cache, void* v_cache,
+                           const int64_t* pos, const float* inv_freq, int B, int H, int Hkv, int hd, int ctx,
+                           long long capacity, float rope_scale, void* stream) {
+  if (B <= 0) return MB200_OK;
+  if ((hd & 7) || ctx >= capacity) return -EINVAL;
+  const int total = (H + Hkv) * (hd / 2) + Hkv * hd / 8;
+  dim3 grid((total + 255) / 256, B);
+  rope_append_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)q_out,
+                                                            (bf16*)k_cache, (bf16*)v_cache, pos, inv_freq, H, Hkv, hd, ctx,
+                                                            capacity, rope_scale);
   MB200_CHECK_LAUNCH();
   return MB200_OK;
 }

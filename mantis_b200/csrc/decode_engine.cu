@@ -91,19 +91,14 @@ int mb200_llama_decode_step(const int* dims, const float* fparm, const void* con
   for (int l = 0; l < L; ++l) {
     const void* const* w = layers + (size_t)l * 11;
     TRY(mb200_rmsnorm_fwd(x, w[7], xn, nullptr, B, D, eps, dt, stream));
-    TRY(mb200_skinny_gemm_bf16(xn, w[0], q, nullptr, nullptr, B, HD, D, D, D, HD, 0, stream));
-    TRY(mb200_skinny_gemm_bf16(xn, w[1], k, nullptr, nullptr, B, KD, D, D, D, KD, 0, stream));
-    TRY(mb200_skinny_gemm_bf16(xn, w[2], v, nullptr, nullptr, B, KD, D, D, D, KD, 0, stream));
-    TRY(mb200_rope(q, qr, pos, inv_freq, B, H, hd, HD, HD, rope_scale, 0, dt, stream));
-    TRY(mb200_rope(k, kr, pos, inv_freq, B, Hkv, hd, KD, KD, rope_scale, 0, dt, stream));
-    TRY(mb200_kv_append(kr, v, const_cast<void*>(w[9]), const_cast<void*>(w[10]), nullptr, ctx, B, KD, KD, cap, stream));
+    TRY(mb200_skinny_gemm3_bf16(xn, w[0], w[1], w[2], q, k, v, B, HD, KD, KD, D, D, D, stream));
+    TRY(mb200_rope_append_bf16(q, k, v, qr, const_cast<void*>(w[9]), const_cast<void*>(w[10]), pos, inv_freq, B, H, Hkv, hd,
+                               ctx, cap, rope_scale, stream));
     TRY(mb200_decode_attn_bf16(qr, w[9], w[10], ao, part, B, H, Hkv, ctx + 1, hd, HD, hd, cap * KD, KD, hd, HD, hd, scale,
                                kbits, kbs, stream));
     TRY(mb200_skinny_gemm_bf16(ao, w[3], x, nullptr, x, B, D, HD, HD, HD, D, D, stream));          // x += o_proj(attn)
     TRY(mb200_rmsnorm_fwd(x, w[8], xn, nullptr, B, D, eps, dt, stream));
-    TRY(mb200_skinny_gemm_bf16(xn, w[4], g, nullptr, nullptr, B, I, D, D, D, I, 0, stream));
-    TRY(mb200_skinny_gemm_bf16(xn, w[5], u, nullptr, nullptr, B, I, D, D, D, I, 0, stream));
-    TRY(mb200_swiglu_fwd(g, u, act, (long long)B * I, dt, stream));
+    TRY(mb200_skinny_swiglu_bf16(xn, w[4], w[5], act, B, I, D, D, D, I, stream));                   // silu(gate) * up
     TRY(mb200_skinny_gemm_bf16(act, w[6], x, nullptr, x, B, D, I, I, I, D, D, stream));            // x += down(act)
   }
   TRY(mb200_rmsnorm_fwd(x, fnorm, xn, nullptr, B, D, eps, dt, stream));
