@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-gemm", action="store_true", help="only run the per-kernel roofline section")
+    ap.add_argument("--workload", default="mllava", choices=["mllava", "idefics2"],
+                    help="mllava = BASELINE configs[1] (the headline); idefics2 = configs[2] (perceiver-resampler path)")
     return ap.parse_args()
 
 
@@ -52,6 +54,32 @@ def make_sample(i, torch):
     gp = torch.Generator().manual_seed(4321 + i)
     pv = torch.randn(N_IMG, 3, IMG_RES, IMG_RES, generator=gp).to(torch.bfloat16)
     return dict(input_ids=ids, attention_mask=torch.ones_like(ids), labels=labels, pixel_values=pv)
+
+
+def make_sample_idefics2(i, torch):
+    """configs[2]: 2048 tokens containing 8 runs of <fake><image>x64<fake>; pixel_values [1, 8, 3, 384, 384]"""
+    g = torch.Generator().manual_seed(1234 + i)
+    ids = torch.randint(3, 32000, (1, T_TEXT), generator=g)
+    for j in range(N_IMG):
+        s0 = j * 256 + 16
+        ids[0, s0] = 32000; ids[0, s0 + 1:s0 + 65] = 32001; ids[0, s0 + 65] = 32000
+    labels = ids.clone(); labels[ids == 32001] = 32001
+    gp = torch.Generator().manual_seed(4321 + i)
+    pv = torch.randn(1, N_IMG, 3, IMG_RES, IMG_RES, generator=gp).to(torch.bfloat16)
+    return dict(input_ids=ids, attention_mask=torch.ones_like(ids), labels=labels, pixel_values=pv)
+
+
+def idefics2_8b_config(text_layers=32, vision_layers=27):
+    from transformers import Idefics2Config
+    return Idefics2Config(
+        vision_config=dict(hidden_size=1152, intermediate_size=4304, num_hidden_layers=vision_layers, num_attention_heads=16,
+                           image_size=980, patch_size=14, hidden_act="gelu_pytorch_tanh", layer_norm_eps=1e-6),
+        perceiver_config=dict(resampler_n_latents=64, resampler_depth=3, resampler_n_heads=16, resampler_head_dim=96,
+                              num_key_value_heads=4, hidden_act="silu", hidden_size=4096, rms_norm_eps=1e-5),
+        text_config=dict(model_type="mistral", hidden_size=4096, intermediate_size=14336, num_hidden_layers=text_layers,
+                         num_attention_heads=32, num_key_value_heads=8, vocab_size=32003, rms_norm_eps=1e-5,
+                         rope_theta=10000.0, sliding_window=4096, max_position_embeddings=32768, pad_token_id=0),
+        image_token_id=32001, tie_word_embeddings=False)
 
 
 class ClockSampler:
@@ -244,22 +272,28 @@ def run_ours(args):
         print(json.dumps(gemm_roofline(torch, ops, peaks)))
         return
 
-    cfg = mantis_8b_siglip_llama3_config(num_vision_layers=args.vision_layers, num_text_layers=args.text_layers)
     torch.manual_seed(0)
     old = torch.get_default_dtype()
     torch.set_default_dtype(torch.bfloat16)
-    with torch.device(dev):
-        model = LlavaForConditionalGeneration(cfg)
+    if args.workload == "idefics2":
+        from mantis_b200.models.idefics2 import Idefics2ForConditionalGeneration
+        with torch.device(dev):
+            model = Idefics2ForConditionalGeneration(idefics2_8b_config(args.text_layers, args.vision_layers))
+    else:
+        cfg = mantis_8b_siglip_llama3_config(num_vision_layers=args.vision_layers, num_text_layers=args.text_layers)
+        with torch.device(dev):
+            model = LlavaForConditionalGeneration(cfg)
     torch.set_default_dtype(old)
     model.train()
     trainer = B200Trainer(model, lr=1e-5, weight_decay=0.0, max_grad_norm=1.0, grad_accum=args.samples)
     n_train = sum(p.numel() for p in trainer.params)
 
-    host = [make_sample(rank * args.samples + i, torch) for i in range(args.samples)]
+    mk = make_sample_idefics2 if args.workload == "idefics2" else make_sample
+    host = [mk(rank * args.samples + i, torch) for i in range(args.samples)]
     host = [{k: v.pin_memory() for k, v in s.items()} for s in host]
     resident = [{k: v.to(dev, non_blocking=True) for k, v in s.items()} for s in host]
     torch.cuda.synchronize()
-    S_merged = T_TEXT + N_IMG * 727
+    S_merged = T_TEXT if args.workload == "idefics2" else T_TEXT + N_IMG * 727
     tokens_per_step_rank = args.samples * S_merged
     h2d = sum(v.numel() * v.element_size() for s in host for v in s.values())
 
@@ -307,14 +341,18 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     value = world * tokens_per_step_rank * args.steps / (ms * 1e-3)
-    step_tflops = world * FLOP_PER_STEP * (args.samples / SAMPLES_PER_STEP) * args.steps / (ms * 1e-3) / 1e12
+    flop_per_step = 449e12 if args.workload == "idefics2" else FLOP_PER_STEP
+    step_tflops = world * flop_per_step * (args.samples / SAMPLES_PER_STEP) * args.steps / (ms * 1e-3) / 1e12
     roof = gemm_roofline(torch, ops, peaks) if world == 1 else None
     full = (args.text_layers == 32 and args.vision_layers == 27 and args.samples == SAMPLES_PER_STEP)
     line = {
-        "metric": "training tokens/sec Mantis-8B-SigLIP 8-img/2048-tok", "value": value, "unit": "tokens/s",
+        "metric": ("training tokens/sec Mantis-8B-SigLIP 8-img/2048-tok" if args.workload == "mllava"
+                   else "training tokens/sec Mantis-8B-Idefics2 8-img/2048-tok"), "value": value, "unit": "tokens/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "Mantis-8B-SigLIP-LLaMA-3 instruction-tuning step, random init (configs[1])",
+        "config": {"workload": ("Mantis-8B-SigLIP-LLaMA-3 instruction-tuning step, random init (configs[1])"
+                                if args.workload == "mllava" else
+                                "Mantis-8B-Idefics2 instruction-tuning step, random init (configs[2])"),
                    "samples_per_rank_per_step": args.samples, "images_per_sample": N_IMG, "text_tokens": T_TEXT,
                    "merged_seq_len": S_merged, "micro_batch": 1, "grad_accum": args.samples,
                    "parallelism": f"dp{world}", "optimizer": "fused AdamW (fp32 moments) + grad-norm clip",

@@ -37,7 +37,7 @@ class B200Trainer:
         self.model = model
         if freeze_vision:                                   # mantis/train/train_mllava.py:239-242
             for n, p in model.named_parameters():
-                if "vision_tower" in n:
+                if "vision_tower" in n or "vision_model" in n:
                     p.requires_grad_(False)
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.flat_grad = flat_grad_buffer(self.params)
