@@ -12,6 +12,7 @@
 // The same [rows x 64] swizzled tile serves as a K-major operand (rows = M/N) and as an MN-major operand
 // (rows = K) -- only the descriptor differs -- so Q, dO, K, V are each loaded once per use.
 // Backward of LlamaAttention's SDPA/flash call (transformers llama/modeling_llama.py:199-289).
+#include <stdlib.h>
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -46,6 +47,9 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   bf162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
 }
 // write 32 bf16 (16 packed words) = chunks [4*half, 4*half+4) of the 128-byte swizzled row r
 __device__ __forceinline__ void store_row32(uint8_t* tile, int r, int half, const uint32_t* pk) {
@@ -83,6 +87,9 @@ __device__ __forceinline__ void store_acc_row(uint32_t taddr, bf16* dst, bool ok
 }
 
 // ============================================================================================ dK / dV
+// TS = true: P^T / dS^T (bf16) are written back into the TMEM columns of the S^T / dP^T tiles and feed the dV / dK MMAs as
+// TMEM A operands (no shared-memory round trip: shared-memory bandwidth is what limits these kernels).
+template <bool TS>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant__ CUtensorMap tmDO64,
                           const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -167,7 +174,7 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __gri
       auto issue_sdp = [&](int n) {
         const int s = n & 1; const uint32_t ph = (n >> 1) & 1;
         mbar_wait(&qdo_full[s], ph);
-        mbar_wait(&sdp_empty[s], ph ^ 1);
+        if (!TS) mbar_wait(&sdp_empty[s], ph ^ 1);   // TS: stage s is recycled by dV/dK of sub-tile n-2, issued earlier (in-order pipe)
         tc_fence_after();
         const uint32_t q_addr = smem_u32(sQ + s * SUB_TILE), do_addr = smem_u32(sDO + s * SUB_TILE);
 #pragma unroll
@@ -191,13 +198,17 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __gri
         tc_fence_after();
         const uint32_t q_addr = smem_u32(sQ + s * SUB_TILE), do_addr = smem_u32(sDO + s * SUB_TILE);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)     // dV += P^T (K = 64 queries) x dO (MN-major: rows = queries)
-          umma_bf16_ss(tDV, make_smem_desc(pt_addr + kk * 32, 16, 1024),
-                       make_smem_desc(do_addr + kk * 2048, SUB_HALF, 1024), idesc_acc, (n | kk) != 0);
+        for (int kk = 0; kk < 4; ++kk) {   // dV += P^T (K = 64 queries) x dO (MN-major: rows = queries)
+          const uint64_t bd = make_smem_desc(do_addr + kk * 2048, SUB_HALF, 1024);
+          if (TS) umma_bf16_ts(tDV, tST[s] + kk * 8, bd, idesc_acc, (n | kk) != 0);
+          else    umma_bf16_ss(tDV, make_smem_desc(pt_addr + kk * 32, 16, 1024), bd, idesc_acc, (n | kk) != 0);
+        }
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)     // dK += dS^T x Q
-          umma_bf16_ss(tDK, make_smem_desc(dst_addr + kk * 32, 16, 1024),
-                       make_smem_desc(q_addr + kk * 2048, SUB_HALF, 1024), idesc_acc, (n | kk) != 0);
+        for (int kk = 0; kk < 4; ++kk) {   // dK += dS^T x Q
+          const uint64_t bd = make_smem_desc(q_addr + kk * 2048, SUB_HALF, 1024);
+          if (TS) umma_bf16_ts(tDK, tDPT[s] + kk * 8, bd, idesc_acc, (n | kk) != 0);
+          else    umma_bf16_ss(tDK, make_smem_desc(dst_addr + kk * 32, 16, 1024), bd, idesc_acc, (n | kk) != 0);
+        }
         umma_commit(&qdo_empty[s]);
         umma_commit(pds_empty);
       }
@@ -250,10 +261,17 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __gri
         }
       }
       mbar_arrive(&ld_empty[s]);
-      if (n > 0) mbar_wait(pds_empty, (n - 1) & 1);
-      store_row32(sPT, r, half, pk);
-      store_row32(sDST, r, half, dk_);
-      fence_proxy_async();
+      if (TS) {
+        named_bar_sync(1, SM_THREADS);            // both column halves have read S^T / dP^T before anyone overwrites them
+        tmem_st_32x32b_x16(tST[s] + lane_off + half * 16, pk);
+        tmem_st_32x32b_x16(tDPT[s] + lane_off + half * 16, dk_);
+        tmem_st_wait();
+      } else {
+        if (n > 0) mbar_wait(pds_empty, (n - 1) & 1);
+        store_row32(sPT, r, half, pk);
+        store_row32(sDST, r, half, dk_);
+        fence_proxy_async();
+      }
       tc_fence_before();
       mbar_arrive(pds_full);
     }
@@ -279,6 +297,7 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __gri
 }
 
 // ============================================================================================ dQ
+template <bool TS>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                          const __grid_constant__ CUtensorMap tmK64, const __grid_constant__ CUtensorMap tmV64,
@@ -354,7 +373,7 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       auto issue_sdp = [&](int n) {
         const int s = n & 1; const uint32_t ph = (n >> 1) & 1;
         mbar_wait(&kv_full[s], ph);
-        mbar_wait(&sdp_empty[s], ph ^ 1);
+        if (!TS) mbar_wait(&sdp_empty[s], ph ^ 1);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sK + s * SUB_TILE), v_addr = smem_u32(sV + s * SUB_TILE);
 #pragma unroll
@@ -378,9 +397,11 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sK + s * SUB_TILE);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)     // dQ += dS (K = 64 keys) x K (MN-major: rows = keys)
-          umma_bf16_ss(tDQ, make_smem_desc(ds_addr + kk * 32, 16, 1024),
-                       make_smem_desc(k_addr + kk * 2048, SUB_HALF, 1024), idesc_acc, (n | kk) != 0);
+        for (int kk = 0; kk < 4; ++kk) {   // dQ += dS (K = 64 keys) x K (MN-major: rows = keys)
+          const uint64_t bd = make_smem_desc(k_addr + kk * 2048, SUB_HALF, 1024);
+          if (TS) umma_bf16_ts(tDQ, tS[s] + kk * 8, bd, idesc_acc, (n | kk) != 0);
+          else    umma_bf16_ss(tDQ, make_smem_desc(ds_addr + kk * 32, 16, 1024), bd, idesc_acc, (n | kk) != 0);
+        }
         umma_commit(&kv_empty[s]);
         umma_commit(ds_empty);
       }
@@ -427,9 +448,15 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           dsk[i] = pack_bf16(p0 * (dp[2 * i] - dl), p1 * (dp[2 * i + 1] - dl));
         }
       }
-      if (n > 0) mbar_wait(ds_empty, (n - 1) & 1);
-      store_row32(sDS, r, half, dsk);
-      fence_proxy_async();
+      if (TS) {
+        named_bar_sync(1, SM_THREADS);
+        tmem_st_32x32b_x16(tS[s] + lane_off + half * 16, dsk);
+        tmem_st_wait();
+      } else {
+        if (n > 0) mbar_wait(ds_empty, (n - 1) & 1);
+        store_row32(sDS, r, half, dsk);
+        fence_proxy_async();
+      }
       tc_fence_before();
       mbar_arrive(ds_full);
     }
@@ -565,16 +592,26 @@ int mb200_attn_bwd_bf16(const void* q, const void* k, const void* v, const void*
   constexpr int smem_dkv = 2 * FULL_TILE + 4 * SUB_TILE + 2 * FULL_HALF + 1024 + 256 + 1024;
   constexpr int smem_dq = 2 * FULL_TILE + 4 * SUB_TILE + FULL_HALF + 1024 + 256;
   static bool configured = false;
+  static int ts = 1;
   if (!configured) {
-    if (cudaFuncSetAttribute(attn_bwd_dkv_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dkv) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_bwd_dq_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq) != cudaSuccess) {
+    const char* e = getenv("MB200_ATTN_P_TMEM");
+    if (e) ts = atoi(e);
+    if (cudaFuncSetAttribute(attn_bwd_dkv_sm100_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dkv) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd_dkv_sm100_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dkv) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd_dq_sm100_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd_dq_sm100_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq) != cudaSuccess) {
       mb200_set_last_error("cudaFuncSetAttribute(attn bwd smem) failed"); return -EIO;
     }
     configured = true;
   }
   dim3 gkv((Sk + 127) / 128, Hkv, B), gq((Sq + 127) / 128, H, B);
-  attn_bwd_dkv_sm100_kernel<<<gkv, NTHREADS, smem_dkv, st>>>(tmQ64, tmDO64, tmK, tmV, p);
-  attn_bwd_dq_sm100_kernel<<<gq, NTHREADS, smem_dq, st>>>(tmQ, tmDO, tmK64, tmV64, p);
+  if (ts) {
+    attn_bwd_dkv_sm100_kernel<true><<<gkv, NTHREADS, smem_dkv, st>>>(tmQ64, tmDO64, tmK, tmV, p);
+    attn_bwd_dq_sm100_kernel<true><<<gq, NTHREADS, smem_dq, st>>>(tmQ, tmDO, tmK64, tmV64, p);
+  } else {
+    attn_bwd_dkv_sm100_kernel<false><<<gkv, NTHREADS, smem_dkv, st>>>(tmQ64, tmDO64, tmK, tmV, p);
+    attn_bwd_dq_sm100_kernel<false><<<gq, NTHREADS, smem_dq, st>>>(tmQ, tmDO, tmK64, tmV64, p);
+  }
   MB200_CHECK_LAUNCH();
   return MB200_OK;
 }

@@ -13,6 +13,7 @@
 //   warps 2-5  softmax: tcgen05.ld S row -> mask -> online max/sum -> P (bf16) -> swizzled smem (A operand of
 //              the P V MMA) ; rescale O in TMEM only when a row maximum moved ; epilogue O / l -> global
 // TMEM columns: [0,128) S0, [128,256) S1, [256,384) O.
+#include <stdlib.h>
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -51,6 +52,11 @@ constexpr int SMW = 8;                    // softmax warps: two per TMEM lane qu
 constexpr int SMT = SMW * 32;
 constexpr int FWD_THREADS = 64 + SMT;
 
+// P_TMEM = true : P (bf16) is written back into the TMEM columns of the S tile it came from and the P V MMA reads its A
+//                  operand from tensor memory (tcgen05.mma "ts" form): no P store to / P read from shared memory, which
+//                  is the scarce resource here (Q, K, P, V operand reads + TMA writes exceed 128 B/clk otherwise).
+// P_TMEM = false: P goes through 128B-swizzled shared memory (first version, kept as the cross-check).
+template <bool P_TMEM>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
@@ -126,7 +132,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       auto issue_s = [&](int j) {
         const int s = j & 1; const uint32_t ph = (j >> 1) & 1;
         mbar_wait(&k_full[s], ph);
-        mbar_wait(&s_empty[s], ph ^ 1);
+        if (!P_TMEM) mbar_wait(&s_empty[s], ph ^ 1);     // P_TMEM: buffer s is recycled by P_j V_j, which was issued before
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sK + s * TILE_BYTES);
 #pragma unroll
@@ -149,9 +155,13 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const uint32_t v_addr = smem_u32(sV + s * TILE_BYTES);
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk) {
-          const uint64_t ad = make_smem_desc(p_addr + (kk >> 2) * HALF_BYTES + (kk & 3) * 32, 16, 1024);
           const uint64_t bd = make_smem_desc(v_addr + kk * 2048, HALF_BYTES, 1024);
-          umma_bf16_ss(tO, ad, bd, idesc_pv, (j | kk) != 0 ? 1u : 0u);
+          if (P_TMEM) {
+            umma_bf16_ts(tO, tS[s] + kk * 8, bd, idesc_pv, (j | kk) != 0 ? 1u : 0u);   // 16 bf16 of K = 8 TMEM columns
+          } else {
+            const uint64_t ad = make_smem_desc(p_addr + (kk >> 2) * HALF_BYTES + (kk & 3) * 32, 16, 1024);
+            umma_bf16_ss(tO, ad, bd, idesc_pv, (j | kk) != 0 ? 1u : 0u);
+          }
         }
         umma_commit(&v_empty[s]);
         umma_commit(pv_done);
@@ -238,14 +248,19 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         }
         tmem_st_wait();
       }
-      // write this thread's 64 P columns = one 128-byte row of half-tile `half` (K-major, 128B swizzle: chunk ^ (r & 7))
-      {
+      if (P_TMEM) {
+        // P (bf16 pairs) overwrites columns [32*half, 32*half + 32) of the S tile: lane = row, 2 elements per column
+        tmem_st_32x32b_x16(tS[s] + lane_off + half * 32, pk);
+        tmem_st_32x32b_x16(tS[s] + lane_off + half * 32 + 16, pk + 16);
+        tmem_st_wait();
+      } else {
+        // one 128-byte row of half-tile `half` (K-major, 128B swizzle: chunk ^ (r & 7))
         uint8_t* rowp = sP + half * HALF_BYTES + r * 128;
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch)
           *reinterpret_cast<uint4*>(rowp + ((ch ^ (r & 7)) << 4)) = make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+        fence_proxy_async();
       }
-      fence_proxy_async();
       tc_fence_before();
       mbar_arrive(p_full);
       named_bar_sync(2, SMT);      // sx[] is reused by the next tile
@@ -374,14 +389,19 @@ int mb200_attn_fwd_bf16(const void* q, const void* k, const void* v, void* o, fl
   }
   constexpr int smem = 7 * TILE_BYTES + 1024 + 256 + 1024;
   static bool configured = false;
+  static int p_tmem = 1;
   if (!configured) {
-    if (cudaFuncSetAttribute(attn_fwd_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    const char* e = getenv("MB200_ATTN_P_TMEM");
+    if (e) p_tmem = atoi(e);
+    if (cudaFuncSetAttribute(attn_fwd_sm100_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_fwd_sm100_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       mb200_set_last_error("cudaFuncSetAttribute(attn smem) failed"); return -EIO;
     }
     configured = true;
   }
   dim3 grid((Sq + BQ - 1) / BQ, H, B);
-  attn_fwd_sm100_kernel<<<grid, FWD_THREADS, smem, st>>>(tmQ, tmK, tmV, p);
+  if (p_tmem) attn_fwd_sm100_kernel<true><<<grid, FWD_THREADS, smem, st>>>(tmQ, tmK, tmV, p);
+  else        attn_fwd_sm100_kernel<false><<<grid, FWD_THREADS, smem, st>>>(tmQ, tmK, tmV, p);
   MB200_CHECK_LAUNCH();
   return MB200_OK;
 }
