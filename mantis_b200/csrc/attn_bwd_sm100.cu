@@ -2,10 +2,12 @@
 // (TMA -> 128B-swizzled smem, tcgen05.mma with TMEM accumulators, one softmax thread per TMEM lane):
 //
 //   dKV kernel : CTA owns a 128-key tile of one (batch, kv head); loops over the query heads of the GQA group and
-//                over 64-query sub-tiles.  S^T = K Q^T and dP^T = V dO^T (128x64, double buffered in TMEM),
-//                P^T / dS^T -> swizzled smem, dV += P^T dO, dK += dS^T Q accumulate in TMEM over the whole loop.
+//                over 64-query sub-tiles.  S^T = K Q^T and dP^T = V dO^T (128x64, two TMEM stages), P^T / dS^T are
+//                written back into those TMEM columns (bf16) and consumed as TMEM A operands: dV += P^T dO,
+//                dK += dS^T Q accumulate in TMEM over the whole loop.
 //   dQ kernel  : CTA owns a 128-query tile of one (batch, head); loops over 64-key sub-tiles.
-//                S = Q K^T, dP = dO V^T (double buffered), dS -> smem, dQ += dS K accumulates in TMEM.
+//                S = Q K^T, dP = dO V^T (two TMEM stages), dS -> TMEM (bf16), dQ += dS K accumulates in TMEM.
+//   Two softmax warp groups ping-pong over the sub-tiles (one TMEM stage each).
 //
 // No atomics, deterministic.  S/dP are recomputed in both kernels (7 GEMMs instead of the fused 5) -- the price of
 // keeping every accumulator resident in the 512 TMEM columns without a global dQ reduction.
@@ -26,6 +28,7 @@ constexpr int SUB_HALF = 64 * 128;       // [64 rows x 64 bf16] (8 KB)
 constexpr int SUB_TILE = 2 * SUB_HALF;   // [64 rows x 128 hd] (16 KB)
 constexpr float LOG2E = 1.44269504088896340736f;
 
+constexpr int QS = 3;                    // shared-memory stages of the streamed operand tiles (TMEM stages stay 2)
 constexpr int SM_WARPS = 8;              // softmax warps (two per TMEM lane quarter, each takes half of the columns)
 constexpr int SM_THREADS = SM_WARPS * 32;
 constexpr int NTHREADS = 64 + SM_THREADS;
@@ -47,18 +50,6 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   bf162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&h);
-}
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
-}
-// write 32 bf16 (16 packed words) = chunks [4*half, 4*half+4) of the 128-byte swizzled row r
-__device__ __forceinline__ void store_row32(uint8_t* tile, int r, int half, const uint32_t* pk) {
-  uint8_t* rowp = tile + r * 128;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const int ch = half * 4 + c;
-    *reinterpret_cast<uint4*>(rowp + ((ch ^ (r & 7)) << 4)) = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
-  }
 }
 // 1-D bulk copy global -> shared, completion credited to an mbarrier (bytes % 16 == 0, 16-byte aligned)
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -87,9 +78,10 @@ __device__ __forceinline__ void store_acc_row(uint32_t taddr, bf16* dst, bool ok
 }
 
 // ============================================================================================ dK / dV
-// TS = true: P^T / dS^T (bf16) are written back into the TMEM columns of the S^T / dP^T tiles and feed the dV / dK MMAs as
-// TMEM A operands (no shared-memory round trip: shared-memory bandwidth is what limits these kernels).
-template <bool TS>
+// Softmax warps form two groups (warps 2-5 and 6-9) that ping-pong over the 64-query sub-tiles: group g owns TMEM stage g
+// (S^T_g, dP^T_g), so while one group waits on barriers / TMEM latency the other computes, and the MMA thread always has
+// the other stage's products to issue.  P^T / dS^T (bf16) are written back into the first 32 columns of S^T_g / dP^T_g and
+// feed the dV / dK MMAs as TMEM A operands: nothing but Q / dO / K / V tiles ever touches shared memory.
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant__ CUtensorMap tmDO64,
                           const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -98,22 +90,17 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __gri
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;                           // 32 KB resident
   uint8_t* sV = sK + FULL_TILE;                 // 32 KB resident
-  uint8_t* sQ = sV + FULL_TILE;                 // 2 stages x 16 KB
-  uint8_t* sDO = sQ + 2 * SUB_TILE;             // 2 stages x 16 KB
-  uint8_t* sPT = sDO + 2 * SUB_TILE;            // 16 KB  [128 keys x 64 q]
-  uint8_t* sDST = sPT + FULL_HALF;              // 16 KB
-  float2* sLD = reinterpret_cast<float2*>(sDST + FULL_HALF);   // [2][64] {lse2, delta}
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sLD + 128);
+  uint8_t* sQ = sV + FULL_TILE;                 // QS stages x 16 KB
+  uint8_t* sDO = sQ + QS * SUB_TILE;            // QS stages x 16 KB
+  float2* sLD = reinterpret_cast<float2*>(sDO + QS * SUB_TILE);   // [QS][64] {lse2, delta}
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sLD + QS * 64);
   uint64_t* kv_full = bars + 0;
-  uint64_t* qdo_full = bars + 1;    // [2]
-  uint64_t* qdo_empty = bars + 3;   // [2]
-  uint64_t* sdp_full = bars + 5;    // [2]
-  uint64_t* sdp_empty = bars + 7;   // [2]
-  uint64_t* pds_full = bars + 9;
-  uint64_t* pds_empty = bars + 10;
+  uint64_t* qdo_full = bars + 1;    // [QS]
+  uint64_t* qdo_empty = bars + 4;   // [QS]
+  uint64_t* sdp_full = bars + 7;    // [2]
+  uint64_t* pds_full = bars + 9;    // [2]
   uint64_t* acc_done = bars + 11;
-  uint64_t* ld_empty = bars + 12;   // [2]  softmax finished reading sLD[s]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
@@ -129,11 +116,9 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __gri
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmQ64); prefetch_tmap(&tmDO64); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
     mbar_init(kv_full, 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1); mbar_init(&sdp_full[s], 1);
-      mbar_init(&sdp_empty[s], SM_THREADS); mbar_init(&ld_empty[s], SM_THREADS);
-    }
-    mbar_init(pds_full, SM_THREADS); mbar_init(pds_empty, 1); mbar_init(acc_done, 1);
+    for (int s = 0; s < QS; ++s) { mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&sdp_full[s], 1); mbar_init(&pds_full[s], 128); }
+    mbar_init(acc_done, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -153,10 +138,9 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __gri
       tma_load_4d(sV, &tmV, kv_full, 0, hk, k0, b);
       tma_load_4d(sV + FULL_HALF, &tmV, kv_full, 64, hk, k0, b);
       for (int n = 0; n < n_it; ++n) {
-        const int s = n & 1; const uint32_t ph = (n >> 1) & 1;
+        const int s = n % QS; const uint32_t ph = (n / QS) & 1;
         const int h = hk * G + n / per_head, qs = qs_begin + n % per_head;
-        mbar_wait(&qdo_empty[s], ph ^ 1);
-        mbar_wait(&ld_empty[s], ph ^ 1);
+        mbar_wait(&qdo_empty[s], ph ^ 1);      // dV/dK of sub-tile n-QS done => Q/dO stage and sLD[s] are free
         mbar_arrive_expect_tx(&qdo_full[s], 2 * SUB_TILE + 64 * 8);
         tma_load_4d(sQ + s * SUB_TILE, &tmQ64, &qdo_full[s], 0, h, qs * 64, b);
         tma_load_4d(sQ + s * SUB_TILE + SUB_HALF, &tmQ64, &qdo_full[s], 64, h, qs * 64, b);
@@ -170,13 +154,11 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __gri
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, false, false);
       constexpr uint32_t idesc_acc = make_idesc_bf16(128, 128, false, true);
       const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
-      const uint32_t pt_addr = smem_u32(sPT), dst_addr = smem_u32(sDST);
-      auto issue_sdp = [&](int n) {
-        const int s = n & 1; const uint32_t ph = (n >> 1) & 1;
-        mbar_wait(&qdo_full[s], ph);
-        if (!TS) mbar_wait(&sdp_empty[s], ph ^ 1);   // TS: stage s is recycled by dV/dK of sub-tile n-2, issued earlier (in-order pipe)
+      auto issue_sdp = [&](int n) {             // TMEM stage n&1 was last read by dV/dK(n-2), issued earlier (in-order tensor pipe)
+        const int s = n & 1, ss = n % QS;
+        mbar_wait(&qdo_full[ss], (n / QS) & 1);
         tc_fence_after();
-        const uint32_t q_addr = smem_u32(sQ + s * SUB_TILE), do_addr = smem_u32(sDO + s * SUB_TILE);
+        const uint32_t q_addr = smem_u32(sQ + ss * SUB_TILE), do_addr = smem_u32(sDO + ss * SUB_TILE);
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk) {
           const uint32_t oa = (kk >> 2) * FULL_HALF + (kk & 3) * 32, ob = (kk >> 2) * SUB_HALF + (kk & 3) * 32;
@@ -191,102 +173,91 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __gri
       };
       mbar_wait(kv_full, 0);
       issue_sdp(0);
+      if (n_it > 1) issue_sdp(1);
       for (int n = 0; n < n_it; ++n) {
-        if (n + 1 < n_it) issue_sdp(n + 1);
-        const int s = n & 1;
-        mbar_wait(pds_full, n & 1);
+        const int s = n & 1, ss = n % QS; const uint32_t ph = (n >> 1) & 1;
+        mbar_wait(&pds_full[s], ph);
         tc_fence_after();
-        const uint32_t q_addr = smem_u32(sQ + s * SUB_TILE), do_addr = smem_u32(sDO + s * SUB_TILE);
+        const uint32_t q_addr = smem_u32(sQ + ss * SUB_TILE), do_addr = smem_u32(sDO + ss * SUB_TILE);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {   // dV += P^T (K = 64 queries) x dO (MN-major: rows = queries)
-          const uint64_t bd = make_smem_desc(do_addr + kk * 2048, SUB_HALF, 1024);
-          if (TS) umma_bf16_ts(tDV, tST[s] + kk * 8, bd, idesc_acc, (n | kk) != 0);
-          else    umma_bf16_ss(tDV, make_smem_desc(pt_addr + kk * 32, 16, 1024), bd, idesc_acc, (n | kk) != 0);
-        }
+        for (int kk = 0; kk < 4; ++kk)     // dV += P^T (TMEM A, K = 64 queries) x dO (MN-major: rows = queries)
+          umma_bf16_ts(tDV, tST[s] + kk * 8, make_smem_desc(do_addr + kk * 2048, SUB_HALF, 1024), idesc_acc, (n | kk) != 0);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {   // dK += dS^T x Q
-          const uint64_t bd = make_smem_desc(q_addr + kk * 2048, SUB_HALF, 1024);
-          if (TS) umma_bf16_ts(tDK, tDPT[s] + kk * 8, bd, idesc_acc, (n | kk) != 0);
-          else    umma_bf16_ss(tDK, make_smem_desc(dst_addr + kk * 32, 16, 1024), bd, idesc_acc, (n | kk) != 0);
-        }
-        umma_commit(&qdo_empty[s]);
-        umma_commit(pds_empty);
+        for (int kk = 0; kk < 4; ++kk)     // dK += dS^T (TMEM A) x Q
+          umma_bf16_ts(tDK, tDPT[s] + kk * 8, make_smem_desc(q_addr + kk * 2048, SUB_HALF, 1024), idesc_acc, (n | kk) != 0);
+        umma_commit(&qdo_empty[ss]);
+        if (n + 2 < n_it) issue_sdp(n + 2);
       }
       umma_commit(acc_done);
     }
   } else {
     const int qd = warp & 3;                     // TMEM lane quarter
-    const int half = (warp - 2) >> 2;            // which 32 of the 64 query columns
+    const int grp = (warp - 2) >> 2;             // ping-pong group == TMEM stage it owns
     const int r = qd * 32 + lane;                // key row in tile == TMEM lane
     const int kj = k0 + r;
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
     bool key_ok = kj < p.Sk;
     if (key_ok && p.kbits) key_ok = (__ldg(p.kbits + (size_t)b * p.kbits_stride + (kj >> 5)) >> (kj & 31)) & 1u;
     const int qlim = kj - off;                   // causal: query qi sees key kj iff qi >= kj - off
-    for (int n = 0; n < n_it; ++n) {
-      const int s = n & 1; const uint32_t ph = (n >> 1) & 1;
+    const int s = grp;
+    for (int n = grp; n < n_it; n += 2) {
+      const uint32_t ph = (n >> 1) & 1;
       const int qs = qs_begin + n % per_head;
-      const int q0 = qs * 64 + half * 32;
-      mbar_wait(&qdo_full[s], ph);               // lse/delta of this sub-tile landed (bulk copy on the same barrier)
+      const int ss = n % QS;
+      mbar_wait(&qdo_full[ss], (n / QS) & 1);    // lse/delta landed (bulk copy on the same barrier as Q/dO)
       mbar_wait(&sdp_full[s], ph);
       tc_fence_after();
-      float sv[32], dp[32];
-      tmem_ld_32x32b_x32(tST[s] + lane_off + half * 32, reinterpret_cast<uint32_t*>(sv));
-      tmem_ld_32x32b_x32(tDPT[s] + lane_off + half * 32, reinterpret_cast<uint32_t*>(dp));
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&sdp_empty[s]);
-      const float2* ldp = sLD + s * 64 + half * 32;
-      uint32_t pk[16], dk_[16];
-      const bool full_vis = key_ok && (!p.causal || q0 >= qlim);
-      if (full_vis) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float2 l0 = ldp[2 * i], l1 = ldp[2 * i + 1];
-          const float p0 = fast_exp2(fmaf(sv[2 * i], p.scale_log2, -l0.x));
-          const float p1 = fast_exp2(fmaf(sv[2 * i + 1], p.scale_log2, -l1.x));
-          pk[i] = pack_bf16(p0, p1);
-          dk_[i] = pack_bf16(p0 * (dp[2 * i] - l0.y), p1 * (dp[2 * i + 1] - l1.y));
-        }
-      } else {
+      for (int c = 0; c < 2; ++c) {              // two chunks of 32 query columns
+        const int q0 = qs * 64 + c * 32;
+        float sv[32], dp[32];
+        tmem_ld_32x32b_x32(tST[s] + lane_off + c * 32, reinterpret_cast<uint32_t*>(sv));
+        tmem_ld_32x32b_x32(tDPT[s] + lane_off + c * 32, reinterpret_cast<uint32_t*>(dp));
+        tmem_ld_wait();
+        const float2* ldp = sLD + ss * 64 + c * 32;
+        uint32_t pk[16], dk_[16];
+        const bool full_vis = key_ok && (!p.causal || q0 >= qlim);
+        if (full_vis) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float2 l0 = ldp[2 * i], l1 = ldp[2 * i + 1];
-          const bool v0 = key_ok && (!p.causal || q0 + 2 * i >= qlim);
-          const bool v1 = key_ok && (!p.causal || q0 + 2 * i + 1 >= qlim);
-          const float p0 = v0 ? fast_exp2(fmaf(sv[2 * i], p.scale_log2, -l0.x)) : 0.f;
-          const float p1 = v1 ? fast_exp2(fmaf(sv[2 * i + 1], p.scale_log2, -l1.x)) : 0.f;
-          pk[i] = pack_bf16(p0, p1);
-          dk_[i] = pack_bf16(p0 * (dp[2 * i] - l0.y), p1 * (dp[2 * i + 1] - l1.y));
+          for (int i = 0; i < 16; ++i) {
+            const float2 l0 = ldp[2 * i], l1 = ldp[2 * i + 1];
+            const float p0 = fast_exp2(fmaf(sv[2 * i], p.scale_log2, -l0.x));
+            const float p1 = fast_exp2(fmaf(sv[2 * i + 1], p.scale_log2, -l1.x));
+            pk[i] = pack_bf16(p0, p1);
+            dk_[i] = pack_bf16(p0 * (dp[2 * i] - l0.y), p1 * (dp[2 * i + 1] - l1.y));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float2 l0 = ldp[2 * i], l1 = ldp[2 * i + 1];
+            const bool v0 = key_ok && (!p.causal || q0 + 2 * i >= qlim);
+            const bool v1 = key_ok && (!p.causal || q0 + 2 * i + 1 >= qlim);
+            const float p0 = v0 ? fast_exp2(fmaf(sv[2 * i], p.scale_log2, -l0.x)) : 0.f;
+            const float p1 = v1 ? fast_exp2(fmaf(sv[2 * i + 1], p.scale_log2, -l1.x)) : 0.f;
+            pk[i] = pack_bf16(p0, p1);
+            dk_[i] = pack_bf16(p0 * (dp[2 * i] - l0.y), p1 * (dp[2 * i + 1] - l1.y));
+          }
         }
+        // packed columns [16c, 16c+16) lie inside the fp32 columns this thread has already consumed (lane-private)
+        tmem_st_32x32b_x16(tST[s] + lane_off + c * 16, pk);
+        tmem_st_32x32b_x16(tDPT[s] + lane_off + c * 16, dk_);
       }
-      mbar_arrive(&ld_empty[s]);
-      if (TS) {
-        named_bar_sync(1, SM_THREADS);            // both column halves have read S^T / dP^T before anyone overwrites them
-        tmem_st_32x32b_x16(tST[s] + lane_off + half * 16, pk);
-        tmem_st_32x32b_x16(tDPT[s] + lane_off + half * 16, dk_);
-        tmem_st_wait();
-      } else {
-        if (n > 0) mbar_wait(pds_empty, (n - 1) & 1);
-        store_row32(sPT, r, half, pk);
-        store_row32(sDST, r, half, dk_);
-        fence_proxy_async();
-      }
+      tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(pds_full);
+      mbar_arrive(&pds_full[s]);
     }
-    // ---- epilogue: dK (x softmax scale), dV rows -> global; the two column halves split the 4 chunks of 32 dims ----
+    // ---- epilogue: group 0 stores dK (x softmax scale), group 1 stores dV ----
     const bool row_ok = kj < p.Sk;
     bf16* dkp = p.dk + (size_t)b * p.dk_sb + (size_t)(row_ok ? kj : 0) * p.dk_ss + (size_t)hk * p.dk_sh;
     bf16* dvp = p.dv + (size_t)b * p.dv_sb + (size_t)(row_ok ? kj : 0) * p.dv_ss + (size_t)hk * p.dv_sh;
     if (n_it > 0) {
       mbar_wait(acc_done, 0);
       tc_fence_after();
-      if (half == 0) store_acc_row(tDK + lane_off, dkp, row_ok, p.scale);
-      else           store_acc_row(tDV + lane_off, dvp, row_ok, 1.f);
+      if (grp == 0) store_acc_row(tDK + lane_off, dkp, row_ok, p.scale);
+      else          store_acc_row(tDV + lane_off, dvp, row_ok, 1.f);
     } else if (row_ok) {
       const uint4 z = make_uint4(0, 0, 0, 0);
-      bf16* dst = half == 0 ? dkp : dvp;
+      bf16* dst = grp == 0 ? dkp : dvp;
 #pragma unroll
       for (int c = 0; c < 16; ++c) *reinterpret_cast<uint4*>(dst + c * 8) = z;
     }
@@ -297,7 +268,6 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __gri
 }
 
 // ============================================================================================ dQ
-template <bool TS>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                          const __grid_constant__ CUtensorMap tmK64, const __grid_constant__ CUtensorMap tmV64,
@@ -306,17 +276,14 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                           // 32 KB resident
   uint8_t* sDO = sQ + FULL_TILE;                // 32 KB resident
-  uint8_t* sK = sDO + FULL_TILE;                // 2 x 16 KB
-  uint8_t* sV = sK + 2 * SUB_TILE;              // 2 x 16 KB
-  uint8_t* sDS = sV + 2 * SUB_TILE;             // 16 KB [128 q x 64 keys]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + FULL_HALF);
+  uint8_t* sK = sDO + FULL_TILE;                // QS x 16 KB
+  uint8_t* sV = sK + QS * SUB_TILE;             // QS x 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + QS * SUB_TILE);
   uint64_t* qdo_full = bars + 0;
-  uint64_t* kv_full = bars + 1;     // [2]
-  uint64_t* kv_empty = bars + 3;    // [2]
-  uint64_t* sdp_full = bars + 5;    // [2]
-  uint64_t* sdp_empty = bars + 7;   // [2]
-  uint64_t* ds_full = bars + 9;
-  uint64_t* ds_empty = bars + 10;
+  uint64_t* kv_full = bars + 1;     // [QS]
+  uint64_t* kv_empty = bars + 4;    // [QS]
+  uint64_t* sdp_full = bars + 7;    // [2]
+  uint64_t* ds_full = bars + 9;     // [2]
   uint64_t* acc_done = bars + 11;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
@@ -333,10 +300,9 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmQ); prefetch_tmap(&tmDO); prefetch_tmap(&tmK64); prefetch_tmap(&tmV64);
     mbar_init(qdo_full, 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); mbar_init(&sdp_full[s], 1); mbar_init(&sdp_empty[s], SM_THREADS);
-    }
-    mbar_init(ds_full, SM_THREADS); mbar_init(ds_empty, 1); mbar_init(acc_done, 1);
+    for (int s = 0; s < QS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&sdp_full[s], 1); mbar_init(&ds_full[s], 128); }
+    mbar_init(acc_done, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -356,7 +322,7 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       tma_load_4d(sDO, &tmDO, qdo_full, 0, h, q0, b);
       tma_load_4d(sDO + FULL_HALF, &tmDO, qdo_full, 64, h, q0, b);
       for (int n = 0; n < n_it; ++n) {
-        const int s = n & 1; const uint32_t ph = (n >> 1) & 1;
+        const int s = n % QS; const uint32_t ph = (n / QS) & 1;
         mbar_wait(&kv_empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&kv_full[s], 2 * SUB_TILE);
         tma_load_4d(sK + s * SUB_TILE, &tmK64, &kv_full[s], 0, hk, n * 64, b);
@@ -369,13 +335,12 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     if (lane == 0 && n_it > 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, false, false);
       constexpr uint32_t idesc_acc = make_idesc_bf16(128, 128, false, true);
-      const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sDO), ds_addr = smem_u32(sDS);
+      const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sDO);
       auto issue_sdp = [&](int n) {
-        const int s = n & 1; const uint32_t ph = (n >> 1) & 1;
-        mbar_wait(&kv_full[s], ph);
-        if (!TS) mbar_wait(&sdp_empty[s], ph ^ 1);
+        const int s = n & 1, ss = n % QS;
+        mbar_wait(&kv_full[ss], (n / QS) & 1);
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(sK + s * SUB_TILE), v_addr = smem_u32(sV + s * SUB_TILE);
+        const uint32_t k_addr = smem_u32(sK + ss * SUB_TILE), v_addr = smem_u32(sV + ss * SUB_TILE);
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk) {
           const uint32_t oa = (kk >> 2) * FULL_HALF + (kk & 3) * 32, ob = (kk >> 2) * SUB_HALF + (kk & 3) * 32;
@@ -390,26 +355,23 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       };
       mbar_wait(qdo_full, 0);
       issue_sdp(0);
+      if (n_it > 1) issue_sdp(1);
       for (int n = 0; n < n_it; ++n) {
-        if (n + 1 < n_it) issue_sdp(n + 1);
-        const int s = n & 1;
-        mbar_wait(ds_full, n & 1);
+        const int s = n & 1, ss = n % QS; const uint32_t ph = (n >> 1) & 1;
+        mbar_wait(&ds_full[s], ph);
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(sK + s * SUB_TILE);
+        const uint32_t k_addr = smem_u32(sK + ss * SUB_TILE);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {   // dQ += dS (K = 64 keys) x K (MN-major: rows = keys)
-          const uint64_t bd = make_smem_desc(k_addr + kk * 2048, SUB_HALF, 1024);
-          if (TS) umma_bf16_ts(tDQ, tS[s] + kk * 8, bd, idesc_acc, (n | kk) != 0);
-          else    umma_bf16_ss(tDQ, make_smem_desc(ds_addr + kk * 32, 16, 1024), bd, idesc_acc, (n | kk) != 0);
-        }
-        umma_commit(&kv_empty[s]);
-        umma_commit(ds_empty);
+        for (int kk = 0; kk < 4; ++kk)     // dQ += dS (TMEM A, K = 64 keys) x K (MN-major: rows = keys)
+          umma_bf16_ts(tDQ, tS[s] + kk * 8, make_smem_desc(k_addr + kk * 2048, SUB_HALF, 1024), idesc_acc, (n | kk) != 0);
+        umma_commit(&kv_empty[ss]);
+        if (n + 2 < n_it) issue_sdp(n + 2);
       }
       umma_commit(acc_done);
     }
   } else {
     const int qd = warp & 3;
-    const int half = (warp - 2) >> 2;            // which 32 of the 64 key columns
+    const int grp = (warp - 2) >> 2;             // ping-pong group == stage
     const int r = qd * 32 + lane;
     const int qi = q0 + r;
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
@@ -417,58 +379,53 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     const float2 ldv = p.ld[((size_t)b * p.H + h) * p.Sq_pad + qi];        // padded rows hold {+inf, 0}
     const float L = ldv.x, dl = ldv.y;
     const int limit = p.causal ? min(qi + off, p.Sk - 1) : (p.Sk - 1);
-    for (int n = 0; n < n_it; ++n) {
-      const int s = n & 1; const uint32_t ph = (n >> 1) & 1;
-      const int k0 = n * 64 + half * 32;
+    const int s = grp;
+    for (int n = grp; n < n_it; n += 2) {
+      const uint32_t ph = (n >> 1) & 1;
       mbar_wait(&sdp_full[s], ph);
       tc_fence_after();
-      float sv[32], dp[32];
-      tmem_ld_32x32b_x32(tS[s] + lane_off + half * 32, reinterpret_cast<uint32_t*>(sv));
-      tmem_ld_32x32b_x32(tDP[s] + lane_off + half * 32, reinterpret_cast<uint32_t*>(dp));
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&sdp_empty[s]);
-      uint32_t w = 0xffffffffu;
-      if (p.kbits) { const int wi = k0 >> 5; w = (wi < p.kbits_stride) ? __ldg(p.kbits + (size_t)b * p.kbits_stride + wi) : 0u; }
-      uint32_t dsk[16];
-      if (w == 0xffffffffu && k0 + 31 <= limit) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float p0 = fast_exp2(fmaf(sv[2 * i], p.scale_log2, -L));
-          const float p1 = fast_exp2(fmaf(sv[2 * i + 1], p.scale_log2, -L));
-          dsk[i] = pack_bf16(p0 * (dp[2 * i] - dl), p1 * (dp[2 * i + 1] - dl));
-        }
-      } else {
+      for (int c = 0; c < 2; ++c) {
+        const int k0 = n * 64 + c * 32;
+        float sv[32], dp[32];
+        tmem_ld_32x32b_x32(tS[s] + lane_off + c * 32, reinterpret_cast<uint32_t*>(sv));
+        tmem_ld_32x32b_x32(tDP[s] + lane_off + c * 32, reinterpret_cast<uint32_t*>(dp));
+        tmem_ld_wait();
+        uint32_t w = 0xffffffffu;
+        if (p.kbits) { const int wi = k0 >> 5; w = (wi < p.kbits_stride) ? __ldg(p.kbits + (size_t)b * p.kbits_stride + wi) : 0u; }
+        uint32_t dsk[16];
+        if (w == 0xffffffffu && k0 + 31 <= limit) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const bool v0 = (k0 + 2 * i <= limit) && ((w >> (2 * i)) & 1u);
-          const bool v1 = (k0 + 2 * i + 1 <= limit) && ((w >> (2 * i + 1)) & 1u);
-          const float p0 = v0 ? fast_exp2(fmaf(sv[2 * i], p.scale_log2, -L)) : 0.f;
-          const float p1 = v1 ? fast_exp2(fmaf(sv[2 * i + 1], p.scale_log2, -L)) : 0.f;
-          dsk[i] = pack_bf16(p0 * (dp[2 * i] - dl), p1 * (dp[2 * i + 1] - dl));
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = fast_exp2(fmaf(sv[2 * i], p.scale_log2, -L));
+            const float p1 = fast_exp2(fmaf(sv[2 * i + 1], p.scale_log2, -L));
+            dsk[i] = pack_bf16(p0 * (dp[2 * i] - dl), p1 * (dp[2 * i + 1] - dl));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const bool v0 = (k0 + 2 * i <= limit) && ((w >> (2 * i)) & 1u);
+            const bool v1 = (k0 + 2 * i + 1 <= limit) && ((w >> (2 * i + 1)) & 1u);
+            const float p0 = v0 ? fast_exp2(fmaf(sv[2 * i], p.scale_log2, -L)) : 0.f;
+            const float p1 = v1 ? fast_exp2(fmaf(sv[2 * i + 1], p.scale_log2, -L)) : 0.f;
+            dsk[i] = pack_bf16(p0 * (dp[2 * i] - dl), p1 * (dp[2 * i + 1] - dl));
+          }
         }
+        tmem_st_32x32b_x16(tS[s] + lane_off + c * 16, dsk);
       }
-      if (TS) {
-        named_bar_sync(1, SM_THREADS);
-        tmem_st_32x32b_x16(tS[s] + lane_off + half * 16, dsk);
-        tmem_st_wait();
-      } else {
-        if (n > 0) mbar_wait(ds_empty, (n - 1) & 1);
-        store_row32(sDS, r, half, dsk);
-        fence_proxy_async();
-      }
+      tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(ds_full);
+      mbar_arrive(&ds_full[s]);
     }
-    // epilogue: each column-half warp stores 64 of the 128 head dims of its dQ row (x softmax scale)
-    bf16* dqp = p.dq + (size_t)b * p.dq_sb + (size_t)(row_ok ? qi : 0) * p.dq_ss + (size_t)h * p.dq_sh + half * 64;
+    // epilogue: each group stores 64 of the 128 head dims of its dQ row (x softmax scale)
+    bf16* dqp = p.dq + (size_t)b * p.dq_sb + (size_t)(row_ok ? qi : 0) * p.dq_ss + (size_t)h * p.dq_sh + grp * 64;
     if (n_it > 0) {
       mbar_wait(acc_done, 0);
       tc_fence_after();
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t ov[32];
-        tmem_ld_32x32b_x32(tDQ + lane_off + half * 64 + c * 32, ov);
+        tmem_ld_32x32b_x32(tDQ + lane_off + grp * 64 + c * 32, ov);
         tmem_ld_wait();
         if (row_ok) {
 #pragma unroll
@@ -589,29 +546,19 @@ int mb200_attn_bwd_bf16(const void* q, const void* k, const void* v, const void*
   p.dv = (bf16*)dv; p.dv_sb = dk_sb; p.dv_ss = dk_ss; p.dv_sh = hd;
   p.kbits = kmask ? (const uint32_t*)kbits : nullptr; p.kbits_stride = (Sk + 31) / 32;
   p.B = B; p.H = H; p.Hkv = Hkv; p.Sq = Sq; p.Sk = Sk; p.scale = scale; p.scale_log2 = scale * LOG2E; p.causal = causal;
-  constexpr int smem_dkv = 2 * FULL_TILE + 4 * SUB_TILE + 2 * FULL_HALF + 1024 + 256 + 1024;
-  constexpr int smem_dq = 2 * FULL_TILE + 4 * SUB_TILE + FULL_HALF + 1024 + 256;
+  constexpr int smem_dkv = 2 * FULL_TILE + 2 * QS * SUB_TILE + 1024 + 256 + QS * 512;
+  constexpr int smem_dq = 2 * FULL_TILE + 2 * QS * SUB_TILE + 1024 + 256;
   static bool configured = false;
-  static int ts = 1;
   if (!configured) {
-    const char* e = getenv("MB200_ATTN_P_TMEM");
-    if (e) ts = atoi(e);
-    if (cudaFuncSetAttribute(attn_bwd_dkv_sm100_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dkv) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_bwd_dkv_sm100_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dkv) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_bwd_dq_sm100_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_bwd_dq_sm100_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq) != cudaSuccess) {
+    if (cudaFuncSetAttribute(attn_bwd_dkv_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dkv) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd_dq_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq) != cudaSuccess) {
       mb200_set_last_error("cudaFuncSetAttribute(attn bwd smem) failed"); return -EIO;
     }
     configured = true;
   }
   dim3 gkv((Sk + 127) / 128, Hkv, B), gq((Sq + 127) / 128, H, B);
-  if (ts) {
-    attn_bwd_dkv_sm100_kernel<true><<<gkv, NTHREADS, smem_dkv, st>>>(tmQ64, tmDO64, tmK, tmV, p);
-    attn_bwd_dq_sm100_kernel<true><<<gq, NTHREADS, smem_dq, st>>>(tmQ, tmDO, tmK64, tmV64, p);
-  } else {
-    attn_bwd_dkv_sm100_kernel<false><<<gkv, NTHREADS, smem_dkv, st>>>(tmQ64, tmDO64, tmK, tmV, p);
-    attn_bwd_dq_sm100_kernel<false><<<gq, NTHREADS, smem_dq, st>>>(tmQ, tmDO, tmK64, tmV64, p);
-  }
+  attn_bwd_dkv_sm100_kernel<<<gkv, NTHREADS, smem_dkv, st>>>(tmQ64, tmDO64, tmK, tmV, p);
+  attn_bwd_dq_sm100_kernel<<<gq, NTHREADS, smem_dq, st>>>(tmQ, tmDO, tmK64, tmV64, p);
   MB200_CHECK_LAUNCH();
   return MB200_OK;
 }

@@ -31,9 +31,24 @@ def flat_grad_buffer(params):
     return flat
 
 
+class _GradReady(torch.autograd.Function):
+    """identity whose backward fires a callback: placed at a decoder layer's input, it runs once that layer's backward
+    (and therefore every gradient of the layers above it) has been produced"""
+
+    @staticmethod
+    def forward(ctx, x, cb):
+        ctx.cb = cb
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        ctx.cb()
+        return g, None
+
+
 class B200Trainer:
     def __init__(self, model, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0,
-                 grad_accum=1, freeze_vision=True, fused_wgrad_accum=True):
+                 grad_accum=1, freeze_vision=True, fused_wgrad_accum=True, overlap_allreduce=True):
         self.model = model
         if freeze_vision:                                   # mantis/train/train_mllava.py:239-242
             for n, p in model.named_parameters():
@@ -55,6 +70,55 @@ class B200Trainer:
         self.step_count = 0
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self._norm = torch.zeros(1, dtype=torch.float32, device=self.flat_grad.device)
+        self._overlap = False
+        self._works = []
+        self._reduced_from = None
+        if overlap_allreduce and self.world > 1:
+            self._install_overlap_hooks()
+
+    # ---- overlapped gradient all-reduce (N > 1): during the LAST micro-batch's backward, the slice of the flat buffer
+    # belonging to decoder layer i+1 (and everything after it) is reduced as soon as layer i's backward has run, so the
+    # collective hides under the remaining backward; the head of the buffer is reduced after backward.
+    def _install_overlap_hooks(self):
+        layers = None
+        for name, mod in self.model.named_modules():
+            if name.endswith("language_model.model.layers") or name.endswith("text_model.layers"):
+                layers = mod
+        if layers is None:
+            return
+        base = self.flat_grad.data_ptr(); esz = self.flat_grad.element_size()
+        starts = []
+        for layer in layers:
+            ps = [p for p in layer.parameters() if p.requires_grad]
+            starts.append(min((p.grad.data_ptr() - base) // esz for p in ps) if ps else None)
+        if any(s is None for s in starts) or starts != sorted(starts):
+            return
+        self._layer_starts = starts
+        n = len(layers)
+
+        def make_cb(i):
+            def cb():
+                if not self._overlap:
+                    return
+                lo = self._layer_starts[i + 1] if i + 1 < n else None
+                if lo is None or self._reduced_from is None or lo >= self._reduced_from:
+                    return
+                self._works.append(dist.all_reduce(self.flat_grad[lo:self._reduced_from], op=dist.ReduceOp.SUM, async_op=True))
+                self._reduced_from = lo
+            return cb
+
+        def make_hook(i):
+            cb = make_cb(i)
+
+            def hook(mod, args):
+                if self._overlap and torch.is_grad_enabled() and args and args[0].requires_grad:
+                    return (_GradReady.apply(args[0], cb),) + tuple(args[1:])
+                return None
+            return hook
+
+        for i, layer in enumerate(layers):
+            layer.register_forward_pre_hook(make_hook(i))
+        self._has_hooks = True
 
     def zero_grad(self):
         self.flat_grad.zero_()
@@ -71,10 +135,17 @@ class B200Trainer:
         assert p.grad.data_ptr() == self.flat_grad.data_ptr(), "param.grad was rebound away from the flat buffer"
 
     def reduce_gradients(self):
-        """the one collective of the data-parallel path: sum the flat gradient buffer over ranks.
-        Returns the scale (1/world) still to be applied (folded into the AdamW kernel)."""
+        """the one collective of the data-parallel path: sum the flat gradient buffer over ranks (the part not already
+        reduced under the last backward).  Returns the scale (1/world) still to be applied (folded into AdamW)."""
         if self.world > 1:
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
+            rf = getattr(self, "_reduced_from", None)
+            hi = rf if rf is not None else self.flat_grad.numel()
+            if hi > 0:
+                dist.all_reduce(self.flat_grad[:hi], op=dist.ReduceOp.SUM)
+            for w in getattr(self, "_works", []):
+                w.wait()
+            self._works = []
+            self._reduced_from = None
         return 1.0 / self.world
 
     def optimizer_step(self):
@@ -95,6 +166,15 @@ class B200Trainer:
         self.zero_grad()
 
     def train_step(self, micro_batches):
-        losses = [self.micro_step(b) for b in micro_batches]
+        losses = []
+        for i, b in enumerate(micro_batches):
+            last = i == len(micro_batches) - 1
+            if last and self.world > 1 and getattr(self, "_has_hooks", False):
+                self._overlap = True
+                self._reduced_from = self.flat_grad.numel()
+            try:
+                losses.append(self.micro_step(b))
+            finally:
+                self._overlap = False
         self.optimizer_step()
         return torch.stack(losses).mean()

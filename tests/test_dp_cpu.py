@@ -57,3 +57,73 @@ def test_flat_grad_views_are_aligned():
     for p in ps:
         assert (p.grad.data_ptr() - flat.data_ptr()) % 16 == 0
         assert p.grad.shape == p.shape
+
+
+def _overlap_worker(rank, world, port, q):
+    import torch.nn as nn
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mantis_b200.train.engine import B200Trainer, flat_grad_buffer
+
+    class Layer(nn.Module):
+        def __init__(self):
+            super().__init__(); self.a = nn.Linear(8, 8); self.b = nn.Linear(8, 8)
+
+        def forward(self, x):
+            return x + self.b(torch.tanh(self.a(x)))
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.language_model = nn.Module(); self.language_model.model = nn.Module()
+            self.language_model.model.embed = nn.Linear(8, 8)
+            self.language_model.model.layers = nn.ModuleList([Layer() for _ in range(4)])
+            self.language_model.head = nn.Linear(8, 3)
+
+        def forward(self, x):
+            x = self.language_model.model.embed(x)
+            for l in self.language_model.model.layers:
+                x = l(x)
+            return self.language_model.head(x)
+
+    torch.manual_seed(0)
+    model = Net()
+    tr = B200Trainer.__new__(B200Trainer)
+    tr.model = model
+    tr.params = [p for p in model.parameters()]
+    tr.flat_grad = flat_grad_buffer(tr.params)
+    tr.world = world; tr.grad_accum = 2; tr._overlap = False; tr._works = []; tr._reduced_from = None
+    tr._install_overlap_hooks()
+    assert getattr(tr, "_has_hooks", False)
+    g = torch.Generator().manual_seed(10 + rank)
+    xs = [torch.randn(5, 8, generator=g) for _ in range(2)]
+    # reference: plain accumulation, then one all-reduce
+    for x in xs:
+        (model(x).pow(2).mean() / 2).backward()
+    ref = tr.flat_grad.clone(); dist.all_reduce(ref); ref /= world
+    tr.flat_grad.zero_()
+    # overlapped path: hooks active only during the last micro-batch
+    for i, x in enumerate(xs):
+        if i == 1:
+            tr._overlap = True; tr._reduced_from = tr.flat_grad.numel()
+        (model(x).pow(2).mean() / 2).backward()
+        tr._overlap = False
+    n_async = len(tr._works)
+    scale = tr.reduce_gradients()
+    q.put((rank, n_async, torch.allclose(tr.flat_grad * scale, ref, atol=1e-6)))
+    dist.destroy_process_group()
+
+
+def test_overlapped_allreduce_matches_single_allreduce():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_overlap_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, n_async, ok in res:
+        assert ok and n_async >= 3
