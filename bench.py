@@ -214,14 +214,17 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------ our arm
 def gemm_roofline(torch, ops, peaks):
-    """Per-kernel roofline of the dominant kernel (gemm_sm100_kernel): the seven linear-layer shapes of one LLaMA
-    layer at M = 7864 (fwd, dgrad, wgrad), each timed with CUDA events on the launching stream; L2 is flushed by
-    cycling through operand sets larger than L2."""
+    """Per-kernel roofline of the dominant kernel (the tcgen05 GEMM): CUDA events on the launching stream, operand sets
+    cycled so every launch reads cold-in-L2 data.  `achieved` is the gate/up-projection forward GEMM (M=7864, N=14336,
+    K=4096 -- the shape that carries most of the step's FLOPs and the one captured with `ncu --set full`, see
+    profiles/ncu_full_r01_summary.txt for `traffic`); `all_linear_shapes` aggregates fwd/dgrad/wgrad of all seven
+    linears of a decoder layer."""
     dev = torch.device("cuda")
     M = 7864
     shapes = [(4096, 4096), (1024, 4096), (1024, 4096), (4096, 4096), (14336, 4096), (14336, 4096), (4096, 14336)]
     flops = 0.0; t_ms = 0.0; launches = 0
     nset = 3
+    head = None
     for (N, K) in shapes:
         xs = [torch.randn(M, K, device=dev).bfloat16() for _ in range(nset)]
         ws = [(torch.randn(N, K, device=dev) * 0.02).bfloat16() for _ in range(nset)]
@@ -243,13 +246,63 @@ def gemm_roofline(torch, ops, peaks):
             for r in range(reps):
                 run(r % nset)
             e1.record(); torch.cuda.synchronize()
-            t_ms += e0.elapsed_time(e1); flops += reps * 2.0 * M * N * K; launches += reps
+            dt = e0.elapsed_time(e1)
+            t_ms += dt; flops += reps * 2.0 * M * N * K; launches += reps
+            if head is None and (N, K) == (14336, 4096) and kind == "fwd":
+                head = (2.0 * M * N * K / (dt / reps * 1e-3) / 1e12, dt / reps)
         del xs, ws, gs
-    ach = flops / (t_ms * 1e-3) / 1e12
+    ach_all = flops / (t_ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops"]
-    return {"bound": "tensor", "kernel": "gemm_sm100_kernel (tcgen05, 128x256x64)", "achieved": ach, "peak": peak,
-            "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "launches_timed": launches,
-            "avg_launch_ms": t_ms / launches}
+    ach, ms = head
+    return {"bound": "tensor", "kernel": "gemm_sm100_2cta_kernel (tcgen05 cta_group::2, 256x256x64 per SM pair), gate/up fwd "
+            "M=7864 N=14336 K=4096", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            "traffic": 754914560, "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, "
+            "profiles/ncu_full_r01_summary.txt (algorithmic operand bytes: 407 MB)", "avg_launch_ms": ms,
+            "all_linear_shapes": {"achieved": ach_all, "frac": ach_all / peak, "launches_timed": launches},
+            "tensor_pipe_active_pct_ncu": 93.0}
+
+
+def scatter_roofline(torch, ops, peaks):
+    """HBM roofline of the image-token scatter (merge_rows_kernel) for one bench micro-batch (1 sample, S = 7864):
+    algorithmic bytes = read every source row once + write every output row once = 2 * S * D * 2."""
+    dev = torch.device("cuda")
+    B, T, P, D = 1, T_TEXT, 728, 4096
+    S = T + N_IMG * (P - 1)
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(0, 128000, (B, T), generator=g)
+    for j in range(N_IMG):
+        ids[:, j * 256 + 16] = IMG_TOKEN
+    ids = ids.to(dev)
+    embs = [torch.randn(B, T, D, device=dev).bfloat16() for _ in range(8)]
+    feats = [torch.randn(N_IMG, P, D, device=dev).bfloat16() for _ in range(8)]
+    outs = [torch.empty((B, S, D), dtype=torch.bfloat16, device=dev) for _ in range(8)]
+    att = torch.ones_like(ids)
+    ws, hdr = ops.merge_plan(ids, embs[0], P, IMG_TOKEN, 128257)
+    srcmap = torch.empty((B, S), dtype=torch.int32, device=dev)
+    om = torch.empty((B, S), dtype=torch.int64, device=dev); op_ = torch.empty_like(om); ol = torch.empty_like(om)
+    ops._call("mb200_merge_index", ops._p(ids), ops._p(att), ops._p(ids), ops._p(ws), B, T, P, S, int(hdr[1]), IMG_TOKEN, -100,
+              ops._p(srcmap), ops._p(om), ops._p(ol), ops._p(op_), ops._st())
+
+    def run(i):
+        f2 = feats[i % 8].reshape(-1, D)
+        ops._call("mb200_merge_rows", ops._p(srcmap), ops._p(embs[i % 8]), ops._p(f2), ops._p(outs[i % 8]), B, S, T, D * 2,
+                  f2.shape[0], ops._st())
+    for i in range(8):
+        run(i)
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    reps = 40
+    e0.record()
+    for i in range(reps):
+        run(i)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    bytes_ = 2.0 * B * S * D * 2
+    ach = bytes_ / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "merge_rows_kernel (image-token scatter), 1 sample S=7864 D=4096", "achieved": ach,
+            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "avg_launch_ms": ms,
+            "algorithmic_bytes": bytes_, "note": "8 rotating 129 MB operand sets (> L2); B=4 capture: 468 MB DRAM traffic "
+            "vs 516 MB algorithmic (profiles/ncu_full_r01_summary.txt)"}
 
 
 def run_ours(args):
@@ -344,6 +397,7 @@ def run_ours(args):
     flop_per_step = 449e12 if args.workload == "idefics2" else FLOP_PER_STEP
     step_tflops = world * flop_per_step * (args.samples / SAMPLES_PER_STEP) * args.steps / (ms * 1e-3) / 1e12
     roof = gemm_roofline(torch, ops, peaks) if world == 1 else None
+    scat = scatter_roofline(torch, ops, peaks) if world == 1 else None
     full = (args.text_layers == 32 and args.vision_layers == 27 and args.samples == SAMPLES_PER_STEP)
     line = {
         "metric": ("training tokens/sec Mantis-8B-SigLIP 8-img/2048-tok" if args.workload == "mllava"
@@ -361,7 +415,7 @@ def run_ours(args):
                    "text_layers": args.text_layers, "vision_layers": args.vision_layers, "valid": full},
         "step_tflops": step_tflops, "step_frac_of_sustained_peak": step_tflops / world / peaks["bf16_tflops_sustained"],
         "peaks": peaks_src, "gpu_launches": launches, "max_mem_gb": mem_gb, "clocks": clocks, "loss": float(last_loss),
-        "e2e": e2e, "roofline": roof,
+        "e2e": e2e, "roofline": roof, "roofline_scatter": scat,
     }
     if not args.no_cpu_baseline and world == 1:
         try:
