@@ -24,14 +24,12 @@ using namespace sm100;
 constexpr int HD = 128;
 constexpr int FULL_HALF = 128 * 128;     // [128 rows x 64 bf16] swizzled sub-tile (16 KB)
 constexpr int FULL_TILE = 2 * FULL_HALF; // [128 rows x 128 hd]
-constexpr int SUB = 32;                  // streamed sub-tile width (queries in the dKV kernel, keys in the dQ kernel)
-constexpr int SUB_HALF = SUB * 128;      // [SUB rows x 64 bf16] swizzled sub-tile (4 KB)
-constexpr int SUB_TILE = 2 * SUB_HALF;   // [SUB rows x 128 hd] (8 KB)
-constexpr int NG = 4;                    // softmax groups == TMEM stages of (S, dP): four sub-tiles in flight per CTA
+constexpr int SUB_HALF = 64 * 128;       // [64 rows x 64 bf16] (8 KB)
+constexpr int SUB_TILE = 2 * SUB_HALF;   // [64 rows x 128 hd] (16 KB)
 constexpr float LOG2E = 1.44269504088896340736f;
 
-constexpr int QS = 6;                    // shared-memory stages of the streamed operand tiles
-constexpr int SM_WARPS = 4 * NG;         // softmax warps: NG groups of 4 (one warp per TMEM lane quarter)
+constexpr int QS = 3;                    // shared-memory stages of the streamed operand tiles (TMEM stages stay 2)
+constexpr int SM_WARPS = 8;              // softmax warps (two per TMEM lane quarter, each takes half of the columns)
 constexpr int SM_THREADS = SM_WARPS * 32;
 constexpr int NTHREADS = 64 + SM_THREADS;
 
@@ -58,11 +56,31 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// store one 128-lane x 128-column fp32 accumulator row as bf16 (256 B) to global
+__device__ __forceinline__ void store_acc_row(uint32_t taddr, bf16* dst, bool ok, float mul) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t ov[32];
+    tmem_ld_32x32b_x32(taddr + c * 32, ov);
+    tmem_ld_wait();
+    if (ok) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 o4;
+        o4.x = pack_bf16(__uint_as_float(ov[g * 8 + 0]) * mul, __uint_as_float(ov[g * 8 + 1]) * mul);
+        o4.y = pack_bf16(__uint_as_float(ov[g * 8 + 2]) * mul, __uint_as_float(ov[g * 8 + 3]) * mul);
+        o4.z = pack_bf16(__uint_as_float(ov[g * 8 + 4]) * mul, __uint_as_float(ov[g * 8 + 5]) * mul);
+        o4.w = pack_bf16(__uint_as_float(ov[g * 8 + 6]) * mul, __uint_as_float(ov[g * 8 + 7]) * mul);
+        *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = o4;
+      }
+    }
+  }
+}
+
 // ============================================================================================ dK / dV
-// Softmax warps form NG = 4 groups of four warps that rotate over the 32-query sub-tiles: group g owns TMEM stage g
-// (S^T_g, dP^T_g), so while some groups wait on barriers / TMEM / MUFU latency the others compute, and the MMA thread
-// always has another stage's products to issue (these kernels are latency-bound, not throughput-bound: ncu shows
-// tensor 32-36 %, MUFU 22-26 %, issue 25 % with two groups).  P^T / dS^T (bf16) are written back into the first 32 columns of S^T_g / dP^T_g and
+// Softmax warps form two groups (warps 2-5 and 6-9) that ping-pong over the 64-query sub-tiles: group g owns TMEM stage g
+// (S^T_g, dP^T_g), so while one group waits on barriers / TMEM latency the other computes, and the MMA thread always has
+// the other stage's products to issue.  P^T / dS^T (bf16) are written back into the first 32 columns of S^T_g / dP^T_g and
 // feed the dV / dK MMAs as TMEM A operands: nothing but Q / dO / K / V tiles ever touches shared memory.
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant__ CUtensorMap tmDO64,
@@ -74,24 +92,24 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __gri
   uint8_t* sV = sK + FULL_TILE;                 // 32 KB resident
   uint8_t* sQ = sV + FULL_TILE;                 // QS stages x 16 KB
   uint8_t* sDO = sQ + QS * SUB_TILE;            // QS stages x 16 KB
-  float2* sLD = reinterpret_cast<float2*>(sDO + QS * SUB_TILE);   // [QS][SUB] {lse2, delta}
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sLD + QS * SUB);
+  float2* sLD = reinterpret_cast<float2*>(sDO + QS * SUB_TILE);   // [QS][64] {lse2, delta}
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sLD + QS * 64);
   uint64_t* kv_full = bars + 0;
-  uint64_t* qdo_full = bars + 1;             // [QS]
-  uint64_t* qdo_empty = qdo_full + QS;       // [QS]
-  uint64_t* sdp_full = qdo_empty + QS;       // [NG]
-  uint64_t* pds_full = sdp_full + NG;        // [NG]
-  uint64_t* acc_done = pds_full + NG;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+  uint64_t* qdo_full = bars + 1;    // [QS]
+  uint64_t* qdo_empty = bars + 4;   // [QS]
+  uint64_t* sdp_full = bars + 7;    // [2]
+  uint64_t* pds_full = bars + 9;    // [2]
+  uint64_t* acc_done = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
   const int G = p.H / p.Hkv;
   const int k0 = kt * 128;
   const int off = p.Sk - p.Sq;
-  const int n_qs = (p.Sq + SUB - 1) / SUB;
+  const int n_qs = (p.Sq + 63) / 64;
   int qs_begin = 0;
-  if (p.causal) { int qb = k0 - off; if (qb < 0) qb = 0; qs_begin = qb / SUB; }
+  if (p.causal) { int qb = k0 - off; if (qb < 0) qb = 0; qs_begin = qb / 64; }
   const int per_head = (n_qs > qs_begin) ? (n_qs - qs_begin) : 0;
   const int n_it = per_head * G;
 
@@ -99,7 +117,7 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __gri
     prefetch_tmap(&tmQ64); prefetch_tmap(&tmDO64); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
     mbar_init(kv_full, 1);
     for (int s = 0; s < QS; ++s) { mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1); }
-    for (int s = 0; s < NG; ++s) { mbar_init(&sdp_full[s], 1); mbar_init(&pds_full[s], 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&sdp_full[s], 1); mbar_init(&pds_full[s], 128); }
     mbar_init(acc_done, 1);
     fence_barrier_init();
   }
@@ -109,8 +127,8 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __gri
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tDK = tmem_base, tDV = tmem_base + 128;
-  const uint32_t tST0 = tmem_base + 256;            // stage g: S^T at tST0 + 64 g (SUB fp32 columns), dP^T right after it
-  const uint32_t tDPT0 = tmem_base + 256 + SUB;
+  const uint32_t tST[2] = {tmem_base + 256, tmem_base + 384};
+  const uint32_t tDPT[2] = {tmem_base + 320, tmem_base + 448};
 
   if (warp == 0) {
     if (lane == 0) {
@@ -123,51 +141,52 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __gri
         const int s = n % QS; const uint32_t ph = (n / QS) & 1;
         const int h = hk * G + n / per_head, qs = qs_begin + n % per_head;
         mbar_wait(&qdo_empty[s], ph ^ 1);      // dV/dK of sub-tile n-QS done => Q/dO stage and sLD[s] are free
-        mbar_arrive_expect_tx(&qdo_full[s], 2 * SUB_TILE + SUB * 8);
-        tma_load_4d(sQ + s * SUB_TILE, &tmQ64, &qdo_full[s], 0, h, qs * SUB, b);
-        tma_load_4d(sQ + s * SUB_TILE + SUB_HALF, &tmQ64, &qdo_full[s], 64, h, qs * SUB, b);
-        tma_load_4d(sDO + s * SUB_TILE, &tmDO64, &qdo_full[s], 0, h, qs * SUB, b);
-        tma_load_4d(sDO + s * SUB_TILE + SUB_HALF, &tmDO64, &qdo_full[s], 64, h, qs * SUB, b);
-        bulk_load_1d(sLD + s * SUB, p.ld + ((size_t)b * p.H + h) * p.Sq_pad + qs * SUB, SUB * 8, &qdo_full[s]);
+        mbar_arrive_expect_tx(&qdo_full[s], 2 * SUB_TILE + 64 * 8);
+        tma_load_4d(sQ + s * SUB_TILE, &tmQ64, &qdo_full[s], 0, h, qs * 64, b);
+        tma_load_4d(sQ + s * SUB_TILE + SUB_HALF, &tmQ64, &qdo_full[s], 64, h, qs * 64, b);
+        tma_load_4d(sDO + s * SUB_TILE, &tmDO64, &qdo_full[s], 0, h, qs * 64, b);
+        tma_load_4d(sDO + s * SUB_TILE + SUB_HALF, &tmDO64, &qdo_full[s], 64, h, qs * 64, b);
+        bulk_load_1d(sLD + s * 64, p.ld + ((size_t)b * p.H + h) * p.Sq_pad + qs * 64, 64 * 8, &qdo_full[s]);
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && n_it > 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, SUB, false, false);
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, false, false);
       constexpr uint32_t idesc_acc = make_idesc_bf16(128, 128, false, true);
       const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
-      auto issue_sdp = [&](int n) {             // TMEM stage n % NG was last read by dV/dK(n - NG), issued earlier (in-order pipe)
-        const int g = n % NG, ss = n % QS;
+      auto issue_sdp = [&](int n) {             // TMEM stage n&1 was last read by dV/dK(n-2), issued earlier (in-order tensor pipe)
+        const int s = n & 1, ss = n % QS;
         mbar_wait(&qdo_full[ss], (n / QS) & 1);
         tc_fence_after();
         const uint32_t q_addr = smem_u32(sQ + ss * SUB_TILE), do_addr = smem_u32(sDO + ss * SUB_TILE);
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk) {
           const uint32_t oa = (kk >> 2) * FULL_HALF + (kk & 3) * 32, ob = (kk >> 2) * SUB_HALF + (kk & 3) * 32;
-          umma_bf16_ss(tST0 + g * 64, make_smem_desc(k_addr + oa, 16, 1024), make_smem_desc(q_addr + ob, 16, 1024), idesc_s, kk != 0);
+          umma_bf16_ss(tST[s], make_smem_desc(k_addr + oa, 16, 1024), make_smem_desc(q_addr + ob, 16, 1024), idesc_s, kk != 0);
         }
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk) {
           const uint32_t oa = (kk >> 2) * FULL_HALF + (kk & 3) * 32, ob = (kk >> 2) * SUB_HALF + (kk & 3) * 32;
-          umma_bf16_ss(tDPT0 + g * 64, make_smem_desc(v_addr + oa, 16, 1024), make_smem_desc(do_addr + ob, 16, 1024), idesc_s, kk != 0);
+          umma_bf16_ss(tDPT[s], make_smem_desc(v_addr + oa, 16, 1024), make_smem_desc(do_addr + ob, 16, 1024), idesc_s, kk != 0);
         }
-        umma_commit(&sdp_full[g]);
+        umma_commit(&sdp_full[s]);
       };
       mbar_wait(kv_full, 0);
-      for (int n = 0; n < NG && n < n_it; ++n) issue_sdp(n);
+      issue_sdp(0);
+      if (n_it > 1) issue_sdp(1);
       for (int n = 0; n < n_it; ++n) {
-        const int g = n % NG, ss = n % QS;
-        mbar_wait(&pds_full[g], (n / NG) & 1);
+        const int s = n & 1, ss = n % QS; const uint32_t ph = (n >> 1) & 1;
+        mbar_wait(&pds_full[s], ph);
         tc_fence_after();
         const uint32_t q_addr = smem_u32(sQ + ss * SUB_TILE), do_addr = smem_u32(sDO + ss * SUB_TILE);
 #pragma unroll
-        for (int kk = 0; kk < SUB / 16; ++kk)   // dV += P^T (TMEM A, K = SUB queries) x dO (MN-major: rows = queries)
-          umma_bf16_ts(tDV, tST0 + g * 64 + kk * 8, make_smem_desc(do_addr + kk * 2048, SUB_HALF, 1024), idesc_acc, (n | kk) != 0);
+        for (int kk = 0; kk < 4; ++kk)     // dV += P^T (TMEM A, K = 64 queries) x dO (MN-major: rows = queries)
+          umma_bf16_ts(tDV, tST[s] + kk * 8, make_smem_desc(do_addr + kk * 2048, SUB_HALF, 1024), idesc_acc, (n | kk) != 0);
 #pragma unroll
-        for (int kk = 0; kk < SUB / 16; ++kk)   // dK += dS^T (TMEM A) x Q
-          umma_bf16_ts(tDK, tDPT0 + g * 64 + kk * 8, make_smem_desc(q_addr + kk * 2048, SUB_HALF, 1024), idesc_acc, (n | kk) != 0);
+        for (int kk = 0; kk < 4; ++kk)     // dK += dS^T (TMEM A) x Q
+          umma_bf16_ts(tDK, tDPT[s] + kk * 8, make_smem_desc(q_addr + kk * 2048, SUB_HALF, 1024), idesc_acc, (n | kk) != 0);
         umma_commit(&qdo_empty[ss]);
-        if (n + NG < n_it) issue_sdp(n + NG);
+        if (n + 2 < n_it) issue_sdp(n + 2);
       }
       umma_commit(acc_done);
     }
@@ -180,83 +199,67 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __gri
     bool key_ok = kj < p.Sk;
     if (key_ok && p.kbits) key_ok = (__ldg(p.kbits + (size_t)b * p.kbits_stride + (kj >> 5)) >> (kj & 31)) & 1u;
     const int qlim = kj - off;                   // causal: query qi sees key kj iff qi >= kj - off
-    for (int n = grp; n < n_it; n += NG) {
-      const uint32_t ph = (n / NG) & 1;
+    const int s = grp;
+    for (int n = grp; n < n_it; n += 2) {
+      const uint32_t ph = (n >> 1) & 1;
       const int qs = qs_begin + n % per_head;
       const int ss = n % QS;
-      const int q0 = qs * SUB;
       mbar_wait(&qdo_full[ss], (n / QS) & 1);    // lse/delta landed (bulk copy on the same barrier as Q/dO)
-      mbar_wait(&sdp_full[grp], ph);
+      mbar_wait(&sdp_full[s], ph);
       tc_fence_after();
-      float sv[32], dp[32];
-      tmem_ld_32x32b_x32(tST0 + grp * 64 + lane_off, reinterpret_cast<uint32_t*>(sv));
-      tmem_ld_32x32b_x32(tDPT0 + grp * 64 + lane_off, reinterpret_cast<uint32_t*>(dp));
-      tmem_ld_wait();
-      const float2* ldp = sLD + ss * SUB;
-      uint32_t pk[16], dk_[16];
-      const bool full_vis = key_ok && (!p.causal || q0 >= qlim);
-      if (full_vis) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float2 l0 = ldp[2 * i], l1 = ldp[2 * i + 1];
-          const float p0 = fast_exp2(fmaf(sv[2 * i], p.scale_log2, -l0.x));
-          const float p1 = fast_exp2(fmaf(sv[2 * i + 1], p.scale_log2, -l1.x));
-          pk[i] = pack_bf16(p0, p1);
-          dk_[i] = pack_bf16(p0 * (dp[2 * i] - l0.y), p1 * (dp[2 * i + 1] - l1.y));
-        }
-      } else {
+      for (int c = 0; c < 2; ++c) {              // two chunks of 32 query columns
+        const int q0 = qs * 64 + c * 32;
+        float sv[32], dp[32];
+        tmem_ld_32x32b_x32(tST[s] + lane_off + c * 32, reinterpret_cast<uint32_t*>(sv));
+        tmem_ld_32x32b_x32(tDPT[s] + lane_off + c * 32, reinterpret_cast<uint32_t*>(dp));
+        tmem_ld_wait();
+        const float2* ldp = sLD + ss * 64 + c * 32;
+        uint32_t pk[16], dk_[16];
+        const bool full_vis = key_ok && (!p.causal || q0 >= qlim);
+        if (full_vis) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float2 l0 = ldp[2 * i], l1 = ldp[2 * i + 1];
-          const bool v0 = key_ok && (!p.causal || q0 + 2 * i >= qlim);
-          const bool v1 = key_ok && (!p.causal || q0 + 2 * i + 1 >= qlim);
-          const float p0 = v0 ? fast_exp2(fmaf(sv[2 * i], p.scale_log2, -l0.x)) : 0.f;
-          const float p1 = v1 ? fast_exp2(fmaf(sv[2 * i + 1], p.scale_log2, -l1.x)) : 0.f;
-          pk[i] = pack_bf16(p0, p1);
-          dk_[i] = pack_bf16(p0 * (dp[2 * i] - l0.y), p1 * (dp[2 * i + 1] - l1.y));
+          for (int i = 0; i < 16; ++i) {
+            const float2 l0 = ldp[2 * i], l1 = ldp[2 * i + 1];
+            const float p0 = fast_exp2(fmaf(sv[2 * i], p.scale_log2, -l0.x));
+            const float p1 = fast_exp2(fmaf(sv[2 * i + 1], p.scale_log2, -l1.x));
+            pk[i] = pack_bf16(p0, p1);
+            dk_[i] = pack_bf16(p0 * (dp[2 * i] - l0.y), p1 * (dp[2 * i + 1] - l1.y));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float2 l0 = ldp[2 * i], l1 = ldp[2 * i + 1];
+            const bool v0 = key_ok && (!p.causal || q0 + 2 * i >= qlim);
+            const bool v1 = key_ok && (!p.causal || q0 + 2 * i + 1 >= qlim);
+            const float p0 = v0 ? fast_exp2(fmaf(sv[2 * i], p.scale_log2, -l0.x)) : 0.f;
+            const float p1 = v1 ? fast_exp2(fmaf(sv[2 * i + 1], p.scale_log2, -l1.x)) : 0.f;
+            pk[i] = pack_bf16(p0, p1);
+            dk_[i] = pack_bf16(p0 * (dp[2 * i] - l0.y), p1 * (dp[2 * i + 1] - l1.y));
+          }
         }
+        // packed columns [16c, 16c+16) lie inside the fp32 columns this thread has already consumed (lane-private)
+        tmem_st_32x32b_x16(tST[s] + lane_off + c * 16, pk);
+        tmem_st_32x32b_x16(tDPT[s] + lane_off + c * 16, dk_);
       }
-      // packed columns [0, 16) lie inside the fp32 columns this thread has already consumed (lane-private)
-      tmem_st_32x32b_x16(tST0 + grp * 64 + lane_off, pk);
-      tmem_st_32x32b_x16(tDPT0 + grp * 64 + lane_off, dk_);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&pds_full[grp]);
+      mbar_arrive(&pds_full[s]);
     }
-    // ---- epilogue ----
+    // ---- epilogue: group 0 stores dK (x softmax scale), group 1 stores dV ----
     const bool row_ok = kj < p.Sk;
     bf16* dkp = p.dk + (size_t)b * p.dk_sb + (size_t)(row_ok ? kj : 0) * p.dk_ss + (size_t)hk * p.dk_sh;
     bf16* dvp = p.dv + (size_t)b * p.dv_sb + (size_t)(row_ok ? kj : 0) * p.dv_ss + (size_t)hk * p.dv_sh;
     if (n_it > 0) {
       mbar_wait(acc_done, 0);
       tc_fence_after();
-      // four groups split the work: group g stores 64 head dims of dK (g = 0,1) or dV (g = 2,3)
-      const int hsel = (grp & 1) * 64;
-      const uint32_t tsrc = (grp < 2 ? tDK : tDV) + lane_off + hsel;
-      bf16* dst = (grp < 2 ? dkp : dvp) + hsel;
-      const float mul = grp < 2 ? p.scale : 1.f;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t ov[32];
-        tmem_ld_32x32b_x32(tsrc + c * 32, ov);
-        tmem_ld_wait();
-        if (row_ok) {
-#pragma unroll
-          for (int g4 = 0; g4 < 4; ++g4) {
-            uint4 o4;
-            o4.x = pack_bf16(__uint_as_float(ov[g4 * 8 + 0]) * mul, __uint_as_float(ov[g4 * 8 + 1]) * mul);
-            o4.y = pack_bf16(__uint_as_float(ov[g4 * 8 + 2]) * mul, __uint_as_float(ov[g4 * 8 + 3]) * mul);
-            o4.z = pack_bf16(__uint_as_float(ov[g4 * 8 + 4]) * mul, __uint_as_float(ov[g4 * 8 + 5]) * mul);
-            o4.w = pack_bf16(__uint_as_float(ov[g4 * 8 + 6]) * mul, __uint_as_float(ov[g4 * 8 + 7]) * mul);
-            *reinterpret_cast<uint4*>(dst + c * 32 + g4 * 8) = o4;
-          }
-        }
-      }
+      if (grp == 0) store_acc_row(tDK + lane_off, dkp, row_ok, p.scale);
+      else          store_acc_row(tDV + lane_off, dvp, row_ok, 1.f);
     } else if (row_ok) {
       const uint4 z = make_uint4(0, 0, 0, 0);
-      bf16* dst = (grp < 2 ? dkp : dvp) + (grp & 1) * 64;
+      bf16* dst = grp == 0 ? dkp : dvp;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(dst + c * 8) = z;
+      for (int c = 0; c < 16; ++c) *reinterpret_cast<uint4*>(dst + c * 8) = z;
     }
   }
   tc_fence_before();
@@ -277,12 +280,12 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   uint8_t* sV = sK + QS * SUB_TILE;             // QS x 16 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + QS * SUB_TILE);
   uint64_t* qdo_full = bars + 0;
-  uint64_t* kv_full = bars + 1;              // [QS]
-  uint64_t* kv_empty = kv_full + QS;         // [QS]
-  uint64_t* sdp_full = kv_empty + QS;        // [NG]
-  uint64_t* ds_full = sdp_full + NG;         // [NG]
-  uint64_t* acc_done = ds_full + NG;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+  uint64_t* kv_full = bars + 1;     // [QS]
+  uint64_t* kv_empty = bars + 4;    // [QS]
+  uint64_t* sdp_full = bars + 7;    // [2]
+  uint64_t* ds_full = bars + 9;     // [2]
+  uint64_t* acc_done = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = gridDim.x - 1 - blockIdx.x;
@@ -292,13 +295,13 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   const int off = p.Sk - p.Sq;
   int kv_end = p.Sk;
   if (p.causal) { kv_end = min(p.Sk, q0 + 128 + off); if (kv_end < 0) kv_end = 0; }
-  const int n_it = (kv_end + SUB - 1) / SUB;
+  const int n_it = (kv_end + 63) / 64;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmQ); prefetch_tmap(&tmDO); prefetch_tmap(&tmK64); prefetch_tmap(&tmV64);
     mbar_init(qdo_full, 1);
     for (int s = 0; s < QS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    for (int s = 0; s < NG; ++s) { mbar_init(&sdp_full[s], 1); mbar_init(&ds_full[s], 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&sdp_full[s], 1); mbar_init(&ds_full[s], 128); }
     mbar_init(acc_done, 1);
     fence_barrier_init();
   }
@@ -308,8 +311,8 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tDQ = tmem_base;
-  const uint32_t tS0 = tmem_base + 128;               // stage g: S at tS0 + 64 g (SUB fp32 columns), dP right after it
-  const uint32_t tDP0 = tmem_base + 128 + SUB;
+  const uint32_t tS[2] = {tmem_base + 128, tmem_base + 256};
+  const uint32_t tDP[2] = {tmem_base + 192, tmem_base + 320};
 
   if (warp == 0) {
     if (lane == 0 && n_it > 0) {
@@ -322,46 +325,47 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         const int s = n % QS; const uint32_t ph = (n / QS) & 1;
         mbar_wait(&kv_empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&kv_full[s], 2 * SUB_TILE);
-        tma_load_4d(sK + s * SUB_TILE, &tmK64, &kv_full[s], 0, hk, n * SUB, b);
-        tma_load_4d(sK + s * SUB_TILE + SUB_HALF, &tmK64, &kv_full[s], 64, hk, n * SUB, b);
-        tma_load_4d(sV + s * SUB_TILE, &tmV64, &kv_full[s], 0, hk, n * SUB, b);
-        tma_load_4d(sV + s * SUB_TILE + SUB_HALF, &tmV64, &kv_full[s], 64, hk, n * SUB, b);
+        tma_load_4d(sK + s * SUB_TILE, &tmK64, &kv_full[s], 0, hk, n * 64, b);
+        tma_load_4d(sK + s * SUB_TILE + SUB_HALF, &tmK64, &kv_full[s], 64, hk, n * 64, b);
+        tma_load_4d(sV + s * SUB_TILE, &tmV64, &kv_full[s], 0, hk, n * 64, b);
+        tma_load_4d(sV + s * SUB_TILE + SUB_HALF, &tmV64, &kv_full[s], 64, hk, n * 64, b);
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && n_it > 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, SUB, false, false);
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, false, false);
       constexpr uint32_t idesc_acc = make_idesc_bf16(128, 128, false, true);
       const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sDO);
       auto issue_sdp = [&](int n) {
-        const int g = n % NG, ss = n % QS;
+        const int s = n & 1, ss = n % QS;
         mbar_wait(&kv_full[ss], (n / QS) & 1);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sK + ss * SUB_TILE), v_addr = smem_u32(sV + ss * SUB_TILE);
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk) {
           const uint32_t oa = (kk >> 2) * FULL_HALF + (kk & 3) * 32, ob = (kk >> 2) * SUB_HALF + (kk & 3) * 32;
-          umma_bf16_ss(tS0 + g * 64, make_smem_desc(q_addr + oa, 16, 1024), make_smem_desc(k_addr + ob, 16, 1024), idesc_s, kk != 0);
+          umma_bf16_ss(tS[s], make_smem_desc(q_addr + oa, 16, 1024), make_smem_desc(k_addr + ob, 16, 1024), idesc_s, kk != 0);
         }
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk) {
           const uint32_t oa = (kk >> 2) * FULL_HALF + (kk & 3) * 32, ob = (kk >> 2) * SUB_HALF + (kk & 3) * 32;
-          umma_bf16_ss(tDP0 + g * 64, make_smem_desc(do_addr + oa, 16, 1024), make_smem_desc(v_addr + ob, 16, 1024), idesc_s, kk != 0);
+          umma_bf16_ss(tDP[s], make_smem_desc(do_addr + oa, 16, 1024), make_smem_desc(v_addr + ob, 16, 1024), idesc_s, kk != 0);
         }
-        umma_commit(&sdp_full[g]);
+        umma_commit(&sdp_full[s]);
       };
       mbar_wait(qdo_full, 0);
-      for (int n = 0; n < NG && n < n_it; ++n) issue_sdp(n);
+      issue_sdp(0);
+      if (n_it > 1) issue_sdp(1);
       for (int n = 0; n < n_it; ++n) {
-        const int g = n % NG, ss = n % QS;
-        mbar_wait(&ds_full[g], (n / NG) & 1);
+        const int s = n & 1, ss = n % QS; const uint32_t ph = (n >> 1) & 1;
+        mbar_wait(&ds_full[s], ph);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sK + ss * SUB_TILE);
 #pragma unroll
-        for (int kk = 0; kk < SUB / 16; ++kk)   // dQ += dS (TMEM A, K = SUB keys) x K (MN-major: rows = keys)
-          umma_bf16_ts(tDQ, tS0 + g * 64 + kk * 8, make_smem_desc(k_addr + kk * 2048, SUB_HALF, 1024), idesc_acc, (n | kk) != 0);
+        for (int kk = 0; kk < 4; ++kk)     // dQ += dS (TMEM A, K = 64 keys) x K (MN-major: rows = keys)
+          umma_bf16_ts(tDQ, tS[s] + kk * 8, make_smem_desc(k_addr + kk * 2048, SUB_HALF, 1024), idesc_acc, (n | kk) != 0);
         umma_commit(&kv_empty[ss]);
-        if (n + NG < n_it) issue_sdp(n + NG);
+        if (n + 2 < n_it) issue_sdp(n + 2);
       }
       umma_commit(acc_done);
     }
@@ -375,63 +379,70 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     const float2 ldv = p.ld[((size_t)b * p.H + h) * p.Sq_pad + qi];        // padded rows hold {+inf, 0}
     const float L = ldv.x, dl = ldv.y;
     const int limit = p.causal ? min(qi + off, p.Sk - 1) : (p.Sk - 1);
-    for (int n = grp; n < n_it; n += NG) {
-      const uint32_t ph = (n / NG) & 1;
-      const int k0 = n * SUB;
-      mbar_wait(&sdp_full[grp], ph);
+    const int s = grp;
+    for (int n = grp; n < n_it; n += 2) {
+      const uint32_t ph = (n >> 1) & 1;
+      mbar_wait(&sdp_full[s], ph);
       tc_fence_after();
-      float sv[32], dp[32];
-      tmem_ld_32x32b_x32(tS0 + grp * 64 + lane_off, reinterpret_cast<uint32_t*>(sv));
-      tmem_ld_32x32b_x32(tDP0 + grp * 64 + lane_off, reinterpret_cast<uint32_t*>(dp));
-      tmem_ld_wait();
-      uint32_t w = 0xffffffffu;
-      if (p.kbits) { const int wi = k0 >> 5; w = (wi < p.kbits_stride) ? __ldg(p.kbits + (size_t)b * p.kbits_stride + wi) : 0u; }
-      uint32_t dsk[16];
-      if (w == 0xffffffffu && k0 + 31 <= limit) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float p0 = fast_exp2(fmaf(sv[2 * i], p.scale_log2, -L));
-          const float p1 = fast_exp2(fmaf(sv[2 * i + 1], p.scale_log2, -L));
-          dsk[i] = pack_bf16(p0 * (dp[2 * i] - dl), p1 * (dp[2 * i + 1] - dl));
-        }
-      } else {
+      for (int c = 0; c < 2; ++c) {
+        const int k0 = n * 64 + c * 32;
+        float sv[32], dp[32];
+        tmem_ld_32x32b_x32(tS[s] + lane_off + c * 32, reinterpret_cast<uint32_t*>(sv));
+        tmem_ld_32x32b_x32(tDP[s] + lane_off + c * 32, reinterpret_cast<uint32_t*>(dp));
+        tmem_ld_wait();
+        uint32_t w = 0xffffffffu;
+        if (p.kbits) { const int wi = k0 >> 5; w = (wi < p.kbits_stride) ? __ldg(p.kbits + (size_t)b * p.kbits_stride + wi) : 0u; }
+        uint32_t dsk[16];
+        if (w == 0xffffffffu && k0 + 31 <= limit) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const bool v0 = (k0 + 2 * i <= limit) && ((w >> (2 * i)) & 1u);
-          const bool v1 = (k0 + 2 * i + 1 <= limit) && ((w >> (2 * i + 1)) & 1u);
-          const float p0 = v0 ? fast_exp2(fmaf(sv[2 * i], p.scale_log2, -L)) : 0.f;
-          const float p1 = v1 ? fast_exp2(fmaf(sv[2 * i + 1], p.scale_log2, -L)) : 0.f;
-          dsk[i] = pack_bf16(p0 * (dp[2 * i] - dl), p1 * (dp[2 * i + 1] - dl));
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = fast_exp2(fmaf(sv[2 * i], p.scale_log2, -L));
+            const float p1 = fast_exp2(fmaf(sv[2 * i + 1], p.scale_log2, -L));
+            dsk[i] = pack_bf16(p0 * (dp[2 * i] - dl), p1 * (dp[2 * i + 1] - dl));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const bool v0 = (k0 + 2 * i <= limit) && ((w >> (2 * i)) & 1u);
+            const bool v1 = (k0 + 2 * i + 1 <= limit) && ((w >> (2 * i + 1)) & 1u);
+            const float p0 = v0 ? fast_exp2(fmaf(sv[2 * i], p.scale_log2, -L)) : 0.f;
+            const float p1 = v1 ? fast_exp2(fmaf(sv[2 * i + 1], p.scale_log2, -L)) : 0.f;
+            dsk[i] = pack_bf16(p0 * (dp[2 * i] - dl), p1 * (dp[2 * i + 1] - dl));
+          }
         }
+        tmem_st_32x32b_x16(tS[s] + lane_off + c * 16, dsk);
       }
-      tmem_st_32x32b_x16(tS0 + grp * 64 + lane_off, dsk);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&ds_full[grp]);
+      mbar_arrive(&ds_full[s]);
     }
-    // epilogue: each of the four groups stores 32 of the 128 head dims of its dQ row (x softmax scale)
-    bf16* dqp = p.dq + (size_t)b * p.dq_sb + (size_t)(row_ok ? qi : 0) * p.dq_ss + (size_t)h * p.dq_sh + grp * 32;
+    // epilogue: each group stores 64 of the 128 head dims of its dQ row (x softmax scale)
+    bf16* dqp = p.dq + (size_t)b * p.dq_sb + (size_t)(row_ok ? qi : 0) * p.dq_ss + (size_t)h * p.dq_sh + grp * 64;
     if (n_it > 0) {
       mbar_wait(acc_done, 0);
       tc_fence_after();
-      uint32_t ov[32];
-      tmem_ld_32x32b_x32(tDQ + lane_off + grp * 32, ov);
-      tmem_ld_wait();
-      if (row_ok) {
 #pragma unroll
-        for (int g4 = 0; g4 < 4; ++g4) {
-          uint4 o4;
-          o4.x = pack_bf16(__uint_as_float(ov[g4 * 8 + 0]) * p.scale, __uint_as_float(ov[g4 * 8 + 1]) * p.scale);
-          o4.y = pack_bf16(__uint_as_float(ov[g4 * 8 + 2]) * p.scale, __uint_as_float(ov[g4 * 8 + 3]) * p.scale);
-          o4.z = pack_bf16(__uint_as_float(ov[g4 * 8 + 4]) * p.scale, __uint_as_float(ov[g4 * 8 + 5]) * p.scale);
-          o4.w = pack_bf16(__uint_as_float(ov[g4 * 8 + 6]) * p.scale, __uint_as_float(ov[g4 * 8 + 7]) * p.scale);
-          *reinterpret_cast<uint4*>(dqp + g4 * 8) = o4;
+      for (int c = 0; c < 2; ++c) {
+        uint32_t ov[32];
+        tmem_ld_32x32b_x32(tDQ + lane_off + grp * 64 + c * 32, ov);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 o4;
+            o4.x = pack_bf16(__uint_as_float(ov[g * 8 + 0]) * p.scale, __uint_as_float(ov[g * 8 + 1]) * p.scale);
+            o4.y = pack_bf16(__uint_as_float(ov[g * 8 + 2]) * p.scale, __uint_as_float(ov[g * 8 + 3]) * p.scale);
+            o4.z = pack_bf16(__uint_as_float(ov[g * 8 + 4]) * p.scale, __uint_as_float(ov[g * 8 + 5]) * p.scale);
+            o4.w = pack_bf16(__uint_as_float(ov[g * 8 + 6]) * p.scale, __uint_as_float(ov[g * 8 + 7]) * p.scale);
+            *reinterpret_cast<uint4*>(dqp + c * 32 + g * 8) = o4;
+          }
         }
       }
     } else if (row_ok) {
       const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(dqp + c * 8) = z;
+      for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(dqp + c * 8) = z;
     }
   }
   tc_fence_before();
@@ -521,13 +532,13 @@ int mb200_attn_bwd_bf16(const void* q, const void* k, const void* v, const void*
   CUtensorMap tmQ, tmDO, tmK, tmV, tmQ64, tmDO64, tmK64, tmV64;
   int rc;
   if ((rc = make_tmap_bshd(&tmQ, q, B, Sq, H, hd, strides[0], strides[1], strides[2], 128))) return rc;
-  if ((rc = make_tmap_bshd(&tmQ64, q, B, Sq, H, hd, strides[0], strides[1], strides[2], SUB))) return rc;
+  if ((rc = make_tmap_bshd(&tmQ64, q, B, Sq, H, hd, strides[0], strides[1], strides[2], 64))) return rc;
   if ((rc = make_tmap_bshd(&tmDO, dout, B, Sq, H, hd, dq_sb, dq_ss, hd, 128))) return rc;
-  if ((rc = make_tmap_bshd(&tmDO64, dout, B, Sq, H, hd, dq_sb, dq_ss, hd, SUB))) return rc;
+  if ((rc = make_tmap_bshd(&tmDO64, dout, B, Sq, H, hd, dq_sb, dq_ss, hd, 64))) return rc;
   if ((rc = make_tmap_bshd(&tmK, k, B, Sk, Hkv, hd, strides[3], strides[4], strides[5], 128))) return rc;
-  if ((rc = make_tmap_bshd(&tmK64, k, B, Sk, Hkv, hd, strides[3], strides[4], strides[5], SUB))) return rc;
+  if ((rc = make_tmap_bshd(&tmK64, k, B, Sk, Hkv, hd, strides[3], strides[4], strides[5], 64))) return rc;
   if ((rc = make_tmap_bshd(&tmV, v, B, Sk, Hkv, hd, strides[6], strides[7], strides[8], 128))) return rc;
-  if ((rc = make_tmap_bshd(&tmV64, v, B, Sk, Hkv, hd, strides[6], strides[7], strides[8], SUB))) return rc;
+  if ((rc = make_tmap_bshd(&tmV64, v, B, Sk, Hkv, hd, strides[6], strides[7], strides[8], 64))) return rc;
   BwdParams p;
   p.ld = (const float2*)delta; p.Sq_pad = Sq_pad;
   p.dq = (bf16*)dq; p.dq_sb = dq_sb; p.dq_ss = dq_ss; p.dq_sh = hd;
@@ -535,8 +546,8 @@ int mb200_attn_bwd_bf16(const void* q, const void* k, const void* v, const void*
   p.dv = (bf16*)dv; p.dv_sb = dk_sb; p.dv_ss = dk_ss; p.dv_sh = hd;
   p.kbits = kmask ? (const uint32_t*)kbits : nullptr; p.kbits_stride = (Sk + 31) / 32;
   p.B = B; p.H = H; p.Hkv = Hkv; p.Sq = Sq; p.Sk = Sk; p.scale = scale; p.scale_log2 = scale * LOG2E; p.causal = causal;
-  constexpr int smem_dkv = 2 * FULL_TILE + 2 * QS * SUB_TILE + 1024 + 512 + QS * SUB * 8;
-  constexpr int smem_dq = 2 * FULL_TILE + 2 * QS * SUB_TILE + 1024 + 512;
+  constexpr int smem_dkv = 2 * FULL_TILE + 2 * QS * SUB_TILE + 1024 + 256 + QS * 512;
+  constexpr int smem_dq = 2 * FULL_TILE + 2 * QS * SUB_TILE + 1024 + 256;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(attn_bwd_dkv_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dkv) != cudaSuccess ||
