@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include "common.cuh"
 #include "sm100_ptx.cuh"
+#include "tmap.cuh"
 
 namespace {
 using namespace sm100;
@@ -475,33 +476,6 @@ attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, con
   }
 }
 
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static PFN_encodeTiled get_encode() {
-  static PFN_encodeTiled fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr; cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = (PFN_encodeTiled)ptr;
-  }
-  return fn;
-}
-static int make_tmap_bshd(CUtensorMap* tm, const void* base, int B, int S, int H, int hd, long long sb, long long ss,
-                          long long sh, int box_rows) {
-  PFN_encodeTiled enc = get_encode();
-  if (!enc) { mb200_set_last_error("cuTensorMapEncodeTiled unavailable"); return -ENOSYS; }
-  cuuint64_t dims[4] = {(cuuint64_t)hd, (cuuint64_t)H, (cuuint64_t)S, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)sh * 2, (cuuint64_t)ss * 2, (cuuint64_t)sb * 2};
-  cuuint32_t box[4] = {64, 1, (cuuint32_t)box_rows, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { mb200_set_last_error("cuTensorMapEncodeTiled (attention bwd) failed"); return -EINVAL; }
-  return 0;
-}
 }  // namespace
 
 extern "C" {
@@ -531,14 +505,14 @@ int mb200_attn_bwd_bf16(const void* q, const void* k, const void* v, const void*
   }
   CUtensorMap tmQ, tmDO, tmK, tmV, tmQ64, tmDO64, tmK64, tmV64;
   int rc;
-  if ((rc = make_tmap_bshd(&tmQ, q, B, Sq, H, hd, strides[0], strides[1], strides[2], 128))) return rc;
-  if ((rc = make_tmap_bshd(&tmQ64, q, B, Sq, H, hd, strides[0], strides[1], strides[2], 64))) return rc;
-  if ((rc = make_tmap_bshd(&tmDO, dout, B, Sq, H, hd, dq_sb, dq_ss, hd, 128))) return rc;
-  if ((rc = make_tmap_bshd(&tmDO64, dout, B, Sq, H, hd, dq_sb, dq_ss, hd, 64))) return rc;
-  if ((rc = make_tmap_bshd(&tmK, k, B, Sk, Hkv, hd, strides[3], strides[4], strides[5], 128))) return rc;
-  if ((rc = make_tmap_bshd(&tmK64, k, B, Sk, Hkv, hd, strides[3], strides[4], strides[5], 64))) return rc;
-  if ((rc = make_tmap_bshd(&tmV, v, B, Sk, Hkv, hd, strides[6], strides[7], strides[8], 128))) return rc;
-  if ((rc = make_tmap_bshd(&tmV64, v, B, Sk, Hkv, hd, strides[6], strides[7], strides[8], 64))) return rc;
+  if ((rc = mbtmap::make_bshd(&tmQ, q, B, Sq, H, hd, strides[0], strides[1], strides[2], 128))) return rc;
+  if ((rc = mbtmap::make_bshd(&tmQ64, q, B, Sq, H, hd, strides[0], strides[1], strides[2], 64))) return rc;
+  if ((rc = mbtmap::make_bshd(&tmDO, dout, B, Sq, H, hd, dq_sb, dq_ss, hd, 128))) return rc;
+  if ((rc = mbtmap::make_bshd(&tmDO64, dout, B, Sq, H, hd, dq_sb, dq_ss, hd, 64))) return rc;
+  if ((rc = mbtmap::make_bshd(&tmK, k, B, Sk, Hkv, hd, strides[3], strides[4], strides[5], 128))) return rc;
+  if ((rc = mbtmap::make_bshd(&tmK64, k, B, Sk, Hkv, hd, strides[3], strides[4], strides[5], 64))) return rc;
+  if ((rc = mbtmap::make_bshd(&tmV, v, B, Sk, Hkv, hd, strides[6], strides[7], strides[8], 128))) return rc;
+  if ((rc = mbtmap::make_bshd(&tmV64, v, B, Sk, Hkv, hd, strides[6], strides[7], strides[8], 64))) return rc;
   BwdParams p;
   p.ld = (const float2*)delta; p.Sq_pad = Sq_pad;
   p.dq = (bf16*)dq; p.dq_sb = dq_sb; p.dq_ss = dq_ss; p.dq_sh = hd;

@@ -16,6 +16,7 @@
 #include <stdlib.h>
 #include "common.cuh"
 #include "sm100_ptx.cuh"
+#include "tmap.cuh"
 
 namespace {
 using namespace sm100;
@@ -315,34 +316,6 @@ __global__ void kmask_bits_kernel(const int64_t* __restrict__ kmask, long long k
   if (lane == 0) bits[(size_t)b * words + w] = word;
 }
 
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static PFN_encodeTiled get_encode() {
-  static PFN_encodeTiled fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr; cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = (PFN_encodeTiled)ptr;
-  }
-  return fn;
-}
-// 4-D bf16 map over x[B, S, H, hd] (element strides sb, ss, sh; hd contiguous): dims (hd, H, S, B), box (64,1,rows,1)
-static int make_tmap_bshd(CUtensorMap* tm, const void* base, int B, int S, int H, int hd, long long sb, long long ss,
-                          long long sh, int box_rows) {
-  PFN_encodeTiled enc = get_encode();
-  if (!enc) { mb200_set_last_error("cuTensorMapEncodeTiled unavailable"); return -ENOSYS; }
-  cuuint64_t dims[4] = {(cuuint64_t)hd, (cuuint64_t)H, (cuuint64_t)S, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)sh * 2, (cuuint64_t)ss * 2, (cuuint64_t)sb * 2};
-  cuuint32_t box[4] = {64, 1, (cuuint32_t)box_rows, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { mb200_set_last_error("cuTensorMapEncodeTiled (attention) failed"); return -EINVAL; }
-  return 0;
-}
 }  // namespace
 
 extern "C" {
@@ -372,9 +345,9 @@ int mb200_attn_fwd_bf16(const void* q, const void* k, const void* v, void* o, fl
   cudaStream_t st = (cudaStream_t)stream;
   CUtensorMap tmQ, tmK, tmV;
   int rc;
-  if ((rc = make_tmap_bshd(&tmQ, q, B, Sq, H, hd, strides[0], strides[1], strides[2], BQ))) return rc;
-  if ((rc = make_tmap_bshd(&tmK, k, B, Sk, Hkv, hd, strides[3], strides[4], strides[5], BKV))) return rc;
-  if ((rc = make_tmap_bshd(&tmV, v, B, Sk, Hkv, hd, strides[6], strides[7], strides[8], BKV))) return rc;
+  if ((rc = mbtmap::make_bshd(&tmQ, q, B, Sq, H, hd, strides[0], strides[1], strides[2], BQ))) return rc;
+  if ((rc = mbtmap::make_bshd(&tmK, k, B, Sk, Hkv, hd, strides[3], strides[4], strides[5], BKV))) return rc;
+  if ((rc = mbtmap::make_bshd(&tmV, v, B, Sk, Hkv, hd, strides[6], strides[7], strides[8], BKV))) return rc;
   FwdParams p;
   p.o = (bf16*)o; p.lse = lse; p.o_sb = strides[9]; p.o_ss = strides[10]; p.o_sh = strides[11];
   p.kbits = nullptr; p.kbits_stride = 0;

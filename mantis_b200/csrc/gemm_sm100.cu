@@ -19,6 +19,7 @@
 // M/N/K tails are handled by TMA zero-fill on loads and predication on stores.
 #include "common.cuh"
 #include "sm100_ptx.cuh"
+#include "tmap.cuh"
 
 namespace {
 using namespace sm100;
@@ -210,35 +211,6 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 // ------------------------------------------------------------------ host side
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static PFN_encodeTiled get_encode() {
-  static PFN_encodeTiled fn = nullptr;
-  if (!fn) {
-    void* p = nullptr; cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = (PFN_encodeTiled)p;
-  }
-  return fn;
-}
-
-// 2-D bf16 tensor map over a row-major [rows, cols] matrix with leading dimension ld (elements).
-static int make_tmap_2d(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld,
-                        int box_cols, int box_rows) {
-  PFN_encodeTiled enc = get_encode();
-  if (!enc) { mb200_set_last_error("cuTensorMapEncodeTiled unavailable"); return -ENOSYS; }
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { mb200_set_last_error("cuTensorMapEncodeTiled failed"); return -EINVAL; }
-  return 0;
-}
 
 template <int BN, int STAGES, bool A_MN, bool B_MN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpi& epi, int M, int N, int K,
@@ -283,11 +255,11 @@ int mb200_gemm_bf16(const void* A, const void* B, void* C, const void* bias, con
   const int BN = (N > 128) ? 256 : 128;
   CUtensorMap tmA, tmB;
   int rc;
-  if (!transA) rc = make_tmap_2d(&tmA, A, M, K, lda, BK, BM);        // [M,K]: box 64(K) x 128(M)
-  else         rc = make_tmap_2d(&tmA, A, K, M, lda, 64, BK);        // [K,M]: box 64(M) x 64(K)
+  if (!transA) rc = mbtmap::make_2d(&tmA, A, M, K, lda, BK, BM);        // [M,K]: box 64(K) x 128(M)
+  else         rc = mbtmap::make_2d(&tmA, A, K, M, lda, 64, BK);        // [K,M]: box 64(M) x 64(K)
   if (rc) return rc;
-  if (transB)  rc = make_tmap_2d(&tmB, B, N, K, ldb, BK, BN);        // [N,K]: box 64(K) x BN
-  else         rc = make_tmap_2d(&tmB, B, K, N, ldb, 64, BK);        // [K,N]: box 64(N) x 64(K)
+  if (transB)  rc = mbtmap::make_2d(&tmB, B, N, K, ldb, BK, BN);        // [N,K]: box 64(K) x BN
+  else         rc = mbtmap::make_2d(&tmB, B, K, N, ldb, 64, BK);        // [K,N]: box 64(N) x 64(K)
   if (rc) return rc;
   GemmEpi epi;
   epi.C = (bf16*)C; epi.ldc = ldc; epi.bias = (const bf16*)bias; epi.addend = (const bf16*)addend;

@@ -5,6 +5,7 @@
 // 0-127 in CTA0's TMEM and rows 128-255 in CTA1's.  Same epilogue / majorness options as gemm_sm100.cu.
 #include "common.cuh"
 #include "sm100_ptx.cuh"
+#include "tmap.cuh"
 
 namespace {
 using namespace sm100;
@@ -193,33 +194,6 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc_2cta(tmem_base, TMEM_COLS); }
 }
 
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static PFN_encodeTiled get_encode() {
-  static PFN_encodeTiled fn = nullptr;
-  if (!fn) {
-    void* p = nullptr; cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = (PFN_encodeTiled)p;
-  }
-  return fn;
-}
-static int make_tmap_2d(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld,
-                        int box_cols, int box_rows) {
-  PFN_encodeTiled enc = get_encode();
-  if (!enc) { mb200_set_last_error("cuTensorMapEncodeTiled unavailable"); return -ENOSYS; }
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { mb200_set_last_error("cuTensorMapEncodeTiled failed"); return -EINVAL; }
-  return 0;
-}
 
 template <bool A_MN, bool B_MN>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpi& epi, int M, int N, int K, cudaStream_t st) {
@@ -249,9 +223,9 @@ extern "C" int mb200_gemm_bf16_2cta(const void* A, const void* B, void* C, const
     return -ENOTSUP;
   CUtensorMap tmA, tmB;
   int rc;
-  if (!transA) rc = make_tmap_2d(&tmA, A, M, K, lda, BK, BM); else rc = make_tmap_2d(&tmA, A, K, M, lda, 64, BK);
+  if (!transA) rc = mbtmap::make_2d(&tmA, A, M, K, lda, BK, BM); else rc = mbtmap::make_2d(&tmA, A, K, M, lda, 64, BK);
   if (rc) return rc;
-  if (transB) rc = make_tmap_2d(&tmB, B, N, K, ldb, BK, BN_HALF); else rc = make_tmap_2d(&tmB, B, K, N, ldb, 64, BK);
+  if (transB) rc = mbtmap::make_2d(&tmB, B, N, K, ldb, BK, BN_HALF); else rc = mbtmap::make_2d(&tmB, B, K, N, ldb, 64, BK);
   if (rc) return rc;
   GemmEpi epi;
   epi.C = (bf16*)C; epi.ldc = ldc; epi.bias = (const bf16*)bias; epi.addend = (const bf16*)addend; epi.ld_add = ld_add; epi.act = act;
