@@ -157,3 +157,47 @@ def test_native_decode_engine_matches_python_path(cuda):
     assert used_a and not used_b
     for x, y in zip(a, b):
         assert rel_err(x, y) < 3e-2, rel_err(x, y)
+
+
+def test_fullwidth_bf16_tensor_core_path_vs_fp32_simt_path(cuda):
+    """Full-width (d=4096, 32q/8kv x 128, ff 14336, SigLIP d=1152 / head_dim 72) one-layer model: the bf16 run goes through
+    the tcgen05 GEMM (1- and 2-CTA), the tcgen05 attention fwd+bwd, the padded-head ViT path and the fused LM-head/CE;
+    the fp32 run of the SAME weights goes through the SIMT kernels.  They must agree to bf16 rounding."""
+    from transformers import LlamaConfig, SiglipVisionConfig
+    from mantis_b200.models.mllava import LlavaConfig, LlavaForConditionalGeneration
+    vc = SiglipVisionConfig(hidden_size=1152, intermediate_size=4304, num_hidden_layers=2, num_attention_heads=16,
+                            image_size=112, patch_size=14, hidden_act="gelu_pytorch_tanh", layer_norm_eps=1e-6)
+    tc = LlamaConfig(hidden_size=4096, intermediate_size=14336, num_hidden_layers=1, num_attention_heads=32,
+                     num_key_value_heads=8, vocab_size=2048, rms_norm_eps=1e-5, rope_theta=500000.0)
+    cfg = LlavaConfig(vision_config=vc, text_config=tc, image_token_index=2040, pad_token_id=2041, vocab_size=2048,
+                      vision_feature_select_strategy="full")
+    torch.manual_seed(0)
+    m16 = LlavaForConditionalGeneration(cfg).to(cuda).to(torch.bfloat16)
+    m32 = LlavaForConditionalGeneration(cfg).to(cuda)
+    m32.load_state_dict({k: v.float() for k, v in m16.state_dict().items()})
+    for m in (m16, m32):
+        for n, p in m.named_parameters():
+            if "vision_tower" in n:
+                p.requires_grad_(False)
+        m.train()
+    ids = torch.randint(0, 2000, (1, 700), device=cuda)
+    ids[0, 5] = 2040; ids[0, 300] = 2040; ids[0, 301] = 2040
+    labels = ids.clone(); labels[ids == 2040] = -100
+    pv = torch.randn(3, 3, 112, 112, device=cuda)
+    outs = []
+    for m, dt in ((m16, torch.bfloat16), (m32, torch.float32)):
+        out = m(input_ids=ids, pixel_values=pv.to(dt), attention_mask=torch.ones_like(ids), labels=labels)
+        out.loss.backward()
+        outs.append(out)
+    assert abs(outs[0].loss.item() - outs[1].loss.item()) < 3e-2, (outs[0].loss.item(), outs[1].loss.item())
+    p16, p32 = dict(m16.named_parameters()), dict(m32.named_parameters())
+    for k in ["language_model.model.layers.0.self_attn.q_proj.weight", "language_model.model.layers.0.self_attn.v_proj.weight",
+              "language_model.model.layers.0.mlp.down_proj.weight", "language_model.lm_head.weight",
+              "multi_modal_projector.linear_1.weight", "language_model.model.layers.0.input_layernorm.weight"]:
+        e = rel_err(p16[k].grad, p32[k].grad)
+        assert e < 5e-2, (k, e)
+    m16.eval(); m32.eval()
+    with torch.no_grad():
+        l16 = m16(input_ids=ids, pixel_values=pv.bfloat16(), attention_mask=torch.ones_like(ids)).logits
+        l32 = m32(input_ids=ids, pixel_values=pv, attention_mask=torch.ones_like(ids)).logits
+    assert rel_err(l16, l32) < 3e-2, rel_err(l16, l32)
