@@ -119,6 +119,82 @@ skinny_gemm_kernel(const bf16* __restrict__ X, SkinnySeg sg, const bf16* __restr
   }
 }
 
+// ------------------------------------------------------------------ skinny GEMM, 8 < M <= 16: mma.sync m16n8k16
+// At M = 16 the SIMT kernel above is FMA-bound (16 FMAs per weight element); here one warp owns 8 output rows and the
+// batch rows form the M = 16 side of an HMMA tile, so the kernel is HBM-bound again.  K is consumed 32 elements per lane
+// group at a time with 16-byte loads: the dot product does not care about the order of k, so lane `tid` simply feeds
+// memory elements [8 tid, 8 tid + 8) of every 32-chunk to the fragment slots of two consecutive k16 steps -- for A (X)
+// and B (W) alike.  (tcgen05 is not used here: a 128-row MMA tile with 16 useful rows buys nothing for an HBM-bound op,
+// and mma.sync needs no TMEM / TMA setup per launch.)
+__device__ __forceinline__ void mma_16816(float* c, const uint32_t a0, const uint32_t a1, const uint32_t a2, const uint32_t a3,
+                                          const uint32_t b0, const uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int KU>
+__global__ void __launch_bounds__(128)
+skinny_mma_kernel(const bf16* __restrict__ X, SkinnySeg sg, const bf16* __restrict__ bias, const bf16* __restrict__ addend,
+                  int M, int K, long long ldx, long long ldw, long long ld_add) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gid = lane >> 2, tid = lane & 3;
+  const int Ntot = (sg.mode == 1) ? sg.N[0] : (sg.N[0] + sg.N[1] + sg.N[2]);
+  const int n0 = (blockIdx.x * 4 + warp) * 8;
+  if (n0 >= Ntot) return;
+  int n = n0 + gid; if (n >= Ntot) n = Ntot - 1;
+  const bf16 *w0, *w1;
+  if (sg.mode == 1) { w0 = sg.W[0] + (size_t)n * ldw; w1 = sg.W[1] + (size_t)n * ldw; }
+  else {
+    int seg = 0, nn = n;
+    if (nn >= sg.N[0]) { nn -= sg.N[0]; seg = 1; if (nn >= sg.N[1]) { nn -= sg.N[1]; seg = 2; } }
+    w0 = sg.W[seg] + (size_t)nn * ldw; w1 = w0;
+  }
+  const bf16* xlo = X + (size_t)gid * ldx;            // batch row gid
+  const bf16* xhi = X + (size_t)(gid + 8) * ldx;      // batch row gid + 8
+  const bool lo_ok = gid < M, hi_ok = gid + 8 < M;
+  float c[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
+  const int4 z = make_int4(0, 0, 0, 0);
+  for (int k = tid * 8; k < K; k += 32 * KU) {
+    int4 wv[KU], wv2[KU], xl[KU], xh[KU];
+#pragma unroll
+    for (int u = 0; u < KU; ++u) {
+      const int kk = k + u * 32;
+      const bool ok = kk < K;
+      wv[u] = ok ? mb::ld_stream(reinterpret_cast<const int4*>(w0 + kk)) : z;
+      if (sg.mode == 1) wv2[u] = ok ? mb::ld_stream(reinterpret_cast<const int4*>(w1 + kk)) : z;
+      xl[u] = (ok && lo_ok) ? *reinterpret_cast<const int4*>(xlo + kk) : z;
+      xh[u] = (ok && hi_ok) ? *reinterpret_cast<const int4*>(xhi + kk) : z;
+    }
+#pragma unroll
+    for (int u = 0; u < KU; ++u) {
+      mma_16816(c, xl[u].x, xh[u].x, xl[u].y, xh[u].y, wv[u].x, wv[u].y);
+      mma_16816(c, xl[u].z, xh[u].z, xl[u].w, xh[u].w, wv[u].z, wv[u].w);
+      if (sg.mode == 1) {
+        mma_16816(c2, xl[u].x, xh[u].x, xl[u].y, xh[u].y, wv2[u].x, wv2[u].y);
+        mma_16816(c2, xl[u].z, xh[u].z, xl[u].w, xh[u].w, wv2[u].z, wv2[u].w);
+      }
+    }
+  }
+  // c[0], c[1]: (row gid, cols n0 + 2 tid, +1) ; c[2], c[3]: (row gid + 8, same cols)
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int m = gid + ((e >> 1) ? 8 : 0);
+    const int nn_abs = n0 + tid * 2 + (e & 1);
+    if (m >= M || nn_abs >= Ntot) continue;
+    int seg = 0, nn = nn_abs;
+    if (sg.mode != 1 && nn >= sg.N[0]) { nn -= sg.N[0]; seg = 1; if (nn >= sg.N[1]) { nn -= sg.N[1]; seg = 2; } }
+    float v = c[e] + ((bias && seg == 0) ? __bfloat162float(bias[nn]) : 0.f);
+    if (sg.mode == 1) {
+      const float gq = __bfloat162float(__float2bfloat16_rn(v));
+      const float uq = __bfloat162float(__float2bfloat16_rn(c2[e]));
+      const float sl = __bfloat162float(__float2bfloat16_rn(gq / (1.f + __expf(-gq))));
+      v = sl * uq;
+    }
+    if (addend && seg == 0) v += __bfloat162float(addend[(size_t)m * ld_add + nn]);
+    sg.C[seg][(size_t)m * sg.ldc[seg] + nn] = __float2bfloat16_rn(v);
+  }
+}
+
 // ------------------------------------------------------------------ KV append
 // k_new/v_new: [B, Hkv*hd] rows (row stride ld_new) -> cache[b, pos[b], :, :]  (cache: [B, cap, Hkv*hd])
 __global__ void __launch_bounds__(256)
@@ -306,6 +382,13 @@ int launch_skinny(const void* X, const SkinnySeg& sg, const void* bias, const vo
 }
 int dispatch_skinny(const void* X, const SkinnySeg& sg, const void* bias, const void* addend, int M, int K, long long ldx,
                     long long ldw, long long ld_add, cudaStream_t st) {
+  if (M > 8 && (K % 32) == 0) {           // tensor-core (mma.sync) variant: HBM-bound instead of FMA-bound
+    const int Ntot = (sg.mode == 1) ? sg.N[0] : (sg.N[0] + sg.N[1] + sg.N[2]);
+    const int grid = (Ntot + 31) / 32;
+    if (sg.mode == 1) skinny_mma_kernel<2><<<grid, 128, 0, st>>>((const bf16*)X, sg, (const bf16*)bias, (const bf16*)addend, M, K, ldx, ldw, ld_add);
+    else              skinny_mma_kernel<4><<<grid, 128, 0, st>>>((const bf16*)X, sg, (const bf16*)bias, (const bf16*)addend, M, K, ldx, ldw, ld_add);
+    return 0;
+  }
   if (M == 1) return launch_skinny<1>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
   if (M == 2) return launch_skinny<2>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
   if (M <= 4) return launch_skinny<4>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
