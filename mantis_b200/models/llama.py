@@ -23,6 +23,11 @@ except Exception:  # pragma: no cover
     LlamaConfig = MistralConfig = None
 
 
+def _plain(*mods):
+    """True if every module is an unwrapped, bias-free B200Linear (so its weight can be used directly)"""
+    return all(type(m) is B200Linear and m.bias is None for m in mods)
+
+
 def _rope_params(config):
     theta = getattr(config, "rope_theta", None)
     rs = getattr(config, "rope_scaling", None)
@@ -53,9 +58,13 @@ class B200Attention(nn.Module):
 
     def forward(self, x, residual, position_ids, inv_freq, rope_scale, key_mask, cache, kbits=None):
         B, S, _ = x.shape
-        q = self.q_proj(x).view(B, S, self.num_heads, self.head_dim)
-        k = self.k_proj(x).view(B, S, self.num_kv_heads, self.head_dim)
-        v = self.v_proj(x).view(B, S, self.num_kv_heads, self.head_dim)
+        if _plain(self.q_proj, self.k_proj, self.v_proj):
+            q, k, v = ops.multi_linear(x, self.q_proj.weight, self.k_proj.weight, self.v_proj.weight)
+        else:                                  # biased or wrapped (peft LoRA) projections: go through the modules
+            q, k, v = self.q_proj(x), self.k_proj(x), self.v_proj(x)
+        q = q.view(B, S, self.num_heads, self.head_dim)
+        k = k.view(B, S, self.num_kv_heads, self.head_dim)
+        v = v.view(B, S, self.num_kv_heads, self.head_dim)
         q, k = ops.rope(q, k, position_ids, inv_freq, rope_scale)
         if cache is not None:
             k, v = cache.append(k, v, self.layer_idx)
@@ -76,7 +85,11 @@ class B200MLP(nn.Module):
         self.down_proj = B200Linear(config.intermediate_size, config.hidden_size, bias=bias)
 
     def forward(self, x, residual=None):
-        return self.down_proj(ops.swiglu(self.gate_proj(x), self.up_proj(x)), residual=residual)
+        if _plain(self.gate_proj, self.up_proj):
+            g, u = ops.multi_linear(x, self.gate_proj.weight, self.up_proj.weight)
+        else:
+            g, u = self.gate_proj(x), self.up_proj(x)
+        return self.down_proj(ops.swiglu(g, u), residual=residual)
 
 
 class B200DecoderLayer(nn.Module):

@@ -176,6 +176,51 @@ class _LinearFn(torch.autograd.Function):
         return gx, gw, gb, None, gres
 
 
+class _MultiLinearFn(torch.autograd.Function):
+    """(x W1^T, x W2^T[, x W3^T]) for bias-free projections that share their input (q/k/v, gate/up).  Same GEMMs as separate
+    linears in forward; in backward the input gradient is accumulated inside the dgrad epilogues (dx = g1 W1; dx += g2 W2;
+    ...) instead of autograd summing three tensors with extra elementwise passes."""
+
+    @staticmethod
+    def forward(ctx, x, *weights):
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1])
+        if x2.stride(1) != 1:
+            x2 = x2.contiguous()
+        ctx.save_for_backward(x2, *weights)
+        ctx.wrefs = [w if getattr(w, "_b200_fused_grad", False) else None for w in weights]
+        ctx.in_shape = shp
+        return tuple(gemm(x2, w).reshape(*shp[:-1], w.shape[0]) for w in weights)
+
+    @staticmethod
+    def backward(ctx, *gys):
+        x2, *weights = ctx.saved_tensors
+        gx = None
+        gws = []
+        for i, (w, gy) in enumerate(zip(weights, gys)):
+            g2 = gy.reshape(-1, w.shape[0])
+            if g2.stride(1) != 1:
+                g2 = g2.contiguous()
+            if ctx.needs_input_grad[0]:
+                if gx is None:
+                    gx = gemm(g2, w, trans_a=False, trans_b=False)
+                else:
+                    gemm(g2, w, trans_a=False, trans_b=False, addend=gx, out=gx)
+            gw = None
+            if ctx.needs_input_grad[1 + i]:
+                wref = ctx.wrefs[i]
+                if wref is not None and wref.grad is not None and wref.grad.is_contiguous():
+                    gemm(g2, x2, trans_a=True, trans_b=False, addend=wref.grad, out=wref.grad)
+                else:
+                    gw = gemm(g2, x2, trans_a=True, trans_b=False)
+            gws.append(gw)
+        return (gx.reshape(ctx.in_shape) if gx is not None else None, *gws)
+
+
+def multi_linear(x, *weights):
+    return _MultiLinearFn.apply(x, *weights)
+
+
 def linear(x, weight, bias=None, act=None, residual=None):
     """y = act(x @ weight^T + bias) + residual  (weight in nn.Linear [out, in] layout)"""
     return _LinearFn.apply(x, weight, bias, act, residual)

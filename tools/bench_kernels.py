@@ -129,6 +129,49 @@ def bench_rowwise():
     report("ce_fwd_bwd chunk [4096,128258]", ms, bytes_=2 * n * V * 2, note="algorithmic = 1 read + 1 write")
 
 
+def bench_decode():
+    """decode-step kernels at bs = 1 and 16 (weights cycled so each launch streams from HBM)"""
+    import ctypes
+    from mantis_b200 import _lib
+    L = _lib.lib()
+    for B in (1, 16):
+        nset = 4
+        x = torch.randn(B, 4096, device=dev).bfloat16(); xi = torch.randn(B, 14336, device=dev).bfloat16()
+        wq = [(torch.randn(4096, 4096, device=dev) * 0.02).bfloat16() for _ in range(nset)]
+        wk = [(torch.randn(1024, 4096, device=dev) * 0.02).bfloat16() for _ in range(nset)]
+        wv = [(torch.randn(1024, 4096, device=dev) * 0.02).bfloat16() for _ in range(nset)]
+        wg = [(torch.randn(14336, 4096, device=dev) * 0.02).bfloat16() for _ in range(nset)]
+        wu = [(torch.randn(14336, 4096, device=dev) * 0.02).bfloat16() for _ in range(nset)]
+        wd = [(torch.randn(4096, 14336, device=dev) * 0.02).bfloat16() for _ in range(nset)]
+        q = torch.empty(B, 4096, device=dev, dtype=torch.bfloat16); k = torch.empty(B, 1024, device=dev, dtype=torch.bfloat16)
+        v = torch.empty_like(k); act = torch.empty(B, 14336, device=dev, dtype=torch.bfloat16)
+        st = ops._st
+        ms = timeit(lambda i: ops._call("mb200_skinny_gemm3_bf16", ops._p(x), ops._p(wq[i % nset]), ops._p(wk[i % nset]), ops._p(wv[i % nset]),
+                                        ops._p(q), ops._p(k), ops._p(v), B, 4096, 1024, 1024, 4096, 4096, 4096, st()), reps=20)
+        report(f"decode qkv skinny gemm bs={B}", ms, bytes_=6144 * 4096 * 2)
+        ms = timeit(lambda i: ops._call("mb200_skinny_swiglu_bf16", ops._p(x), ops._p(wg[i % nset]), ops._p(wu[i % nset]), ops._p(act),
+                                        B, 14336, 4096, 4096, 4096, 14336, st()), reps=20)
+        report(f"decode gate/up + swiglu bs={B}", ms, bytes_=2 * 14336 * 4096 * 2)
+        ms = timeit(lambda i: ops._call("mb200_skinny_gemm_bf16", ops._p(xi), ops._p(wd[i % nset]), ops._p(q), None, ops._p(q), B, 4096, 14336,
+                                        14336, 14336, 4096, 4096, st()), reps=20)
+        report(f"decode down proj (+residual) bs={B}", ms, bytes_=4096 * 14336 * 2)
+        del wq, wk, wv, wg, wu, wd
+        wl = (torch.randn(128258, 4096, device=dev) * 0.02).bfloat16()
+        lg = torch.empty(B, 128264, device=dev, dtype=torch.bfloat16)
+        ms = timeit(lambda i: ops._call("mb200_skinny_gemm_bf16", ops._p(x), ops._p(wl), ops._p(lg), None, None, B, 128258, 4096, 4096, 4096,
+                                        128264, 0, st()), reps=5)
+        report(f"decode lm_head bs={B}", ms, bytes_=128258 * 4096 * 2)
+        del wl
+        ctx = 6200
+        qd = torch.randn(B, 1, 32, 128, device=dev).bfloat16()
+        kc = torch.randn(B, ctx, 8, 128, device=dev).bfloat16(); vc = torch.randn(B, ctx, 8, 128, device=dev).bfloat16()
+        ms = timeit(lambda i: ops.decode_attention(qd, kc, vc, ctx, None, 128 ** -0.5), reps=20)
+        report(f"decode attention ctx={ctx} bs={B}", ms, bytes_=2.0 * B * ctx * 8 * 128 * 2)
+        xr = torch.randn(B, 4096, device=dev).bfloat16(); w = torch.ones(4096, device=dev).bfloat16()
+        ms = timeit(lambda i: ops.rms_norm(xr, w, 1e-5), reps=50)
+        report(f"decode rmsnorm bs={B} (launch-latency bound)", ms, bytes_=2 * B * 4096 * 2)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "attn", "row"]
     if "gemm" in which:
@@ -137,3 +180,5 @@ if __name__ == "__main__":
         bench_attention()
     if "row" in which:
         bench_rowwise()
+    if "decode" in which:
+        bench_decode()
