@@ -136,11 +136,11 @@ template <int KU>
 __global__ void __launch_bounds__(128)
 skinny_mma_kernel(const bf16* __restrict__ X, SkinnySeg sg, const bf16* __restrict__ bias, const bf16* __restrict__ addend,
                   int M, int K, long long ldx, long long ldw, long long ld_add) {
+  __shared__ float red[3][32][8];           // partial accumulators of warps 1..3 (K is split across the 4 warps of a CTA)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gid = lane >> 2, tid = lane & 3;
   const int Ntot = (sg.mode == 1) ? sg.N[0] : (sg.N[0] + sg.N[1] + sg.N[2]);
-  const int n0 = (blockIdx.x * 4 + warp) * 8;
-  if (n0 >= Ntot) return;
+  const int n0 = blockIdx.x * 8;
   int n = n0 + gid; if (n >= Ntot) n = Ntot - 1;
   const bf16 *w0, *w1;
   if (sg.mode == 1) { w0 = sg.W[0] + (size_t)n * ldw; w1 = sg.W[1] + (size_t)n * ldw; }
@@ -154,7 +154,7 @@ skinny_mma_kernel(const bf16* __restrict__ X, SkinnySeg sg, const bf16* __restri
   const bool lo_ok = gid < M, hi_ok = gid + 8 < M;
   float c[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
   const int4 z = make_int4(0, 0, 0, 0);
-  for (int k = tid * 8; k < K; k += 32 * KU) {
+  for (int k = (warp * KU) * 32 + tid * 8; k < K; k += 4 * 32 * KU) {
     int4 wv[KU], wv2[KU], xl[KU], xh[KU];
 #pragma unroll
     for (int u = 0; u < KU; ++u) {
@@ -175,6 +175,16 @@ skinny_mma_kernel(const bf16* __restrict__ X, SkinnySeg sg, const bf16* __restri
       }
     }
   }
+  if (warp > 0) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { red[warp - 1][lane][e] = c[e]; red[warp - 1][lane][4 + e] = c2[e]; }
+  }
+  __syncthreads();
+  if (warp > 0) return;
+#pragma unroll
+  for (int w = 0; w < 3; ++w)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { c[e] += red[w][lane][e]; c2[e] += red[w][lane][4 + e]; }
   // c[0], c[1]: (row gid, cols n0 + 2 tid, +1) ; c[2], c[3]: (row gid + 8, same cols)
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
@@ -384,7 +394,7 @@ int dispatch_skinny(const void* X, const SkinnySeg& sg, const void* bias, const 
                     long long ldw, long long ld_add, cudaStream_t st) {
   if (M > 8 && (K % 32) == 0) {           // tensor-core (mma.sync) variant: HBM-bound instead of FMA-bound
     const int Ntot = (sg.mode == 1) ? sg.N[0] : (sg.N[0] + sg.N[1] + sg.N[2]);
-    const int grid = (Ntot + 31) / 32;
+    const int grid = (Ntot + 7) / 8;
     if (sg.mode == 1) skinny_mma_kernel<2><<<grid, 128, 0, st>>>((const bf16*)X, sg, (const bf16*)bias, (const bf16*)addend, M, K, ldx, ldw, ld_add);
     else              skinny_mma_kernel<4><<<grid, 128, 0, st>>>((const bf16*)X, sg, (const bf16*)bias, (const bf16*)addend, M, K, ldx, ldw, ld_add);
     return 0;
@@ -466,7 +476,7 @@ int mb200_rope_append_bf16(const void* q, const void* k, const void* v, void* q_
   return MB200_OK;
 }
 
-int mb200_decode_attn_splits(int ctx) { int s = (ctx + 255) / 256; if (s < 1) s = 1; if (s > 64) s = 64; return s; }
+int mb200_decode_attn_splits(int ctx) { int s = (ctx + 127) / 128; if (s < 1) s = 1; if (s > 64) s = 64; return s; }
 
 // q [B,H,128] (strides q_sb,q_sh), cache k/v [B,cap,Hkv,128] (strides kv_sb, kv_ss, kv_sh), o [B,H,128].
 // part: fp32 scratch of B*H*splits*(130) floats with splits = mb200_decode_attn_splits(ctx).
