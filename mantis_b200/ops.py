@@ -664,45 +664,79 @@ def shift_labels(labels, attention_mask, ignore_index=-100):
 LM_HEAD_CHUNK = int(os.environ.get("MB200_LM_HEAD_CHUNK", "4096"))
 
 
+LM_HEAD_SKIP_IGNORED = os.environ.get("MB200_LMHEAD_SKIP_IGNORED", "1") == "1"
+
+
+def gather_rows(x2, idx):
+    """out[i, :] = x2[idx[i], :]  (row gather on the embedding kernel)"""
+    n, D = idx.numel(), x2.shape[1]
+    out = torch.empty((n, D), dtype=x2.dtype, device=x2.device)
+    if n:
+        _call("mb200_embedding_fwd", _p(idx), _p(x2), _p(out), n, D, x2.shape[0], _dt(x2), _st())
+    return out
+
+
 class _LMHeadCEFn(torch.autograd.Function):
     """Fused LM head + shifted masked cross-entropy: logits are produced chunk by chunk, consumed by the CE kernel
     (which overwrites them with dlogits), and immediately folded into d(hidden) and d(W) -- the [B,S,V] logits
-    tensor (8 GB at Mantis-8B scale) is never materialised.  loss = sum_rows(lse - logit[target]) / n_valid."""
+    tensor (8 GB at Mantis-8B scale) is never materialised.  loss = sum_rows(lse - logit[target]) / n_valid.
+
+    Rows whose effective label is ignored (image slots, prompt tokens, padding: the reference gathers them away *after*
+    computing their logits, modeling_llava.py:526-531) contribute neither to the loss nor to any gradient, so they are
+    compacted away *before* the LM-head GEMMs (LM_HEAD_SKIP_IGNORED): identical loss / gradients, fewer FLOPs."""
 
     @staticmethod
     def forward(ctx, hidden, weight, eff_labels, count):
         h2 = hidden.reshape(-1, hidden.shape[-1])
         if h2.stride(1) != 1:
             h2 = h2.contiguous()
-        n, D = h2.shape
+        n_all, D = h2.shape
         V = weight.shape[0]
         lab = eff_labels.reshape(-1)
         dev = h2.device
         need_h, need_w = hidden.requires_grad, weight.requires_grad
+        idx = None
+        if LM_HEAD_SKIP_IGNORED:
+            idx = (lab >= 0).nonzero(as_tuple=False).squeeze(1)       # one host sync (row count)
+            if idx.numel() == n_all:
+                idx = None
+        if idx is not None:
+            hsrc = gather_rows(h2, idx)
+            lsrc = lab.index_select(0, idx)
+        else:
+            hsrc, lsrc = h2, lab
+        n = hsrc.shape[0]
         ld = (V + 7) // 8 * 8
         acc = torch.zeros((2,), dtype=torch.float32, device=dev)
         inv = (1.0 / count).to(torch.float32)                # device scalar: dlogits scale (mean over valid rows)
-        dh = torch.empty_like(h2) if need_h else None
+        dh = torch.empty_like(hsrc) if need_h else None
         dw = None
-        chunk = min(LM_HEAD_CHUNK, n)
+        chunk = max(1, min(LM_HEAD_CHUNK, n))
         buf = torch.empty((chunk, ld), dtype=h2.dtype, device=dev)
         loss_rows = torch.empty((chunk,), dtype=torch.float32, device=dev)
         for r0 in range(0, n, chunk):
             r1 = min(n, r0 + chunk)
             m = r1 - r0
             logits = buf[:m, :V]
-            gemm(h2[r0:r1], weight, out=logits)
-            _call("mb200_ce_fwd_bwd", _p(logits), _p(lab[r0:r1]), _p(loss_rows), None,
+            gemm(hsrc[r0:r1], weight, out=logits)
+            _call("mb200_ce_fwd_bwd", _p(logits), _p(lsrc[r0:r1]), _p(loss_rows), None,
                   _p(logits) if (need_h or need_w) else None, m, V, ld, _p(inv), 1.0, _dt(h2), _st())
-            _call("mb200_ce_reduce", _p(loss_rows), _p(lab[r0:r1]), m, V, _p(acc), 1, _st())
+            _call("mb200_ce_reduce", _p(loss_rows), _p(lsrc[r0:r1]), m, V, _p(acc), 1, _st())
             if need_h:
                 gemm(logits, weight, trans_a=False, trans_b=False, out=dh[r0:r1])
             if need_w:
                 if dw is None:
-                    dw = gemm(logits, h2[r0:r1], trans_a=True, trans_b=False)
+                    dw = gemm(logits, hsrc[r0:r1], trans_a=True, trans_b=False)
                 else:
-                    gemm(logits, h2[r0:r1], trans_a=True, trans_b=False, addend=dw, out=dw)
-        loss = (acc[0] / acc[1]).to(hidden.dtype if hidden.dtype == torch.float32 else torch.float32)
+                    gemm(logits, hsrc[r0:r1], trans_a=True, trans_b=False, addend=dw, out=dw)
+        if need_w and dw is None:
+            dw = torch.zeros_like(weight)
+        if need_h and idx is not None:                       # scatter the compacted rows back (others get zero gradient)
+            full = torch.zeros((n_all, D), dtype=dh.dtype, device=dev)
+            if n:
+                _call("mb200_embedding_bwd", _p(idx), _p(dh), _p(full), n, D, n_all, _dt(dh), _st())
+            dh = full
+        loss = acc[0] / acc[1]
         ctx.save_for_backward(dh, dw)
         ctx.shape = hidden.shape
         return loss
