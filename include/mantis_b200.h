@@ -131,6 +131,12 @@ int mb200_attn_fwd_bf16(const void* q, const void* k, const void* v, void* o, fl
                         int Sk, int hd, const long long* strides, float scale, int causal, const int64_t* kmask,
                         long long kmask_sb, void* kbits_ws, void* stream);
 
+/* two-query-tiles-per-CTA variant of mb200_attn_fwd_bf16 (tiles ping-pong on the tensor pipe and share K/V loads);
+ * kbits = bitmask from mb200_kmask_bits (NULL = no key padding mask) */
+int mb200_attn_fwd2_bf16(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Hkv, int Sq,
+                         int Sk, int hd, const long long* strides, float scale, int causal, const void* kbits,
+                         int kbits_stride, void* stream);
+
 /* tcgen05 flash attention backward (dK/dV kernel + dQ kernel, deterministic, no atomics).  dq/dk/dv/dout contiguous;
  * kbits = the bitmask scratch filled by mb200_attn_fwd_bf16 for the same kmask (NULL iff kmask == NULL);
  * delta = fp32 scratch of 2 * B * H * mb200_attn_bwd_sq_pad(Sq) floats. */

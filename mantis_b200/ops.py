@@ -443,6 +443,7 @@ def _strides12(q, k, v, o):
 
 
 FAST_ATTN_MIN_SQ = int(os.environ.get("MB200_FAST_ATTN_MIN_SQ", "64"))
+ATTN_FWD2 = os.environ.get("MB200_ATTN_FWD2", "0") == "1"      # two query tiles per CTA (ping-pong) forward kernel
 
 
 def _attn_fast_ok(q, k, v, hd, Sq, Sk):
@@ -468,6 +469,14 @@ def attention_fwd(q, k, v, causal, kmask, scale, return_kbits=False):
     st = _strides12(q, k, v, o)
     if _attn_fast_ok(q, k, v, hd, Sq, Sk):
         kbits = None
+        if ATTN_FWD2 and Sq > 128:
+            if kmask is not None:
+                kbits = kmask_bits(kmask).reshape(-1)
+            _call("mb200_attn_fwd2_bf16", _p(q), _p(k), _p(v), _p(o), _p(lse), B, H, Hkv, Sq, Sk, hd, st, float(scale),
+                  int(causal), _p(kbits), (Sk + 31) // 32 if kmask is not None else 0, _st())
+            if return_kbits:
+                return o, lse, kbits, True
+            return o, lse
         if kmask is not None:
             kbits = torch.empty((B * ((Sk + 31) // 32),), dtype=torch.int32, device=q.device)
         _call("mb200_attn_fwd_bf16", _p(q), _p(k), _p(v), _p(o), _p(lse), B, H, Hkv, Sq, Sk, hd, st, float(scale),

@@ -255,7 +255,17 @@ def test_attention_generic(ops, cuda, dtype, hd, H, Hkv, causal, Sq, Sk):
 @pytest.mark.parametrize("B,H,Hkv,Sq,Sk,causal,masked", [(1, 4, 2, 128, 128, True, False), (2, 8, 2, 300, 300, True, True),
                                                          (1, 4, 4, 257, 257, False, False), (2, 4, 1, 200, 455, True, True),
                                                          (1, 32, 8, 1000, 1000, True, False), (1, 2, 2, 130, 700, False, True)])
-def test_attention_tcgen05_fwd(ops, cuda, B, H, Hkv, Sq, Sk, causal, masked):
+@pytest.mark.parametrize("fwd2", [False, True])
+def test_attention_tcgen05_fwd(ops, cuda, B, H, Hkv, Sq, Sk, causal, masked, fwd2):
+    import mantis_b200.ops as om0
+    old2 = om0.ATTN_FWD2; om0.ATTN_FWD2 = fwd2
+    try:
+        _attention_tcgen05_fwd(ops, cuda, B, H, Hkv, Sq, Sk, causal, masked)
+    finally:
+        om0.ATTN_FWD2 = old2
+
+
+def _attention_tcgen05_fwd(ops, cuda, B, H, Hkv, Sq, Sk, causal, masked):
     torch.manual_seed(12)
     hd = 128
     q = torch.randn(B, Sq, H, hd, device=cuda).bfloat16()

@@ -75,6 +75,10 @@ def bench_attention():
     fl = 4.0 * S * S * hd * H / 2            # causal: half the square
     ms = timeit(lambda i: ops.attention_fwd(qs[i % nset], ks[i % nset], vs[i % nset], True, None, scale), reps=5)
     report("attn fwd causal S=7864 32q/8kv hd128", ms, flops=fl)
+    ops.ATTN_FWD2 = not ops.ATTN_FWD2
+    ms = timeit(lambda i: ops.attention_fwd(qs[i % nset], ks[i % nset], vs[i % nset], True, None, scale), reps=5)
+    report(f"attn fwd causal S=7864 (ATTN_FWD2={ops.ATTN_FWD2})", ms, flops=fl)
+    ops.ATTN_FWD2 = not ops.ATTN_FWD2
     o, lse = ops.attention_fwd(qs[0], ks[0], vs[0], True, None, scale)
     do = torch.randn_like(o)
     ms = timeit(lambda i: ops.attention_bwd(qs[0], ks[0], vs[0], o, do, lse, True, None, scale, fast=True), reps=5)
