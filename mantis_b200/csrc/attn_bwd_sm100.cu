@@ -269,7 +269,12 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __gri
 }
 
 // ============================================================================================ dQ
-__global__ void __launch_bounds__(NTHREADS, 1)
+// NGQ softmax groups rotate over the key sub-tiles, one TMEM stage (S, dP) each: 128 (dQ) + 3 x 128 = 512 columns.
+constexpr int NGQ = 3;
+constexpr int QSQ = 4;                   // smem stages of the streamed K/V sub-tiles
+constexpr int DQ_THREADS = 64 + NGQ * 128;
+
+__global__ void __launch_bounds__(DQ_THREADS, 1)
 attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                          const __grid_constant__ CUtensorMap tmK64, const __grid_constant__ CUtensorMap tmV64,
                          const BwdParams p) {
@@ -277,16 +282,16 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                           // 32 KB resident
   uint8_t* sDO = sQ + FULL_TILE;                // 32 KB resident
-  uint8_t* sK = sDO + FULL_TILE;                // QS x 16 KB
-  uint8_t* sV = sK + QS * SUB_TILE;             // QS x 16 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + QS * SUB_TILE);
+  uint8_t* sK = sDO + FULL_TILE;                // QSQ x 16 KB
+  uint8_t* sV = sK + QSQ * SUB_TILE;            // QSQ x 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + QSQ * SUB_TILE);
   uint64_t* qdo_full = bars + 0;
-  uint64_t* kv_full = bars + 1;     // [QS]
-  uint64_t* kv_empty = bars + 4;    // [QS]
-  uint64_t* sdp_full = bars + 7;    // [2]
-  uint64_t* ds_full = bars + 9;     // [2]
-  uint64_t* acc_done = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* kv_full = bars + 1;              // [QSQ]
+  uint64_t* kv_empty = kv_full + QSQ;        // [QSQ]
+  uint64_t* sdp_full = kv_empty + QSQ;       // [NGQ]
+  uint64_t* ds_full = sdp_full + NGQ;        // [NGQ]
+  uint64_t* acc_done = ds_full + NGQ;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = gridDim.x - 1 - blockIdx.x;
@@ -301,8 +306,8 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmQ); prefetch_tmap(&tmDO); prefetch_tmap(&tmK64); prefetch_tmap(&tmV64);
     mbar_init(qdo_full, 1);
-    for (int s = 0; s < QS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&sdp_full[s], 1); mbar_init(&ds_full[s], 128); }
+    for (int s = 0; s < QSQ; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < NGQ; ++s) { mbar_init(&sdp_full[s], 1); mbar_init(&ds_full[s], 128); }
     mbar_init(acc_done, 1);
     fence_barrier_init();
   }
@@ -312,8 +317,7 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tDQ = tmem_base;
-  const uint32_t tS[2] = {tmem_base + 128, tmem_base + 256};
-  const uint32_t tDP[2] = {tmem_base + 192, tmem_base + 320};
+  const uint32_t tS0 = tmem_base + 128, tDP0 = tmem_base + 192;      // stage g: +128 g
 
   if (warp == 0) {
     if (lane == 0 && n_it > 0) {
@@ -323,7 +327,7 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       tma_load_4d(sDO, &tmDO, qdo_full, 0, h, q0, b);
       tma_load_4d(sDO + FULL_HALF, &tmDO, qdo_full, 64, h, q0, b);
       for (int n = 0; n < n_it; ++n) {
-        const int s = n % QS; const uint32_t ph = (n / QS) & 1;
+        const int s = n % QSQ; const uint32_t ph = (n / QSQ) & 1;
         mbar_wait(&kv_empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&kv_full[s], 2 * SUB_TILE);
         tma_load_4d(sK + s * SUB_TILE, &tmK64, &kv_full[s], 0, hk, n * 64, b);
@@ -338,35 +342,34 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       constexpr uint32_t idesc_acc = make_idesc_bf16(128, 128, false, true);
       const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sDO);
       auto issue_sdp = [&](int n) {
-        const int s = n & 1, ss = n % QS;
-        mbar_wait(&kv_full[ss], (n / QS) & 1);
+        const int s = n % NGQ, ss = n % QSQ;
+        mbar_wait(&kv_full[ss], (n / QSQ) & 1);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sK + ss * SUB_TILE), v_addr = smem_u32(sV + ss * SUB_TILE);
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk) {
           const uint32_t oa = (kk >> 2) * FULL_HALF + (kk & 3) * 32, ob = (kk >> 2) * SUB_HALF + (kk & 3) * 32;
-          umma_bf16_ss(tS[s], make_smem_desc(q_addr + oa, 16, 1024), make_smem_desc(k_addr + ob, 16, 1024), idesc_s, kk != 0);
+          umma_bf16_ss(tS0 + s * 128, make_smem_desc(q_addr + oa, 16, 1024), make_smem_desc(k_addr + ob, 16, 1024), idesc_s, kk != 0);
         }
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk) {
           const uint32_t oa = (kk >> 2) * FULL_HALF + (kk & 3) * 32, ob = (kk >> 2) * SUB_HALF + (kk & 3) * 32;
-          umma_bf16_ss(tDP[s], make_smem_desc(do_addr + oa, 16, 1024), make_smem_desc(v_addr + ob, 16, 1024), idesc_s, kk != 0);
+          umma_bf16_ss(tDP0 + s * 128, make_smem_desc(do_addr + oa, 16, 1024), make_smem_desc(v_addr + ob, 16, 1024), idesc_s, kk != 0);
         }
         umma_commit(&sdp_full[s]);
       };
       mbar_wait(qdo_full, 0);
-      issue_sdp(0);
-      if (n_it > 1) issue_sdp(1);
+      for (int n = 0; n < NGQ && n < n_it; ++n) issue_sdp(n);
       for (int n = 0; n < n_it; ++n) {
-        const int s = n & 1, ss = n % QS; const uint32_t ph = (n >> 1) & 1;
+        const int s = n % NGQ, ss = n % QSQ; const uint32_t ph = (n / NGQ) & 1;
         mbar_wait(&ds_full[s], ph);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sK + ss * SUB_TILE);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)     // dQ += dS (TMEM A, K = 64 keys) x K (MN-major: rows = keys)
-          umma_bf16_ts(tDQ, tS[s] + kk * 8, make_smem_desc(k_addr + kk * 2048, SUB_HALF, 1024), idesc_acc, (n | kk) != 0);
+          umma_bf16_ts(tDQ, tS0 + s * 128 + kk * 8, make_smem_desc(k_addr + kk * 2048, SUB_HALF, 1024), idesc_acc, (n | kk) != 0);
         umma_commit(&kv_empty[ss]);
-        if (n + 2 < n_it) issue_sdp(n + 2);
+        if (n + NGQ < n_it) issue_sdp(n + NGQ);
       }
       umma_commit(acc_done);
     }
@@ -381,16 +384,16 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     const float L = ldv.x, dl = ldv.y;
     const int limit = p.causal ? min(qi + off, p.Sk - 1) : (p.Sk - 1);
     const int s = grp;
-    for (int n = grp; n < n_it; n += 2) {
-      const uint32_t ph = (n >> 1) & 1;
+    for (int n = grp; n < n_it; n += NGQ) {
+      const uint32_t ph = (n / NGQ) & 1;
       mbar_wait(&sdp_full[s], ph);
       tc_fence_after();
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int k0 = n * 64 + c * 32;
         float sv[32], dp[32];
-        tmem_ld_32x32b_x32(tS[s] + lane_off + c * 32, reinterpret_cast<uint32_t*>(sv));
-        tmem_ld_32x32b_x32(tDP[s] + lane_off + c * 32, reinterpret_cast<uint32_t*>(dp));
+        tmem_ld_32x32b_x32(tS0 + s * 128 + lane_off + c * 32, reinterpret_cast<uint32_t*>(sv));
+        tmem_ld_32x32b_x32(tDP0 + s * 128 + lane_off + c * 32, reinterpret_cast<uint32_t*>(dp));
         tmem_ld_wait();
         uint32_t w = 0xffffffffu;
         if (p.kbits) { const int wi = k0 >> 5; w = (wi < p.kbits_stride) ? __ldg(p.kbits + (size_t)b * p.kbits_stride + wi) : 0u; }
@@ -412,15 +415,17 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             dsk[i] = pack_bf16(p0 * (dp[2 * i] - dl), p1 * (dp[2 * i + 1] - dl));
           }
         }
-        tmem_st_32x32b_x16(tS[s] + lane_off + c * 16, dsk);
+        tmem_st_32x32b_x16(tS0 + s * 128 + lane_off + c * 16, dsk);
       }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&ds_full[s]);
     }
-    // epilogue: each group stores 64 of the 128 head dims of its dQ row (x softmax scale)
+    // epilogue: groups 0 and 1 each store 64 of the 128 head dims of their dQ row (x softmax scale); group 2 is done
     bf16* dqp = p.dq + (size_t)b * p.dq_sb + (size_t)(row_ok ? qi : 0) * p.dq_ss + (size_t)h * p.dq_sh + grp * 64;
-    if (n_it > 0) {
+    if (grp >= 2) {
+      // nothing to store
+    } else if (n_it > 0) {
       mbar_wait(acc_done, 0);
       tc_fence_after();
 #pragma unroll
@@ -521,7 +526,7 @@ int mb200_attn_bwd_bf16(const void* q, const void* k, const void* v, const void*
   p.kbits = kmask ? (const uint32_t*)kbits : nullptr; p.kbits_stride = (Sk + 31) / 32;
   p.B = B; p.H = H; p.Hkv = Hkv; p.Sq = Sq; p.Sk = Sk; p.scale = scale; p.scale_log2 = scale * LOG2E; p.causal = causal;
   constexpr int smem_dkv = 2 * FULL_TILE + 2 * QS * SUB_TILE + 1024 + 256 + QS * 512;
-  constexpr int smem_dq = 2 * FULL_TILE + 2 * QS * SUB_TILE + 1024 + 256;
+  constexpr int smem_dq = 2 * FULL_TILE + 2 * QSQ * SUB_TILE + 1024 + 256;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(attn_bwd_dkv_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dkv) != cudaSuccess ||
@@ -532,7 +537,7 @@ int mb200_attn_bwd_bf16(const void* q, const void* k, const void* v, const void*
   }
   dim3 gkv((Sk + 127) / 128, Hkv, B), gq((Sq + 127) / 128, H, B);
   attn_bwd_dkv_sm100_kernel<<<gkv, NTHREADS, smem_dkv, st>>>(tmQ64, tmDO64, tmK, tmV, p);
-  attn_bwd_dq_sm100_kernel<<<gq, NTHREADS, smem_dq, st>>>(tmQ, tmDO, tmK64, tmV64, p);
+  attn_bwd_dq_sm100_kernel<<<gq, DQ_THREADS, smem_dq, st>>>(tmQ, tmDO, tmK64, tmV64, p);
   MB200_CHECK_LAUNCH();
   return MB200_OK;
 }
