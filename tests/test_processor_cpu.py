@@ -62,3 +62,19 @@ def test_conversation_templates():
     c = conv_templates["idefics_2"].copy(); c.messages = []
     c.append_message("User", "q"); c.append_message("Assistant", "")
     assert c.get_prompt() == "User:q<end_of_utterance>\nAssistant:"
+
+
+def test_chat_history_bookkeeping():
+    from mantis_b200.models.mllava.utils import _extend_dialogue
+    c = conv_templates["mllava_v1"].copy()
+    h = _extend_dialogue(c, "hello <image>", None)
+    assert h == [{"role": "USER", "text": "hello <image>"}, {"role": "ASSISTANT", "text": ""}]
+    assert c.messages[-1] == ["ASSISTANT", ""]
+    h[-1]["text"] = "hi"
+    c2 = conv_templates["mllava_v1"].copy()
+    h2 = _extend_dialogue(c2, "and now?", h)
+    assert [t["role"] for t in h2] == ["USER", "ASSISTANT", "USER", "ASSISTANT"] and h2[-1]["text"] == ""
+    assert c2.get_prompt().endswith("USER: and now?</s>ASSISTANT:")
+    import pytest
+    with pytest.raises(AssertionError):
+        _extend_dialogue(conv_templates["mllava_v1"].copy(), "x", [{"role": "USER", "text": "q"}])
