@@ -24,7 +24,7 @@ from transformers.models.idefics2.configuration_idefics2 import Idefics2Config, 
 
 from ... import ops
 from ..kv_cache import B200KVCache
-from ..layers import B200LayerNorm, B200Linear, B200RMSNorm
+from ..layers import B200LayerNorm, B200Linear, B200RMSNorm, hf_key_remap_disabled, init_module_weights
 from ..llama import B200DecoderModel
 from ..vision import B200VisionEncoder, PatchEmbedGemm
 
@@ -221,16 +221,16 @@ class Idefics2PreTrainedModel(PreTrainedModel):
 
     def _init_weights(self, module):
         std = getattr(self.config, "initializer_range", None) or getattr(self.config.text_config, "initializer_range", 0.02)
-        if hasattr(module, "class_embedding"):
-            module.class_embedding.data.normal_(mean=0.0, std=std)
-        if isinstance(module, (nn.Linear, nn.Conv2d)):
-            module.weight.data.normal_(mean=0.0, std=std)
-            if module.bias is not None:
-                module.bias.data.zero_()
-        elif isinstance(module, nn.Embedding):
-            module.weight.data.normal_(mean=0.0, std=std)
-            if module.padding_idx is not None:
-                module.weight.data[module.padding_idx].zero_()
+        init_module_weights(module, std)
+
+    @classmethod
+    def from_pretrained(cls, *args, **kwargs):
+        with hf_key_remap_disabled("idefics2", "mistral"):
+            return super().from_pretrained(*args, **kwargs)
+
+    def save_pretrained(self, *args, **kwargs):
+        with hf_key_remap_disabled("idefics2", "mistral"):
+            return super().save_pretrained(*args, **kwargs)
 
 
 class Idefics2Model(Idefics2PreTrainedModel):

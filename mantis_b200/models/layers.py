@@ -62,3 +62,56 @@ def llama3_inv_freq(head_dim, theta, rope_scaling, device=None):
     smoothed = (1 - smooth) * inv_llama / factor + smooth * inv_llama
     is_medium = ~(wavelen < high_wl) * ~(wavelen > low_wl)
     return torch.where(is_medium, smoothed, inv_llama)
+
+
+# ---------------------------------------------------------------------------------------------- HF plumbing helpers
+def _fresh(t):
+    """transformers >= 5 flags tensors that were just loaded from a checkpoint; never re-initialise those"""
+    return t is not None and not getattr(t, "_is_hf_initialized", False)
+
+
+def init_module_weights(module, std):
+    """normal(0, std) for Linear / Conv / Embedding weights, zeros for biases, ones/zeros for norms -- the rule the
+    reference's `_init_weights` applies (mantis/models/mllava/modeling_llava.py:153-170) -- skipping loaded tensors."""
+    if hasattr(module, "class_embedding") and _fresh(module.class_embedding):
+        module.class_embedding.data.normal_(mean=0.0, std=std)
+    if isinstance(module, (nn.Linear, nn.Conv2d)):
+        if _fresh(module.weight):
+            module.weight.data.normal_(mean=0.0, std=std)
+        if _fresh(module.bias):
+            module.bias.data.zero_()
+    elif isinstance(module, nn.Embedding):
+        if _fresh(module.weight):
+            module.weight.data.normal_(mean=0.0, std=std)
+            if module.padding_idx is not None:
+                module.weight.data[module.padding_idx].zero_()
+    elif isinstance(module, nn.LayerNorm):
+        if _fresh(module.weight):
+            module.weight.data.fill_(1.0)
+        if _fresh(module.bias):
+            module.bias.data.zero_()
+    elif isinstance(module, B200RMSNorm):
+        if _fresh(module.weight):
+            module.weight.data.fill_(1.0)
+
+
+from contextlib import contextmanager
+
+
+@contextmanager
+def hf_key_remap_disabled(*model_types):
+    """transformers >= 5 registers checkpoint *key renamings* per `model_type` (e.g. "llava": language_model.model.* ->
+    language_model.*) for its own re-organised classes.  Our classes keep the reference's module tree / key layout, so
+    those renamings must not be applied while loading or saving them.  Restores the registry afterwards."""
+    try:
+        from transformers import conversion_mapping as cm
+    except Exception:       # older transformers: nothing to disable
+        yield
+        return
+    cm.get_checkpoint_conversion_mapping("llava")          # make sure the registry is built
+    cache = cm._checkpoint_conversion_mapping_cache
+    saved = {mt: cache.pop(mt) for mt in model_types if mt in cache}
+    try:
+        yield
+    finally:
+        cache.update(saved)

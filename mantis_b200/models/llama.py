@@ -15,7 +15,8 @@ from transformers.modeling_outputs import BaseModelOutputWithPast, CausalLMOutpu
 
 from .. import ops
 from .kv_cache import B200KVCache
-from .layers import B200Embedding, B200Linear, B200RMSNorm, default_inv_freq, llama3_inv_freq
+from .layers import (B200Embedding, B200Linear, B200RMSNorm, default_inv_freq, init_module_weights,
+                     llama3_inv_freq)
 
 try:
     from transformers import LlamaConfig, MistralConfig
@@ -115,17 +116,7 @@ class B200DecoderPreTrainedModel(PreTrainedModel):
     _supports_flash_attn_2 = True
 
     def _init_weights(self, module):
-        std = getattr(self.config, "initializer_range", 0.02)
-        if isinstance(module, nn.Linear):
-            module.weight.data.normal_(mean=0.0, std=std)
-            if module.bias is not None:
-                module.bias.data.zero_()
-        elif isinstance(module, nn.Embedding):
-            module.weight.data.normal_(mean=0.0, std=std)
-            if module.padding_idx is not None:
-                module.weight.data[module.padding_idx].zero_()
-        elif isinstance(module, B200RMSNorm):
-            module.weight.data.fill_(1.0)
+        init_module_weights(module, getattr(self.config, "initializer_range", 0.02))
 
 
 class B200DecoderModel(B200DecoderPreTrainedModel):

@@ -24,7 +24,7 @@ from transformers.modeling_outputs import ModelOutput
 
 from ... import ops
 from ..kv_cache import B200KVCache
-from ..layers import B200Linear
+from ..layers import B200Linear, hf_key_remap_disabled, init_module_weights
 from ..llama import B200CausalLM
 from ..vision import B200VisionEncoder, build_vision_tower
 from .configuration_llava import LlavaConfig
@@ -68,16 +68,18 @@ class LlavaPreTrainedModel(PreTrainedModel):
         std = getattr(self.config, "initializer_range", None)
         if std is None:
             std = getattr(self.config.text_config, "initializer_range", 0.02)
-        if hasattr(module, "class_embedding"):
-            module.class_embedding.data.normal_(mean=0.0, std=std)
-        if isinstance(module, (nn.Linear, nn.Conv2d)):
-            module.weight.data.normal_(mean=0.0, std=std)
-            if module.bias is not None:
-                module.bias.data.zero_()
-        elif isinstance(module, nn.Embedding):
-            module.weight.data.normal_(mean=0.0, std=std)
-            if module.padding_idx is not None:
-                module.weight.data[module.padding_idx].zero_()
+        init_module_weights(module, std)
+
+    # transformers >= 5 would rename `language_model.model.*` keys for model_type "llava" (its own re-organised class);
+    # ours keeps the reference layout, so checkpoints are read / written verbatim.
+    @classmethod
+    def from_pretrained(cls, *args, **kwargs):
+        with hf_key_remap_disabled("llava"):
+            return super().from_pretrained(*args, **kwargs)
+
+    def save_pretrained(self, *args, **kwargs):
+        with hf_key_remap_disabled("llava"):
+            return super().save_pretrained(*args, **kwargs)
 
 
 class LlavaForConditionalGeneration(LlavaPreTrainedModel, GenerationMixin):

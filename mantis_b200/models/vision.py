@@ -15,7 +15,7 @@ from transformers import PreTrainedModel
 from transformers.modeling_outputs import BaseModelOutputWithPooling
 
 from .. import ops
-from .layers import B200LayerNorm, B200Linear
+from .layers import B200LayerNorm, B200Linear, init_module_weights
 
 
 class B200VisionAttention(nn.Module):
@@ -272,15 +272,7 @@ class B200VisionPreTrainedModel(PreTrainedModel):
     _supports_flash_attn_2 = True
 
     def _init_weights(self, module):
-        std = getattr(self.config, "initializer_range", 0.02)
-        if isinstance(module, (nn.Linear, nn.Conv2d)):
-            module.weight.data.normal_(mean=0.0, std=std)
-            if module.bias is not None:
-                module.bias.data.zero_()
-        elif isinstance(module, nn.Embedding):
-            module.weight.data.normal_(mean=0.0, std=std)
-        elif isinstance(module, nn.LayerNorm):
-            module.bias.data.zero_(); module.weight.data.fill_(1.0)
+        init_module_weights(module, getattr(self.config, "initializer_range", 0.02))
 
     def get_input_embeddings(self):
         return self.vision_model.embeddings.patch_embedding
