@@ -223,6 +223,16 @@ class B200CausalLM(B200DecoderPreTrainedModel):
     def set_output_embeddings(self, new):
         self.lm_head = new
 
+    def resize_token_embeddings(self, *args, **kwargs):
+        out = super().resize_token_embeddings(*args, **kwargs)
+        # HF builds plain nn.Embedding / nn.Linear replacements: put them back on the CUDA-kernel classes
+        emb, head = self.get_input_embeddings(), self.get_output_embeddings()
+        if type(emb) is nn.Embedding:
+            emb.__class__ = B200Embedding
+        if type(head) is nn.Linear:
+            head.__class__ = B200Linear
+        return self.get_input_embeddings() if out is not None else out
+
     def set_decoder(self, decoder):
         self.model = decoder
 
