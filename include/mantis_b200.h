@@ -62,6 +62,12 @@ int mb200_layernorm_bwd(const void* x, const void* w, const void* dy, const floa
 int mb200_rope(const void* x, void* y, const int64_t* pos, const float* inv_freq, long long n_tok, int H, int hd,
                long long tok_stride, long long out_stride, float attn_scaling, int backward, int dtype, void* stream);
 
+/* cos/sin table of one forward pass (shared by all layers) + q and k rotated in one vectorised launch from it */
+int mb200_rope_table(const int64_t* pos, const float* inv_freq, void* tab, long long n_tok, int hd, float attn_scaling,
+                     int dtype, void* stream);
+int mb200_rope2_bf16(const void* q, const void* k, void* qo, void* ko, const void* tab, long long n_tok, int Hq, int Hk,
+                     int hd, long long q_stride, long long k_stride, int backward, void* stream);
+
 /* ---- SwiGLU (llama/modeling_llama.py:182-184; idefics2 :506-521) and GELU family
  *      (projector modeling_llava.py:110-118; SigLIP / CLIP MLP).  kind: 0 erf, 1 tanh, 2 quick ------------- */
 int mb200_swiglu_fwd(const void* gate, const void* up, void* out, long long n, int dtype, void* stream);

@@ -333,6 +333,54 @@ rope_kernel(const T* x, T* y, const int64_t* __restrict__ pos, const float* __re
   }
 }
 
+// cos/sin table for one forward pass: tab[t, i] = {T-rounded cos, T-rounded sin}(pos[t] * inv_freq[i]) -- computed once per
+// micro-batch and shared by every layer's q and k, forward and backward (the per-element sincosf dominated rope_kernel).
+template <typename T>
+__global__ void __launch_bounds__(256)
+rope_table_kernel(const int64_t* __restrict__ pos, const float* __restrict__ inv_freq, float2* __restrict__ tab,
+                  long long n_tok, int half, float attn_scaling) {
+  const long long total = n_tok * half;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % half); const long long t = idx / half;
+    float sn, cs;
+    sincosf((float)pos[t] * inv_freq[i], &sn, &cs);
+    tab[idx] = make_float2(mb::rnd<T>(cs * attn_scaling), mb::rnd<T>(sn * attn_scaling));
+  }
+}
+
+// q and k rotated in ONE launch from the table, 8 elements (16 B) per thread and per half.
+// x layout: [n_tok, H, hd] with token stride; heads [0, Hq) come from q, [Hq, Hq + Hk) from k.
+__global__ void __launch_bounds__(256)
+rope2_bf16_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, bf16* __restrict__ qo, bf16* __restrict__ ko,
+                  const float2* __restrict__ tab, long long n_tok, int Hq, int Hk, int hd, long long q_stride,
+                  long long k_stride, float sign) {
+  const int half = hd >> 1, vec_per_head = half >> 3;           // 8-element vectors per half head
+  const long long total = n_tok * (Hq + Hk) * vec_per_head;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % vec_per_head);
+    const long long th = idx / vec_per_head;
+    const int h = (int)(th % (Hq + Hk));
+    const long long t = th / (Hq + Hk);
+    const bool isq = h < Hq;
+    const bf16* src = isq ? q + (size_t)t * q_stride + (size_t)h * hd : k + (size_t)t * k_stride + (size_t)(h - Hq) * hd;
+    bf16* dst = isq ? qo + ((size_t)t * Hq + h) * hd : ko + ((size_t)t * Hk + (h - Hq)) * hd;
+    float x1[8], x2[8], y1[8], y2[8];
+    mb::Vec8<bf16>::load(src + v * 8, x1);
+    mb::Vec8<bf16>::load(src + half + v * 8, x2);
+    const float2* tb = tab + (size_t)t * half + v * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 cs = tb[j];
+      const float sn = cs.y * sign;
+      // q_embed = (q * cos) + (rotate_half(q) * sin), each product rounded to bf16 like the reference
+      y1[j] = mb::rnd<bf16>(x1[j] * cs.x) + mb::rnd<bf16>(-x2[j] * sn);
+      y2[j] = mb::rnd<bf16>(x2[j] * cs.x) + mb::rnd<bf16>(x1[j] * sn);
+    }
+    mb::Vec8<bf16>::store(dst + v * 8, y1);
+    mb::Vec8<bf16>::store(dst + half + v * 8, y2);
+  }
+}
+
 // ------------------------------------------------------------------ SwiGLU
 __device__ __forceinline__ float silu_f(float g) { return g / (1.f + __expf(-g)); }
 
@@ -615,6 +663,27 @@ int mb200_rope(const void* x, void* y, const int64_t* pos, const float* inv_freq
   DISPATCH_T(dtype, (rope_kernel<T><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(
                         (const T*)x, (T*)y, pos, inv_freq, n_tok, H, hd, tok_stride, out_stride, attn_scaling,
                         backward ? -1.f : 1.f)));
+  MB200_CHECK_LAUNCH(); return MB200_OK;
+}
+
+int mb200_rope_table(const int64_t* pos, const float* inv_freq, void* tab, long long n_tok, int hd, float attn_scaling,
+                     int dtype, void* stream) {
+  if (n_tok <= 0) return MB200_OK;
+  if (hd & 1) return -EINVAL;
+  const long long total = n_tok * (hd / 2);
+  DISPATCH_T(dtype, (rope_table_kernel<T><<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(pos, inv_freq, (float2*)tab, n_tok, hd / 2,
+                                                                                           attn_scaling)));
+  MB200_CHECK_LAUNCH(); return MB200_OK;
+}
+// bf16, hd % 16 == 0, 16-byte aligned rows; outputs contiguous [n_tok, Hq, hd] / [n_tok, Hk, hd]
+int mb200_rope2_bf16(const void* q, const void* k, void* qo, void* ko, const void* tab, long long n_tok, int Hq, int Hk,
+                     int hd, long long q_stride, long long k_stride, int backward, void* stream) {
+  if (n_tok <= 0) return MB200_OK;
+  if ((hd & 15) || (q_stride & 7) || (k_stride & 7)) return -ENOTSUP;
+  const long long total = n_tok * (Hq + Hk) * (hd / 16);
+  rope2_bf16_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>((const bf16*)q, (const bf16*)k, (bf16*)qo, (bf16*)ko,
+                                                                     (const float2*)tab, n_tok, Hq, Hk, hd, q_stride, k_stride,
+                                                                     backward ? -1.f : 1.f);
   MB200_CHECK_LAUNCH(); return MB200_OK;
 }
 

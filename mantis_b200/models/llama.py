@@ -57,7 +57,7 @@ class B200Attention(nn.Module):
         self.o_proj = B200Linear(self.num_heads * self.head_dim, self.hidden_size, bias=bias)
         self.scaling = self.head_dim ** -0.5
 
-    def forward(self, x, residual, position_ids, inv_freq, rope_scale, key_mask, cache, kbits=None):
+    def forward(self, x, residual, position_ids, inv_freq, rope_scale, key_mask, cache, kbits=None, rope_tab=None):
         B, S, _ = x.shape
         if _plain(self.q_proj, self.k_proj, self.v_proj):
             q, k, v = ops.multi_linear(x, self.q_proj.weight, self.k_proj.weight, self.v_proj.weight)
@@ -66,7 +66,7 @@ class B200Attention(nn.Module):
         q = q.view(B, S, self.num_heads, self.head_dim)
         k = k.view(B, S, self.num_kv_heads, self.head_dim)
         v = v.view(B, S, self.num_kv_heads, self.head_dim)
-        q, k = ops.rope(q, k, position_ids, inv_freq, rope_scale)
+        q, k = ops.rope(q, k, position_ids, inv_freq, rope_scale, rope_tab)
         if cache is not None:
             k, v = cache.append(k, v, self.layer_idx)
             if (S == 1 and self.head_dim == 128 and q.dtype == torch.bfloat16 and not torch.is_grad_enabled()
@@ -101,8 +101,8 @@ class B200DecoderLayer(nn.Module):
         self.input_layernorm = B200RMSNorm(config.hidden_size, eps=config.rms_norm_eps)
         self.post_attention_layernorm = B200RMSNorm(config.hidden_size, eps=config.rms_norm_eps)
 
-    def forward(self, x, position_ids, inv_freq, rope_scale, key_mask, cache, kbits=None):
-        x = self.self_attn(self.input_layernorm(x), x, position_ids, inv_freq, rope_scale, key_mask, cache, kbits)
+    def forward(self, x, position_ids, inv_freq, rope_scale, key_mask, cache, kbits=None, rope_tab=None):
+        x = self.self_attn(self.input_layernorm(x), x, position_ids, inv_freq, rope_scale, key_mask, cache, kbits, rope_tab)
         x = self.mlp(self.post_attention_layernorm(x), residual=x)
         return x
 
@@ -184,15 +184,18 @@ class B200DecoderModel(B200DecoderPreTrainedModel):
         if (S == 1 and cache is not None and key_mask is not None and x.dtype == torch.bfloat16
                 and not torch.is_grad_enabled()):
             kbits = ops.kmask_bits(key_mask)                 # one bitmask per decode step, shared by all layers
+        rope_tab = None
+        if x.dtype == torch.bfloat16 and x.is_cuda and S > 1:
+            rope_tab = ops.rope_table(position_ids, inv_freq, self.layers[0].self_attn.head_dim, rope_scale, x.dtype)
         all_hidden = () if output_hidden_states else None
         for layer in self.layers:
             if output_hidden_states:
                 all_hidden += (x,)
             if self.gradient_checkpointing and self.training and cache is None:
-                x = torch.utils.checkpoint.checkpoint(layer, x, position_ids, inv_freq, rope_scale, key_mask, None,
-                                                      use_reentrant=False)
+                x = torch.utils.checkpoint.checkpoint(layer, x, position_ids, inv_freq, rope_scale, key_mask, None, None,
+                                                      rope_tab, use_reentrant=False)
             else:
-                x = layer(x, position_ids, inv_freq, rope_scale, key_mask, cache, kbits)
+                x = layer(x, position_ids, inv_freq, rope_scale, key_mask, cache, kbits, rope_tab)
         x = self.norm(x)
         if output_hidden_states:
             all_hidden += (x,)

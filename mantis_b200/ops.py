@@ -414,25 +414,62 @@ def rope_apply(x, pos, inv_freq, attn_scaling=1.0, backward=False):
     return y
 
 
+def rope_table(pos, inv_freq, hd, attn_scaling, dtype):
+    """[B*S, hd/2] float2 {cos, sin} table (rounded to `dtype` like the reference's cos/sin tensors)"""
+    pos = pos.contiguous().to(torch.int64)
+    n = pos.numel()
+    tab = torch.empty((n, hd // 2, 2), dtype=torch.float32, device=pos.device)
+    _call("mb200_rope_table", _p(pos), _p(inv_freq), _p(tab), n, hd, float(attn_scaling), BF16 if dtype == torch.bfloat16 else F32, _st())
+    return tab
+
+
+def _rope2(q, k, tab, backward):
+    B, S, Hq, hd = q.shape
+    Hk = k.shape[2]
+    qo = torch.empty((B, S, Hq, hd), dtype=q.dtype, device=q.device)
+    ko = torch.empty((B, S, Hk, hd), dtype=k.dtype, device=k.device)
+    _call("mb200_rope2_bf16", _p(q), _p(k), _p(qo), _p(ko), _p(tab), B * S, Hq, Hk, hd, q.stride(1), k.stride(1),
+          int(backward), _st())
+    return qo, ko
+
+
+def _rope2_ok(q, k):
+    def ok(x):
+        B, S, H, hd = x.shape
+        return (x.dtype == torch.bfloat16 and hd % 16 == 0 and x.stride(3) == 1 and x.stride(2) == hd
+                and x.stride(0) == S * x.stride(1) and x.stride(1) % 8 == 0 and x.data_ptr() % 16 == 0)
+    return ok(q) and ok(k) and not FORCE_GENERIC
+
+
 class _RopeFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, k, pos, inv_freq, attn_scaling):
-        qo = rope_apply(q, pos, inv_freq, attn_scaling)
-        ko = rope_apply(k, pos, inv_freq, attn_scaling)
-        ctx.save_for_backward(pos, inv_freq)
+    def forward(ctx, q, k, pos, inv_freq, attn_scaling, tab):
+        ctx.fast = tab is not None and _rope2_ok(q, k)
+        if ctx.fast:
+            qo, ko = _rope2(q, k, tab, False)
+            ctx.save_for_backward(tab)
+        else:
+            qo = rope_apply(q, pos, inv_freq, attn_scaling)
+            ko = rope_apply(k, pos, inv_freq, attn_scaling)
+            ctx.save_for_backward(pos, inv_freq)
         ctx.scaling = attn_scaling
         return qo, ko
 
     @staticmethod
     def backward(ctx, dq, dk):
+        if ctx.fast:
+            (tab,) = ctx.saved_tensors
+            gq, gk = _rope2(dq.contiguous(), dk.contiguous(), tab, True)
+            return gq, gk, None, None, None, None
         pos, inv_freq = ctx.saved_tensors
         return (rope_apply(dq.contiguous(), pos, inv_freq, ctx.scaling, backward=True),
-                rope_apply(dk.contiguous(), pos, inv_freq, ctx.scaling, backward=True), None, None, None)
+                rope_apply(dk.contiguous(), pos, inv_freq, ctx.scaling, backward=True), None, None, None, None)
 
 
-def rope(q, k, pos, inv_freq, attn_scaling=1.0):
-    """q: [B,S,H,hd], k: [B,S,Hkv,hd] -> rotated copies (rotate_half convention)"""
-    return _RopeFn.apply(q, k, pos, inv_freq, attn_scaling)
+def rope(q, k, pos, inv_freq, attn_scaling=1.0, tab=None):
+    """q: [B,S,H,hd], k: [B,S,Hkv,hd] -> rotated copies (rotate_half convention).  `tab` = rope_table(...) of this forward
+    pass enables the one-launch vectorised path."""
+    return _RopeFn.apply(q, k, pos, inv_freq, attn_scaling, tab)
 
 
 # ---------------------------------------------------------------------------------------------- attention

@@ -30,21 +30,22 @@ def _worker(rank, world, port, q):
     assert tr.params[0].grad.data_ptr() == tr.flat_grad.data_ptr()
     local = tr.flat_grad.clone()
     scale = tr.reduce_gradients()
-    q.put((rank, local, tr.flat_grad.clone() * scale))
+    torch.save((rank, local, tr.flat_grad.clone() * scale), os.path.join(q, f"r{rank}.pt"))
     dist.destroy_process_group()
 
 
 def test_flat_buffer_allreduce_world2():
+    import tempfile
     ctx = mp.get_context("spawn")
-    q = ctx.Queue()
+    q = tempfile.mkdtemp()                     # results come back through files (robust against queue teardown races)
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted([q.get(timeout=120) for _ in range(2)], key=lambda t: t[0])
     for p in procs:
-        p.join(timeout=60)
+        p.join(timeout=180)
         assert p.exitcode == 0
+    res = sorted([torch.load(os.path.join(q, f"r{r}.pt")) for r in range(2)], key=lambda t: t[0])
     mean = (res[0][1] + res[1][1]) / 2
     assert torch.allclose(res[0][2], mean, atol=1e-6) and torch.allclose(res[1][2], mean, atol=1e-6)
     assert not torch.allclose(res[0][1], res[1][1])          # ranks really saw different data
@@ -110,20 +111,21 @@ def _overlap_worker(rank, world, port, q):
         tr._overlap = False
     n_async = len(tr._works)
     scale = tr.reduce_gradients()
-    q.put((rank, n_async, torch.allclose(tr.flat_grad * scale, ref, atol=1e-6)))
+    torch.save((rank, n_async, bool(torch.allclose(tr.flat_grad * scale, ref, atol=1e-6))), os.path.join(q, f"r{rank}.pt"))
     dist.destroy_process_group()
 
 
 def test_overlapped_allreduce_matches_single_allreduce():
+    import tempfile
     ctx = mp.get_context("spawn")
-    q = ctx.Queue()
+    q = tempfile.mkdtemp()
     port = _free_port()
     procs = [ctx.Process(target=_overlap_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=120) for _ in range(2)]
     for p in procs:
-        p.join(timeout=60)
+        p.join(timeout=180)
         assert p.exitcode == 0
+    res = [torch.load(os.path.join(q, f"r{r}.pt")) for r in range(2)]
     for rank, n_async, ok in res:
         assert ok and n_async >= 3
