@@ -480,7 +480,7 @@ def _strides12(q, k, v, o):
 
 
 FAST_ATTN_MIN_SQ = int(os.environ.get("MB200_FAST_ATTN_MIN_SQ", "64"))
-ATTN_FWD2 = os.environ.get("MB200_ATTN_FWD2", "0") == "1"      # two query tiles per CTA (ping-pong) forward kernel
+ATTN_FWD2 = os.environ.get("MB200_ATTN_FWD2", "1") == "1"      # two query tiles per CTA (ping-pong) forward kernel
 
 
 def _attn_fast_ok(q, k, v, hd, Sq, Sk):
