@@ -78,3 +78,20 @@ def test_chat_history_bookkeeping():
     import pytest
     with pytest.raises(AssertionError):
         _extend_dialogue(conv_templates["mllava_v1"].copy(), "x", [{"role": "USER", "text": "q"}])
+
+
+def test_collator_single_and_batched():
+    from mantis_b200.train.data import Collator
+    p = MLlavaProcessor(_IP(), _Tok())
+    one = dict(p(text="x <image> y", images=[_Img()]))
+    one["labels"] = one["input_ids"].clone()
+    col = Collator(p)([one])
+    assert isinstance(col["pixel_values"], list) and col["input_ids"].shape[0] == 1      # reference batch==1 contract
+    two = dict(p(text="a b c d <image> e", images=[_Img()]))
+    two["labels"] = two["input_ids"].clone()
+    out = Collator(p, pad_token_id=0)([one, two])
+    L = max(one["input_ids"].shape[1], two["input_ids"].shape[1])
+    assert out["input_ids"].shape == (2, L) and out["attention_mask"].shape == (2, L) and out["labels"].shape == (2, L)
+    short = 0 if one["input_ids"].shape[1] < L else 1
+    assert out["attention_mask"][short, -1] == 0 and out["labels"][short, -1] == -100 and out["input_ids"][short, -1] == 0
+    assert len(out["pixel_values"]) == 2
