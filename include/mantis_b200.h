@@ -173,6 +173,22 @@ int mb200_decode_attn_bf16(const void* q, const void* k, const void* v, void* o,
 
 /* ---- native decode step: the whole single-token LLaMA/Mistral step (all layers, final norm, LM head, greedy argmax)
  *      enqueued by one call (hf: llama/modeling_llama.py:375-427 at q_len 1).  See decode_engine.cu for the tables. ---- */
+/* Paged KV cache for generate() (replaces transformers' DynamicCache torch.cat growth used by the reference's
+ * prepare_inputs_for_generation, mantis/models/mllava/modeling_llava.py:551-602).  A page holds
+ * mb200_kv_page_tokens() tokens of all layers, [L][2 (k,v)][128][Hkv][hd]; the block table is int64 [B, table_stride]
+ * of page base addresses.  *_off arguments are in elements for the bf16 kernels and in bytes for mb200_kv_page_copy. */
+int mb200_kv_page_tokens(void);
+int mb200_kv_page_copy(void* k_lin, void* v_lin, const int64_t* table, int table_stride, long long layer_off_bytes,
+                       long long v_off_bytes, int B, int S, int start, int row_bytes, long long lin_sb, long long lin_ss,
+                       int to_pages, void* stream);
+int mb200_rope_append_paged_bf16(const void* q, const void* k, const void* v, void* q_out, const int64_t* table,
+                                 int table_stride, long long layer_off, long long v_off, const int64_t* pos,
+                                 const float* inv_freq, int B, int H, int Hkv, int hd, int ctx, float rope_scale,
+                                 void* stream);
+int mb200_decode_attn_paged_bf16(const void* q, const int64_t* table, int table_stride, long long layer_off, long long v_off,
+                                 void* o, float* part, int B, int H, int Hkv, int ctx, int hd, long long q_sb,
+                                 long long q_sh, long long o_sb, long long o_sh, float scale, const void* kbits,
+                                 int kbits_stride, void* stream);
 int mb200_argmax_bf16(const void* logits, long long ld, int B, int V, int64_t* out, void* stream);
 long long mb200_decode_ws_bytes(int B, int hidden, int n_heads, int n_kv_heads, int head_dim, int inter, int ctx_max);
 int mb200_llama_decode_step(const int* dims, const float* fparm, const void* const* layers, const void* const* misc,

@@ -220,13 +220,49 @@ kv_append_kernel(const bf16* __restrict__ k_new, const bf16* __restrict__ v_new,
   *reinterpret_cast<int4*>(vc + dst) = *reinterpret_cast<const int4*>(v_new + (size_t)b * ld_new + i);
 }
 
+// ------------------------------------------------------------------ paged KV cache (mantis_b200/models/kv_cache.py)
+// A page holds KV_PAGE tokens of ALL layers: [L][2 (k,v)][KV_PAGE][Hkv][hd].  The block table is int64 [B, max_blocks] of
+// page base ADDRESSES (slabs are separate allocations, so the cache grows without copying or re-laying out old tokens).
+constexpr int KV_PAGE_SHIFT = 7;
+constexpr int KV_PAGE = 1 << KV_PAGE_SHIFT;
+
+// TO_PAGES: rows [B, S, row] (strides in bytes) -> pages at token offsets start..start+S ; else the reverse (gather)
+template <bool TO_PAGES>
+__global__ void __launch_bounds__(128)
+kv_page_copy_kernel(char* __restrict__ k_lin, char* __restrict__ v_lin, const int64_t* __restrict__ table, int table_stride,
+                    long long layer_off_b, long long v_off_b, int start, int row_bytes, long long lin_sb, long long lin_ss) {
+  const int s = blockIdx.x, b = blockIdx.y;
+  const int t = start + s;
+  char* page = reinterpret_cast<char*>(table[(size_t)b * table_stride + (t >> KV_PAGE_SHIFT)]) + layer_off_b +
+               (size_t)(t & (KV_PAGE - 1)) * row_bytes;
+  char* kl = k_lin + (size_t)b * lin_sb + (size_t)s * lin_ss;
+  char* vl = v_lin + (size_t)b * lin_sb + (size_t)s * lin_ss;
+  for (int i = threadIdx.x * 16; i < row_bytes; i += blockDim.x * 16) {
+    if (TO_PAGES) {
+      *reinterpret_cast<int4*>(page + i) = *reinterpret_cast<const int4*>(kl + i);
+      *reinterpret_cast<int4*>(page + v_off_b + i) = *reinterpret_cast<const int4*>(vl + i);
+    } else {
+      *reinterpret_cast<int4*>(kl + i) = *reinterpret_cast<const int4*>(page + i);
+      *reinterpret_cast<int4*>(vl + i) = *reinterpret_cast<const int4*>(page + v_off_b + i);
+    }
+  }
+}
+
 // RoPE(q) -> q_out ; RoPE(k) and v -> cache[b, ctx] : one launch per layer for the decode step
 __global__ void __launch_bounds__(256)
 rope_append_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v, bf16* __restrict__ q_out,
                    bf16* __restrict__ kc, bf16* __restrict__ vc, const int64_t* __restrict__ pos, const float* __restrict__ inv_freq,
-                   int H, int Hkv, int hd, int ctx, long long cap, float rope_scale) {
+                   int H, int Hkv, int hd, int ctx, long long cap, float rope_scale, const int64_t* __restrict__ table,
+                   int table_stride, long long layer_off, long long v_off) {
   const int b = blockIdx.y;
   const int half = hd >> 1;
+  if (table) {          // paged cache: token ctx of sequence b lives in page table[b][ctx / 128], row ctx % 128
+    kc = reinterpret_cast<bf16*>(table[(size_t)b * table_stride + (ctx >> KV_PAGE_SHIFT)]) + layer_off +
+         (size_t)(ctx & (KV_PAGE - 1)) * Hkv * hd;
+    vc = kc + v_off;
+  } else {
+    kc += ((size_t)b * cap + ctx) * Hkv * hd; vc += ((size_t)b * cap + ctx) * Hkv * hd;
+  }
   const int n_q = H * half, n_k = Hkv * half, n_v = Hkv * hd / 8;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const float ps = (float)pos[b];
@@ -237,14 +273,14 @@ rope_append_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const
     float sn, cs; sincosf(ps * inv_freq[d], &sn, &cs);
     cs = __bfloat162float(__float2bfloat16_rn(cs * rope_scale)); sn = __bfloat162float(__float2bfloat16_rn(sn * rope_scale));
     const bf16* src = (isq ? q + (size_t)b * H * hd : k + (size_t)b * Hkv * hd) + (size_t)h * hd;
-    bf16* dst = (isq ? q_out + (size_t)b * H * hd : kc + ((size_t)b * cap + ctx) * Hkv * hd) + (size_t)h * hd;
+    bf16* dst = (isq ? q_out + (size_t)b * H * hd : kc) + (size_t)h * hd;
     const float x1 = __bfloat162float(src[d]), x2 = __bfloat162float(src[d + half]);
     const float y1 = __bfloat162float(__float2bfloat16_rn(x1 * cs)) + __bfloat162float(__float2bfloat16_rn(-x2 * sn));
     const float y2 = __bfloat162float(__float2bfloat16_rn(x2 * cs)) + __bfloat162float(__float2bfloat16_rn(x1 * sn));
     dst[d] = __float2bfloat16_rn(y1); dst[d + half] = __float2bfloat16_rn(y2);
   } else if (i < n_q + n_k + n_v) {
     const int j = i - n_q - n_k;
-    *reinterpret_cast<int4*>(vc + ((size_t)b * cap + ctx) * Hkv * hd + j * 8) =
+    *reinterpret_cast<int4*>(vc + j * 8) =
         *reinterpret_cast<const int4*>(v + (size_t)b * Hkv * hd + j * 8);
   }
 }
@@ -260,6 +296,7 @@ struct DecP {
   const uint32_t* kbits; int kbits_stride;      // key-valid bitmask or null
   float* part;                                  // [B, H, splits, hd + 2]
   int B, H, Hkv, ctx, splits, chunk; float scale;
+  const int64_t* table; int table_stride; long long layer_off, v_off;   // paged cache (table != null): k/v unused
 };
 
 template <int G>
@@ -279,11 +316,21 @@ decode_attn_kernel(DecP p) {
 #pragma unroll
   for (int g = 0; g < G; ++g) { m[g] = -INFINITY; l[g] = 0.f; acc[g][0] = acc[g][1] = acc[g][2] = acc[g][3] = 0.f; }
   for (int k0 = k_begin + w * DKT; k0 < k_end; k0 += DWARPS * DKT) {
+    // chunk is a multiple of DKT, so a 32-key tile never straddles a 128-token page: one table lookup per tile
+    const bf16* kt; const bf16* vt;
+    if (p.table) {
+      kt = reinterpret_cast<const bf16*>(p.table[(size_t)b * p.table_stride + (k0 >> KV_PAGE_SHIFT)]) + p.layer_off +
+           (size_t)(k0 & (KV_PAGE - 1)) * p.kv_ss + (size_t)hk * p.kv_sh;
+      vt = kt + p.v_off;
+    } else {
+      kt = p.k + (size_t)b * p.kv_sb + (size_t)k0 * p.kv_ss + (size_t)hk * p.kv_sh;
+      vt = p.v + (size_t)b * p.kv_sb + (size_t)k0 * p.kv_ss + (size_t)hk * p.kv_sh;
+    }
     // stage 32 keys (each 256 B) coalesced: lane handles 16 B pieces
     for (int e = lane; e < DKT * 16; e += 32) {
       const int j = e >> 4, c = e & 15, kj = k0 + j;
       int4 raw = make_int4(0, 0, 0, 0);
-      if (kj < k_end) raw = *reinterpret_cast<const int4*>(p.k + (size_t)b * p.kv_sb + (size_t)kj * p.kv_ss + (size_t)hk * p.kv_sh + c * 8);
+      if (kj < k_end) raw = *reinterpret_cast<const int4*>(kt + (size_t)j * p.kv_ss + c * 8);
       const bf162* rh = reinterpret_cast<const bf162*>(&raw);
 #pragma unroll
       for (int t = 0; t < 4; ++t) Ks[w][j][c * 4 + t] = rh[t];
@@ -321,7 +368,7 @@ decode_attn_kernel(DecP p) {
     for (int j = 0; j < DKT; ++j) {
       const int kv_j = k0 + j;
       if (kv_j >= k_end) break;
-      const uint2 raw = *reinterpret_cast<const uint2*>(p.v + (size_t)b * p.kv_sb + (size_t)kv_j * p.kv_ss + (size_t)hk * p.kv_sh + lane * 4);
+      const uint2 raw = *reinterpret_cast<const uint2*>(vt + (size_t)j * p.kv_ss + lane * 4);
       const bf162* vh = reinterpret_cast<const bf162*>(&raw);
       const float2 v01 = __bfloat1622float2(vh[0]), v23 = __bfloat1622float2(vh[1]);
 #pragma unroll
@@ -471,12 +518,66 @@ int mb200_rope_append_bf16(const void* q, const void* k, const void* v, void* q_
   dim3 grid((total + 255) / 256, B);
   rope_append_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)q_out,
                                                             (bf16*)k_cache, (bf16*)v_cache, pos, inv_freq, H, Hkv, hd, ctx,
-                                                            capacity, rope_scale);
+                                                            capacity, rope_scale, nullptr, 0, 0, 0);
+  MB200_CHECK_LAUNCH();
+  return MB200_OK;
+}
+
+// Paged variant: the new token's K/V go to page table[b][ctx / 128] (+ layer_off elements; V at + v_off elements).
+int mb200_rope_append_paged_bf16(const void* q, const void* k, const void* v, void* q_out, const int64_t* table,
+                                 int table_stride, long long layer_off, long long v_off, const int64_t* pos,
+                                 const float* inv_freq, int B, int H, int Hkv, int hd, int ctx, float rope_scale,
+                                 void* stream) {
+  if (B <= 0) return MB200_OK;
+  if ((hd & 7) || !table || (ctx >> KV_PAGE_SHIFT) >= table_stride) return -EINVAL;
+  const int total = (H + Hkv) * (hd / 2) + Hkv * hd / 8;
+  dim3 grid((total + 255) / 256, B);
+  rope_append_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)q_out,
+                                                            nullptr, nullptr, pos, inv_freq, H, Hkv, hd, ctx, 0, rope_scale,
+                                                            table, table_stride, layer_off, v_off);
+  MB200_CHECK_LAUNCH();
+  return MB200_OK;
+}
+
+int mb200_kv_page_tokens(void) { return KV_PAGE; }
+
+// Scatter rows k_lin/v_lin [B, S, row_bytes] (byte strides lin_sb / lin_ss) into the pages at token offsets
+// start .. start+S (to_pages = 1), or gather them back (to_pages = 0).  Offsets in BYTES; rows 16-byte multiples.
+int mb200_kv_page_copy(void* k_lin, void* v_lin, const int64_t* table, int table_stride, long long layer_off_bytes,
+                       long long v_off_bytes, int B, int S, int start, int row_bytes, long long lin_sb, long long lin_ss,
+                       int to_pages, void* stream) {
+  if (B <= 0 || S <= 0) return MB200_OK;
+  if ((row_bytes & 15) || (lin_sb & 15) || (lin_ss & 15) || !table) return -EINVAL;
+  if (((start + S - 1) >> KV_PAGE_SHIFT) >= table_stride) return -EINVAL;
+  if ((reinterpret_cast<uintptr_t>(k_lin) | reinterpret_cast<uintptr_t>(v_lin)) & 15) return -EINVAL;
+  dim3 grid(S, B);
+  if (to_pages)
+    kv_page_copy_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>((char*)k_lin, (char*)v_lin, table, table_stride,
+                                                                     layer_off_bytes, v_off_bytes, start, row_bytes, lin_sb, lin_ss);
+  else
+    kv_page_copy_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>((char*)k_lin, (char*)v_lin, table, table_stride,
+                                                                      layer_off_bytes, v_off_bytes, start, row_bytes, lin_sb, lin_ss);
   MB200_CHECK_LAUNCH();
   return MB200_OK;
 }
 
 int mb200_decode_attn_splits(int ctx) { int s = (ctx + 127) / 128; if (s < 1) s = 1; if (s > 64) s = 64; return s; }
+
+static int decode_attn_launch(DecP& p, void* o, long long o_sb, long long o_sh, void* stream) {
+  const int G = p.H / p.Hkv;
+  p.splits = mb200_decode_attn_splits(p.ctx);
+  p.chunk = ((p.ctx + p.splits - 1) / p.splits + DKT - 1) / DKT * DKT;      // tile-aligned chunks (see the kernel)
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(p.splits, p.Hkv, p.B);
+  if (G == 1) decode_attn_kernel<1><<<grid, DWARPS * 32, 0, st>>>(p);
+  else if (G == 2) decode_attn_kernel<2><<<grid, DWARPS * 32, 0, st>>>(p);
+  else if (G == 4) decode_attn_kernel<4><<<grid, DWARPS * 32, 0, st>>>(p);
+  else if (G == 8) decode_attn_kernel<8><<<grid, DWARPS * 32, 0, st>>>(p);
+  else return -ENOTSUP;
+  decode_combine_kernel<<<dim3(p.H, p.B), DHD, 0, st>>>(p.part, (bf16*)o, o_sb, o_sh, p.H, p.splits);
+  MB200_CHECK_LAUNCH();
+  return MB200_OK;
+}
 
 // q [B,H,128] (strides q_sb,q_sh), cache k/v [B,cap,Hkv,128] (strides kv_sb, kv_ss, kv_sh), o [B,H,128].
 // part: fp32 scratch of B*H*splits*(130) floats with splits = mb200_decode_attn_splits(ctx).
@@ -486,22 +587,29 @@ int mb200_decode_attn_bf16(const void* q, const void* k, const void* v, void* o,
                            int kbits_stride, void* stream) {
   if (B <= 0 || ctx <= 0) return MB200_OK;
   if (hd != DHD || H % Hkv != 0) return -ENOTSUP;
-  const int G = H / Hkv;
   DecP p;
   p.q = (const bf16*)q; p.q_sb = q_sb; p.q_sh = q_sh; p.k = (const bf16*)k; p.v = (const bf16*)v;
   p.kv_sb = kv_sb; p.kv_ss = kv_ss; p.kv_sh = kv_sh; p.kbits = (const uint32_t*)kbits; p.kbits_stride = kbits_stride;
-  p.part = part; p.B = B; p.H = H; p.Hkv = Hkv; p.ctx = ctx; p.splits = mb200_decode_attn_splits(ctx);
-  p.chunk = (ctx + p.splits - 1) / p.splits; p.scale = scale;
-  cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid(p.splits, Hkv, B);
-  if (G == 1) decode_attn_kernel<1><<<grid, DWARPS * 32, 0, st>>>(p);
-  else if (G == 2) decode_attn_kernel<2><<<grid, DWARPS * 32, 0, st>>>(p);
-  else if (G == 4) decode_attn_kernel<4><<<grid, DWARPS * 32, 0, st>>>(p);
-  else if (G == 8) decode_attn_kernel<8><<<grid, DWARPS * 32, 0, st>>>(p);
-  else return -ENOTSUP;
-  decode_combine_kernel<<<dim3(H, B), DHD, 0, st>>>(part, (bf16*)o, o_sb, o_sh, H, p.splits);
-  MB200_CHECK_LAUNCH();
-  return MB200_OK;
+  p.part = part; p.B = B; p.H = H; p.Hkv = Hkv; p.ctx = ctx; p.scale = scale;
+  p.table = nullptr; p.table_stride = 0; p.layer_off = 0; p.v_off = 0;
+  return decode_attn_launch(p, o, o_sb, o_sh, stream);
+}
+
+// Same over the paged cache: keys/values of sequence b, token j at table[b][j / 128] + layer_off + (j % 128) * Hkv * 128
+// (+ v_off for V), offsets in elements.
+int mb200_decode_attn_paged_bf16(const void* q, const int64_t* table, int table_stride, long long layer_off, long long v_off,
+                                 void* o, float* part, int B, int H, int Hkv, int ctx, int hd, long long q_sb,
+                                 long long q_sh, long long o_sb, long long o_sh, float scale, const void* kbits,
+                                 int kbits_stride, void* stream) {
+  if (B <= 0 || ctx <= 0) return MB200_OK;
+  if (hd != DHD || H % Hkv != 0) return -ENOTSUP;
+  if (!table || ((ctx - 1) >> KV_PAGE_SHIFT) >= table_stride) return -EINVAL;
+  DecP p;
+  p.q = (const bf16*)q; p.q_sb = q_sb; p.q_sh = q_sh; p.k = nullptr; p.v = nullptr;
+  p.kv_sb = 0; p.kv_ss = (long long)Hkv * hd; p.kv_sh = hd; p.kbits = (const uint32_t*)kbits; p.kbits_stride = kbits_stride;
+  p.part = part; p.B = B; p.H = H; p.Hkv = Hkv; p.ctx = ctx; p.scale = scale;
+  p.table = table; p.table_stride = table_stride; p.layer_off = layer_off; p.v_off = v_off;
+  return decode_attn_launch(p, o, o_sb, o_sh, stream);
 }
 
 }  // extern "C"

@@ -47,11 +47,13 @@ int mb200_argmax_bf16(const void* logits, long long ld, int B, int V, int64_t* o
   return MB200_OK;
 }
 
-// dims  : {n_layers, hidden, n_heads, n_kv_heads, head_dim, intermediate, vocab, B, ctx, capacity, kbits_stride}
+// dims  : {n_layers, hidden, n_heads, n_kv_heads, head_dim, intermediate, vocab, B, ctx, capacity, kbits_stride,
+//          table_stride}   table_stride > 0 selects the paged cache (misc[9] = int64 block table [B, table_stride] of page
+//          addresses, page = [L][2][128][Hkv][hd]); layers[..][9..10] are then unused and capacity = table_stride * 128.
 // fparm : {rms_eps, rope_scaling}
 // layers: n_layers x 11 device pointers {wq, wk, wv, wo, w_gate, w_up, w_down, ln1, ln2, k_cache, v_cache}
 // misc  : {embed, final_norm, lm_head, inv_freq, ids(int64[B]), pos(int64[B]), kbits (or null), logits_out [B, ld_logits] bf16,
-//          next_ids (int64[B]) or null}
+//          next_ids (int64[B]) or null, block table (paged cache) or null}
 // ws    : device scratch, mb200_decode_ws_bytes(...) bytes.   bf16 only; head_dim 128.
 long long mb200_decode_ws_bytes(int B, int hidden, int n_heads, int n_kv_heads, int head_dim, int inter, int ctx_max) {
   const long long e = 2;
@@ -67,8 +69,12 @@ long long mb200_decode_ws_bytes(int B, int hidden, int n_heads, int n_kv_heads, 
 int mb200_llama_decode_step(const int* dims, const float* fparm, const void* const* layers, const void* const* misc,
                             void* ws, long long ld_logits, void* stream) {
   const int L = dims[0], D = dims[1], H = dims[2], Hkv = dims[3], hd = dims[4], I = dims[5], V = dims[6], B = dims[7];
-  const int ctx = dims[8]; const long long cap = dims[9]; const int kbs = dims[10];
+  const int ctx = dims[8]; const long long cap = dims[9]; const int kbs = dims[10]; const int tstride = dims[11];
   if (B <= 0 || B > 16 || hd != 128) return -ENOTSUP;
+  const int64_t* table = tstride > 0 ? (const int64_t*)misc[9] : nullptr;
+  if (tstride > 0 && !table) return -EINVAL;
+  const long long page_tok = mb200_kv_page_tokens();
+  const long long v_off = page_tok * Hkv * hd, layer_stride = 2 * v_off;
   if (ctx + 1 > cap) return -EINVAL;
   const float eps = fparm[0], rope_scale = fparm[1];
   const void* embed = misc[0]; const void* fnorm = misc[1]; const void* lm_head = misc[2];
@@ -92,10 +98,17 @@ int mb200_llama_decode_step(const int* dims, const float* fparm, const void* con
     const void* const* w = layers + (size_t)l * 11;
     TRY(mb200_rmsnorm_fwd(x, w[7], xn, nullptr, B, D, eps, dt, stream));
     TRY(mb200_skinny_gemm3_bf16(xn, w[0], w[1], w[2], q, k, v, B, HD, KD, KD, D, D, D, stream));
-    TRY(mb200_rope_append_bf16(q, k, v, qr, const_cast<void*>(w[9]), const_cast<void*>(w[10]), pos, inv_freq, B, H, Hkv, hd,
-                               ctx, cap, rope_scale, stream));
-    TRY(mb200_decode_attn_bf16(qr, w[9], w[10], ao, part, B, H, Hkv, ctx + 1, hd, HD, hd, cap * KD, KD, hd, HD, hd, scale,
-                               kbits, kbs, stream));
+    if (table) {
+      TRY(mb200_rope_append_paged_bf16(q, k, v, qr, table, tstride, l * layer_stride, v_off, pos, inv_freq, B, H, Hkv, hd,
+                                       ctx, rope_scale, stream));
+      TRY(mb200_decode_attn_paged_bf16(qr, table, tstride, l * layer_stride, v_off, ao, part, B, H, Hkv, ctx + 1, hd, HD, hd,
+                                       HD, hd, scale, kbits, kbs, stream));
+    } else {
+      TRY(mb200_rope_append_bf16(q, k, v, qr, const_cast<void*>(w[9]), const_cast<void*>(w[10]), pos, inv_freq, B, H, Hkv,
+                                 hd, ctx, cap, rope_scale, stream));
+      TRY(mb200_decode_attn_bf16(qr, w[9], w[10], ao, part, B, H, Hkv, ctx + 1, hd, HD, hd, cap * KD, KD, hd, HD, hd, scale,
+                                 kbits, kbs, stream));
+    }
     TRY(mb200_skinny_gemm_bf16(ao, w[3], x, nullptr, x, B, D, HD, HD, HD, D, D, stream));          // x += o_proj(attn)
     TRY(mb200_rmsnorm_fwd(x, w[8], xn, nullptr, B, D, eps, dt, stream));
     TRY(mb200_skinny_swiglu_bf16(xn, w[4], w[5], act, B, I, D, D, D, I, stream));                   // silu(gate) * up

@@ -21,7 +21,7 @@ class DecodeEngine:
         self.decoder, self.lm_head_weight, self.cache = decoder, lm_head_weight, cache
         self.device = lm_head_weight.device
         self.inv_freq, self.rope_scale = decoder.rope_tables(self.device)
-        self.B = cache.k[0].shape[0]
+        self.B = cache.batch
         cache.reserve(cache.get_seq_length() + reserve_tokens)
         self._build_tables()
         self.ld_logits = (self.V + 7) // 8 * 8
@@ -32,10 +32,10 @@ class DecodeEngine:
 
     @staticmethod
     def eligible(decoder, cache, x_dtype):
-        if not isinstance(cache, B200KVCache) or len(cache.k) != len(decoder.layers) or ops.FORCE_GENERIC:
+        if not isinstance(cache, B200KVCache) or len(cache) != len(decoder.layers) or ops.FORCE_GENERIC:
             return False
         a = decoder.layers[0].self_attn
-        if x_dtype != torch.bfloat16 or a.head_dim != 128 or cache.k[0].shape[0] > 16:
+        if x_dtype != torch.bfloat16 or cache.dtype != torch.bfloat16 or a.head_dim != 128 or not 0 < cache.batch <= 16:
             return False
         for layer in decoder.layers:
             for lin in (layer.self_attn.q_proj, layer.self_attn.o_proj, layer.mlp.gate_proj):
@@ -49,25 +49,24 @@ class DecodeEngine:
             a, m = layer.self_attn, layer.mlp
             ptrs += [a.q_proj.weight, a.k_proj.weight, a.v_proj.weight, a.o_proj.weight, m.gate_proj.weight,
                      m.up_proj.weight, m.down_proj.weight, layer.input_layernorm.weight,
-                     layer.post_attention_layernorm.weight, self.cache.k[i], self.cache.v[i]]
+                     layer.post_attention_layernorm.weight, None, None]      # KV: paged, reached through the block table
         self._keep = ptrs
-        self.layer_tab = (ctypes.c_void_p * len(ptrs))(*[t.data_ptr() for t in ptrs])
-        self.capacity = self.cache.capacity()
+        self.layer_tab = (ctypes.c_void_p * len(ptrs))(*[t.data_ptr() if t is not None else None for t in ptrs])
 
     def step(self, ids, pos, kbits=None):
         """ids, pos: int64 [B] on device.  Appends one token per sequence to the cache, returns (logits [B,V], next_ids)."""
         ctx = self.cache.get_seq_length()
-        if ctx + 1 > self.capacity:
-            self.cache.reserve(2 * self.capacity)
-            self._build_tables()
-        dims = (ctypes.c_int * 11)(self.L, self.D, self.H, self.Hkv, self.hd, self.I, self.V, self.B, ctx, self.capacity,
-                                   kbits.shape[1] if kbits is not None else 0)
+        self.cache.ensure(ctx + 1)                    # new pages only extend the block table; nothing is copied
+        table = self.cache.device_table()
+        dims = (ctypes.c_int * 12)(self.L, self.D, self.H, self.Hkv, self.hd, self.I, self.V, self.B, ctx,
+                                   table.shape[1] * self.cache.PAGE, kbits.shape[1] if kbits is not None else 0,
+                                   table.shape[1])
         fparm = (ctypes.c_float * 2)(self.eps, float(self.rope_scale))
         ids = ids.contiguous(); pos = pos.contiguous()
-        misc = (ctypes.c_void_p * 9)(self.decoder.embed_tokens.weight.data_ptr(), self.decoder.norm.weight.data_ptr(),
+        misc = (ctypes.c_void_p * 10)(self.decoder.embed_tokens.weight.data_ptr(), self.decoder.norm.weight.data_ptr(),
                                      self.lm_head_weight.data_ptr(), self.inv_freq.data_ptr(), ids.data_ptr(),
                                      pos.data_ptr(), kbits.data_ptr() if kbits is not None else None,
-                                     self.logits.data_ptr(), self.next_ids.data_ptr())
+                                     self.logits.data_ptr(), self.next_ids.data_ptr(), table.data_ptr())
         ops._call("mb200_llama_decode_step", dims, fparm, self.layer_tab, misc, ops._p(self.ws), self.ld_logits, ops._st())
         self.cache.advance(1)
         return self.logits[:, : self.V], self.next_ids

@@ -68,11 +68,12 @@ class B200Attention(nn.Module):
         v = v.view(B, S, self.num_kv_heads, self.head_dim)
         q, k = ops.rope(q, k, position_ids, inv_freq, rope_scale, rope_tab)
         if cache is not None:
-            k, v = cache.append(k, v, self.layer_idx)
             if (S == 1 and self.head_dim == 128 and q.dtype == torch.bfloat16 and not torch.is_grad_enabled()
                     and not ops.FORCE_GENERIC):
-                o = ops.decode_attention(q, k, v, k.shape[1], key_mask, self.scaling, kbits=kbits)   # split-KV decode kernel
+                ctx = cache.write(k, v, self.layer_idx)                 # split-KV decode kernel reads the pages in place
+                o = ops.decode_attention_paged(q, cache, self.layer_idx, ctx, key_mask, self.scaling, kbits=kbits)
                 return self.o_proj(o.view(B, S, self.num_heads * self.head_dim), residual=residual)
+            k, v = cache.append(k, v, self.layer_idx)
         o = ops.attention(q, k, v, causal=True, kmask=key_mask, scale=self.scaling)
         return self.o_proj(o.view(B, S, self.num_heads * self.head_dim), residual=residual)
 
@@ -168,6 +169,8 @@ class B200DecoderModel(B200DecoderPreTrainedModel):
                     raise ValueError("mantis_b200 needs its own B200KVCache for cached decoding")
                 past_key_values = B200KVCache()
             cache = past_key_values
+            if cache.n_layers is None:
+                cache.n_layers = len(self.layers)
         past = cache.get_seq_length() if cache is not None else 0
         if position_ids is None:
             position_ids = torch.arange(past, past + S, device=inputs_embeds.device).unsqueeze(0).expand(B, S)

@@ -556,6 +556,25 @@ def decode_attention(q, k_cache, v_cache, ctx, kmask, scale, kbits=None):
     return o
 
 
+def decode_attention_paged(q, cache, layer_idx, ctx, kmask, scale, kbits=None):
+    """decode_attention over the paged cache (models/kv_cache.py): q [B,1,H,128] bf16 against the first `ctx` cached
+    tokens of layer `layer_idx`; the kernel walks the block table itself."""
+    B, _, H, hd = q.shape
+    o = torch.empty((B, 1, H, hd), dtype=q.dtype, device=q.device)
+    splits = _L().mb200_decode_attn_splits(ctx)
+    part = torch.empty((B * H * splits * (hd + 2),), dtype=torch.float32, device=q.device)
+    words = 0
+    if kbits is None and kmask is not None:
+        kbits = kmask_bits(kmask[:, :ctx])
+    if kbits is not None:
+        words = kbits.shape[1]
+    tab = cache.device_table()
+    _call("mb200_decode_attn_paged_bf16", _p(q), _p(tab), tab.shape[1], layer_idx * cache.layer_stride, cache.v_off,
+          _p(o), _p(part), B, H, cache.Hkv, ctx, hd, q.stride(0), q.stride(2), o.stride(0), o.stride(2), float(scale),
+          _p(kbits), words, _st())
+    return o
+
+
 def attention_bwd(q, k, v, o, do, lse, causal, kmask, scale, kbits=None, fast=False):
     B, Sq, H, hd = q.shape
     Sk, Hkv = k.shape[1], k.shape[2]

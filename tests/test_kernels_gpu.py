@@ -362,6 +362,75 @@ def test_decode_attention(ops, cuda, B, H, Hkv, ctx):
     assert _rel(o2, ref2) < 1e-2
 
 
+def _paged_cache(cuda, L, B, Hkv, hd, dtype, slab_tokens=256):
+    from mantis_b200.models.kv_cache import B200KVCache
+    return B200KVCache(n_layers=L, slab_tokens=slab_tokens)
+
+
+@pytest.mark.parametrize("dtype,hd", [(torch.bfloat16, 128), (torch.float32, 16)])
+def test_paged_kv_cache_roundtrip(ops, cuda, dtype, hd):
+    """prefill + token-by-token appends land in (non-contiguous, multi-slab) pages; gather returns exactly what went in"""
+    torch.manual_seed(32)
+    L, B, Hkv = 3, 2, 2
+    cache = _paged_cache(cuda, L, B, Hkv, hd, dtype)
+    chunks = [200, 1, 1, 57, 1, 130]
+    ks = [[torch.randn(B, s, Hkv, hd, device=cuda).to(dtype) for s in chunks] for _ in range(L)]
+    vs = [[torch.randn(B, s, Hkv, hd, device=cuda).to(dtype) for s in chunks] for _ in range(L)]
+    first_pages = None
+    for ci, s in enumerate(chunks):
+        for l in range(L):
+            if ci == 3 and l == 1:       # strided source rows (a slice of a fused projection)
+                wide = torch.zeros(B, s, Hkv * hd * 2, device=cuda, dtype=dtype)
+                kk = wide[..., : Hkv * hd].unflatten(-1, (Hkv, hd)); kk.copy_(ks[l][ci])
+                vv = wide[..., Hkv * hd:].unflatten(-1, (Hkv, hd)); vv.copy_(vs[l][ci])
+                k, v = cache.append(kk, vv, l)
+            else:
+                k, v = cache.append(ks[l][ci], vs[l][ci], l)
+            tot = sum(chunks[: ci + 1])
+            assert k.shape == (B, tot, Hkv, hd)
+            assert torch.equal(k, torch.cat(ks[l][: ci + 1], 1)) and torch.equal(v, torch.cat(vs[l][: ci + 1], 1))
+        if ci == 0:
+            first_pages = [list(b) for b in cache.blocks]
+    assert len(cache.slabs) > 1                                   # grew by adding slabs ...
+    assert all(b[: len(f)] == f for b, f in zip(cache.blocks, first_pages))   # ... without moving old pages
+    assert cache.get_seq_length() == sum(chunks) and len(cache) == L
+    k0, v0 = cache[0]
+    assert k0.shape == (B, Hkv, sum(chunks), hd) and torch.equal(k0.permute(0, 2, 1, 3), torch.cat(ks[0], 1))
+    cache.reorder_cache(torch.tensor([1, 1, 0], device=cuda))
+    k1, _ = cache.gather(1)
+    assert torch.equal(k1, torch.cat(ks[1], 1)[[1, 1, 0]])
+    cache.crop(100)
+    assert cache.get_seq_length() == 100 and all(len(b) == 1 for b in cache.blocks)
+    k2, _ = cache.gather(2)
+    assert torch.equal(k2, torch.cat(ks[2], 1)[[1, 1, 0], :100])
+
+
+@pytest.mark.parametrize("B,H,Hkv,ctx", [(1, 32, 8, 6137), (3, 8, 2, 300), (2, 4, 4, 128), (2, 4, 4, 129), (16, 32, 8, 1000),
+                                         (1, 8, 8, 9000)])
+def test_decode_attention_paged(ops, cuda, B, H, Hkv, ctx):
+    """block-table walk == contiguous cache, bit for bit (same kernel, same split partition)"""
+    torch.manual_seed(33)
+    hd, L, layer = 128, 2, 1
+    q = torch.randn(B, 1, H, hd, device=cuda).bfloat16()
+    kc = torch.randn(B, ctx, Hkv, hd, device=cuda).bfloat16()
+    vc = torch.randn(B, ctx, Hkv, hd, device=cuda).bfloat16()
+    cache = _paged_cache(cuda, L, B, Hkv, hd, torch.bfloat16, slab_tokens=512)
+    for l in range(L):
+        if l == layer:
+            cache.write(kc[:, : ctx - 1], vc[:, : ctx - 1], l) if ctx > 1 else None
+            cache.write(kc[:, ctx - 1:], vc[:, ctx - 1:], l)
+        else:
+            cache.write(torch.zeros_like(kc), torch.zeros_like(vc), l)
+    kmask = torch.ones(B, ctx, dtype=torch.int64, device=cuda)
+    kmask[B - 1, : min(7, ctx - 1)] = 0
+    for km in (kmask, None):
+        o = ops.decode_attention_paged(q, cache, layer, ctx, km, hd ** -0.5)
+        o_lin = ops.decode_attention(q, kc, vc, ctx, km, hd ** -0.5)
+        assert torch.equal(o, o_lin)
+        ref = _attn_ref(q.float(), kc.float(), vc.float(), True, km, hd ** -0.5)
+        assert _rel(o, ref) < 1e-2, _rel(o, ref)
+
+
 # ------------------------------------------------------------------------------------------------ merge
 def _merge_case(rng, B, T, P, D, mode, zero_pad_rows):
     ids = rng.integers(1, 12, size=(B, T))

@@ -47,3 +47,34 @@ def test_model_classes_importable_with_reference_names():
     model = build_from_meta(fx["meta"])
     missing, unexpected = model.load_state_dict(fx["state_dict"], strict=False)
     assert not missing and not unexpected
+
+
+def test_paged_kv_allocator_host_logic():
+    """page allocator of the paged KV cache (no kernels involved): unique page addresses inside the slabs, growth that
+    only appends block-table entries, crop returning pages to the free list"""
+    import torch
+    from mantis_b200.models.kv_cache import B200KVCache
+    c = B200KVCache(n_layers=2, slab_tokens=256)
+    with pytest.raises(ValueError):
+        B200KVCache().write(torch.zeros(1, 1, 2, 8), torch.zeros(1, 1, 2, 8), 0)       # n_layers unknown
+    c._configure(3, 2, 8, torch.float32, torch.device("cpu"))
+    assert len(c) == 2 and c.capacity() == 0
+    c.ensure(130)                                      # 2 pages per sequence
+    assert [len(b) for b in c.blocks] == [2, 2, 2] and c.capacity() == 256
+    before = [list(b) for b in c.blocks]
+    tab = c.device_table()
+    assert tab.shape == (3, 8) and tab[:, :2].tolist() == before and int(tab[:, 2:].abs().sum()) == 0
+    c.ensure(1500)                                     # needs more slabs
+    assert len(c.slabs) >= 2 and all(b[:2] == f for b, f in zip(c.blocks, before))
+    pages = [p for b in c.blocks for p in b]
+    assert len(set(pages)) == len(pages) and not set(pages) & set(c.free)
+    page_bytes = c.page_elems * 4
+    for p in pages:
+        assert any(s.data_ptr() <= p and p + page_bytes <= s.data_ptr() + s.numel() * 4 and (p - s.data_ptr()) % page_bytes == 0
+                   for s in c.slabs)
+    assert c.device_table().shape[1] == 16
+    n_free = len(c.free)
+    c.lengths = [300, 300]
+    c.crop(129)
+    assert [len(b) for b in c.blocks] == [2, 2, 2] and len(c.free) == n_free + 3 * 10 and c.get_seq_length() == 129
+    assert c.device_table()[:, :2].tolist() == before
