@@ -3,6 +3,8 @@
 #include <string.h>
 
 static thread_local char g_last_error[512] = {0};
+static thread_local int g_pdl_mode = 0;
+namespace mb { int& pdl_mode() { return g_pdl_mode; } }
 
 extern "C" {
 

@@ -119,6 +119,27 @@ template <> struct Vec8<float> {  // 32 bytes
   }
 };
 
+// ---- programmatic dependent launch (PDL): a kernel launched with the attribute may become resident while its
+// predecessor on the stream is still draining; it must call pdl_wait() before touching anything the predecessor writes
+// (and before writing anything the predecessor reads).  Weights are constant, so the decode kernels prefetch them first.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// set by mb200_llama_decode_step around its launch sequence (thread-local: the C ABI stays re-entrant)
+int& pdl_mode();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                                    Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int num_sms() {
   static int n = 0;
   if (n == 0) {

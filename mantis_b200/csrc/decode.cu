@@ -8,9 +8,12 @@
 // These replace DynamicCache's torch.cat growth + SDPA at q_len 1 in the reference stack
 // (hf: llama/modeling_llama.py:269-270; mantis/models/mllava/modeling_llava.py:477-519).
 #include "common.cuh"
+#include "sm100_ptx.cuh"
+#include <stdlib.h>
 
 namespace {
 using mb::Cvt;
+using namespace sm100;
 
 // ------------------------------------------------------------------ skinny GEMM
 // Up to three weight matrices that share the same input X are served by ONE launch (q/k/v, or gate/up): `seg` picks the
@@ -205,6 +208,216 @@ skinny_mma_kernel(const bf16* __restrict__ X, SkinnySeg sg, const bf16* __restri
   }
 }
 
+// ------------------------------------------------------------------ skinny GEMM, TMA-ring variant (the default)
+// The register-staged kernels above keep only ~64 KB per SM in flight during their load phases and stall in between
+// (ncu: 25 % of DRAM peak, 75 % of issue slots waiting on L1TEX).  Here a producer warp streams the CTA's 8 weight rows
+// (16 in SwiGLU mode) through a shared-memory ring with 1-D bulk copies (cp.async.bulk + mbarrier tx counts, no tensor
+// maps needed), so ~70 KB per CTA x 3 CTAs per SM are always in flight regardless of register pressure, and the weight
+// stream starts BEFORE griddepcontrol.wait: under programmatic dependent launch it overlaps the previous kernel's tail.
+//   MT <= 4 : warp w owns output row w, SIMT FMAs against X read through L1
+//   MT == 16: mma.sync m16n8k16, the 8 warps split each 512-element stage along k and reduce once at the end
+constexpr int SK_KC = 512;                   // k elements per ring stage
+constexpr int SK_ROWB = SK_KC * 2 + 64;      // padded smem row: 272 words = 16 mod 32 -> conflict-free 16-byte fragment reads
+constexpr int SK_THREADS = 288;              // 8 consumer warps + 1 producer warp
+template <int MODE> struct SkRing {
+  static constexpr int ROWS = MODE ? 16 : 8;
+  static constexpr int NS = MODE ? 4 : 8;
+  static constexpr int STAGE_B = ROWS * SK_ROWB;
+  static constexpr int SMEM = NS * STAGE_B + 2 * NS * 8;
+};
+
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+template <int MT, int MODE>
+__global__ void __launch_bounds__(SK_THREADS)
+skinny_ring_kernel(const bf16* __restrict__ X, SkinnySeg sg, const bf16* __restrict__ bias, const bf16* __restrict__ addend,
+                   int M, int K, long long ldx, long long ldw, long long ld_add) {
+  using R = SkRing<MODE>;
+  extern __shared__ __align__(128) unsigned char ring[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + R::NS * R::STAGE_B);
+  uint64_t* empty = full + R::NS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Ntot = (MODE == 1) ? sg.N[0] : (sg.N[0] + sg.N[1] + sg.N[2]);
+  const int n0 = blockIdx.x * 8;
+  const int nchunks = (K + SK_KC - 1) / SK_KC;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < R::NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 8); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  mb::pdl_trigger();
+  if (warp == 8) {
+    // ---------------- producer: weights do not depend on the previous kernel -> no pdl_wait here
+    const bf16* wrow = nullptr;
+    if (lane < R::ROWS) {
+      int n = n0 + (lane & 7); if (n >= Ntot) n = Ntot - 1;
+      if (MODE == 1) wrow = sg.W[lane >> 3] + (size_t)n * ldw;
+      else {
+        int seg = 0, nn = n;
+        if (nn >= sg.N[0]) { nn -= sg.N[0]; seg = 1; if (nn >= sg.N[1]) { nn -= sg.N[1]; seg = 2; } }
+        wrow = sg.W[seg] + (size_t)nn * ldw;
+      }
+    }
+    for (int it = 0; it < nchunks; ++it) {
+      const int s = it % R::NS;
+      if (it >= R::NS) mbar_wait(&empty[s], ((it / R::NS) - 1) & 1);
+      const int kc = min(SK_KC, K - it * SK_KC);
+      if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)(kc * 2 * R::ROWS));
+      __syncwarp();
+      if (lane < R::ROWS) bulk_g2s(ring + s * R::STAGE_B + lane * SK_ROWB, wrow + (size_t)it * SK_KC, (uint32_t)(kc * 2), &full[s]);
+    }
+    return;
+  }
+  // ---------------- consumers
+  mb::pdl_wait();                       // X / addend are the previous kernel's outputs
+  if constexpr (MT <= 4) {
+    float acc[MT], acc2[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) { acc[m] = 0.f; acc2[m] = 0.f; }
+    for (int it = 0; it < nchunks; ++it) {
+      const int s = it % R::NS;
+      const int kbase = it * SK_KC, kc = min(SK_KC, K - kbase);
+      int4 xr[2][MT];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int kk = u * 256 + lane * 8;
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+          xr[u][m] = (kk < kc && m < M) ? __ldg(reinterpret_cast<const int4*>(X + (size_t)m * ldx + kbase + kk)) : make_int4(0, 0, 0, 0);
+      }
+      mbar_wait(&full[s], (it / R::NS) & 1);
+      const unsigned char* st = ring + s * R::STAGE_B + warp * SK_ROWB;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int kk = u * 256 + lane * 8;
+        if (kk < kc) {
+          const int4 wv = *reinterpret_cast<const int4*>(st + kk * 2);
+          const bf162* wh = reinterpret_cast<const bf162*>(&wv);
+          float wf[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { const float2 t = __bfloat1622float2(wh[j]); wf[2 * j] = t.x; wf[2 * j + 1] = t.y; }
+          float wf2[8];
+          if (MODE == 1) {
+            const int4 wv2 = *reinterpret_cast<const int4*>(st + 8 * SK_ROWB + kk * 2);
+            const bf162* wh2 = reinterpret_cast<const bf162*>(&wv2);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const float2 t = __bfloat1622float2(wh2[j]); wf2[2 * j] = t.x; wf2[2 * j + 1] = t.y; }
+          }
+#pragma unroll
+          for (int m = 0; m < MT; ++m) {
+            const bf162* xh = reinterpret_cast<const bf162*>(&xr[u][m]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 xf = __bfloat1622float2(xh[j]);
+              acc[m] = fmaf(wf[2 * j + 1], xf.y, fmaf(wf[2 * j], xf.x, acc[m]));
+              if (MODE == 1) acc2[m] = fmaf(wf2[2 * j + 1], xf.y, fmaf(wf2[2 * j], xf.x, acc2[m]));
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+#pragma unroll
+    for (int m = 0; m < MT; ++m) { acc[m] = mb::warp_sum(acc[m]); if (MODE == 1) acc2[m] = mb::warp_sum(acc2[m]); }
+    const int n = n0 + warp;
+    if (lane == 0 && n < Ntot) {
+      int seg = 0, nn = n;
+      if (MODE != 1 && nn >= sg.N[0]) { nn -= sg.N[0]; seg = 1; if (nn >= sg.N[1]) { nn -= sg.N[1]; seg = 2; } }
+      const float b = (bias && seg == 0) ? __bfloat162float(bias[nn]) : 0.f;
+      bf16* Cs = (seg == 0) ? sg.C[0] : (seg == 1 ? sg.C[1] : sg.C[2]);
+      const long long ldc = (seg == 0) ? sg.ldc[0] : (seg == 1 ? sg.ldc[1] : sg.ldc[2]);
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        if (m < M) {
+          float v = acc[m] + b;
+          if (MODE == 1) {
+            // reference order: act_fn(gate) rounded to bf16, then * up (hf: llama/modeling_llama.py:182-184)
+            const float gq = __bfloat162float(__float2bfloat16_rn(v));
+            const float uq = __bfloat162float(__float2bfloat16_rn(acc2[m]));
+            const float sl = __bfloat162float(__float2bfloat16_rn(gq / (1.f + __expf(-gq))));
+            v = sl * uq;
+          }
+          if (addend && seg == 0) v += __bfloat162float(addend[(size_t)m * ld_add + nn]);
+          Cs[(size_t)m * ldc + nn] = __float2bfloat16_rn(v);
+        }
+      }
+    }
+  } else {
+    // ---------------- mma.sync consumers (M <= 16, K % 32 == 0)
+    const int gid = lane >> 2, tid = lane & 3;
+    const bf16* xlo = X + (size_t)gid * ldx;
+    const bf16* xhi = X + (size_t)(gid + 8) * ldx;
+    const bool lo_ok = gid < M, hi_ok = gid + 8 < M;
+    float c[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
+    const int4 z = make_int4(0, 0, 0, 0);
+    for (int it = 0; it < nchunks; ++it) {
+      const int s = it % R::NS;
+      const int kbase = it * SK_KC, kc = min(SK_KC, K - kbase);
+      int4 xl[2], xh[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int kk = (warp * 2 + u) * 32 + tid * 8;
+        xl[u] = (kk < kc && lo_ok) ? __ldg(reinterpret_cast<const int4*>(xlo + kbase + kk)) : z;
+        xh[u] = (kk < kc && hi_ok) ? __ldg(reinterpret_cast<const int4*>(xhi + kbase + kk)) : z;
+      }
+      mbar_wait(&full[s], (it / R::NS) & 1);
+      const unsigned char* st = ring + s * R::STAGE_B + gid * SK_ROWB;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int kk = (warp * 2 + u) * 32 + tid * 8;
+        if (kk < kc) {
+          const int4 wv = *reinterpret_cast<const int4*>(st + kk * 2);
+          mma_16816(c, xl[u].x, xh[u].x, xl[u].y, xh[u].y, wv.x, wv.y);
+          mma_16816(c, xl[u].z, xh[u].z, xl[u].w, xh[u].w, wv.z, wv.w);
+          if (MODE == 1) {
+            const int4 wv2 = *reinterpret_cast<const int4*>(st + 8 * SK_ROWB + kk * 2);
+            mma_16816(c2, xl[u].x, xh[u].x, xl[u].y, xh[u].y, wv2.x, wv2.y);
+            mma_16816(c2, xl[u].z, xh[u].z, xl[u].w, xh[u].w, wv2.z, wv2.w);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+    consumer_sync();                                   // every stage consumed: the ring is free for the reduction
+    float* red = reinterpret_cast<float*>(ring);       // [7 warps][32 lanes][8]
+    if (warp > 0) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { red[((warp - 1) * 32 + lane) * 8 + e] = c[e]; red[((warp - 1) * 32 + lane) * 8 + 4 + e] = c2[e]; }
+    }
+    consumer_sync();
+    if (warp > 0) return;
+#pragma unroll
+    for (int w = 0; w < 7; ++w)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { c[e] += red[(w * 32 + lane) * 8 + e]; c2[e] += red[(w * 32 + lane) * 8 + 4 + e]; }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int m = gid + ((e >> 1) ? 8 : 0);
+      const int nn_abs = n0 + tid * 2 + (e & 1);
+      if (m >= M || nn_abs >= Ntot) continue;
+      int seg = 0, nn = nn_abs;
+      if (MODE != 1 && nn >= sg.N[0]) { nn -= sg.N[0]; seg = 1; if (nn >= sg.N[1]) { nn -= sg.N[1]; seg = 2; } }
+      bf16* Cs = (seg == 0) ? sg.C[0] : (seg == 1 ? sg.C[1] : sg.C[2]);
+      const long long ldc = (seg == 0) ? sg.ldc[0] : (seg == 1 ? sg.ldc[1] : sg.ldc[2]);
+      float v = c[e] + ((bias && seg == 0) ? __bfloat162float(bias[nn]) : 0.f);
+      if (MODE == 1) {
+        const float gq = __bfloat162float(__float2bfloat16_rn(v));
+        const float uq = __bfloat162float(__float2bfloat16_rn(c2[e]));
+        const float sl = __bfloat162float(__float2bfloat16_rn(gq / (1.f + __expf(-gq))));
+        v = sl * uq;
+      }
+      if (addend && seg == 0) v += __bfloat162float(addend[(size_t)m * ld_add + nn]);
+      Cs[(size_t)m * ldc + nn] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ KV append
 // k_new/v_new: [B, Hkv*hd] rows (row stride ld_new) -> cache[b, pos[b], :, :]  (cache: [B, cap, Hkv*hd])
 __global__ void __launch_bounds__(256)
@@ -254,6 +467,8 @@ rope_append_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const
                    bf16* __restrict__ kc, bf16* __restrict__ vc, const int64_t* __restrict__ pos, const float* __restrict__ inv_freq,
                    int H, int Hkv, int hd, int ctx, long long cap, float rope_scale, const int64_t* __restrict__ table,
                    int table_stride, long long layer_off, long long v_off) {
+  mb::pdl_trigger();
+  mb::pdl_wait();       // q/k/v come from the projection kernel just before
   const int b = blockIdx.y;
   const int half = hd >> 1;
   if (table) {          // paged cache: token ctx of sequence b lives in page table[b][ctx / 128], row ctx % 128
@@ -286,9 +501,18 @@ rope_append_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const
 }
 
 // ------------------------------------------------------------------ split-KV decode attention (head_dim 128)
+// grid (splits, kv_heads, batch), 4 warps; each warp owns 32-key tiles of the CTA's key range.  A warp puts its whole K and
+// V tile in flight at once with 16-byte cp.async (2 x 8 KB per warp, ~200 KB per SM with 3 resident CTAs) and only then
+// waits, so the kernel pays one HBM round trip per tile instead of one per dependent load (the first version streamed
+// 33 KB per CTA through registers: 0.9 TB/s at bs 1).  Keys of older tokens do not depend on the previous kernel, so under
+// programmatic dependent launch their loads are issued before griddepcontrol.wait.
 constexpr int DHD = 128;
-constexpr int DKT = 32;             // keys per smem tile
+constexpr int DKT = 32;             // keys per tile (one per lane)
 constexpr int DWARPS = 4;
+constexpr int DK_ROWB = DHD * 2 + 16;                     // padded K row: lane = key, conflict-free 16-byte reads
+constexpr int DV_ROWB = DHD * 2;
+constexpr int DWARP_SMEM = DKT * (DK_ROWB + DV_ROWB);     // 16896 B per warp
+template <int G> constexpr int dec_smem() { return DWARPS * DWARP_SMEM + G * DHD * 4; }
 
 struct DecP {
   const bf16* q; long long q_sb, q_sh;          // q [B, H, hd]
@@ -299,24 +523,28 @@ struct DecP {
   const int64_t* table; int table_stride; long long layer_off, v_off;   // paged cache (table != null): k/v unused
 };
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
 template <int G>
 __global__ void __launch_bounds__(DWARPS * 32)
 decode_attn_kernel(DecP p) {
-  __shared__ __align__(16) bf162 Ks[DWARPS][DKT][DHD / 2 + 1];   // 65-word rows: conflict-free column walks
-  __shared__ float Qs[G][DHD];
+  extern __shared__ __align__(16) unsigned char dsm[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned char* Kt = dsm + w * DWARP_SMEM;
+  unsigned char* Vt = Kt + DKT * DK_ROWB;
+  float* Qs = reinterpret_cast<float*>(dsm + DWARPS * DWARP_SMEM);      // [G][DHD], pre-scaled
   const int sp = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
-  for (int i = threadIdx.x; i < G * DHD; i += blockDim.x) {
-    const int g = i / DHD, d = i % DHD;
-    Qs[g][d] = __bfloat162float(p.q[(size_t)b * p.q_sb + (size_t)(hk * G + g) * p.q_sh + d]) * p.scale;
-  }
-  __syncthreads();
   const int k_begin = sp * p.chunk, k_end = min(p.ctx, k_begin + p.chunk);
-  float m[G], l[G], acc[G][4];
-#pragma unroll
-  for (int g = 0; g < G; ++g) { m[g] = -INFINITY; l[g] = 0.f; acc[g][0] = acc[g][1] = acc[g][2] = acc[g][3] = 0.f; }
-  for (int k0 = k_begin + w * DKT; k0 < k_end; k0 += DWARPS * DKT) {
-    // chunk is a multiple of DKT, so a 32-key tile never straddles a 128-token page: one table lookup per tile
+  mb::pdl_trigger();
+  const bool has_new = (k_end == p.ctx);       // the range holding the token the previous kernel just appended
+  if (has_new) mb::pdl_wait();
+
+  // chunk is a multiple of DKT, so a 32-key tile never straddles a 128-token page: one table lookup per tile
+  auto issue_tile = [&](int k0) {
     const bf16* kt; const bf16* vt;
     if (p.table) {
       kt = reinterpret_cast<const bf16*>(p.table[(size_t)b * p.table_stride + (k0 >> KV_PAGE_SHIFT)]) + p.layer_off +
@@ -326,15 +554,37 @@ decode_attn_kernel(DecP p) {
       kt = p.k + (size_t)b * p.kv_sb + (size_t)k0 * p.kv_ss + (size_t)hk * p.kv_sh;
       vt = p.v + (size_t)b * p.kv_sb + (size_t)k0 * p.kv_ss + (size_t)hk * p.kv_sh;
     }
-    // stage 32 keys (each 256 B) coalesced: lane handles 16 B pieces
-    for (int e = lane; e < DKT * 16; e += 32) {
-      const int j = e >> 4, c = e & 15, kj = k0 + j;
-      int4 raw = make_int4(0, 0, 0, 0);
-      if (kj < k_end) raw = *reinterpret_cast<const int4*>(kt + (size_t)j * p.kv_ss + c * 8);
-      const bf162* rh = reinterpret_cast<const bf162*>(&raw);
-#pragma unroll
-      for (int t = 0; t < 4; ++t) Ks[w][j][c * 4 + t] = rh[t];
+    const int nk = min(DKT, k_end - k0);
+#pragma unroll 4
+    for (int e = lane; e < DKT * 16; e += 32) {          // 16 pieces of 16 B per key; rows past k_end are zero-filled
+      const int j = e >> 4, c = e & 15;
+      const bool ok = j < nk;
+      cp_async16(Kt + j * DK_ROWB + c * 16, ok ? (const void*)(kt + (size_t)j * p.kv_ss + c * 8) : (const void*)kt, ok ? 16 : 0);
     }
+    cp_async_commit();
+#pragma unroll 4
+    for (int e = lane; e < DKT * 16; e += 32) {
+      const int j = e >> 4, c = e & 15;
+      const bool ok = j < nk;
+      cp_async16(Vt + j * DV_ROWB + c * 16, ok ? (const void*)(vt + (size_t)j * p.kv_ss + c * 8) : (const void*)vt, ok ? 16 : 0);
+    }
+    cp_async_commit();
+  };
+
+  int k0 = k_begin + w * DKT;
+  if (k0 < k_end) issue_tile(k0);
+  if (!has_new) mb::pdl_wait();                // q is the previous kernel's output
+  for (int i = threadIdx.x; i < G * DHD; i += blockDim.x) {
+    const int g = i / DHD, d = i % DHD;
+    Qs[i] = __bfloat162float(p.q[(size_t)b * p.q_sb + (size_t)(hk * G + g) * p.q_sh + d]) * p.scale;
+  }
+  __syncthreads();
+
+  float m[G], l[G], acc[G][4];
+#pragma unroll
+  for (int g = 0; g < G; ++g) { m[g] = -INFINITY; l[g] = 0.f; acc[g][0] = acc[g][1] = acc[g][2] = acc[g][3] = 0.f; }
+  for (; k0 < k_end; k0 += DWARPS * DKT) {
+    cp_async_wait<1>();                        // K tile landed, V may still be in flight
     __syncwarp();
     const int kj = k0 + lane;
     bool vis = kj < k_end;
@@ -342,11 +592,21 @@ decode_attn_kernel(DecP p) {
     float s[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) s[g] = 0.f;
-    if (vis) {
-      for (int d2 = 0; d2 < DHD / 2; ++d2) {
-        const float2 kv = __bfloat1622float2(Ks[w][lane][d2]);
+    const unsigned char* krow = Kt + lane * DK_ROWB;
+#pragma unroll 4
+    for (int c = 0; c < 16; ++c) {
+      const int4 raw = *reinterpret_cast<const int4*>(krow + c * 16);
+      const bf162* kh = reinterpret_cast<const bf162*>(&raw);
+      const float2 k01 = __bfloat1622float2(kh[0]), k23 = __bfloat1622float2(kh[1]);
+      const float2 k45 = __bfloat1622float2(kh[2]), k67 = __bfloat1622float2(kh[3]);
 #pragma unroll
-        for (int g = 0; g < G; ++g) s[g] = fmaf(Qs[g][2 * d2 + 1], kv.y, fmaf(Qs[g][2 * d2], kv.x, s[g]));
+      for (int g = 0; g < G; ++g) {
+        const float4 qa = *reinterpret_cast<const float4*>(Qs + g * DHD + c * 8);
+        const float4 qb = *reinterpret_cast<const float4*>(Qs + g * DHD + c * 8 + 4);
+        float t = s[g];
+        t = fmaf(qa.x, k01.x, t); t = fmaf(qa.y, k01.y, t); t = fmaf(qa.z, k23.x, t); t = fmaf(qa.w, k23.y, t);
+        t = fmaf(qb.x, k45.x, t); t = fmaf(qb.y, k45.y, t); t = fmaf(qb.z, k67.x, t); t = fmaf(qb.w, k67.y, t);
+        s[g] = t;
       }
     }
     float pj[G];
@@ -363,12 +623,11 @@ decode_attn_kernel(DecP p) {
 #pragma unroll
       for (int t = 0; t < 4; ++t) acc[g][t] *= corr;
     }
+    cp_async_wait<0>();                        // V tile
     __syncwarp();
-    // V: lanes own 4 consecutive dims; rows read straight from global (coalesced 256 B per key)
-    for (int j = 0; j < DKT; ++j) {
-      const int kv_j = k0 + j;
-      if (kv_j >= k_end) break;
-      const uint2 raw = *reinterpret_cast<const uint2*>(vt + (size_t)j * p.kv_ss + lane * 4);
+    const int nk = min(DKT, k_end - k0);
+    for (int j = 0; j < nk; ++j) {             // lanes own 4 consecutive dims
+      const uint2 raw = *reinterpret_cast<const uint2*>(Vt + j * DV_ROWB + lane * 8);
       const bf162* vh = reinterpret_cast<const bf162*>(&raw);
       const float2 v01 = __bfloat1622float2(vh[0]), v23 = __bfloat1622float2(vh[1]);
 #pragma unroll
@@ -379,9 +638,10 @@ decode_attn_kernel(DecP p) {
       }
     }
     __syncwarp();
+    if (k0 + DWARPS * DKT < k_end) issue_tile(k0 + DWARPS * DKT);     // only for contexts beyond 64 x 128 keys
   }
-  // combine the 4 warps through shared memory (reuse Ks)
-  float* red = reinterpret_cast<float*>(&Ks[0][0][0]);   // [DWARPS][G][DHD + 2] floats (<= 16.6 KB of the 33 KB tile)
+  // combine the 4 warps through shared memory (the tiles are dead by now)
+  float* red = reinterpret_cast<float*>(dsm);            // [DWARPS][G][DHD + 2] floats (<= 16.6 KB)
   __syncthreads();
 #pragma unroll
   for (int g = 0; g < G; ++g) {
@@ -412,6 +672,8 @@ decode_attn_kernel(DecP p) {
 __global__ void __launch_bounds__(DHD)
 decode_combine_kernel(const float* __restrict__ part, bf16* __restrict__ o, long long o_sb, long long o_sh, int H,
                       int splits) {
+  mb::pdl_trigger();
+  mb::pdl_wait();
   const int h = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
   const float* base = part + ((size_t)b * H + h) * splits * (DHD + 2);
   float M_ = -INFINITY;
@@ -437,8 +699,44 @@ int launch_skinny(const void* X, const SkinnySeg& sg, const void* bias, const vo
                                                        ldx, ldw, ld_add);
   return 0;
 }
+template <int MT, int MODE>
+int launch_ring(const void* X, const SkinnySeg& sg, const void* bias, const void* addend, int M, int K, long long ldx,
+                long long ldw, long long ld_add, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(skinny_ring_kernel<MT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkRing<MODE>::SMEM);
+    configured = true;
+  }
+  const int Ntot = (MODE == 1) ? sg.N[0] : (sg.N[0] + sg.N[1] + sg.N[2]);
+  mb::launch_ex(skinny_ring_kernel<MT, MODE>, dim3((Ntot + 7) / 8), dim3(SK_THREADS), SkRing<MODE>::SMEM, st,
+                mb::pdl_mode() != 0, (const bf16*)X, sg, (const bf16*)bias, (const bf16*)addend, M, K, ldx, ldw, ld_add);
+  return 0;
+}
+static int skinny_ring_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MB200_SKINNY_RING"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v;
+}
 int dispatch_skinny(const void* X, const SkinnySeg& sg, const void* bias, const void* addend, int M, int K, long long ldx,
                     long long ldw, long long ld_add, cudaStream_t st) {
+  if (skinny_ring_enabled() && (sg.mode == 1 || sg.mode == 0)) {
+    const bool aligned = !((reinterpret_cast<uintptr_t>(sg.W[0]) | reinterpret_cast<uintptr_t>(sg.W[1]) |
+                            reinterpret_cast<uintptr_t>(sg.W[2])) & 15);
+    if (aligned && M <= 4) {
+      if (sg.mode == 1) {
+        if (M == 1) return launch_ring<1, 1>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
+        if (M == 2) return launch_ring<2, 1>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
+        return launch_ring<4, 1>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
+      }
+      if (M == 1) return launch_ring<1, 0>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
+      if (M == 2) return launch_ring<2, 0>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
+      return launch_ring<4, 0>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
+    }
+    if (aligned && (K % 32) == 0) {
+      if (sg.mode == 1) return launch_ring<16, 1>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
+      return launch_ring<16, 0>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
+    }
+  }
   if (M > 8 && (K % 32) == 0) {           // tensor-core (mma.sync) variant: HBM-bound instead of FMA-bound
     const int Ntot = (sg.mode == 1) ? sg.N[0] : (sg.N[0] + sg.N[1] + sg.N[2]);
     const int grid = (Ntot + 7) / 8;
@@ -516,9 +814,9 @@ int mb200_rope_append_bf16(const void* q, const void* k, const void* v, void* q_
   if ((hd & 7) || ctx >= capacity) return -EINVAL;
   const int total = (H + Hkv) * (hd / 2) + Hkv * hd / 8;
   dim3 grid((total + 255) / 256, B);
-  rope_append_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)q_out,
-                                                            (bf16*)k_cache, (bf16*)v_cache, pos, inv_freq, H, Hkv, hd, ctx,
-                                                            capacity, rope_scale, nullptr, 0, 0, 0);
+  mb::launch_ex(rope_append_kernel, grid, dim3(256), 0, (cudaStream_t)stream, mb::pdl_mode() != 0, (const bf16*)q,
+                (const bf16*)k, (const bf16*)v, (bf16*)q_out, (bf16*)k_cache, (bf16*)v_cache, pos, inv_freq, H, Hkv, hd, ctx,
+                (long long)capacity, rope_scale, (const int64_t*)nullptr, 0, 0LL, 0LL);
   MB200_CHECK_LAUNCH();
   return MB200_OK;
 }
@@ -532,9 +830,9 @@ int mb200_rope_append_paged_bf16(const void* q, const void* k, const void* v, vo
   if ((hd & 7) || !table || (ctx >> KV_PAGE_SHIFT) >= table_stride) return -EINVAL;
   const int total = (H + Hkv) * (hd / 2) + Hkv * hd / 8;
   dim3 grid((total + 255) / 256, B);
-  rope_append_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)q_out,
-                                                            nullptr, nullptr, pos, inv_freq, H, Hkv, hd, ctx, 0, rope_scale,
-                                                            table, table_stride, layer_off, v_off);
+  mb::launch_ex(rope_append_kernel, grid, dim3(256), 0, (cudaStream_t)stream, mb::pdl_mode() != 0, (const bf16*)q,
+                (const bf16*)k, (const bf16*)v, (bf16*)q_out, (bf16*)nullptr, (bf16*)nullptr, pos, inv_freq, H, Hkv, hd, ctx,
+                0LL, rope_scale, table, table_stride, layer_off, v_off);
   MB200_CHECK_LAUNCH();
   return MB200_OK;
 }
@@ -569,12 +867,22 @@ static int decode_attn_launch(DecP& p, void* o, long long o_sb, long long o_sh, 
   p.chunk = ((p.ctx + p.splits - 1) / p.splits + DKT - 1) / DKT * DKT;      // tile-aligned chunks (see the kernel)
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(p.splits, p.Hkv, p.B);
-  if (G == 1) decode_attn_kernel<1><<<grid, DWARPS * 32, 0, st>>>(p);
-  else if (G == 2) decode_attn_kernel<2><<<grid, DWARPS * 32, 0, st>>>(p);
-  else if (G == 4) decode_attn_kernel<4><<<grid, DWARPS * 32, 0, st>>>(p);
-  else if (G == 8) decode_attn_kernel<8><<<grid, DWARPS * 32, 0, st>>>(p);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(decode_attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem<1>());
+    cudaFuncSetAttribute(decode_attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem<2>());
+    cudaFuncSetAttribute(decode_attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem<4>());
+    cudaFuncSetAttribute(decode_attn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem<8>());
+    configured = true;
+  }
+  const bool pdl = mb::pdl_mode() != 0;
+  if (G == 1) mb::launch_ex(decode_attn_kernel<1>, grid, dim3(DWARPS * 32), dec_smem<1>(), st, pdl, p);
+  else if (G == 2) mb::launch_ex(decode_attn_kernel<2>, grid, dim3(DWARPS * 32), dec_smem<2>(), st, pdl, p);
+  else if (G == 4) mb::launch_ex(decode_attn_kernel<4>, grid, dim3(DWARPS * 32), dec_smem<4>(), st, pdl, p);
+  else if (G == 8) mb::launch_ex(decode_attn_kernel<8>, grid, dim3(DWARPS * 32), dec_smem<8>(), st, pdl, p);
   else return -ENOTSUP;
-  decode_combine_kernel<<<dim3(p.H, p.B), DHD, 0, st>>>(p.part, (bf16*)o, o_sb, o_sh, p.H, p.splits);
+  mb::launch_ex(decode_combine_kernel, dim3(p.H, p.B), dim3(DHD), 0, st, pdl, (const float*)p.part, (bf16*)o, o_sb, o_sh, p.H,
+                p.splits);
   MB200_CHECK_LAUNCH();
   return MB200_OK;
 }

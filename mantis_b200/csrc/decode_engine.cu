@@ -5,11 +5,14 @@
 // mantis_b200/models/kv_cache.py (token-major [B, capacity, Hkv, hd]).
 #include "common.cuh"
 #include "../../include/mantis_b200.h"
+#include <stdlib.h>
 
 namespace {
 __global__ void __launch_bounds__(1024)
 argmax_kernel(const bf16* __restrict__ logits, long long ld, int V, int64_t* __restrict__ out) {
   __shared__ float bv[32]; __shared__ int bi[32];
+  mb::pdl_trigger();
+  mb::pdl_wait();
   const bf16* row = logits + (size_t)blockIdx.x * ld;
   float best = -INFINITY; int idx = 0x7fffffff;
   for (int i = threadIdx.x; i < V; i += blockDim.x) {
@@ -42,7 +45,7 @@ extern "C" {
 
 int mb200_argmax_bf16(const void* logits, long long ld, int B, int V, int64_t* out, void* stream) {
   if (B <= 0) return MB200_OK;
-  argmax_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>((const bf16*)logits, ld, V, out);
+  mb::launch_ex(argmax_kernel, dim3(B), dim3(1024), 0, (cudaStream_t)stream, mb::pdl_mode() != 0, (const bf16*)logits, ld, V, out);
   MB200_CHECK_LAUNCH();
   return MB200_OK;
 }
@@ -66,6 +69,13 @@ long long mb200_decode_ws_bytes(int B, int hidden, int n_heads, int n_kv_heads, 
   return b + 4096;
 }
 
+// Every kernel of the step after the embedding gather is launched with programmatic stream serialization: each one
+// triggers its dependents at entry and calls griddepcontrol.wait before touching the previous kernel's outputs, so launch
+// latency, block scheduling and the weight-stream ramp of kernel n+1 hide under the tail of kernel n (MB200_PDL=0 disables).
+struct PdlScope {            // thread-local launch mode, restored on every exit path
+  explicit PdlScope(int on) { mb::pdl_mode() = on; }
+  ~PdlScope() { mb::pdl_mode() = 0; }
+};
 int mb200_llama_decode_step(const int* dims, const float* fparm, const void* const* layers, const void* const* misc,
                             void* ws, long long ld_logits, void* stream) {
   const int L = dims[0], D = dims[1], H = dims[2], Hkv = dims[3], hd = dims[4], I = dims[5], V = dims[6], B = dims[7];
@@ -93,7 +103,10 @@ int mb200_llama_decode_step(const int* dims, const float* fparm, const void* con
   const float scale = 1.0f / sqrtf((float)hd);
   const int HD = H * hd, KD = Hkv * hd;
 
-  TRY(mb200_embedding_fwd(ids, embed, x, B, D, V, dt, stream));
+  static int pdl = -1;
+  if (pdl < 0) { const char* e = getenv("MB200_PDL"); pdl = (e && e[0] == '0') ? 0 : 1; }
+  TRY(mb200_embedding_fwd(ids, embed, x, B, D, V, dt, stream));      // plain launch: its inputs come from torch kernels
+  PdlScope scope(pdl);
   for (int l = 0; l < L; ++l) {
     const void* const* w = layers + (size_t)l * 11;
     TRY(mb200_rmsnorm_fwd(x, w[7], xn, nullptr, B, D, eps, dt, stream));

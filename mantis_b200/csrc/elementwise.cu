@@ -121,6 +121,8 @@ __global__ void __launch_bounds__(256)
 rmsnorm_fwd_vec_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
                        float* __restrict__ rstd_out, long long n, float eps) {
   constexpr int D = NV * 256;
+  mb::pdl_trigger();          // no-ops unless launched with the programmatic-serialization attribute (decode engine)
+  mb::pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -584,9 +586,10 @@ int mb200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, long l
       !((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(w)) & 15)) {
     long long g = (n + 7) / 8; const long long cap = (long long)mb::num_sms() * 8; if (g > cap) g = cap;
     cudaStream_t st = (cudaStream_t)stream;
-    if (D == 4096) rmsnorm_fwd_vec_kernel<16><<<(int)g, 256, 0, st>>>((const bf16*)x, (const bf16*)w, (bf16*)y, rstd, n, eps);
-    else if (D == 2048) rmsnorm_fwd_vec_kernel<8><<<(int)g, 256, 0, st>>>((const bf16*)x, (const bf16*)w, (bf16*)y, rstd, n, eps);
-    else rmsnorm_fwd_vec_kernel<4><<<(int)g, 256, 0, st>>>((const bf16*)x, (const bf16*)w, (bf16*)y, rstd, n, eps);
+    const bool pdl = mb::pdl_mode() != 0;
+    if (D == 4096) mb::launch_ex(rmsnorm_fwd_vec_kernel<16>, dim3((int)g), dim3(256), 0, st, pdl, (const bf16*)x, (const bf16*)w, (bf16*)y, rstd, n, eps);
+    else if (D == 2048) mb::launch_ex(rmsnorm_fwd_vec_kernel<8>, dim3((int)g), dim3(256), 0, st, pdl, (const bf16*)x, (const bf16*)w, (bf16*)y, rstd, n, eps);
+    else mb::launch_ex(rmsnorm_fwd_vec_kernel<4>, dim3((int)g), dim3(256), 0, st, pdl, (const bf16*)x, (const bf16*)w, (bf16*)y, rstd, n, eps);
     MB200_CHECK_LAUNCH(); return MB200_OK;
   }
   int grid = (int)(n < (long long)mb::num_sms() * 8 ? n : (long long)mb::num_sms() * 8);
