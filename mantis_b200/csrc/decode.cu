@@ -208,215 +208,292 @@ skinny_mma_kernel(const bf16* __restrict__ X, SkinnySeg sg, const bf16* __restri
   }
 }
 
-// ------------------------------------------------------------------ skinny GEMM, TMA-ring variant (the default)
+// ------------------------------------------------------------------ skinny GEMM, TMA-ring variants (the default)
 // The register-staged kernels above keep only ~64 KB per SM in flight during their load phases and stall in between
-// (ncu: 25 % of DRAM peak, 75 % of issue slots waiting on L1TEX).  Here a producer warp streams the CTA's 8 weight rows
-// (16 in SwiGLU mode) through a shared-memory ring with 1-D bulk copies (cp.async.bulk + mbarrier tx counts, no tensor
-// maps needed), so ~70 KB per CTA x 3 CTAs per SM are always in flight regardless of register pressure, and the weight
-// stream starts BEFORE griddepcontrol.wait: under programmatic dependent launch it overlaps the previous kernel's tail.
-//   MT <= 4 : warp w owns output row w, SIMT FMAs against X read through L1
-//   MT == 16: mma.sync m16n8k16, the 8 warps split each 512-element stage along k and reduce once at the end
-constexpr int SK_KC = 512;                   // k elements per ring stage
-constexpr int SK_ROWB = SK_KC * 2 + 64;      // padded smem row: 272 words = 16 mod 32 -> conflict-free 16-byte fragment reads
+// (ncu: 25 % of DRAM peak, 75 % of issue slots waiting on L1TEX).  Here a producer warp streams weights through a
+// shared-memory ring with 1-D bulk copies (cp.async.bulk + mbarrier tx counts, no tensor maps), so ~64 KB per CTA x 3 CTAs
+// per SM stay in flight regardless of register pressure, and the stream starts BEFORE griddepcontrol.wait: under
+// programmatic dependent launch it overlaps the previous kernel's tail.  CTAs are persistent (a balanced number of 8-row
+// groups each), so barriers are set up once and the ring never drains between groups.
+//   skinny_rows_kernel (M <= 4): a stage is ONE weight row (up to 4096 elements = one 8 KB bulk copy -- the first ring
+//     version moved 1 KB per copy and was bound by the per-SM TMA issue rate); the 8 warps split the row along k, keep
+//     8 x M partial sums in registers and reduce across warps once per group.
+//   skinny_ring_kernel (M <= 16): a stage is 8 rows x 1024 k (padded rows) feeding mma.sync m16n8k16; the warps split the
+//     stage along k and keep their X fragments in registers across 4 consecutive 8-row groups.
 constexpr int SK_THREADS = 288;              // 8 consumer warps + 1 producer warp
-template <int MODE> struct SkRing {
-  static constexpr int ROWS = MODE ? 16 : 8;
-  static constexpr int NS = MODE ? 4 : 8;
-  static constexpr int STAGE_B = ROWS * SK_ROWB;
-  static constexpr int SMEM = NS * STAGE_B + 2 * NS * 8;
-};
-
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+__device__ __forceinline__ const bf16* skinny_row_ptr(const SkinnySeg& sg, int n, int which, long long ldw) {
+  if (sg.mode == 1) return (which ? sg.W[1] : sg.W[0]) + (size_t)n * ldw;
+  if (n < sg.N[0]) return sg.W[0] + (size_t)n * ldw;
+  n -= sg.N[0];
+  if (n < sg.N[1]) return sg.W[1] + (size_t)n * ldw;
+  return sg.W[2] + (size_t)(n - sg.N[1]) * ldw;
+}
+// epilogue for output (m, n): bias, SwiGLU, residual addend, store
+__device__ __forceinline__ void skinny_store(const SkinnySeg& sg, int mode, int m, int n, float v, float v2, const bf16* bias,
+                                             const bf16* addend, long long ld_add) {
+  int seg = 0, nn = n;
+  if (mode != 1 && nn >= sg.N[0]) { nn -= sg.N[0]; seg = 1; if (nn >= sg.N[1]) { nn -= sg.N[1]; seg = 2; } }
+  bf16* Cs = (seg == 0) ? sg.C[0] : (seg == 1 ? sg.C[1] : sg.C[2]);
+  const long long ldc = (seg == 0) ? sg.ldc[0] : (seg == 1 ? sg.ldc[1] : sg.ldc[2]);
+  if (bias && seg == 0) v += __bfloat162float(bias[nn]);
+  if (mode == 1) {
+    // reference order: act_fn(gate) rounded to bf16, then * up (hf: llama/modeling_llama.py:182-184)
+    const float gq = __bfloat162float(__float2bfloat16_rn(v));
+    const float uq = __bfloat162float(__float2bfloat16_rn(v2));
+    const float sl = __bfloat162float(__float2bfloat16_rn(gq / (1.f + __expf(-gq))));
+    v = sl * uq;
+  }
+  if (addend && seg == 0) v += __bfloat162float(addend[(size_t)m * ld_add + nn]);
+  Cs[(size_t)m * ldc + nn] = __float2bfloat16_rn(v);
+}
+
+constexpr int RS_K = 4096;                   // elements per row stage (8 KB)
+constexpr int RS_NS = 8;                     // stages in the ring (64 KB)
+constexpr int RS_SMEM = RS_NS * RS_K * 2 + 2 * RS_NS * 8 + 8 * 8 * 4 * 2 * 4;    // ring + barriers + reduction scratch
+
 template <int MT, int MODE>
 __global__ void __launch_bounds__(SK_THREADS)
-skinny_ring_kernel(const bf16* __restrict__ X, SkinnySeg sg, const bf16* __restrict__ bias, const bf16* __restrict__ addend,
-                   int M, int K, long long ldx, long long ldw, long long ld_add) {
-  using R = SkRing<MODE>;
+skinny_rows_kernel(const bf16* __restrict__ X, SkinnySeg sg, const bf16* __restrict__ bias, const bf16* __restrict__ addend,
+                   int M, int K, long long ldx, long long ldw, long long ld_add, int ngroups) {
   extern __shared__ __align__(128) unsigned char ring[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(ring + R::NS * R::STAGE_B);
-  uint64_t* empty = full + R::NS;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + RS_NS * RS_K * 2);
+  uint64_t* empty = full + RS_NS;
+  float* red = reinterpret_cast<float*>(empty + RS_NS);          // [8 warps][8 rows][MT][2]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Ntot = (MODE == 1) ? sg.N[0] : (sg.N[0] + sg.N[1] + sg.N[2]);
-  const int n0 = blockIdx.x * 8;
-  const int nchunks = (K + SK_KC - 1) / SK_KC;
+  const int nkc = (K + RS_K - 1) / RS_K;
+  constexpr int NW = MODE ? 2 : 1;           // matrices per output row (gate, up)
   if (threadIdx.x == 0) {
-    for (int i = 0; i < R::NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 8); }
+    for (int i = 0; i < RS_NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 8); }
     fence_barrier_init();
   }
   __syncthreads();
   mb::pdl_trigger();
   if (warp == 8) {
-    // ---------------- producer: weights do not depend on the previous kernel -> no pdl_wait here
-    const bf16* wrow = nullptr;
-    if (lane < R::ROWS) {
-      int n = n0 + (lane & 7); if (n >= Ntot) n = Ntot - 1;
-      if (MODE == 1) wrow = sg.W[lane >> 3] + (size_t)n * ldw;
-      else {
-        int seg = 0, nn = n;
-        if (nn >= sg.N[0]) { nn -= sg.N[0]; seg = 1; if (nn >= sg.N[1]) { nn -= sg.N[1]; seg = 2; } }
-        wrow = sg.W[seg] + (size_t)nn * ldw;
+    // ---------------- producer (one lane): weights do not depend on the previous kernel -> no pdl_wait
+    if (lane != 0) return;
+    uint32_t it = 0;
+    for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+      for (int kc = 0; kc < nkc; ++kc) {
+        const uint32_t bytes = (uint32_t)min(RS_K, K - kc * RS_K) * 2;
+        for (int r = 0; r < 8; ++r) {
+          int n = g * 8 + r; if (n >= Ntot) n = Ntot - 1;
+#pragma unroll
+          for (int wh = 0; wh < NW; ++wh, ++it) {
+            const uint32_t s = it % RS_NS;
+            if (it >= RS_NS) mbar_wait(&empty[s], ((it / RS_NS) - 1) & 1);
+            mbar_arrive_expect_tx(&full[s], bytes);
+            bulk_g2s(ring + s * (RS_K * 2), skinny_row_ptr(sg, n, wh, ldw) + (size_t)kc * RS_K, bytes, &full[s]);
+          }
+        }
       }
-    }
-    for (int it = 0; it < nchunks; ++it) {
-      const int s = it % R::NS;
-      if (it >= R::NS) mbar_wait(&empty[s], ((it / R::NS) - 1) & 1);
-      const int kc = min(SK_KC, K - it * SK_KC);
-      if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)(kc * 2 * R::ROWS));
-      __syncwarp();
-      if (lane < R::ROWS) bulk_g2s(ring + s * R::STAGE_B + lane * SK_ROWB, wrow + (size_t)it * SK_KC, (uint32_t)(kc * 2), &full[s]);
     }
     return;
   }
-  // ---------------- consumers
+  // ---------------- consumers: warp w owns elements [512 w, 512 w + 512) of every row stage
   mb::pdl_wait();                       // X / addend are the previous kernel's outputs
-  if constexpr (MT <= 4) {
-    float acc[MT], acc2[MT];
+  uint32_t it = 0;
+  for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    float acc[8][MT], acc2[8][MT];
 #pragma unroll
-    for (int m = 0; m < MT; ++m) { acc[m] = 0.f; acc2[m] = 0.f; }
-    for (int it = 0; it < nchunks; ++it) {
-      const int s = it % R::NS;
-      const int kbase = it * SK_KC, kc = min(SK_KC, K - kbase);
-      int4 xr[2][MT];
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int m = 0; m < MT; ++m) { acc[r][m] = 0.f; acc2[r][m] = 0.f; }
+    for (int kc = 0; kc < nkc; ++kc) {
+      const int kbase = kc * RS_K, klen = min(RS_K, K - kbase);
+      float xf[2][MT][8];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const int kk = u * 256 + lane * 8;
+        const int kk = warp * 512 + u * 256 + lane * 8;
 #pragma unroll
-        for (int m = 0; m < MT; ++m)
-          xr[u][m] = (kk < kc && m < M) ? __ldg(reinterpret_cast<const int4*>(X + (size_t)m * ldx + kbase + kk)) : make_int4(0, 0, 0, 0);
+        for (int m = 0; m < MT; ++m) {
+          const int4 xr = (kk < klen && m < M) ? __ldg(reinterpret_cast<const int4*>(X + (size_t)m * ldx + kbase + kk))
+                                               : make_int4(0, 0, 0, 0);
+          const bf162* xh = reinterpret_cast<const bf162*>(&xr);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { const float2 t = __bfloat1622float2(xh[j]); xf[u][m][2 * j] = t.x; xf[u][m][2 * j + 1] = t.y; }
+        }
       }
-      mbar_wait(&full[s], (it / R::NS) & 1);
-      const unsigned char* st = ring + s * R::STAGE_B + warp * SK_ROWB;
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int kk = u * 256 + lane * 8;
-        if (kk < kc) {
-          const int4 wv = *reinterpret_cast<const int4*>(st + kk * 2);
-          const bf162* wh = reinterpret_cast<const bf162*>(&wv);
-          float wf[8];
+      for (int r = 0; r < 8; ++r) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) { const float2 t = __bfloat1622float2(wh[j]); wf[2 * j] = t.x; wf[2 * j + 1] = t.y; }
-          float wf2[8];
-          if (MODE == 1) {
-            const int4 wv2 = *reinterpret_cast<const int4*>(st + 8 * SK_ROWB + kk * 2);
-            const bf162* wh2 = reinterpret_cast<const bf162*>(&wv2);
+        for (int wh = 0; wh < NW; ++wh, ++it) {
+          const uint32_t s = it % RS_NS;
+          mbar_wait(&full[s], (it / RS_NS) & 1);
+          const unsigned char* st = ring + s * (RS_K * 2) + warp * 1024 + lane * 16;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { const float2 t = __bfloat1622float2(wh2[j]); wf2[2 * j] = t.x; wf2[2 * j + 1] = t.y; }
-          }
+          for (int u = 0; u < 2; ++u) {
+            const int kk = warp * 512 + u * 256 + lane * 8;
+            if (kk < klen) {
+              const int4 wv = *reinterpret_cast<const int4*>(st + u * 512);
+              const bf162* wh2 = reinterpret_cast<const bf162*>(&wv);
 #pragma unroll
-          for (int m = 0; m < MT; ++m) {
-            const bf162* xh = reinterpret_cast<const bf162*>(&xr[u][m]);
+              for (int j = 0; j < 4; ++j) {
+                const float2 t = __bfloat1622float2(wh2[j]);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 xf = __bfloat1622float2(xh[j]);
-              acc[m] = fmaf(wf[2 * j + 1], xf.y, fmaf(wf[2 * j], xf.x, acc[m]));
-              if (MODE == 1) acc2[m] = fmaf(wf2[2 * j + 1], xf.y, fmaf(wf2[2 * j], xf.x, acc2[m]));
+                for (int m = 0; m < MT; ++m) {
+                  if (wh == 0) acc[r][m] = fmaf(t.y, xf[u][m][2 * j + 1], fmaf(t.x, xf[u][m][2 * j], acc[r][m]));
+                  else acc2[r][m] = fmaf(t.y, xf[u][m][2 * j + 1], fmaf(t.x, xf[u][m][2 * j], acc2[r][m]));
+                }
+              }
             }
           }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[s]);
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);
     }
+    // cross-lane, then cross-warp reduction; thread t < 8 * MT finishes output (row t / MT, batch t % MT)
 #pragma unroll
-    for (int m = 0; m < MT; ++m) { acc[m] = mb::warp_sum(acc[m]); if (MODE == 1) acc2[m] = mb::warp_sum(acc2[m]); }
-    const int n = n0 + warp;
-    if (lane == 0 && n < Ntot) {
-      int seg = 0, nn = n;
-      if (MODE != 1 && nn >= sg.N[0]) { nn -= sg.N[0]; seg = 1; if (nn >= sg.N[1]) { nn -= sg.N[1]; seg = 2; } }
-      const float b = (bias && seg == 0) ? __bfloat162float(bias[nn]) : 0.f;
-      bf16* Cs = (seg == 0) ? sg.C[0] : (seg == 1 ? sg.C[1] : sg.C[2]);
-      const long long ldc = (seg == 0) ? sg.ldc[0] : (seg == 1 ? sg.ldc[1] : sg.ldc[2]);
+    for (int r = 0; r < 8; ++r)
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
-        if (m < M) {
-          float v = acc[m] + b;
-          if (MODE == 1) {
-            // reference order: act_fn(gate) rounded to bf16, then * up (hf: llama/modeling_llama.py:182-184)
-            const float gq = __bfloat162float(__float2bfloat16_rn(v));
-            const float uq = __bfloat162float(__float2bfloat16_rn(acc2[m]));
-            const float sl = __bfloat162float(__float2bfloat16_rn(gq / (1.f + __expf(-gq))));
-            v = sl * uq;
+        const float a = mb::warp_sum(acc[r][m]);
+        const float a2 = MODE ? mb::warp_sum(acc2[r][m]) : 0.f;
+        if (lane == 0) { red[((warp * 8 + r) * 4 + m) * 2] = a; red[((warp * 8 + r) * 4 + m) * 2 + 1] = a2; }
+      }
+    consumer_sync();
+    if (threadIdx.x < 8 * MT) {
+      const int r = threadIdx.x / MT, m = threadIdx.x % MT;
+      float v = 0.f, v2 = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) { v += red[((w * 8 + r) * 4 + m) * 2]; v2 += red[((w * 8 + r) * 4 + m) * 2 + 1]; }
+      const int n = g * 8 + r;
+      if (n < Ntot && m < M) skinny_store(sg, MODE, m, n, v, v2, bias, addend, ld_add);
+    }
+    consumer_sync();                    // red is reused by the next group
+  }
+}
+
+constexpr int SK_KC = 1024;                  // k elements per mma ring stage (2 KB bulk copies)
+constexpr int SK_ROWB = SK_KC * 2 + 64;      // padded smem row: 528 words = 16 mod 32 -> conflict-free 16-byte fragment reads
+constexpr int SK_NS = 6;
+constexpr int SK_RG = 4;                     // 8-row groups per X-fragment load: X is re-read from L2 once per 32 weight rows
+constexpr int SK_STAGE_B = 8 * SK_ROWB;      // (with one group per load the X traffic was 2x the weight traffic: L2-bound)
+constexpr int SK_SMEM = SK_NS * SK_STAGE_B + 2 * SK_NS * 8;
+
+template <int MODE>
+__global__ void __launch_bounds__(SK_THREADS, 2)
+skinny_ring_kernel(const bf16* __restrict__ X, SkinnySeg sg, const bf16* __restrict__ bias, const bf16* __restrict__ addend,
+                   int M, int K, long long ldx, long long ldw, long long ld_add, int nsuper) {
+  extern __shared__ __align__(128) unsigned char ring[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + SK_NS * SK_STAGE_B);
+  uint64_t* empty = full + SK_NS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Ntot = (MODE == 1) ? sg.N[0] : (sg.N[0] + sg.N[1] + sg.N[2]);
+  const int nchunks = (K + SK_KC - 1) / SK_KC;
+  constexpr int NW = MODE ? 2 : 1;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < SK_NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 8); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  mb::pdl_trigger();
+  if (warp == 8) {
+    // ---------------- producer: lanes 0..7 each own one row of the stage
+    uint32_t it = 0;
+    for (int su = blockIdx.x; su < nsuper; su += gridDim.x) {
+      for (int c = 0; c < nchunks; ++c) {
+        const uint32_t bytes = (uint32_t)min(SK_KC, K - c * SK_KC) * 2;
+        for (int rg = 0; rg < SK_RG; ++rg) {
+          int n = (su * SK_RG + rg) * 8 + (lane & 7); if (n >= Ntot) n = Ntot - 1;
+#pragma unroll
+          for (int wh = 0; wh < NW; ++wh, ++it) {
+            const uint32_t s = it % SK_NS;
+            if (it >= SK_NS) mbar_wait(&empty[s], ((it / SK_NS) - 1) & 1);
+            if (lane == 0) mbar_arrive_expect_tx(&full[s], bytes * 8);
+            __syncwarp();
+            if (lane < 8) bulk_g2s(ring + s * SK_STAGE_B + lane * SK_ROWB, skinny_row_ptr(sg, n, wh, ldw) + (size_t)c * SK_KC, bytes, &full[s]);
           }
-          if (addend && seg == 0) v += __bfloat162float(addend[(size_t)m * ld_add + nn]);
-          Cs[(size_t)m * ldc + nn] = __float2bfloat16_rn(v);
         }
       }
     }
-  } else {
-    // ---------------- mma.sync consumers (M <= 16, K % 32 == 0)
-    const int gid = lane >> 2, tid = lane & 3;
-    const bf16* xlo = X + (size_t)gid * ldx;
-    const bf16* xhi = X + (size_t)(gid + 8) * ldx;
-    const bool lo_ok = gid < M, hi_ok = gid + 8 < M;
-    float c[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
-    const int4 z = make_int4(0, 0, 0, 0);
-    for (int it = 0; it < nchunks; ++it) {
-      const int s = it % R::NS;
-      const int kbase = it * SK_KC, kc = min(SK_KC, K - kbase);
-      int4 xl[2], xh[2];
+    return;
+  }
+  // ---------------- consumers: warp w owns k32-chunks 4w .. 4w+3 of every stage
+  mb::pdl_wait();
+  const int gid = lane >> 2, tid = lane & 3;
+  const bf16* xlo = X + (size_t)gid * ldx;
+  const bf16* xhi = X + (size_t)(gid + 8) * ldx;
+  const bool lo_ok = gid < M, hi_ok = gid + 8 < M;
+  const int4 z = make_int4(0, 0, 0, 0);
+  float* scratch = reinterpret_cast<float*>(empty + SK_NS);     // [7 warps][32 lanes][8] partial tiles of one group
+  uint32_t it = 0;
+  for (int su = blockIdx.x; su < nsuper; su += gridDim.x) {
+    float c[SK_RG][4], c2[SK_RG][4];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int kk = (warp * 2 + u) * 32 + tid * 8;
+    for (int rg = 0; rg < SK_RG; ++rg)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { c[rg][e] = 0.f; c2[rg][e] = 0.f; }
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const int kbase = ch * SK_KC, kc = min(SK_KC, K - kbase);
+      int4 xl[4], xh[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int kk = (warp * 4 + u) * 32 + tid * 8;
         xl[u] = (kk < kc && lo_ok) ? __ldg(reinterpret_cast<const int4*>(xlo + kbase + kk)) : z;
         xh[u] = (kk < kc && hi_ok) ? __ldg(reinterpret_cast<const int4*>(xhi + kbase + kk)) : z;
       }
-      mbar_wait(&full[s], (it / R::NS) & 1);
-      const unsigned char* st = ring + s * R::STAGE_B + gid * SK_ROWB;
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int kk = (warp * 2 + u) * 32 + tid * 8;
-        if (kk < kc) {
-          const int4 wv = *reinterpret_cast<const int4*>(st + kk * 2);
-          mma_16816(c, xl[u].x, xh[u].x, xl[u].y, xh[u].y, wv.x, wv.y);
-          mma_16816(c, xl[u].z, xh[u].z, xl[u].w, xh[u].w, wv.z, wv.w);
-          if (MODE == 1) {
-            const int4 wv2 = *reinterpret_cast<const int4*>(st + 8 * SK_ROWB + kk * 2);
-            mma_16816(c2, xl[u].x, xh[u].x, xl[u].y, xh[u].y, wv2.x, wv2.y);
-            mma_16816(c2, xl[u].z, xh[u].z, xl[u].w, xh[u].w, wv2.z, wv2.w);
+      for (int rg = 0; rg < SK_RG; ++rg) {
+#pragma unroll
+        for (int wh = 0; wh < NW; ++wh, ++it) {
+          const uint32_t s = it % SK_NS;
+          mbar_wait(&full[s], (it / SK_NS) & 1);
+          const unsigned char* st = ring + s * SK_STAGE_B + gid * SK_ROWB;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int kk = (warp * 4 + u) * 32 + tid * 8;
+            if (kk < kc) {
+              const int4 wv = *reinterpret_cast<const int4*>(st + kk * 2);
+              if (wh == 0) {
+                mma_16816(c[rg], xl[u].x, xh[u].x, xl[u].y, xh[u].y, wv.x, wv.y);
+                mma_16816(c[rg], xl[u].z, xh[u].z, xl[u].w, xh[u].w, wv.z, wv.w);
+              } else {
+                mma_16816(c2[rg], xl[u].x, xh[u].x, xl[u].y, xh[u].y, wv.x, wv.y);
+                mma_16816(c2[rg], xl[u].z, xh[u].z, xl[u].w, xh[u].w, wv.z, wv.w);
+              }
+            }
           }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[s]);
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);
     }
-    consumer_sync();                                   // every stage consumed: the ring is free for the reduction
-    float* red = reinterpret_cast<float*>(ring);       // [7 warps][32 lanes][8]
-    if (warp > 0) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { red[((warp - 1) * 32 + lane) * 8 + e] = c[e]; red[((warp - 1) * 32 + lane) * 8 + 4 + e] = c2[e]; }
-    }
-    consumer_sync();
-    if (warp > 0) return;
+    for (int rg = 0; rg < SK_RG; ++rg) {                 // cross-warp reduction, one 8-row group per round (7 KB scratch)
+      if (warp > 0) {
 #pragma unroll
-    for (int w = 0; w < 7; ++w)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) { c[e] += red[(w * 32 + lane) * 8 + e]; c2[e] += red[(w * 32 + lane) * 8 + 4 + e]; }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int m = gid + ((e >> 1) ? 8 : 0);
-      const int nn_abs = n0 + tid * 2 + (e & 1);
-      if (m >= M || nn_abs >= Ntot) continue;
-      int seg = 0, nn = nn_abs;
-      if (MODE != 1 && nn >= sg.N[0]) { nn -= sg.N[0]; seg = 1; if (nn >= sg.N[1]) { nn -= sg.N[1]; seg = 2; } }
-      bf16* Cs = (seg == 0) ? sg.C[0] : (seg == 1 ? sg.C[1] : sg.C[2]);
-      const long long ldc = (seg == 0) ? sg.ldc[0] : (seg == 1 ? sg.ldc[1] : sg.ldc[2]);
-      float v = c[e] + ((bias && seg == 0) ? __bfloat162float(bias[nn]) : 0.f);
-      if (MODE == 1) {
-        const float gq = __bfloat162float(__float2bfloat16_rn(v));
-        const float uq = __bfloat162float(__float2bfloat16_rn(c2[e]));
-        const float sl = __bfloat162float(__float2bfloat16_rn(gq / (1.f + __expf(-gq))));
-        v = sl * uq;
+        for (int e = 0; e < 4; ++e) {
+          scratch[((warp - 1) * 32 + lane) * 8 + e] = c[rg][e];
+          scratch[((warp - 1) * 32 + lane) * 8 + 4 + e] = c2[rg][e];
+        }
       }
-      if (addend && seg == 0) v += __bfloat162float(addend[(size_t)m * ld_add + nn]);
-      Cs[(size_t)m * ldc + nn] = __float2bfloat16_rn(v);
+      consumer_sync();
+      if (warp == 0) {
+#pragma unroll
+        for (int w = 0; w < 7; ++w)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { c[rg][e] += scratch[(w * 32 + lane) * 8 + e]; c2[rg][e] += scratch[(w * 32 + lane) * 8 + 4 + e]; }
+        // c[0], c[1]: (row gid, cols 2 tid, +1) ; c[2], c[3]: (row gid + 8, same cols)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int m = gid + ((e >> 1) ? 8 : 0);
+          const int n = (su * SK_RG + rg) * 8 + tid * 2 + (e & 1);
+          if (m < M && n < Ntot) skinny_store(sg, MODE, m, n, c[rg][e], c2[rg][e], bias, addend, ld_add);
+        }
+      }
+      consumer_sync();
     }
   }
 }
+constexpr int SK_SMEM_TOTAL = SK_SMEM + 7 * 32 * 8 * 4;
 
 // ------------------------------------------------------------------ KV append
 // k_new/v_new: [B, Hkv*hd] rows (row stride ld_new) -> cache[b, pos[b], :, :]  (cache: [B, cap, Hkv*hd])
@@ -669,22 +746,204 @@ decode_attn_kernel(DecP p) {
   }
 }
 
+// ---- tensor-core variant (the default): same tiling and loads, but the per-tile math runs on mma.sync m16n8k16 --
+// S = Q K^T with the GQA group's query heads on the M side (rows >= G are zero), P V with the S accumulators re-packed as the
+// A operand (their register layouts coincide) and V^T fetched with ldmatrix.trans.  ~220 instructions per 32-key tile instead
+// of ~1700 on the FMA pipe, so a warp spends its time waiting for HBM, not issuing (the SIMT kernel reached 3.3 TB/s at
+// batch 16).  fp32 softmax, P rounded to bf16 before P V like the reference (hf: llama/modeling_llama.py:216-218).
+constexpr int DM_ROWB = DHD * 2 + 16;                       // K and V rows padded to 272 B (conflict-free LDS.32 / ldmatrix)
+constexpr int DM_WARP_SMEM = DKT * DM_ROWB * 2;             // 17408 B per warp
+constexpr int DM_QPITCH = DHD + 8;
+constexpr int DM_SMEM = DWARPS * DM_WARP_SMEM + 8 * DM_QPITCH * 2;
+
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(smem_u32(row)));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  const bf162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(DWARPS * 32, 3)
+decode_attn_mma_kernel(DecP p, int G) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int gid = lane >> 2, tid = lane & 3;
+  unsigned char* Kt = dsm + w * DM_WARP_SMEM;
+  unsigned char* Vt = Kt + DKT * DM_ROWB;
+  bf16* Qs = reinterpret_cast<bf16*>(dsm + DWARPS * DM_WARP_SMEM);        // [8][DM_QPITCH], rows >= G zero
+  const int sp = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
+  const int k_begin = sp * p.chunk, k_end = min(p.ctx, k_begin + p.chunk);
+  mb::pdl_trigger();
+  const bool has_new = (k_end == p.ctx);
+  if (has_new) mb::pdl_wait();
+
+  auto issue_tile = [&](int k0) {
+    const bf16* kt; const bf16* vt;
+    if (p.table) {
+      kt = reinterpret_cast<const bf16*>(p.table[(size_t)b * p.table_stride + (k0 >> KV_PAGE_SHIFT)]) + p.layer_off +
+           (size_t)(k0 & (KV_PAGE - 1)) * p.kv_ss + (size_t)hk * p.kv_sh;
+      vt = kt + p.v_off;
+    } else {
+      kt = p.k + (size_t)b * p.kv_sb + (size_t)k0 * p.kv_ss + (size_t)hk * p.kv_sh;
+      vt = p.v + (size_t)b * p.kv_sb + (size_t)k0 * p.kv_ss + (size_t)hk * p.kv_sh;
+    }
+    const int nk = min(DKT, k_end - k0);
+#pragma unroll 4
+    for (int e = lane; e < DKT * 16; e += 32) {
+      const int j = e >> 4, c = e & 15;
+      const bool ok = j < nk;
+      cp_async16(Kt + j * DM_ROWB + c * 16, ok ? (const void*)(kt + (size_t)j * p.kv_ss + c * 8) : (const void*)kt, ok ? 16 : 0);
+    }
+    cp_async_commit();
+#pragma unroll 4
+    for (int e = lane; e < DKT * 16; e += 32) {
+      const int j = e >> 4, c = e & 15;
+      const bool ok = j < nk;
+      cp_async16(Vt + j * DM_ROWB + c * 16, ok ? (const void*)(vt + (size_t)j * p.kv_ss + c * 8) : (const void*)vt, ok ? 16 : 0);
+    }
+    cp_async_commit();
+  };
+
+  int k0 = k_begin + w * DKT;
+  if (k0 < k_end) issue_tile(k0);
+  if (!has_new) mb::pdl_wait();
+  for (int i = threadIdx.x; i < 8 * DHD; i += blockDim.x) {
+    const int g = i / DHD, d = i % DHD;
+    Qs[g * DM_QPITCH + d] = (g < G) ? p.q[(size_t)b * p.q_sb + (size_t)(hk * G + g) * p.q_sh + d] : __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+  uint32_t qa[8][2];
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    qa[ks][0] = *reinterpret_cast<const uint32_t*>(Qs + gid * DM_QPITCH + ks * 16 + 2 * tid);
+    qa[ks][1] = *reinterpret_cast<const uint32_t*>(Qs + gid * DM_QPITCH + ks * 16 + 8 + 2 * tid);
+  }
+  float m_run = -INFINITY, l_run = 0.f;          // row gid's running max / sum (replicated over the 4 lanes of a quad)
+  float o[16][4];
+#pragma unroll
+  for (int nt = 0; nt < 16; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
+
+  for (; k0 < k_end; k0 += DWARPS * DKT) {
+    cp_async_wait<1>();
+    __syncwarp();
+    float sc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+      const unsigned char* kr = Kt + (nt * 8 + gid) * DM_ROWB + 4 * tid;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + ks * 32);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + ks * 32 + 16);
+        mma_16816(sc[nt], qa[ks][0], 0u, qa[ks][1], 0u, b0, b1);
+      }
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int kj = k0 + nt * 8 + 2 * tid + e;
+        bool vis = kj < k_end;
+        if (vis && p.kbits) vis = (p.kbits[(size_t)b * p.kbits_stride + (kj >> 5)] >> (kj & 31)) & 1u;
+        sc[nt][e] = vis ? sc[nt][e] * p.scale : -INFINITY;
+        mx = fmaxf(mx, sc[nt][e]);
+      }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    const float m_new = fmaxf(m_run, mx);
+    const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+    const float corr = (m_run == -INFINITY) ? 0.f : __expf(m_run - m_use);
+    float rs = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float pv = (sc[nt][e] == -INFINITY) ? 0.f : __expf(sc[nt][e] - m_use);
+        sc[nt][e] = pv; rs += pv;
+      }
+    rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+    rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+    l_run = l_run * corr + rs; m_run = m_new;
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) { o[nt][0] *= corr; o[nt][1] *= corr; }
+    uint32_t pa[2][2];
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      pa[kk][0] = pack_bf16x2(sc[2 * kk][0], sc[2 * kk][1]);
+      pa[kk][1] = pack_bf16x2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
+    }
+    cp_async_wait<0>();
+    __syncwarp();
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) {
+      uint32_t v0, v1, v2, v3;          // (keys 0-7, 8-15, 16-23, 24-31) x dims nt*8..+7, transposed
+      ldmatrix_x4_trans(v0, v1, v2, v3, Vt + lane * DM_ROWB + nt * 16);
+      mma_16816(o[nt], pa[0][0], 0u, pa[0][1], 0u, v0, v1);
+      mma_16816(o[nt], pa[1][0], 0u, pa[1][1], 0u, v2, v3);
+    }
+    __syncwarp();
+    if (k0 + DWARPS * DKT < k_end) issue_tile(k0 + DWARPS * DKT);
+  }
+  // combine the 4 warps through shared memory (the tiles are dead by now)
+  float* red = reinterpret_cast<float*>(dsm);            // [DWARPS][G][DHD + 2] floats
+  __syncthreads();
+  if (gid < G) {
+    float* r = red + ((size_t)w * G + gid) * (DHD + 2);
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) { r[nt * 8 + 2 * tid] = o[nt][0]; r[nt * 8 + 2 * tid + 1] = o[nt][1]; }
+    if (tid == 0) { r[DHD] = m_run; r[DHD + 1] = l_run; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < G * DHD; i += blockDim.x) {
+    const int g = i / DHD, d = i % DHD;
+    float M_ = -INFINITY;
+#pragma unroll
+    for (int ww = 0; ww < DWARPS; ++ww) M_ = fmaxf(M_, red[((size_t)ww * G + g) * (DHD + 2) + DHD]);
+    float ov = 0.f, L = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < DWARPS; ++ww) {
+      const float* r = red + ((size_t)ww * G + g) * (DHD + 2);
+      const float s2 = (r[DHD] == -INFINITY) ? 0.f : __expf(r[DHD] - M_);
+      ov += r[d] * s2; L += r[DHD + 1] * s2;
+    }
+    float* out = p.part + (((size_t)b * p.H + hk * G + g) * p.splits + sp) * (DHD + 2);
+    out[d] = ov;
+    if (d == 0) { out[DHD] = M_; out[DHD + 1] = L; }
+  }
+}
+
+// merges the per-split (max, sum, out) triples: warp 0 turns the <= 64 (m, l) pairs into rescale factors with two parallel
+// loads per lane, then every thread sums its output dim over the splits with independent (unrolled) loads
 __global__ void __launch_bounds__(DHD)
 decode_combine_kernel(const float* __restrict__ part, bf16* __restrict__ o, long long o_sb, long long o_sh, int H,
                       int splits) {
+  __shared__ float sc_s[64];
+  __shared__ float inv_l;
   mb::pdl_trigger();
   mb::pdl_wait();
   const int h = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
   const float* base = part + ((size_t)b * H + h) * splits * (DHD + 2);
-  float M_ = -INFINITY;
-  for (int s = 0; s < splits; ++s) M_ = fmaxf(M_, base[(size_t)s * (DHD + 2) + DHD]);
-  float acc = 0.f, L = 0.f;
-  for (int s = 0; s < splits; ++s) {
-    const float* r = base + (size_t)s * (DHD + 2);
-    const float sc = (r[DHD] == -INFINITY) ? 0.f : __expf(r[DHD] - M_);
-    acc += r[d] * sc; L += r[DHD + 1] * sc;
+  if (d < 32) {
+    const int s0 = d, s1 = d + 32;
+    const float m0 = s0 < splits ? base[(size_t)s0 * (DHD + 2) + DHD] : -INFINITY;
+    const float m1 = s1 < splits ? base[(size_t)s1 * (DHD + 2) + DHD] : -INFINITY;
+    const float l0 = s0 < splits ? base[(size_t)s0 * (DHD + 2) + DHD + 1] : 0.f;
+    const float l1 = s1 < splits ? base[(size_t)s1 * (DHD + 2) + DHD + 1] : 0.f;
+    const float M_ = mb::warp_max(fmaxf(m0, m1));
+    const float c0 = (m0 == -INFINITY) ? 0.f : __expf(m0 - M_);
+    const float c1 = (m1 == -INFINITY) ? 0.f : __expf(m1 - M_);
+    const float L = mb::warp_sum(l0 * c0 + l1 * c1);
+    sc_s[s0] = c0; sc_s[s1] = c1;
+    if (d == 0) inv_l = L > 0.f ? 1.f / L : 0.f;
   }
-  o[(size_t)b * o_sb + (size_t)h * o_sh + d] = __float2bfloat16_rn(L > 0.f ? acc / L : 0.f);
+  __syncthreads();
+  float acc = 0.f;
+#pragma unroll 8
+  for (int s = 0; s < splits; ++s) acc = fmaf(base[(size_t)s * (DHD + 2) + d], sc_s[s], acc);
+  o[(size_t)b * o_sb + (size_t)h * o_sh + d] = __float2bfloat16_rn(acc * inv_l);
 }
 
 template <int MT>
@@ -699,17 +958,40 @@ int launch_skinny(const void* X, const SkinnySeg& sg, const void* bias, const vo
                                                        ldx, ldw, ld_add);
   return 0;
 }
+// persistent grid: every CTA resident at once (occupancy x SMs slots), a balanced number of 8-row groups per CTA
+static inline int skinny_grid(int ngroups, int ctas_per_sm) {
+  const int slots = mb::num_sms() * (ctas_per_sm > 0 ? ctas_per_sm : 1);
+  const int per = (ngroups + slots - 1) / slots;
+  return (ngroups + per - 1) / per;
+}
 template <int MT, int MODE>
-int launch_ring(const void* X, const SkinnySeg& sg, const void* bias, const void* addend, int M, int K, long long ldx,
+int launch_rows(const void* X, const SkinnySeg& sg, const void* bias, const void* addend, int M, int K, long long ldx,
                 long long ldw, long long ld_add, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(skinny_ring_kernel<MT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkRing<MODE>::SMEM);
-    configured = true;
+  static int occ = 0;
+  if (!occ) {
+    cudaFuncSetAttribute(skinny_rows_kernel<MT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, skinny_rows_kernel<MT, MODE>, SK_THREADS, RS_SMEM);
+    if (occ < 1) occ = 1;
   }
   const int Ntot = (MODE == 1) ? sg.N[0] : (sg.N[0] + sg.N[1] + sg.N[2]);
-  mb::launch_ex(skinny_ring_kernel<MT, MODE>, dim3((Ntot + 7) / 8), dim3(SK_THREADS), SkRing<MODE>::SMEM, st,
-                mb::pdl_mode() != 0, (const bf16*)X, sg, (const bf16*)bias, (const bf16*)addend, M, K, ldx, ldw, ld_add);
+  const int ngroups = (Ntot + 7) / 8;
+  mb::launch_ex(skinny_rows_kernel<MT, MODE>, dim3(skinny_grid(ngroups, occ)), dim3(SK_THREADS), RS_SMEM, st, mb::pdl_mode() != 0,
+                (const bf16*)X, sg, (const bf16*)bias, (const bf16*)addend, M, K, ldx, ldw, ld_add, ngroups);
+  return 0;
+}
+template <int MODE>
+int launch_ring(const void* X, const SkinnySeg& sg, const void* bias, const void* addend, int M, int K, long long ldx,
+                long long ldw, long long ld_add, cudaStream_t st) {
+  static int occ = 0;
+  if (!occ) {
+    cudaFuncSetAttribute(skinny_ring_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM_TOTAL);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, skinny_ring_kernel<MODE>, SK_THREADS, SK_SMEM_TOTAL);
+    if (occ < 1) occ = 1;
+  }
+  const int Ntot = (MODE == 1) ? sg.N[0] : (sg.N[0] + sg.N[1] + sg.N[2]);
+  const int ngroups = (Ntot + 8 * SK_RG - 1) / (8 * SK_RG);
+  mb::launch_ex(skinny_ring_kernel<MODE>, dim3(skinny_grid(ngroups, occ)), dim3(SK_THREADS), SK_SMEM_TOTAL, st, mb::pdl_mode() != 0,
+                (const bf16*)X, sg, (const bf16*)bias, (const bf16*)addend, M, K, ldx, ldw, ld_add, ngroups);
   return 0;
 }
 static int skinny_ring_enabled() {
@@ -722,19 +1004,19 @@ int dispatch_skinny(const void* X, const SkinnySeg& sg, const void* bias, const 
   if (skinny_ring_enabled() && (sg.mode == 1 || sg.mode == 0)) {
     const bool aligned = !((reinterpret_cast<uintptr_t>(sg.W[0]) | reinterpret_cast<uintptr_t>(sg.W[1]) |
                             reinterpret_cast<uintptr_t>(sg.W[2])) & 15);
-    if (aligned && M <= 4) {
+    if (aligned && (M <= 2 || (M <= 4 && (K % 32) != 0))) {
       if (sg.mode == 1) {
-        if (M == 1) return launch_ring<1, 1>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
-        if (M == 2) return launch_ring<2, 1>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
-        return launch_ring<4, 1>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
+        if (M == 1) return launch_rows<1, 1>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
+        if (M == 2) return launch_rows<2, 1>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
+        return launch_rows<4, 1>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
       }
-      if (M == 1) return launch_ring<1, 0>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
-      if (M == 2) return launch_ring<2, 0>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
-      return launch_ring<4, 0>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
+      if (M == 1) return launch_rows<1, 0>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
+      if (M == 2) return launch_rows<2, 0>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
+      return launch_rows<4, 0>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
     }
     if (aligned && (K % 32) == 0) {
-      if (sg.mode == 1) return launch_ring<16, 1>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
-      return launch_ring<16, 0>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
+      if (sg.mode == 1) return launch_ring<1>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
+      return launch_ring<0>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
     }
   }
   if (M > 8 && (K % 32) == 0) {           // tensor-core (mma.sync) variant: HBM-bound instead of FMA-bound
@@ -876,7 +1158,13 @@ static int decode_attn_launch(DecP& p, void* o, long long o_sb, long long o_sh, 
     configured = true;
   }
   const bool pdl = mb::pdl_mode() != 0;
-  if (G == 1) mb::launch_ex(decode_attn_kernel<1>, grid, dim3(DWARPS * 32), dec_smem<1>(), st, pdl, p);
+  static int use_mma = -1;
+  if (use_mma < 0) {
+    const char* e = getenv("MB200_DECODE_ATTN_MMA"); use_mma = (e && e[0] == '0') ? 0 : 1;
+    cudaFuncSetAttribute(decode_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM);
+  }
+  if (use_mma && G <= 8) mb::launch_ex(decode_attn_mma_kernel, grid, dim3(DWARPS * 32), DM_SMEM, st, pdl, p, G);
+  else if (G == 1) mb::launch_ex(decode_attn_kernel<1>, grid, dim3(DWARPS * 32), dec_smem<1>(), st, pdl, p);
   else if (G == 2) mb::launch_ex(decode_attn_kernel<2>, grid, dim3(DWARPS * 32), dec_smem<2>(), st, pdl, p);
   else if (G == 4) mb::launch_ex(decode_attn_kernel<4>, grid, dim3(DWARPS * 32), dec_smem<4>(), st, pdl, p);
   else if (G == 8) mb::launch_ex(decode_attn_kernel<8>, grid, dim3(DWARPS * 32), dec_smem<8>(), st, pdl, p);

@@ -114,6 +114,55 @@ rmsnorm_bwd_kernel(const T* __restrict__ x, const T* __restrict__ w, const T* __
   if (dw_part) for (int i = threadIdx.x; i < D; i += blockDim.x) dw_part[(size_t)blockIdx.x * D + i] = dw_acc[i];
 }
 
+// Few rows (the decode step: one row per sequence): one 128-thread CTA per row so the load -> reduce -> scale chain is
+// 4 vectors deep per thread instead of 16; gamma is constant and fetched before griddepcontrol.wait.
+template <int NV>   // 16-byte vectors per thread: D = NV * 1024
+__global__ void __launch_bounds__(128)
+rmsnorm_fwd_row_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
+                       float* __restrict__ rstd_out, float eps) {
+  constexpr int D = NV * 1024;
+  __shared__ float red[4];
+  mb::pdl_trigger();
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const long long r = blockIdx.x;
+  int4 wv[NV], xv[NV];
+  const int4* wr = reinterpret_cast<const int4*>(w);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) wv[v] = __ldg(wr + v * 128 + tid);
+  mb::pdl_wait();
+  const int4* xr = reinterpret_cast<const int4*>(x + (size_t)r * D);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) xv[v] = mb::ld_stream(xr + v * 128 + tid);
+  float ss = 0.f;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const bf162* h = reinterpret_cast<const bf162*>(&xv[v]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); ss += f.x * f.x + f.y * f.y; }
+  }
+  ss = mb::warp_sum(ss);
+  if (lane == 0) red[wid] = ss;
+  __syncthreads();
+  ss = (red[0] + red[1]) + (red[2] + red[3]);
+  const float rstd = rsqrtf(ss / (float)D + eps);
+  if (tid == 0 && rstd_out) rstd_out[r] = rstd;
+  int4* yr = reinterpret_cast<int4*>(y + (size_t)r * D);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const bf162* h = reinterpret_cast<const bf162*>(&xv[v]);
+    const bf162* wh = reinterpret_cast<const bf162*>(&wv[v]);
+    int4 o; bf162* oh = reinterpret_cast<bf162*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(h[j]), g = __bfloat1622float2(wh[j]);
+      const bf162 nx = __floats2bfloat162_rn(f.x * rstd, f.y * rstd);        // .to(input_dtype) first, like the reference
+      const float2 nf = __bfloat1622float2(nx);
+      oh[j] = __floats2bfloat162_rn(g.x * nf.x, g.y * nf.y);
+    }
+    yr[v * 128 + tid] = o;
+  }
+}
+
 // ---- vectorised RMSNorm (bf16, D % 256 == 0, D <= 8192): one warp per row, the row lives in registers,
 //      16-byte loads/stores, no block barriers.  HBM traffic = 1 read + 1 write of the activation.
 template <int NV>   // 16-byte vectors per lane: D = NV * 256
@@ -587,6 +636,12 @@ int mb200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, long l
     long long g = (n + 7) / 8; const long long cap = (long long)mb::num_sms() * 8; if (g > cap) g = cap;
     cudaStream_t st = (cudaStream_t)stream;
     const bool pdl = mb::pdl_mode() != 0;
+    if (n <= 32) {
+      if (D == 4096) mb::launch_ex(rmsnorm_fwd_row_kernel<4>, dim3((int)n), dim3(128), 0, st, pdl, (const bf16*)x, (const bf16*)w, (bf16*)y, rstd, eps);
+      else if (D == 2048) mb::launch_ex(rmsnorm_fwd_row_kernel<2>, dim3((int)n), dim3(128), 0, st, pdl, (const bf16*)x, (const bf16*)w, (bf16*)y, rstd, eps);
+      else mb::launch_ex(rmsnorm_fwd_row_kernel<1>, dim3((int)n), dim3(128), 0, st, pdl, (const bf16*)x, (const bf16*)w, (bf16*)y, rstd, eps);
+      MB200_CHECK_LAUNCH(); return MB200_OK;
+    }
     if (D == 4096) mb::launch_ex(rmsnorm_fwd_vec_kernel<16>, dim3((int)g), dim3(256), 0, st, pdl, (const bf16*)x, (const bf16*)w, (bf16*)y, rstd, n, eps);
     else if (D == 2048) mb::launch_ex(rmsnorm_fwd_vec_kernel<8>, dim3((int)g), dim3(256), 0, st, pdl, (const bf16*)x, (const bf16*)w, (bf16*)y, rstd, n, eps);
     else mb::launch_ex(rmsnorm_fwd_vec_kernel<4>, dim3((int)g), dim3(256), 0, st, pdl, (const bf16*)x, (const bf16*)w, (bf16*)y, rstd, n, eps);

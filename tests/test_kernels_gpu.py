@@ -334,7 +334,7 @@ def test_attention_tcgen05_bwd(ops, cuda, B, H, Hkv, Sq, Sk, causal, masked):
 @pytest.mark.parametrize("M", [1, 2, 3, 8, 16])
 def test_skinny_gemm(ops, cuda, M):
     torch.manual_seed(30)
-    for (N, K) in [(4096, 4096), (1024, 4096), (14336, 4096), (4096, 14336), (1003, 512)]:
+    for (N, K) in [(4096, 4096), (1024, 4096), (14336, 4096), (4096, 14336), (1003, 512), (264, 1096), (37, 8200)]:
         x = torch.randn(M, K, device=cuda).bfloat16() * 0.3
         w = torch.randn(N, K, device=cuda).bfloat16() * 0.05
         b = torch.randn(N, device=cuda).bfloat16()
@@ -342,6 +342,28 @@ def test_skinny_gemm(ops, cuda, M):
         y = ops.gemm(x, w, bias=b, addend=r)
         ref = x.float() @ w.float().t() + b.float() + r.float()
         assert _rel(y, ref) < 5e-3, (M, N, K, _rel(y, ref))
+
+
+@pytest.mark.parametrize("M", [1, 2, 4, 5, 16])
+def test_skinny_fused_projections(ops, cuda, M):
+    """the decode engine's fused launches: q/k/v in one skinny GEMM, and gate/up + SwiGLU (rounded like the HF MLP)"""
+    torch.manual_seed(36)
+    for (D, I, Nq, Nkv) in [(4096, 14336, 4096, 1024), (256, 520, 256, 64)]:
+        x = torch.randn(M, D, device=cuda).bfloat16() * 0.5
+        wq = (torch.randn(Nq, D, device=cuda) * 0.03).bfloat16(); wk = (torch.randn(Nkv, D, device=cuda) * 0.03).bfloat16()
+        wv = (torch.randn(Nkv, D, device=cuda) * 0.03).bfloat16()
+        q = torch.empty(M, Nq, device=cuda, dtype=torch.bfloat16); k = torch.empty(M, Nkv, device=cuda, dtype=torch.bfloat16)
+        v = torch.empty_like(k)
+        ops._call("mb200_skinny_gemm3_bf16", ops._p(x), ops._p(wq), ops._p(wk), ops._p(wv), ops._p(q), ops._p(k), ops._p(v),
+                  M, Nq, Nkv, Nkv, D, D, D, ops._st())
+        for got, w in ((q, wq), (k, wk), (v, wv)):
+            assert _rel(got, x.float() @ w.float().t()) < 5e-3
+        wg = (torch.randn(I, D, device=cuda) * 0.03).bfloat16(); wu = (torch.randn(I, D, device=cuda) * 0.03).bfloat16()
+        act = torch.empty(M, I, device=cuda, dtype=torch.bfloat16)
+        ops._call("mb200_skinny_swiglu_bf16", ops._p(x), ops._p(wg), ops._p(wu), ops._p(act), M, I, D, D, D, I, ops._st())
+        g = (x.float() @ wg.float().t()).bfloat16(); u = (x.float() @ wu.float().t()).bfloat16()
+        ref = torch.nn.functional.silu(g) * u
+        assert _rel(act, ref) < 1e-2, (M, D, _rel(act, ref))
 
 
 @pytest.mark.parametrize("B,H,Hkv,ctx", [(1, 32, 8, 6137), (3, 8, 2, 300), (2, 4, 4, 33), (16, 32, 8, 1000)])
@@ -360,6 +382,36 @@ def test_decode_attention(ops, cuda, B, H, Hkv, ctx):
     o2 = ops.decode_attention(q, kc[:, :ctx], vc[:, :ctx], ctx, None, hd ** -0.5)
     ref2 = _attn_ref(q.float(), kc[:, :ctx].float(), vc[:, :ctx].float(), True, None, hd ** -0.5)
     assert _rel(o2, ref2) < 1e-2
+
+
+@pytest.mark.parametrize("n,D", [(1, 4096), (16, 4096), (5, 2048), (32, 1024), (33, 4096)])
+def test_rmsnorm_few_rows(ops, cuda, n, D):
+    """decode-sized inputs take the one-CTA-per-row kernel (n <= 32); same op-by-op bf16 rounding as the HF module"""
+    torch.manual_seed(34)
+    x = (torch.randn(n, D, device=cuda) * 2).bfloat16()
+    w = (1 + 0.1 * torch.randn(D, device=cuda)).bfloat16()
+    y = ops.rms_norm(x, w, 1e-5)
+    hf = w * (x.float() * torch.rsqrt(x.float().pow(2).mean(-1, keepdim=True) + 1e-5)).bfloat16()
+    assert (y.float() - hf.float()).abs().max().item() <= 2 * torch.finfo(torch.bfloat16).eps * hf.abs().max().item()
+
+
+@pytest.mark.parametrize("B,V,ld", [(1, 128258, 128264), (16, 128258, 128264), (3, 32003, 32008), (2, 1000, 1000), (2, 1003, 1003)])
+def test_argmax(ops, cuda, B, V, ld):
+    """greedy token pick of the decode engine: cluster kernel (aligned rows) and the single-CTA fallback, ties -> lowest index"""
+    torch.manual_seed(35)
+    buf = torch.full((B, ld), 1e4, device=cuda).bfloat16()           # padding columns must never win
+    logits = buf[:, :V]
+    logits.copy_(torch.randn(B, V, device=cuda))
+    for b in range(B):
+        j = (b * 7919 + V // 3) % (V - 5)
+        logits[b, j] = 50.0; logits[b, j + 3] = 50.0                  # tie: the first one wins
+    logits[B - 1] = -1.0; logits[B - 1, V - 1] = 0.5                  # winner in the last (partial) vector
+    out = torch.empty(B, dtype=torch.int64, device=cuda)
+    ops._call("mb200_argmax_bf16", ops._p(buf), ld, B, V, ops._p(out), ops._st())
+    lf = logits.float().cpu()
+    expect = [int((lf[b] == lf[b].max()).nonzero()[0]) for b in range(B)]
+    assert out.tolist() == expect
+    assert out[B - 1].item() == V - 1
 
 
 def _paged_cache(cuda, L, B, Hkv, hd, dtype, slab_tokens=256):
