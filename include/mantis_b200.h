@@ -87,6 +87,11 @@ int mb200_colsum(const void* x, float* part, void* out, int accumulate, long lon
 int mb200_im2col(const void* px, int px_dtype, void* out, int out_dtype, int N, int C, int H, int W, int p, int Kpad,
                  void* stream);
 int mb200_cast(const void* x, int in_dtype, void* y, int out_dtype, long long n, void* stream);
+/* Image processor tail on the device (replaces the numpy rescale + normalize + transpose of the HF image
+ * processor called from MLlavaProcessor.__call__, mantis/models/mllava/processing_llava.py:226-252): uint8 pixels
+ * [N,H,W,C] (channels_last) or [N,C,H,W] -> out[n,c,h,w] = lut[c][pixel]; lut is fp32 [C][256] on the device. */
+int mb200_image_normalize_u8(const void* px, const float* lut, void* out, int out_dtype, int N, int C, int H, int W,
+                             int channels_last, void* stream);
 /* flags[r] = 1 iff row r is all zeros: Idefics2 padding-image removal (mantis/models/idefics2/modeling_idefics2.py:1637-1639) */
 int mb200_rows_all_zero(const void* x, long long n_rows, long long row_elems, int* flags, int dtype, void* stream);
 

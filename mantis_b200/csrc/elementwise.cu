@@ -611,6 +611,40 @@ inline int ew_grid(long long work_items, int threads = 256) {
   else if ((dtype) == MB200_DTYPE_F32) { typedef float T; __VA_ARGS__; }   \
   else return -EINVAL;
 
+
+// ---------------------------------------------------------------- image rescale + normalize + layout (caller side, 8f-2)
+// uint8 pixels (HWC as decoded, or CHW as HF processors hand them over) -> normalized [N, C, H, W] fp32/bf16 through a
+// 256-entry table per channel.  The table holds (float32(float64(v) * rescale) - mean) / std evaluated exactly like the
+// reference's numpy image processor, so the result is bit-identical to it for every pixel value; the device only gathers.
+// One thread = 8 consecutive pixels of one output row: 16-byte (bf16) / 2 x 16-byte (fp32) coalesced stores.
+namespace {
+template <typename OT>
+__global__ void __launch_bounds__(256)
+image_normalize_u8_kernel(const unsigned char* __restrict__ px, const float* __restrict__ lut, OT* __restrict__ out, int N, int C,
+                          int H, int W, int channels_last) {
+  __shared__ float tab[4 * 256];
+  for (int i = threadIdx.x; i < C * 256; i += blockDim.x) tab[i] = lut[i];
+  __syncthreads();
+  const int wv = (W + 7) / 8;
+  const long long total = (long long)N * C * H * wv;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int w0 = (int)(t % wv) * 8;
+    long long r = t / wv;
+    const int h = (int)(r % H); r /= H;
+    const int c = (int)(r % C);
+    const long long n = r / C;
+    OT* o = out + (((size_t)n * C + c) * H + h) * W + w0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (w0 + j < W) {
+        const size_t src = channels_last ? ((((size_t)n * H + h) * W + w0 + j) * C + c) : ((((size_t)n * C + c) * H + h) * W + w0 + j);
+        mb::stf(o + j, tab[c * 256 + px[src]]);
+      }
+    }
+  }
+}
+}  // namespace
+
 extern "C" {
 
 int mb200_embedding_fwd(const int64_t* ids, const void* table, void* out, long long n, int D, long long V,
@@ -830,6 +864,23 @@ int mb200_cast(const void* x, int in_dtype, void* y, int out_dtype, long long n,
   else if (in_dtype == MB200_DTYPE_BF16 && out_dtype == MB200_DTYPE_F32) cast_kernel<bf16, float><<<g, 256, 0, st>>>((const bf16*)x, (float*)y, n);
   else if (in_dtype == MB200_DTYPE_F32 && out_dtype == MB200_DTYPE_F32) cast_kernel<float, float><<<g, 256, 0, st>>>((const float*)x, (float*)y, n);
   else if (in_dtype == MB200_DTYPE_BF16 && out_dtype == MB200_DTYPE_BF16) cast_kernel<bf16, bf16><<<g, 256, 0, st>>>((const bf16*)x, (bf16*)y, n);
+  else return -EINVAL;
+  MB200_CHECK_LAUNCH(); return MB200_OK;
+}
+
+
+// px: uint8 [N,H,W,C] (channels_last = 1) or [N,C,H,W]; lut: fp32 [C][256] on device; out: [N,C,H,W] fp32 / bf16.  C <= 4.
+int mb200_image_normalize_u8(const void* px, const float* lut, void* out, int out_dtype, int N, int C, int H, int W,
+                             int channels_last, void* stream) {
+  if (N <= 0) return MB200_OK;
+  if (C < 1 || C > 4 || H <= 0 || W <= 0) return -EINVAL;
+  const long long total = (long long)N * C * H * ((W + 7) / 8);
+  const int g = ew_grid(total);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_dtype == MB200_DTYPE_F32)
+    image_normalize_u8_kernel<float><<<g, 256, 0, st>>>((const unsigned char*)px, lut, (float*)out, N, C, H, W, channels_last);
+  else if (out_dtype == MB200_DTYPE_BF16)
+    image_normalize_u8_kernel<bf16><<<g, 256, 0, st>>>((const unsigned char*)px, lut, (bf16*)out, N, C, H, W, channels_last);
   else return -EINVAL;
   MB200_CHECK_LAUNCH(); return MB200_OK;
 }

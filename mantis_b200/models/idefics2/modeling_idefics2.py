@@ -314,7 +314,7 @@ class Idefics2Model(Idefics2PreTrainedModel):
             inputs_embeds = self.inputs_merger(input_ids, inputs_embeds, image_hidden_states)
         out = self.text_model(inputs_embeds=inputs_embeds, attention_mask=attention_mask, position_ids=position_ids,
                               past_key_values=past_key_values, use_cache=use_cache,
-                              output_hidden_states=output_hidden_states)
+                              output_hidden_states=output_hidden_states, cu_segments=kw.get("cu_segments"))
         return Idefics2BaseModelOutputWithPast(last_hidden_state=out.last_hidden_state, past_key_values=out.past_key_values,
                                                hidden_states=out.hidden_states, attentions=None,
                                                image_hidden_states=image_hidden_states)
@@ -358,10 +358,13 @@ class Idefics2ForConditionalGeneration(Idefics2PreTrainedModel, GenerationMixin)
         outputs = self.model(input_ids=input_ids, attention_mask=attention_mask, position_ids=position_ids,
                              past_key_values=past_key_values, inputs_embeds=inputs_embeds, pixel_values=pixel_values,
                              pixel_attention_mask=pixel_attention_mask, image_hidden_states=image_hidden_states,
-                             use_cache=use_cache, output_hidden_states=output_hidden_states)
+                             use_cache=use_cache, output_hidden_states=output_hidden_states,
+                             cu_segments=kw.get("cu_segments"))
         hidden = outputs.last_hidden_state
         loss = None
         logits = None
+        if attention_mask is not None and attention_mask.dim() == 4:       # packed batch: loss mask = key validity
+            attention_mask = (attention_mask != 0).any(dim=1).any(dim=1).to(torch.int64)
         want_logits = (not (self.training and torch.is_grad_enabled())) or self.materialize_logits_in_training \
             or labels is None
         if labels is not None:

@@ -57,7 +57,8 @@ class B200Attention(nn.Module):
         self.o_proj = B200Linear(self.num_heads * self.head_dim, self.hidden_size, bias=bias)
         self.scaling = self.head_dim ** -0.5
 
-    def forward(self, x, residual, position_ids, inv_freq, rope_scale, key_mask, cache, kbits=None, rope_tab=None):
+    def forward(self, x, residual, position_ids, inv_freq, rope_scale, key_mask, cache, kbits=None, rope_tab=None,
+                segs=None):
         B, S, _ = x.shape
         if _plain(self.q_proj, self.k_proj, self.v_proj):
             q, k, v = ops.multi_linear(x, self.q_proj.weight, self.k_proj.weight, self.v_proj.weight)
@@ -74,7 +75,10 @@ class B200Attention(nn.Module):
                 o = ops.decode_attention_paged(q, cache, self.layer_idx, ctx, key_mask, self.scaling, kbits=kbits)
                 return self.o_proj(o.view(B, S, self.num_heads * self.head_dim), residual=residual)
             k, v = cache.append(k, v, self.layer_idx)
-        o = ops.attention(q, k, v, causal=True, kmask=key_mask, scale=self.scaling)
+        if segs is not None:                   # packed sequences: block-diagonal causal attention, one launch per segment
+            o = ops.attention_varlen(q, k, v, segs, kmask=key_mask, scale=self.scaling)
+        else:
+            o = ops.attention(q, k, v, causal=True, kmask=key_mask, scale=self.scaling)
         return self.o_proj(o.view(B, S, self.num_heads * self.head_dim), residual=residual)
 
 
@@ -102,8 +106,9 @@ class B200DecoderLayer(nn.Module):
         self.input_layernorm = B200RMSNorm(config.hidden_size, eps=config.rms_norm_eps)
         self.post_attention_layernorm = B200RMSNorm(config.hidden_size, eps=config.rms_norm_eps)
 
-    def forward(self, x, position_ids, inv_freq, rope_scale, key_mask, cache, kbits=None, rope_tab=None):
-        x = self.self_attn(self.input_layernorm(x), x, position_ids, inv_freq, rope_scale, key_mask, cache, kbits, rope_tab)
+    def forward(self, x, position_ids, inv_freq, rope_scale, key_mask, cache, kbits=None, rope_tab=None, segs=None):
+        x = self.self_attn(self.input_layernorm(x), x, position_ids, inv_freq, rope_scale, key_mask, cache, kbits, rope_tab,
+                           segs)
         x = self.mlp(self.post_attention_layernorm(x), residual=x)
         return x
 
@@ -175,9 +180,24 @@ class B200DecoderModel(B200DecoderPreTrainedModel):
         if position_ids is None:
             position_ids = torch.arange(past, past + S, device=inputs_embeds.device).unsqueeze(0).expand(B, S)
         key_mask = None
+        segs = kwargs.get("cu_segments")
+        if attention_mask is not None and attention_mask.dim() == 4:
+            # sequence packing (ref: mantis/train/data.py:1622-1645): [B, 1, S, S] block-diagonal 0/1 mask + per-sample
+            # position ids.  The blocks are recovered from the position-id restarts, the key padding from the mask columns.
+            if cache is not None or position_ids is None:
+                raise ValueError("a packed (4-D) attention_mask needs position_ids and cannot be combined with a KV cache")
+            if attention_mask.shape[-2:] != (S, S):
+                raise ValueError(f"packed attention_mask must be [B, 1, {S}, {S}]")
+            if position_ids.dim() == 1:
+                position_ids = position_ids.unsqueeze(0)
+            if segs is None:
+                segs = ops.packed_segments(position_ids)
+            attention_mask = (attention_mask != 0).any(dim=1).any(dim=1).to(torch.int64)       # [B, S] key validity
+        elif segs is not None and cache is not None:
+            raise ValueError("packed sequences cannot be combined with a KV cache")
         if attention_mask is not None:
             if attention_mask.dim() != 2:
-                raise ValueError("mantis_b200 expects a 2-D [batch, kv_len] attention_mask")
+                raise ValueError("mantis_b200 expects a 2-D [batch, kv_len] or a packed 4-D attention_mask")
             key_mask = attention_mask
             if key_mask.shape[1] != past + S:
                 raise ValueError(f"attention_mask length {key_mask.shape[1]} != past({past}) + seq({S})")
@@ -196,9 +216,9 @@ class B200DecoderModel(B200DecoderPreTrainedModel):
                 all_hidden += (x,)
             if self.gradient_checkpointing and self.training and cache is None:
                 x = torch.utils.checkpoint.checkpoint(layer, x, position_ids, inv_freq, rope_scale, key_mask, None, None,
-                                                      rope_tab, use_reentrant=False)
+                                                      rope_tab, segs, use_reentrant=False)
             else:
-                x = layer(x, position_ids, inv_freq, rope_scale, key_mask, cache, kbits, rope_tab)
+                x = layer(x, position_ids, inv_freq, rope_scale, key_mask, cache, kbits, rope_tab, segs)
         x = self.norm(x)
         if output_hidden_states:
             all_hidden += (x,)
@@ -250,7 +270,7 @@ class B200CausalLM(B200DecoderPreTrainedModel):
                 return_dict=None, logits_to_keep=0, **kwargs):
         out = self.model(input_ids=input_ids, attention_mask=attention_mask, position_ids=position_ids,
                          past_key_values=past_key_values, inputs_embeds=inputs_embeds, use_cache=use_cache,
-                         output_hidden_states=output_hidden_states)
+                         output_hidden_states=output_hidden_states, cu_segments=kwargs.get("cu_segments"))
         h = out.last_hidden_state
         if isinstance(logits_to_keep, int) and logits_to_keep > 0:
             h = h[:, -logits_to_keep:, :]

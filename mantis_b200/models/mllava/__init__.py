@@ -8,3 +8,4 @@ from .processing_llava import MLlavaProcessor  # noqa: E402
 from .utils import chat_mllava  # noqa: E402
 
 __all__ += ["MLlavaProcessor", "chat_mllava"]
+from .image_processing import B200ImageProcessor  # noqa: F401,E402

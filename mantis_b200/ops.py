@@ -492,13 +492,15 @@ def _attn_fast_ok(q, k, v, hd, Sq, Sk):
     return True
 
 
-def attention_fwd(q, k, v, causal, kmask, scale, return_kbits=False):
-    """q [B,Sq,H,hd], k/v [B,Sk,Hkv,hd] (hd contiguous). Returns (o [B,Sq,H,hd] contiguous, lse [B,H,Sq] fp32)."""
+def attention_fwd(q, k, v, causal, kmask, scale, return_kbits=False, out=None):
+    """q [B,Sq,H,hd], k/v [B,Sk,Hkv,hd] (hd contiguous). Returns (o [B,Sq,H,hd] contiguous, lse [B,H,Sq] fp32).
+    `out`: optional contiguous destination for o (a slice of a packed output, see attention_varlen)."""
     _need_cuda(q, k, v)
     B, Sq, H, hd = q.shape
     Sk, Hkv = k.shape[1], k.shape[2]
     assert q.stride(3) == 1 and k.stride(3) == 1 and v.stride(3) == 1
-    o = torch.empty((B, Sq, H, hd), dtype=q.dtype, device=q.device)
+    o = out if out is not None else torch.empty((B, Sq, H, hd), dtype=q.dtype, device=q.device)
+    assert o.is_contiguous() and o.shape == (B, Sq, H, hd)
     lse = torch.empty((B, H, Sq), dtype=torch.float32, device=q.device)
     if kmask is not None:
         kmask = kmask.contiguous().to(torch.int64)
@@ -575,15 +577,20 @@ def decode_attention_paged(q, cache, layer_idx, ctx, kmask, scale, kbits=None):
     return o
 
 
-def attention_bwd(q, k, v, o, do, lse, causal, kmask, scale, kbits=None, fast=False):
+def attention_bwd(q, k, v, o, do, lse, causal, kmask, scale, kbits=None, fast=False, out=None):
+    """`out`: optional (dq, dk, dv) contiguous destinations (slices of packed gradients, see attention_varlen)."""
     B, Sq, H, hd = q.shape
     Sk, Hkv = k.shape[1], k.shape[2]
     do = do.contiguous()
     assert o.is_contiguous()
     if fast:
-        dq = torch.empty((B, Sq, H, hd), dtype=q.dtype, device=q.device)
-        dk = torch.empty((B, Sk, Hkv, hd), dtype=q.dtype, device=q.device)
-        dv = torch.empty((B, Sk, Hkv, hd), dtype=q.dtype, device=q.device)
+        if out is not None:
+            dq, dk, dv = out
+            assert dq.is_contiguous() and dk.is_contiguous() and dv.is_contiguous()
+        else:
+            dq = torch.empty((B, Sq, H, hd), dtype=q.dtype, device=q.device)
+            dk = torch.empty((B, Sk, Hkv, hd), dtype=q.dtype, device=q.device)
+            dv = torch.empty((B, Sk, Hkv, hd), dtype=q.dtype, device=q.device)
         delta = torch.empty((2 * B * H * _L().mb200_attn_bwd_sq_pad(Sq),), dtype=torch.float32, device=q.device)
         st = _strides12(q, k, v, o)
         _call("mb200_attn_bwd_bf16", _p(q), _p(k), _p(v), _p(o), _p(do), _p(lse), _p(delta), _p(dq), _p(dk), _p(dv),
@@ -597,6 +604,9 @@ def attention_bwd(q, k, v, o, do, lse, causal, kmask, scale, kbits=None, fast=Fa
     _call("mb200_attn_generic_bwd", _p(qc), _p(kc), _p(vc), _p(o), _p(do), _p(lse), _p(delta), _p(dq), _p(dk), _p(dv),
           B, H, Hkv, Sq, Sk, hd, st, float(scale), int(causal), _p(kmask), Sk if kmask is not None else 0,
           _dt(q), _st())
+    if out is not None:
+        out[0].copy_(dq); out[1].copy_(dk); out[2].copy_(dv)
+        return out
     return dq, dk, dv
 
 
@@ -622,6 +632,67 @@ def attention(q, k, v, causal=False, kmask=None, scale=None):
     if scale is None:
         scale = 1.0 / math.sqrt(q.shape[-1])
     return _AttentionFn.apply(q, k, v, bool(causal), kmask, float(scale))
+
+
+class _VarlenAttentionFn(torch.autograd.Function):
+    """Causal attention over PACKED sequences (sequence packing, ref: mantis/train/data.py:1546-1671 builds a block-diagonal
+    4-D mask + per-sample position ids for this): every (batch row, start, end) segment attends only to itself.  One kernel
+    launch per segment on strided views of the packed q/k/v -- outputs and gradients are written straight into slices of
+    ONE packed tensor, so packing adds no copies and no masked-out FLOPs (a dense block-diagonal mask would compute
+    S^2 scores and throw most of them away)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, segs, kmask, scale):
+        B, S, H, hd = q.shape
+        o = torch.zeros((B, S, H, hd), dtype=q.dtype, device=q.device)       # positions outside every segment stay 0
+        if kmask is not None:
+            kmask = kmask.contiguous().to(torch.int64)
+        per_seg = []
+        for (b, s0, s1) in segs:
+            km = kmask[b:b + 1, s0:s1] if kmask is not None else None
+            _, lse, kbits, fast = attention_fwd(q[b:b + 1, s0:s1], k[b:b + 1, s0:s1], v[b:b + 1, s0:s1], True, km, scale,
+                                                return_kbits=True, out=o[b:b + 1, s0:s1])
+            per_seg.append((lse, kbits, fast))
+        ctx.save_for_backward(q, k, v, o, kmask)
+        ctx.segs, ctx.per_seg, ctx.scale = segs, per_seg, scale
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, o, kmask = ctx.saved_tensors
+        do = do.contiguous()
+        dq = torch.zeros_like(q, memory_format=torch.contiguous_format)
+        dk = torch.zeros_like(k, memory_format=torch.contiguous_format)
+        dv = torch.zeros_like(v, memory_format=torch.contiguous_format)
+        for (b, s0, s1), (lse, kbits, fast) in zip(ctx.segs, ctx.per_seg):
+            km = kmask[b:b + 1, s0:s1] if kmask is not None else None
+            attention_bwd(q[b:b + 1, s0:s1], k[b:b + 1, s0:s1], v[b:b + 1, s0:s1], o[b:b + 1, s0:s1], do[b:b + 1, s0:s1], lse,
+                          True, km, ctx.scale, kbits=kbits, fast=fast,
+                          out=(dq[b:b + 1, s0:s1], dk[b:b + 1, s0:s1], dv[b:b + 1, s0:s1]))
+        return dq, dk, dv, None, None, None
+
+
+def attention_varlen(q, k, v, segs, kmask=None, scale=None):
+    """causal self-attention over packed sequences.  q [B,S,H,hd]; k,v [B,S,Hkv,hd]; segs: list of (batch row, start, end)
+    with non-overlapping [start, end) ranges; kmask [B,S] (non-zero = attend) or None."""
+    if scale is None:
+        scale = 1.0 / math.sqrt(q.shape[-1])
+    return _VarlenAttentionFn.apply(q, k, v, tuple(tuple(int(x) for x in sgm) for sgm in segs), kmask, float(scale))
+
+
+def packed_segments(position_ids):
+    """[B, S] per-sample position ids of a packed batch (each packed sample restarts at 0) -> list of (b, start, end).
+    One host sync (the segment table drives the launch loop)."""
+    pos = position_ids if position_ids.dim() == 2 else position_ids.unsqueeze(0)
+    B, S = pos.shape
+    starts = (pos == 0)
+    starts[:, 0] = True
+    idx = starts.nonzero().tolist()
+    segs = []
+    for i, (b, s0) in enumerate(idx):
+        s1 = idx[i + 1][1] if i + 1 < len(idx) and idx[i + 1][0] == b else S
+        segs.append((b, s0, s1))
+    return segs
 
 
 # ---------------------------------------------------------------------------------------------- merge (scatter)
@@ -857,6 +928,22 @@ def im2col(pixels, patch, k_pad, out_dtype):
     out = torch.empty((N * gh * gw, k_pad), dtype=out_dtype, device=px.device)
     _call("mb200_im2col", _p(px), _dt(px), _p(out), BF16 if out_dtype == torch.bfloat16 else F32, N, C, H, W, patch,
           k_pad, _st())
+    return out
+
+
+def image_normalize_u8(pixels_u8, lut, channels_last, out_dtype):
+    """uint8 [N,H,W,C] (channels_last) or [N,C,H,W] on the device + fp32 lut [C,256] -> normalized [N,C,H,W] out_dtype"""
+    _need_cuda(pixels_u8, lut)
+    assert pixels_u8.dtype == torch.uint8 and lut.dtype == torch.float32 and lut.shape[1] == 256
+    px = pixels_u8.contiguous()
+    if channels_last:
+        N, H, W, C = px.shape
+    else:
+        N, C, H, W = px.shape
+    assert lut.shape[0] == C
+    out = torch.empty((N, C, H, W), dtype=out_dtype, device=px.device)
+    _call("mb200_image_normalize_u8", _p(px), _p(lut.contiguous()), _p(out), BF16 if out_dtype == torch.bfloat16 else F32,
+          N, C, H, W, int(bool(channels_last)), _st())
     return out
 
 

@@ -33,7 +33,8 @@ class Collator:
         return torch.cat([t, pad], dim=1)
 
     def __call__(self, batch: List[Dict]):
-        if len(batch) == 1 and self.processor is not None and hasattr(self.processor, "_right_pad_inputs_with_attention_mask"):
+        if (len(batch) == 1 and "cu_segments" not in batch[0] and self.processor is not None
+                and hasattr(self.processor, "_right_pad_inputs_with_attention_mask")):
             return self.processor._right_pad_inputs_with_attention_mask(model_inputs=batch)      # the reference's path
         out = {}
         for k in batch[0].keys():
@@ -42,10 +43,117 @@ class Collator:
                 out[k] = [v for v in vals]                       # list of per-sample tensors (None kept, model skips them)
             elif vals[0] is None:
                 out[k] = None
+            elif k == "cu_segments":                             # packed rows (PackingDataset): renumber the batch row
+                out[k] = [(i, s0, s1) for i, segs in enumerate(vals) for (_, s0, s1) in segs]
+            elif isinstance(vals[0], torch.Tensor) and vals[0].dim() == 4:
+                # packed block-diagonal masks [1, 1, q, kv]: zero-pad both sequence dims (ref: data.py:1441-1474)
+                L = max(v.shape[2] for v in vals)
+                padded = []
+                for v in vals:
+                    m = torch.zeros((v.shape[0], v.shape[1], L, L), dtype=v.dtype, device=v.device)
+                    m[:, :, : v.shape[2], : v.shape[3]] = v
+                    padded.append(m)
+                out[k] = torch.cat(padded, dim=0)
             else:
                 L = max(v.shape[1] for v in vals)
                 if self.max_length is not None:
                     L = min(L, self.max_length)
                 fill = self._pad_id() if k == "input_ids" else (self.label_pad if k == "labels" else 0)
                 out[k] = torch.cat([self._pad_to(v[:, :L], L, fill) for v in vals], dim=0)
+        return out
+
+
+class PackingDataset(torch.utils.data.Dataset):
+    """Sequence packing for the self-attention models (ref: mantis/train/data.py:1546-1671).
+
+    Consecutive items of `dataset` (dicts with `input_ids [1, T]`, `attention_mask [1, T]`, `labels [1, T]` or `[T]`,
+    `pixel_values`) are concatenated until the running length exceeds `max_self_attn_len` -- the item that crosses the
+    limit is included, like the reference -- and returned as ONE row with
+      * `attention_mask` [1, 1, S, S] int32 block-diagonal (block i = item i's key mask broadcast over its queries),
+      * `position_ids` restarting at 0 for every item,
+      * `cu_segments`: the (row, start, end) table the varlen attention launches from (no device sync needed).
+    Differences from the reference, which cannot be instantiated as written (it reads `self.packing_same_mm_media` before
+    assigning it, data.py:1555-1558): `position_ids` / `labels` keep a leading batch dim of 1 so the row can go straight into
+    `model(**batch)`, and the packing interval is estimated lazily from the first `probe` packs.
+    The block-diagonal mask is only materialised for callers that want the reference's tensors (`dense_mask=True`):
+    it is S^2 int32 (268 MB at S = 8192) and the model needs just the segment table + a [1, S] key mask."""
+
+    def __init__(self, dataset, max_self_attn_len, dense_mask=True, probe=20):
+        super().__init__()
+        self.dataset = dataset
+        self.max_self_attn_len = max_self_attn_len
+        self.dense_mask = dense_mask
+        self.packing_same_mm_media = getattr(dataset, "packing_same_mm_media", False)
+        assert not self.packing_same_mm_media, "Packing same mm media is not supported for self-attention based models"
+        self.average_packing_interval = self._infer_interval(probe)
+        self.num_last_packed_items = self.average_packing_interval
+
+    def _take(self, start):
+        items, total, i = [], 0, start
+        while True:
+            item = self.dataset[i % len(self.dataset)]
+            total += item["input_ids"].shape[1]
+            items.append(item)
+            if (self.max_self_attn_len and total > self.max_self_attn_len) or len(items) >= len(self.dataset):
+                return items
+            i += 1
+
+    def _infer_interval(self, probe):
+        counts, i = [], 0
+        for _ in range(min(probe, max(1, len(self.dataset)))):
+            n = len(self._take(i))
+            counts.append(n)
+            i += n
+        return max(1, -(-sum(counts) // len(counts)))
+
+    def __len__(self):
+        return max(1, len(self.dataset) // self.average_packing_interval)
+
+    def __getitem__(self, idx):
+        offset = self.num_last_packed_items - self.average_packing_interval
+        items = self._take(idx * self.average_packing_interval + offset)
+        self.num_last_packed_items = len(items)
+        return self.pack_batch(items)
+
+    def pack_batch(self, items):
+        ids = torch.cat([x["input_ids"] for x in items], dim=1)
+        S = ids.shape[1]
+        pv = [x.get("pixel_values") for x in items]
+        if any(isinstance(p, list) for p in pv):
+            pixel_values = sum([p or [] for p in pv], []) or None
+        elif all(p is None for p in pv):
+            pixel_values = None
+        else:
+            pixel_values = torch.cat([torch.as_tensor(p) for p in pv if p is not None], dim=0)
+        key_mask = torch.cat([x["attention_mask"].reshape(1, -1) for x in items], dim=1).to(torch.int32)
+        segs, pos, acc = [], [], 0
+        for x in items:
+            n = x["input_ids"].shape[1]
+            segs.append((0, acc, acc + n))
+            pos.append(torch.arange(n, dtype=torch.long))
+            acc += n
+        out = {
+            "input_ids": ids,
+            "pixel_values": pixel_values,
+            "position_ids": torch.cat(pos).unsqueeze(0),
+            "labels": torch.cat([x["labels"].reshape(1, -1) for x in items], dim=1),
+            "cu_segments": segs,
+        }
+        if self.dense_mask:
+            mask = torch.zeros((1, 1, S, S), dtype=torch.int32)
+            for (_, s0, s1) in segs:
+                mask[0, 0, s0:s1, s0:s1] = key_mask[:, s0:s1].expand(s1 - s0, s1 - s0)
+            out["attention_mask"] = mask
+        else:
+            out["attention_mask"] = key_mask.to(torch.long)
+        for k in items[0].keys():
+            if k in out or k in ("encoder_attention_mask", "encoder_position_ids"):
+                continue
+            v0 = items[0][k]
+            if isinstance(v0, torch.Tensor):
+                out[k] = torch.cat([x[k] for x in items], dim=0)
+            elif isinstance(v0, list):
+                out[k] = sum([x[k] for x in items], [])
+            else:
+                out[k] = [x[k] for x in items]
         return out

@@ -1,0 +1,61 @@
+"""PackingDataset / Collator host logic (ref: mantis/train/data.py:1546-1671 `PackingDataset.pack_batch`)."""
+import torch
+
+from mantis_b200.train import Collator, PackingDataset
+
+
+class _DS(torch.utils.data.Dataset):
+    lens = [5, 3, 7, 4, 6, 2, 9]
+
+    def __len__(self):
+        return len(self.lens)
+
+    def __getitem__(self, i):
+        n = self.lens[i]
+        am = torch.ones(1, n, dtype=torch.long)
+        if i == 2:
+            am[0, -2:] = 0                                     # a sample that carries its own padding
+        return {"input_ids": torch.arange(n).unsqueeze(0) + 100 * i, "attention_mask": am,
+                "labels": torch.arange(n).unsqueeze(0) + 100 * i, "pixel_values": torch.full((1, 3, 2, 2), float(i))}
+
+
+def test_pack_batch_layout_follows_the_reference():
+    pd = PackingDataset(_DS(), max_self_attn_len=10)
+    assert pd.average_packing_interval == 3 and len(pd) == 2
+    row = pd[0]                                               # items 0, 1, 2: 5 + 3 = 8 <= 10, the 7-token item crosses it
+    S = 15
+    assert row["input_ids"].tolist() == [[0, 1, 2, 3, 4, 100, 101, 102, 200, 201, 202, 203, 204, 205, 206]]
+    assert row["labels"].tolist() == row["input_ids"].tolist()
+    assert row["position_ids"].tolist() == [[0, 1, 2, 3, 4, 0, 1, 2, 0, 1, 2, 3, 4, 5, 6]]
+    assert row["cu_segments"] == [(0, 0, 5), (0, 5, 8), (0, 8, 15)]
+    assert row["pixel_values"].shape == (3, 3, 2, 2) and row["pixel_values"][:, 0, 0, 0].tolist() == [0.0, 1.0, 2.0]
+    m = row["attention_mask"]
+    assert m.shape == (1, 1, S, S) and m.dtype == torch.int32
+    expect = torch.zeros(S, S, dtype=torch.int32)
+    expect[0:5, 0:5] = 1; expect[5:8, 5:8] = 1; expect[8:15, 8:13] = 1      # block i = item i's key mask, every query row
+    assert torch.equal(m[0, 0], expect)
+    # the sync-free variant carries a 2-D key mask instead of the S^2 tensor
+    row2 = PackingDataset(_DS(), max_self_attn_len=10, dense_mask=False)[0]
+    assert row2["attention_mask"].tolist() == [[1] * 13 + [0, 0]]
+    assert torch.equal((m != 0).any(dim=1).any(dim=1).long(), row2["attention_mask"])
+
+
+def test_collator_batches_packed_rows():
+    pd = PackingDataset(_DS(), max_self_attn_len=10)
+    a, b = pd[0], pd[1]
+    Sa, Sb = a["input_ids"].shape[1], b["input_ids"].shape[1]
+    batch = Collator(pad_token_id=7)([a, b])
+    L = max(Sa, Sb)
+    assert batch["input_ids"].shape == (2, L) and batch["attention_mask"].shape == (2, 1, L, L)
+    assert batch["attention_mask"][1, 0, Sb:, :].sum() == 0 and batch["attention_mask"][1, 0, :, Sb:].sum() == 0
+    assert batch["labels"][1, Sb:].tolist() == [-100] * (L - Sb) and batch["input_ids"][1, Sb:].tolist() == [7] * (L - Sb)
+    assert batch["cu_segments"][: len(a["cu_segments"])] == a["cu_segments"]
+    assert [s[0] for s in batch["cu_segments"][len(a["cu_segments"]):]] == [1] * len(b["cu_segments"])
+    assert isinstance(batch["pixel_values"], list) and len(batch["pixel_values"]) == 2
+
+
+def test_packed_segments_from_position_ids():
+    from mantis_b200 import ops
+    pos = torch.tensor([[0, 1, 2, 0, 1, 0, 1, 2, 3], [0, 1, 2, 3, 4, 5, 0, 1, 2]])
+    assert ops.packed_segments(pos) == [(0, 0, 3), (0, 3, 5), (0, 5, 9), (1, 0, 6), (1, 6, 9)]
+    assert ops.packed_segments(torch.tensor([5, 6, 0, 1])) == [(0, 0, 2), (0, 2, 4)]    # 1-D ids (reference layout)
