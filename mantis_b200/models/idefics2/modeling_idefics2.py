@@ -292,7 +292,10 @@ class Idefics2Model(Idefics2PreTrainedModel):
             mask_is_full = not bool(torch.any(~patch_attention_mask))
         x = self.vision_model(pixel_values, patch_attention_mask, mask_is_full).last_hidden_state
         am = None if mask_is_full else patch_attention_mask.view(pixel_values.size(0), -1)
-        return self.connector(x, am)
+        return self._connect(x, am)
+
+    def _connect(self, x, patch_key_mask):
+        return self.connector(x, patch_key_mask)
 
     def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None,
                 inputs_embeds=None, pixel_values=None, pixel_attention_mask=None, image_hidden_states=None,
@@ -322,10 +325,14 @@ class Idefics2Model(Idefics2PreTrainedModel):
 
 class Idefics2ForConditionalGeneration(Idefics2PreTrainedModel, GenerationMixin):
     _tied_weights_keys = {}
+    _backbone_cls = None          # set below (Idefics2Model); the Idefics3 shell swaps in its own backbone
+
+    def _loss_ignore_index(self):
+        return self.image_token_id                               # CrossEntropyLoss(ignore_index=image_token_id), ref:1894
 
     def __init__(self, config):
         super().__init__(config)
-        self.model = Idefics2Model(config)
+        self.model = (self._backbone_cls or Idefics2Model)(config)
         self.image_token_id = self.config.image_token_id
         self.lm_head = B200Linear(config.text_config.hidden_size, config.text_config.vocab_size, bias=False)
         self.vocab_size = config.text_config.vocab_size
@@ -368,7 +375,7 @@ class Idefics2ForConditionalGeneration(Idefics2PreTrainedModel, GenerationMixin)
         want_logits = (not (self.training and torch.is_grad_enabled())) or self.materialize_logits_in_training \
             or labels is None
         if labels is not None:
-            eff, count = ops.shift_labels(labels, attention_mask, self.image_token_id)               # ref:1887-1899
+            eff, count = ops.shift_labels(labels, attention_mask, self._loss_ignore_index())         # ref:1887-1899
         if want_logits:
             h = hidden[:, -logits_to_keep:, :] if (isinstance(logits_to_keep, int) and logits_to_keep > 0) else hidden
             lg = self.lm_head(h)

@@ -76,6 +76,38 @@ def load_reference_idefics2():
     return mod
 
 
+def load_reference_idefics3():
+    """-> (configuration module, modeling module) of mantis/models/idefics3, loaded by file path"""
+    if "idefics3" in _CACHE:
+        return _CACHE["idefics3"]
+    root = find_ref_root()
+    if root is None:
+        raise RuntimeError("reference tree not found (only available in the build container)")
+    pkg_name = "_mantis_ref.models.idefics3"
+    for p in ("_mantis_ref", "_mantis_ref.models", pkg_name):
+        if p not in sys.modules:
+            m = types.ModuleType(p)
+            m.__path__ = []
+            sys.modules[p] = m
+    base = os.path.join(root, "mantis", "models", "idefics3")
+    cfg = _load(pkg_name + ".configuration_idefics3", os.path.join(base, "configuration_idefics3.py"))
+    mod = _load(pkg_name + ".modeling_idefics3", os.path.join(base, "modeling_idefics3.py"))
+    _CACHE["idefics3"] = (cfg, mod)
+    return cfg, mod
+
+
+def ref_idefics3_classes():
+    cfg, modm = load_reference_idefics3()
+
+    class RefIdefics3(modm.Idefics3ForConditionalGeneration):
+        _supports_sdpa = True
+
+        def tie_weights(self, *a, **k):
+            return None
+
+    return cfg.Idefics3Config, cfg.Idefics3VisionConfig, RefIdefics3
+
+
 def ref_llava_classes():
     cfg, modm = load_reference_mllava()
 

@@ -18,3 +18,11 @@ def cuda():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="session")
+def ops(cuda):
+    from mantis_b200 import ops as o
+    from mantis_b200 import _lib
+    assert _lib.lib().mb200_check_device() == 0
+    return o

@@ -14,14 +14,6 @@ def _rel(a, b):
     return ((a - b).norm() / (b.norm() + 1e-12)).item()
 
 
-@pytest.fixture(scope="module")
-def ops(cuda):
-    from mantis_b200 import ops as o
-    from mantis_b200 import _lib
-    assert _lib.lib().mb200_check_device() == 0
-    return o
-
-
 # ------------------------------------------------------------------------------------------------ GEMM
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("ta,tb", [(False, True), (False, False), (True, False), (True, True)])

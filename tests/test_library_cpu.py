@@ -78,3 +78,14 @@ def test_paged_kv_allocator_host_logic():
     c.crop(129)
     assert [len(b) for b in c.blocks] == [2, 2, 2] and len(c.free) == n_free + 3 * 10 and c.get_seq_length() == 129
     assert c.device_table()[:, :2].tolist() == before
+
+
+def test_idefics3_shell_has_the_reference_state_dict_layout():
+    """same class names through the `mantis.models.idefics3` alias, same state-dict keys as the reference"""
+    from helpers import load_fixture
+    from mantis.models.idefics3 import Idefics3Config, Idefics3ForConditionalGeneration
+    fx = load_fixture("idefics3_full.pt")
+    model = Idefics3ForConditionalGeneration(Idefics3Config(**fx["cfg"]))
+    missing, unexpected = model.load_state_dict(fx["state_dict"], strict=False)
+    assert not missing and not unexpected
+    assert model.model.image_seq_len == 16
