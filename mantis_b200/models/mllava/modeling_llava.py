@@ -124,11 +124,12 @@ class LlavaForConditionalGeneration(LlavaPreTrainedModel, GenerationMixin):
         return model_embeds
 
     # ---- the merge (reference :293-360) ----
-    def _merge_input_ids_with_image_features(self, image_features, inputs_embeds, input_ids, attention_mask, labels):
+    def _merge_input_ids_with_image_features(self, image_features, inputs_embeds, input_ids, attention_mask, labels,
+                                             plan_hint=None):
         return ops.merge_input_ids_with_image_features(
             image_features, inputs_embeds, input_ids, attention_mask, labels,
             image_token_index=self.config.image_token_index, pad_token_id=self.pad_token_id,
-            ignore_index=self.config.ignore_index)
+            ignore_index=self.config.ignore_index, plan_hint=plan_hint)
 
     # ---- vision path ----
     def _select(self, feats, strategy):
@@ -187,7 +188,8 @@ class LlavaForConditionalGeneration(LlavaPreTrainedModel, GenerationMixin):
                 image_features = self._image_features(pixel_values, vision_feature_layer,
                                                       vision_feature_select_strategy)
                 inputs_embeds, attention_mask, labels, position_ids = self._merge_input_ids_with_image_features(
-                    image_features, inputs_embeds, input_ids, attention_mask, labels)
+                    image_features, inputs_embeds, input_ids, attention_mask, labels,
+                    plan_hint=kwargs.get("merge_hint"))               # optional: sync-free merge (train.data.Collator)
                 merged = True
                 if isinstance(past_key_values, B200KVCache):
                     past_key_values.prefill_mask = attention_mask

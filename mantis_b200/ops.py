@@ -709,16 +709,28 @@ def _merge_ws(B, T, device):
     return ws
 
 
-def merge_plan(input_ids, inputs_embeds, P, image_token, pad_token):
+_deferred_checks = []
+
+
+def check_deferred():
+    """Raise the errors of sync-free merges (see merge_input_ids_with_image_features(plan_hint=...)): call at a point where
+    the host synchronises anyway (B200Trainer does, right after the gradient-norm readback)."""
+    pending, _deferred_checks[:] = list(_deferred_checks), []
+    for flag, msg in pending:
+        if not bool(flag.item()):
+            raise ValueError(msg)
+
+
+def merge_plan(input_ids, inputs_embeds, P, image_token, pad_token, sync=True):
     """Runs the plan kernel and reads the 8-word header back (the ONE host sync of the merge: the output
-    length is data dependent).  Returns (ws, header list)."""
+    length is data dependent).  Returns (ws, header list); with sync=False the header stays on the device."""
     B, T = input_ids.shape
     D = inputs_embeds.shape[-1]
     ws = _merge_ws(B, T, input_ids.device)
     header = torch.empty((8,), dtype=torch.int64, device=input_ids.device)
     _call("mb200_merge_plan", _p(input_ids), _p(inputs_embeds), _dt(inputs_embeds), B, T, D, P, int(image_token),
           int(pad_token), _p(ws), _p(header), _st())
-    return ws, header.tolist()
+    return ws, (header.tolist() if sync else header)
 
 
 class _MergeRowsFn(torch.autograd.Function):
@@ -753,9 +765,14 @@ class _MergeRowsFn(torch.autograd.Function):
 
 
 def merge_input_ids_with_image_features(image_features, inputs_embeds, input_ids, attention_mask, labels,
-                                        image_token_index, pad_token_id, ignore_index=-100):
+                                        image_token_index, pad_token_id, ignore_index=-100, plan_hint=None):
     """CUDA re-implementation of LlavaForConditionalGeneration._merge_input_ids_with_image_features
-    (mantis/models/mllava/modeling_llava.py:293-360).  Same return tuple, same ValueError."""
+    (mantis/models/mllava/modeling_llava.py:293-360).  Same return tuple, same ValueError.
+
+    plan_hint = {"max_image_tokens": n, "left_padding": bool} (emitted by train.data.Collator from the host copy of
+    input_ids) removes the merge's host sync: the merged length n * (P - 1) + T and the padding side are then known
+    up front, the plan kernel's own result is compared with them ON THE DEVICE and a mismatch (wrong hint, or the
+    reference's image-count ValueError) is raised by ops.check_deferred() at the caller's next sync point."""
     _need_cuda(image_features, inputs_embeds, input_ids)
     num_images, P, D = image_features.shape
     B, T = input_ids.shape
@@ -766,12 +783,22 @@ def merge_input_ids_with_image_features(image_features, inputs_embeds, input_ids
     mask_dtype = attention_mask.dtype
     am = attention_mask.contiguous().to(torch.int64)
     lab = labels.contiguous().to(torch.int64) if labels is not None else None
-    ws, hdr = merge_plan(ids, emb, P, image_token_index, pad_token_id)
-    S, left_padding, n_slots = int(hdr[0]), int(hdr[1]), int(hdr[2])
-    if n_slots != num_images * P:
-        raise ValueError(
-            f"The input provided to the model are wrong. The number of image tokens is {int(hdr[4])} while"
-            f" the number of image given to the model is {num_images}. This prevents correct indexing and breaks batch generation.")
+    if plan_hint is not None:
+        ws, hdr = merge_plan(ids, emb, P, image_token_index, pad_token_id, sync=False)
+        S = int(plan_hint["max_image_tokens"]) * (P - 1) + T
+        left_padding = int(bool(plan_hint["left_padding"]))
+        expect = torch.tensor([S, left_padding, num_images * P], dtype=torch.int64, device=ids.device)
+        _deferred_checks.append(((hdr[:3] == expect).all(),
+                                 "The input provided to the model are wrong (sync-free merge): the plan_hint or the number of"
+                                 f" images ({num_images}) does not match the image tokens in input_ids. This prevents correct"
+                                 " indexing and breaks batch generation."))
+    else:
+        ws, hdr = merge_plan(ids, emb, P, image_token_index, pad_token_id)
+        S, left_padding, n_slots = int(hdr[0]), int(hdr[1]), int(hdr[2])
+        if n_slots != num_images * P:
+            raise ValueError(
+                f"The input provided to the model are wrong. The number of image tokens is {int(hdr[4])} while"
+                f" the number of image given to the model is {num_images}. This prevents correct indexing and breaks batch generation.")
     dev = ids.device
     srcmap = torch.empty((B, S), dtype=torch.int32, device=dev)
     out_mask = torch.empty((B, S), dtype=torch.int64, device=dev)

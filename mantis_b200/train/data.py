@@ -11,11 +11,20 @@ import torch
 
 
 class Collator:
-    def __init__(self, processor=None, max_length=None, pad_token_id=None, label_pad=-100):
+    def __init__(self, processor=None, max_length=None, pad_token_id=None, label_pad=-100, image_token_index=None):
         self.processor = processor
         self.max_length = max_length
         self.pad_token_id = pad_token_id
         self.label_pad = label_pad
+        # when set, every batch carries `merge_hint` = what the model's image-token merge would otherwise read back from
+        # the device ("emitting merged lengths so the scatter needs no host sync"): the largest number of
+        # <image> placeholders in a row and the padding side, both from the host copy of input_ids
+        self.image_token_index = image_token_index
+
+    def merge_hint(self, input_ids, pad_token_id):
+        n = int((input_ids == self.image_token_index).sum(dim=-1).max())
+        left = not bool((input_ids[:, -1] == pad_token_id).any())          # ref: modeling_llava.py:296
+        return {"max_image_tokens": n, "left_padding": left}
 
     def _pad_id(self):
         if self.pad_token_id is not None:
@@ -60,6 +69,8 @@ class Collator:
                     L = min(L, self.max_length)
                 fill = self._pad_id() if k == "input_ids" else (self.label_pad if k == "labels" else 0)
                 out[k] = torch.cat([self._pad_to(v[:, :L], L, fill) for v in vals], dim=0)
+        if self.image_token_index is not None and out.get("input_ids") is not None and "cu_segments" not in out:
+            out["merge_hint"] = self.merge_hint(out["input_ids"], self._pad_id())
         return out
 
 

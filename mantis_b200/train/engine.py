@@ -159,6 +159,7 @@ class B200Trainer:
             total = math.sqrt(float(self._norm.item())) * scale
             if total > self.max_grad_norm:
                 scale *= self.max_grad_norm / (total + 1e-6)
+        ops.check_deferred()                       # errors of sync-free merges surface here, after the step's one readback
         self.step_count += 1
         for p, m, v in zip(self.params, self.m, self.v):
             ops.adamw_step(p.data, p.grad, m, v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,

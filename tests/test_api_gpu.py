@@ -65,3 +65,28 @@ def test_value_error_on_image_count_mismatch(cuda):
         model(**inp)
     with pytest.raises(ValueError):
         model(vision_feature_select_strategy="bogus", **_inputs(fx, cuda))
+
+
+def test_sync_free_merge_with_collator_hint(cuda):
+    """the Collator's merge_hint replaces the merge's host read-back; same outputs, and a wrong hint / image
+    count still raises the reference's ValueError -- deferred to ops.check_deferred()."""
+    from mantis_b200 import ops
+    from mantis_b200.train import Collator
+    fx = load_fixture("llava_batch_pad.pt")
+    model = load_model(fx, torch.float32, cuda).eval()
+    cfgk = fx["meta"]["cfg_kwargs"]
+    col = Collator(pad_token_id=cfgk["pad_token_id"], image_token_index=cfgk["image_token_index"])
+    hint = col.merge_hint(fx["input_ids"], cfgk["pad_token_id"])
+    kw = _inputs(fx, cuda)
+    with torch.no_grad():
+        ref = model(**kw)
+        got = model(**kw, merge_hint=hint)
+    ops.check_deferred()
+    assert torch.equal(ref.logits, got.logits) and torch.equal(ref.loss, got.loss)
+    assert rel_err(got.logits, fx["logits"]) < 1e-3
+    bad = dict(hint, max_image_tokens=hint["max_image_tokens"] + 1)
+    with torch.no_grad():
+        model(**kw, merge_hint=bad)
+    with pytest.raises(ValueError):
+        ops.check_deferred()
+    ops.check_deferred()                                              # the queue is drained
