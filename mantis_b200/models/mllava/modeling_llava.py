@@ -87,7 +87,7 @@ class LlavaForConditionalGeneration(LlavaPreTrainedModel, GenerationMixin):
         super().__init__(config)
         self.vision_tower = build_vision_tower(config.vision_config) if vision_tower is None else vision_tower
         self.multi_modal_projector = LlavaMultiModalProjector(config)
-        self.vocab_size = config.vocab_size
+        self.vocab_size = getattr(config, "vocab_size", None) or config.text_config.vocab_size
         self.language_model = B200CausalLM(config.text_config) if language_model is None else language_model
         self.pad_token_id = self.config.pad_token_id if self.config.pad_token_id is not None else -1
         # training: skip the [B,S,V] logits tensor unless the caller asks for it (set True for parity checks)

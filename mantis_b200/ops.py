@@ -765,14 +765,18 @@ class _MergeRowsFn(torch.autograd.Function):
 
 
 def merge_input_ids_with_image_features(image_features, inputs_embeds, input_ids, attention_mask, labels,
-                                        image_token_index, pad_token_id, ignore_index=-100, plan_hint=None):
+                                        image_token_index, pad_token_id, ignore_index=-100, plan_hint=None,
+                                        zero_pad_rows=False):
     """CUDA re-implementation of LlavaForConditionalGeneration._merge_input_ids_with_image_features
     (mantis/models/mllava/modeling_llava.py:293-360).  Same return tuple, same ValueError.
 
     plan_hint = {"max_image_tokens": n, "left_padding": bool} (emitted by train.data.Collator from the host copy of
     input_ids) removes the merge's host sync: the merged length n * (P - 1) + T and the padding side are then known
     up front, the plan kernel's own result is compared with them ON THE DEVICE and a mismatch (wrong hint, or the
-    reference's image-count ValueError) is raised by ops.check_deferred() at the caller's next sync point."""
+    reference's image-count ValueError) is raised by ops.check_deferred() at the caller's next sync point.
+
+    zero_pad_rows: the LLaVA-NeXT variant additionally zeroes the merged rows that came from pad tokens
+    (mantis/models/mllava_next/modeling_llava_next.py:455-461) -- done by pointing their source-map entries at "zero fill"."""
     _need_cuda(image_features, inputs_embeds, input_ids)
     num_images, P, D = image_features.shape
     B, T = input_ids.shape
@@ -806,6 +810,9 @@ def merge_input_ids_with_image_features(image_features, inputs_embeds, input_ids
     out_labels = torch.empty((B, S), dtype=torch.int64, device=dev) if lab is not None else None
     _call("mb200_merge_index", _p(ids), _p(am), _p(lab), _p(ws), B, T, P, S, left_padding, int(image_token_index),
           int(ignore_index), _p(srcmap), _p(out_mask), _p(out_labels), _p(out_pos), _st())
+    if zero_pad_rows:
+        src_tok = torch.gather(ids, 1, srcmap.clamp(min=0).to(torch.int64))
+        srcmap = torch.where((srcmap >= 0) & (src_tok == int(pad_token_id)), torch.full_like(srcmap, -1), srcmap)
     final = _MergeRowsFn.apply(emb, image_features, srcmap, S)
     if mask_dtype != torch.int64:
         out_mask = out_mask.to(mask_dtype)

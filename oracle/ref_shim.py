@@ -108,6 +108,36 @@ def ref_idefics3_classes():
     return cfg.Idefics3Config, cfg.Idefics3VisionConfig, RefIdefics3
 
 
+def load_reference_llava_next():
+    if "llava_next" in _CACHE:
+        return _CACHE["llava_next"]
+    root = find_ref_root()
+    if root is None:
+        raise RuntimeError("reference tree not found (only available in the build container)")
+    pkg_name = "_mantis_ref.models.mllava_next"
+    for p in ("_mantis_ref", "_mantis_ref.models", pkg_name):
+        if p not in sys.modules:
+            m = types.ModuleType(p)
+            m.__path__ = []
+            sys.modules[p] = m
+    mod = _load(pkg_name + ".modeling_llava_next",
+                os.path.join(root, "mantis", "models", "mllava_next", "modeling_llava_next.py"))
+    _CACHE["llava_next"] = mod
+    return mod
+
+
+def ref_llava_next_classes():
+    modm = load_reference_llava_next()
+
+    class RefLlavaNext(modm.LlavaNextForConditionalGeneration):
+        _supports_sdpa = True
+
+        def tie_weights(self, *a, **k):
+            return None
+
+    return modm.LlavaNextConfig, RefLlavaNext
+
+
 def ref_llava_classes():
     cfg, modm = load_reference_mllava()
 

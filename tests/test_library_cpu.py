@@ -4,6 +4,7 @@ import os
 import subprocess
 
 import pytest
+import torch
 
 from mantis_b200 import _lib
 
@@ -89,3 +90,17 @@ def test_idefics3_shell_has_the_reference_state_dict_layout():
     missing, unexpected = model.load_state_dict(fx["state_dict"], strict=False)
     assert not missing and not unexpected
     assert model.model.image_seq_len == 16
+
+
+def test_llava_next_shell_has_the_reference_state_dict_layout():
+    from helpers import load_fixture
+    from transformers import CLIPVisionConfig, LlamaConfig
+    from mantis.models.mllava_next import LlavaNextConfig, LlavaNextForConditionalGeneration
+    fx = load_fixture("llava_next_batch.pt")
+    cfg = LlavaNextConfig(vision_config=CLIPVisionConfig(**fx["vision"]), text_config=LlamaConfig(**fx["text"]), **fx["cfg"])
+    model = LlavaNextForConditionalGeneration(cfg)
+    missing, unexpected = model.load_state_dict(fx["state_dict"], strict=False)
+    assert not missing and not unexpected
+    assert "image_newline" in dict(model.named_parameters())
+    crops = [torch.zeros(3, 3, 8, 8) + 1, torch.zeros(1, 3, 8, 8) + 2]
+    assert LlavaNextForConditionalGeneration._base_crops(crops)[:, 0, 0, 0].tolist() == [1.0, 2.0]
