@@ -178,6 +178,14 @@ int mb200_decode_attn_bf16(const void* q, const void* k, const void* v, void* o,
 
 /* ---- native decode step: the whole single-token LLaMA/Mistral step (all layers, final norm, LM head, greedy argmax)
  *      enqueued by one call (hf: llama/modeling_llama.py:375-427 at q_len 1).  See decode_engine.cu for the tables. ---- */
+/* RMSNorm fused into the decode projections (hf: llama/modeling_llama.py:53-68 + 171-184 / 225-262): the activations are
+ * normalised inside the skinny GEMM when M <= 2, else into xn_scratch [M, K] first.  Same results as mb200_rmsnorm_fwd +
+ * mb200_skinny_gemm3_bf16 / mb200_skinny_swiglu_bf16 up to the summation order of the row norm. */
+int mb200_skinny_gemm3_norm_bf16(const void* X, const void* gamma, float eps, void* xn_scratch, const void* W0, const void* W1,
+                                 const void* W2, void* C0, void* C1, void* C2, int M, int N0, int N1, int N2, int K,
+                                 long long ldw, void* stream);
+int mb200_skinny_swiglu_norm_bf16(const void* X, const void* gamma, float eps, void* xn_scratch, const void* Wg,
+                                  const void* Wu, void* C, int M, int N, int K, long long ldw, long long ldc, void* stream);
 /* Paged KV cache for generate() (replaces transformers' DynamicCache torch.cat growth used by the reference's
  * prepare_inputs_for_generation, mantis/models/mllava/modeling_llava.py:551-602).  A page holds
  * mb200_kv_page_tokens() tokens of all layers, [L][2 (k,v)][128][Hkv][hd]; the block table is int64 [B, table_stride]

@@ -9,6 +9,7 @@
 // (hf: llama/modeling_llama.py:269-270; mantis/models/mllava/modeling_llava.py:477-519).
 #include "common.cuh"
 #include "sm100_ptx.cuh"
+#include "../../include/mantis_b200.h"
 #include <stdlib.h>
 
 namespace {
@@ -260,7 +261,8 @@ constexpr int RS_SMEM = RS_NS * RS_K * 2 + 2 * RS_NS * 8 + 8 * 8 * 4 * 2 * 4;   
 template <int MT, int MODE>
 __global__ void __launch_bounds__(SK_THREADS)
 skinny_rows_kernel(const bf16* __restrict__ X, SkinnySeg sg, const bf16* __restrict__ bias, const bf16* __restrict__ addend,
-                   int M, int K, long long ldx, long long ldw, long long ld_add, int ngroups) {
+                   int M, int K, long long ldx, long long ldw, long long ld_add, int ngroups,
+                   const bf16* __restrict__ gamma, float eps) {
   extern __shared__ __align__(128) unsigned char ring[];
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + RS_NS * RS_K * 2);
   uint64_t* empty = full + RS_NS;
@@ -298,6 +300,39 @@ skinny_rows_kernel(const bf16* __restrict__ X, SkinnySeg sg, const bf16* __restr
   }
   // ---------------- consumers: warp w owns elements [512 w, 512 w + 512) of every row stage
   mb::pdl_wait();                       // X / addend are the previous kernel's outputs
+  // Optional fused RMSNorm of X (gamma != null; K = the full hidden size): every CTA recomputes the M row norms from L2
+  // (M x K x 2 bytes, while the producer already streams weights) and normalises X on the fly with the standalone
+  // kernel's rounding order -- bf16(gamma * bf16(x * rstd)) -- which saves a launch and a round trip of the activations.
+  float rstd[MT];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) rstd[m] = 1.f;
+  if (gamma) {
+    float ss[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) ss[m] = 0.f;
+    for (int k = threadIdx.x * 8; k < K; k += 256 * 8) {
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        if (m < M) {
+          const int4 xr = __ldg(reinterpret_cast<const int4*>(X + (size_t)m * ldx + k));
+          const bf162* xh = reinterpret_cast<const bf162*>(&xr);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { const float2 t = __bfloat1622float2(xh[j]); ss[m] += t.x * t.x + t.y * t.y; }
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < MT; ++m) { ss[m] = mb::warp_sum(ss[m]); if (lane == 0) red[warp * 4 + m] = ss[m]; }
+    consumer_sync();
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) tot += red[w * 4 + m];
+      rstd[m] = rsqrtf(tot / (float)K + eps);
+    }
+    consumer_sync();
+  }
   uint32_t it = 0;
   for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
     float acc[8][MT], acc2[8][MT];
@@ -318,6 +353,19 @@ skinny_rows_kernel(const bf16* __restrict__ X, SkinnySeg sg, const bf16* __restr
           const bf162* xh = reinterpret_cast<const bf162*>(&xr);
 #pragma unroll
           for (int j = 0; j < 4; ++j) { const float2 t = __bfloat1622float2(xh[j]); xf[u][m][2 * j] = t.x; xf[u][m][2 * j + 1] = t.y; }
+        }
+        if (gamma && kk < klen) {
+          const int4 gr = __ldg(reinterpret_cast<const int4*>(gamma + kbase + kk));
+          const bf162* gh = reinterpret_cast<const bf162*>(&gr);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 gg = __bfloat1622float2(gh[j]);
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+              xf[u][m][2 * j] = mb::rnd<bf16>(gg.x * mb::rnd<bf16>(xf[u][m][2 * j] * rstd[m]));
+              xf[u][m][2 * j + 1] = mb::rnd<bf16>(gg.y * mb::rnd<bf16>(xf[u][m][2 * j + 1] * rstd[m]));
+            }
+          }
         }
       }
 #pragma unroll
@@ -966,7 +1014,7 @@ static inline int skinny_grid(int ngroups, int ctas_per_sm) {
 }
 template <int MT, int MODE>
 int launch_rows(const void* X, const SkinnySeg& sg, const void* bias, const void* addend, int M, int K, long long ldx,
-                long long ldw, long long ld_add, cudaStream_t st) {
+                long long ldw, long long ld_add, cudaStream_t st, const void* gamma = nullptr, float eps = 0.f) {
   static int occ = 0;
   if (!occ) {
     cudaFuncSetAttribute(skinny_rows_kernel<MT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM);
@@ -976,7 +1024,7 @@ int launch_rows(const void* X, const SkinnySeg& sg, const void* bias, const void
   const int Ntot = (MODE == 1) ? sg.N[0] : (sg.N[0] + sg.N[1] + sg.N[2]);
   const int ngroups = (Ntot + 7) / 8;
   mb::launch_ex(skinny_rows_kernel<MT, MODE>, dim3(skinny_grid(ngroups, occ)), dim3(SK_THREADS), RS_SMEM, st, mb::pdl_mode() != 0,
-                (const bf16*)X, sg, (const bf16*)bias, (const bf16*)addend, M, K, ldx, ldw, ld_add, ngroups);
+                (const bf16*)X, sg, (const bf16*)bias, (const bf16*)addend, M, K, ldx, ldw, ld_add, ngroups, (const bf16*)gamma, eps);
   return 0;
 }
 template <int MODE>
@@ -999,20 +1047,26 @@ static int skinny_ring_enabled() {
   if (v < 0) { const char* e = getenv("MB200_SKINNY_RING"); v = (e && e[0] == '0') ? 0 : 1; }
   return v;
 }
+// can the row-stage kernel (the only one with the fused RMSNorm prologue) take this problem?
+static bool skinny_rows_ok(const SkinnySeg& sg, int M, int K) {
+  const bool aligned = !((reinterpret_cast<uintptr_t>(sg.W[0]) | reinterpret_cast<uintptr_t>(sg.W[1]) |
+                          reinterpret_cast<uintptr_t>(sg.W[2])) & 15);
+  return skinny_ring_enabled() && aligned && (M <= 2 || (M <= 4 && (K % 32) != 0));
+}
 int dispatch_skinny(const void* X, const SkinnySeg& sg, const void* bias, const void* addend, int M, int K, long long ldx,
-                    long long ldw, long long ld_add, cudaStream_t st) {
+                    long long ldw, long long ld_add, cudaStream_t st, const void* gamma = nullptr, float eps = 0.f) {
   if (skinny_ring_enabled() && (sg.mode == 1 || sg.mode == 0)) {
     const bool aligned = !((reinterpret_cast<uintptr_t>(sg.W[0]) | reinterpret_cast<uintptr_t>(sg.W[1]) |
                             reinterpret_cast<uintptr_t>(sg.W[2])) & 15);
     if (aligned && (M <= 2 || (M <= 4 && (K % 32) != 0))) {
       if (sg.mode == 1) {
-        if (M == 1) return launch_rows<1, 1>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
-        if (M == 2) return launch_rows<2, 1>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
-        return launch_rows<4, 1>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
+        if (M == 1) return launch_rows<1, 1>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st, gamma, eps);
+        if (M == 2) return launch_rows<2, 1>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st, gamma, eps);
+        return launch_rows<4, 1>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st, gamma, eps);
       }
-      if (M == 1) return launch_rows<1, 0>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
-      if (M == 2) return launch_rows<2, 0>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
-      return launch_rows<4, 0>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
+      if (M == 1) return launch_rows<1, 0>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st, gamma, eps);
+      if (M == 2) return launch_rows<2, 0>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st, gamma, eps);
+      return launch_rows<4, 0>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st, gamma, eps);
     }
     if (aligned && (K % 32) == 0) {
       if (sg.mode == 1) return launch_ring<1>(X, sg, bias, addend, M, K, ldx, ldw, ld_add, st);
@@ -1074,6 +1128,48 @@ int mb200_skinny_swiglu_bf16(const void* X, const void* Wg, const void* Wu, void
   sg.C[0] = (bf16*)C; sg.C[1] = sg.C[2] = nullptr; sg.N[0] = N; sg.N[1] = N; sg.N[2] = 0;
   sg.ldc[0] = ldc; sg.ldc[1] = sg.ldc[2] = 0;
   dispatch_skinny(X, sg, nullptr, nullptr, M, K, ldx, ldw, 0, (cudaStream_t)stream);
+  MB200_CHECK_LAUNCH();
+  return MB200_OK;
+}
+
+// Fused RMSNorm + projections for the decode step: Ci = rmsnorm(X; gamma, eps) Wi^T.  The norm runs inside the GEMM when
+// the row-stage kernel applies (M <= 2); otherwise X is normalised into xn_scratch [M, K] first.
+int mb200_skinny_gemm3_norm_bf16(const void* X, const void* gamma, float eps, void* xn_scratch, const void* W0, const void* W1,
+                                 const void* W2, void* C0, void* C1, void* C2, int M, int N0, int N1, int N2, int K,
+                                 long long ldw, void* stream) {
+  if (M <= 0) return MB200_OK;
+  if (M > 16 || (K & 7) || (ldw & 7)) return -ENOTSUP;
+  SkinnySeg sg; sg.nseg = 3; sg.mode = 0;
+  sg.W[0] = (const bf16*)W0; sg.W[1] = (const bf16*)W1; sg.W[2] = (const bf16*)W2;
+  sg.C[0] = (bf16*)C0; sg.C[1] = (bf16*)C1; sg.C[2] = (bf16*)C2;
+  sg.N[0] = N0; sg.N[1] = N1; sg.N[2] = N2; sg.ldc[0] = N0; sg.ldc[1] = N1; sg.ldc[2] = N2;
+  if (skinny_rows_ok(sg, M, K) && !(reinterpret_cast<uintptr_t>(gamma) & 15)) {
+    dispatch_skinny(X, sg, nullptr, nullptr, M, K, K, ldw, 0, (cudaStream_t)stream, gamma, eps);
+  } else {
+    const int rc = mb200_rmsnorm_fwd(X, gamma, xn_scratch, nullptr, M, K, eps, MB200_DTYPE_BF16, stream);
+    if (rc) return rc;
+    dispatch_skinny(xn_scratch, sg, nullptr, nullptr, M, K, K, ldw, 0, (cudaStream_t)stream);
+  }
+  MB200_CHECK_LAUNCH();
+  return MB200_OK;
+}
+
+// C[M,N] = silu(xn Wg^T) * (xn Wu^T) with xn = rmsnorm(X; gamma, eps)
+int mb200_skinny_swiglu_norm_bf16(const void* X, const void* gamma, float eps, void* xn_scratch, const void* Wg,
+                                  const void* Wu, void* C, int M, int N, int K, long long ldw, long long ldc, void* stream) {
+  if (M <= 0) return MB200_OK;
+  if (M > 16 || (K & 7) || (ldw & 7)) return -ENOTSUP;
+  SkinnySeg sg; sg.nseg = 2; sg.mode = 1;
+  sg.W[0] = (const bf16*)Wg; sg.W[1] = (const bf16*)Wu; sg.W[2] = nullptr;
+  sg.C[0] = (bf16*)C; sg.C[1] = sg.C[2] = nullptr; sg.N[0] = N; sg.N[1] = N; sg.N[2] = 0;
+  sg.ldc[0] = ldc; sg.ldc[1] = sg.ldc[2] = 0;
+  if (skinny_rows_ok(sg, M, K) && !(reinterpret_cast<uintptr_t>(gamma) & 15)) {
+    dispatch_skinny(X, sg, nullptr, nullptr, M, K, K, ldw, 0, (cudaStream_t)stream, gamma, eps);
+  } else {
+    const int rc = mb200_rmsnorm_fwd(X, gamma, xn_scratch, nullptr, M, K, eps, MB200_DTYPE_BF16, stream);
+    if (rc) return rc;
+    dispatch_skinny(xn_scratch, sg, nullptr, nullptr, M, K, K, ldw, 0, (cudaStream_t)stream);
+  }
   MB200_CHECK_LAUNCH();
   return MB200_OK;
 }

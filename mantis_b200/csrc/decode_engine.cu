@@ -164,14 +164,19 @@ int mb200_llama_decode_step(const int* dims, const float* fparm, const void* con
   const float scale = 1.0f / sqrtf((float)hd);
   const int HD = H * hd, KD = Hkv * hd;
 
-  static int pdl = -1;
+  static int pdl = -1, fuse_norm = -1;
   if (pdl < 0) { const char* e = getenv("MB200_PDL"); pdl = (e && e[0] == '0') ? 0 : 1; }
+  if (fuse_norm < 0) { const char* e = getenv("MB200_DECODE_FUSE_NORM"); fuse_norm = (e && e[0] == '0') ? 0 : 1; }
   TRY(mb200_embedding_fwd(ids, embed, x, B, D, V, dt, stream));      // plain launch: its inputs come from torch kernels
   PdlScope scope(pdl);
   for (int l = 0; l < L; ++l) {
     const void* const* w = layers + (size_t)l * 11;
-    TRY(mb200_rmsnorm_fwd(x, w[7], xn, nullptr, B, D, eps, dt, stream));
-    TRY(mb200_skinny_gemm3_bf16(xn, w[0], w[1], w[2], q, k, v, B, HD, KD, KD, D, D, D, stream));
+    if (fuse_norm) {
+      TRY(mb200_skinny_gemm3_norm_bf16(x, w[7], eps, xn, w[0], w[1], w[2], q, k, v, B, HD, KD, KD, D, D, stream));
+    } else {
+      TRY(mb200_rmsnorm_fwd(x, w[7], xn, nullptr, B, D, eps, dt, stream));
+      TRY(mb200_skinny_gemm3_bf16(xn, w[0], w[1], w[2], q, k, v, B, HD, KD, KD, D, D, D, stream));
+    }
     if (table) {
       TRY(mb200_rope_append_paged_bf16(q, k, v, qr, table, tstride, l * layer_stride, v_off, pos, inv_freq, B, H, Hkv, hd,
                                        ctx, rope_scale, stream));
@@ -184,8 +189,12 @@ int mb200_llama_decode_step(const int* dims, const float* fparm, const void* con
                                  kbits, kbs, stream));
     }
     TRY(mb200_skinny_gemm_bf16(ao, w[3], x, nullptr, x, B, D, HD, HD, HD, D, D, stream));          // x += o_proj(attn)
-    TRY(mb200_rmsnorm_fwd(x, w[8], xn, nullptr, B, D, eps, dt, stream));
-    TRY(mb200_skinny_swiglu_bf16(xn, w[4], w[5], act, B, I, D, D, D, I, stream));                   // silu(gate) * up
+    if (fuse_norm) {
+      TRY(mb200_skinny_swiglu_norm_bf16(x, w[8], eps, xn, w[4], w[5], act, B, I, D, D, I, stream));
+    } else {
+      TRY(mb200_rmsnorm_fwd(x, w[8], xn, nullptr, B, D, eps, dt, stream));
+      TRY(mb200_skinny_swiglu_bf16(xn, w[4], w[5], act, B, I, D, D, D, I, stream));                 // silu(gate) * up
+    }
     TRY(mb200_skinny_gemm_bf16(act, w[6], x, nullptr, x, B, D, I, I, I, D, D, stream));            // x += down(act)
   }
   TRY(mb200_rmsnorm_fwd(x, fnorm, xn, nullptr, B, D, eps, dt, stream));

@@ -356,6 +356,19 @@ def test_skinny_fused_projections(ops, cuda, M):
         g = (x.float() @ wg.float().t()).bfloat16(); u = (x.float() @ wu.float().t()).bfloat16()
         ref = torch.nn.functional.silu(g) * u
         assert _rel(act, ref) < 1e-2, (M, D, _rel(act, ref))
+        # RMSNorm fused into the projections (in-kernel for M <= 2, through the scratch buffer otherwise)
+        gam = (1 + 0.1 * torch.randn(D, device=cuda)).bfloat16()
+        xn = ops.rms_norm(x, gam, 1e-5)
+        scratch = torch.empty_like(x)
+        q2 = torch.empty_like(q); k2 = torch.empty_like(k); v2 = torch.empty_like(v); act2 = torch.empty_like(act)
+        ops._call("mb200_skinny_gemm3_norm_bf16", ops._p(x), ops._p(gam), 1e-5, ops._p(scratch), ops._p(wq), ops._p(wk),
+                  ops._p(wv), ops._p(q2), ops._p(k2), ops._p(v2), M, Nq, Nkv, Nkv, D, D, ops._st())
+        for got, w in ((q2, wq), (k2, wk), (v2, wv)):
+            assert _rel(got, xn.float() @ w.float().t()) < 5e-3
+        ops._call("mb200_skinny_swiglu_norm_bf16", ops._p(x), ops._p(gam), 1e-5, ops._p(scratch), ops._p(wg), ops._p(wu),
+                  ops._p(act2), M, I, D, D, I, ops._st())
+        g = (xn.float() @ wg.float().t()).bfloat16(); u = (xn.float() @ wu.float().t()).bfloat16()
+        assert _rel(act2, torch.nn.functional.silu(g) * u) < 1e-2
 
 
 @pytest.mark.parametrize("B,H,Hkv,ctx", [(1, 32, 8, 6137), (3, 8, 2, 300), (2, 4, 4, 33), (16, 32, 8, 1000)])
