@@ -92,6 +92,11 @@ int mb200_cast(const void* x, int in_dtype, void* y, int out_dtype, long long n,
  * [N,H,W,C] (channels_last) or [N,C,H,W] -> out[n,c,h,w] = lut[c][pixel]; lut is fp32 [C][256] on the device. */
 int mb200_image_normalize_u8(const void* px, const float* lut, void* out, int out_dtype, int N, int C, int H, int W,
                              int channels_last, void* stream);
+/* One pass of Pillow's antialiased 8-bit resampler (what `PIL.Image.resize` does inside the reference's image processor):
+ * [in_h, in_w, C] uint8 -> [in_h, out_len, C] (horizontal) or [out_len, in_w, C]; bounds int32 [out_len][2] = (first tap,
+ * taps), coef int32 [out_len][ksize] in 22-bit fixed point, both computed on the host like Pillow's precompute_coeffs. */
+int mb200_resize_u8_pass(const void* in, void* out, const int* bounds, const int* coef, int ksize, int in_h, int in_w,
+                         int out_len, int C, int horizontal, void* stream);
 /* flags[r] = 1 iff row r is all zeros: Idefics2 padding-image removal (mantis/models/idefics2/modeling_idefics2.py:1637-1639) */
 int mb200_rows_all_zero(const void* x, long long n_rows, long long row_elems, int* flags, int dtype, void* stream);
 

@@ -612,6 +612,39 @@ inline int ew_grid(long long work_items, int threads = 256) {
   else return -EINVAL;
 
 
+// ---------------------------------------------------------------- antialiased resize of 8-bit images (caller side, 8f-2)
+// One pass of Pillow's two-pass resampler (src/libImaging/Resample.c, ImagingResampleHorizontal_8bpc / Vertical_8bpc), which
+// the reference's image processors call through PIL for every image: acc = 2^21 + sum_k pixel * coef (22-bit fixed point,
+// int32), out = clip8(acc >> 22).  The per-output-index tap ranges and coefficients come from the host (double precision,
+// same operation order as Pillow), so the device result is bit-identical to Image.resize.  HWC uint8 in and out.
+namespace {
+template <bool HORIZ>
+__global__ void __launch_bounds__(256)
+resize_pass_u8_kernel(const unsigned char* __restrict__ in, unsigned char* __restrict__ out, const int* __restrict__ bounds,
+                      const int* __restrict__ coef, int ksize, int in_h, int in_w, int out_len, int C) {
+  const int oh = HORIZ ? in_h : out_len, ow = HORIZ ? out_len : in_w;
+  const long long total = (long long)oh * ow * C;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(t % C);
+    const int x = (int)((t / C) % ow);
+    const int y = (int)(t / ((long long)C * ow));
+    const int o = HORIZ ? x : y;
+    const int lo = bounds[2 * o], n = bounds[2 * o + 1];
+    const int* k = coef + (size_t)o * ksize;
+    int acc = 1 << 21;
+    if (HORIZ) {
+      const unsigned char* p = in + ((size_t)y * in_w + lo) * C + c;
+      for (int i = 0; i < n; ++i) acc += (int)p[(size_t)i * C] * k[i];
+    } else {
+      const unsigned char* p = in + ((size_t)lo * in_w + x) * C + c;
+      for (int i = 0; i < n; ++i) acc += (int)p[(size_t)i * in_w * C] * k[i];
+    }
+    acc >>= 22;
+    out[t] = (unsigned char)(acc < 0 ? 0 : (acc > 255 ? 255 : acc));
+  }
+}
+}  // namespace
+
 // ---------------------------------------------------------------- image rescale + normalize + layout (caller side, 8f-2)
 // uint8 pixels (HWC as decoded, or CHW as HF processors hand them over) -> normalized [N, C, H, W] fp32/bf16 through a
 // 256-entry table per channel.  The table holds (float32(float64(v) * rescale) - mean) / std evaluated exactly like the
@@ -882,6 +915,22 @@ int mb200_image_normalize_u8(const void* px, const float* lut, void* out, int ou
   else if (out_dtype == MB200_DTYPE_BF16)
     image_normalize_u8_kernel<bf16><<<g, 256, 0, st>>>((const unsigned char*)px, lut, (bf16*)out, N, C, H, W, channels_last);
   else return -EINVAL;
+  MB200_CHECK_LAUNCH(); return MB200_OK;
+}
+
+
+// One resampling pass over an [in_h, in_w, C] uint8 image: horizontal -> out [in_h, out_len, C], else -> [out_len, in_w, C].
+// bounds: int32 [out_len][2] = (first tap, tap count); coef: int32 [out_len][ksize] 22-bit fixed point (device pointers).
+int mb200_resize_u8_pass(const void* in, void* out, const int* bounds, const int* coef, int ksize, int in_h, int in_w,
+                         int out_len, int C, int horizontal, void* stream) {
+  if (in_h <= 0 || in_w <= 0 || out_len <= 0 || C <= 0 || ksize <= 0) return -EINVAL;
+  const long long total = (long long)(horizontal ? in_h : out_len) * (horizontal ? out_len : in_w) * C;
+  const int g = ew_grid(total);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (horizontal)
+    resize_pass_u8_kernel<true><<<g, 256, 0, st>>>((const unsigned char*)in, (unsigned char*)out, bounds, coef, ksize, in_h, in_w, out_len, C);
+  else
+    resize_pass_u8_kernel<false><<<g, 256, 0, st>>>((const unsigned char*)in, (unsigned char*)out, bounds, coef, ksize, in_h, in_w, out_len, C);
   MB200_CHECK_LAUNCH(); return MB200_OK;
 }
 

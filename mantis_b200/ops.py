@@ -965,6 +965,19 @@ def im2col(pixels, patch, k_pad, out_dtype):
     return out
 
 
+def resize_u8_pass(img, bounds, coef, out_len, horizontal):
+    """one pass of the antialiased 8-bit resampler: img [H, W, C] uint8 -> [H, out_len, C] (horizontal) / [out_len, W, C];
+    bounds int32 [out_len, 2], coef int32 [out_len, ksize] on the device"""
+    _need_cuda(img, bounds, coef)
+    assert img.dtype == torch.uint8 and img.dim() == 3 and bounds.dtype == torch.int32 and coef.dtype == torch.int32
+    img = img.contiguous()
+    H, W, C = img.shape
+    out = torch.empty((H, out_len, C) if horizontal else (out_len, W, C), dtype=torch.uint8, device=img.device)
+    _call("mb200_resize_u8_pass", _p(img), _p(out), _p(bounds.contiguous()), _p(coef.contiguous()), coef.shape[1], H, W,
+          int(out_len), C, int(bool(horizontal)), _st())
+    return out
+
+
 def image_normalize_u8(pixels_u8, lut, channels_last, out_dtype):
     """uint8 [N,H,W,C] (channels_last) or [N,C,H,W] on the device + fp32 lut [C,256] -> normalized [N,C,H,W] out_dtype"""
     _need_cuda(pixels_u8, lut)
