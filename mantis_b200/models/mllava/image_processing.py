@@ -149,7 +149,7 @@ class B200ImageProcessor:
                 ow, oh = (new_short, new_long) if w <= h else (new_long, new_short)
             else:
                 return None
-            t = torch.from_numpy(np.ascontiguousarray(arr))
+            t = torch.from_numpy(np.array(arr, copy=True))          # PIL hands out read-only buffers
             if self.device.type == "cuda":
                 t = t.pin_memory()
             t = self.resize_u8(t.to(self.device, non_blocking=True), oh, ow)
