@@ -70,3 +70,31 @@ class DecodeEngine:
         ops._call("mb200_llama_decode_step", dims, fparm, self.layer_tab, misc, ops._p(self.ws), self.ld_logits, ops._st())
         self.cache.advance(1)
         return self.logits[:, : self.V], self.next_ids
+
+
+def native_decode_logits(decoder, lm_head, cache, input_ids, x_dtype, attention_mask, position_ids, labels=None,
+                         output_hidden_states=False):
+    """Single-token decode of any model whose text stack is a B200DecoderModel + a bias-free LM head (LLaVA, LLaVA-NeXT,
+    Idefics2, Idefics3): one C call per token through the engine cached on the KV cache.  Returns logits [B, V] (bf16), or
+    None when the step is not eligible (then the caller takes the Python path)."""
+    if (input_ids is None or input_ids.shape[1] != 1 or labels is not None or output_hidden_states
+            or torch.is_grad_enabled() or not isinstance(cache, B200KVCache) or cache.get_seq_length() == 0):
+        return None
+    if type(lm_head).__name__ != "B200Linear" or lm_head.bias is not None:
+        return None
+    if not DecodeEngine.eligible(decoder, cache, x_dtype):
+        return None
+    eng = getattr(cache, "_engine", None)
+    if eng is None or eng.decoder is not decoder:
+        eng = DecodeEngine(decoder, lm_head.weight, cache)
+        cache._engine = eng
+    ctx = cache.get_seq_length()
+    kbits = None
+    if attention_mask is not None:
+        if attention_mask.dim() != 2 or attention_mask.shape[1] != ctx + 1:
+            return None
+        kbits = ops.kmask_bits(attention_mask)
+    if position_ids is None:
+        position_ids = torch.full((input_ids.shape[0], 1), ctx, dtype=torch.int64, device=input_ids.device)
+    logits, _ = eng.step(input_ids[:, 0], position_ids[:, -1].to(torch.int64), kbits)
+    return logits

@@ -362,6 +362,17 @@ class Idefics2ForConditionalGeneration(Idefics2PreTrainedModel, GenerationMixin)
                 inputs_embeds=None, pixel_values=None, pixel_attention_mask=None, image_hidden_states=None,
                 labels=None, use_cache=None, output_attentions=None, output_hidden_states=None, return_dict=None,
                 logits_to_keep=0, **kw):
+        if (input_ids is not None and input_ids.shape[1] == 1 and inputs_embeds is None and labels is None
+                and isinstance(past_key_values, B200KVCache) and not output_hidden_states):
+            # decode step: the image states were merged at prefill (ref:1961-1990 caches them), the text stack runs through
+            # the native engine -- one C call per generated token instead of ~420 Python launches
+            from ..decode_engine import native_decode_logits
+            lg = native_decode_logits(self.model.text_model, self.lm_head, past_key_values, input_ids,
+                                      self.model.text_model.embed_tokens.weight.dtype, attention_mask, position_ids)
+            if lg is not None:
+                return Idefics2CausalLMOutputWithPast(loss=None, logits=lg.float().unsqueeze(1),
+                                                      past_key_values=past_key_values, hidden_states=None, attentions=None,
+                                                      image_hidden_states=image_hidden_states)
         outputs = self.model(input_ids=input_ids, attention_mask=attention_mask, position_ids=position_ids,
                              past_key_values=past_key_values, inputs_embeds=inputs_embeds, pixel_values=pixel_values,
                              pixel_attention_mask=pixel_attention_mask, image_hidden_states=image_hidden_states,

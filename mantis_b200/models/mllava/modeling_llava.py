@@ -243,26 +243,11 @@ class LlavaForConditionalGeneration(LlavaPreTrainedModel, GenerationMixin):
 
     def _native_decode(self, input_ids, inputs_embeds, attention_mask, position_ids, cache, labels, output_hidden_states):
         """single-token decode through the C++ engine (one call per token); None if not applicable"""
-        from ..decode_engine import DecodeEngine
-        if (input_ids is None or input_ids.shape[1] != 1 or labels is not None or output_hidden_states
-                or torch.is_grad_enabled() or not isinstance(cache, B200KVCache) or cache.get_seq_length() == 0):
+        from ..decode_engine import native_decode_logits
+        logits = native_decode_logits(self.language_model.model, self.language_model.lm_head, cache, input_ids,
+                                      inputs_embeds.dtype, attention_mask, position_ids, labels, output_hidden_states)
+        if logits is None:
             return None
-        dec = self.language_model.model
-        if not DecodeEngine.eligible(dec, cache, inputs_embeds.dtype):
-            return None
-        eng = getattr(cache, "_engine", None)
-        if eng is None or eng.decoder is not dec:
-            eng = DecodeEngine(dec, self.language_model.lm_head.weight, cache)
-            cache._engine = eng
-        ctx = cache.get_seq_length()
-        kbits = None
-        if attention_mask is not None:
-            if attention_mask.shape[1] != ctx + 1:
-                return None
-            kbits = ops.kmask_bits(attention_mask)
-        if position_ids is None:
-            position_ids = torch.full((input_ids.shape[0], 1), ctx, dtype=torch.int64, device=input_ids.device)
-        logits, _ = eng.step(input_ids[:, 0], position_ids[:, -1].to(torch.int64), kbits)
         return LlavaCausalLMOutputWithPast(loss=None, logits=logits.unsqueeze(1), past_key_values=cache,
                                            hidden_states=None, attentions=None)
 

@@ -65,3 +65,54 @@ def test_idefics2_generate_caches_image_states(cuda):
             lg = model(input_ids=seq, attention_mask=torch.ones_like(seq), pixel_values=pv).logits
             seq = torch.cat([seq, lg[:, -1].argmax(-1, keepdim=True)], 1)
     assert out.cpu().tolist() == seq.cpu().tolist()
+
+
+def test_idefics2_decode_uses_native_engine(cuda):
+    """bf16, head_dim 128: single-token steps of Idefics2 run through the C++ decode engine (one call per token) and
+    reproduce the Python-path logits step after step"""
+    from transformers import Idefics2Config
+    import mantis_b200.ops as om
+    from mantis_b200.models.idefics2 import Idefics2ForConditionalGeneration
+    from mantis_b200.models.kv_cache import B200KVCache
+    cfg = Idefics2Config(
+        vision_config=dict(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, image_size=112,
+                           patch_size=14),
+        perceiver_config=dict(resampler_n_latents=8, resampler_depth=1, resampler_n_heads=2, resampler_head_dim=32,
+                              num_key_value_heads=1, hidden_size=256, rms_norm_eps=1e-5),
+        text_config=dict(model_type="mistral", hidden_size=256, intermediate_size=512, num_hidden_layers=2,
+                         num_attention_heads=2, num_key_value_heads=1, vocab_size=1000, pad_token_id=0, rms_norm_eps=1e-5,
+                         sliding_window=4096),
+        image_token_id=990, tie_word_embeddings=False)
+    torch.manual_seed(0)
+    model = Idefics2ForConditionalGeneration(cfg).to(cuda).to(torch.bfloat16).eval()
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.dim() >= 2:
+                p.mul_(3.0)
+    ids = torch.randint(1, 980, (2, 24), device=cuda); ids[:, 3:11] = 990
+    pv = torch.randn(2, 1, 3, 112, 112, device=cuda).bfloat16()
+
+    def run(native):
+        old = om.FORCE_GENERIC
+        logits = []
+        with torch.no_grad():
+            cache = B200KVCache()
+            am = torch.ones_like(ids)
+            out = model(input_ids=ids, pixel_values=pv, attention_mask=am, past_key_values=cache, use_cache=True)
+            for step in range(4):
+                nxt = torch.tensor([7, 11], device=cuda) + step
+                am = torch.cat([am, torch.ones_like(nxt[:, None])], 1)
+                om.FORCE_GENERIC = not native
+                try:
+                    out = model(input_ids=nxt[:, None], attention_mask=am, past_key_values=cache, use_cache=True,
+                                image_hidden_states=out.image_hidden_states)
+                finally:
+                    om.FORCE_GENERIC = old
+                logits.append(out.logits[:, -1].float().clone())
+        return logits, hasattr(cache, "_engine")
+
+    a, used_a = run(True)
+    b, used_b = run(False)
+    assert used_a and not used_b
+    for x, y in zip(a, b):
+        assert rel_err(x, y) < 3e-2, rel_err(x, y)
