@@ -35,6 +35,9 @@ def parse():
     ap.add_argument("--text-layers", type=int, default=32, help="debug only: fewer layers => INVALID as a bench number")
     ap.add_argument("--vision-layers", type=int, default=27)
     ap.add_argument("--samples", type=int, default=SAMPLES_PER_STEP)
+    ap.add_argument("--micro-batch", type=int, default=0,
+                    help="samples per forward/backward (0 = workload default: 1 for mllava, whose merged sequence is 7864 "
+                         "tokens per sample; 4 for idefics2, whose sequences stay at 2048 tokens)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-gemm", action="store_true", help="only run the per-kernel roofline section")
@@ -340,11 +343,17 @@ def run_ours(args):
             model = LlavaForConditionalGeneration(cfg)
     torch.set_default_dtype(old)
     model.train()
-    trainer = B200Trainer(model, lr=1e-5, weight_decay=0.0, max_grad_norm=1.0, grad_accum=args.samples)
+    mb = args.micro_batch or (4 if args.workload == "idefics2" else 1)
+    mb = max(1, min(mb, args.samples))
+    while args.samples % mb:
+        mb -= 1
+    trainer = B200Trainer(model, lr=1e-5, weight_decay=0.0, max_grad_norm=1.0, grad_accum=args.samples // mb)
     n_train = sum(p.numel() for p in trainer.params)
 
     mk = make_sample_idefics2 if args.workload == "idefics2" else make_sample
     host = [mk(rank * args.samples + i, torch) for i in range(args.samples)]
+    if mb > 1:                                   # same-shape synthetic samples: a micro-batch is a plain concatenation
+        host = [{k: torch.cat([s[k] for s in host[i:i + mb]], dim=0) for k in host[0]} for i in range(0, len(host), mb)]
     host = [{k: v.pin_memory() for k, v in s.items()} for s in host]
     resident = [{k: v.to(dev, non_blocking=True) for k, v in s.items()} for s in host]
     torch.cuda.synchronize()
@@ -418,7 +427,7 @@ def run_ours(args):
                                 if args.workload == "mllava" else
                                 "Mantis-8B-Idefics2 instruction-tuning step, random init (configs[2])"),
                    "samples_per_rank_per_step": args.samples, "images_per_sample": N_IMG, "text_tokens": T_TEXT,
-                   "merged_seq_len": S_merged, "micro_batch": 1, "grad_accum": args.samples,
+                   "merged_seq_len": S_merged, "micro_batch": mb, "grad_accum": args.samples // mb,
                    "parallelism": f"dp{world}", "optimizer": "fused AdamW (fp32 moments) + grad-norm clip",
                    "trainable_params": n_train, "vision_tower": "frozen (train_mllava.py:239-242)",
                    "l2": "working set >> L2 (35 GB of activations + 16 GB weights per micro-batch), no flush needed",
