@@ -46,10 +46,32 @@ class _GradReady(torch.autograd.Function):
         return g, None
 
 
+def lr_lambda(step, total_steps, warmup_steps, kind="cosine"):
+    """Multiplier of the base LR for optimizer step `step` (0-based) -- the schedules HF Trainer builds for
+    `--lr_scheduler_type {cosine,linear,constant}` with `--warmup_ratio` (mantis/train/scripts/train_mllava.sh:162-165;
+    transformers/optimization.py get_cosine_schedule_with_warmup / get_linear_schedule_with_warmup): linear warm-up from 0,
+    then half a cosine period (or a straight line) down to 0 at `total_steps`."""
+    if kind == "constant" or not total_steps:
+        return 1.0 if step >= warmup_steps or not warmup_steps else float(step) / float(max(1, warmup_steps))
+    if step < warmup_steps:
+        return float(step) / float(max(1, warmup_steps))
+    if kind == "linear":
+        return max(0.0, float(total_steps - step) / float(max(1, total_steps - warmup_steps)))
+    if kind == "cosine":
+        progress = float(step - warmup_steps) / float(max(1, total_steps - warmup_steps))
+        return max(0.0, 0.5 * (1.0 + math.cos(math.pi * 2.0 * 0.5 * progress)))
+    raise ValueError(f"unknown lr schedule {kind!r}")
+
+
 class B200Trainer:
     def __init__(self, model, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0,
-                 grad_accum=1, freeze_vision=True, fused_wgrad_accum=True, overlap_allreduce=True):
+                 grad_accum=1, freeze_vision=True, fused_wgrad_accum=True, overlap_allreduce=True,
+                 lr_schedule="constant", total_steps=None, warmup_ratio=0.0, warmup_steps=None):
         self.model = model
+        self.lr_schedule, self.total_steps = lr_schedule, total_steps
+        # HF Trainer: warmup_steps wins over warmup_ratio; the ratio is rounded up (TrainingArguments.get_warmup_steps)
+        self.warmup_steps = (warmup_steps if warmup_steps is not None
+                             else int(math.ceil((total_steps or 0) * warmup_ratio)))
         if freeze_vision:                                   # mantis/train/train_mllava.py:239-242
             for n, p in model.named_parameters():
                 if "vision_tower" in n or "vision_model" in n:
@@ -120,6 +142,30 @@ class B200Trainer:
             layer.register_forward_pre_hook(make_hook(i))
         self._has_hooks = True
 
+    def current_lr(self):
+        """learning rate of the NEXT optimizer step (scheduler value after `step_count` completed steps)"""
+        return self.lr * lr_lambda(self.step_count, self.total_steps, self.warmup_steps, self.lr_schedule)
+
+    # ---- checkpoint / resume of the optimizer side (the model itself goes through save_pretrained) ----
+    def state_dict(self):
+        return {"step": self.step_count, "lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.wd,
+                "lr_schedule": self.lr_schedule, "total_steps": self.total_steps, "warmup_steps": self.warmup_steps,
+                "exp_avg": [m.detach().cpu() for m in self.m], "exp_avg_sq": [v.detach().cpu() for v in self.v]}
+
+    def load_state_dict(self, state):
+        if len(state["exp_avg"]) != len(self.m):
+            raise ValueError(f"optimizer state has {len(state['exp_avg'])} tensors, the model has {len(self.m)} trainable ones")
+        for dst, src in zip(self.m, state["exp_avg"]):
+            if dst.shape != src.shape:
+                raise ValueError("optimizer state does not match the trainable parameters")
+            dst.copy_(src)
+        for dst, src in zip(self.v, state["exp_avg_sq"]):
+            dst.copy_(src)
+        self.step_count = int(state["step"])
+        self.lr, self.betas, self.eps, self.wd = state["lr"], tuple(state["betas"]), state["eps"], state["weight_decay"]
+        self.lr_schedule, self.total_steps = state["lr_schedule"], state["total_steps"]
+        self.warmup_steps = state["warmup_steps"]
+
     def zero_grad(self):
         self.flat_grad.zero_()
 
@@ -160,9 +206,10 @@ class B200Trainer:
             if total > self.max_grad_norm:
                 scale *= self.max_grad_norm / (total + 1e-6)
         ops.check_deferred()                       # errors of sync-free merges surface here, after the step's one readback
+        lr = self.current_lr()
         self.step_count += 1
         for p, m, v in zip(self.params, self.m, self.v):
-            ops.adamw_step(p.data, p.grad, m, v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
+            ops.adamw_step(p.data, p.grad, m, v, lr, self.betas[0], self.betas[1], self.eps, self.wd,
                            self.step_count, grad_scale=scale)
         self.zero_grad()
 
