@@ -168,3 +168,32 @@ class PackingDataset(torch.utils.data.Dataset):
             else:
                 out[k] = [x[k] for x in items]
         return out
+
+
+def merged_length(num_text_tokens: int, num_images: int, patches_per_image: int) -> int:
+    """length of a sample after the image-token merge: every <image> placeholder grows to `patches_per_image` rows
+    (ref: modeling_llava.py:305, max_embed_dim = num_special_image_tokens * (num_image_patches - 1) + sequence_length)"""
+    return num_text_tokens + num_images * (patches_per_image - 1)
+
+
+def partition_balanced(lengths, world_size: int, samples_per_rank=None):
+    """Data-parallel partition of one global step ("ragged sequence lengths in real data => sort/bucket by
+    merged length to balance ranks").  Every rank runs its samples one by one and the step ends with the gradient
+    all-reduce, so the step time is the time of the rank with the most tokens (attention makes it superlinear, which the
+    quadratic term of the cost accounts for).  Longest-processing-time greedy: samples sorted by cost, each handed to the
+    currently lightest rank that still has a free slot.  Returns `world_size` lists of indices into `lengths`.
+    Deterministic (ties by index), every rank gets the same number of samples when `samples_per_rank` is given."""
+    n = len(lengths)
+    if samples_per_rank is None:
+        samples_per_rank = -(-n // world_size)
+    if n > samples_per_rank * world_size:
+        raise ValueError(f"{n} samples do not fit {world_size} ranks x {samples_per_rank}")
+    cost = [float(L) + float(L) * float(L) / 65536.0 for L in lengths]     # linear layers + causal attention (S^2 / 2 x 32 heads ...)
+    order = sorted(range(n), key=lambda i: (-cost[i], i))
+    load = [0.0] * world_size
+    parts = [[] for _ in range(world_size)]
+    for i in order:
+        r = min((r for r in range(world_size) if len(parts[r]) < samples_per_rank), key=lambda r: (load[r], r))
+        parts[r].append(i)
+        load[r] += cost[i]
+    return parts

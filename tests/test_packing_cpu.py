@@ -59,3 +59,22 @@ def test_packed_segments_from_position_ids():
     pos = torch.tensor([[0, 1, 2, 0, 1, 0, 1, 2, 3], [0, 1, 2, 3, 4, 5, 0, 1, 2]])
     assert ops.packed_segments(pos) == [(0, 0, 3), (0, 3, 5), (0, 5, 9), (1, 0, 6), (1, 6, 9)]
     assert ops.packed_segments(torch.tensor([5, 6, 0, 1])) == [(0, 0, 2), (0, 2, 4)]    # 1-D ids (reference layout)
+
+
+def test_partition_balanced_by_merged_length():
+    from mantis_b200.train import merged_length, partition_balanced
+    assert merged_length(2048, 8, 728) == 7864                          # the bench sample
+    import random
+    rnd = random.Random(0)
+    lens = [merged_length(rnd.randint(64, 2048), rnd.randint(1, 20), 728) for _ in range(32)]
+    parts = partition_balanced(lens, world_size=8, samples_per_rank=4)
+    assert sorted(i for p in parts for i in p) == list(range(32)) and all(len(p) == 4 for p in parts)
+    tok = [sum(lens[i] for i in p) for p in parts]
+    naive = [sum(lens[r * 4:(r + 1) * 4]) for r in range(8)]              # the order the sampler happened to deliver
+    assert max(tok) <= max(naive) and max(tok) - min(tok) < max(naive) - min(naive)
+    assert max(tok) <= 1.15 * (sum(tok) / 8)                             # within 15 % of the perfect split
+    assert partition_balanced(lens, 8, 4) == parts                       # deterministic
+    assert partition_balanced([5, 5, 5], 2) == [[0, 2], [1]]
+    import pytest
+    with pytest.raises(ValueError):
+        partition_balanced(lens, 4, 4)
