@@ -201,3 +201,18 @@ def test_fullwidth_bf16_tensor_core_path_vs_fp32_simt_path(cuda):
         l16 = m16(input_ids=ids, pixel_values=pv.bfloat16(), attention_mask=torch.ones_like(ids)).logits
         l32 = m32(input_ids=ids, pixel_values=pv, attention_mask=torch.ones_like(ids)).logits
     assert rel_err(l16, l32) < 3e-2, rel_err(l16, l32)
+
+
+def test_batched_greedy_with_left_padding_and_uneven_images(cuda):
+    """decode-time branch (ref :477-508): a left-padded batch whose samples carry different numbers of images keeps masked
+    slots inside the merged prompt; the cached decode must reproduce the reference's cache-free loop token for token
+    (fixture: oracle/make_golden_batch_greedy.py)"""
+    fx = load_fixture("greedy_llava_batch.pt")
+    model = load_model(fx, torch.float32, cuda).eval()
+    ids = fx["input_ids"].to(cuda); att = fx["attention_mask"].to(cuda); pv = fx["pixel_values"].to(cuda)
+    n_new = fx["generated"].shape[1] - ids.shape[1]
+    seq = model.greedy_generate(ids, pixel_values=pv, attention_mask=att, max_new_tokens=n_new)
+    assert seq.cpu().tolist() == fx["generated"].tolist()
+    out = model.generate(input_ids=ids, pixel_values=pv, attention_mask=att, max_new_tokens=n_new, do_sample=False,
+                         num_beams=1, pad_token_id=301)
+    assert out.cpu().tolist() == fx["generated"].tolist()
