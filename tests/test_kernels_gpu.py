@@ -564,6 +564,38 @@ def test_merge_backward_and_large(ops, cuda):
                         g.float().pow(2).sum().item(), rel_tol=1e-5)
 
 
+def test_merge_full_baseline_size_properties(ops, cuda):
+    """BASELINE config 2 shape (B = 4 samples x (2048 tokens with 8 placeholders), P = 728, D = 4096, bf16 -> S = 7864): too
+    big for the numpy oracle, so the kernels are checked through size-independent properties (tests/helpers.merge_properties,
+    itself pinned to the oracle in tests/test_oracle.py): exact conservation checksum, exact layout, mask / position ids,
+    gradient = the inverse permutation, determinism, and the sync-free (Collator hint) path == the synchronising one."""
+    from helpers import merge_properties
+    g = torch.Generator(device="cpu").manual_seed(12)
+    B, T, P, D, n_img = 4, 2048, 728, 4096, 8
+    ids = torch.randint(0, 128000, (B, T), generator=g)
+    for j in range(n_img):
+        ids[:, j * 256 + 16] = 128256                                  # the bench's placeholder offsets (SURVEY 8d)
+    emb = torch.randint(-2, 3, (B, T, D), generator=g).to(torch.bfloat16)
+    feats = torch.randint(-2, 3, (B * n_img, P, D), generator=g).to(torch.bfloat16)
+    ids, emb, feats = ids.to(cuda), emb.to(cuda).requires_grad_(True), feats.to(cuda).requires_grad_(True)
+    att = torch.ones_like(ids)
+    final, mask, labels, pos = ops.merge_input_ids_with_image_features(feats, emb, ids, att, ids.clone(), 128256, 128257)
+    assert final.shape == (B, 7864, D)
+    merge_properties(final.detach(), mask, pos, emb.detach(), feats.detach(), ids, 128256)
+    assert int((labels == -100).sum()) == B * n_img * P                 # image rows carry the ignore label, text rows their id
+    again = ops.merge_input_ids_with_image_features(feats, emb, ids, att, ids.clone(), 128256, 128257)
+    hinted = ops.merge_input_ids_with_image_features(feats, emb, ids, att, ids.clone(), 128256, 128257,
+                                                     plan_hint={"max_image_tokens": n_img, "left_padding": True})
+    ops.check_deferred()
+    for other in (again, hinted):
+        assert all(torch.equal(a, b) for a, b in zip((final, mask, labels, pos), other))
+    go = torch.randint(-2, 3, final.shape, generator=g).to(torch.bfloat16).to(cuda)
+    final.backward(go)
+    assert torch.equal(emb.grad.float().sum(dim=(0, 1)) + feats.grad.float().sum(dim=(0, 1)), go.float().sum(dim=(0, 1)))
+    assert emb.grad[:, 16].abs().sum() == 0                             # placeholder rows receive no gradient
+    assert torch.equal(feats.grad[0, 0], go[0, 16]) and torch.equal(emb.grad[0, 17], go[0, 16 + P])
+
+
 # ------------------------------------------------------------------------------------------------ loss / optimiser
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_lm_head_ce(ops, cuda, dtype):
