@@ -38,3 +38,31 @@ def test_idefics2_save_load_roundtrip():
     m2 = Idefics2ForConditionalGeneration.from_pretrained(d)
     for k, v in fx["state_dict"].items():
         assert torch.equal(m2.state_dict()[k], v), k
+
+
+def test_idefics3_save_load_roundtrip():
+    from mantis_b200.models.idefics3 import Idefics3Config, Idefics3ForConditionalGeneration
+    fx = load_fixture("idefics3_full.pt")
+    m = Idefics3ForConditionalGeneration(Idefics3Config(**fx["cfg"])); m.load_state_dict(fx["state_dict"])
+    d = tempfile.mkdtemp()
+    m.save_pretrained(d)
+    assert set(load_file(os.path.join(d, "model.safetensors")).keys()) == set(fx["state_dict"].keys())
+    m2 = Idefics3ForConditionalGeneration.from_pretrained(d)
+    for k, v in fx["state_dict"].items():
+        assert torch.equal(m2.state_dict()[k], v), k
+    assert m2.config.scale_factor == 2 and type(m2.config.text_config).__name__ == "LlamaConfig"
+
+
+def test_llava_next_save_load_roundtrip():
+    from transformers import CLIPVisionConfig, LlamaConfig
+    from mantis_b200.models.mllava_next import LlavaNextConfig, LlavaNextForConditionalGeneration
+    fx = load_fixture("llava_next_batch.pt")
+    cfg = LlavaNextConfig(vision_config=CLIPVisionConfig(**fx["vision"]), text_config=LlamaConfig(**fx["text"]), **fx["cfg"])
+    m = LlavaNextForConditionalGeneration(cfg); m.load_state_dict(fx["state_dict"])
+    d = tempfile.mkdtemp()
+    m.save_pretrained(d)
+    assert set(load_file(os.path.join(d, "model.safetensors")).keys()) == set(fx["state_dict"].keys())
+    m2 = LlavaNextForConditionalGeneration.from_pretrained(d)
+    for k, v in fx["state_dict"].items():
+        assert torch.equal(m2.state_dict()[k], v), k
+    assert torch.equal(m2.image_newline, fx["state_dict"]["image_newline"])
