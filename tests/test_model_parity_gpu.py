@@ -216,3 +216,24 @@ def test_batched_greedy_with_left_padding_and_uneven_images(cuda):
     out = model.generate(input_ids=ids, pixel_values=pv, attention_mask=att, max_new_tokens=n_new, do_sample=False,
                          num_beams=1, pad_token_id=301)
     assert out.cpu().tolist() == fx["generated"].tolist()
+
+
+def test_decode_engine_bitexact_with_and_without_pdl(cuda, tmp_path):
+    """programmatic dependent launch only changes WHEN the kernels of a decode step become resident, never what they read:
+    12 native decode steps give bit-identical logits with MB200_PDL=1 (default) and MB200_PDL=0.
+    Written after the round's GPU budget was spent, so it is opt-in (MB200_RUN_PDL_PROBE=1) until it has run once on a B200."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("MB200_RUN_PDL_PROBE") != "1":
+        pytest.skip("opt-in: set MB200_RUN_PDL_PROBE=1")
+    probe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "pdl_probe.py")
+    outs = []
+    for flag in ("1", "0"):
+        path = str(tmp_path / f"logits_pdl{flag}.pt")
+        env = dict(os.environ, MB200_PDL=flag)
+        r = subprocess.run([sys.executable, probe, path], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(torch.load(path))
+    assert outs[0].shape == (12, 2, 2000) and torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1])
