@@ -3,7 +3,8 @@
 Same behaviour as mantis/models/mllava/processing_llava.py:44-285: balances `<image>` placeholders against the number of
 images (prepend missing / drop surplus), rewrites each placeholder to "(image {j}: <Image><image></Image>)", tokenizes,
 drops images whose placeholders were truncated away, runs the image processor, returns input_ids / attention_mask /
-pixel_values.  `_right_pad_inputs_with_attention_mask` keeps the reference's batch==1 contract (pixel_values stays a list).
+pixel_values.  `_right_pad_inputs_with_attention_mask` returns the reference's result for one sample (pixel_values stays a
+list) and, unlike the reference (which asserts), right-pads real batches.
 """
 from typing import Dict, List
 
@@ -108,11 +109,12 @@ class MLlavaProcessor:
         return list(dict.fromkeys(list(self.tokenizer.model_input_names) + list(self.image_processor.model_input_names)))
 
     def _right_pad_inputs_with_attention_mask(self, model_inputs: List[Dict]):
-        assert len(model_inputs) == 1, f"This method only supports a single input, but get {len(model_inputs)} inputs"
-        results = {}
-        for k in model_inputs[0].keys():
-            if k == "pixel_values":
-                results[k] = [inp[k] if inp[k] is not None else None for inp in model_inputs]
-            else:
-                results[k] = torch.cat([inp[k] for inp in model_inputs], dim=0)
-        return results
+        """Batch a list of per-sample processor outputs.  The reference only supports one sample here (it asserts, :279); real
+        batches are right-padded like its training collator does (mantis/train/data.py:1392-1527): input_ids with the pad id,
+        attention_mask with 0, labels with -100, `pixel_values` stays a list of per-sample tensors (the model concatenates
+        it, modeling_llava.py:431-432)."""
+        if len(model_inputs) > 1:
+            from ...train.data import Collator
+            return Collator(processor=None, pad_token_id=getattr(self.tokenizer, "pad_token_id", None))(model_inputs)
+        sample = model_inputs[0]
+        return {k: ([v] if k == "pixel_values" else v) for k, v in sample.items()}

@@ -95,3 +95,25 @@ def test_collator_single_and_batched():
     short = 0 if one["input_ids"].shape[1] < L else 1
     assert out["attention_mask"][short, -1] == 0 and out["labels"][short, -1] == -100 and out["input_ids"][short, -1] == 0
     assert len(out["pixel_values"]) == 2
+
+
+def test_processor_batches_more_than_one_sample():
+    """the reference asserts batch == 1 in _right_pad_inputs_with_attention_mask (processing_llava.py:279); ours
+    right-pads real batches the way the reference's training collator does"""
+    import torch
+    from mantis_b200.models.mllava import MLlavaProcessor
+
+    class Tok:
+        pad_token_id = 7
+    proc = MLlavaProcessor(image_processor=None, tokenizer=Tok())
+    a = {"input_ids": torch.tensor([[1, 2, 3, 4, 5]]), "attention_mask": torch.ones(1, 5, dtype=torch.long),
+         "labels": torch.tensor([[1, 2, 3, 4, 5]]), "pixel_values": torch.zeros(2, 3, 4, 4)}
+    b = {"input_ids": torch.tensor([[9, 8]]), "attention_mask": torch.ones(1, 2, dtype=torch.long),
+         "labels": torch.tensor([[9, 8]]), "pixel_values": None}
+    one = proc._right_pad_inputs_with_attention_mask([a])
+    assert torch.equal(one["input_ids"], a["input_ids"]) and isinstance(one["pixel_values"], list) and len(one["pixel_values"]) == 1
+    two = proc._right_pad_inputs_with_attention_mask([a, b])
+    assert two["input_ids"].tolist() == [[1, 2, 3, 4, 5], [9, 8, 7, 7, 7]]
+    assert two["attention_mask"].tolist() == [[1, 1, 1, 1, 1], [1, 1, 0, 0, 0]]
+    assert two["labels"].tolist() == [[1, 2, 3, 4, 5], [9, 8, -100, -100, -100]]
+    assert isinstance(two["pixel_values"], list) and two["pixel_values"][1] is None
