@@ -12,7 +12,6 @@ the Idefics2 modules of this package:
 State-dict keys are identical to the reference's (`model.vision_model.*`, `model.connector.modality_projection.proj.weight`,
 `model.text_model.*`, `lm_head.weight`).
 """
-import torch
 from torch import nn
 
 try:                                                     # transformers >= 4.46 ships the config; the reference vendors a copy
