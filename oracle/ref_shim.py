@@ -138,6 +138,33 @@ def ref_llava_next_classes():
     return modm.LlavaNextConfig, RefLlavaNext
 
 
+def load_reference_processor():
+    """mantis/models/mllava/processing_llava.py loaded by path.  It imports two hub helpers that transformers 5 removed
+    (`is_remote_url`, `download_url`; only used by its from_pretrained override), so inert stand-ins are installed first."""
+    if "processor" in _CACHE:
+        return _CACHE["processor"]
+    root = find_ref_root()
+    if root is None:
+        raise RuntimeError("reference tree not found (only available in the build container)")
+    import transformers
+    import transformers.processing_utils as pu
+    import transformers.utils.hub as hub
+    for name in ("is_remote_url", "download_url", "is_offline_mode", "cached_file"):
+        if not hasattr(hub, name):
+            setattr(hub, name, lambda *a, **k: None)
+    if not hasattr(pu, "transformers_module"):
+        pu.transformers_module = transformers
+    for p in ("_mantis_ref", "_mantis_ref.models", "_mantis_ref.models.mllava_proc"):
+        if p not in sys.modules:
+            m = types.ModuleType(p)
+            m.__path__ = []
+            sys.modules[p] = m
+    mod = _load("_mantis_ref.models.mllava_proc.processing_llava",
+                os.path.join(root, "mantis", "models", "mllava", "processing_llava.py"))
+    _CACHE["processor"] = mod
+    return mod
+
+
 def ref_llava_classes():
     cfg, modm = load_reference_mllava()
 

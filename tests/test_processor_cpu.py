@@ -117,3 +117,50 @@ def test_processor_batches_more_than_one_sample():
     assert two["attention_mask"].tolist() == [[1, 1, 1, 1, 1], [1, 1, 0, 0, 0]]
     assert two["labels"].tolist() == [[1, 2, 3, 4, 5], [9, 8, -100, -100, -100]]
     assert isinstance(two["pixel_values"], list) and two["pixel_values"][1] is None
+
+
+def test_processor_matches_the_live_reference():
+    """Where the reference tree is present: MLlavaProcessor (placeholder balancing, "(image j: <Image><image></Image>)" tags,
+    tokenisation, dropping images whose placeholders were truncated away) against the UNMODIFIED reference processor
+    (mantis/models/mllava/processing_llava.py:66-252) on random interleaved prompts, with the same stub tokenizer / image
+    processor on both sides."""
+    import random
+    import pytest
+    from PIL import Image
+    from oracle.ref_shim import find_ref_root
+    if find_ref_root() is None:
+        pytest.skip("reference tree not available here")
+    from oracle.ref_shim import load_reference_processor
+    RefProc = load_reference_processor().MLlavaProcessor
+
+    class IP(_IP):
+        def __call__(self, images, return_tensors=None):
+            if not images:
+                return {"pixel_values": torch.zeros(0, 3, 2, 2)}
+            return {"pixel_values": torch.stack([torch.full((3, 2, 2), float(im.size[0])) for im in images])}
+
+    def make(cls):
+        p = object.__new__(cls)                      # ProcessorMixin.__init__ type-checks real tokenizers; not needed here
+        p.image_processor, p.tokenizer, p.image_token_index = IP(), _Tok(), None
+        return p
+    ref, ours = make(RefProc), MLlavaProcessor(IP(), _Tok())
+    rnd = random.Random(5)
+    words = ["USER:", "Human:", "HUMAN:", "look", "at", "<image>", "and", "<image>", "tell", "me", "ASSISTANT:"]
+    n = 0
+    for _ in range(200):
+        n_img = rnd.randint(1, 4)
+        imgs = [Image.new("RGB", (3 + i, 5)) for i in range(n_img)]          # width identifies the image downstream
+        text = " ".join(rnd.choice(words) for _ in range(rnd.randint(1, 12)))
+        kw = dict(truncation=True, max_length=rnd.randint(3, 40)) if rnd.random() < 0.5 else {}
+        for batched in (False, True):
+            t_in = [text, text + " again <image>"] if batched else text
+            i_in = [list(imgs), list(imgs)] if batched else list(imgs)
+            a_t, a_i = ref.preprocess_interleaved_images_and_text(t_in if not batched else list(t_in), [list(x) for x in i_in] if batched else list(i_in))
+            b_t, b_i = ours.preprocess_interleaved_images_and_text(t_in if not batched else list(t_in), [list(x) for x in i_in] if batched else list(i_in))
+            assert a_t == b_t and [[im.size for im in g] for g in a_i] == [[im.size for im in g] for g in b_i]
+            a = ref(text=t_in if not batched else list(t_in), images=[list(x) for x in i_in] if batched else list(i_in), **kw)
+            b = ours(text=t_in if not batched else list(t_in), images=[list(x) for x in i_in] if batched else list(i_in), **kw)
+            assert torch.equal(a["input_ids"], b["input_ids"]) and torch.equal(a["attention_mask"], b["attention_mask"])
+            assert torch.equal(a["pixel_values"], b["pixel_values"])
+            n += 1
+    assert n == 400
