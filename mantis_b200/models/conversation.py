@@ -1,8 +1,8 @@
 """Conversation templates of the hot-path families (prompt layout the models see).
 
 Mirrors the pieces of mantis/models/conversation.py the mllava / idefics2 path uses: the `Conversation` container,
-`SeparatorStyle.{SINGLE,TWO,LLAMA_3,IDEFICS_2}` rendering (ref :43-145) and the templates `mllava_v1`,
-`mllava_v1_mmtag`, `llama_3`, `idefics_2` (ref :452-491).  Other families' templates are out of scope.
+`SeparatorStyle.{SINGLE,TWO,LLAMA_3,IDEFICS_2,IDEFICS_3}` rendering (ref :43-158) and the templates `mllava_v1`,
+`mllava_v1_mmtag`, `llama_3`, `idefics_2`, `idefics_3` (ref :452-500).  Other families' templates are out of scope.
 """
 import dataclasses
 from enum import Enum, auto
@@ -14,6 +14,7 @@ class SeparatorStyle(Enum):
     TWO = auto()
     LLAMA_3 = auto()
     IDEFICS_2 = auto()
+    IDEFICS_3 = auto()
 
 
 @dataclasses.dataclass
@@ -48,6 +49,10 @@ class Conversation:
             ret = (self.system + self.sep) if self.system else ""
             for role, message in msgs:
                 ret += (role + ":" + message + self.sep + "\n") if message else (role + ":")
+        elif self.sep_style == SeparatorStyle.IDEFICS_3:          # IDEFICS_2 layout behind the LLaMA-3 BOS token (ref :146-158)
+            ret = "<|begin_of_text|>" + ((self.system + self.sep) if self.system else "")
+            for role, message in msgs:
+                ret += (role + ":" + message + self.sep + "\n") if message else (role + ":")
         else:
             raise ValueError(f"Invalid style: {self.sep_style}")
         return ret
@@ -79,6 +84,9 @@ conv_llama_3 = Conversation(
 conv_idefics_2 = Conversation(system="", roles=("User", "Assistant"), messages=(), offset=0,
                               sep_style=SeparatorStyle.IDEFICS_2, sep="<end_of_utterance>")
 
+conv_idefics_3 = Conversation(system="", roles=("User", "Assistant"), messages=(), offset=0,
+                              sep_style=SeparatorStyle.IDEFICS_3, sep="<end_of_utterance>")
+
 default_conversation = conv_mllava_v1
 conv_templates = {"mllava_v1": conv_mllava_v1, "mllava_v1_mmtag": conv_mllava_v1_mmtag, "llama_3": conv_llama_3,
-                  "idefics_2": conv_idefics_2}
+                  "idefics_2": conv_idefics_2, "idefics_3": conv_idefics_3}

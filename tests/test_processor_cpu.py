@@ -164,3 +164,31 @@ def test_processor_matches_the_live_reference():
             assert torch.equal(a["pixel_values"], b["pixel_values"])
             n += 1
     assert n == 400
+
+
+def test_conversation_templates_match_the_live_reference():
+    """every template this package ships renders exactly like mantis/models/conversation.py for random dialogues
+    (incl. the empty trailing assistant turn that opens a generation and a non-empty system prompt)"""
+    import os
+    import random
+    import pytest
+    from oracle import ref_shim
+    root = ref_shim.find_ref_root()
+    if root is None:
+        pytest.skip("reference tree not available here")
+    ref = ref_shim._load("_mantis_ref_conversation", os.path.join(root, "mantis", "models", "conversation.py"))
+    rnd = random.Random(3)
+    vocab = ["hi", "<image>", "what is this?", "a cat", "", "compare (image 1: <Image><image></Image>) please", "ok\nfine"]
+    for name, tmpl in conv_templates.items():
+        assert name in ref.conv_templates
+        for trial in range(50):
+            a, b = tmpl.copy(), ref.conv_templates[name].copy()
+            a.messages, b.messages = [], []
+            if trial % 5 == 0:
+                a.system = b.system = "SYSTEM PROMPT"
+            for turn in range(rnd.randint(1, 6)):
+                msg = rnd.choice(vocab)
+                a.append_message(a.roles[turn % 2], msg); b.append_message(b.roles[turn % 2], msg)
+            if rnd.random() < 0.5:
+                a.append_message(a.roles[1], None); b.append_message(b.roles[1], None)
+            assert a.get_prompt() == b.get_prompt(), (name, a.messages)
