@@ -154,14 +154,23 @@ def load_reference_processor():
             setattr(hub, name, lambda *a, **k: None)
     if not hasattr(pu, "transformers_module"):
         pu.transformers_module = transformers
-    for p in ("_mantis_ref", "_mantis_ref.models", "_mantis_ref.models.mllava_proc"):
-        if p not in sys.modules:
-            m = types.ModuleType(p)
-            m.__path__ = []
-            sys.modules[p] = m
-    mod = _load("_mantis_ref.models.mllava_proc.processing_llava",
+    load_reference_mllava()                                    # creates the synthetic parent packages
+    mod = _load("_mantis_ref.models.mllava.processing_llava",
                 os.path.join(root, "mantis", "models", "mllava", "processing_llava.py"))
     _CACHE["processor"] = mod
+    return mod
+
+
+def load_reference_chat_utils():
+    """mantis/models/mllava/utils.py (chat_mllava) with its relative imports satisfied by the modules loaded above."""
+    if "chat_utils" in _CACHE:
+        return _CACHE["chat_utils"]
+    root = find_ref_root()
+    load_reference_processor()
+    if "_mantis_ref.models.conversation" not in sys.modules:
+        _load("_mantis_ref.models.conversation", os.path.join(root, "mantis", "models", "conversation.py"))
+    mod = _load("_mantis_ref.models.mllava.utils", os.path.join(root, "mantis", "models", "mllava", "utils.py"))
+    _CACHE["chat_utils"] = mod
     return mod
 
 

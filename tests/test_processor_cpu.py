@@ -192,3 +192,68 @@ def test_conversation_templates_match_the_live_reference():
             if rnd.random() < 0.5:
                 a.append_message(a.roles[1], None); b.append_message(b.roles[1], None)
             assert a.get_prompt() == b.get_prompt(), (name, a.messages)
+
+
+def test_chat_mllava_matches_the_live_reference():
+    """chat_mllava (template choice by language-model name, history bookkeeping, prompt, terminators, decoding of the new
+    tokens only) vs mantis/models/mllava/utils.py:10-97 with recording stubs for the model and the processor"""
+    import copy
+    import random
+    import pytest
+    from oracle.ref_shim import find_ref_root
+    if find_ref_root() is None:
+        pytest.skip("reference tree not available here")
+    from oracle.ref_shim import load_reference_chat_utils
+    from mantis_b200.models.mllava import chat_mllava
+    ref_chat = load_reference_chat_utils().chat_mllava
+
+    class Tok:
+        eos_token_id = 2
+
+        def convert_tokens_to_ids(self, t):
+            return 128009
+
+    class Proc:
+        def __init__(self):
+            self.tokenizer, self.calls = Tok(), []
+
+        def __call__(self, images=None, text=None, **kw):
+            self.calls.append((text, None if images is None else len(images), kw))
+            return {"input_ids": torch.arange(len(text.split()))[None], "pixel_values": None if not images else [torch.zeros(1)]}
+
+        def decode(self, ids, skip_special_tokens=True):
+            return "reply:" + ",".join(str(int(i)) for i in ids)
+
+    class LM:
+        def __init__(self, name):
+            self.name_or_path = name
+
+    class Model:
+        device = torch.device("cpu")
+
+        def __init__(self, name):
+            self.language_model, self.calls = LM(name), []
+
+        def generate(self, **kw):
+            self.calls.append({k: (v if not torch.is_tensor(v) else v.clone()) for k, v in kw.items()})
+            return torch.cat([kw["input_ids"], torch.tensor([[41, 42, 43]])], dim=1)
+
+    rnd = random.Random(8)
+    for trial in range(60):
+        name = rnd.choice(["meta-llama/Meta-Llama-3-8B-Instruct", "lmsys/vicuna-7b", ""])
+        roles = ("user", "assistant") if "llama-3" in name.lower() else ("USER", "ASSISTANT")
+        history = None
+        if rnd.random() < 0.6:
+            history = []
+            for t in range(rnd.randint(1, 3)):
+                history += [{"role": roles[0], "text": f"q{t} <image>"}, {"role": roles[1], "text": f"a{t}"}]
+        text = rnd.choice(["what about <image> and <image>?", "again", "compare them"])
+        images = [object()] * rnd.randint(0, 3)
+        outs = []
+        for fn in (ref_chat, chat_mllava):
+            m, p = Model(name), Proc()
+            h = copy.deepcopy(history)
+            reply, h2 = fn(text, list(images), m, p, max_input_length=77, history=h, max_new_tokens=5, do_sample=False)
+            gen = m.calls[0]
+            outs.append((reply, h2, p.calls, gen["eos_token_id"], gen["max_new_tokens"], gen["do_sample"], gen["input_ids"].tolist()))
+        assert outs[0] == outs[1], (name, history, text)
