@@ -174,6 +174,36 @@ def load_reference_chat_utils():
     return mod
 
 
+def load_reference_train_data():
+    """mantis/train/data.py (Collator, PackingDataset, ...) loaded by path.  Its video dependencies (av, decord) are absent
+    from the image and unused by the classes the tests need -> empty stand-in modules; its `mantis.train.*` /
+    `mantis.models.conversation` imports are satisfied with the reference's own files (the repo-root `mantis` package is the
+    alias shim of the product and does not define them)."""
+    if "train_data" in _CACHE:
+        return _CACHE["train_data"]
+    root = find_ref_root()
+    if root is None:
+        raise RuntimeError("reference tree not found (only available in the build container)")
+    for name in ("av", "decord"):
+        try:
+            __import__(name)
+        except ImportError:
+            sys.modules[name] = types.ModuleType(name)
+    import mantis  # noqa: F401  (the alias shim; submodules below are added next to it)
+    if "mantis.train" not in sys.modules:
+        m = types.ModuleType("mantis.train")
+        m.__path__ = []
+        sys.modules["mantis.train"] = m
+    if "mantis.models.conversation" not in sys.modules:
+        _load("mantis.models.conversation", os.path.join(root, "mantis", "models", "conversation.py"))
+    for sub in ("train_utils", "conversation"):
+        if f"mantis.train.{sub}" not in sys.modules:
+            _load(f"mantis.train.{sub}", os.path.join(root, "mantis", "train", f"{sub}.py"))
+    mod = _load("_mantis_ref_train_data", os.path.join(root, "mantis", "train", "data.py"))
+    _CACHE["train_data"] = mod
+    return mod
+
+
 def ref_llava_classes():
     cfg, modm = load_reference_mllava()
 

@@ -78,3 +78,54 @@ def test_partition_balanced_by_merged_length():
     import pytest
     with pytest.raises(ValueError):
         partition_balanced(lens, 4, 4)
+
+
+def _ref_data():
+    import pytest
+    from oracle.ref_shim import find_ref_root
+    if find_ref_root() is None:
+        pytest.skip("reference tree not available here")
+    from oracle.ref_shim import load_reference_train_data
+    return load_reference_train_data()
+
+
+def test_pack_batch_matches_the_live_reference():
+    """PackingDataset.pack_batch vs the unmodified mantis/train/data.py:1607-1671 (its __init__ cannot run -- it reads
+    `self.packing_same_mm_media` before assigning it -- so the method is called on a bare instance).  The reference emits 1-D
+    position_ids / labels (it concatenates per-item 1-D tensors); ours keeps a leading batch dim of 1, compared flattened."""
+    ref = _ref_data()
+    ds = _DS()
+    items = [ds[i] for i in (0, 2, 3, 5)]
+    r = object.__new__(ref.PackingDataset).pack_batch([dict(it, labels=it["labels"][0]) for it in items])
+    o = PackingDataset(ds, max_self_attn_len=10).pack_batch(items)
+    assert torch.equal(o["input_ids"], r["input_ids"])
+    assert torch.equal(o["attention_mask"], r["attention_mask"]) and o["attention_mask"].dtype == r["attention_mask"].dtype
+    assert torch.equal(o["position_ids"].reshape(-1), r["position_ids"]) and torch.equal(o["labels"].reshape(-1), r["labels"])
+    assert torch.equal(o["pixel_values"], r["pixel_values"])
+
+
+def test_collator_matches_the_live_reference():
+    """right padding of real batches (ids with the pad id, masks with 0 -- 2-D and packed 4-D --, labels with -100, position ids
+    with 0) vs the reference Collator's own `_right_pad_inputs_with_attention_mask` (data.py:1392-1527)"""
+    ref = _ref_data()
+
+    class Tok:
+        pad_token_id = 7
+
+    class Proc:                                    # no `_right_pad_inputs_with_attention_mask` -> the Collator's own is used
+        tokenizer = Tok()
+    rc = ref.Collator(Proc())
+    rc.tokenizer = Tok()                           # the reference's method reads self.tokenizer, which its __init__ never sets
+    oc = Collator(pad_token_id=7)
+    ds = _DS()
+    plain = [{k: v for k, v in ds[i].items() if k != "pixel_values"} for i in (0, 1, 6)]
+    for it in plain:
+        it["position_ids"] = torch.arange(it["input_ids"].shape[1])[None]
+    r, o = rc([dict(x) for x in plain]), oc([dict(x) for x in plain])
+    for k in ("input_ids", "attention_mask", "labels", "position_ids"):
+        assert torch.equal(o[k], r[k]), k
+    pd = PackingDataset(ds, max_self_attn_len=10)
+    packed = [{k: v for k, v in pd[i].items() if k not in ("pixel_values", "cu_segments")} for i in (0, 1)]
+    r, o = rc([dict(x) for x in packed]), oc([dict(x) for x in packed])
+    for k in ("input_ids", "attention_mask", "labels", "position_ids"):
+        assert torch.equal(o[k], r[k]), k
