@@ -197,3 +197,83 @@ def partition_balanced(lengths, world_size: int, samples_per_rank=None):
         parts[r].append(i)
         load[r] += cost[i]
     return parts
+
+
+def assistant_labels(input_ids: torch.Tensor, sep_id: int, style: str, has_system: bool = True, sep_offset: int = 0,
+                     ignore_index: int = -100) -> torch.Tensor:
+    """Labels of one tokenised conversation: the assistant turns keep their token ids, everything else (system prompt, user
+    turns, image placeholders' surroundings) is `ignore_index` -- the supervision mask of instruction tuning, derived from
+    the positions of the turn separator exactly like the reference's ChatDataset (mantis/train/data.py:421-452).
+
+    style "single" / "llama_3" (mllava_v1, llama_3 templates): the text after every ODD separator (0-based: 0 closes the
+        system prompt, 1 the first user turn, ...) up to and including the next separator is supervised; after the last
+        separator, if it is odd, everything to the end.
+    style "idefics" (idefics_2 / idefics_3 templates, separator = the stripped `conv.sep`): same walk, but the parity flips
+        when there is no system prompt (then separator 0 already closes a user turn) and the supervised span starts
+        `1 + sep_offset` tokens after the separator (skipping the "\nAssistant:" role tokens is left to sep_offset)."""
+    ids = input_ids.reshape(-1)
+    labels = torch.full_like(ids, ignore_index)
+    seps = torch.nonzero(ids == sep_id, as_tuple=True)[0].tolist()
+    if style in ("single", "llama_3"):
+        skip_parity, start = 0, 1
+    elif style == "idefics":
+        skip_parity, start = (0 if has_system else 1), 1 + sep_offset
+    else:
+        raise ValueError(f"unknown separator style {style!r}")
+    for i, pos in enumerate(seps):
+        if i % 2 == skip_parity:
+            continue
+        end = ids.numel() if i == len(seps) - 1 else seps[i + 1] + 1
+        labels[pos + start:end] = ids[pos + start:end]
+    return labels.view_as(input_ids)
+
+
+class ChatDataset(torch.utils.data.Dataset):
+    """Conversation-style fine-tuning items for the hot path (the part of mantis/train/data.py:94-505 `ChatDataset` that
+    produces model inputs; dataset download / caching / video are out of scope): every record is
+    {"conversation": [{"role"|"from": "human"/"user"/"gpt"/"assistant", "content"|"text"|"value": str}, ...], "images": [PIL...]}.
+    Missing `<image>` placeholders are prepended to the first turn (ref:403-406), the prompt is rendered with a
+    `mantis_b200.models.conversation` template, tokenised + image-processed by the processor (truncation to `max_seq_len`),
+    and `labels` supervise the assistant turns only (`assistant_labels`)."""
+
+    _STYLE = {"SINGLE": "single", "LLAMA_3": "llama_3", "IDEFICS_2": "idefics", "IDEFICS_3": "idefics"}
+
+    def __init__(self, records, processor, conv, max_seq_len=None, image_key="images", ignore_index=-100):
+        self.records, self.processor, self.conv = records, processor, conv
+        self.max_seq_len, self.image_key, self.ignore_index = max_seq_len, image_key, ignore_index
+
+    def __len__(self):
+        return len(self.records)
+
+    def messages(self, record):
+        conv = self.conv
+        roles = {"human": conv.roles[0], "user": conv.roles[0], "gpt": conv.roles[1], "assistant": conv.roles[1]}
+        turns = record["conversation" if "conversation" in record else "conversations"]
+        if roles[turns[0].get("from", turns[0].get("role"))] != conv.roles[0]:
+            turns = turns[1:]                                                     # a leading non-user turn is dropped (ref:355-357)
+        out = []
+        for j, t in enumerate(turns):
+            role = roles[t.get("from", t.get("role"))]
+            if role != conv.roles[j % 2]:
+                raise ValueError("conversation turns must alternate user / assistant")
+            out.append([role, t.get("content", t.get("text", t.get("value", "")))])
+        return out
+
+    def __getitem__(self, idx):
+        record = self.records[idx]
+        msgs = self.messages(record)
+        images = record.get(self.image_key)
+        if images is not None and not isinstance(images, list):
+            images = [images]
+        n_tok = sum(m[1].count("<image>") for m in msgs)
+        if isinstance(images, list) and n_tok < len(images):
+            msgs[0][1] = "<image>" * (len(images) - n_tok) + msgs[0][1]
+        conv = self.conv.copy()
+        conv.messages = msgs
+        enc = self.processor(conv.get_prompt(), images, return_tensors="pt", truncation=True, max_length=self.max_seq_len)
+        style = self._STYLE[conv.sep_style.name]
+        sep_tok = conv.sep.strip(" \n") if style == "idefics" else conv.sep
+        sep_id = self.processor.tokenizer.convert_tokens_to_ids(sep_tok)
+        enc["labels"] = assistant_labels(enc["input_ids"], sep_id, style, has_system=bool(conv.system),
+                                         sep_offset=getattr(conv, "sep_offset", 0), ignore_index=self.ignore_index)
+        return enc
