@@ -108,8 +108,27 @@ int mb200_ce_fwd_bwd(const void* logits, const int64_t* labels, float* loss_rows
                      void* stream);
 int mb200_ce_reduce(const float* loss_rows, const int64_t* labels, long long n, int V, float* out2, int accumulate,
                     void* stream);
-int mb200_adamw(void* p, const void* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
-                float wd, int step, float grad_scale, int dtype, void* stream);
+/* Fused AdamW over FLAT parameter / gradient / moment buffers (one launch per optimizer step) with fp32 master weights.
+ * Replaces torch.optim.AdamW on DeepSpeed's fp32 master copy (mantis/train/zero_configs/zero3.json "bf16": enabled,
+ * mantis/train/scripts/train_mllava.sh:148,162-165 `--bf16 True --learning_rate 1e-5 --weight_decay 0.`).
+ *   p_dtype BF16: p = bf16 weights (what the model computes with), lo = their 16 low fp32 bits (uint16): the pair IS the
+ *                 fp32 master, master_bits = (bf16_bits << 16) + (int16) lo; lo must not be NULL.
+ *   p_dtype F32 : p = fp32 weights, lo ignored.
+ *   g (g_dtype F32 or BF16): accumulated gradients, multiplied by grad_scale (1 / world size) and by the global-norm clip
+ *                 factor min(1, max_norm / (sqrt(*norm_sq) * grad_scale + 1e-6)) computed ON THE DEVICE (norm_sq NULL or
+ *                 max_norm <= 0: no clipping); zero_grad != 0 clears g on the way out.
+ *   blk_group[n / 1024] (nullable): 1 = this 1024-element block takes no weight decay (biases, norm weights).
+ * n must be a multiple of 8 and all buffers 16-byte aligned (every tensor's slice starts on a 1024-element boundary). */
+int mb200_adamw_flat(void* p, void* lo, void* g, float* m, float* v, const unsigned char* blk_group, long long n, float lr,
+                     float beta1, float beta2, float eps, float wd, int step, float grad_scale, const float* norm_sq,
+                     float max_norm, int zero_grad, int p_dtype, int g_dtype, void* stream);
+/* fp32 master <-> (bf16 weight, uint16 low half) over a flat range (trainer construction, optimizer checkpoints). lo may be
+ * NULL in join (treated as zero). */
+int mb200_master_split(const float* master, void* hi_bf16, void* lo_u16, long long n, void* stream);
+int mb200_master_join(const void* hi_bf16, const void* lo_u16, float* master, long long n, void* stream);
+/* dst (fp32) += scale * src (src_dtype): folds a gradient autograd produced in the parameter dtype into the fp32 main
+ * gradient buffer (what DeepSpeed's fp32 gradient accumulation does). */
+int mb200_accum_f32(float* dst, const void* src, long long n, float scale, int src_dtype, void* stream);
 int mb200_sumsq(const void* g, long long n, float* out, int dtype, void* stream);
 
 /* ---- GEMM: nn.Linear forward / dgrad / wgrad (llama/modeling_llama.py:171-184,238-249,487; siglip :270-273,
@@ -123,6 +142,10 @@ int mb200_gemm_bf16(const void* A, const void* B, void* C, const void* bias, con
                     long long lda, long long ldb, long long ldc, long long ld_add, int transA, int transB, int act,
                     void* stream);
 
+/* C32[M,N] (fp32) = (accumulate ? C32 : 0) + op(A) op(B): bf16 operands, fp32 accumulation kept in fp32 all the way to
+ * memory -- the weight-gradient product dW += dy^T x into the fp32 main-gradient buffer (same operand rules as above). */
+int mb200_gemm_bf16_acc32(const void* A, const void* B, float* C32, int M, int N, int K, long long lda, long long ldb,
+                          long long ldc, int transA, int transB, int accumulate, void* stream);
 /* CTA-pair (cta_group::2, 256x256 tile per SM pair) variant of mb200_gemm_bf16; identical contract. */
 int mb200_gemm_bf16_2cta(const void* A, const void* B, void* C, const void* bias, const void* addend, int M, int N, int K,
                          long long lda, long long ldb, long long ldc, long long ld_add, int transA, int transB, int act,

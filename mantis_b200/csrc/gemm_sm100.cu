@@ -20,27 +20,16 @@
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 #include "tmap.cuh"
+#include "gemm_epi.cuh"
 
 namespace {
 using namespace sm100;
+using gemm_epi::GemmEpi;
 
 constexpr int BM = 128, BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
 constexpr int GROUP_M = 16;                  // rasterisation: 16 m-blocks share each sweep over n for L2 reuse
 
-struct GemmEpi {
-  bf16* C; long long ldc;
-  const bf16* bias;
-  const bf16* addend; long long ld_add;
-  int act;            // 0 none, 1 gelu(erf), 2 gelu(tanh), 3 quick_gelu
-};
-
-__device__ __forceinline__ float epi_act(float x, int kind) {
-  if (kind == 1) return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
-  if (kind == 2) { const float k = 0.79788456080286535588f; return 0.5f * x * (1.f + tanhf(k * (x + 0.044715f * x * x * x))); }
-  if (kind == 3) return x / (1.f + __expf(-1.702f * x));
-  return x;
-}
 
 __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& mb_, int& nb_) {
   const int per_group = GROUP_M * num_n;
@@ -150,10 +139,6 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       const bool row_ok = row < M;
-      bf16* crow = epi.C + (size_t)(row_ok ? row : 0) * epi.ldc;
-      const bf16* arow = epi.addend ? epi.addend + (size_t)(row_ok ? row : 0) * epi.ld_add : nullptr;
-      const bool vec_ok = ((epi.ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(epi.C) & 15) == 0) &&
-                          (!epi.addend || (((epi.ld_add & 7) == 0) && ((reinterpret_cast<uintptr_t>(epi.addend) & 15) == 0)));
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
@@ -164,40 +149,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (epi.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (col0 + j < N) v[j] += __bfloat162float(__ldg(epi.bias + col0 + j));
-          }
-          if (epi.act) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = epi_act(v[j], epi.act);
-          }
-          if (vec_ok && col0 + 32 <= N) {
-            if (arow) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                int4 a4 = *reinterpret_cast<const int4*>(arow + col0 + g * 8);
-                const bf162* ah = reinterpret_cast<const bf162*>(&a4);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(ah[j]); v[g * 8 + 2 * j] += f.x; v[g * 8 + 2 * j + 1] += f.y; }
-              }
-            }
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              int4 o4; bf162* oh = reinterpret_cast<bf162*>(&o4);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
-              *reinterpret_cast<int4*>(crow + col0 + g * 8) = o4;
-            }
-          } else {
-            for (int j = 0; j < 32; ++j) {
-              if (col0 + j < N) {
-                float x = v[j];
-                if (arow) x += __bfloat162float(arow[col0 + j]);
-                crow[col0 + j] = __float2bfloat16_rn(x);
-              }
-            }
-          }
+          gemm_epi::store32(epi, row, col0, N, v);
         }
       }
       tc_fence_before();
@@ -217,13 +169,9 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
                        cudaStream_t st) {
   constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256;
   auto kern = gemm_sm100_kernel<BN, STAGES, A_MN, B_MN>;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
-      mb200_set_last_error("cudaFuncSetAttribute(max dynamic smem) failed"); return -EIO;
-    }
-    configured = true;
-  }
+  static const cudaError_t cfg = cudaFuncSetAttribute(gemm_sm100_kernel<BN, STAGES, A_MN, B_MN>,
+                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // once, thread-safe
+  if (cfg != cudaSuccess) { mb200_set_last_error("cudaFuncSetAttribute(max dynamic smem) failed"); return -EIO; }
   const int num_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = num_tiles < mb::num_sms() ? num_tiles : mb::num_sms();
   kern<<<grid, 192, smem, st>>>(tmA, tmB, epi, M, N, K);
@@ -241,13 +189,13 @@ static int dispatch_major(int transA, int transB, const CUtensorMap& tmA, const 
 }
 }  // namespace
 
-extern "C" {
+int mb200_gemm_2cta_impl(const void* A, const void* B, void* C, const void* bias, const void* addend, int M, int N, int K,
+                         long long lda, long long ldb, long long ldc, long long ld_add, int transA, int transB, int act,
+                         int c_f32, void* stream);
 
-// Returns 0 on success, -ENOTSUP when the operands do not meet the TMA alignment rules (caller then uses
-// mb200_gemm_generic), other negative errno on failure.
-int mb200_gemm_bf16(const void* A, const void* B, void* C, const void* bias, const void* addend, int M, int N, int K,
-                    long long lda, long long ldb, long long ldc, long long ld_add, int transA, int transB, int act,
-                    void* stream) {
+static int gemm_1cta_impl(const void* A, const void* B, void* C, const void* bias, const void* addend, int M, int N, int K,
+                          long long lda, long long ldb, long long ldc, long long ld_add, int transA, int transB, int act,
+                          int c_f32, void* stream) {
   if (M <= 0 || N <= 0) return MB200_OK;
   if (K <= 0) return -EINVAL;
   if ((lda & 7) || (ldb & 7) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
@@ -262,14 +210,34 @@ int mb200_gemm_bf16(const void* A, const void* B, void* C, const void* bias, con
   else         rc = mbtmap::make_2d(&tmB, B, K, N, ldb, 64, BK);        // [K,N]: box 64(N) x 64(K)
   if (rc) return rc;
   GemmEpi epi;
-  epi.C = (bf16*)C; epi.ldc = ldc; epi.bias = (const bf16*)bias; epi.addend = (const bf16*)addend;
-  epi.ld_add = ld_add; epi.act = act;
+  epi.C = C; epi.ldc = ldc; epi.bias = (const bf16*)bias; epi.addend = addend;
+  epi.ld_add = ld_add; epi.act = act; epi.c_f32 = c_f32;
   cudaStream_t st = (cudaStream_t)stream;
   if (BN == 256) rc = dispatch_major<256, 4>(transA, transB, tmA, tmB, epi, M, N, K, st);
   else           rc = dispatch_major<128, 6>(transA, transB, tmA, tmB, epi, M, N, K, st);
   if (rc) return rc;
   MB200_CHECK_LAUNCH();
   return MB200_OK;
+}
+
+extern "C" {
+
+// Returns 0 on success, -ENOTSUP when the operands do not meet the TMA alignment rules (caller then uses
+// mb200_gemm_generic), other negative errno on failure.
+int mb200_gemm_bf16(const void* A, const void* B, void* C, const void* bias, const void* addend, int M, int N, int K,
+                    long long lda, long long ldb, long long ldc, long long ld_add, int transA, int transB, int act,
+                    void* stream) {
+  return gemm_1cta_impl(A, B, C, bias, addend, M, N, K, lda, ldb, ldc, ld_add, transA, transB, act, 0, stream);
+}
+
+// C32[M,N] (fp32, leading dimension ldc floats) = (accumulate ? C32 : 0) + op(A) op(B), bf16 operands, fp32 accumulation
+// in TMEM and fp32 all the way into memory: the weight-gradient product dW += dy^T x of the fp32 main-gradient buffer.
+int mb200_gemm_bf16_acc32(const void* A, const void* B, float* C32, int M, int N, int K, long long lda, long long ldb,
+                          long long ldc, int transA, int transB, int accumulate, void* stream) {
+  const void* add = accumulate ? (const void*)C32 : nullptr;
+  if (M >= 512 && N >= 512)
+    return mb200_gemm_2cta_impl(A, B, C32, nullptr, add, M, N, K, lda, ldb, ldc, ldc, transA, transB, 0, 1, stream);
+  return gemm_1cta_impl(A, B, C32, nullptr, add, M, N, K, lda, ldb, ldc, ldc, transA, transB, 0, 1, stream);
 }
 
 }  // extern "C"

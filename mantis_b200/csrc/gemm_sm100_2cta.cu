@@ -6,9 +6,11 @@
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 #include "tmap.cuh"
+#include "gemm_epi.cuh"
 
 namespace {
 using namespace sm100;
+using gemm_epi::GemmEpi;
 
 constexpr int BM = 128, BK = 64, BN_HALF = 128;          // per CTA; the pair covers 256 x 256
 constexpr int A_STAGE = BM * BK * 2;                     // 16 KB
@@ -16,19 +18,6 @@ constexpr int B_STAGE = BN_HALF * BK * 2;                // 16 KB
 constexpr int STAGES = 6;
 constexpr int GROUP_M = 8;                               // in units of 256-row tile rows
 
-struct GemmEpi {
-  bf16* C; long long ldc;
-  const bf16* bias;
-  const bf16* addend; long long ld_add;
-  int act;
-};
-
-__device__ __forceinline__ float epi_act(float x, int kind) {
-  if (kind == 1) return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
-  if (kind == 2) { const float k = 0.79788456080286535588f; return 0.5f * x * (1.f + tanhf(k * (x + 0.044715f * x * x * x))); }
-  if (kind == 3) return x / (1.f + __expf(-1.702f * x));
-  return x;
-}
 __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& mb_, int& nb_) {
   const int per_group = GROUP_M * num_n;
   const int g = t / per_group, r = t % per_group;
@@ -134,10 +123,6 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       const bool row_ok = row < M;
-      bf16* crow = epi.C + (size_t)(row_ok ? row : 0) * epi.ldc;
-      const bf16* arow = epi.addend ? epi.addend + (size_t)(row_ok ? row : 0) * epi.ld_add : nullptr;
-      const bool vec_ok = ((epi.ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(epi.C) & 15) == 0) &&
-                          (!epi.addend || (((epi.ld_add & 7) == 0) && ((reinterpret_cast<uintptr_t>(epi.addend) & 15) == 0)));
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
         uint32_t r[32];
@@ -148,40 +133,7 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (epi.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (col0 + j < N) v[j] += __bfloat162float(__ldg(epi.bias + col0 + j));
-          }
-          if (epi.act) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = epi_act(v[j], epi.act);
-          }
-          if (vec_ok && col0 + 32 <= N) {
-            if (arow) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                int4 a4 = *reinterpret_cast<const int4*>(arow + col0 + g * 8);
-                const bf162* ah = reinterpret_cast<const bf162*>(&a4);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(ah[j]); v[g * 8 + 2 * j] += f.x; v[g * 8 + 2 * j + 1] += f.y; }
-              }
-            }
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              int4 o4; bf162* oh = reinterpret_cast<bf162*>(&o4);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
-              *reinterpret_cast<int4*>(crow + col0 + g * 8) = o4;
-            }
-          } else {
-            for (int j = 0; j < 32; ++j) {
-              if (col0 + j < N) {
-                float x = v[j];
-                if (arow) x += __bfloat162float(arow[col0 + j]);
-                crow[col0 + j] = __float2bfloat16_rn(x);
-              }
-            }
-          }
+          gemm_epi::store32(epi, row, col0, N, v);
         }
       }
       tc_fence_before();
@@ -199,13 +151,11 @@ template <bool A_MN, bool B_MN>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpi& epi, int M, int N, int K, cudaStream_t st) {
   constexpr int smem = STAGES * (A_STAGE + B_STAGE) + 1024 + 256;
   auto kern = gemm_sm100_2cta_kernel<A_MN, B_MN>;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
-      mb200_set_last_error("cudaFuncSetAttribute(max dynamic smem) failed"); return -EIO;
-    }
-    configured = true;
-  }
+  // function-local static with a dynamic initialiser: initialised exactly once even when several host threads race here
+  // (generate() on a worker thread, mantis/models/mllava/utils.py:100-186)
+  static const cudaError_t cfg = cudaFuncSetAttribute(gemm_sm100_2cta_kernel<A_MN, B_MN>,
+                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (cfg != cudaSuccess) { mb200_set_last_error("cudaFuncSetAttribute(max dynamic smem) failed"); return -EIO; }
   const int num_tiles = ((M + 255) / 256) * ((N + 255) / 256);
   int clusters = mb::num_sms() / 2;
   if (num_tiles < clusters) clusters = num_tiles;
@@ -214,9 +164,10 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpi&
 }
 }  // namespace
 
-extern "C" int mb200_gemm_bf16_2cta(const void* A, const void* B, void* C, const void* bias, const void* addend, int M,
-                                    int N, int K, long long lda, long long ldb, long long ldc, long long ld_add,
-                                    int transA, int transB, int act, void* stream) {
+// shared by mb200_gemm_bf16_2cta (bf16 C) and mb200_gemm_bf16_acc32 (fp32 C); not part of the public header
+int mb200_gemm_2cta_impl(const void* A, const void* B, void* C, const void* bias, const void* addend, int M, int N, int K,
+                         long long lda, long long ldb, long long ldc, long long ld_add, int transA, int transB, int act,
+                         int c_f32, void* stream) {
   if (M <= 0 || N <= 0) return MB200_OK;
   if (K <= 0) return -EINVAL;
   if ((lda & 7) || (ldb & 7) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
@@ -228,7 +179,8 @@ extern "C" int mb200_gemm_bf16_2cta(const void* A, const void* B, void* C, const
   if (transB) rc = mbtmap::make_2d(&tmB, B, N, K, ldb, BK, BN_HALF); else rc = mbtmap::make_2d(&tmB, B, K, N, ldb, 64, BK);
   if (rc) return rc;
   GemmEpi epi;
-  epi.C = (bf16*)C; epi.ldc = ldc; epi.bias = (const bf16*)bias; epi.addend = (const bf16*)addend; epi.ld_add = ld_add; epi.act = act;
+  epi.C = C; epi.ldc = ldc; epi.bias = (const bf16*)bias; epi.addend = addend; epi.ld_add = ld_add; epi.act = act;
+  epi.c_f32 = c_f32;
   cudaStream_t st = (cudaStream_t)stream;
   const bool a_mn = transA != 0, b_mn = transB == 0;
   if (!a_mn && !b_mn) rc = launch<false, false>(tmA, tmB, epi, M, N, K, st);
@@ -238,4 +190,10 @@ extern "C" int mb200_gemm_bf16_2cta(const void* A, const void* B, void* C, const
   if (rc) return rc;
   MB200_CHECK_LAUNCH();
   return MB200_OK;
+}
+
+extern "C" int mb200_gemm_bf16_2cta(const void* A, const void* B, void* C, const void* bias, const void* addend, int M,
+                                    int N, int K, long long lda, long long ldb, long long ldc, long long ld_add,
+                                    int transA, int transB, int act, void* stream) {
+  return mb200_gemm_2cta_impl(A, B, C, bias, addend, M, N, K, lda, ldb, ldc, ld_add, transA, transB, act, 0, stream);
 }

@@ -12,8 +12,8 @@ using mb::Cvt;
 // written in T (may alias logits).
 template <typename T>
 __global__ void __launch_bounds__(512)
-ce_fwd_bwd_kernel(const T* __restrict__ logits, const int64_t* __restrict__ labels, float* __restrict__ loss_rows,
-                  float* __restrict__ lse_rows, T* __restrict__ dlogits, long long n, int V, long long ld,
+ce_fwd_bwd_kernel(const T* logits, const int64_t* __restrict__ labels, float* __restrict__ loss_rows,
+                  float* __restrict__ lse_rows, T* dlogits /* may alias logits */, long long n, int V, long long ld,
                   const float* __restrict__ gscale_ptr, float gscale_const) {
   __shared__ float red[33];
   const long long r = blockIdx.x;
@@ -25,6 +25,9 @@ ce_fwd_bwd_kernel(const T* __restrict__ logits, const int64_t* __restrict__ labe
     if (dlogits) { T* dr = dlogits + (size_t)r * ld; for (int i = threadIdx.x; i < V; i += blockDim.x) dr[i] = Cvt<T>::from_f(0.f); }
     return;
   }
+  // every thread reads the target logit BEFORE the block reductions: dlogits may alias logits, and the first warps to leave the
+  // last reduction start overwriting the row while thread 0 is still composing the loss
+  const float tgt = ignored ? 0.f : Cvt<T>::to_f(lr[y]);
   float mx = -INFINITY;
   for (int i = threadIdx.x; i < V; i += blockDim.x) mx = fmaxf(mx, Cvt<T>::to_f(lr[i]));
   mx = mb::block_max(mx, red);
@@ -34,7 +37,7 @@ ce_fwd_bwd_kernel(const T* __restrict__ logits, const int64_t* __restrict__ labe
   const float lse = mx + logf(se);
   if (threadIdx.x == 0) {
     if (lse_rows) lse_rows[r] = lse;
-    if (loss_rows) loss_rows[r] = ignored ? 0.f : (lse - Cvt<T>::to_f(lr[y]));
+    if (loss_rows) loss_rows[r] = ignored ? 0.f : (lse - tgt);
   }
   if (dlogits) {
     const float gs = ignored ? 0.f : (gscale_ptr ? *gscale_ptr : gscale_const);
@@ -50,8 +53,8 @@ ce_fwd_bwd_kernel(const T* __restrict__ logits, const int64_t* __restrict__ labe
 // bf16 fast path: 16-byte vector loads, online (max, sum-exp) in ONE read pass, then one read + one write pass for dlogits
 // (algorithmic minimum for forward+backward is 1 read + 1 write; the second read mostly hits L2: a row is 256 KB).
 __global__ void __launch_bounds__(512)
-ce_fwd_bwd_vec_kernel(const bf16* __restrict__ logits, const int64_t* __restrict__ labels, float* __restrict__ loss_rows,
-                      float* __restrict__ lse_rows, bf16* __restrict__ dlogits, long long n, int V, long long ld,
+ce_fwd_bwd_vec_kernel(const bf16* logits, const int64_t* __restrict__ labels, float* __restrict__ loss_rows,
+                      float* __restrict__ lse_rows, bf16* dlogits /* may alias logits */, long long n, int V, long long ld,
                       const float* __restrict__ gscale_ptr, float gscale_const) {
   __shared__ float red[33];
   const long long r = blockIdx.x;
@@ -69,6 +72,7 @@ ce_fwd_bwd_vec_kernel(const bf16* __restrict__ logits, const int64_t* __restrict
     }
     return;
   }
+  const float tgt = ignored ? 0.f : __bfloat162float(lr[y]);      // read before anything is overwritten (see above)
   float m = -INFINITY, sacc = 0.f;
   for (int i = threadIdx.x; i < nv; i += blockDim.x) {
     float f[8];
@@ -94,7 +98,7 @@ ce_fwd_bwd_vec_kernel(const bf16* __restrict__ logits, const int64_t* __restrict
   const float lse = M + logf(se);
   if (threadIdx.x == 0) {
     if (lse_rows) lse_rows[r] = lse;
-    if (loss_rows) loss_rows[r] = ignored ? 0.f : (lse - __bfloat162float(lr[y]));
+    if (loss_rows) loss_rows[r] = ignored ? 0.f : (lse - tgt);
   }
   if (dlogits) {
     const float gs = ignored ? 0.f : (gscale_ptr ? *gscale_ptr : gscale_const);
@@ -159,25 +163,6 @@ shift_labels_kernel(const int64_t* __restrict__ labels, const int64_t* __restric
   }
 }
 
-// ------------------------------------------------------------------ AdamW
-template <typename T>
-__global__ void __launch_bounds__(256)
-adamw_kernel(T* __restrict__ p, const T* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-             long long n, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt,
-             float grad_scale) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float pv = Cvt<T>::to_f(p[i]);
-    const float gv = Cvt<T>::to_f(g[i]) * grad_scale;
-    pv *= (1.f - lr * wd);
-    const float mv = beta1 * m[i] + (1.f - beta1) * gv;
-    const float vv = beta2 * v[i] + (1.f - beta2) * gv * gv;
-    m[i] = mv; v[i] = vv;
-    const float denom = sqrtf(vv) / bc2_sqrt + eps;
-    pv -= (lr / bc1) * (mv / denom);
-    p[i] = Cvt<T>::from_f(pv);
-  }
-}
-
 // sum of squares (for grad-norm clipping), fp32 partial per CTA then atomic add
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -186,6 +171,131 @@ sumsq_kernel(const T* __restrict__ g, long long n, float* __restrict__ out) {
   float s = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float v = Cvt<T>::to_f(g[i]); s += v * v;
+  }
+  s = mb::block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
+
+// ------------------------------------------------------------------ flat AdamW with fp32 master weights
+// The reference recipe (mantis/train/scripts/train_mllava.sh:148,162 `--bf16 True --learning_rate 1e-5`,
+// zero_configs/zero3.json "bf16": enabled) keeps an fp32 master copy of every weight inside DeepSpeed's optimizer; the
+// bf16 weights are its rounding.  Updating bf16 weights in place instead rounds an lr = 1e-5 step to nothing (ulp(0.02) in
+// bf16 = 1.2e-4).  Here the master is stored SPLIT: the bf16 weight the model computes with + the 16 low bits of the fp32
+// word, master_bits = (bf16_bits << 16) + (int16) lo, with the bf16 half rounded to nearest (ties away from zero) so that
+// it is at the same time the model's weight -- an exact fp32 master for 2 extra bytes per parameter (16 GB, not 32 GB, for
+// Mantis-8B).  One launch covers the whole flat parameter buffer; param groups (weight decay on / off) are resolved per
+// 1024-element block (every tensor's slice of the flat buffers starts on a 1024 boundary); the gradient-norm clip factor is
+// computed on the device from the squared norm, and the gradient buffer is zeroed on the way out.
+__device__ __forceinline__ float clip_factor(const float* norm_sq, float max_norm, float grad_scale) {
+  if (!norm_sq || max_norm <= 0.f) return 1.f;
+  const float total = sqrtf(*norm_sq) * grad_scale;
+  const float c = max_norm / (total + 1e-6f);              // torch.nn.utils.clip_grad_norm_: clamp(max_norm / (norm + 1e-6), max = 1)
+  return (c < 1.f || !(c == c)) ? c : 1.f;                 // NaN norm propagates like torch
+}
+__device__ __forceinline__ float master_join(uint16_t hi, uint16_t lo) {
+  return __uint_as_float(((uint32_t)hi << 16) + (uint32_t)(int32_t)(int16_t)lo);
+}
+__device__ __forceinline__ void master_split(float x, uint16_t& hi, uint16_t& lo) {
+  const uint32_t b = __float_as_uint(x);
+  if ((b & 0x7f800000u) == 0x7f800000u) { hi = (uint16_t)(b >> 16) | ((b & 0xffffu) ? 0x40u : 0u); lo = 0; return; }   // inf / nan
+  hi = (uint16_t)((b + 0x8000u) >> 16);
+  lo = (uint16_t)(b - ((uint32_t)hi << 16));
+}
+
+struct AdamHyper { float lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_scale, max_norm; };
+
+template <bool SPLIT, typename GT>
+__global__ void __launch_bounds__(256)
+adamw_flat_kernel(void* __restrict__ p_, uint16_t* __restrict__ lo_, GT* __restrict__ g_, float* __restrict__ m_,
+                  float* __restrict__ v_, const unsigned char* __restrict__ blk_group, long long n8, AdamHyper h,
+                  const float* __restrict__ norm_sq, int zero_grad) {
+  const float gs = h.grad_scale * clip_factor(norm_sq, h.max_norm, h.grad_scale);
+  const float step_size = h.lr / h.bc1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const long long e0 = i * 8;
+    const float wd = (blk_group && blk_group[e0 >> 10]) ? 0.f : h.wd;
+    float p[8], g[8], m[8], v[8];
+    uint16_t hi[8], lo[8];
+    if (SPLIT) {
+      const int4 ph = mb::ld_stream(reinterpret_cast<const int4*>(reinterpret_cast<uint16_t*>(p_) + e0));
+      const int4 pl = mb::ld_stream(reinterpret_cast<const int4*>(lo_ + e0));
+      const uint16_t* phs = reinterpret_cast<const uint16_t*>(&ph); const uint16_t* pls = reinterpret_cast<const uint16_t*>(&pl);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) p[j] = master_join(phs[j], pls[j]);
+    } else {
+      mb::Vec8<float>::load(reinterpret_cast<const float*>(p_) + e0, p);
+    }
+    mb::Vec8<GT>::load(g_ + e0, g);
+    mb::Vec8<float>::load(m_ + e0, m);
+    mb::Vec8<float>::load(v_ + e0, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float gv = g[j] * gs;
+      float pv = p[j] * (1.f - h.lr * wd);
+      m[j] = h.beta1 * m[j] + (1.f - h.beta1) * gv;
+      v[j] = h.beta2 * v[j] + (1.f - h.beta2) * gv * gv;
+      const float denom = sqrtf(v[j]) / h.bc2_sqrt + h.eps;
+      pv -= step_size * (m[j] / denom);
+      p[j] = pv;
+    }
+    mb::Vec8<float>::store(m_ + e0, m);
+    mb::Vec8<float>::store(v_ + e0, v);
+    if (SPLIT) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) master_split(p[j], hi[j], lo[j]);
+      mb::st_stream(reinterpret_cast<int4*>(reinterpret_cast<uint16_t*>(p_) + e0), *reinterpret_cast<const int4*>(hi));
+      mb::st_stream(reinterpret_cast<int4*>(lo_ + e0), *reinterpret_cast<const int4*>(lo));
+    } else {
+      mb::Vec8<float>::store(reinterpret_cast<float*>(p_) + e0, p);
+    }
+    if (zero_grad) {
+      float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      mb::Vec8<GT>::store(g_ + e0, z);
+    }
+  }
+}
+
+// master <-> (bf16, lo) conversion of a flat range (trainer construction / optimizer checkpoints)
+__global__ void __launch_bounds__(256)
+master_split_kernel(const float* __restrict__ master, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    master_split(master[i], hi[i], lo[i]);
+}
+__global__ void __launch_bounds__(256)
+master_join_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo, float* __restrict__ master, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    master[i] = master_join(hi[i], lo ? lo[i] : (uint16_t)0);
+}
+
+// dst (fp32) += src (bf16 / fp32): gradients that autograd produced in the parameter dtype folded into the fp32 main gradient
+template <typename T>
+__global__ void __launch_bounds__(256)
+accum_f32_kernel(float* __restrict__ dst, const T* __restrict__ src, long long n, float scale) {
+  const long long n8 = n >> 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float a[8], b[8];
+    mb::Vec8<float>::load(dst + i * 8, a);
+    mb::Vec8<T>::load(src + i * 8, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += b[j] * scale;
+    mb::Vec8<float>::store(dst + i * 8, a);
+  }
+  for (long long i = n8 * 8 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] += Cvt<T>::to_f(src[i]) * scale;
+}
+
+// vectorised sum of squares (fp32 / bf16), fp32 partial per CTA then one atomic
+template <typename T>
+__global__ void __launch_bounds__(256)
+sumsq_vec_kernel(const T* __restrict__ g, long long n8, float* __restrict__ out) {
+  __shared__ float red[33];
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float f[8];
+    mb::Vec8<T>::load(g + i * 8, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += f[j] * f[j];
   }
   s = mb::block_sum(s, red);
   if (threadIdx.x == 0) atomicAdd(out, s);
@@ -228,18 +338,60 @@ int mb200_shift_labels(const int64_t* labels, const int64_t* mask, int64_t* out,
   shift_labels_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(labels, mask, out, B, S, ignore_index, count_out);
   MB200_CHECK_LAUNCH(); return MB200_OK;
 }
-int mb200_adamw(void* p, const void* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                float eps, float wd, int step, float grad_scale, int dtype, void* stream) {
+int mb200_adamw_flat(void* p, void* lo, void* g, float* m, float* v, const unsigned char* blk_group, long long n, float lr,
+                     float beta1, float beta2, float eps, float wd, int step, float grad_scale, const float* norm_sq,
+                     float max_norm, int zero_grad, int p_dtype, int g_dtype, void* stream) {
   if (n <= 0) return MB200_OK;
-  const float bc1 = 1.f - powf(beta1, (float)step);
-  const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
-  long long g0 = (n + 255) / 256; long long cap = (long long)mb::num_sms() * 16; if (g0 > cap) g0 = cap;
-  DISPATCH_T(dtype, (adamw_kernel<T><<<(int)g0, 256, 0, (cudaStream_t)stream>>>(
-                        (T*)p, (const T*)g, m, v, n, lr, beta1, beta2, eps, wd, bc1, bc2s, grad_scale)));
+  if ((n & 7) || (reinterpret_cast<uintptr_t>(p) & 15) || (reinterpret_cast<uintptr_t>(g) & 15) ||
+      (reinterpret_cast<uintptr_t>(m) & 15) || (reinterpret_cast<uintptr_t>(v) & 15) || (reinterpret_cast<uintptr_t>(lo) & 15))
+    return -EINVAL;
+  if (p_dtype == MB200_DTYPE_BF16 && !lo) return -EINVAL;            // bf16 weights need their low halves (no silent RTN path)
+  AdamHyper h;
+  h.lr = lr; h.beta1 = beta1; h.beta2 = beta2; h.eps = eps; h.wd = wd; h.grad_scale = grad_scale; h.max_norm = max_norm;
+  h.bc1 = 1.f - powf(beta1, (float)step);
+  h.bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  const long long n8 = n >> 3;
+  long long g0 = (n8 + 255) / 256; const long long cap = (long long)mb::num_sms() * 8; if (g0 > cap) g0 = cap;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p_dtype == MB200_DTYPE_BF16 && g_dtype == MB200_DTYPE_F32)
+    adamw_flat_kernel<true, float><<<(int)g0, 256, 0, st>>>(p, (uint16_t*)lo, (float*)g, m, v, blk_group, n8, h, norm_sq, zero_grad);
+  else if (p_dtype == MB200_DTYPE_BF16 && g_dtype == MB200_DTYPE_BF16)
+    adamw_flat_kernel<true, bf16><<<(int)g0, 256, 0, st>>>(p, (uint16_t*)lo, (bf16*)g, m, v, blk_group, n8, h, norm_sq, zero_grad);
+  else if (p_dtype == MB200_DTYPE_F32 && g_dtype == MB200_DTYPE_F32)
+    adamw_flat_kernel<false, float><<<(int)g0, 256, 0, st>>>(p, nullptr, (float*)g, m, v, blk_group, n8, h, norm_sq, zero_grad);
+  else return -EINVAL;
+  MB200_CHECK_LAUNCH(); return MB200_OK;
+}
+int mb200_master_split(const float* master, void* hi_bf16, void* lo_u16, long long n, void* stream) {
+  if (n <= 0) return MB200_OK;
+  long long g0 = (n + 255) / 256; const long long cap = (long long)mb::num_sms() * 16; if (g0 > cap) g0 = cap;
+  master_split_kernel<<<(int)g0, 256, 0, (cudaStream_t)stream>>>(master, (uint16_t*)hi_bf16, (uint16_t*)lo_u16, n);
+  MB200_CHECK_LAUNCH(); return MB200_OK;
+}
+int mb200_master_join(const void* hi_bf16, const void* lo_u16, float* master, long long n, void* stream) {
+  if (n <= 0) return MB200_OK;
+  long long g0 = (n + 255) / 256; const long long cap = (long long)mb::num_sms() * 16; if (g0 > cap) g0 = cap;
+  master_join_kernel<<<(int)g0, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)hi_bf16, (const uint16_t*)lo_u16, master, n);
+  MB200_CHECK_LAUNCH(); return MB200_OK;
+}
+int mb200_accum_f32(float* dst, const void* src, long long n, float scale, int src_dtype, void* stream) {
+  if (n <= 0) return MB200_OK;
+  if ((reinterpret_cast<uintptr_t>(dst) & 31) || (reinterpret_cast<uintptr_t>(src) & 15)) return -EINVAL;
+  long long g0 = ((n >> 3) + 255) / 256; if (g0 < 1) g0 = 1;
+  const long long cap = (long long)mb::num_sms() * 8; if (g0 > cap) g0 = cap;
+  typedef float F;
+  if (src_dtype == MB200_DTYPE_BF16) accum_f32_kernel<bf16><<<(int)g0, 256, 0, (cudaStream_t)stream>>>(dst, (const bf16*)src, n, scale);
+  else if (src_dtype == MB200_DTYPE_F32) accum_f32_kernel<F><<<(int)g0, 256, 0, (cudaStream_t)stream>>>(dst, (const F*)src, n, scale);
+  else return -EINVAL;
   MB200_CHECK_LAUNCH(); return MB200_OK;
 }
 int mb200_sumsq(const void* g, long long n, float* out, int dtype, void* stream) {
   if (n <= 0) return MB200_OK;
+  if (!(n & 7) && !(reinterpret_cast<uintptr_t>(g) & 31)) {
+    long long b0 = ((n >> 3) + 255) / 256; const long long bcap = (long long)mb::num_sms() * 8; if (b0 > bcap) b0 = bcap;
+    DISPATCH_T(dtype, (sumsq_vec_kernel<T><<<(int)b0, 256, 0, (cudaStream_t)stream>>>((const T*)g, n >> 3, out)));
+    MB200_CHECK_LAUNCH(); return MB200_OK;
+  }
   long long g0 = (n + 255) / 256; long long cap = (long long)mb::num_sms() * 8; if (g0 > cap) g0 = cap;
   DISPATCH_T(dtype, (sumsq_kernel<T><<<(int)g0, 256, 0, (cudaStream_t)stream>>>((const T*)g, n, out)));
   MB200_CHECK_LAUNCH(); return MB200_OK;

@@ -8,6 +8,9 @@ from .. import _lib, ops
 from .kv_cache import B200KVCache
 
 
+native_steps = 0          # process-wide count of tokens decoded through the C++ engine (tests / bench read it)
+
+
 class DecodeEngine:
     def __init__(self, decoder, lm_head_weight, cache: B200KVCache, reserve_tokens=1024):
         cfg = decoder.config
@@ -38,8 +41,11 @@ class DecodeEngine:
         if x_dtype != torch.bfloat16 or cache.dtype != torch.bfloat16 or a.head_dim != 128 or not 0 < cache.batch <= 16:
             return False
         for layer in decoder.layers:
-            for lin in (layer.self_attn.q_proj, layer.self_attn.o_proj, layer.mlp.gate_proj):
-                if type(lin).__name__ != "B200Linear" or lin.bias is not None:   # peft-wrapped / biased layers: Python path
+            a, m = layer.self_attn, layer.mlp
+            # every projection the engine reads raw weights of (_build_tables): a peft wrapper or a bias on ANY of them
+            # (e.g. LoRA on k_proj/v_proj or down_proj only) sends the step down the Python path, which honours it
+            for lin in (a.q_proj, a.k_proj, a.v_proj, a.o_proj, m.gate_proj, m.up_proj, m.down_proj):
+                if type(lin).__name__ != "B200Linear" or lin.bias is not None:
                     return False
         return True
 
@@ -54,7 +60,9 @@ class DecodeEngine:
         self.layer_tab = (ctypes.c_void_p * len(ptrs))(*[t.data_ptr() if t is not None else None for t in ptrs])
 
     def step(self, ids, pos, kbits=None):
-        """ids, pos: int64 [B] on device.  Appends one token per sequence to the cache, returns (logits [B,V], next_ids)."""
+        """ids, pos: int64 [B] on device.  Appends one token per sequence to the cache, returns (logits [B,V], next_ids).
+        The returned tensors are VIEWS of the engine's persistent buffers: the next step() overwrites them (callers that keep
+        logits across steps must clone)."""
         ctx = self.cache.get_seq_length()
         self.cache.ensure(ctx + 1)                    # new pages only extend the block table; nothing is copied
         table = self.cache.device_table()
@@ -85,7 +93,7 @@ def native_decode_logits(decoder, lm_head, cache, input_ids, x_dtype, attention_
     if not DecodeEngine.eligible(decoder, cache, x_dtype):
         return None
     eng = getattr(cache, "_engine", None)
-    if eng is None or eng.decoder is not decoder:
+    if eng is None or eng.decoder is not decoder or eng.B != cache.batch or eng.lm_head_weight is not lm_head.weight:
         eng = DecodeEngine(decoder, lm_head.weight, cache)
         cache._engine = eng
     ctx = cache.get_seq_length()
@@ -97,4 +105,6 @@ def native_decode_logits(decoder, lm_head, cache, input_ids, x_dtype, attention_
     if position_ids is None:
         position_ids = torch.full((input_ids.shape[0], 1), ctx, dtype=torch.int64, device=input_ids.device)
     logits, _ = eng.step(input_ids[:, 0], position_ids[:, -1].to(torch.int64), kbits)
+    global native_steps
+    native_steps += 1
     return logits

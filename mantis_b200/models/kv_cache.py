@@ -105,6 +105,7 @@ class B200KVCache:
 
     def reset(self):
         self.slabs, self.free, self.blocks, self.table = [], [], [], None
+        self.__dict__.pop("_engine", None)         # the native decode engine holds buffers sized for the old batch
         self.batch = 0
         self.lengths = []
 

@@ -92,6 +92,17 @@ def gemm(a, b, trans_a=False, trans_b=True, bias=None, act=None, addend=None, ou
         _call("mb200_skinny_gemm_bf16", _p(a), _p(b), _p(out), _p(bias), _p(addend), M, N, K, a.stride(0), b.stride(0),
               out.stride(0), addend.stride(0) if addend is not None else 0, _st())
         return out
+    if out.dtype == torch.float32 and a.dtype == torch.bfloat16:
+        # fp32 destination of a bf16 product: the wgrad into the fp32 main-gradient buffer (C32 (+)= op(a) op(b))
+        assert bias is None and act is None and (addend is None or addend.data_ptr() == out.data_ptr()), \
+            "the fp32-output GEMM only accumulates into its own destination"
+        if _fast_ok(a, b, M, N, K) and out.stride(0) % 4 == 0 and out.data_ptr() % 16 == 0:
+            _call("mb200_gemm_bf16_acc32", _p(a), _p(b), _p(out), M, N, K, a.stride(0), b.stride(0), out.stride(0),
+                  int(trans_a), int(trans_b), int(addend is not None), _st())
+            return out
+        _call("mb200_gemm_generic", _p(a), _p(b), _p(out), None, M, N, K, a.stride(0), b.stride(0), out.stride(0),
+              int(trans_a), int(trans_b), 1.0, 1.0 if addend is not None else 0.0, 1, 0, 0, 0, _dt(a), _dt(out), _st())
+        return out
     if _fast_ok(a, b, M, N, K) and out.dtype == torch.bfloat16:
         fn = "mb200_gemm_bf16_2cta" if (GEMM_2CTA and M >= 512 and N >= 512) else "mb200_gemm_bf16"
         _call(fn, _p(a), _p(b), _p(out), _p(bias), _p(addend), M, N, K, a.stride(0), b.stride(0),
@@ -127,6 +138,13 @@ def colsum(x2d, out=None, accumulate=False):
     return out
 
 
+def _wgrad_into_main(g2, x2, w):
+    """main_grad += g2^T @ x2 for a weight whose gradient lives in a B200Trainer flat buffer (`w._b200_main_grad`, an
+    [out, in] view; fp32 by default): accumulation happens in the wgrad epilogue, in the buffer's own precision."""
+    mg = w._b200_main_grad
+    gemm(g2, x2, trans_a=True, trans_b=False, addend=mg, out=mg)
+
+
 class _LinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, act, residual):
@@ -145,7 +163,7 @@ class _LinearFn(torch.autograd.Function):
             pre = None
             y = gemm(x2, weight, bias=bias, act=act, addend=res2)
         ctx.save_for_backward(x2, weight, pre)
-        ctx.weight_ref = weight if getattr(weight, "_b200_fused_grad", False) else None
+        ctx.weight_ref = weight if getattr(weight, "_b200_main_grad", None) is not None else None
         ctx.act = act
         ctx.has_bias = bias is not None
         ctx.has_res = residual is not None
@@ -166,9 +184,10 @@ class _LinearFn(torch.autograd.Function):
             gx = gemm(g2, weight, trans_a=False, trans_b=False).reshape(ctx.in_shape)      # dx = dy @ W
         if ctx.needs_input_grad[1]:
             wref = ctx.weight_ref
-            if wref is not None and wref.grad is not None and wref.grad.is_contiguous():
-                # gradient accumulation fused into the wgrad epilogue: grad += dy^T @ x (no temporary, no extra pass)
-                gemm(g2, x2, trans_a=True, trans_b=False, addend=wref.grad, out=wref.grad)
+            if wref is not None:
+                # gradient accumulation fused into the wgrad epilogue: main_grad += dy^T @ x (no temporary, no extra pass;
+                # main_grad is the trainer's flat buffer, fp32 by default)
+                _wgrad_into_main(g2, x2, wref)
             else:
                 gw = gemm(g2, x2, trans_a=True, trans_b=False)                             # dW = dy^T @ x
         if ctx.has_bias and ctx.needs_input_grad[2]:
@@ -188,7 +207,7 @@ class _MultiLinearFn(torch.autograd.Function):
         if x2.stride(1) != 1:
             x2 = x2.contiguous()
         ctx.save_for_backward(x2, *weights)
-        ctx.wrefs = [w if getattr(w, "_b200_fused_grad", False) else None for w in weights]
+        ctx.wrefs = [w if getattr(w, "_b200_main_grad", None) is not None else None for w in weights]
         ctx.in_shape = shp
         return tuple(gemm(x2, w).reshape(*shp[:-1], w.shape[0]) for w in weights)
 
@@ -209,8 +228,8 @@ class _MultiLinearFn(torch.autograd.Function):
             gw = None
             if ctx.needs_input_grad[1 + i]:
                 wref = ctx.wrefs[i]
-                if wref is not None and wref.grad is not None and wref.grad.is_contiguous():
-                    gemm(g2, x2, trans_a=True, trans_b=False, addend=wref.grad, out=wref.grad)
+                if wref is not None:
+                    _wgrad_into_main(g2, x2, wref)
                 else:
                     gw = gemm(g2, x2, trans_a=True, trans_b=False)
             gws.append(gw)
@@ -709,16 +728,36 @@ def _merge_ws(B, T, device):
     return ws
 
 
-_deferred_checks = []
+_deferred_checks = []       # (pinned host flag, event that marks its arrival, message)
 
 
-def check_deferred():
-    """Raise the errors of sync-free merges (see merge_input_ids_with_image_features(plan_hint=...)): call at a point where
-    the host synchronises anyway (B200Trainer does, right after the gradient-norm readback)."""
-    pending, _deferred_checks[:] = list(_deferred_checks), []
-    for flag, msg in pending:
-        if not bool(flag.item()):
-            raise ValueError(msg)
+def _defer_check(flag_dev, msg):
+    """queue a device-side boolean for a later host-side check WITHOUT synchronising: the flag travels to pinned host memory
+    on the current stream and is looked at once its event has completed"""
+    host = torch.empty((1,), dtype=torch.bool).pin_memory()
+    host.copy_(flag_dev.reshape(1), non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    _deferred_checks.append((host, ev, msg))
+
+
+def check_deferred(block=True):
+    """Raise the errors of sync-free merges (see merge_input_ids_with_image_features(plan_hint=...)).  block=False (what
+    B200Trainer.optimizer_step uses, every step) only looks at flags that have already arrived, so the host never waits for
+    the device; block=True (call it wherever the host synchronises anyway, e.g. when the loss is read) drains them all."""
+    keep = []
+    err = None
+    for host, ev, msg in _deferred_checks:
+        if block:
+            ev.synchronize()
+        elif not ev.query():
+            keep.append((host, ev, msg))
+            continue
+        if err is None and not bool(host[0]):
+            err = msg
+    _deferred_checks[:] = keep
+    if err is not None:
+        raise ValueError(err)
 
 
 def merge_plan(input_ids, inputs_embeds, P, image_token, pad_token, sync=True):
@@ -792,10 +831,10 @@ def merge_input_ids_with_image_features(image_features, inputs_embeds, input_ids
         S = int(plan_hint["max_image_tokens"]) * (P - 1) + T
         left_padding = int(bool(plan_hint["left_padding"]))
         expect = torch.tensor([S, left_padding, num_images * P], dtype=torch.int64, device=ids.device)
-        _deferred_checks.append(((hdr[:3] == expect).all(),
-                                 "The input provided to the model are wrong (sync-free merge): the plan_hint or the number of"
-                                 f" images ({num_images}) does not match the image tokens in input_ids. This prevents correct"
-                                 " indexing and breaks batch generation."))
+        _defer_check((hdr[:3] == expect).all(),
+                     "The input provided to the model are wrong (sync-free merge): the plan_hint or the number of"
+                     f" images ({num_images}) does not match the image tokens in input_ids. This prevents correct"
+                     " indexing and breaks batch generation.")
     else:
         ws, hdr = merge_plan(ids, emb, P, image_token_index, pad_token_id)
         S, left_padding, n_slots = int(hdr[0]), int(hdr[1]), int(hdr[2])
@@ -1033,9 +1072,34 @@ def rows_all_zero(x2):
     return flags
 
 
-def adamw_step(p, g, m, v, lr, beta1, beta2, eps, wd, step, grad_scale=1.0):
-    _call("mb200_adamw", _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
-          float(wd), int(step), float(grad_scale), _dt(p), _st())
+def adamw_flat(p, lo, g, m, v, blk_group, lr, beta1, beta2, eps, wd, step, grad_scale=1.0, norm_sq=None, max_norm=0.0,
+               zero_grad=True):
+    """ONE launch of AdamW over flat buffers.  p bf16 + lo (int16 low halves = fp32 master) or p fp32 (lo None); g fp32/bf16."""
+    _need_cuda(p, g, m, v)
+    if p.dtype == torch.bfloat16 and lo is None:
+        raise ValueError("bf16 parameters need their fp32-master low halves (lo)")
+    _call("mb200_adamw_flat", _p(p), _p(lo), _p(g), _p(m), _p(v), _p(blk_group), p.numel(), float(lr), float(beta1),
+          float(beta2), float(eps), float(wd), int(step), float(grad_scale), _p(norm_sq), float(max_norm or 0.0),
+          int(bool(zero_grad)), _dt(p), _dt(g), _st())
+
+
+def master_split(master, hi, lo):
+    """fp32 master -> (bf16 weight `hi`, int16 low half `lo`), flat tensors of equal length"""
+    _call("mb200_master_split", _p(master), _p(hi), _p(lo), master.numel(), _st())
+
+
+def master_join(hi, lo, out=None):
+    """(bf16 weight, int16 low half or None) -> fp32 master"""
+    if out is None:
+        out = torch.empty(hi.shape, dtype=torch.float32, device=hi.device)
+    _call("mb200_master_join", _p(hi), _p(lo), _p(out), hi.numel(), _st())
+    return out
+
+
+def accum_f32(dst, src, scale=1.0):
+    """dst (fp32, contiguous) += scale * src (bf16 / fp32, contiguous, same numel)"""
+    assert dst.dtype == torch.float32 and dst.is_contiguous() and src.is_contiguous() and dst.numel() == src.numel()
+    _call("mb200_accum_f32", _p(dst), _p(src), dst.numel(), float(scale), _dt(src), _st())
 
 
 def sumsq(g, out):

@@ -1,3 +1,3 @@
-from .engine import B200Trainer, flat_grad_buffer  # noqa: F401
+from .engine import B200Trainer, FlatState  # noqa: F401
 from .data import (ChatDataset, Collator, PackingDataset, assistant_labels, merged_length,  # noqa: F401
                    partition_balanced)

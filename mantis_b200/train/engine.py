@@ -1,12 +1,18 @@
 """Minimal data-parallel instruction-tuning engine for the hot path (what HF Trainer + accelerate/DeepSpeed do for
 mantis/train/train_mllava.py:312-329 with per_device_train_batch_size=1 + gradient accumulation,
-mantis/train/scripts/train_mllava.sh:137-168), reduced to what the step needs:
+mantis/train/scripts/train_mllava.sh:137-168, zero_configs/zero3.json "bf16": enabled), reduced to what the step needs:
 
-  * micro-batches of one sample: loss/accum -> backward (gradients accumulate in ONE flat bf16 buffer that every
-    trainable parameter's .grad is a view of),
-  * one NCCL all-reduce (sum, then 1/world) of that flat buffer per optimizer step -- the only exchange of the
-    data-parallel path; the vision tower is frozen and excluded,
-  * optional global-norm clipping + fused AdamW (bf16 params, fp32 moments) on our CUDA kernel.
+  * FLAT training state, one allocation each, every tensor's slice starting on a 1024-element boundary:
+      P   bf16  the model's weights (every trainable parameter is re-pointed at its slice)
+      LO  int16 the 16 low bits of each weight's fp32 master copy -- (P, LO) together ARE the fp32 master weights DeepSpeed's
+                bf16 optimizer keeps (an lr = 1e-5 AdamW step is far below half a bf16 ulp of a typical weight and would be
+                rounded away if the bf16 weights were updated in place); 2 extra bytes per parameter instead of 4
+      G   fp32  the main gradient: micro-batches accumulate here in fp32 (wgrad GEMMs write it from their epilogue; gradients
+                autograd produces in bf16 are folded in by a post-accumulate hook), and it is the ONE buffer the data-parallel
+                all-reduce exchanges; the vision tower is frozen and excluded
+      M,V fp32  AdamW moments
+  * one fused launch per optimizer step: global-norm clip factor computed on the device from sum(G^2) (no host read-back),
+    AdamW on the fp32 master, bf16 weights re-rounded, G zeroed.
 """
 import math
 
@@ -15,20 +21,64 @@ import torch.distributed as dist
 
 from .. import ops
 
+ALIGN = 1024        # elements; one param-group byte per block (ops.adamw_flat)
 
-def flat_grad_buffer(params):
-    """Allocates one contiguous buffer and makes every param.grad a view into it. Returns (flat, views)."""
-    params = [p for p in params if p.requires_grad]
-    total = sum((p.numel() + 7) // 8 * 8 for p in params)      # keep every view 16-byte aligned
-    dtype = params[0].dtype
-    assert all(p.dtype == dtype for p in params), "trainable parameters must share a dtype"
-    flat = torch.zeros(total, dtype=dtype, device=params[0].device)
-    off = 0
-    for p in params:
+
+def _aligned(n):
+    return (n + ALIGN - 1) // ALIGN * ALIGN
+
+
+class FlatState:
+    """The flat buffers above for an ordered list of parameters."""
+
+    def __init__(self, params, grad_dtype=torch.float32):
+        self.params = params
+        dtype = params[0].dtype
+        if not all(p.dtype == dtype for p in params):
+            raise ValueError("trainable parameters must share a dtype")
+        dev = params[0].device
+        self.offsets, off = [], 0
+        for p in params:
+            self.offsets.append(off)
+            off += _aligned(p.numel())
+        self.total = off
+        self.split = dtype == torch.bfloat16
+        self.P = torch.zeros(self.total, dtype=dtype, device=dev)
+        self.LO = torch.zeros(self.total, dtype=torch.int16, device=dev) if self.split else None
+        self.G = torch.zeros(self.total, dtype=grad_dtype if self.split else torch.float32, device=dev)
+        self.M = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        self.V = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        groups = torch.zeros(self.total // ALIGN, dtype=torch.uint8)
+        for p, o in zip(params, self.offsets):
+            n = p.numel()
+            with torch.no_grad():
+                self.P[o:o + n].copy_(p.detach().reshape(-1))
+            p.data = self.P[o:o + n].view(p.shape)                     # the model now computes with the flat buffer
+            p._b200_main_grad = self.G[o:o + n].view(p.shape)
+            if p.dim() <= 1:                                           # biases / norm weights: no weight decay (HF Trainer's
+                groups[o // ALIGN:(o + _aligned(n)) // ALIGN] = 1      # get_decay_parameter_names excludes exactly these)
+        self.groups = groups.to(dev)
+
+    def view(self, buf, i):
+        p, o = self.params[i], self.offsets[i]
+        return buf[o:o + p.numel()].view(p.shape)
+
+    def master(self, i):
+        """fp32 master copy of parameter i (reconstructed from the bf16 weight and its low half)"""
+        p, o = self.params[i], self.offsets[i]
         n = p.numel()
-        p.grad = flat[off:off + n].view_as(p)
-        off += (n + 7) // 8 * 8
-    return flat
+        if not self.split:
+            return self.P[o:o + n].view(p.shape).clone()
+        return ops.master_join(self.P[o:o + n], self.LO[o:o + n]).view(p.shape)
+
+    def set_master(self, i, value):
+        p, o = self.params[i], self.offsets[i]
+        n = p.numel()
+        src = value.to(device=self.P.device, dtype=torch.float32).reshape(-1).contiguous()
+        if not self.split:
+            self.P[o:o + n].copy_(src)
+        else:
+            ops.master_split(src, self.P[o:o + n], self.LO[o:o + n])
 
 
 class _GradReady(torch.autograd.Function):
@@ -66,7 +116,7 @@ def lr_lambda(step, total_steps, warmup_steps, kind="cosine"):
 class B200Trainer:
     def __init__(self, model, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0,
                  grad_accum=1, freeze_vision=True, fused_wgrad_accum=True, overlap_allreduce=True,
-                 lr_schedule="constant", total_steps=None, warmup_ratio=0.0, warmup_steps=None):
+                 lr_schedule="constant", total_steps=None, warmup_ratio=0.0, warmup_steps=None, grad_dtype=torch.float32):
         self.model = model
         self.lr_schedule, self.total_steps = lr_schedule, total_steps
         # HF Trainer: warmup_steps wins over warmup_ratio; the ratio is rounded up (TrainingArguments.get_warmup_steps)
@@ -76,27 +126,84 @@ class B200Trainer:
             for n, p in model.named_parameters():
                 if "vision_tower" in n or "vision_model" in n:
                     p.requires_grad_(False)
-        self.params = [p for p in model.parameters() if p.requires_grad]
-        self.flat_grad = flat_grad_buffer(self.params)
+        self.params, self._layer_ranges = self._ordered_params(model)
+        self.state = FlatState(self.params, grad_dtype=grad_dtype)
+        self.flat_grad = self.state.G
+        from ..models.layers import B200Linear
+        fused = set()
         if fused_wgrad_accum:
-            # linear layers accumulate dW straight into the flat buffer from the wgrad GEMM epilogue
-            from ..models.layers import B200Linear
+            # linear layers accumulate dW straight into the flat main gradient from the wgrad GEMM epilogue
             for mod in model.modules():
-                if isinstance(mod, B200Linear) and mod.weight.requires_grad and mod.weight.grad is not None:
-                    mod.weight._b200_fused_grad = True
-        self.m = [torch.zeros(p.shape, dtype=torch.float32, device=p.device) for p in self.params]
-        self.v = [torch.zeros(p.shape, dtype=torch.float32, device=p.device) for p in self.params]
+                if isinstance(mod, B200Linear) and mod.weight.requires_grad and mod.weight.dim() == 2:
+                    fused.add(id(mod.weight))
+        for p in self.params:
+            if id(p) not in fused:
+                # autograd hands these gradients over in the parameter dtype: fold each into the fp32 main gradient as soon
+                # as it is produced and drop the temporary
+                mg = p._b200_main_grad
+                p._b200_main_grad = None                       # ops._LinearFn: not a fused-wgrad weight
+                p._b200_unfused_main_grad = mg
+                p.register_post_accumulate_grad_hook(self._fold_grad)
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.max_grad_norm = max_grad_norm
         self.grad_accum = grad_accum
         self.step_count = 0
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self._norm = torch.zeros(1, dtype=torch.float32, device=self.flat_grad.device)
+        self.last_grad_norm_sq = self._norm               # device scalar: sum(G^2) of the last step (before the 1/world scale)
         self._overlap = False
         self._works = []
         self._reduced_from = None
         if overlap_allreduce and self.world > 1:
             self._install_overlap_hooks()
+
+    @staticmethod
+    def _fold_grad(p):
+        mg = p._b200_unfused_main_grad
+        g = p.grad
+        if g is None:
+            return
+        if g.is_cuda and mg.dtype == torch.float32:
+            ops.accum_f32(mg.reshape(-1), g.contiguous().view(-1))
+        else:                                  # bf16 main gradient, or the CPU/gloo plumbing tests (no kernels there)
+            mg.add_(g.to(mg.dtype))
+        p.grad = None
+
+    @staticmethod
+    def _ordered_params(model):
+        """Trainable parameters in flat-buffer order + the [start, end) parameter-index range of each decoder layer.
+        Order: everything that is NOT part of the text decoder's layers / final norm / LM head first (projector, connector,
+        MLlava's image_type_embeddings and vision_xatten_layers, token embeddings: their gradients are only final at the very
+        end of backward), then decoder layer 0 .. L-1, then the final norm and the LM head (final first).  The overlapped
+        all-reduce walks this buffer from the tail, so a slice is only ever reduced after all of its gradients exist."""
+        layers = None
+        for name, mod in model.named_modules():
+            if name.endswith("language_model.model.layers") or name.endswith("text_model.layers"):
+                layers = mod
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        if layers is None:
+            return [p for _, p in named], None
+        layer_ids = [{id(p) for p in layer.parameters()} for layer in layers]
+        in_layer = set().union(*layer_ids) if layer_ids else set()
+        tail_names = ("language_model.model.norm.", "language_model.lm_head.", "text_model.norm.", "lm_head.")
+        head, tail = [], []
+        for n, p in named:
+            if id(p) in in_layer:
+                continue
+            (tail if any(t in n for t in tail_names) and "vision" not in n and "perceiver" not in n else head).append(p)
+        order, ranges = list(head), []
+        for layer in layers:
+            ps = [p for p in layer.parameters() if p.requires_grad]
+            ranges.append((len(order), len(order) + len(ps)))
+            order += ps
+        order += tail
+        seen, uniq = set(), []
+        for p in order:                                     # tied weights appear once
+            if id(p) not in seen:
+                seen.add(id(p)); uniq.append(p)
+        if len(uniq) != len(order):
+            return [p for _, p in named], None
+        return order, ranges
 
     # ---- overlapped gradient all-reduce (N > 1): during the LAST micro-batch's backward, the slice of the flat buffer
     # belonging to decoder layer i+1 (and everything after it) is reduced as soon as layer i's backward has run, so the
@@ -106,16 +213,9 @@ class B200Trainer:
         for name, mod in self.model.named_modules():
             if name.endswith("language_model.model.layers") or name.endswith("text_model.layers"):
                 layers = mod
-        if layers is None:
+        if layers is None or self._layer_ranges is None or any(a == b for a, b in self._layer_ranges):
             return
-        base = self.flat_grad.data_ptr(); esz = self.flat_grad.element_size()
-        starts = []
-        for layer in layers:
-            ps = [p for p in layer.parameters() if p.requires_grad]
-            starts.append(min((p.grad.data_ptr() - base) // esz for p in ps) if ps else None)
-        if any(s is None for s in starts) or starts != sorted(starts):
-            return
-        self._layer_starts = starts
+        self._layer_starts = [self.state.offsets[a] for a, _ in self._layer_ranges]      # ascending by construction
         n = len(layers)
 
         def make_cb(i):
@@ -148,19 +248,28 @@ class B200Trainer:
 
     # ---- checkpoint / resume of the optimizer side (the model itself goes through save_pretrained) ----
     def state_dict(self):
+        st = self.state
+        n = len(self.params)
         return {"step": self.step_count, "lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.wd,
                 "lr_schedule": self.lr_schedule, "total_steps": self.total_steps, "warmup_steps": self.warmup_steps,
-                "exp_avg": [m.detach().cpu() for m in self.m], "exp_avg_sq": [v.detach().cpu() for v in self.v]}
+                "exp_avg": [st.view(st.M, i).detach().cpu().clone() for i in range(n)],
+                "exp_avg_sq": [st.view(st.V, i).detach().cpu().clone() for i in range(n)],
+                # the fp32 master weights (DeepSpeed checkpoints them too): without them a resumed run restarts from the
+                # bf16 rounding of every weight
+                "master_params": [st.master(i).detach().cpu() for i in range(n)]}
 
     def load_state_dict(self, state):
-        if len(state["exp_avg"]) != len(self.m):
-            raise ValueError(f"optimizer state has {len(state['exp_avg'])} tensors, the model has {len(self.m)} trainable ones")
-        for dst, src in zip(self.m, state["exp_avg"]):
-            if dst.shape != src.shape:
+        st = self.state
+        if len(state["exp_avg"]) != len(self.params):
+            raise ValueError(f"optimizer state has {len(state['exp_avg'])} tensors, the model has {len(self.params)} trainable ones")
+        for i, src in enumerate(state["exp_avg"]):
+            if st.view(st.M, i).shape != src.shape:
                 raise ValueError("optimizer state does not match the trainable parameters")
-            dst.copy_(src)
-        for dst, src in zip(self.v, state["exp_avg_sq"]):
-            dst.copy_(src)
+            st.view(st.M, i).copy_(src)
+        for i, src in enumerate(state["exp_avg_sq"]):
+            st.view(st.V, i).copy_(src)
+        for i, src in enumerate(state.get("master_params") or []):
+            st.set_master(i, src)
         self.step_count = int(state["step"])
         self.lr, self.betas, self.eps, self.wd = state["lr"], tuple(state["betas"]), state["eps"], state["weight_decay"]
         self.lr_schedule, self.total_steps = state["lr_schedule"], state["total_steps"]
@@ -175,10 +284,11 @@ class B200Trainer:
         (out.loss / self.grad_accum).backward()
         return out.loss.detach()
 
-    def _restore_grad_views(self):
-        # autograd accumulates in place into existing .grad tensors, so the views stay bound; assert cheaply
+    def _check_views(self):
         p = self.params[0]
-        assert p.grad.data_ptr() == self.flat_grad.data_ptr(), "param.grad was rebound away from the flat buffer"
+        if p.data_ptr() != self.state.P.data_ptr():
+            raise RuntimeError("a trainable parameter was re-allocated after B200Trainer was built (model.to()/load with "
+                               "assign=True?): its storage must stay the trainer's flat buffer")
 
     def reduce_gradients(self):
         """the one collective of the data-parallel path: sum the flat gradient buffer over ranks (the part not already
@@ -195,23 +305,23 @@ class B200Trainer:
         return 1.0 / self.world
 
     def optimizer_step(self):
-        self._restore_grad_views()
+        self._check_views()
         scale = self.reduce_gradients()
-        if self.max_grad_norm is not None and self.max_grad_norm > 0:
+        st = self.state
+        clip = self.max_grad_norm is not None and self.max_grad_norm > 0
+        if clip:
             self._norm.zero_()
-            ops.sumsq(self.flat_grad, self._norm)
-            # clip factor computed on device; read back lazily (no sync needed: pass through a tiny host value
-            # only when logging).  The fused kernel takes the scale as a host float, so one 4-byte readback here.
-            total = math.sqrt(float(self._norm.item())) * scale
-            if total > self.max_grad_norm:
-                scale *= self.max_grad_norm / (total + 1e-6)
-        ops.check_deferred()                       # errors of sync-free merges surface here, after the step's one readback
+            ops.sumsq(self.flat_grad, self._norm)        # the clip factor is derived from it INSIDE the AdamW kernel: no read-back
+        ops.check_deferred(block=False)                  # errors of sync-free merges surface here once their flag has arrived
         lr = self.current_lr()
         self.step_count += 1
-        for p, m, v in zip(self.params, self.m, self.v):
-            ops.adamw_step(p.data, p.grad, m, v, lr, self.betas[0], self.betas[1], self.eps, self.wd,
-                           self.step_count, grad_scale=scale)
-        self.zero_grad()
+        ops.adamw_flat(st.P, st.LO, st.G, st.M, st.V, st.groups, lr, self.betas[0], self.betas[1], self.eps, self.wd,
+                       self.step_count, grad_scale=scale, norm_sq=self._norm if clip else None,
+                       max_norm=self.max_grad_norm if clip else 0.0, zero_grad=True)
+
+    def grad_norm(self):
+        """global gradient norm of the last optimizer step (after the 1/world scale, before clipping); one host read-back"""
+        return math.sqrt(float(self._norm.item())) / self.world
 
     def train_step(self, micro_batches):
         losses = []

@@ -18,16 +18,15 @@ def _worker(rank, world, port, q):
     from mantis_b200.train.engine import B200Trainer
     torch.manual_seed(0)
     model = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.GELU(), torch.nn.Linear(32, 4))
-    tr = B200Trainer.__new__(B200Trainer)            # plumbing only: no CUDA kernels on this box
-    from mantis_b200.train.engine import flat_grad_buffer
-    tr.params = [p for p in model.parameters()]
-    tr.flat_grad = flat_grad_buffer(tr.params)
-    tr.world = world; tr.grad_accum = 2
+    # plumbing only (no CUDA kernels on this box): flat fp32 state, gradients folded into the flat main gradient by hooks
+    tr = B200Trainer(model, grad_accum=2, freeze_vision=False, fused_wgrad_accum=False, overlap_allreduce=False)
+    assert tr.world == world
     g = torch.Generator().manual_seed(100 + rank)
     xs = [torch.randn(8, 16, generator=g) for _ in range(2)]
     for x in xs:                                     # two micro-batches accumulate into the flat buffer
         (model(x).pow(2).mean() / tr.grad_accum).backward()
-    assert tr.params[0].grad.data_ptr() == tr.flat_grad.data_ptr()
+    assert all(p.grad is None for p in tr.params)                      # folded into the flat buffer and released
+    assert tr.params[0]._b200_unfused_main_grad.data_ptr() == tr.flat_grad.data_ptr()
     local = tr.flat_grad.clone()
     scale = tr.reduce_gradients()
     torch.save((rank, local, tr.flat_grad.clone() * scale), os.path.join(q, f"r{rank}.pt"))
@@ -51,20 +50,22 @@ def test_flat_buffer_allreduce_world2():
     assert not torch.allclose(res[0][1], res[1][1])          # ranks really saw different data
 
 
-def test_flat_grad_views_are_aligned():
-    from mantis_b200.train.engine import flat_grad_buffer
-    ps = [torch.nn.Parameter(torch.randn(n)) for n in (3, 17, 64, 5)]
-    flat = flat_grad_buffer(ps)
-    for p in ps:
-        assert (p.grad.data_ptr() - flat.data_ptr()) % 16 == 0
-        assert p.grad.shape == p.shape
+def test_flat_state_views_are_aligned():
+    from mantis_b200.train.engine import FlatState
+    ps = [torch.nn.Parameter(torch.randn(n)) for n in (3, 17, 2064, 5)]
+    vals = [p.detach().clone() for p in ps]
+    st = FlatState(ps)
+    assert st.total == 1024 * 6
+    for p, v, o in zip(ps, vals, st.offsets):
+        assert o % 1024 == 0 and p.data_ptr() == st.P.data_ptr() + 4 * o
+        assert torch.equal(p.detach(), v) and p._b200_main_grad.shape == p.shape
 
 
 def _overlap_worker(rank, world, port, q):
     import torch.nn as nn
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from mantis_b200.train.engine import B200Trainer, flat_grad_buffer
+    from mantis_b200.train.engine import B200Trainer
 
     class Layer(nn.Module):
         def __init__(self):
@@ -89,13 +90,16 @@ def _overlap_worker(rank, world, port, q):
 
     torch.manual_seed(0)
     model = Net()
-    tr = B200Trainer.__new__(B200Trainer)
-    tr.model = model
-    tr.params = [p for p in model.parameters()]
-    tr.flat_grad = flat_grad_buffer(tr.params)
-    tr.world = world; tr.grad_accum = 2; tr._overlap = False; tr._works = []; tr._reduced_from = None
-    tr._install_overlap_hooks()
+    # MLlava registers trainable modules AFTER language_model (image_type_embeddings, vision_xatten_layers): their gradients
+    # are only final at the end of backward, so they must not sit in the tail slice the first overlapped all-reduce takes
+    model.image_type_embeddings = nn.Embedding(4, 8)
+    inner = model.forward
+    model.forward = lambda x: inner(x + model.image_type_embeddings.weight[:1])
+    tr = B200Trainer(model, grad_accum=2, freeze_vision=False, fused_wgrad_accum=False, overlap_allreduce=True)
     assert getattr(tr, "_has_hooks", False)
+    idx = lambda t: [i for i, p in enumerate(tr.params) if p is t][0]
+    late = idx(model.image_type_embeddings.weight)
+    assert tr.state.offsets[late] < tr._layer_starts[0], "late parameters must precede the decoder layers in the flat buffer"
     g = torch.Generator().manual_seed(10 + rank)
     xs = [torch.randn(5, 8, generator=g) for _ in range(2)]
     # reference: plain accumulation, then one all-reduce
@@ -111,7 +115,8 @@ def _overlap_worker(rank, world, port, q):
         tr._overlap = False
     n_async = len(tr._works)
     scale = tr.reduce_gradients()
-    torch.save((rank, n_async, bool(torch.allclose(tr.flat_grad * scale, ref, atol=1e-6))), os.path.join(q, f"r{rank}.pt"))
+    ok = bool(torch.allclose(tr.flat_grad * scale, ref, atol=1e-6)) and ref[tr.state.offsets[late]:].abs().sum() > 0
+    torch.save((rank, n_async, ok), os.path.join(q, f"r{rank}.pt"))
     dist.destroy_process_group()
 
 

@@ -624,13 +624,104 @@ def test_lm_head_ce(ops, cuda, dtype):
     assert _rel(h.grad, hr.grad) < tol and _rel(w.grad, wr.grad) < tol
 
 
-def test_adamw(ops, cuda):
+def test_adamw_flat_fp32(ops, cuda):
+    """flat fused AdamW on fp32 weights == torch.optim.AdamW (weight decay only on the blocks whose group byte is 0)"""
     torch.manual_seed(11)
-    p = torch.randn(10007, device=cuda); g = torch.randn_like(p)
-    pr = p.clone().requires_grad_(True)
-    opt = torch.optim.AdamW([pr], lr=1e-2, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1)
+    n = 4096
+    p = torch.randn(n, device=cuda); g0 = torch.randn_like(p)
+    pr_decay = p[:3072].clone().requires_grad_(True); pr_nodecay = p[3072:].clone().requires_grad_(True)
+    opt = torch.optim.AdamW([{"params": [pr_decay], "weight_decay": 0.1}, {"params": [pr_nodecay], "weight_decay": 0.0}],
+                            lr=1e-2, betas=(0.9, 0.95), eps=1e-8)
+    groups = torch.tensor([0, 0, 0, 1], dtype=torch.uint8, device=cuda)
     m = torch.zeros_like(p); v = torch.zeros_like(p)
     for step in range(1, 4):
-        pr.grad = g.clone(); opt.step()
-        ops.adamw_step(p, g, m, v, 1e-2, 0.9, 0.95, 1e-8, 0.1, step)
-        assert _rel(p, pr.detach()) < 1e-5
+        g = g0.clone()
+        pr_decay.grad = g[:3072].clone(); pr_nodecay.grad = g[3072:].clone(); opt.step()
+        ops.adamw_flat(p, None, g, m, v, groups, 1e-2, 0.9, 0.95, 1e-8, 0.1, step)
+        assert _rel(p, torch.cat([pr_decay, pr_nodecay]).detach()) < 1e-6
+        assert g.abs().sum().item() == 0                         # gradient buffer zeroed by the same launch
+
+
+def test_adamw_flat_clip_on_device(ops, cuda):
+    """the clip factor min(1, max_norm / (||g|| * scale + 1e-6)) is derived on the device from sum(g^2)"""
+    torch.manual_seed(12)
+    n = 8192
+    p = torch.randn(n, device=cuda); g = torch.randn_like(p) * 3
+    pr = p.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([pr], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0)
+    pr.grad = g.clone() * 0.5                                     # grad_scale = 1 / world = 0.5
+    torch.nn.utils.clip_grad_norm_([pr], 1.0)
+    opt.step()
+    nsq = torch.zeros(1, device=cuda); ops.sumsq(g, nsq)
+    assert abs(nsq.item() - g.double().pow(2).sum().item()) < 1e-4 * nsq.item()
+    m = torch.zeros_like(p); v = torch.zeros_like(p)
+    ops.adamw_flat(p, None, g, m, v, None, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, grad_scale=0.5, norm_sq=nsq, max_norm=1.0)
+    assert _rel(p, pr.detach()) < 1e-6
+    assert _rel(m, opt.state[pr]["exp_avg"]) < 1e-5
+
+
+def test_master_split_join_exact(ops, cuda):
+    """(bf16 weight, int16 low half) is an EXACT encoding of the fp32 master; the bf16 half is its round-to-nearest"""
+    torch.manual_seed(13)
+    x = torch.cat([torch.randn(100000, device=cuda) * 0.02, torch.tensor([0.0, -0.0, 1.0, -1.0, 3.0e38, -3.0e38, 1e-40,
+                                                                           float("inf")], device=cuda)])
+    # exact ties (low half == 0x8000) in both directions
+    ties = torch.tensor([0x3F808000, 0x3F818000, 0xBF808000], dtype=torch.int64, device=cuda).to(torch.int32).view(torch.float32)
+    x = torch.cat([x, ties])
+    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=cuda); lo = torch.empty(x.shape, dtype=torch.int16, device=cuda)
+    ops.master_split(x, hi, lo)
+    back = ops.master_join(hi, lo)
+    assert torch.equal(back.view(torch.int32), x.view(torch.int32))
+    rtn = x.bfloat16()
+    differ = (hi.view(torch.int16) != rtn.view(torch.int16))
+    assert differ.sum().item() <= 2                       # only exact ties round the other way (away from zero vs to even)
+    fin = torch.isfinite(x)
+    assert (hi.float() - x)[fin].abs().le((rtn.float() - x)[fin].abs()).all()
+
+
+def test_adamw_flat_bf16_master_weights_lr1e5(ops, cuda):
+    """The reference recipe's optimizer numerics (mantis/train/scripts/train_mllava.sh:148,162 --bf16 True --learning_rate 1e-5,
+    zero3.json bf16.enabled => fp32 master weights): 50 AdamW steps at lr 1e-5 on bf16 weights of typical magnitude.  Updating
+    bf16 in place would leave almost every weight where it started (|w| ~ 0.02 has ulp 1.2e-4 >> 1e-5); with the split master the
+    result equals torch.optim.AdamW run on fp32 masters, and the bf16 weights are the rounding of those masters."""
+    torch.manual_seed(14)
+    n = 1 << 16
+    w0 = (torch.randn(n, device=cuda) * 0.02).bfloat16()
+    p = w0.clone(); lo = torch.zeros(n, dtype=torch.int16, device=cuda)
+    m = torch.zeros(n, device=cuda); v = torch.zeros(n, device=cuda)
+    master = w0.float().clone().requires_grad_(True)
+    opt = torch.optim.AdamW([master], lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0)
+    gen = torch.Generator(device=cuda).manual_seed(5)
+    drift = torch.randn(n, device=cuda, generator=gen) * 1e-3          # a consistent direction + noise, like real gradients
+    for step in range(1, 51):
+        g = drift + torch.randn(n, device=cuda, generator=gen) * 1e-3
+        master.grad = g.clone(); opt.step()
+        gb = g.clone()
+        ops.adamw_flat(p, lo, gb, m, v, None, 1e-5, 0.9, 0.999, 1e-8, 0.0, step)
+    ours = ops.master_join(p, lo)
+    assert _rel(ours, master.detach()) < 1e-6
+    assert (ours - master.detach()).abs().max().item() < 1e-7
+    moved = (ours != w0.float()).float().mean().item()
+    assert moved > 0.99, moved                                        # the fp32 masters all moved ...
+    same_as_rtn = (p.view(torch.int16) == master.detach().bfloat16().view(torch.int16)).float().mean().item()
+    assert same_as_rtn > 0.999, same_as_rtn                           # ... the bf16 weights are their rounding ...
+    moved_bf16 = (p != w0).float().mean().item()
+    assert moved_bf16 > 0.25, moved_bf16                              # ... and a good part of those crossed a bf16 step too
+    with pytest.raises(ValueError):
+        ops.adamw_flat(p, None, g, m, v, None, 1e-5, 0.9, 0.999, 1e-8, 0.0, 1)       # bf16 without low halves: refused
+
+
+@pytest.mark.parametrize("shape", [(7864, 4096, 1024), (300, 200, 512), (640, 1152, 4304)])
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_gemm_fp32_accumulate_output(ops, cuda, shape, accumulate):
+    """wgrad into the fp32 main gradient: C32 (+)= dy^T x with bf16 operands, fp32 all the way to memory"""
+    torch.manual_seed(15)
+    M, N, K = shape                       # tokens, out features, in features
+    dy = (torch.randn(M, N, device=cuda) * 0.5).bfloat16(); x = (torch.randn(M, K, device=cuda) * 0.5).bfloat16()
+    c0 = torch.randn(N, K, device=cuda) * 50
+    c = c0.clone()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = dy.float().t() @ x.float() + (c0 if accumulate else 0)
+    ops.gemm(dy, x, trans_a=True, trans_b=False, addend=c if accumulate else None, out=c)
+    assert c.dtype == torch.float32
+    assert (c - ref).abs().max().item() <= 2e-5 * ref.abs().max().item() + 1e-4     # fp32, not bf16, resolution

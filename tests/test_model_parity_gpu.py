@@ -220,13 +220,10 @@ def test_batched_greedy_with_left_padding_and_uneven_images(cuda):
 
 def test_decode_engine_bitexact_with_and_without_pdl(cuda, tmp_path):
     """programmatic dependent launch only changes WHEN the kernels of a decode step become resident, never what they read:
-    12 native decode steps give bit-identical logits with MB200_PDL=1 (default) and MB200_PDL=0.
-    Written after the round's GPU budget was spent, so it is opt-in (MB200_RUN_PDL_PROBE=1) until it has run once on a B200."""
+    12 native decode steps give bit-identical logits with MB200_PDL=1 (default) and MB200_PDL=0."""
     import os
     import subprocess
     import sys
-    if os.environ.get("MB200_RUN_PDL_PROBE") != "1":
-        pytest.skip("opt-in: set MB200_RUN_PDL_PROBE=1")
     probe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "pdl_probe.py")
     outs = []
     for flag in ("1", "0"):

@@ -24,8 +24,35 @@ def test_fused_wgrad_accumulation_matches_autograd(cuda, dtype):
         tr.micro_step(b); tr.micro_step(b)
         grads.append(tr.flat_grad.clone())
     tol = 1e-5 if dtype == torch.float32 else 2e-2
+    assert grads[0].dtype == torch.float32                    # the main gradient accumulates in fp32 whatever the model dtype
     assert rel_err(grads[1], grads[0]) < tol
     assert grads[0].abs().sum() > 0
+
+
+def test_bf16_training_at_reference_lr_moves_the_weights(cuda):
+    """bf16 model, lr 1e-5 (the reference recipe): after 10 steps through B200Trainer every trainable tensor's fp32 master has
+    moved, the bf16 weights are the rounding of the masters, and the optimizer checkpoint carries the masters."""
+    from mantis_b200.train import B200Trainer
+    fx = load_fixture("llava_siglip_full.pt")
+    model = load_model(fx, torch.bfloat16, cuda).train()
+    tr = B200Trainer(model, lr=1e-5, grad_accum=1, max_grad_norm=1.0)
+    before = [tr.state.master(i).clone() for i in range(len(tr.params))]
+    b = _batch(fx, cuda, torch.bfloat16)
+    for _ in range(10):
+        loss = tr.train_step([b])
+    assert torch.isfinite(loss)
+    moved = []
+    for i, p in enumerate(tr.params):
+        now = tr.state.master(i)
+        moved.append((now != before[i]).float().mean().item())
+        assert torch.equal(p.detach().view(torch.int16), tr.state.view(tr.state.P, i).view(torch.int16))
+        # bf16 weight == round-to-nearest of its master (exact ties aside)
+        assert (p.detach().view(torch.int16) == now.bfloat16().view(torch.int16)).float().mean().item() > 0.999
+    assert min(moved) > 0.9 and sum(moved) / len(moved) > 0.99, moved
+    assert tr.flat_grad.abs().sum().item() == 0                 # zeroed by the optimizer launch
+    sd = tr.state_dict()
+    assert all(m.dtype == torch.float32 for m in sd["master_params"])
+    assert 0 < tr.grad_norm() < 1e4
 
 
 def test_training_reduces_loss(cuda):

@@ -34,17 +34,21 @@ def test_trainer_schedule_and_state_roundtrip():
     assert tr.current_lr() == pytest.approx(2e-5)
     tr.step_count = 100
     assert tr.current_lr() == pytest.approx(0.0, abs=1e-12)
-    # all gradients live in one flat buffer
-    assert all(p.grad.data_ptr() >= tr.flat_grad.data_ptr() for p in tr.params)
+    # weights, gradients and moments live in flat buffers; every slice starts on a 1024-element boundary
+    st = tr.state
+    assert all(p.data_ptr() == st.P.data_ptr() + 4 * o and o % 1024 == 0 for p, o in zip(tr.params, st.offsets))
+    assert st.groups.tolist() == [0, 1, 0, 1]                 # weight, bias, weight, bias: biases take no weight decay
     tr.step_count = 17
-    for m, v in zip(tr.m, tr.v):
-        m.normal_(); v.uniform_()
+    st.M.normal_(); st.V.uniform_()
     state = tr.state_dict()
     tr2 = B200Trainer(torch.nn.Sequential(torch.nn.Linear(8, 8), torch.nn.Linear(8, 4)), freeze_vision=False,
                       fused_wgrad_accum=False, overlap_allreduce=False)
     tr2.load_state_dict(state)
     assert tr2.step_count == 17 and tr2.lr == 2e-5 and tr2.lr_schedule == "cosine" and tr2.warmup_steps == 3
-    assert all(torch.equal(a, b) for a, b in zip(tr.m, tr2.m)) and all(torch.equal(a, b) for a, b in zip(tr.v, tr2.v))
+    for i in range(len(tr.params)):
+        assert torch.equal(st.view(st.M, i), tr2.state.view(tr2.state.M, i))
+        assert torch.equal(st.view(st.V, i), tr2.state.view(tr2.state.V, i))
+        assert torch.equal(tr.params[i], tr2.params[i])       # the fp32 master weights travel with the optimizer state
     assert tr2.current_lr() == tr.current_lr()
     with pytest.raises(ValueError):
         B200Trainer(torch.nn.Linear(4, 4), freeze_vision=False, fused_wgrad_accum=False,
