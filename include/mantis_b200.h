@@ -153,7 +153,9 @@ int mb200_gemm_bf16_2cta(const void* A, const void* B, void* C, const void* bias
 
 /* ---- attention: softmax(q k^T * scale + causal/padding mask) v, GQA (llama/modeling_llama.py:199-289;
  *      siglip/modeling_siglip.py:229-303; idefics2 perceiver :812-910).  q/o [B,Sq,H,hd], k/v [B,Sk,Hkv,hd];
- *      strides = {q_b,q_s,q_h, k_b,k_s,k_h, v_b,v_s,v_h, o_b,o_s,o_h} in elements -------------------------- */
+ *      strides = {q_b,q_s,q_h, k_b,k_s,k_h, v_b,v_s,v_h, o_b,o_s,o_h} in elements.
+ *      `causal` of the generic kernels: 0 = none, 1 = causal (key j visible to query i iff j <= i + Sk - Sq), W > 1 = causal
+ *      with Mistral's sliding window of W keys (additionally (i + Sk - Sq) - j < W; mistral/modeling_mistral.py) ----------- */
 int mb200_attn_generic_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Hkv,
                            int Sq, int Sk, int hd, const long long* strides, float scale, int causal,
                            const int64_t* kmask, long long kmask_sb, int dtype, void* stream);

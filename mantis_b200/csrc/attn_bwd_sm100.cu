@@ -527,14 +527,10 @@ int mb200_attn_bwd_bf16(const void* q, const void* k, const void* v, const void*
   p.B = B; p.H = H; p.Hkv = Hkv; p.Sq = Sq; p.Sk = Sk; p.scale = scale; p.scale_log2 = scale * LOG2E; p.causal = causal;
   constexpr int smem_dkv = 2 * FULL_TILE + 2 * QS * SUB_TILE + 1024 + 256 + QS * 512;
   constexpr int smem_dq = 2 * FULL_TILE + 2 * QSQ * SUB_TILE + 1024 + 256;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(attn_bwd_dkv_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dkv) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_bwd_dq_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq) != cudaSuccess) {
-      mb200_set_last_error("cudaFuncSetAttribute(attn bwd smem) failed"); return -EIO;
-    }
-    configured = true;
-  }
+  static const bool cfg_ok =        // thread-safe one-time setup
+      cudaFuncSetAttribute(attn_bwd_dkv_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dkv) == cudaSuccess &&
+      cudaFuncSetAttribute(attn_bwd_dq_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq) == cudaSuccess;
+  if (!cfg_ok) { mb200_set_last_error("cudaFuncSetAttribute(attn bwd smem) failed"); return -EIO; }
   dim3 gkv((Sk + 127) / 128, Hkv, B), gq((Sq + 127) / 128, H, B);
   attn_bwd_dkv_sm100_kernel<<<gkv, NTHREADS, smem_dkv, st>>>(tmQ64, tmDO64, tmK, tmV, p);
   attn_bwd_dq_sm100_kernel<<<gq, DQ_THREADS, smem_dq, st>>>(tmQ, tmDO, tmK64, tmV64, p);

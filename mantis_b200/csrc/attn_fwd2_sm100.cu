@@ -278,13 +278,9 @@ extern "C" int mb200_attn_fwd2_bf16(const void* q, const void* k, const void* v,
   p.B = B; p.H = H; p.Hkv = Hkv; p.Sq = Sq; p.Sk = Sk;
   p.scale_log2 = scale * 1.44269504088896340736f; p.causal = causal;
   constexpr int smem = 6 * TILE_BYTES + 1024 + 256;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(attn_fwd2_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
-      mb200_set_last_error("cudaFuncSetAttribute(attn fwd2 smem) failed"); return -EIO;
-    }
-    configured = true;
-  }
+  // thread-safe one-time setup (C++11 static initialisation): generate() may be driven from a worker thread
+  static const cudaError_t cfg = cudaFuncSetAttribute(attn_fwd2_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (cfg != cudaSuccess) { mb200_set_last_error("cudaFuncSetAttribute(attn fwd2 smem) failed"); return -EIO; }
   const int n_qt = (Sq + BQ - 1) / BQ;
   dim3 grid((n_qt + 1) / 2, H, B);
   attn_fwd2_sm100_kernel<<<grid, F2_THREADS, smem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);

@@ -21,6 +21,8 @@ struct AttnP {
   int B, H, Hkv, Sq, Sk, hd;
   long long q_sb, q_ss, q_sh, k_sb, k_ss, k_sh, v_sb, v_ss, v_sh, o_sb, o_ss, o_sh;
   float scale; int causal;    // causal: key j visible to query i iff j <= i + (Sk - Sq)
+  int window;                 // > 0: additionally (i + (Sk - Sq)) - j < window  (Mistral sliding-window attention,
+                              //      transformers mistral/modeling_mistral.py sliding_window_overlay: kv_idx > q_idx - window)
   const int64_t* kmask;       // [B, Sk] or null
   long long kmask_sb;
 };
@@ -68,7 +70,7 @@ attn_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __res
     __syncthreads();
     if (!row_ok) continue;
     const int kj = k0 + lane;
-    bool vis = kvalid[lane] && (!p.causal || kj <= qi + off);
+    bool vis = kvalid[lane] && (!p.causal || (kj <= qi + off && (p.window <= 0 || qi + off - kj < p.window)));
     float s = -INFINITY;
     if (vis) {
       s = 0.f;
@@ -153,7 +155,7 @@ attn_bwd_dq_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __
     __syncthreads();
     if (!row_ok || L == -INFINITY) continue;
     const int kj = k0 + lane;
-    const bool vis = kvalid[lane] && (!p.causal || kj <= qi + off);
+    const bool vis = kvalid[lane] && (!p.causal || (kj <= qi + off && (p.window <= 0 || qi + off - kj < p.window)));
     float ds = 0.f;
     if (vis) {
       float s = 0.f, dp = 0.f;
@@ -225,7 +227,7 @@ attn_bwd_dkv_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* _
       __syncthreads();
       if (!kvis) continue;
       const int qi = q0 + lane;
-      const bool vis = (qi < p.Sq) && (Ls[lane] != -INFINITY) && (!p.causal || kj <= qi + off);
+      const bool vis = (qi < p.Sq) && (Ls[lane] != -INFINITY) && (!p.causal || (kj <= qi + off && (p.window <= 0 || qi + off - kj < p.window)));
       float pij = 0.f, ds = 0.f;
       if (vis) {
         float s = 0.f, dp = 0.f;
@@ -264,7 +266,8 @@ inline AttnP make_params(int B, int H, int Hkv, int Sq, int Sk, int hd, const lo
   p.B = B; p.H = H; p.Hkv = Hkv; p.Sq = Sq; p.Sk = Sk; p.hd = hd;
   p.q_sb = st[0]; p.q_ss = st[1]; p.q_sh = st[2]; p.k_sb = st[3]; p.k_ss = st[4]; p.k_sh = st[5];
   p.v_sb = st[6]; p.v_ss = st[7]; p.v_sh = st[8]; p.o_sb = st[9]; p.o_ss = st[10]; p.o_sh = st[11];
-  p.scale = scale; p.causal = causal; p.kmask = kmask; p.kmask_sb = kmask_sb;
+  // `causal` argument: 0 = none, 1 = causal, W > 1 = causal with a sliding window of W keys
+  p.scale = scale; p.causal = causal != 0; p.window = causal > 1 ? causal : 0; p.kmask = kmask; p.kmask_sb = kmask_sb;
   return p;
 }
 }  // namespace

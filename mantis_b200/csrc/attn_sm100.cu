@@ -361,17 +361,11 @@ int mb200_attn_fwd_bf16(const void* q, const void* k, const void* v, void* o, fl
     p.kbits = (const uint32_t*)kbits_ws; p.kbits_stride = words;
   }
   constexpr int smem = 7 * TILE_BYTES + 1024 + 256 + 1024;
-  static bool configured = false;
-  static int p_tmem = 1;
-  if (!configured) {
-    const char* e = getenv("MB200_ATTN_P_TMEM");
-    if (e) p_tmem = atoi(e);
-    if (cudaFuncSetAttribute(attn_fwd_sm100_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_fwd_sm100_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
-      mb200_set_last_error("cudaFuncSetAttribute(attn smem) failed"); return -EIO;
-    }
-    configured = true;
-  }
+  static const int p_tmem = [] { const char* e = getenv("MB200_ATTN_P_TMEM"); return e ? atoi(e) : 1; }();   // thread-safe once
+  static const bool cfg_ok =
+      cudaFuncSetAttribute(attn_fwd_sm100_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess &&
+      cudaFuncSetAttribute(attn_fwd_sm100_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess;
+  if (!cfg_ok) { mb200_set_last_error("cudaFuncSetAttribute(attn smem) failed"); return -EIO; }
   dim3 grid((Sq + BQ - 1) / BQ, H, B);
   if (p_tmem) attn_fwd_sm100_kernel<true><<<grid, FWD_THREADS, smem, st>>>(tmQ, tmK, tmV, p);
   else        attn_fwd_sm100_kernel<false><<<grid, FWD_THREADS, smem, st>>>(tmQ, tmK, tmV, p);

@@ -141,12 +141,11 @@ static inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 bl
 }
 
 static inline int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0; cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
+  static const int n = [] {
+    int dev = 0, v = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v <= 0 ? 148 : v;
+  }();
   return n;
 }
 

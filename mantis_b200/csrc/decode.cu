@@ -1015,12 +1015,12 @@ static inline int skinny_grid(int ngroups, int ctas_per_sm) {
 template <int MT, int MODE>
 int launch_rows(const void* X, const SkinnySeg& sg, const void* bias, const void* addend, int M, int K, long long ldx,
                 long long ldw, long long ld_add, cudaStream_t st, const void* gamma = nullptr, float eps = 0.f) {
-  static int occ = 0;
-  if (!occ) {
+  static const int occ = [] {             // thread-safe one-time setup
+    int o = 0;
     cudaFuncSetAttribute(skinny_rows_kernel<MT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, skinny_rows_kernel<MT, MODE>, SK_THREADS, RS_SMEM);
-    if (occ < 1) occ = 1;
-  }
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, skinny_rows_kernel<MT, MODE>, SK_THREADS, RS_SMEM);
+    return o < 1 ? 1 : o;
+  }();
   const int Ntot = (MODE == 1) ? sg.N[0] : (sg.N[0] + sg.N[1] + sg.N[2]);
   const int ngroups = (Ntot + 7) / 8;
   mb::launch_ex(skinny_rows_kernel<MT, MODE>, dim3(skinny_grid(ngroups, occ)), dim3(SK_THREADS), RS_SMEM, st, mb::pdl_mode() != 0,
@@ -1030,12 +1030,12 @@ int launch_rows(const void* X, const SkinnySeg& sg, const void* bias, const void
 template <int MODE>
 int launch_ring(const void* X, const SkinnySeg& sg, const void* bias, const void* addend, int M, int K, long long ldx,
                 long long ldw, long long ld_add, cudaStream_t st) {
-  static int occ = 0;
-  if (!occ) {
+  static const int occ = [] {
+    int o = 0;
     cudaFuncSetAttribute(skinny_ring_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM_TOTAL);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, skinny_ring_kernel<MODE>, SK_THREADS, SK_SMEM_TOTAL);
-    if (occ < 1) occ = 1;
-  }
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, skinny_ring_kernel<MODE>, SK_THREADS, SK_SMEM_TOTAL);
+    return o < 1 ? 1 : o;
+  }();
   const int Ntot = (MODE == 1) ? sg.N[0] : (sg.N[0] + sg.N[1] + sg.N[2]);
   const int ngroups = (Ntot + 8 * SK_RG - 1) / (8 * SK_RG);
   mb::launch_ex(skinny_ring_kernel<MODE>, dim3(skinny_grid(ngroups, occ)), dim3(SK_THREADS), SK_SMEM_TOTAL, st, mb::pdl_mode() != 0,
@@ -1043,8 +1043,7 @@ int launch_ring(const void* X, const SkinnySeg& sg, const void* bias, const void
   return 0;
 }
 static int skinny_ring_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("MB200_SKINNY_RING"); v = (e && e[0] == '0') ? 0 : 1; }
+  static const int v = [] { const char* e = getenv("MB200_SKINNY_RING"); return (e && e[0] == '0') ? 0 : 1; }();
   return v;
 }
 // can the row-stage kernel (the only one with the fused RMSNorm prologue) take this problem?
@@ -1245,20 +1244,16 @@ static int decode_attn_launch(DecP& p, void* o, long long o_sb, long long o_sh, 
   p.chunk = ((p.ctx + p.splits - 1) / p.splits + DKT - 1) / DKT * DKT;      // tile-aligned chunks (see the kernel)
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(p.splits, p.Hkv, p.B);
-  static bool configured = false;
-  if (!configured) {
+  static const int use_mma = [] {         // thread-safe one-time setup of every decode-attention variant
     cudaFuncSetAttribute(decode_attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem<1>());
     cudaFuncSetAttribute(decode_attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem<2>());
     cudaFuncSetAttribute(decode_attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem<4>());
     cudaFuncSetAttribute(decode_attn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem<8>());
-    configured = true;
-  }
-  const bool pdl = mb::pdl_mode() != 0;
-  static int use_mma = -1;
-  if (use_mma < 0) {
-    const char* e = getenv("MB200_DECODE_ATTN_MMA"); use_mma = (e && e[0] == '0') ? 0 : 1;
     cudaFuncSetAttribute(decode_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM);
-  }
+    const char* e = getenv("MB200_DECODE_ATTN_MMA");
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
+  const bool pdl = mb::pdl_mode() != 0;
   if (use_mma && G <= 8) mb::launch_ex(decode_attn_mma_kernel, grid, dim3(DWARPS * 32), DM_SMEM, st, pdl, p, G);
   else if (G == 1) mb::launch_ex(decode_attn_kernel<1>, grid, dim3(DWARPS * 32), dec_smem<1>(), st, pdl, p);
   else if (G == 2) mb::launch_ex(decode_attn_kernel<2>, grid, dim3(DWARPS * 32), dec_smem<2>(), st, pdl, p);

@@ -164,9 +164,10 @@ int mb200_llama_decode_step(const int* dims, const float* fparm, const void* con
   const float scale = 1.0f / sqrtf((float)hd);
   const int HD = H * hd, KD = Hkv * hd;
 
-  static int pdl = -1, fuse_norm = -1;
-  if (pdl < 0) { const char* e = getenv("MB200_PDL"); pdl = (e && e[0] == '0') ? 0 : 1; }
-  if (fuse_norm < 0) { const char* e = getenv("MB200_DECODE_FUSE_NORM"); fuse_norm = (e && e[0] == '0') ? 0 : 1; }
+  // process-wide switches, read once (thread-safe static initialisation); the launch mode itself is scoped to this call on
+  // the calling thread (PdlScope), so a decode step issued from a worker thread behaves exactly like one from the main thread
+  static const int pdl = [] { const char* e = getenv("MB200_PDL"); return (e && e[0] == '0') ? 0 : 1; }();
+  static const int fuse_norm = [] { const char* e = getenv("MB200_DECODE_FUSE_NORM"); return (e && e[0] == '0') ? 0 : 1; }();
   TRY(mb200_embedding_fwd(ids, embed, x, B, D, V, dt, stream));      // plain launch: its inputs come from torch kernels
   PdlScope scope(pdl);
   for (int l = 0; l < L; ++l) {

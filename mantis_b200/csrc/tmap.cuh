@@ -14,13 +14,13 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static inline PFN_encodeTiled get_encode() {
-  static PFN_encodeTiled fn = nullptr;
-  if (!fn) {
+  static const PFN_encodeTiled fn = [] {
     void* p = nullptr; cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
         qres == cudaDriverEntryPointSuccess)
-      fn = (PFN_encodeTiled)p;
-  }
+      return (PFN_encodeTiled)p;
+    return (PFN_encodeTiled) nullptr;
+  }();
   return fn;
 }
 

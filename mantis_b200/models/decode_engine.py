@@ -98,9 +98,13 @@ def native_decode_logits(decoder, lm_head, cache, input_ids, x_dtype, attention_
         cache._engine = eng
     ctx = cache.get_seq_length()
     kbits = None
+    if attention_mask is not None and (attention_mask.dim() != 2 or attention_mask.shape[1] != ctx + 1):
+        return None
+    window = getattr(decoder.config, "sliding_window", None)
+    if window and ctx + 1 > window:                       # Mistral: keys that slid out of the window are masked
+        from .llama import window_key_mask
+        attention_mask = window_key_mask(attention_mask, ctx + 1, window, input_ids.shape[0], input_ids.device)
     if attention_mask is not None:
-        if attention_mask.dim() != 2 or attention_mask.shape[1] != ctx + 1:
-            return None
         kbits = ops.kmask_bits(attention_mask)
     if position_ids is None:
         position_ids = torch.full((input_ids.shape[0], 1), ctx, dtype=torch.int64, device=input_ids.device)

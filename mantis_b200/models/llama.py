@@ -42,6 +42,15 @@ def _rope_params(config):
     return float(theta), rs
 
 
+def window_key_mask(key_mask, total, window, batch, device):
+    """decode step over a context longer than the sliding window: the new token (index total-1) sees key j iff
+    (total-1) - j < window, so the keys before total - window are masked out of the (optional) padding mask"""
+    keep = torch.arange(total, device=device) >= (total - window)
+    if key_mask is None:
+        return keep.to(torch.int64).unsqueeze(0).expand(batch, total).contiguous()
+    return key_mask * keep.to(key_mask.dtype).unsqueeze(0)
+
+
 class B200Attention(nn.Module):
     def __init__(self, config, layer_idx):
         super().__init__()
@@ -56,6 +65,9 @@ class B200Attention(nn.Module):
         self.v_proj = B200Linear(self.hidden_size, self.num_kv_heads * self.head_dim, bias=bias)
         self.o_proj = B200Linear(self.num_heads * self.head_dim, self.hidden_size, bias=bias)
         self.scaling = self.head_dim ** -0.5
+        # Mistral (Idefics2's text model): key j is visible to query i iff i - j < sliding_window
+        # (transformers mistral/modeling_mistral.py); LLaMA configs carry no such field
+        self.sliding_window = getattr(config, "sliding_window", None)
 
     def forward(self, x, residual, position_ids, inv_freq, rope_scale, key_mask, cache, kbits=None, rope_tab=None,
                 segs=None):
@@ -78,7 +90,7 @@ class B200Attention(nn.Module):
         if segs is not None:                   # packed sequences: block-diagonal causal attention, one launch per segment
             o = ops.attention_varlen(q, k, v, segs, kmask=key_mask, scale=self.scaling)
         else:
-            o = ops.attention(q, k, v, causal=True, kmask=key_mask, scale=self.scaling)
+            o = ops.attention(q, k, v, causal=True, kmask=key_mask, scale=self.scaling, window=self.sliding_window)
         return self.o_proj(o.view(B, S, self.num_heads * self.head_dim), residual=residual)
 
 
@@ -126,7 +138,8 @@ class B200DecoderPreTrainedModel(PreTrainedModel):
 
 
 class B200DecoderModel(B200DecoderPreTrainedModel):
-    """== LlamaModel / MistralModel (sliding window is not applied: S << sliding_window on this path)."""
+    """== LlamaModel / MistralModel.  Mistral's sliding window is honoured once the context exceeds it: prefill through the
+    window-aware attention kernel, single-token decode by masking the keys that have slid out (`window_key_mask`)."""
 
     def __init__(self, config):
         super().__init__(config)
@@ -201,6 +214,9 @@ class B200DecoderModel(B200DecoderPreTrainedModel):
             key_mask = attention_mask
             if key_mask.shape[1] != past + S:
                 raise ValueError(f"attention_mask length {key_mask.shape[1]} != past({past}) + seq({S})")
+        window = getattr(self.config, "sliding_window", None)
+        if window and S == 1 and cache is not None and past + 1 > window:
+            key_mask = window_key_mask(key_mask, past + 1, window, B, inputs_embeds.device)
         inv_freq, rope_scale = self.rope_tables(inputs_embeds.device)
         x = inputs_embeds
         kbits = None

@@ -1,7 +1,8 @@
-"""chat_mllava: one-call multi-image chat on top of generate().
+"""chat_mllava / chat_mllava_stream: one-call multi-image chat on top of generate().
 
-Behavioural mirror of mantis/models/mllava/utils.py:10-97 (template choice by language-model name, history bookkeeping,
-image loading, prompt -> processor -> generate -> decode), written independently for this package.
+Behavioural mirror of mantis/models/mllava/utils.py:10-97 and :100-186 (template choice by language-model name, history
+bookkeeping, image loading, prompt -> processor -> generate -> decode; the streaming variant runs generate() on a worker
+thread and yields the growing reply), written independently for this package.
 """
 from typing import List, Optional, Tuple, Union
 
@@ -66,6 +67,15 @@ def _to_device(inputs, device):
 def chat_mllava(text: str, images: List[Union["PIL.Image.Image", str]], model, processor, max_input_length: int = None,
                 history: List[dict] = None, **kwargs) -> Tuple[str, List[dict]]:
     """Returns (generated_text, history); `history` items are {"role": ..., "text": ...} like the reference's."""
+    inputs, history = _prepare_chat(text, images, model, processor, max_input_length, history, kwargs, convert_rgb=True)
+    prompt_len = inputs["input_ids"].shape[-1]
+    new_ids = model.generate(**inputs, **kwargs)[0][prompt_len:]
+    reply = processor.decode(new_ids, skip_special_tokens=True)
+    history[-1]["text"] = reply
+    return reply, history
+
+
+def _prepare_chat(text, images, model, processor, max_input_length, history, kwargs, convert_rgb):
     conv, terminators = _pick_template(model, processor)
     kwargs["eos_token_id"] = terminators
     history = _extend_dialogue(conv, text, history)
@@ -73,12 +83,53 @@ def chat_mllava(text: str, images: List[Union["PIL.Image.Image", str]], model, p
     assert tail_role == conv.roles[1] and tail_text == "", "Format check"
     if images:
         import PIL.Image
-        images[:] = [PIL.Image.open(im).convert("RGB") if isinstance(im, str) else im for im in images]
+        if convert_rgb:
+            images[:] = [PIL.Image.open(im).convert("RGB") if isinstance(im, str) else im for im in images]
+        else:                                   # the streaming variant opens files without converting (ref :166-169)
+            images[:] = [PIL.Image.open(im) if isinstance(im, str) else im for im in images]
     inputs = processor(images=images, text=conv.get_prompt(), return_tensors="pt", truncation=True,
                        max_length=max_input_length)
-    inputs = _to_device(inputs, model.device)
-    prompt_len = inputs["input_ids"].shape[-1]
-    new_ids = model.generate(**inputs, **kwargs)[0][prompt_len:]
-    reply = processor.decode(new_ids, skip_special_tokens=True)
-    history[-1]["text"] = reply
-    return reply, history
+    return _to_device(inputs, model.device), history
+
+
+def chat_mllava_stream(text: str, images: List[Union["PIL.Image.Image", str]], model, processor,
+                       max_input_length: int = None, history: List[dict] = None, **kwargs):
+    """Generator version of chat_mllava (ref: mantis/models/mllava/utils.py:100-186): `model.generate` runs on a worker
+    thread feeding a transformers.TextIteratorStreamer; every decoded piece is appended to the last history entry and
+    (reply_so_far, history) is yielded.
+
+    The worker thread drives the CUDA kernels through the C ABI: the library keeps no per-thread state that changes results
+    (one-time kernel attributes are set under C++ static-initialisation guards, the launch mode of the decode engine is scoped
+    to the call), but a new thread starts on device 0 and on the default stream -- so the worker first binds the model's device
+    and orders itself after the caller's stream."""
+    from threading import Thread
+
+    from transformers import TextIteratorStreamer
+    inputs, history = _prepare_chat(text, images, model, processor, max_input_length, history, kwargs, convert_rgb=False)
+    streamer = TextIteratorStreamer(processor, skip_prompt=True, skip_special_tokens=True)
+    kwargs["streamer"] = streamer
+    inputs.update(kwargs)
+    device = model.device
+    ready = torch.cuda.Event() if device.type == "cuda" else None
+    if ready is not None:
+        ready.record(torch.cuda.current_stream(device))
+    failure = []
+
+    def work():
+        try:
+            if ready is not None:
+                torch.cuda.set_device(device)
+                torch.cuda.current_stream(device).wait_event(ready)
+            model.generate(**inputs)
+        except BaseException as e:             # surface worker failures to the consumer instead of hanging the iterator
+            failure.append(e)
+            streamer.end()
+
+    thread = Thread(target=work, daemon=True)
+    thread.start()
+    for piece in streamer:
+        history[-1]["text"] += piece
+        yield history[-1]["text"], history
+    thread.join()
+    if failure:
+        raise failure[0]

@@ -511,9 +511,18 @@ def _attn_fast_ok(q, k, v, hd, Sq, Sk):
     return True
 
 
-def attention_fwd(q, k, v, causal, kmask, scale, return_kbits=False, out=None):
+def _window_code(causal, window, Sk):
+    """the kernels' `causal` argument: 0 none, 1 causal, W > 1 causal with a sliding window of W keys (only when it bites)"""
+    if window is not None and causal and Sk > int(window) > 1:
+        return int(window)
+    return int(bool(causal))
+
+
+def attention_fwd(q, k, v, causal, kmask, scale, return_kbits=False, out=None, window=None):
     """q [B,Sq,H,hd], k/v [B,Sk,Hkv,hd] (hd contiguous). Returns (o [B,Sq,H,hd] contiguous, lse [B,H,Sq] fp32).
-    `out`: optional contiguous destination for o (a slice of a packed output, see attention_varlen)."""
+    `out`: optional contiguous destination for o (a slice of a packed output, see attention_varlen).
+    `window`: Mistral sliding window (key j visible to query i iff i - j < window); contexts longer than the window run on
+    the generic kernel."""
     _need_cuda(q, k, v)
     B, Sq, H, hd = q.shape
     Sk, Hkv = k.shape[1], k.shape[2]
@@ -525,7 +534,8 @@ def attention_fwd(q, k, v, causal, kmask, scale, return_kbits=False, out=None):
         kmask = kmask.contiguous().to(torch.int64)
         assert kmask.shape == (B, Sk)
     st = _strides12(q, k, v, o)
-    if _attn_fast_ok(q, k, v, hd, Sq, Sk):
+    code = _window_code(causal, window, Sk)
+    if code <= 1 and _attn_fast_ok(q, k, v, hd, Sq, Sk):
         kbits = None
         if ATTN_FWD2 and Sq > 128:
             if kmask is not None:
@@ -543,7 +553,7 @@ def attention_fwd(q, k, v, causal, kmask, scale, return_kbits=False, out=None):
             return o, lse, kbits, True
         return o, lse
     _call("mb200_attn_generic_fwd", _p(q), _p(k), _p(v), _p(o), _p(lse), B, H, Hkv, Sq, Sk, hd, st, float(scale),
-          int(causal), _p(kmask), Sk if kmask is not None else 0, _dt(q), _st())
+          code, _p(kmask), Sk if kmask is not None else 0, _dt(q), _st())
     if return_kbits:
         return o, lse, None, False
     return o, lse
@@ -596,7 +606,7 @@ def decode_attention_paged(q, cache, layer_idx, ctx, kmask, scale, kbits=None):
     return o
 
 
-def attention_bwd(q, k, v, o, do, lse, causal, kmask, scale, kbits=None, fast=False, out=None):
+def attention_bwd(q, k, v, o, do, lse, causal, kmask, scale, kbits=None, fast=False, out=None, window=None):
     """`out`: optional (dq, dk, dv) contiguous destinations (slices of packed gradients, see attention_varlen)."""
     B, Sq, H, hd = q.shape
     Sk, Hkv = k.shape[1], k.shape[2]
@@ -621,8 +631,8 @@ def attention_bwd(q, k, v, o, do, lse, causal, kmask, scale, kbits=None, fast=Fa
     delta = torch.empty((B, H, Sq), dtype=torch.float32, device=q.device)
     st = _strides12(qc, kc, vc, o)
     _call("mb200_attn_generic_bwd", _p(qc), _p(kc), _p(vc), _p(o), _p(do), _p(lse), _p(delta), _p(dq), _p(dk), _p(dv),
-          B, H, Hkv, Sq, Sk, hd, st, float(scale), int(causal), _p(kmask), Sk if kmask is not None else 0,
-          _dt(q), _st())
+          B, H, Hkv, Sq, Sk, hd, st, float(scale), _window_code(causal, window, Sk), _p(kmask),
+          Sk if kmask is not None else 0, _dt(q), _st())
     if out is not None:
         out[0].copy_(dq); out[1].copy_(dk); out[2].copy_(dv)
         return out
@@ -631,26 +641,28 @@ def attention_bwd(q, k, v, o, do, lse, causal, kmask, scale, kbits=None, fast=Fa
 
 class _AttentionFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, k, v, causal, kmask, scale):
+    def forward(ctx, q, k, v, causal, kmask, scale, window):
         if kmask is not None:
             kmask = kmask.contiguous().to(torch.int64)
-        o, lse, kbits, fast = attention_fwd(q, k, v, causal, kmask, scale, return_kbits=True)
+        o, lse, kbits, fast = attention_fwd(q, k, v, causal, kmask, scale, return_kbits=True, window=window)
         ctx.save_for_backward(q, k, v, o, lse, kmask, kbits)
-        ctx.causal, ctx.scale, ctx.fast = causal, scale, fast
+        ctx.causal, ctx.scale, ctx.fast, ctx.window = causal, scale, fast, window
         return o
 
     @staticmethod
     def backward(ctx, do):
         q, k, v, o, lse, kmask, kbits = ctx.saved_tensors
-        dq, dk, dv = attention_bwd(q, k, v, o, do, lse, ctx.causal, kmask, ctx.scale, kbits=kbits, fast=ctx.fast)
-        return dq, dk, dv, None, None, None
+        dq, dk, dv = attention_bwd(q, k, v, o, do, lse, ctx.causal, kmask, ctx.scale, kbits=kbits, fast=ctx.fast,
+                                   window=ctx.window)
+        return dq, dk, dv, None, None, None, None
 
 
-def attention(q, k, v, causal=False, kmask=None, scale=None):
-    """softmax(q k^T * scale + mask) v with GQA.  q [B,Sq,H,hd]; k,v [B,Sk,Hkv,hd]; kmask [B,Sk] (non-zero = attend)"""
+def attention(q, k, v, causal=False, kmask=None, scale=None, window=None):
+    """softmax(q k^T * scale + mask) v with GQA.  q [B,Sq,H,hd]; k,v [B,Sk,Hkv,hd]; kmask [B,Sk] (non-zero = attend);
+    window: causal sliding window (Mistral), None = unlimited"""
     if scale is None:
         scale = 1.0 / math.sqrt(q.shape[-1])
-    return _AttentionFn.apply(q, k, v, bool(causal), kmask, float(scale))
+    return _AttentionFn.apply(q, k, v, bool(causal), kmask, float(scale), window)
 
 
 class _VarlenAttentionFn(torch.autograd.Function):

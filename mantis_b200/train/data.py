@@ -3,7 +3,10 @@
 The reference delegates to `MLlavaProcessor._right_pad_inputs_with_attention_mask`, which asserts batch == 1.  This
 collator keeps that contract when given one sample and additionally right-pads real batches (input_ids with the pad id,
 attention_mask with 0, labels with -100, position_ids with 0) so that the B > 1 merge path of the model can be used;
-`pixel_values` stays a python list of per-sample tensors exactly like the reference (modeling_llava.py:431-432 cats it).
+with an MLlavaProcessor `pixel_values` stays a python list of per-sample tensors (modeling_llava.py:431-432 cats it); with
+any other processor (Idefics2/3) the reference's own `_right_pad_inputs_with_attention_mask` (data.py:1392-1532) is followed:
+`pixel_values` [1, N, C, H, W] are concatenated on dim 0, 4-D masks (packed [1,1,q,kv] and `pixel_attention_mask`
+[1,N,H,W]) are zero-padded on their last two dims.
 """
 from typing import Dict, List
 
@@ -42,33 +45,44 @@ class Collator:
         return torch.cat([t, pad], dim=1)
 
     def __call__(self, batch: List[Dict]):
-        if (len(batch) == 1 and "cu_segments" not in batch[0] and self.processor is not None
-                and hasattr(self.processor, "_right_pad_inputs_with_attention_mask")):
+        # no processor, or an MLlavaProcessor: the LLaVA data contract (pixel_values = list of per-sample [n_img, C, H, W]);
+        # any other processor (Idefics2/3): the reference Collator's own padding rules
+        mllava = self.processor is None or hasattr(self.processor, "_right_pad_inputs_with_attention_mask")
+        if len(batch) == 1 and "cu_segments" not in batch[0] and self.processor is not None and mllava:
             return self.processor._right_pad_inputs_with_attention_mask(model_inputs=batch)      # the reference's path
+        packed = any("cu_segments" in b or (isinstance(b.get("attention_mask"), torch.Tensor) and b["attention_mask"].dim() == 4)
+                     for b in batch)
         out = {}
         for k in batch[0].keys():
             vals = [b[k] for b in batch]
-            if "pixel_values" in k:
-                out[k] = [v for v in vals]                       # list of per-sample tensors (None kept, model skips them)
-            elif vals[0] is None:
+            if vals[0] is None:
                 out[k] = None
+            elif "pixel_values" in k and (mllava or isinstance(vals[0], list)):
+                # MLlavaProcessor contract (processing_llava.py / modeling_llava.py:431-432): a python list of per-sample
+                # tensors that the model concatenates itself (None kept, the model skips them)
+                out[k] = [v for v in vals]
             elif k == "cu_segments":                             # packed rows (PackingDataset): renumber the batch row
                 out[k] = [(i, s0, s1) for i, segs in enumerate(vals) for (_, s0, s1) in segs]
-            elif isinstance(vals[0], torch.Tensor) and vals[0].dim() == 4:
-                # packed block-diagonal masks [1, 1, q, kv]: zero-pad both sequence dims (ref: data.py:1441-1474)
-                L = max(v.shape[2] for v in vals)
+            elif "attention_mask" in k and isinstance(vals[0], torch.Tensor) and vals[0].dim() == 4:
+                # ref data.py:1444-1479: zero-pad dim 2 to the batch max and dim 3 to the batch max, independently -- packed
+                # block-diagonal masks [1, 1, q, kv] and Idefics2's pixel_attention_mask [1, N, H, W] both come through here
+                d2 = max(v.shape[2] for v in vals); d3 = max(v.shape[3] for v in vals)
                 padded = []
                 for v in vals:
-                    m = torch.zeros((v.shape[0], v.shape[1], L, L), dtype=v.dtype, device=v.device)
+                    m = torch.zeros((v.shape[0], v.shape[1], d2, d3), dtype=v.dtype, device=v.device)
                     m[:, :, : v.shape[2], : v.shape[3]] = v
                     padded.append(m)
                 out[k] = torch.cat(padded, dim=0)
-            else:
+            elif k == "input_ids" or k == "labels" or "attention_mask" in k or "position_ids" in k:
                 L = max(v.shape[1] for v in vals)
-                if self.max_length is not None:
-                    L = min(L, self.max_length)
+                if self.max_length is not None and not packed:   # truncating a packed row would cut through its segment
+                    L = min(L, self.max_length)                  # table and 4-D mask: packed rows are sized by PackingDataset
                 fill = self._pad_id() if k == "input_ids" else (self.label_pad if k == "labels" else 0)
                 out[k] = torch.cat([self._pad_to(v[:, :L], L, fill) for v in vals], dim=0)
+            else:
+                # everything else (Idefics2/3 pixel_values [1, N, C, H, W], ...): plain concatenation like the reference
+                # (data.py:1529)
+                out[k] = torch.cat(vals, dim=0)
         if self.image_token_index is not None and out.get("input_ids") is not None and "cu_segments" not in out:
             out["merge_hint"] = self.merge_hint(out["input_ids"], self._pad_id())
         return out

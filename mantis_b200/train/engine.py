@@ -137,13 +137,13 @@ class B200Trainer:
                 if isinstance(mod, B200Linear) and mod.weight.requires_grad and mod.weight.dim() == 2:
                     fused.add(id(mod.weight))
         for p in self.params:
+            # Gradients that reach a parameter through autograd (norm weights, biases, embeddings, the LM head's dW out of the
+            # fused LM-head/CE, any weight used outside ops.linear) arrive in the parameter dtype: fold each into the fp32 main
+            # gradient as soon as it is produced and drop the temporary.  Fused-wgrad weights normally never see one.
+            p._b200_unfused_main_grad = p._b200_main_grad
             if id(p) not in fused:
-                # autograd hands these gradients over in the parameter dtype: fold each into the fp32 main gradient as soon
-                # as it is produced and drop the temporary
-                mg = p._b200_main_grad
                 p._b200_main_grad = None                       # ops._LinearFn: not a fused-wgrad weight
-                p._b200_unfused_main_grad = mg
-                p.register_post_accumulate_grad_hook(self._fold_grad)
+            p.register_post_accumulate_grad_hook(self._fold_grad)
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.max_grad_norm = max_grad_norm
         self.grad_accum = grad_accum

@@ -35,9 +35,9 @@ GRAD_KEYS = ["lm_head.weight", "model.text_model.embed_tokens.weight", "model.te
              "model.vision_model.embeddings.patch_embedding.weight"]
 
 
-def build(seed):
+def build(seed, cfg_dict=None):
     Ref = ref_idefics2_classes()
-    cfg = Idefics2Config(**CFG)
+    cfg = Idefics2Config(**(cfg_dict or CFG))
     cfg._attn_implementation = "eager"
     torch.manual_seed(seed)
     model = Ref(cfg)
@@ -51,13 +51,14 @@ def build(seed):
     return model.train()
 
 
-def run(model, name, **inputs):
+def run(model, name, cfg_dict=None, extra=None, **inputs):
     out = model(use_cache=False, **inputs)
     model.zero_grad()
     out.loss.backward()
     grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if k in GRAD_KEYS and p.grad is not None}
-    fx = dict(cfg=CFG, state_dict={k: v.detach().clone() for k, v in model.state_dict().items()}, inputs=inputs,
+    fx = dict(cfg=cfg_dict or CFG, state_dict={k: v.detach().clone() for k, v in model.state_dict().items()}, inputs=inputs,
               logits=out.logits.detach().clone(), loss=out.loss.detach().clone(), grads=grads)
+    fx.update(extra or {})
     torch.save(fx, os.path.join(OUT, name))
     print(name, tuple(out.logits.shape), float(out.loss.detach()), len(grads))
 
@@ -84,6 +85,29 @@ def main():
     labels = ids.clone(); labels[ids == 0] = 300
     run(model, "idefics2_ragged.pt", input_ids=ids, attention_mask=att, pixel_values=pv, pixel_attention_mask=pam,
         labels=labels)
+
+    # Mistral sliding window SMALLER than the sequence (transformers mistral/modeling_mistral.py: kv_idx > q_idx - window):
+    # forward/backward at S = 40 > window = 12, plus a cache-free greedy continuation that keeps sliding
+    import copy
+    cfg_sw = copy.deepcopy(CFG)
+    cfg_sw["text_config"]["sliding_window"] = 12
+    model = build(9, cfg_sw)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.dim() >= 2 and "vision_model" not in n:
+                p.mul_(6.0)
+    ids = torch.randint(1, 299, (1, 40), generator=g)
+    ids[0, 3:11] = 300
+    pv = torch.randn(1, 1, 3, 112, 112, generator=g)
+    model.eval()
+    seq = ids.clone()
+    with torch.no_grad():
+        for _ in range(8):
+            lg = model(input_ids=seq, attention_mask=torch.ones_like(seq), pixel_values=pv, use_cache=False).logits
+            seq = torch.cat([seq, lg[:, -1].argmax(-1, keepdim=True)], 1)
+    model.train()
+    run(model, "idefics2_sliding.pt", cfg_dict=cfg_sw, extra={"generated": seq}, input_ids=ids,
+        attention_mask=torch.ones_like(ids), pixel_values=pv, labels=ids.clone())
 
 
 if __name__ == "__main__":

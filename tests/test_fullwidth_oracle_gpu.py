@@ -64,10 +64,13 @@ def _perturb(model, seed):
                 p.add_(0.05 * torch.randn(p.shape, generator=g).to(p.device))
 
 
-def _check(rows, what, ours, ref16, ref32, floor):
+CAP_LOGITS, CAP_GRAD = 5e-2, 8e-2        # absolute ceilings on top of the budget (B200, round 2: <= 2.8e-2 / <= 4.8e-2 measured)
+
+
+def _check(rows, what, ours, ref16, ref32, cap):
     e_o, e_r = rel_err(ours, ref32), rel_err(ref16, ref32)
     rows.append({"what": what, "ours": e_o, "ref_bf16": e_r, "ratio": e_o / max(e_r, 1e-30)})
-    return e_o <= max(BUDGET * e_r, floor)
+    return e_o <= BUDGET * e_r and e_o <= cap
 
 
 # ------------------------------------------------------------------------------------------------ LLaVA (SigLIP + LLaMA-3)
@@ -151,7 +154,7 @@ def run_llava_budget(dims, device, name):
     lo = _logits(ours, inputs, torch.bfloat16)
     assert lo.shape == l32.shape
     rows, ok = [], []
-    ok.append(_check(rows, "logits rel-L2 (all positions)", lo, l16, l32, 0.0))
+    ok.append(_check(rows, "logits rel-L2 (all positions)", lo, l16, l32, CAP_LOGITS))
     scale = l32.abs().max().item()
     rows.append({"what": "logits max-abs / max|logit|", "ours": (lo - l32).abs().max().item() / scale,
                  "ref_bf16": (l16 - l32).abs().max().item() / scale,
@@ -174,7 +177,7 @@ def run_llava_budget(dims, device, name):
         if k not in g32:
             continue
         assert k in go, f"ours has no gradient for {k}"
-        ok.append(_check(rows, "grad " + k, go[k], g16[k], g32[k], 0.0))
+        ok.append(_check(rows, "grad " + k, go[k], g16[k], g32[k], CAP_GRAD))
         n_grads += 1
     _report(name, rows)
     assert n_grads >= 8
@@ -265,7 +268,7 @@ def run_idefics2_budget(cfgd, device, name, T=1500):
 
     l32, l16, lo = logits(ref32, torch.float32), logits(ref16, torch.bfloat16), logits(ours, torch.bfloat16)
     rows, ok = [], []
-    ok.append(_check(rows, "logits rel-L2", lo, l16, l32, 0.0))
+    ok.append(_check(rows, "logits rel-L2", lo, l16, l32, CAP_LOGITS))
     del l16, lo
     loss32, g32 = fwd_bwd(ref32, torch.float32)
     loss16, g16 = fwd_bwd(ref16, torch.bfloat16)
@@ -278,7 +281,7 @@ def run_idefics2_budget(cfgd, device, name, T=1500):
         if k not in g32:
             continue
         assert k in go, f"ours has no gradient for {k}"
-        ok.append(_check(rows, "grad " + k, go[k], g16[k], g32[k], 0.0))
+        ok.append(_check(rows, "grad " + k, go[k], g16[k], g32[k], CAP_GRAD))
         n_grads += 1
     _report(name, rows)
     assert n_grads >= 8

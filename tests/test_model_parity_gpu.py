@@ -234,3 +234,64 @@ def test_decode_engine_bitexact_with_and_without_pdl(cuda, tmp_path):
         outs.append(torch.load(path))
     assert outs[0].shape == (12, 2, 2000) and torch.isfinite(outs[0]).all()
     assert torch.equal(outs[0], outs[1])
+
+
+def test_labels_none_gives_nan_loss_like_the_reference(cuda):
+    """a7 (ref modeling_llava.py:475-476, 523-537): with pixel_values and NO labels the reference substitutes all-ignore labels,
+    so its `loss` is CrossEntropyLoss over zero rows == NaN (not None); without images and without labels the loss is None"""
+    fx = load_fixture("llava_siglip_full.pt")
+    model = load_model(fx, torch.float32, cuda).eval()
+    ids = fx["input_ids"].to(cuda)
+    with torch.no_grad():
+        out = model(input_ids=ids, pixel_values=fx["pixel_values"].to(cuda), attention_mask=fx["attention_mask"].to(cuda))
+    assert out.loss is not None and torch.isnan(out.loss) and out.loss.dtype == torch.float32
+    assert (out.logits.cpu() - fx["logits"]).abs().max().item() <= 1e-3 * fx["logits"].abs().max().item()
+    text_only = ids[:, 45:]                                   # no <image> placeholder in this span
+    assert not bool((text_only == model.config.image_token_index).any())
+    with torch.no_grad():
+        out = model(input_ids=text_only, attention_mask=torch.ones_like(text_only))
+    assert out.loss is None
+
+
+def test_generate_on_a_worker_thread_matches_the_main_thread(cuda):
+    """chat_mllava_stream (ref utils.py:100-186) runs model.generate() on a second Python thread: the bf16 path (tcgen05 prefill,
+    native decode engine with its call-scoped launch mode) must give the same tokens from a worker thread as from the main one"""
+    import threading
+    from transformers import LlamaConfig, SiglipVisionConfig
+    from mantis_b200.models import decode_engine
+    from mantis_b200.models.mllava import LlavaConfig, LlavaForConditionalGeneration
+    vc = SiglipVisionConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                            image_size=112, patch_size=14)
+    tc = LlamaConfig(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2,
+                     num_key_value_heads=1, vocab_size=1000, rms_norm_eps=1e-5, rope_theta=500000.0)
+    cfg = LlavaConfig(vision_config=vc, text_config=tc, image_token_index=990, pad_token_id=991, vocab_size=1000,
+                      vision_feature_select_strategy="full")
+    torch.manual_seed(3)
+    model = LlavaForConditionalGeneration(cfg).to(cuda).to(torch.bfloat16).eval()
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.dim() >= 2:
+                p.mul_(4.0)
+    ids = torch.randint(0, 980, (2, 200), device=cuda); ids[:, 3] = 990
+    pv = torch.randn(2, 3, 112, 112, device=cuda).bfloat16()
+    kw = dict(input_ids=ids, pixel_values=pv, attention_mask=torch.ones_like(ids), max_new_tokens=12, do_sample=False,
+              num_beams=1, pad_token_id=991)
+    main = model.generate(**kw)
+    got, errs = [], []
+
+    def work():
+        try:
+            torch.cuda.set_device(cuda)
+            got.append(model.generate(**kw))
+            torch.cuda.synchronize()
+        except BaseException as e:  # noqa
+            errs.append(e)
+
+    before = decode_engine.native_steps
+    ts = [threading.Thread(target=work) for _ in range(2)]
+    for t in ts:
+        t.start(); t.join()
+    assert not errs, errs
+    assert decode_engine.native_steps - before >= 2 * 11
+    for g in got:
+        assert torch.equal(g, main)

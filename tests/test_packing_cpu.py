@@ -129,3 +129,45 @@ def test_collator_matches_the_live_reference():
     r, o = rc([dict(x) for x in packed]), oc([dict(x) for x in packed])
     for k in ("input_ids", "attention_mask", "labels", "position_ids"):
         assert torch.equal(o[k], r[k]), k
+
+
+def test_collator_idefics2_pixel_tensors_match_the_live_reference():
+    """Idefics2/3 processors have no `_right_pad_inputs_with_attention_mask`: the reference Collator then concatenates
+    `pixel_values` [1, N, C, H, W] on dim 0 and zero-pads the 4-D `pixel_attention_mask` [1, N, H, W] on its last two dims
+    independently (H != W, different sizes per sample) -- data.py:1444-1479,1529."""
+    ref = _ref_data()
+
+    class Tok:
+        pad_token_id = 7
+
+    class Proc:
+        tokenizer = Tok()
+    rc = ref.Collator(Proc()); rc.tokenizer = Tok()
+    oc = Collator(processor=Proc(), pad_token_id=7)
+    g = torch.Generator().manual_seed(3)
+    items = []
+    for T, (H, W) in ((5, (28, 42)), (9, (28, 42)), (7, (28, 42))):
+        items.append({"input_ids": torch.randint(8, 50, (1, T), generator=g), "attention_mask": torch.ones(1, T, dtype=torch.long),
+                      "labels": torch.randint(8, 50, (1, T), generator=g),
+                      "pixel_values": torch.randn(1, 2, 3, H, W, generator=g),
+                      "pixel_attention_mask": torch.ones(1, 2, H, W, dtype=torch.bool)})
+    # ragged masks (the reference pads them; pixel_values of equal size are concatenated)
+    items[1]["pixel_attention_mask"] = torch.ones(1, 2, 14, 56, dtype=torch.bool)
+    r, o = rc([dict(x) for x in items]), oc([dict(x) for x in items])
+    assert set(r.keys()) <= set(o.keys())
+    for k in r:
+        assert isinstance(o[k], torch.Tensor) and o[k].shape == r[k].shape and torch.equal(o[k], r[k]), k
+    assert o["pixel_values"].shape == (3, 2, 3, 28, 42) and o["pixel_attention_mask"].shape == (3, 2, 28, 56)
+
+
+def test_collator_max_length_leaves_packed_rows_alone():
+    ds = _DS()
+    pd = PackingDataset(ds, max_self_attn_len=10)
+    rows = [pd[0], pd[1]]
+    out = Collator(pad_token_id=7, max_length=4)([dict(x) for x in rows])
+    L = max(r["input_ids"].shape[1] for r in rows)
+    assert out["input_ids"].shape[1] == L and out["attention_mask"].shape[-2:] == (L, L)
+    assert all(s1 <= L for (_, _, s1) in out["cu_segments"])
+    plain = [{k: v for k, v in ds[i].items() if k != "pixel_values"} for i in (0, 1)]
+    out = Collator(pad_token_id=7, max_length=4)([dict(x) for x in plain])
+    assert out["input_ids"].shape[1] == 4 and out["labels"].shape[1] == 4

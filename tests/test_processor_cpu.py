@@ -257,3 +257,73 @@ def test_chat_mllava_matches_the_live_reference():
             gen = m.calls[0]
             outs.append((reply, h2, p.calls, gen["eos_token_id"], gen["max_new_tokens"], gen["do_sample"], gen["input_ids"].tolist()))
         assert outs[0] == outs[1], (name, history, text)
+
+
+def test_chat_mllava_stream_matches_the_live_reference():
+    """chat_mllava_stream (generate() on a worker thread feeding a TextIteratorStreamer, the reply growing in history[-1])
+    vs mantis/models/mllava/utils.py:100-186 with recording stubs: same yielded (reply, history) sequence, same generate kwargs"""
+    import copy
+    import threading
+    import pytest
+    from oracle.ref_shim import find_ref_root
+    if find_ref_root() is None:
+        pytest.skip("reference tree not available here")
+    from oracle.ref_shim import load_reference_chat_utils
+    from mantis_b200.models.mllava import chat_mllava_stream
+    ref_stream = load_reference_chat_utils().chat_mllava_stream
+
+    class Tok:
+        eos_token_id = 2
+
+        def convert_tokens_to_ids(self, t):
+            return 128009
+
+    class Proc:                                         # doubles as the streamer's tokenizer, like MLlavaProcessor does
+        def __init__(self):
+            self.tokenizer = Tok()
+
+        def __call__(self, images=None, text=None, **kw):
+            return {"input_ids": torch.arange(len(text.split()))[None], "pixel_values": None}
+
+        def decode(self, ids, skip_special_tokens=True, **kw):
+            return "".join(f"w{int(i)} " for i in ids)
+
+    class LM:
+        name_or_path = "meta-llama/Meta-Llama-3-8B-Instruct"
+
+    class Model:
+        device = torch.device("cpu")
+        language_model = LM()
+
+        def __init__(self):
+            self.calls, self.threads = [], []
+
+        def generate(self, streamer=None, **kw):
+            self.calls.append(kw)
+            self.threads.append(threading.current_thread())
+            streamer.put(kw["input_ids"])               # the prompt (skipped by the streamer)
+            for t in (41, 42, 43, 44):
+                streamer.put(torch.tensor([t]))
+            streamer.end()
+
+    outs = []
+    for fn in (ref_stream, chat_mllava_stream):
+        m = Model()
+        hist = [{"role": "user", "text": "look <image>"}, {"role": "assistant", "text": "ok"}]
+        seq = [(r, copy.deepcopy(h)) for r, h in fn("and now?", [], m, Proc(), max_input_length=50, history=hist,
+                                                    max_new_tokens=4, do_sample=False)]
+        assert m.threads[0] is not threading.main_thread()            # generate() really ran on a worker thread
+        gen = m.calls[0]
+        outs.append((seq, gen["eos_token_id"], gen["max_new_tokens"], gen["do_sample"], gen["input_ids"].tolist()))
+    assert outs[0] == outs[1]
+    assert outs[1][0][-1][0].split() == ["w41", "w42", "w43", "w44"]
+
+
+def test_mantis_alias_package_exports_fail_loudly():
+    """the `mantis.models.mllava` alias shim re-exports the processor and both chat helpers without swallowing import errors"""
+    import inspect
+    import mantis.models.mllava as alias
+    for name in ("LlavaForConditionalGeneration", "MLlavaForConditionalGeneration", "LlavaConfig", "MLlavaProcessor",
+                 "chat_mllava", "chat_mllava_stream"):
+        assert hasattr(alias, name), name
+    assert "except" not in inspect.getsource(alias)

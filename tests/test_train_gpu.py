@@ -44,11 +44,14 @@ def test_bf16_training_at_reference_lr_moves_the_weights(cuda):
     moved = []
     for i, p in enumerate(tr.params):
         now = tr.state.master(i)
-        moved.append((now != before[i]).float().mean().item())
+        got_grad = tr.state.view(tr.state.M, i) != 0          # e.g. embedding rows of tokens that never occur receive none
+        assert got_grad.any(), i
+        moved.append((now != before[i])[got_grad].float().mean().item())
+        assert torch.equal(now[~got_grad], before[i][~got_grad])
         assert torch.equal(p.detach().view(torch.int16), tr.state.view(tr.state.P, i).view(torch.int16))
         # bf16 weight == round-to-nearest of its master (exact ties aside)
         assert (p.detach().view(torch.int16) == now.bfloat16().view(torch.int16)).float().mean().item() > 0.999
-    assert min(moved) > 0.9 and sum(moved) / len(moved) > 0.99, moved
+    assert min(moved) > 0.99, moved
     assert tr.flat_grad.abs().sum().item() == 0                 # zeroed by the optimizer launch
     sd = tr.state_dict()
     assert all(m.dtype == torch.float32 for m in sd["master_params"])
