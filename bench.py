@@ -41,6 +41,12 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-gemm", action="store_true", help="only run the per-kernel roofline section")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="SURVEY 8d config 4: fix the GLOBAL batch (32) and split it over the ranks (strong scaling: 32/N "
+                         "micro-batches of one sample per rank per optimizer step); default 0 = weak scaling, --samples per rank")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the sub-records of the N=1 line (generate configs[4], idefics2 configs[2], gpu_incumbent)")
+    ap.add_argument("--new-tokens", type=int, default=512, help="generate(): new tokens per sequence (configs[4]: 512)")
     ap.add_argument("--workload", default="mllava", choices=["mllava", "idefics2"],
                     help="mllava = BASELINE configs[1] (the headline); idefics2 = configs[2] (perceiver-resampler path)")
     return ap.parse_args()
@@ -233,11 +239,39 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+def _latest_profile(pattern):
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", pattern)))
+    return files[-1] if files else None
+
+
+def ncu_evidence(kernel, pattern, pick):
+    """Per-launch DRAM traffic / tensor-pipe numbers of `kernel` from the newest `tools/ncu_to_json.py` file under profiles/.
+    The file carries the hash of the kernel's sources; if the kernel in the tree has changed since the capture the numbers are
+    REFUSED (null + a loud note) instead of being quoted for a kernel they no longer describe."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from kernel_hash import kernel_hash
+    path = _latest_profile(pattern)
+    if path is None:
+        return {"traffic": None, "note": f"no profiles/{pattern}"}
+    doc = json.load(open(path))
+    if doc.get("kernel_hash") != kernel_hash(kernel):
+        msg = (f"STALE ncu capture {os.path.relpath(path, ROOT)}: kernel hash {doc.get('kernel_hash')} != tree "
+               f"{kernel_hash(kernel)} -- re-run tools/ncu_to_json.py; traffic / tensor-pipe numbers withheld")
+        print("bench.py: " + msg, file=sys.stderr)
+        return {"traffic": None, "note": msg}
+    launch = next((l for l in doc["launches"] if pick in l["kernel"]), doc["launches"][0])
+    return {"traffic": launch["traffic_bytes"], "tensor_pipe_active_pct_ncu": launch.get("tensor_pipe_active_pct"),
+            "ncu_duration_us": launch.get("duration_us"), "ncu_sm_ghz": launch.get("sm_ghz"),
+            "traffic_source": f"{os.path.relpath(path, ROOT)} (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, "
+                              f"launch {launch['kernel']}; kernel hash {doc['kernel_hash']})"}
+
+
 def gemm_roofline(torch, ops, peaks):
     """Per-kernel roofline of the dominant kernel (the tcgen05 GEMM): CUDA events on the launching stream, operand sets
     cycled so every launch reads cold-in-L2 data.  `achieved` is the gate/up-projection forward GEMM (M=7864, N=14336,
-    K=4096 -- the shape that carries most of the step's FLOPs and the one captured with `ncu --set full`, see
-    profiles/ncu_full_r01_summary.txt for `traffic`); `all_linear_shapes` aggregates fwd/dgrad/wgrad of all seven
+    K=4096 -- the shape that carries most of the step's FLOPs and the one captured with `ncu --set full`);
+    `all_linear_shapes` aggregates fwd/dgrad/wgrad (wgrad into the fp32 main gradient, as the step runs it) of all seven
     linears of a decoder layer."""
     dev = torch.device("cuda")
     M = 7864
@@ -249,6 +283,7 @@ def gemm_roofline(torch, ops, peaks):
         xs = [torch.randn(M, K, device=dev).bfloat16() for _ in range(nset)]
         ws = [(torch.randn(N, K, device=dev) * 0.02).bfloat16() for _ in range(nset)]
         gs = [torch.randn(M, N, device=dev).bfloat16() for _ in range(nset)]
+        g32 = [torch.zeros(N, K, device=dev) for _ in range(nset)]
         for kind in ("fwd", "dgrad", "wgrad"):
             def run(i):
                 if kind == "fwd":
@@ -256,7 +291,7 @@ def gemm_roofline(torch, ops, peaks):
                 elif kind == "dgrad":
                     ops.gemm(gs[i], ws[i], trans_a=False, trans_b=False)
                 else:
-                    ops.gemm(gs[i], xs[i], trans_a=True, trans_b=False)
+                    ops.gemm(gs[i], xs[i], trans_a=True, trans_b=False, addend=g32[i], out=g32[i])
             for i in range(nset):
                 run(i)
             torch.cuda.synchronize()
@@ -270,32 +305,33 @@ def gemm_roofline(torch, ops, peaks):
             t_ms += dt; flops += reps * 2.0 * M * N * K; launches += reps
             if head is None and (N, K) == (14336, 4096) and kind == "fwd":
                 head = (2.0 * M * N * K / (dt / reps * 1e-3) / 1e12, dt / reps)
-        del xs, ws, gs
+        del xs, ws, gs, g32
     ach_all = flops / (t_ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops"]
     ach, ms = head
-    return {"bound": "tensor", "kernel": "gemm_sm100_2cta_kernel (tcgen05 cta_group::2, 256x256x64 per SM pair), gate/up fwd "
-            "M=7864 N=14336 K=4096", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-            "traffic": 754914560, "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, "
-            "profiles/ncu_full_r01_summary.txt (algorithmic operand bytes: 407 MB)", "avg_launch_ms": ms,
-            "all_linear_shapes": {"achieved": ach_all, "frac": ach_all / peak, "launches_timed": launches},
-            "tensor_pipe_active_pct_ncu": 93.0}
+    out = {"bound": "tensor", "kernel": "gemm_sm100_2cta_kernel (tcgen05 cta_group::2, 256x256x64 per SM pair), gate/up fwd "
+           "M=7864 N=14336 K=4096", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+           "avg_launch_ms": ms, "algorithmic_bytes": 2.0 * (M * 4096 + 14336 * 4096 + M * 14336),
+           "all_linear_shapes": {"achieved": ach_all, "frac": ach_all / peak, "launches_timed": launches}}
+    out.update(ncu_evidence("gemm_sm100_2cta_kernel", "ncu_gemm2cta_r*.json", "<0, 0>"))
+    return out
 
 
-def scatter_roofline(torch, ops, peaks):
-    """HBM roofline of the image-token scatter (merge_rows_kernel) for one bench micro-batch (1 sample, S = 7864):
-    algorithmic bytes = read every source row once + write every output row once = 2 * S * D * 2."""
+def scatter_roofline(torch, ops, peaks, B=4):
+    """HBM roofline of the image-token scatter (merge_rows_kernel) at BASELINE config 2's batch (B = 4 samples, S = 7864):
+    algorithmic bytes = read every source row once + write every output row once = 2 * B * S * D * 2 = 516 MB."""
     dev = torch.device("cuda")
-    B, T, P, D = 1, T_TEXT, 728, 4096
+    T, P, D = T_TEXT, 728, 4096
     S = T + N_IMG * (P - 1)
     g = torch.Generator().manual_seed(3)
     ids = torch.randint(0, 128000, (B, T), generator=g)
     for j in range(N_IMG):
         ids[:, j * 256 + 16] = IMG_TOKEN
     ids = ids.to(dev)
-    embs = [torch.randn(B, T, D, device=dev).bfloat16() for _ in range(8)]
-    feats = [torch.randn(N_IMG, P, D, device=dev).bfloat16() for _ in range(8)]
-    outs = [torch.empty((B, S, D), dtype=torch.bfloat16, device=dev) for _ in range(8)]
+    nset = 3 if B > 1 else 8
+    embs = [torch.randn(B, T, D, device=dev).bfloat16() for _ in range(nset)]
+    feats = [torch.randn(B * N_IMG, P, D, device=dev).bfloat16() for _ in range(nset)]
+    outs = [torch.empty((B, S, D), dtype=torch.bfloat16, device=dev) for _ in range(nset)]
     att = torch.ones_like(ids)
     ws, hdr = ops.merge_plan(ids, embs[0], P, IMG_TOKEN, 128257)
     srcmap = torch.empty((B, S), dtype=torch.int32, device=dev)
@@ -304,14 +340,14 @@ def scatter_roofline(torch, ops, peaks):
               ops._p(srcmap), ops._p(om), ops._p(ol), ops._p(op_), ops._st())
 
     def run(i):
-        f2 = feats[i % 8].reshape(-1, D)
-        ops._call("mb200_merge_rows", ops._p(srcmap), ops._p(embs[i % 8]), ops._p(f2), ops._p(outs[i % 8]), B, S, T, D * 2,
+        f2 = feats[i % nset].reshape(-1, D)
+        ops._call("mb200_merge_rows", ops._p(srcmap), ops._p(embs[i % nset]), ops._p(f2), ops._p(outs[i % nset]), B, S, T, D * 2,
                   f2.shape[0], ops._st())
-    for i in range(8):
+    for i in range(nset):
         run(i)
     torch.cuda.synchronize()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    reps = 40
+    reps = 30
     e0.record()
     for i in range(reps):
         run(i)
@@ -319,61 +355,51 @@ def scatter_roofline(torch, ops, peaks):
     ms = e0.elapsed_time(e1) / reps
     bytes_ = 2.0 * B * S * D * 2
     ach = bytes_ / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "merge_rows_kernel (image-token scatter), 1 sample S=7864 D=4096", "achieved": ach,
-            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "avg_launch_ms": ms,
-            "algorithmic_bytes": bytes_, "note": "8 rotating 129 MB operand sets (> L2); B=4 capture: 468 MB DRAM traffic "
-            "vs 516 MB algorithmic (profiles/ncu_full_r01_summary.txt)"}
+    out = {"bound": "hbm", "kernel": f"merge_rows_kernel (image-token scatter), B={B} S=7864 D=4096", "achieved": ach,
+           "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "avg_launch_ms": ms,
+           "algorithmic_bytes": bytes_, "l2": f"{nset} rotating operand sets of {bytes_ / 1e6:.0f} MB (> 126 MB L2)"}
+    out.update(ncu_evidence("merge_rows_kernel", "ncu_merge_rows_r*.json", "merge_rows_kernel"))
+    return out
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    from mantis_b200 import _lib, ops
+def build_model(torch, dev, workload, text_layers, vision_layers):
     from mantis_b200.models.mllava import LlavaForConditionalGeneration, mantis_8b_siglip_llama3_config
-    from mantis_b200.train import B200Trainer
-    assert _lib.lib().mb200_check_device() == 0, _lib.lib().mb200_last_error()
-    peaks, peaks_src = measured_peaks()
-
-    if args.profile_gemm:
-        print(json.dumps(gemm_roofline(torch, ops, peaks)))
-        return
-
     torch.manual_seed(0)
     old = torch.get_default_dtype()
     torch.set_default_dtype(torch.bfloat16)
-    if args.workload == "idefics2":
-        from mantis_b200.models.idefics2 import Idefics2ForConditionalGeneration
-        with torch.device(dev):
-            model = Idefics2ForConditionalGeneration(idefics2_8b_config(args.text_layers, args.vision_layers))
-    else:
-        cfg = mantis_8b_siglip_llama3_config(num_vision_layers=args.vision_layers, num_text_layers=args.text_layers)
-        with torch.device(dev):
-            model = LlavaForConditionalGeneration(cfg)
-    torch.set_default_dtype(old)
-    model.train()
-    mb = args.micro_batch or (4 if args.workload == "idefics2" else 1)
-    mb = max(1, min(mb, args.samples))
-    while args.samples % mb:
-        mb -= 1
-    trainer = B200Trainer(model, lr=1e-5, weight_decay=0.0, max_grad_norm=1.0, grad_accum=args.samples // mb)
-    n_train = sum(p.numel() for p in trainer.params)
+    try:
+        if workload == "idefics2":
+            from mantis_b200.models.idefics2 import Idefics2ForConditionalGeneration
+            with torch.device(dev):
+                model = Idefics2ForConditionalGeneration(idefics2_8b_config(text_layers, vision_layers))
+        else:
+            cfg = mantis_8b_siglip_llama3_config(num_vision_layers=vision_layers, num_text_layers=text_layers)
+            with torch.device(dev):
+                model = LlavaForConditionalGeneration(cfg)
+    finally:
+        torch.set_default_dtype(old)
+    return model
 
-    mk = make_sample_idefics2 if args.workload == "idefics2" else make_sample
-    host = [mk(rank * args.samples + i, torch) for i in range(args.samples)]
+
+def train_measure(torch, dist, ops, model, workload, args, world, rank, dev, steps, warmup, e2e_too, samples):
+    """W warm-up + K timed optimizer steps (device-resident inputs), then optionally K more through the public API with
+    host (pinned) inputs and a loss read-back per step.  Returns a dict of raw measurements."""
+    from mantis_b200.train import B200Trainer
+    model.train()
+    mb = args.micro_batch or (4 if workload == "idefics2" else 1)
+    mb = max(1, min(mb, samples))
+    while samples % mb:
+        mb -= 1
+    trainer = B200Trainer(model, lr=1e-5, weight_decay=0.0, max_grad_norm=1.0, grad_accum=samples // mb)
+    trainer.time_comm = world > 1
+    n_train = sum(p.numel() for p in trainer.params)
+    mk = make_sample_idefics2 if workload == "idefics2" else make_sample
+    host = [mk(rank * samples + i, torch) for i in range(samples)]
     if mb > 1:                                   # same-shape synthetic samples: a micro-batch is a plain concatenation
         host = [{k: torch.cat([s[k] for s in host[i:i + mb]], dim=0) for k in host[0]} for i in range(0, len(host), mb)]
     host = [{k: v.pin_memory() for k, v in s.items()} for s in host]
     resident = [{k: v.to(dev, non_blocking=True) for k, v in s.items()} for s in host]
     torch.cuda.synchronize()
-    S_merged = T_TEXT if args.workload == "idefics2" else T_TEXT + N_IMG * 727
-    tokens_per_step_rank = args.samples * S_merged
     h2d = sum(v.numel() * v.element_size() for s in host for v in s.values())
 
     def step(e2e):
@@ -390,6 +416,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         l0 = ops.launch_count
+        trainer.exposed_comm_ms()                  # drop the brackets of earlier (warm-up) steps
         e0.record()
         last = None
         for _ in range(k):
@@ -398,63 +425,229 @@ def run_ours(args):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        ms = torch.tensor([e0.elapsed_time(e1), trainer.exposed_comm_ms()], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item(), ops.launch_count - l0, last
+        return ms[0].item(), ops.launch_count - l0, last, ms[1].item() / max(k, 1)
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step(False)
-    sampler = ClockSampler(local); sampler.start()
-    ms, launches, last_loss = timed(False, args.steps)
+    sampler = ClockSampler(dev.index or 0); sampler.start()
+    ms, launches, last_loss, comm_ms = timed(False, steps)
     clocks = sampler.stop()
-    mem_gb = torch.cuda.max_memory_allocated() / 2 ** 30
-    e2e = None
-    if not args.no_e2e:
+    res = {"ms": ms, "launches": launches, "loss": float(last_loss), "clocks": clocks, "comm_exposed_ms": comm_ms,
+           "mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30, "n_train": n_train, "micro_batch": mb,
+           "grad_accum": samples // mb, "h2d": h2d, "host": host, "e2e_ms": None}
+    if e2e_too:
         step(True)
-        ms2, _, _ = timed(True, args.steps)
-        e2e = {"value": world * tokens_per_step_rank * args.steps / (ms2 * 1e-3), "unit": "tokens/s",
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
+        res["e2e_ms"], _, _, _ = timed(True, steps)
+    ops.check_deferred()
+    trainer.close()                                # frees G / M / V / LO; the model keeps its (flat) weights
+    del trainer, resident
+    return res
+
+
+def generate_record(torch, ops, model, peaks, bs, new_tokens=512):
+    """BASELINE configs[4]: 8 images + 256-token prompt (merged prefill S = 6072) -> `new_tokens` greedy tokens THROUGH
+    model.generate() (transformers' GenerationMixin, the call mantis/models/mllava/utils.py:88 makes).  Two calls with
+    identical inputs: max_new_tokens = 1 (vision tower + merge + prefill + first token) and max_new_tokens = N; decode time is
+    their difference over N - 1 steps.  HBM bound of a decode step = 15.01 GB of weights + 131,072 B x context per sequence."""
+    from mantis_b200.models import decode_engine
+    dev = next(model.parameters()).device
+    g = torch.Generator().manual_seed(5 + bs)
+    ids = torch.randint(0, 128000, (bs, 256), generator=g)
+    for j in range(N_IMG):
+        ids[:, j * 32 + 4] = IMG_TOKEN
+    pv = torch.randn(bs * N_IMG, 3, IMG_RES, IMG_RES, generator=g).bfloat16().pin_memory()
+    ids = ids.pin_memory()
+    model.eval()
+    S = 256 + N_IMG * 727
+
+    def run(n):
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ids_d = ids.to(dev, non_blocking=True)
+        out = model.generate(input_ids=ids_d, pixel_values=pv.to(dev, non_blocking=True), attention_mask=torch.ones_like(ids_d),
+                             max_new_tokens=n, min_new_tokens=n, do_sample=False, num_beams=1, pad_token_id=128257)
+        out = out.cpu()                                   # the user-visible result
+        e1.record(); torch.cuda.synchronize()
+        assert out.shape == (bs, 256 + n), out.shape
+        return e0.elapsed_time(e1) * 1e-3
+    run(4)                                                # warm-up (allocations, kernel attributes, page slabs)
+    n0 = decode_engine.native_steps
+    l0 = ops.launch_count
+    t1 = run(1)
+    tn = run(new_tokens)
+    native = decode_engine.native_steps - n0
+    t_dec = (tn - t1) / (new_tokens - 1)
+    ctx_avg = S + new_tokens / 2
+    bytes_step = 15.01e9 + 131072.0 * ctx_avg * bs
+    return {"bs": bs, "prefill_len": S, "new_tokens": new_tokens, "api": "model.generate (GenerationMixin, greedy)",
+            "prefill_tok_s": bs * S / t1, "prefill_s": t1, "decode_tok_s": bs / t_dec, "decode_ms_per_step": t_dec * 1e3,
+            "e2e_s": tn, "decode_hbm_gbs": bytes_step / t_dec / 1e9, "hbm_bound_bytes_per_step": bytes_step,
+            "frac": bytes_step / t_dec / 1e9 / peaks["hbm_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "bound": "hbm",
+            "native_engine_steps": native, "gpu_launches": ops.launch_count - l0,
+            "includes": "H2D of prompt + 8 x 384^2 images per sequence, vision tower, merge, prefill, D2H of the tokens"}
+
+
+def gpu_incumbent(torch, peaks):
+    """Context line (not a target): what a Mantis user gets TODAY on this B200 -- the unmodified reference forward+backward
+    (baseline/_ref through oracle/ref_shim.py) in bf16 through PyTorch (cuBLAS GEMMs + SDPA attention), full width at depth 1+1
+    and 3+3 on one config-2 sample (8 images, S = 7864), extrapolated linearly to 27+32 layers like the CPU leg."""
+    from oracle.ref_shim import find_ref_root, ref_llava_classes
+    if find_ref_root() is None:
+        return None
+    from transformers import LlamaConfig, SiglipVisionConfig
+    LlavaConfig, RefLlava, _ = ref_llava_classes()
+    dev = torch.device("cuda")
+    s = make_sample(0, torch)
+    batch = {k: v.to(dev) for k, v in s.items()}
+    times = {}
+    for depth in (1, 3):
+        vc = SiglipVisionConfig(hidden_size=1152, intermediate_size=4304, num_hidden_layers=depth + 1, num_attention_heads=16,
+                                image_size=384, patch_size=14, layer_norm_eps=1e-6, hidden_act="gelu_pytorch_tanh")
+        tc = LlamaConfig(hidden_size=4096, intermediate_size=14336, num_hidden_layers=depth, num_attention_heads=32,
+                         num_key_value_heads=8, vocab_size=128258, rms_norm_eps=1e-5, rope_theta=500000.0,
+                         max_position_embeddings=8192)
+        cfg = LlavaConfig(vision_config=vc, text_config=tc, image_token_index=IMG_TOKEN, pad_token_id=128257, vocab_size=128258)
+        torch.manual_seed(0)
+        m = RefLlava(cfg).to(dev).to(torch.bfloat16).train()
+        for n, p in m.named_parameters():
+            if "vision_tower" in n:
+                p.requires_grad_(False)
+        ts = []
+        for it in range(4):
+            torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = m(**batch)
+            out.loss.backward()
+            m.zero_grad(set_to_none=True)
+            e1.record(); torch.cuda.synchronize()
+            if it >= 2:
+                ts.append(e0.elapsed_time(e1) * 1e-3)
+        times[depth] = min(ts)
+        del m, out
+        torch.cuda.empty_cache()
+    per_layer = max((times[3] - times[1]) / 2.0, 1e-9)
+    full = max(times[1] - per_layer, 0.0) + 32 * per_layer       # ViT depth scales with the same index (27 vs 32: upper bound)
+    S = T_TEXT + N_IMG * 727
+    return {"value": S / full, "unit": "tokens/s", "kind": "reference on GPU (torch eager: cuBLAS + SDPA), bf16, no optimizer step",
+            "seconds_per_sample_extrapolated": full,
+            "sample": f"full-width Mantis-8B-SigLIP reference fwd+bwd, depth 1+1 ({times[1]:.3f} s) and 3+3 ({times[3]:.3f} s), "
+                      f"one config-2 sample (S = {S}); linear extrapolation to 27+32 layers"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from mantis_b200 import _lib, ops
+    assert _lib.lib().mb200_check_device() == 0, _lib.lib().mb200_last_error()
+    peaks, peaks_src = measured_peaks()
+
+    if args.profile_gemm:
+        print(json.dumps(gemm_roofline(torch, ops, peaks)))
+        return
+
+    samples = args.samples
+    scaling = "weak"
+    if args.global_batch:                        # SURVEY 8d config 4: the GLOBAL batch is fixed, ranks split it
+        if args.global_batch % world:
+            raise SystemExit(f"--global-batch {args.global_batch} is not divisible by {world} ranks")
+        samples = args.global_batch // world
+        scaling = "strong"
+    model = build_model(torch, dev, args.workload, args.text_layers, args.vision_layers)
+    r = train_measure(torch, dist, ops, model, args.workload, args, world, rank, dev, args.steps, args.warmup,
+                      not args.no_e2e, samples)
+    S_merged = T_TEXT if args.workload == "idefics2" else T_TEXT + N_IMG * 727
+    tokens_per_step_rank = samples * S_merged
+    ms = r["ms"]
+    full = (args.text_layers == 32 and args.vision_layers == 27)
+    extras = world == 1 and full and not args.no_extras
+    gen = None
+    if extras and args.workload == "mllava":
+        # BASELINE configs[4] on the SAME weights: generate() prefill / decode tok/s (the trainer's state was released above)
+        torch.cuda.empty_cache()
+        try:
+            gen = {f"bs{bs}": generate_record(torch, ops, model, peaks, bs, args.new_tokens) for bs in (1, 16)}
+        except Exception as e:  # noqa
+            gen = {"error": f"{type(e).__name__}: {e}"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    e2e = None
+    if r["e2e_ms"] is not None:
+        e2e = {"value": world * tokens_per_step_rank * args.steps / (r["e2e_ms"] * 1e-3), "unit": "tokens/s",
+               "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": 4}
     value = world * tokens_per_step_rank * args.steps / (ms * 1e-3)
-    flop_per_step = 449e12 if args.workload == "idefics2" else FLOP_PER_STEP
+    per_sample_flop = (449e12 if args.workload == "idefics2" else FLOP_PER_STEP) / SAMPLES_PER_STEP   # SURVEY.md 8d (nominal)
     # executed FLOPs: the fused LM-head/CE skips rows whose label is ignored (no loss, no gradient): 3 x 2*V*D per row
-    from mantis_b200 import ops as _ops
     ign = 32001 if args.workload == "idefics2" else -100
-    valid_rows = sum(int((s_["labels"][0, 1:] != ign).sum()) for s_ in host)
-    rows_total = args.samples * S_merged
+    valid_rows = sum(int((s_["labels"][:, 1:] != ign).sum()) for s_ in r["host"])
     V_ = 32003 if args.workload == "idefics2" else 128258
-    skipped = (rows_total - valid_rows) * 6.0 * V_ * 4096 if _ops.LM_HEAD_SKIP_IGNORED else 0.0
-    flop_executed = flop_per_step * (args.samples / SAMPLES_PER_STEP) - skipped
-    step_tflops = world * flop_per_step * (args.samples / SAMPLES_PER_STEP) * args.steps / (ms * 1e-3) / 1e12
+    skipped = (samples * S_merged - valid_rows) * 6.0 * V_ * 4096 if ops.LM_HEAD_SKIP_IGNORED else 0.0
+    step_tflops = world * per_sample_flop * samples * args.steps / (ms * 1e-3) / 1e12
     roof = gemm_roofline(torch, ops, peaks) if world == 1 else None
     scat = scatter_roofline(torch, ops, peaks) if world == 1 else None
-    full = (args.text_layers == 32 and args.vision_layers == 27 and args.samples == SAMPLES_PER_STEP)
     line = {
         "metric": ("training tokens/sec Mantis-8B-SigLIP 8-img/2048-tok" if args.workload == "mllava"
                    else "training tokens/sec Mantis-8B-Idefics2 8-img/2048-tok"), "value": value, "unit": "tokens/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": ("Mantis-8B-SigLIP-LLaMA-3 instruction-tuning step, random init (configs[1])"
                                 if args.workload == "mllava" else
                                 "Mantis-8B-Idefics2 instruction-tuning step, random init (configs[2])"),
-                   "samples_per_rank_per_step": args.samples, "images_per_sample": N_IMG, "text_tokens": T_TEXT,
-                   "merged_seq_len": S_merged, "micro_batch": mb, "grad_accum": args.samples // mb,
-                   "parallelism": f"dp{world}", "optimizer": "fused AdamW (fp32 moments) + grad-norm clip",
-                   "trainable_params": n_train, "vision_tower": "frozen (train_mllava.py:239-242)",
+                   "samples_per_rank_per_step": samples, "global_batch": samples * world, "images_per_sample": N_IMG,
+                   "text_tokens": T_TEXT, "merged_seq_len": S_merged, "micro_batch": r["micro_batch"],
+                   "grad_accum": r["grad_accum"], "parallelism": f"dp{world}",
+                   "optimizer": "ONE fused AdamW launch over flat buffers: fp32 master weights (bf16 weight + 16 low bits), "
+                                "fp32 main-gradient accumulation, fp32 moments, device-side global-norm clip",
+                   "trainable_params": r["n_train"], "vision_tower": "frozen (train_mllava.py:239-242)",
                    "l2": "working set >> L2 (35 GB of activations + 16 GB weights per micro-batch), no flush needed",
-                   "text_layers": args.text_layers, "vision_layers": args.vision_layers, "valid": full},
+                   "text_layers": args.text_layers, "vision_layers": args.vision_layers,
+                   "valid": full and (args.global_batch or samples == SAMPLES_PER_STEP)},
         "step_tflops": step_tflops, "step_frac_of_sustained_peak": step_tflops / world / peaks["bf16_tflops_sustained"],
-        "step_tflops_executed": world * flop_executed * args.steps / (ms * 1e-3) / 1e12,
+        "step_tflops_executed": world * (per_sample_flop * samples - skipped) * args.steps / (ms * 1e-3) / 1e12,
         "flop_note": ("step_tflops uses the nominal 1.634 PFLOP/step of SURVEY 8d (full-sequence LM head, as the reference "
                       "computes it); step_tflops_executed subtracts the LM-head rows with ignored labels that the fused "
                       "LM-head/CE provably skips (identical loss and gradients)"),
-        "peaks": peaks_src, "gpu_launches": launches, "max_mem_gb": mem_gb, "clocks": clocks, "loss": float(last_loss),
-        "e2e": e2e, "roofline": roof, "roofline_scatter": scat,
+        "peaks": peaks_src, "gpu_launches": r["launches"], "max_mem_gb": r["mem_gb"], "clocks": r["clocks"],
+        "loss": r["loss"], "comm_exposed_ms": r["comm_exposed_ms"] if world > 1 else 0.0,
+        "e2e": e2e, "roofline": roof, "roofline_scatter": scat, "generate": gen,
     }
+    if extras and args.workload == "mllava":
+        # BASELINE configs[2] (Idefics2: NaViT tower + perceiver resampler + Mistral-7B) as a sub-record of the same line
+        del model
+        torch.cuda.empty_cache()
+        try:
+            m2 = build_model(torch, dev, "idefics2", 32, 27)
+            r2 = train_measure(torch, dist, ops, m2, "idefics2", args, 1, 0, dev, max(2, args.steps // 2), 2, False,
+                               SAMPLES_PER_STEP)
+            k2 = max(2, args.steps // 2)
+            v2 = SAMPLES_PER_STEP * T_TEXT * k2 / (r2["ms"] * 1e-3)
+            tf2 = 449e12 * k2 / (r2["ms"] * 1e-3) / 1e12
+            line["idefics2"] = {"metric": "training tokens/sec Mantis-8B-Idefics2 8-img/2048-tok (configs[2])", "value": v2,
+                                "unit": "tokens/s", "ms_per_step": r2["ms"] / k2, "steps": k2, "warmup": 2,
+                                "step_tflops": tf2, "step_frac_of_sustained_peak": tf2 / peaks["bf16_tflops_sustained"],
+                                "micro_batch": r2["micro_batch"], "gpu_launches": r2["launches"], "max_mem_gb": r2["mem_gb"],
+                                "loss": r2["loss"], "trainable_params": r2["n_train"]}
+            del m2, r2
+        except Exception as e:  # noqa
+            line["idefics2"] = {"error": f"{type(e).__name__}: {e}"}
+        torch.cuda.empty_cache()
+        try:
+            line["gpu_incumbent"] = gpu_incumbent(torch, peaks)
+        except Exception as e:  # noqa
+            line["gpu_incumbent"] = {"error": f"{type(e).__name__}: {e}"}
     if not args.no_cpu_baseline and world == 1:
         try:
             cb = cpu_reference_baseline(1, 1)

@@ -52,6 +52,10 @@ int mb200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, long l
 int mb200_norm_bwd_parts(long long n);
 int mb200_rmsnorm_bwd(const void* x, const void* w, const void* dy, const float* rstd, void* dx, float* dw_part,
                       void* dw, int accumulate_dw, int accumulate_dx, long long n, int D, int dtype, void* stream);
+/* dx = rmsnorm backward of dy + dres (the residual-branch gradient that by-passes the norm, llama/modeling_llama.py:
+ * hidden = residual + sublayer(norm(hidden))): one pass instead of the norm backward + autograd's elementwise sum */
+int mb200_rmsnorm_bwd_res(const void* x, const void* w, const void* dy, const float* rstd, const void* dres, void* dx,
+                          float* dw_part, void* dw, int accumulate_dw, long long n, int D, int dtype, void* stream);
 int mb200_layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, long long n,
                         int D, float eps, int dtype, void* stream);
 int mb200_layernorm_bwd(const void* x, const void* w, const void* dy, const float* mean, const float* rstd, void* dx,
@@ -126,9 +130,10 @@ int mb200_adamw_flat(void* p, void* lo, void* g, float* m, float* v, const unsig
  * NULL in join (treated as zero). */
 int mb200_master_split(const float* master, void* hi_bf16, void* lo_u16, long long n, void* stream);
 int mb200_master_join(const void* hi_bf16, const void* lo_u16, float* master, long long n, void* stream);
-/* dst (fp32) += scale * src (src_dtype): folds a gradient autograd produced in the parameter dtype into the fp32 main
- * gradient buffer (what DeepSpeed's fp32 gradient accumulation does). */
-int mb200_accum_f32(float* dst, const void* src, long long n, float scale, int src_dtype, void* stream);
+/* dst (fp32) = (accumulate ? dst : 0) + scale * src (src_dtype): folds a gradient autograd produced in the parameter dtype
+ * into the fp32 main gradient buffer (what DeepSpeed's fp32 gradient accumulation does); accumulate = 0 for the first
+ * micro-batch of an optimizer step (the buffer is then never zero-filled). */
+int mb200_accum_f32(float* dst, const void* src, long long n, float scale, int accumulate, int src_dtype, void* stream);
 int mb200_sumsq(const void* g, long long n, float* out, int dtype, void* stream);
 
 /* ---- GEMM: nn.Linear forward / dgrad / wgrad (llama/modeling_llama.py:171-184,238-249,487; siglip :270-273,

@@ -104,7 +104,8 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __gri
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kt = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
+  const mb::LptIdx li = mb::lpt_index();        // early key tiles see the most queries: they go first, across all kv heads
+  const int kt = li.rank, hk = li.h, b = li.b;
   const int G = p.H / p.Hkv;
   const int k0 = kt * 128;
   const int off = p.Sk - p.Sq;
@@ -294,8 +295,9 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = gridDim.x - 1 - blockIdx.x;
-  const int h = blockIdx.y, b = blockIdx.z;
+  const mb::LptIdx li = mb::lpt_index();        // heavy (late) query tiles first, across all heads
+  const int qt = (int)gridDim.x - 1 - li.rank;
+  const int h = li.h, b = li.b;
   const int hk = h / (p.H / p.Hkv);
   const int q0 = qt * 128;
   const int off = p.Sk - p.Sq;

@@ -49,8 +49,9 @@ attn_fwd2_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pair = gridDim.x - 1 - blockIdx.x;           // heavy (late) causal tiles first
-  const int h = blockIdx.y, b = blockIdx.z;
+  const mb::LptIdx li = mb::lpt_index();                 // heavy (late) causal tiles first, across ALL heads
+  const int pair = (int)gridDim.x - 1 - li.rank;
+  const int h = li.h, b = li.b;
   const int hk = h / (p.H / p.Hkv);
   const int off = p.Sk - p.Sq;
   int q0t[2], nkv[2];

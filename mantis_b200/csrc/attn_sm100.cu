@@ -81,8 +81,9 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   float* sx = reinterpret_cast<float*>(bars + 18);      // [2][128] row-max / row-sum exchange between the column halves
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = gridDim.x - 1 - blockIdx.x;           // heavy (late) causal tiles first
-  const int h = blockIdx.y, b = blockIdx.z;
+  const mb::LptIdx li = mb::lpt_index();               // heavy (late) causal tiles first, across ALL heads
+  const int qt = (int)gridDim.x - 1 - li.rank;
+  const int h = li.h, b = li.b;
   const int hk = h / (p.H / p.Hkv);
   const int q0 = qt * BQ;
   const int off = p.Sk - p.Sq;

@@ -119,6 +119,19 @@ template <> struct Vec8<float> {  // 32 bytes
   }
 };
 
+// Longest-processing-time-first order over a (tiles, heads, batch) grid: CTAs are dispatched in linear blockIdx order, so the
+// tile rank is taken from the SLOW part of the linear index and (head, batch) from the fast part -- every head's heaviest
+// causal tile starts first and the lightest tiles fill the tail (with the natural (x = tile, y = head) mapping the heavy tile
+// of the last head starts after 31/32 of the work has been handed out and runs alone at the end).
+struct LptIdx { int rank, h, b; };
+__device__ __forceinline__ LptIdx lpt_index() {
+  const unsigned L = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  const unsigned nhb = gridDim.y * gridDim.z;
+  const unsigned hb = L % nhb;
+  LptIdx r; r.rank = (int)(L / nhb); r.h = (int)(hb % gridDim.y); r.b = (int)(hb / gridDim.y);
+  return r;
+}
+
 // ---- programmatic dependent launch (PDL): a kernel launched with the attribute may become resident while its
 // predecessor on the stream is still draining; it must call pdl_wait() before touching anything the predecessor writes
 // (and before writing anything the predecessor reads).  Weights are constant, so the decode kernels prefetch them first.

@@ -88,7 +88,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 rmsnorm_bwd_kernel(const T* __restrict__ x, const T* __restrict__ w, const T* __restrict__ dy,
                    const float* __restrict__ rstd_in, T* __restrict__ dx, float* __restrict__ dw_part,
-                   long long n, int D, int accumulate_dx) {
+                   long long n, int D, int accumulate_dx, const T* __restrict__ dres) {
   extern __shared__ float dw_acc[];   // D floats
   __shared__ float red[33];
   for (int i = threadIdx.x; i < D; i += blockDim.x) dw_acc[i] = 0.f;
@@ -107,6 +107,7 @@ rmsnorm_bwd_kernel(const T* __restrict__ x, const T* __restrict__ w, const T* __
       float xh = Cvt<T>::to_f(xr[i]) * rstd, g = Cvt<T>::to_f(gr[i]) * Cvt<T>::to_f(w[i]);
       float v = rstd * (g - xh * dot);
       if (accumulate_dx) v += Cvt<T>::to_f(dxr[i]);
+      if (dres) v += Cvt<T>::to_f(dres[(size_t)r * D + i]);
       dxr[i] = Cvt<T>::from_f(v);
     }
   }
@@ -213,7 +214,8 @@ rmsnorm_fwd_vec_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, b
 template <int NV>
 __global__ void __launch_bounds__(128)
 rmsnorm_bwd_dx_vec_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ dy,
-                          const float* __restrict__ rstd_in, bf16* __restrict__ dx, long long n) {
+                          const float* __restrict__ rstd_in, bf16* __restrict__ dx, long long n,
+                          const bf16* __restrict__ dres /* nullable: gradient of the residual branch, added to dx */) {
   constexpr int D = NV * 256;
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -241,17 +243,23 @@ rmsnorm_bwd_dx_vec_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w
     }
     dot = mb::warp_sum(dot) * rstd / (float)D;       // mean(g*w*xhat)
     int4* dxr = reinterpret_cast<int4*>(dx + (size_t)r * D);
+    const int4* rr = dres ? reinterpret_cast<const int4*>(dres + (size_t)r * D) : nullptr;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       const int4 wv = __ldg(wr + v * 32 + lane);
+      int4 rv = make_int4(0, 0, 0, 0);                 // bf16 zeros
+      if (rr) rv = mb::ld_stream(rr + v * 32 + lane);
       const bf162* xh = reinterpret_cast<const bf162*>(&xv[v]);
       const bf162* gh = reinterpret_cast<const bf162*>(&gv[v]);
       const bf162* wh = reinterpret_cast<const bf162*>(&wv);
+      const bf162* rh = reinterpret_cast<const bf162*>(&rv);
       int4 o; bf162* oh = reinterpret_cast<bf162*>(&o);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 xf = __bfloat1622float2(xh[j]), gf = __bfloat1622float2(gh[j]), wf = __bfloat1622float2(wh[j]);
-        oh[j] = __floats2bfloat162_rn(rstd * (gf.x * wf.x - xf.x * rstd * dot), rstd * (gf.y * wf.y - xf.y * rstd * dot));
+        const float2 rf = __bfloat1622float2(rh[j]);
+        oh[j] = __floats2bfloat162_rn(rstd * (gf.x * wf.x - xf.x * rstd * dot) + rf.x,
+                                      rstd * (gf.y * wf.y - xf.y * rstd * dot) + rf.y);
       }
       mb::st_stream(dxr + v * 32 + lane, o);
     }
@@ -723,18 +731,18 @@ int mb200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, long l
 int mb200_norm_bwd_parts(long long n) {
   long long g = (long long)mb::num_sms() * 2; if (n < g) g = n; if (g < 1) g = 1; return (int)g;
 }
-int mb200_rmsnorm_bwd(const void* x, const void* w, const void* dy, const float* rstd, void* dx,
-                      float* dw_part, void* dw, int accumulate_dw, int accumulate_dx, long long n, int D,
-                      int dtype, void* stream) {
+static int rmsnorm_bwd_impl(const void* x, const void* w, const void* dy, const float* rstd, const void* dres, void* dx,
+                            float* dw_part, void* dw, int accumulate_dw, int accumulate_dx, long long n, int D,
+                            int dtype, void* stream) {
   if (n <= 0) return MB200_OK;
   if (dtype == MB200_DTYPE_BF16 && (D == 4096 || D == 2048 || D == 1024) && !accumulate_dx &&
       !((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) |
-         reinterpret_cast<uintptr_t>(w)) & 15)) {
+         reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(dres)) & 15)) {
     cudaStream_t st = (cudaStream_t)stream;
     long long g = (n + 3) / 4; const long long cap = (long long)mb::num_sms() * 12; if (g > cap) g = cap;
-    if (D == 4096) rmsnorm_bwd_dx_vec_kernel<16><<<(int)g, 128, 0, st>>>((const bf16*)x, (const bf16*)w, (const bf16*)dy, rstd, (bf16*)dx, n);
-    else if (D == 2048) rmsnorm_bwd_dx_vec_kernel<8><<<(int)g, 128, 0, st>>>((const bf16*)x, (const bf16*)w, (const bf16*)dy, rstd, (bf16*)dx, n);
-    else rmsnorm_bwd_dx_vec_kernel<4><<<(int)g, 128, 0, st>>>((const bf16*)x, (const bf16*)w, (const bf16*)dy, rstd, (bf16*)dx, n);
+    if (D == 4096) rmsnorm_bwd_dx_vec_kernel<16><<<(int)g, 128, 0, st>>>((const bf16*)x, (const bf16*)w, (const bf16*)dy, rstd, (bf16*)dx, n, (const bf16*)dres);
+    else if (D == 2048) rmsnorm_bwd_dx_vec_kernel<8><<<(int)g, 128, 0, st>>>((const bf16*)x, (const bf16*)w, (const bf16*)dy, rstd, (bf16*)dx, n, (const bf16*)dres);
+    else rmsnorm_bwd_dx_vec_kernel<4><<<(int)g, 128, 0, st>>>((const bf16*)x, (const bf16*)w, (const bf16*)dy, rstd, (bf16*)dx, n, (const bf16*)dres);
     if (dw && dw_part) {
       const int parts = mb200_norm_bwd_parts(n);
       rmsnorm_bwd_dw_vec_kernel<<<parts, 256, 0, st>>>((const bf16*)x, (const bf16*)dy, rstd, dw_part, n, D);
@@ -747,11 +755,22 @@ int mb200_rmsnorm_bwd(const void* x, const void* w, const void* dy, const float*
   DISPATCH_T(dtype, {
     cudaFuncSetAttribute(rmsnorm_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     rmsnorm_bwd_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>((const T*)x, (const T*)w, (const T*)dy, rstd,
-                                                                   (T*)dx, dw_part, n, D, accumulate_dx);
+                                                                   (T*)dx, dw_part, n, D, accumulate_dx, (const T*)dres);
     if (dw && dw_part)
       colsum_partials_kernel<T><<<(D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dw_part, grid, D, (T*)dw, accumulate_dw);
   });
   MB200_CHECK_LAUNCH(); return MB200_OK;
+}
+int mb200_rmsnorm_bwd(const void* x, const void* w, const void* dy, const float* rstd, void* dx,
+                      float* dw_part, void* dw, int accumulate_dw, int accumulate_dx, long long n, int D,
+                      int dtype, void* stream) {
+  return rmsnorm_bwd_impl(x, w, dy, rstd, nullptr, dx, dw_part, dw, accumulate_dw, accumulate_dx, n, D, dtype, stream);
+}
+// dx = rmsnorm_backward(dy) + dres: the gradient of the residual branch that by-passes the norm is summed in the same pass
+// (autograd would otherwise add the two [n, D] tensors with a separate elementwise kernel).
+int mb200_rmsnorm_bwd_res(const void* x, const void* w, const void* dy, const float* rstd, const void* dres, void* dx,
+                          float* dw_part, void* dw, int accumulate_dw, long long n, int D, int dtype, void* stream) {
+  return rmsnorm_bwd_impl(x, w, dy, rstd, dres, dx, dw_part, dw, accumulate_dw, 0, n, D, dtype, stream);
 }
 
 int mb200_layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd,

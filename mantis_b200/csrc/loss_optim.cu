@@ -271,18 +271,18 @@ master_join_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__
 // dst (fp32) += src (bf16 / fp32): gradients that autograd produced in the parameter dtype folded into the fp32 main gradient
 template <typename T>
 __global__ void __launch_bounds__(256)
-accum_f32_kernel(float* __restrict__ dst, const T* __restrict__ src, long long n, float scale) {
+accum_f32_kernel(float* __restrict__ dst, const T* __restrict__ src, long long n, float scale, int accumulate) {
   const long long n8 = n >> 3;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     float a[8], b[8];
-    mb::Vec8<float>::load(dst + i * 8, a);
+    if (accumulate) mb::Vec8<float>::load(dst + i * 8, a);
     mb::Vec8<T>::load(src + i * 8, b);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] += b[j] * scale;
+    for (int j = 0; j < 8; ++j) a[j] = (accumulate ? a[j] : 0.f) + b[j] * scale;
     mb::Vec8<float>::store(dst + i * 8, a);
   }
   for (long long i = n8 * 8 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    dst[i] += Cvt<T>::to_f(src[i]) * scale;
+    dst[i] = (accumulate ? dst[i] : 0.f) + Cvt<T>::to_f(src[i]) * scale;
 }
 
 // vectorised sum of squares (fp32 / bf16), fp32 partial per CTA then one atomic
@@ -374,14 +374,14 @@ int mb200_master_join(const void* hi_bf16, const void* lo_u16, float* master, lo
   master_join_kernel<<<(int)g0, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)hi_bf16, (const uint16_t*)lo_u16, master, n);
   MB200_CHECK_LAUNCH(); return MB200_OK;
 }
-int mb200_accum_f32(float* dst, const void* src, long long n, float scale, int src_dtype, void* stream) {
+int mb200_accum_f32(float* dst, const void* src, long long n, float scale, int accumulate, int src_dtype, void* stream) {
   if (n <= 0) return MB200_OK;
   if ((reinterpret_cast<uintptr_t>(dst) & 31) || (reinterpret_cast<uintptr_t>(src) & 15)) return -EINVAL;
   long long g0 = ((n >> 3) + 255) / 256; if (g0 < 1) g0 = 1;
   const long long cap = (long long)mb::num_sms() * 8; if (g0 > cap) g0 = cap;
   typedef float F;
-  if (src_dtype == MB200_DTYPE_BF16) accum_f32_kernel<bf16><<<(int)g0, 256, 0, (cudaStream_t)stream>>>(dst, (const bf16*)src, n, scale);
-  else if (src_dtype == MB200_DTYPE_F32) accum_f32_kernel<F><<<(int)g0, 256, 0, (cudaStream_t)stream>>>(dst, (const F*)src, n, scale);
+  if (src_dtype == MB200_DTYPE_BF16) accum_f32_kernel<bf16><<<(int)g0, 256, 0, (cudaStream_t)stream>>>(dst, (const bf16*)src, n, scale, accumulate);
+  else if (src_dtype == MB200_DTYPE_F32) accum_f32_kernel<F><<<(int)g0, 256, 0, (cudaStream_t)stream>>>(dst, (const F*)src, n, scale, accumulate);
   else return -EINVAL;
   MB200_CHECK_LAUNCH(); return MB200_OK;
 }

@@ -119,9 +119,16 @@ class B200DecoderLayer(nn.Module):
         self.post_attention_layernorm = B200RMSNorm(config.hidden_size, eps=config.rms_norm_eps)
 
     def forward(self, x, position_ids, inv_freq, rope_scale, key_mask, cache, kbits=None, rope_tab=None, segs=None):
-        x = self.self_attn(self.input_layernorm(x), x, position_ids, inv_freq, rope_scale, key_mask, cache, kbits, rope_tab,
-                           segs)
-        x = self.mlp(self.post_attention_layernorm(x), residual=x)
+        n1, n2 = self.input_layernorm, self.post_attention_layernorm
+        if torch.is_grad_enabled() and x.requires_grad:
+            # training: the residual stream leaves each norm together with the normed activations, so the two gradients that
+            # meet at x (through the norm and around it) are summed inside the norm's backward kernel
+            h, x = ops.rms_norm_res(x, n1.weight, n1.variance_epsilon)
+            x = self.self_attn(h, x, position_ids, inv_freq, rope_scale, key_mask, cache, kbits, rope_tab, segs)
+            h, x = ops.rms_norm_res(x, n2.weight, n2.variance_epsilon)
+            return self.mlp(h, residual=x)
+        x = self.self_attn(n1(x), x, position_ids, inv_freq, rope_scale, key_mask, cache, kbits, rope_tab, segs)
+        x = self.mlp(n2(x), residual=x)
         return x
 
 

@@ -140,9 +140,13 @@ def colsum(x2d, out=None, accumulate=False):
 
 def _wgrad_into_main(g2, x2, w):
     """main_grad += g2^T @ x2 for a weight whose gradient lives in a B200Trainer flat buffer (`w._b200_main_grad`, an
-    [out, in] view; fp32 by default): accumulation happens in the wgrad epilogue, in the buffer's own precision."""
+    [out, in] view; fp32 by default): accumulation happens in the wgrad epilogue, in the buffer's own precision.  The trainer
+    never zero-fills the buffer: it marks every parameter "fresh" after an optimizer step and the first gradient written
+    afterwards overwrites (B200Trainer._mark_fresh / _fold_grad)."""
     mg = w._b200_main_grad
-    gemm(g2, x2, trans_a=True, trans_b=False, addend=mg, out=mg)
+    fresh = getattr(w, "_b200_grad_fresh", False)      # first product since the optimizer step: write, do not accumulate
+    gemm(g2, x2, trans_a=True, trans_b=False, addend=None if fresh else mg, out=mg)
+    w._b200_grad_fresh = False
 
 
 class _LinearFn(torch.autograd.Function):
@@ -354,6 +358,45 @@ class _RMSNormFn(torch.autograd.Function):
 
 def rms_norm(x, weight, eps):
     return _RMSNormFn.apply(x, weight, eps)
+
+
+class _RMSNormResFn(torch.autograd.Function):
+    """(rms_norm(x), x): the pre-norm residual pattern `h = x + sublayer(norm(x))` (llama/modeling_llama.py decoder layer).
+    The second output is x itself, handed to the residual branch; in backward the gradient arriving through that branch is
+    added inside the norm's dx pass (mb200_rmsnorm_bwd_res) instead of by a separate elementwise kernel of autograd."""
+
+    @staticmethod
+    def forward(ctx, x, w, eps):
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1]).contiguous()
+        n, D = x2.shape
+        y = torch.empty_like(x2)
+        rstd = torch.empty((n,), dtype=torch.float32, device=x.device)
+        w = w.contiguous()
+        _call("mb200_rmsnorm_fwd", _p(x2), _p(w), _p(y), _p(rstd), n, D, float(eps), _dt(x2), _st())
+        ctx.save_for_backward(x2, w, rstd)
+        ctx.shp = shp
+        return y.reshape(shp), x.view(shp)
+
+    @staticmethod
+    def backward(ctx, dy, dres):
+        x2, w, rstd = ctx.saved_tensors
+        n, D = x2.shape
+        dy2 = dy.reshape(-1, D).contiguous()
+        dr2 = dres.reshape(-1, D).contiguous() if dres is not None else None
+        dx = torch.empty_like(x2)
+        parts = _L().mb200_norm_bwd_parts(n)
+        need_w = ctx.needs_input_grad[1]
+        dw_part = torch.empty((parts, D), dtype=torch.float32, device=x2.device) if need_w else None
+        dw = torch.empty_like(w) if need_w else None
+        _call("mb200_rmsnorm_bwd_res", _p(x2), _p(w), _p(dy2), _p(rstd), _p(dr2), _p(dx), _p(dw_part), _p(dw), 0, n, D,
+              _dt(x2), _st())
+        return dx.reshape(ctx.shp), dw, None
+
+
+def rms_norm_res(x, weight, eps):
+    """-> (rms_norm(x), x) with the residual branch's gradient folded into the norm's backward"""
+    return _RMSNormResFn.apply(x, weight, eps)
 
 
 class _LayerNormFn(torch.autograd.Function):
@@ -1108,10 +1151,10 @@ def master_join(hi, lo, out=None):
     return out
 
 
-def accum_f32(dst, src, scale=1.0):
-    """dst (fp32, contiguous) += scale * src (bf16 / fp32, contiguous, same numel)"""
+def accum_f32(dst, src, scale=1.0, accumulate=True):
+    """dst (fp32, contiguous) = (dst if accumulate else 0) + scale * src (bf16 / fp32, contiguous, same numel)"""
     assert dst.dtype == torch.float32 and dst.is_contiguous() and src.is_contiguous() and dst.numel() == src.numel()
-    _call("mb200_accum_f32", _p(dst), _p(src), dst.numel(), float(scale), _dt(src), _st())
+    _call("mb200_accum_f32", _p(dst), _p(src), dst.numel(), float(scale), int(bool(accumulate)), _dt(src), _st())
 
 
 def sumsq(g, out):

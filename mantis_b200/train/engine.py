@@ -126,6 +126,7 @@ class B200Trainer:
             for n, p in model.named_parameters():
                 if "vision_tower" in n or "vision_model" in n:
                     p.requires_grad_(False)
+        self._handles = []
         self.params, self._layer_ranges = self._ordered_params(model)
         self.state = FlatState(self.params, grad_dtype=grad_dtype)
         self.flat_grad = self.state.G
@@ -143,7 +144,7 @@ class B200Trainer:
             p._b200_unfused_main_grad = p._b200_main_grad
             if id(p) not in fused:
                 p._b200_main_grad = None                       # ops._LinearFn: not a fused-wgrad weight
-            p.register_post_accumulate_grad_hook(self._fold_grad)
+            self._handles.append(p.register_post_accumulate_grad_hook(self._fold_grad))
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.max_grad_norm = max_grad_norm
         self.grad_accum = grad_accum
@@ -163,10 +164,14 @@ class B200Trainer:
         g = p.grad
         if g is None:
             return
+        fresh = getattr(p, "_b200_grad_fresh", False)
         if g.is_cuda and mg.dtype == torch.float32:
-            ops.accum_f32(mg.reshape(-1), g.contiguous().view(-1))
-        else:                                  # bf16 main gradient, or the CPU/gloo plumbing tests (no kernels there)
+            ops.accum_f32(mg.reshape(-1), g.contiguous().view(-1), accumulate=not fresh)
+        elif fresh:                            # bf16 main gradient, or the CPU/gloo plumbing tests (no kernels there)
+            mg.copy_(g)
+        else:
             mg.add_(g.to(mg.dtype))
+        p._b200_grad_fresh = False
         p.grad = None
 
     @staticmethod
@@ -239,8 +244,23 @@ class B200Trainer:
             return hook
 
         for i, layer in enumerate(layers):
-            layer.register_forward_pre_hook(make_hook(i))
+            self._handles.append(layer.register_forward_pre_hook(make_hook(i)))
         self._has_hooks = True
+
+    def close(self):
+        """Detach the trainer from the model: hooks removed, gradient / moment / master-low buffers released (112 GB for
+        Mantis-8B).  The weights stay where they are (the flat bf16 buffer), so the model keeps working, e.g. for generate()."""
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+        for p in self.params:
+            for name in ("_b200_main_grad", "_b200_unfused_main_grad"):
+                if hasattr(p, name):
+                    delattr(p, name)
+        st = self.state
+        st.G = st.M = st.V = st.LO = None
+        self.flat_grad = None
+        self._has_hooks = False
 
     def current_lr(self):
         """learning rate of the NEXT optimizer step (scheduler value after `step_count` completed steps)"""
@@ -277,6 +297,20 @@ class B200Trainer:
 
     def zero_grad(self):
         self.flat_grad.zero_()
+        for p in self.params:
+            p._b200_grad_fresh = False
+
+    def _mark_fresh(self):
+        """after an optimizer step nothing is zero-filled: the next gradient written to a parameter's slice overwrites it"""
+        for p in self.params:
+            p._b200_grad_fresh = True
+
+    def _zero_untouched(self):
+        """a parameter that received no gradient since the last optimizer step still holds the previous step's: clear it"""
+        for p in self.params:
+            if getattr(p, "_b200_grad_fresh", False):
+                p._b200_unfused_main_grad.zero_()
+                p._b200_grad_fresh = False
 
     def micro_step(self, batch):
         """forward + backward of one micro-batch (gradients accumulate). Returns the detached loss."""
@@ -292,8 +326,14 @@ class B200Trainer:
 
     def reduce_gradients(self):
         """the one collective of the data-parallel path: sum the flat gradient buffer over ranks (the part not already
-        reduced under the last backward).  Returns the scale (1/world) still to be applied (folded into AdamW)."""
+        reduced under the last backward).  Returns the scale (1/world) still to be applied (folded into AdamW).
+        With `time_comm` set, the time the compute stream spends in / waiting on collectives after backward (the EXPOSED part of
+        the exchange) is bracketed with CUDA events; read it with exposed_comm_ms() after a synchronize."""
         if self.world > 1:
+            timing = getattr(self, "time_comm", False) and self.flat_grad.is_cuda
+            if timing:
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
             rf = getattr(self, "_reduced_from", None)
             hi = rf if rf is not None else self.flat_grad.numel()
             if hi > 0:
@@ -302,10 +342,19 @@ class B200Trainer:
                 w.wait()
             self._works = []
             self._reduced_from = None
+            if timing:
+                e1.record()
+                self.__dict__.setdefault("_comm_events", []).append((e0, e1))
         return 1.0 / self.world
+
+    def exposed_comm_ms(self):
+        """sum of the bracketed collective waits since the last call (call after torch.cuda.synchronize())"""
+        evs = self.__dict__.pop("_comm_events", [])
+        return float(sum(a.elapsed_time(b) for a, b in evs))
 
     def optimizer_step(self):
         self._check_views()
+        self._zero_untouched()
         scale = self.reduce_gradients()
         st = self.state
         clip = self.max_grad_norm is not None and self.max_grad_norm > 0
@@ -317,7 +366,8 @@ class B200Trainer:
         self.step_count += 1
         ops.adamw_flat(st.P, st.LO, st.G, st.M, st.V, st.groups, lr, self.betas[0], self.betas[1], self.eps, self.wd,
                        self.step_count, grad_scale=scale, norm_sq=self._norm if clip else None,
-                       max_norm=self.max_grad_norm if clip else 0.0, zero_grad=True)
+                       max_norm=self.max_grad_norm if clip else 0.0, zero_grad=False)
+        self._mark_fresh()
 
     def grad_norm(self):
         """global gradient norm of the last optimizer step (after the 1/world scale, before clipping); one host read-back"""

@@ -52,7 +52,16 @@ def test_bf16_training_at_reference_lr_moves_the_weights(cuda):
         # bf16 weight == round-to-nearest of its master (exact ties aside)
         assert (p.detach().view(torch.int16) == now.bfloat16().view(torch.int16)).float().mean().item() > 0.999
     assert min(moved) > 0.99, moved
-    assert tr.flat_grad.abs().sum().item() == 0                 # zeroed by the optimizer launch
+    # the main gradient is never zero-filled: after a step every parameter is marked "fresh" and the next gradient overwrites
+    assert all(p._b200_grad_fresh for p in tr.params)
+    g_before = tr.flat_grad.clone()
+    tr.micro_step(b)
+    assert not any(p._b200_grad_fresh for p in tr.params)
+    tr2_model = load_model(fx, torch.bfloat16, cuda).train()
+    tr2_model.load_state_dict(model.state_dict())
+    tr2 = B200Trainer(tr2_model, lr=1e-5, grad_accum=1, max_grad_norm=1.0)
+    tr2.micro_step(b)                                            # same weights, gradient buffer that started from zeros
+    assert torch.equal(tr.flat_grad, tr2.flat_grad) and not torch.equal(tr.flat_grad, g_before)
     sd = tr.state_dict()
     assert all(m.dtype == torch.float32 for m in sd["master_params"])
     assert 0 < tr.grad_norm() < 1e4
