@@ -46,6 +46,9 @@ def parse():
                          "micro-batches of one sample per rank per optimizer step); default 0 = weak scaling, --samples per rank")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the sub-records of the N=1 line (generate configs[4], idefics2 configs[2], gpu_incumbent)")
+    ap.add_argument("--no-hints", action="store_true",
+                    help="do not attach the collator's host-side hints (merged length / supervised-row count): the merge and the "
+                         "LM-head compaction then read their sizes back from the device (2 host syncs per micro-batch)")
     ap.add_argument("--new-tokens", type=int, default=512, help="generate(): new tokens per sequence (configs[4]: 512)")
     ap.add_argument("--workload", default="mllava", choices=["mllava", "idefics2"],
                     help="mllava = BASELINE configs[1] (the headline); idefics2 = configs[2] (perceiver-resampler path)")
@@ -398,13 +401,25 @@ def train_measure(torch, dist, ops, model, workload, args, world, rank, dev, ste
     if mb > 1:                                   # same-shape synthetic samples: a micro-batch is a plain concatenation
         host = [{k: torch.cat([s[k] for s in host[i:i + mb]], dim=0) for k in host[0]} for i in range(0, len(host), mb)]
     host = [{k: v.pin_memory() for k, v in s.items()} for s in host]
-    resident = [{k: v.to(dev, non_blocking=True) for k, v in s.items()} for s in host]
+    # what train.Collator attaches to a batch from the HOST copies of input_ids / labels (merged length, padding side, number of
+    # supervised rows): with it neither the image-token merge nor the LM-head row compaction reads anything back from the device
+    from mantis_b200.train import llava_valid_rows, plain_valid_rows
+    if workload == "idefics2":
+        hints = [{"valid_rows": plain_valid_rows(s["labels"], s["attention_mask"], 32001)} for s in host]
+    else:
+        hints = [{"max_image_tokens": N_IMG, "left_padding": True,
+                  "valid_rows": llava_valid_rows(s["input_ids"], s["labels"], s["attention_mask"], IMG_TOKEN, True)} for s in host]
+    if args.no_hints:
+        hints = [None] * len(host)
+    resident = [dict({k: v.to(dev, non_blocking=True) for k, v in s.items()}, **({"merge_hint": h} if h else {}))
+                for s, h in zip(host, hints)]
     torch.cuda.synchronize()
     h2d = sum(v.numel() * v.element_size() for s in host for v in s.values())
 
     def step(e2e):
         if e2e:
-            batches = [{k: v.to(dev, non_blocking=True) for k, v in s.items()} for s in host]
+            batches = [dict({k: v.to(dev, non_blocking=True) for k, v in s.items()}, **({"merge_hint": h} if h else {}))
+                       for s, h in zip(host, hints)]
         else:
             batches = resident
         loss = trainer.train_step(batches)

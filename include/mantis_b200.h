@@ -110,6 +110,10 @@ int mb200_shift_labels(const int64_t* labels, const int64_t* mask, int64_t* out,
 int mb200_ce_fwd_bwd(const void* logits, const int64_t* labels, float* loss_rows, float* lse_rows, void* dlogits,
                      long long n, int V, long long ld, const float* gscale_ptr, float gscale_const, int dtype,
                      void* stream);
+/* idx_out[j] = index of the j-th row with labels[row] >= 0 (ascending; at most cap entries written), *count_out = their number.
+ * Replaces the boolean-mask gather of the reference's loss (modeling_llava.py:526-531 `shift_logits[shift_attention_mask != 0]`
+ * + ignore_index) and the host read-back its data-dependent size costs: the caller knows the count from the host labels. */
+int mb200_compact_valid_rows(const int64_t* labels, long long n, int64_t* idx_out, long long cap, int* count_out, void* stream);
 int mb200_ce_reduce(const float* loss_rows, const int64_t* labels, long long n, int V, float* out2, int accumulate,
                     void* stream);
 /* Fused AdamW over FLAT parameter / gradient / moment buffers (one launch per optimizer step) with fp32 master weights.

@@ -177,6 +177,41 @@ sumsq_kernel(const T* __restrict__ g, long long n, float* __restrict__ out) {
 }
 
 
+// ------------------------------------------------------------------ row compaction for the LM head
+// idx_out[j] = i for the j-th row with labels[i] >= 0 (ascending order), *count_out = number of such rows.  The reference gathers
+// the rows whose shifted label is not ignored AFTER computing every row's logits (modeling_llava.py:526-531); here they are
+// compacted before the LM-head GEMMs.  One CTA (n is a sequence length: <= a few 10^4), ballot + warp-sum scan per 1024 rows;
+// the output length is known on the host from the collator's label count, so nothing is read back.
+__global__ void __launch_bounds__(1024)
+compact_valid_rows_kernel(const int64_t* __restrict__ labels, long long n, int64_t* __restrict__ idx_out, long long cap,
+                          int* __restrict__ count_out) {
+  __shared__ int warp_sums[32];
+  __shared__ int base_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) base_s = 0;
+  __syncthreads();
+  for (long long start = 0; start < n; start += 1024) {
+    const long long i = start + tid;
+    const bool flag = (i < n) && (labels[i] >= 0);
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    const int prefix = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) warp_sums[wid] = __popc(bal);
+    __syncthreads();
+    int v = warp_sums[lane];                       // every warp scans the 32 warp totals itself (no second barrier needed)
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    const int excl_w = __shfl_sync(0xffffffffu, incl - v, wid);
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const long long pos = (long long)base_s + excl_w + prefix;
+    if (flag && pos < cap) idx_out[pos] = i;
+    __syncthreads();
+    if (tid == 0) base_s += total;
+    __syncthreads();
+  }
+  if (tid == 0) *count_out = base_s;
+}
+
 // ------------------------------------------------------------------ flat AdamW with fp32 master weights
 // The reference recipe (mantis/train/scripts/train_mllava.sh:148,162 `--bf16 True --learning_rate 1e-5`,
 // zero_configs/zero3.json "bf16": enabled) keeps an fp32 master copy of every weight inside DeepSpeed's optimizer; the
@@ -336,6 +371,11 @@ int mb200_shift_labels(const int64_t* labels, const int64_t* mask, int64_t* out,
   long long total = (long long)B * S;
   int grid = (int)((total + 255) / 256); if (grid > mb::num_sms() * 4) grid = mb::num_sms() * 4;
   shift_labels_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(labels, mask, out, B, S, ignore_index, count_out);
+  MB200_CHECK_LAUNCH(); return MB200_OK;
+}
+int mb200_compact_valid_rows(const int64_t* labels, long long n, int64_t* idx_out, long long cap, int* count_out, void* stream) {
+  if (n < 0 || cap < 0) return -EINVAL;
+  compact_valid_rows_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(labels, n, idx_out, cap, count_out);
   MB200_CHECK_LAUNCH(); return MB200_OK;
 }
 int mb200_adamw_flat(void* p, void* lo, void* g, float* m, float* v, const unsigned char* blk_group, long long n, float lr,

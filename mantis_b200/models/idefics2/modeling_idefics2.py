@@ -394,7 +394,9 @@ class Idefics2ForConditionalGeneration(Idefics2PreTrainedModel, GenerationMixin)
                 loss = ops.cross_entropy(lg.reshape(-1, lg.shape[-1]), eff.reshape(-1), count)
             logits = lg.float()                                                                      # ref:1884
         elif labels is not None:
-            loss = ops.lm_head_ce(hidden, self.lm_head.weight, eff, count)
+            hint = kw.get("merge_hint")                                  # {"valid_rows": n} from the collator: no read-back
+            loss = ops.lm_head_ce(hidden, self.lm_head.weight, eff, count,
+                                  valid_rows_hint=hint.get("valid_rows") if hint else None)
         return Idefics2CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=outputs.past_key_values,
                                               hidden_states=outputs.hidden_states, attentions=None,
                                               image_hidden_states=outputs.image_hidden_states)

@@ -230,7 +230,9 @@ class LlavaForConditionalGeneration(LlavaPreTrainedModel, GenerationMixin):
             if labels is not None and not (isinstance(logits_to_keep, int) and logits_to_keep > 0):
                 loss = ops.cross_entropy(logits.reshape(-1, logits.shape[-1]), eff.reshape(-1), count)
         elif labels is not None:
-            loss = ops.lm_head_ce(hidden, lm.lm_head.weight, eff, count)
+            hint = kwargs.get("merge_hint") if merged else None          # the collator's host-side count of supervised rows
+            loss = ops.lm_head_ce(hidden, lm.lm_head.weight, eff, count,
+                                  valid_rows_hint=hint.get("valid_rows") if hint else None)
         if labels is None and merged:
             # reference :475-476 substitutes all-ignore labels, so its loss is the mean over zero rows == NaN
             loss = torch.full((), float("nan"), dtype=torch.float32, device=hidden.device)

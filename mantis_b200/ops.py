@@ -950,7 +950,7 @@ class _LMHeadCEFn(torch.autograd.Function):
     compacted away *before* the LM-head GEMMs (LM_HEAD_SKIP_IGNORED): identical loss / gradients, fewer FLOPs."""
 
     @staticmethod
-    def forward(ctx, hidden, weight, eff_labels, count):
+    def forward(ctx, hidden, weight, eff_labels, count, valid_rows_hint=None):
         h2 = hidden.reshape(-1, hidden.shape[-1])
         if h2.stride(1) != 1:
             h2 = h2.contiguous()
@@ -961,7 +961,17 @@ class _LMHeadCEFn(torch.autograd.Function):
         need_h, need_w = hidden.requires_grad, weight.requires_grad
         idx = None
         if LM_HEAD_SKIP_IGNORED:
-            idx = (lab >= 0).nonzero(as_tuple=False).squeeze(1)       # one host sync (row count)
+            if valid_rows_hint is not None:
+                # sync-free: the collator counted the supervised rows on the host (train.data.Collator `valid_rows`); the device
+                # count is compared with it at the caller's next sync point (ops.check_deferred)
+                n_hint = int(valid_rows_hint)
+                idx = torch.empty((n_hint,), dtype=torch.int64, device=dev)
+                cnt = torch.empty((1,), dtype=torch.int32, device=dev)
+                _call("mb200_compact_valid_rows", _p(lab.contiguous()), n_all, _p(idx), n_hint, _p(cnt), _st())
+                _defer_check(cnt[0] == n_hint, f"loss: the batch's `valid_rows` hint ({n_hint}) does not match the number of "
+                                               "supervised positions after the image-token merge")
+            else:
+                idx = (lab >= 0).nonzero(as_tuple=False).squeeze(1)       # one host sync (row count)
             if idx.numel() == n_all:
                 idx = None
         if idx is not None:
@@ -1013,11 +1023,11 @@ class _LMHeadCEFn(torch.autograd.Function):
             gh = (dh * gloss.to(dh.dtype)).reshape(ctx.shape)
         if dw is not None:
             gw = dw * gloss.to(dw.dtype)
-        return gh, gw, None, None
+        return gh, gw, None, None, None
 
 
-def lm_head_ce(hidden, weight, eff_labels, count):
-    return _LMHeadCEFn.apply(hidden, weight, eff_labels, count)
+def lm_head_ce(hidden, weight, eff_labels, count, valid_rows_hint=None):
+    return _LMHeadCEFn.apply(hidden, weight, eff_labels, count, valid_rows_hint)
 
 
 class _CEFn(torch.autograd.Function):

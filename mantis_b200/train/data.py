@@ -13,6 +13,31 @@ from typing import Dict, List
 import torch
 
 
+def llava_valid_rows(input_ids, labels, attention_mask, image_token_index, left_padding, ignore_index=-100):
+    """Number of supervised rows of the SHIFTED loss after the image-token merge, from the host copies of the batch (no device
+    work): the count the model would otherwise read back to size the compacted LM-head GEMMs.
+    ref modeling_llava.py:293-360 + 523-531: a text token keeps its label and mask, image slots and alignment padding get
+    ignore_index / mask 0, and the loss pairs logits[s] with labels[s+1] where mask[s+1] != 0 -- so every valid text token
+    counts except one sitting on merged position 0, which is original token 0 of a row that is not shifted right (right padding,
+    or a left-padded row carrying the batch's maximum number of images)."""
+    is_img = input_ids == image_token_index
+    valid = (labels != ignore_index) & ~is_img
+    if attention_mask is not None and attention_mask.dim() == 2:
+        valid &= attention_mask != 0
+    n_img = is_img.sum(dim=-1)
+    at_zero = (n_img == n_img.max()) if left_padding else torch.ones_like(n_img, dtype=torch.bool)
+    return int(valid.sum()) - int((valid[:, 0] & at_zero).sum())
+
+
+def plain_valid_rows(labels, attention_mask, ignore_index):
+    """same for models whose sequence is not expanded by a merge (Idefics2/3: ref modeling_idefics2.py:1883-1899): positions
+    1.. whose label is not `ignore_index` and whose mask is set"""
+    valid = labels[:, 1:] != ignore_index
+    if attention_mask is not None and attention_mask.dim() == 2:
+        valid = valid & (attention_mask[:, 1:] != 0)
+    return int(valid.sum())
+
+
 class Collator:
     def __init__(self, processor=None, max_length=None, pad_token_id=None, label_pad=-100, image_token_index=None):
         self.processor = processor
@@ -24,10 +49,14 @@ class Collator:
         # <image> placeholders in a row and the padding side, both from the host copy of input_ids
         self.image_token_index = image_token_index
 
-    def merge_hint(self, input_ids, pad_token_id):
+    def merge_hint(self, input_ids, pad_token_id, labels=None, attention_mask=None):
         n = int((input_ids == self.image_token_index).sum(dim=-1).max())
         left = not bool((input_ids[:, -1] == pad_token_id).any())          # ref: modeling_llava.py:296
-        return {"max_image_tokens": n, "left_padding": left}
+        hint = {"max_image_tokens": n, "left_padding": left}
+        if labels is not None:
+            hint["valid_rows"] = llava_valid_rows(input_ids, labels, attention_mask, self.image_token_index, left,
+                                                  self.label_pad)
+        return hint
 
     def _pad_id(self):
         if self.pad_token_id is not None:
@@ -84,7 +113,7 @@ class Collator:
                 # (data.py:1529)
                 out[k] = torch.cat(vals, dim=0)
         if self.image_token_index is not None and out.get("input_ids") is not None and "cu_segments" not in out:
-            out["merge_hint"] = self.merge_hint(out["input_ids"], self._pad_id())
+            out["merge_hint"] = self.merge_hint(out["input_ids"], self._pad_id(), out.get("labels"), out.get("attention_mask"))
         return out
 
 

@@ -171,3 +171,53 @@ def test_collator_max_length_leaves_packed_rows_alone():
     plain = [{k: v for k, v in ds[i].items() if k != "pixel_values"} for i in (0, 1)]
     out = Collator(pad_token_id=7, max_length=4)([dict(x) for x in plain])
     assert out["input_ids"].shape[1] == 4 and out["labels"].shape[1] == 4
+
+
+def test_llava_valid_rows_hint_matches_the_merge_oracle():
+    """the collator's host-side count of supervised rows (what lets the LM-head row compaction run without a device read-back)
+    == the count obtained by actually merging (numpy restatement of ref modeling_llava.py:293-360, pinned to the reference in
+    tests/test_oracle.py) and applying the shifted loss mask of :523-531 -- left / right padding, uneven image counts, masked
+    text tokens, ignored labels, image placeholder at position 0"""
+    import numpy as np
+    from oracle.merge_oracle import merge_oracle
+    from mantis_b200.train import llava_valid_rows
+    rng = np.random.default_rng(0)
+    IMG, PAD = 90, 91
+    for trial in range(300):
+        B, T, P, D = int(rng.integers(1, 5)), int(rng.integers(4, 24)), int(rng.integers(2, 6)), 2
+        left = bool(rng.integers(0, 2))
+        ids = rng.integers(1, 80, size=(B, T))
+        att = np.ones((B, T), dtype=np.int64)
+        n_img = []
+        for b in range(B):
+            npad = int(rng.integers(0, T // 2)) if B > 1 else 0
+            if b == 0 and not left:
+                npad = max(npad, 1) if B > 1 else 0           # right padding is recognised by a pad token in the last column
+            if left and b == 0:
+                npad = 0                                      # left padding: no pad in the last column of any row
+            body = T - npad
+            k = int(rng.integers(0, min(3, body) + 1))
+            pos = rng.choice(body, size=k, replace=False)
+            row = ids[b, :body].copy(); row[pos] = IMG
+            if left:
+                ids[b, npad:] = row; ids[b, :npad] = PAD; att[b, :npad] = 0
+            else:
+                ids[b, :body] = row; ids[b, body:] = PAD; att[b, body:] = 0
+            n_img.append(k)
+        if not left and not (ids[:, -1] == PAD).any():
+            continue                                          # would be classified as left padding by the reference
+        labels = ids.copy()
+        labels[rng.random((B, T)) < 0.3] = -100
+        labels[ids == IMG] = -100
+        att[(rng.random((B, T)) < 0.1) & (ids != IMG)] = 0     # a few masked text tokens
+        feats = np.ones((sum(n_img), P, D), dtype=np.float32)
+        emb = np.ones((B, T, D), dtype=np.float32) * 0.5
+        emb[ids == PAD] = 0.5                                  # pad rows are ordinary (non-zero) text rows in this check
+        try:
+            _, fmask, flabels, _, _ = merge_oracle(feats, emb, ids, att, labels, IMG, PAD)
+        except ValueError:
+            continue
+        expect = int(((flabels[:, 1:] != -100) & (fmask[:, 1:] != 0)).sum())
+        is_left = not bool((ids[:, -1] == PAD).any())
+        got = llava_valid_rows(torch.from_numpy(ids), torch.from_numpy(labels), torch.from_numpy(att), IMG, is_left)
+        assert got == expect, (trial, left, ids.tolist(), labels.tolist(), att.tolist(), got, expect)

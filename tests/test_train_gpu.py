@@ -78,3 +78,36 @@ def test_training_reduces_loss(cuda):
     for n, p in model.named_parameters():
         if "vision_tower" in n:
             assert not p.requires_grad
+
+
+@pytest.mark.parametrize("name", ["llava_siglip_full.pt", "llava_batch_pad.pt"])
+def test_collator_hints_make_the_step_sync_free_with_identical_results(cuda, name):
+    """train.Collator's host-side hints (merged length, padding side, supervised-row count) replace the two device read-backs of a
+    micro-batch (merge plan header, LM-head row compaction size); loss and every gradient are bit-identical, and a wrong hint
+    is reported by ops.check_deferred()"""
+    from mantis_b200 import ops
+    from mantis_b200.train import Collator
+    fx = load_fixture(name)
+    model = load_model(fx, torch.float32, cuda).train()
+    b = _batch(fx, cuda, torch.float32)
+    pad = fx["meta"]["cfg_kwargs"]["pad_token_id"]
+    col = Collator(pad_token_id=pad, image_token_index=fx["meta"]["cfg_kwargs"]["image_token_index"])
+    hint = col.merge_hint(fx["input_ids"], pad, fx["labels"], fx["attention_mask"])
+    assert set(hint) == {"max_image_tokens", "left_padding", "valid_rows"}
+
+    def run(**extra):
+        model.zero_grad(set_to_none=True)
+        out = model(**b, **extra)
+        out.loss.backward()
+        return out.loss.detach().clone(), {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+
+    l0, g0 = run()
+    l1, g1 = run(merge_hint=hint)
+    ops.check_deferred()                              # nothing to report
+    assert torch.equal(l0, l1) and abs(l1.item() - fx["loss"].item()) < 1e-4
+    assert g0.keys() == g1.keys() and all(torch.equal(g0[k], g1[k]) for k in g0)
+    bad = dict(hint, valid_rows=hint["valid_rows"] - 1)
+    model.zero_grad(set_to_none=True)
+    model(**b, merge_hint=bad)
+    with pytest.raises(ValueError, match="valid_rows"):
+        ops.check_deferred()
