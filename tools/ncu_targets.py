@@ -21,6 +21,10 @@ if which in ("gemm", "gemm2cta"):
         ops.gemm(x, w)                                   # fwd  gate/up
         ops.gemm(g, w, trans_a=False, trans_b=False)     # dgrad
         ops.gemm(g, x, trans_a=True, trans_b=False)      # wgrad
+elif which == "cublas":                                  # the incumbent at the same shape, for a side-by-side ncu capture
+    x = torch.randn(M, 4096, device=dev).bfloat16(); w = (torch.randn(14336, 4096, device=dev) * 0.02).bfloat16()
+    for _ in range(4):
+        torch.matmul(x, w.t())
 elif which == "attn":
     q = torch.randn(1, M, 32, 128, device=dev).bfloat16(); k = torch.randn(1, M, 8, 128, device=dev).bfloat16()
     v = torch.randn(1, M, 8, 128, device=dev).bfloat16()
