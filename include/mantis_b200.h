@@ -155,6 +155,17 @@ int mb200_gemm_bf16(const void* A, const void* B, void* C, const void* bias, con
  * memory -- the weight-gradient product dW += dy^T x into the fp32 main-gradient buffer (same operand rules as above). */
 int mb200_gemm_bf16_acc32(const void* A, const void* B, float* C32, int M, int N, int K, long long lda, long long ldb,
                           long long ldc, int transA, int transB, int accumulate, void* stream);
+/* SwiGLU MLP with the activation fused into the projections around it (llama/modeling_llama.py:182-184
+ * `down_proj(act_fn(gate_proj(x)) * up_proj(x))`; idefics2 :506-521), same tcgen05 kernels and operand rules as above:
+ *   swiglu_fwd: U[M,N] = X[M,K] Wu[N,K]^T, Act[M,N] = silu(G) * U  (G = the gate projection computed just before; U is kept for
+ *               backward).  Replaces the up-projection GEMM + the elementwise SwiGLU kernel.
+ *   swiglu_bwd: d_act[M,N] = dY[M,K] Wd[K,N] is formed in TMEM only; dG = d_act * U * silu'(G), dU = d_act * silu(G) are
+ *               written.  Replaces the down-projection dgrad GEMM + the elementwise SwiGLU backward.
+ * G, U, Act, dG, dU share the leading dimension ld; arithmetic and bf16 rounding points equal mb200_swiglu_fwd / _bwd. */
+int mb200_gemm_bf16_swiglu_fwd(const void* X, const void* Wu, const void* G, void* U, void* Act, int M, int N, int K,
+                               long long lda, long long ldb, long long ld, void* stream);
+int mb200_gemm_bf16_swiglu_bwd(const void* dY, const void* Wd, const void* G, const void* U, void* dG, void* dU, int M, int N,
+                               int K, long long lda, long long ldb, long long ld, void* stream);
 /* CTA-pair (cta_group::2, 256x256 tile per SM pair) variant of mb200_gemm_bf16; identical contract. */
 int mb200_gemm_bf16_2cta(const void* A, const void* B, void* C, const void* bias, const void* addend, int M, int N, int K,
                          long long lda, long long ldb, long long ldc, long long ld_add, int transA, int transB, int act,

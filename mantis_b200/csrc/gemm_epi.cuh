@@ -15,7 +15,72 @@ struct GemmEpi {
   const void* addend; long long ld_add; // same element type as C
   int act;                              // 0 none, 1 gelu(erf), 2 gelu(tanh), 3 quick_gelu
   int c_f32;                            // 1: C / addend are fp32
+  // SwiGLU fused into the projections around it (llama/modeling_llama.py:182-184 `down(act(gate(x)) * up(x))`):
+  //   mode 1 (up-projection forward):   acc = u.   C = u, C2 = silu(aux0 = gate) * u
+  //   mode 2 (down-projection dgrad):   acc = d_act. C = d_gate, C2 = d_up from aux0 = gate, aux1 = up
+  // -- the elementwise kernels (3 resp. 5 passes over [tokens, 14336]) disappear into epilogues that have time to spare.
+  int mode;
+  const bf16* aux0; const bf16* aux1; long long ld_aux;
+  bf16* C2; long long ldc2;
 };
+
+struct SwigluArgs { int mode; const bf16* aux0; const bf16* aux1; long long ld_aux; bf16* C2; long long ldc2; };
+
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// 8 consecutive bf16 <-> floats
+__device__ __forceinline__ void ld8(const bf16* p, float* f) {
+  const int4 v = *reinterpret_cast<const int4*>(p);
+  const bf162* h = reinterpret_cast<const bf162*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { const float2 t = __bfloat1622float2(h[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+}
+__device__ __forceinline__ void st8(bf16* p, const float* f) {
+  int4 v; bf162* h = reinterpret_cast<bf162*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+  *reinterpret_cast<int4*>(p) = v;
+}
+
+// same arithmetic (and the same bf16 rounding points) as swiglu_fwd_kernel / swiglu_bwd_kernel in elementwise.cu
+__device__ __forceinline__ void swiglu_store32(const GemmEpi& epi, int row, int col0, int N, float (&v)[32]) {
+  bf16* c1 = reinterpret_cast<bf16*>(epi.C) + (size_t)row * epi.ldc + col0;
+  bf16* c2 = epi.C2 + (size_t)row * epi.ldc2 + col0;
+  const bf16* g0 = epi.aux0 + (size_t)row * epi.ld_aux + col0;
+  const bf16* u0 = epi.aux1 ? epi.aux1 + (size_t)row * epi.ld_aux + col0 : nullptr;
+  const bool vec = (col0 + 32 <= N) && !((epi.ldc | epi.ldc2 | epi.ld_aux) & 7) &&
+                   !((reinterpret_cast<uintptr_t>(epi.C) | reinterpret_cast<uintptr_t>(epi.C2) | reinterpret_cast<uintptr_t>(epi.aux0) |
+                      reinterpret_cast<uintptr_t>(epi.aux1)) & 15);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float g[8], u[8], o1[8], o2[8];
+    if (vec) { ld8(g0 + q * 8, g); if (u0) ld8(u0 + q * 8, u); }
+    else {
+      for (int j = 0; j < 8; ++j) {
+        const bool ok = col0 + q * 8 + j < N;
+        g[j] = ok ? __bfloat162float(g0[q * 8 + j]) : 0.f;
+        u[j] = (ok && u0) ? __bfloat162float(u0[q * 8 + j]) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float acc = bf16_round(v[q * 8 + j]);          // the value the unfused path would have stored and re-read
+      if (epi.mode == 1) {                                 // acc = up
+        o1[j] = acc;
+        o2[j] = bf16_round(g[j] / (1.f + __expf(-g[j]))) * acc;
+      } else {                                             // acc = d_act
+        const float sg = 1.f / (1.f + __expf(-g[j]));
+        o2[j] = acc * (g[j] * sg);                                          // d_up
+        o1[j] = acc * u[j] * (sg * (1.f + g[j] * (1.f - sg)));              // d_gate
+      }
+    }
+    if (vec) { st8(c1 + q * 8, o1); st8(c2 + q * 8, o2); }
+    else {
+      for (int j = 0; j < 8; ++j)
+        if (col0 + q * 8 + j < N) { c1[q * 8 + j] = __float2bfloat16_rn(o1[j]); c2[q * 8 + j] = __float2bfloat16_rn(o2[j]); }
+    }
+  }
+}
 
 __device__ __forceinline__ float epi_act(float x, int kind) {
   if (kind == 1) return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
@@ -26,6 +91,7 @@ __device__ __forceinline__ float epi_act(float x, int kind) {
 
 // v[32] = raw accumulators of (row, col0 .. col0+31); caller guarantees row < M and col0 < N
 __device__ __forceinline__ void store32(const GemmEpi& epi, int row, int col0, int N, float (&v)[32]) {
+  if (epi.mode) { swiglu_store32(epi, row, col0, N, v); return; }
   if (epi.c_f32) {
     float* crow = reinterpret_cast<float*>(epi.C) + (size_t)row * epi.ldc;
     const float* arow = epi.addend ? reinterpret_cast<const float*>(epi.addend) + (size_t)row * epi.ld_add : nullptr;

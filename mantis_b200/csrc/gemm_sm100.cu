@@ -191,11 +191,11 @@ static int dispatch_major(int transA, int transB, const CUtensorMap& tmA, const 
 
 int mb200_gemm_2cta_impl(const void* A, const void* B, void* C, const void* bias, const void* addend, int M, int N, int K,
                          long long lda, long long ldb, long long ldc, long long ld_add, int transA, int transB, int act,
-                         int c_f32, void* stream);
+                         int c_f32, void* stream, const gemm_epi::SwigluArgs* swiglu);
 
 static int gemm_1cta_impl(const void* A, const void* B, void* C, const void* bias, const void* addend, int M, int N, int K,
                           long long lda, long long ldb, long long ldc, long long ld_add, int transA, int transB, int act,
-                          int c_f32, void* stream) {
+                          int c_f32, void* stream, const gemm_epi::SwigluArgs* swiglu = nullptr) {
   if (M <= 0 || N <= 0) return MB200_OK;
   if (K <= 0) return -EINVAL;
   if ((lda & 7) || (ldb & 7) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
@@ -211,7 +211,8 @@ static int gemm_1cta_impl(const void* A, const void* B, void* C, const void* bia
   if (rc) return rc;
   GemmEpi epi;
   epi.C = C; epi.ldc = ldc; epi.bias = (const bf16*)bias; epi.addend = addend;
-  epi.ld_add = ld_add; epi.act = act; epi.c_f32 = c_f32;
+  epi.ld_add = ld_add; epi.act = act; epi.c_f32 = c_f32; epi.mode = 0; epi.aux0 = nullptr; epi.aux1 = nullptr; epi.ld_aux = 0; epi.C2 = nullptr; epi.ldc2 = 0;
+  if (swiglu) { epi.mode = swiglu->mode; epi.aux0 = swiglu->aux0; epi.aux1 = swiglu->aux1; epi.ld_aux = swiglu->ld_aux; epi.C2 = swiglu->C2; epi.ldc2 = swiglu->ldc2; }
   cudaStream_t st = (cudaStream_t)stream;
   if (BN == 256) rc = dispatch_major<256, 4>(transA, transB, tmA, tmB, epi, M, N, K, st);
   else           rc = dispatch_major<128, 6>(transA, transB, tmA, tmB, epi, M, N, K, st);
@@ -236,8 +237,25 @@ int mb200_gemm_bf16_acc32(const void* A, const void* B, float* C32, int M, int N
                           long long ldc, int transA, int transB, int accumulate, void* stream) {
   const void* add = accumulate ? (const void*)C32 : nullptr;
   if (M >= 512 && N >= 512)
-    return mb200_gemm_2cta_impl(A, B, C32, nullptr, add, M, N, K, lda, ldb, ldc, ldc, transA, transB, 0, 1, stream);
+    return mb200_gemm_2cta_impl(A, B, C32, nullptr, add, M, N, K, lda, ldb, ldc, ldc, transA, transB, 0, 1, stream, nullptr);
   return gemm_1cta_impl(A, B, C32, nullptr, add, M, N, K, lda, ldb, ldc, ldc, transA, transB, 0, 1, stream);
+}
+
+// U[M,N] = X[M,K] Wu[N,K]^T and Act[M,N] = silu(G) * U in the same launch (G, U, Act share the leading dimension ld).
+int mb200_gemm_bf16_swiglu_fwd(const void* X, const void* Wu, const void* G, void* U, void* Act, int M, int N, int K,
+                               long long lda, long long ldb, long long ld, void* stream) {
+  gemm_epi::SwigluArgs sw; sw.mode = 1; sw.aux0 = (const bf16*)G; sw.aux1 = nullptr; sw.ld_aux = ld; sw.C2 = (bf16*)Act; sw.ldc2 = ld;
+  if (M >= 512 && N >= 512)
+    return mb200_gemm_2cta_impl(X, Wu, U, nullptr, nullptr, M, N, K, lda, ldb, ld, 0, 0, 1, 0, 0, stream, &sw);
+  return gemm_1cta_impl(X, Wu, U, nullptr, nullptr, M, N, K, lda, ldb, ld, 0, 0, 1, 0, 0, stream, &sw);
+}
+// d_act[M,N] = dY[M,K] Wd[K,N] (the down-projection's input gradient, never stored) -> dG, dU[M,N] from G, U in the same launch.
+int mb200_gemm_bf16_swiglu_bwd(const void* dY, const void* Wd, const void* G, const void* U, void* dG, void* dU, int M, int N,
+                               int K, long long lda, long long ldb, long long ld, void* stream) {
+  gemm_epi::SwigluArgs sw; sw.mode = 2; sw.aux0 = (const bf16*)G; sw.aux1 = (const bf16*)U; sw.ld_aux = ld; sw.C2 = (bf16*)dU; sw.ldc2 = ld;
+  if (M >= 512 && N >= 512)
+    return mb200_gemm_2cta_impl(dY, Wd, dG, nullptr, nullptr, M, N, K, lda, ldb, ld, 0, 0, 0, 0, 0, stream, &sw);
+  return gemm_1cta_impl(dY, Wd, dG, nullptr, nullptr, M, N, K, lda, ldb, ld, 0, 0, 0, 0, 0, stream, &sw);
 }
 
 }  // extern "C"

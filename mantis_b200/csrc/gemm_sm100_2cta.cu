@@ -167,7 +167,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpi&
 // shared by mb200_gemm_bf16_2cta (bf16 C) and mb200_gemm_bf16_acc32 (fp32 C); not part of the public header
 int mb200_gemm_2cta_impl(const void* A, const void* B, void* C, const void* bias, const void* addend, int M, int N, int K,
                          long long lda, long long ldb, long long ldc, long long ld_add, int transA, int transB, int act,
-                         int c_f32, void* stream) {
+                         int c_f32, void* stream, const gemm_epi::SwigluArgs* swiglu) {
   if (M <= 0 || N <= 0) return MB200_OK;
   if (K <= 0) return -EINVAL;
   if ((lda & 7) || (ldb & 7) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
@@ -180,7 +180,8 @@ int mb200_gemm_2cta_impl(const void* A, const void* B, void* C, const void* bias
   if (rc) return rc;
   GemmEpi epi;
   epi.C = C; epi.ldc = ldc; epi.bias = (const bf16*)bias; epi.addend = addend; epi.ld_add = ld_add; epi.act = act;
-  epi.c_f32 = c_f32;
+  epi.c_f32 = c_f32; epi.mode = 0; epi.aux0 = nullptr; epi.aux1 = nullptr; epi.ld_aux = 0; epi.C2 = nullptr; epi.ldc2 = 0;
+  if (swiglu) { epi.mode = swiglu->mode; epi.aux0 = swiglu->aux0; epi.aux1 = swiglu->aux1; epi.ld_aux = swiglu->ld_aux; epi.C2 = swiglu->C2; epi.ldc2 = swiglu->ldc2; }
   cudaStream_t st = (cudaStream_t)stream;
   const bool a_mn = transA != 0, b_mn = transB == 0;
   if (!a_mn && !b_mn) rc = launch<false, false>(tmA, tmB, epi, M, N, K, st);
@@ -195,5 +196,5 @@ int mb200_gemm_2cta_impl(const void* A, const void* B, void* C, const void* bias
 extern "C" int mb200_gemm_bf16_2cta(const void* A, const void* B, void* C, const void* bias, const void* addend, int M,
                                     int N, int K, long long lda, long long ldb, long long ldc, long long ld_add,
                                     int transA, int transB, int act, void* stream) {
-  return mb200_gemm_2cta_impl(A, B, C, bias, addend, M, N, K, lda, ldb, ldc, ld_add, transA, transB, act, 0, stream);
+  return mb200_gemm_2cta_impl(A, B, C, bias, addend, M, N, K, lda, ldb, ldc, ld_add, transA, transB, act, 0, stream, nullptr);
 }

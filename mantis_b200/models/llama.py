@@ -103,6 +103,9 @@ class B200MLP(nn.Module):
         self.down_proj = B200Linear(config.intermediate_size, config.hidden_size, bias=bias)
 
     def forward(self, x, residual=None):
+        if (_plain(self.gate_proj, self.up_proj, self.down_proj)
+                and ops.swiglu_mlp_ok(x, self.gate_proj.weight, self.up_proj.weight, self.down_proj.weight)):
+            return ops.swiglu_mlp(x, self.gate_proj.weight, self.up_proj.weight, self.down_proj.weight, residual)
         if _plain(self.gate_proj, self.up_proj):
             g, u = ops.multi_linear(x, self.gate_proj.weight, self.up_proj.weight)
         else:

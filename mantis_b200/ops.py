@@ -326,6 +326,78 @@ def swiglu(gate, up):
     return _SwigluFn.apply(gate, up)
 
 
+FUSED_SWIGLU_MLP = os.environ.get("MB200_FUSED_SWIGLU_MLP", "1") == "1"
+
+
+def swiglu_mlp_ok(x, wg, wu, wd):
+    """can down(silu(x Wg^T) * (x Wu^T)) take the fused-epilogue path?  (bf16, TMA-aligned, large enough for the tensor-core GEMM)"""
+    if not FUSED_SWIGLU_MLP or FORCE_GENERIC or x.dtype != torch.bfloat16 or not x.is_cuda:
+        return False
+    D, I = x.shape[-1], wg.shape[0]
+    M = x.numel() // D
+    if any(w.dtype != torch.bfloat16 or w.dim() != 2 or not w.is_contiguous() or w.data_ptr() % 16 for w in (wg, wu, wd)):
+        return False
+    return (M * I * D >= FAST_GEMM_MIN_WORK and D % 8 == 0 and I % 8 == 0 and M > 16
+            and wg.shape == (I, D) and wu.shape == (I, D) and wd.shape == (D, I))
+
+
+class _SwigluMLPFn(torch.autograd.Function):
+    """y = (silu(x Wg^T) * (x Wu^T)) Wd^T (+ residual), the LLaMA / Mistral MLP (llama/modeling_llama.py:171-184), as FOUR tensor-core
+    launches forward (gate GEMM, up GEMM with the SwiGLU in its epilogue, down GEMM with the residual in its epilogue) and the
+    SwiGLU backward inside the down-projection's dgrad epilogue: the two elementwise kernels of the unfused path (3 and 5 passes
+    over [tokens, intermediate]) never run, and d(act) never exists in memory."""
+
+    @staticmethod
+    def forward(ctx, x, wg, wu, wd, residual):
+        shp = x.shape
+        D, I = shp[-1], wg.shape[0]
+        x2 = x.reshape(-1, D)
+        if x2.stride(1) != 1 or x2.stride(0) % 8 or x2.data_ptr() % 16:
+            x2 = x2.contiguous()
+        M = x2.shape[0]
+        g = gemm(x2, wg)
+        u = torch.empty((M, I), dtype=x.dtype, device=x.device)
+        a = torch.empty((M, I), dtype=x.dtype, device=x.device)
+        _call("mb200_gemm_bf16_swiglu_fwd", _p(x2), _p(wu), _p(g), _p(u), _p(a), M, I, D, x2.stride(0), wu.stride(0), I, _st())
+        res2 = residual.reshape(-1, wd.shape[0]) if residual is not None else None
+        y = gemm(a, wd, addend=res2)
+        ctx.save_for_backward(x2, wg, wu, wd, g, u, a)
+        ctx.wrefs = [w if getattr(w, "_b200_main_grad", None) is not None else None for w in (wg, wu, wd)]
+        ctx.in_shape, ctx.has_res = shp, residual is not None
+        return y.reshape(*shp[:-1], wd.shape[0])
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, wg, wu, wd, g, u, a = ctx.saved_tensors
+        Dout, I = wd.shape
+        g2 = gy.reshape(-1, Dout)
+        if g2.stride(1) != 1 or g2.stride(0) % 8 or g2.data_ptr() % 16:
+            g2 = g2.contiguous()
+        M = g2.shape[0]
+        dg = torch.empty_like(g); du = torch.empty_like(u)
+        _call("mb200_gemm_bf16_swiglu_bwd", _p(g2), _p(wd), _p(g), _p(u), _p(dg), _p(du), M, I, Dout, g2.stride(0), wd.stride(0),
+              I, _st())
+        grads_w = []
+        for w, wref, (dy_, x_) in zip((wg, wu, wd), ctx.wrefs, ((dg, x2), (du, x2), (g2, a))):
+            gw = None
+            if ctx.needs_input_grad[1 + len(grads_w)]:
+                if wref is not None:
+                    _wgrad_into_main(dy_, x_, wref)
+                else:
+                    gw = gemm(dy_, x_, trans_a=True, trans_b=False)
+            grads_w.append(gw)
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = gemm(dg, wg, trans_a=False, trans_b=False)
+            gemm(du, wu, trans_a=False, trans_b=False, addend=gx, out=gx)
+            gx = gx.reshape(ctx.in_shape)
+        return gx, grads_w[0], grads_w[1], grads_w[2], (gy if ctx.has_res else None)
+
+
+def swiglu_mlp(x, wg, wu, wd, residual=None):
+    return _SwigluMLPFn.apply(x, wg, wu, wd, residual)
+
+
 # ---------------------------------------------------------------------------------------------- norms
 class _RMSNormFn(torch.autograd.Function):
     @staticmethod

@@ -765,3 +765,39 @@ def test_attention_bwd_8_warp_kernels_still_agree(cuda):
                        timeout=900, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout
+
+
+@pytest.mark.parametrize("M,D,I", [(700, 1024, 2816), (7864, 4096, 14336), (513, 256, 1000)])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_fused_swiglu_mlp_matches_the_unfused_kernels(ops, cuda, M, D, I, with_res):
+    """the SwiGLU fused into the up-projection epilogue (forward) and the down-projection dgrad epilogue (backward) keeps the
+    arithmetic and the bf16 rounding points of the standalone elementwise kernels: outputs and all gradients are bit-identical
+    to the unfused path, and agree with fp32 torch math"""
+    import mantis_b200.ops as om
+    torch.manual_seed(60)
+    x = (torch.randn(1, M, D, device=cuda) * 0.5).bfloat16()
+    wg = (torch.randn(I, D, device=cuda) * D ** -0.5).bfloat16(); wu = (torch.randn(I, D, device=cuda) * D ** -0.5).bfloat16()
+    wd = (torch.randn(D, I, device=cuda) * I ** -0.5).bfloat16()
+    res = (torch.randn(1, M, D, device=cuda) * 0.5).bfloat16() if with_res else None
+    gy = (torch.randn(1, M, D, device=cuda) * 0.1).bfloat16()
+
+    def run(fused):
+        ts = [t.detach().clone().requires_grad_(True) for t in (x, wg, wu, wd)] + ([res.detach().clone().requires_grad_(True)] if with_res else [None])
+        xx, g_, u_, d_, r_ = ts
+        if fused:
+            assert om.swiglu_mlp_ok(xx, g_, u_, d_)
+            y = om.swiglu_mlp(xx, g_, u_, d_, r_)
+        else:
+            gg, uu = om.multi_linear(xx, g_, u_)
+            y = om.linear(om.swiglu(gg, uu), d_, residual=r_)
+        y.backward(gy)
+        return [y.detach()] + [t.grad for t in ts if t is not None]
+
+    a, b = run(True), run(False)
+    names = ["y", "dx", "dWg", "dWu", "dWd", "dres"]
+    for n, p, q in zip(names, a, b):
+        assert torch.equal(p, q), (n, _rel(p, q))
+    xf, gf, uf, df = [t.float().requires_grad_(True) for t in (x, wg, wu, wd)]
+    yr = (torch.nn.functional.silu(xf @ gf.t()) * (xf @ uf.t())) @ df.t() + (res.float() if with_res else 0)
+    yr.backward(gy.float())
+    assert _rel(a[0], yr) < 1e-2 and _rel(a[1], xf.grad) < 2e-2 and _rel(a[2], gf.grad) < 2e-2 and _rel(a[4], df.grad) < 2e-2
