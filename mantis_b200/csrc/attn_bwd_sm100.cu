@@ -269,226 +269,6 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __gri
   if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-constexpr int NTHREADS16 = 64 + 16 * 32;
-
-// 64 columns of one accumulator row (fp32 in TMEM) -> bf16 (128 B) in global memory
-__device__ __forceinline__ void store_acc_half(uint32_t taddr, bf16* dst, bool ok, float mul) {
-#pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    uint32_t ov[32];
-    tmem_ld_32x32b_x32(taddr + c * 32, ov);
-    tmem_ld_wait();
-    if (ok) {
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 o4;
-        o4.x = pack_bf16(__uint_as_float(ov[g * 8 + 0]) * mul, __uint_as_float(ov[g * 8 + 1]) * mul);
-        o4.y = pack_bf16(__uint_as_float(ov[g * 8 + 2]) * mul, __uint_as_float(ov[g * 8 + 3]) * mul);
-        o4.z = pack_bf16(__uint_as_float(ov[g * 8 + 4]) * mul, __uint_as_float(ov[g * 8 + 5]) * mul);
-        o4.w = pack_bf16(__uint_as_float(ov[g * 8 + 6]) * mul, __uint_as_float(ov[g * 8 + 7]) * mul);
-        *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = o4;
-      }
-    }
-  }
-}
-
-// ============================================================================================ dK / dV, 16 softmax warps
-// Variant of the kernel above with TWICE the softmax warps: each ping-pong group has 8 warps -- two per TMEM lane quarter, each
-// taking 32 of the 64 query columns of a sub-tile -- so the TMEM-load -> exp2 -> pack -> TMEM-store chain of a stage is half as
-// long and four warps per scheduler hide each other's latencies (the 8-warp kernel ran at 32 % tensor-pipe active with 25 %
-// issue-active: latency-bound, profiles/ncu_full_r01_summary.txt).  Registers: 576 threads => at most 112 per thread.
-// Softmax warps form two groups (warps 2-9 and 10-17) that ping-pong over the 64-query sub-tiles: group g owns TMEM stage g
-// (S^T_g, dP^T_g), so while one group waits on barriers / TMEM latency the other computes, and the MMA thread always has
-// the other stage's products to issue.  P^T / dS^T (bf16) are written back into the first 32 columns of S^T_g / dP^T_g and
-// feed the dV / dK MMAs as TMEM A operands: nothing but Q / dO / K / V tiles ever touches shared memory.
-__global__ void __launch_bounds__(NTHREADS16, 1)
-attn_bwd_dkv16_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant__ CUtensorMap tmDO64,
-                          const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                          const BwdParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sK = smem;                           // 32 KB resident
-  uint8_t* sV = sK + FULL_TILE;                 // 32 KB resident
-  uint8_t* sQ = sV + FULL_TILE;                 // QS stages x 16 KB
-  uint8_t* sDO = sQ + QS * SUB_TILE;            // QS stages x 16 KB
-  float2* sLD = reinterpret_cast<float2*>(sDO + QS * SUB_TILE);   // [QS][64] {lse2, delta}
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sLD + QS * 64);
-  uint64_t* kv_full = bars + 0;
-  uint64_t* qdo_full = bars + 1;    // [QS]
-  uint64_t* qdo_empty = bars + 4;   // [QS]
-  uint64_t* sdp_full = bars + 7;    // [2]
-  uint64_t* pds_full = bars + 9;    // [2]
-  uint64_t* acc_done = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const mb::LptIdx li = mb::lpt_index();        // early key tiles see the most queries: they go first, across all kv heads
-  const int kt = li.rank, hk = li.h, b = li.b;
-  const int G = p.H / p.Hkv;
-  const int k0 = kt * 128;
-  const int off = p.Sk - p.Sq;
-  const int n_qs = (p.Sq + 63) / 64;
-  int qs_begin = 0;
-  if (p.causal) { int qb = k0 - off; if (qb < 0) qb = 0; qs_begin = qb / 64; }
-  const int per_head = (n_qs > qs_begin) ? (n_qs - qs_begin) : 0;
-  const int n_it = per_head * G;
-
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmQ64); prefetch_tmap(&tmDO64); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
-    mbar_init(kv_full, 1);
-    for (int s = 0; s < QS; ++s) { mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&sdp_full[s], 1); mbar_init(&pds_full[s], 256); }
-    mbar_init(acc_done, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tDK = tmem_base, tDV = tmem_base + 128;
-  const uint32_t tST[2] = {tmem_base + 256, tmem_base + 384};
-  const uint32_t tDPT[2] = {tmem_base + 320, tmem_base + 448};
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(kv_full, 2 * FULL_TILE);
-      tma_load_4d(sK, &tmK, kv_full, 0, hk, k0, b);
-      tma_load_4d(sK + FULL_HALF, &tmK, kv_full, 64, hk, k0, b);
-      tma_load_4d(sV, &tmV, kv_full, 0, hk, k0, b);
-      tma_load_4d(sV + FULL_HALF, &tmV, kv_full, 64, hk, k0, b);
-      for (int n = 0; n < n_it; ++n) {
-        const int s = n % QS; const uint32_t ph = (n / QS) & 1;
-        const int h = hk * G + n / per_head, qs = qs_begin + n % per_head;
-        mbar_wait(&qdo_empty[s], ph ^ 1);      // dV/dK of sub-tile n-QS done => Q/dO stage and sLD[s] are free
-        mbar_arrive_expect_tx(&qdo_full[s], 2 * SUB_TILE + 64 * 8);
-        tma_load_4d(sQ + s * SUB_TILE, &tmQ64, &qdo_full[s], 0, h, qs * 64, b);
-        tma_load_4d(sQ + s * SUB_TILE + SUB_HALF, &tmQ64, &qdo_full[s], 64, h, qs * 64, b);
-        tma_load_4d(sDO + s * SUB_TILE, &tmDO64, &qdo_full[s], 0, h, qs * 64, b);
-        tma_load_4d(sDO + s * SUB_TILE + SUB_HALF, &tmDO64, &qdo_full[s], 64, h, qs * 64, b);
-        bulk_load_1d(sLD + s * 64, p.ld + ((size_t)b * p.H + h) * p.Sq_pad + qs * 64, 64 * 8, &qdo_full[s]);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0 && n_it > 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, false, false);
-      constexpr uint32_t idesc_acc = make_idesc_bf16(128, 128, false, true);
-      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
-      auto issue_sdp = [&](int n) {             // TMEM stage n&1 was last read by dV/dK(n-2), issued earlier (in-order tensor pipe)
-        const int s = n & 1, ss = n % QS;
-        mbar_wait(&qdo_full[ss], (n / QS) & 1);
-        tc_fence_after();
-        const uint32_t q_addr = smem_u32(sQ + ss * SUB_TILE), do_addr = smem_u32(sDO + ss * SUB_TILE);
-#pragma unroll
-        for (int kk = 0; kk < HD / 16; ++kk) {
-          const uint32_t oa = (kk >> 2) * FULL_HALF + (kk & 3) * 32, ob = (kk >> 2) * SUB_HALF + (kk & 3) * 32;
-          umma_bf16_ss(tST[s], make_smem_desc(k_addr + oa, 16, 1024), make_smem_desc(q_addr + ob, 16, 1024), idesc_s, kk != 0);
-        }
-#pragma unroll
-        for (int kk = 0; kk < HD / 16; ++kk) {
-          const uint32_t oa = (kk >> 2) * FULL_HALF + (kk & 3) * 32, ob = (kk >> 2) * SUB_HALF + (kk & 3) * 32;
-          umma_bf16_ss(tDPT[s], make_smem_desc(v_addr + oa, 16, 1024), make_smem_desc(do_addr + ob, 16, 1024), idesc_s, kk != 0);
-        }
-        umma_commit(&sdp_full[s]);
-      };
-      mbar_wait(kv_full, 0);
-      issue_sdp(0);
-      if (n_it > 1) issue_sdp(1);
-      for (int n = 0; n < n_it; ++n) {
-        const int s = n & 1, ss = n % QS; const uint32_t ph = (n >> 1) & 1;
-        mbar_wait(&pds_full[s], ph);
-        tc_fence_after();
-        const uint32_t q_addr = smem_u32(sQ + ss * SUB_TILE), do_addr = smem_u32(sDO + ss * SUB_TILE);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)     // dV += P^T (TMEM A, K = 64 queries) x dO (MN-major: rows = queries)
-          umma_bf16_ts(tDV, tST[s] + (kk >> 1) * 32 + (kk & 1) * 8, make_smem_desc(do_addr + kk * 2048, SUB_HALF, 1024), idesc_acc, (n | kk) != 0);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)     // dK += dS^T (TMEM A) x Q
-          umma_bf16_ts(tDK, tDPT[s] + (kk >> 1) * 32 + (kk & 1) * 8, make_smem_desc(q_addr + kk * 2048, SUB_HALF, 1024), idesc_acc, (n | kk) != 0);
-        umma_commit(&qdo_empty[ss]);
-        if (n + 2 < n_it) issue_sdp(n + 2);
-      }
-      umma_commit(acc_done);
-    }
-  } else {
-    const int qd = warp & 3;                     // TMEM lane quarter (hardware: a warp reaches lanes 32 * (warp % 4) ...)
-    const int grp = (warp - 2) >> 3;             // ping-pong group == TMEM stage it owns
-    const int c = ((warp - 2) >> 2) & 1;         // which 32 query columns of the 64-column sub-tile this warp handles
-    const int r = qd * 32 + lane;                // key row in tile == TMEM lane
-    const int kj = k0 + r;
-    const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-    bool key_ok = kj < p.Sk;
-    if (key_ok && p.kbits) key_ok = (__ldg(p.kbits + (size_t)b * p.kbits_stride + (kj >> 5)) >> (kj & 31)) & 1u;
-    const int qlim = kj - off;                   // causal: query qi sees key kj iff qi >= kj - off
-    const int s = grp;
-    for (int n = grp; n < n_it; n += 2) {
-      const uint32_t ph = (n >> 1) & 1;
-      const int qs = qs_begin + n % per_head;
-      const int ss = n % QS;
-      mbar_wait(&qdo_full[ss], (n / QS) & 1);    // lse/delta landed (bulk copy on the same barrier as Q/dO)
-      mbar_wait(&sdp_full[s], ph);
-      tc_fence_after();
-      {
-        const int q0 = qs * 64 + c * 32;
-        float sv[32], dp[32];
-        tmem_ld_32x32b_x32(tST[s] + lane_off + c * 32, reinterpret_cast<uint32_t*>(sv));
-        tmem_ld_32x32b_x32(tDPT[s] + lane_off + c * 32, reinterpret_cast<uint32_t*>(dp));
-        tmem_ld_wait();
-        const float2* ldp = sLD + ss * 64 + c * 32;
-        uint32_t pk[16], dk_[16];
-        const bool full_vis = key_ok && (!p.causal || q0 >= qlim);
-        if (full_vis) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float2 l0 = ldp[2 * i], l1 = ldp[2 * i + 1];
-            const float p0 = fast_exp2(fmaf(sv[2 * i], p.scale_log2, -l0.x));
-            const float p1 = fast_exp2(fmaf(sv[2 * i + 1], p.scale_log2, -l1.x));
-            pk[i] = pack_bf16(p0, p1);
-            dk_[i] = pack_bf16(p0 * (dp[2 * i] - l0.y), p1 * (dp[2 * i + 1] - l1.y));
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float2 l0 = ldp[2 * i], l1 = ldp[2 * i + 1];
-            const bool v0 = key_ok && (!p.causal || q0 + 2 * i >= qlim);
-            const bool v1 = key_ok && (!p.causal || q0 + 2 * i + 1 >= qlim);
-            const float p0 = v0 ? fast_exp2(fmaf(sv[2 * i], p.scale_log2, -l0.x)) : 0.f;
-            const float p1 = v1 ? fast_exp2(fmaf(sv[2 * i + 1], p.scale_log2, -l1.x)) : 0.f;
-            pk[i] = pack_bf16(p0, p1);
-            dk_[i] = pack_bf16(p0 * (dp[2 * i] - l0.y), p1 * (dp[2 * i + 1] - l1.y));
-          }
-        }
-        // the packed bf16 values go into the first 16 of the 32 fp32 columns THIS warp has just consumed ([32c, 32c+16)):
-        // the other column half belongs to a different warp that may still be reading it
-        tmem_st_32x32b_x16(tST[s] + lane_off + c * 32, pk);
-        tmem_st_32x32b_x16(tDPT[s] + lane_off + c * 32, dk_);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&pds_full[s]);
-    }
-    // ---- epilogue: group 0 stores dK (x softmax scale), group 1 stores dV ----
-    const bool row_ok = kj < p.Sk;
-    bf16* dkp = p.dk + (size_t)b * p.dk_sb + (size_t)(row_ok ? kj : 0) * p.dk_ss + (size_t)hk * p.dk_sh;
-    bf16* dvp = p.dv + (size_t)b * p.dv_sb + (size_t)(row_ok ? kj : 0) * p.dv_ss + (size_t)hk * p.dv_sh;
-    if (n_it > 0) {
-      mbar_wait(acc_done, 0);
-      tc_fence_after();
-      // each of a group's two warps per lane quarter stores 64 of the 128 head dims of its row
-      if (grp == 0) store_acc_half(tDK + lane_off + c * 64, dkp + c * 64, row_ok, p.scale);
-      else          store_acc_half(tDV + lane_off + c * 64, dvp + c * 64, row_ok, 1.f);
-    } else if (row_ok) {
-      const uint4 z = make_uint4(0, 0, 0, 0);
-      bf16* dst = (grp == 0 ? dkp : dvp) + c * 64;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(dst + i * 8) = z;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem_base, 512); }
-}
-
 // ============================================================================================ dQ
 // NGQ softmax groups rotate over the key sub-tiles, one TMEM stage (S, dP) each: 128 (dQ) + 3 x 128 = 512 columns.
 constexpr int NGQ = 3;
@@ -678,199 +458,6 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-// ============================================================================================ dQ, 24 softmax warps
-// Same pipeline as attn_bwd_dq_sm100_kernel with twice the softmax warps: each of the NGQ groups has 8 warps -- two per TMEM lane
-// quarter, each taking 32 of the 64 key columns of a sub-tile in two passes of 16 -- so a stage's TMEM-load -> exp2 -> pack ->
-// TMEM-store chain is half as long and six warps per scheduler hide each other's latencies.  832 threads => 72 registers.
-constexpr int DQ_THREADS24 = 64 + NGQ * 256;
-
-__global__ void __launch_bounds__(DQ_THREADS24, 1)
-attn_bwd_dq24_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
-                         const __grid_constant__ CUtensorMap tmK64, const __grid_constant__ CUtensorMap tmV64,
-                         const BwdParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                           // 32 KB resident
-  uint8_t* sDO = sQ + FULL_TILE;                // 32 KB resident
-  uint8_t* sK = sDO + FULL_TILE;                // QSQ x 16 KB
-  uint8_t* sV = sK + QSQ * SUB_TILE;            // QSQ x 16 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + QSQ * SUB_TILE);
-  uint64_t* qdo_full = bars + 0;
-  uint64_t* kv_full = bars + 1;              // [QSQ]
-  uint64_t* kv_empty = kv_full + QSQ;        // [QSQ]
-  uint64_t* sdp_full = kv_empty + QSQ;       // [NGQ]
-  uint64_t* ds_full = sdp_full + NGQ;        // [NGQ]
-  uint64_t* acc_done = ds_full + NGQ;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const mb::LptIdx li = mb::lpt_index();        // heavy (late) query tiles first, across all heads
-  const int qt = (int)gridDim.x - 1 - li.rank;
-  const int h = li.h, b = li.b;
-  const int hk = h / (p.H / p.Hkv);
-  const int q0 = qt * 128;
-  const int off = p.Sk - p.Sq;
-  int kv_end = p.Sk;
-  if (p.causal) { kv_end = min(p.Sk, q0 + 128 + off); if (kv_end < 0) kv_end = 0; }
-  const int n_it = (kv_end + 63) / 64;
-
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmQ); prefetch_tmap(&tmDO); prefetch_tmap(&tmK64); prefetch_tmap(&tmV64);
-    mbar_init(qdo_full, 1);
-    for (int s = 0; s < QSQ; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    for (int s = 0; s < NGQ; ++s) { mbar_init(&sdp_full[s], 1); mbar_init(&ds_full[s], 256); }
-    mbar_init(acc_done, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tDQ = tmem_base;
-  const uint32_t tS0 = tmem_base + 128, tDP0 = tmem_base + 192;      // stage g: +128 g
-
-  if (warp == 0) {
-    if (lane == 0 && n_it > 0) {
-      mbar_arrive_expect_tx(qdo_full, 2 * FULL_TILE);
-      tma_load_4d(sQ, &tmQ, qdo_full, 0, h, q0, b);
-      tma_load_4d(sQ + FULL_HALF, &tmQ, qdo_full, 64, h, q0, b);
-      tma_load_4d(sDO, &tmDO, qdo_full, 0, h, q0, b);
-      tma_load_4d(sDO + FULL_HALF, &tmDO, qdo_full, 64, h, q0, b);
-      for (int n = 0; n < n_it; ++n) {
-        const int s = n % QSQ; const uint32_t ph = (n / QSQ) & 1;
-        mbar_wait(&kv_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&kv_full[s], 2 * SUB_TILE);
-        tma_load_4d(sK + s * SUB_TILE, &tmK64, &kv_full[s], 0, hk, n * 64, b);
-        tma_load_4d(sK + s * SUB_TILE + SUB_HALF, &tmK64, &kv_full[s], 64, hk, n * 64, b);
-        tma_load_4d(sV + s * SUB_TILE, &tmV64, &kv_full[s], 0, hk, n * 64, b);
-        tma_load_4d(sV + s * SUB_TILE + SUB_HALF, &tmV64, &kv_full[s], 64, hk, n * 64, b);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0 && n_it > 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, false, false);
-      constexpr uint32_t idesc_acc = make_idesc_bf16(128, 128, false, true);
-      const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sDO);
-      auto issue_sdp = [&](int n) {
-        const int s = n % NGQ, ss = n % QSQ;
-        mbar_wait(&kv_full[ss], (n / QSQ) & 1);
-        tc_fence_after();
-        const uint32_t k_addr = smem_u32(sK + ss * SUB_TILE), v_addr = smem_u32(sV + ss * SUB_TILE);
-#pragma unroll
-        for (int kk = 0; kk < HD / 16; ++kk) {
-          const uint32_t oa = (kk >> 2) * FULL_HALF + (kk & 3) * 32, ob = (kk >> 2) * SUB_HALF + (kk & 3) * 32;
-          umma_bf16_ss(tS0 + s * 128, make_smem_desc(q_addr + oa, 16, 1024), make_smem_desc(k_addr + ob, 16, 1024), idesc_s, kk != 0);
-        }
-#pragma unroll
-        for (int kk = 0; kk < HD / 16; ++kk) {
-          const uint32_t oa = (kk >> 2) * FULL_HALF + (kk & 3) * 32, ob = (kk >> 2) * SUB_HALF + (kk & 3) * 32;
-          umma_bf16_ss(tDP0 + s * 128, make_smem_desc(do_addr + oa, 16, 1024), make_smem_desc(v_addr + ob, 16, 1024), idesc_s, kk != 0);
-        }
-        umma_commit(&sdp_full[s]);
-      };
-      mbar_wait(qdo_full, 0);
-      for (int n = 0; n < NGQ && n < n_it; ++n) issue_sdp(n);
-      for (int n = 0; n < n_it; ++n) {
-        const int s = n % NGQ, ss = n % QSQ; const uint32_t ph = (n / NGQ) & 1;
-        mbar_wait(&ds_full[s], ph);
-        tc_fence_after();
-        const uint32_t k_addr = smem_u32(sK + ss * SUB_TILE);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)     // dQ += dS (TMEM A, K = 64 keys) x K (MN-major: rows = keys)
-          umma_bf16_ts(tDQ, tS0 + s * 128 + (kk >> 1) * 32 + (kk & 1) * 8, make_smem_desc(k_addr + kk * 2048, SUB_HALF, 1024), idesc_acc, (n | kk) != 0);
-        umma_commit(&kv_empty[ss]);
-        if (n + NGQ < n_it) issue_sdp(n + NGQ);
-      }
-      umma_commit(acc_done);
-    }
-  } else {
-    const int qd = warp & 3;
-    const int grp = (warp - 2) >> 3;             // rotating group == TMEM stage
-    const int c = ((warp - 2) >> 2) & 1;         // which 32 key columns of the 64-column sub-tile this warp handles
-    const int r = qd * 32 + lane;
-    const int qi = q0 + r;
-    const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-    const bool row_ok = qi < p.Sq;
-    const float2 ldv = p.ld[((size_t)b * p.H + h) * p.Sq_pad + qi];        // padded rows hold {+inf, 0}
-    const float L = ldv.x, dl = ldv.y;
-    const int limit = p.causal ? min(qi + off, p.Sk - 1) : (p.Sk - 1);
-    const int s = grp;
-    for (int n = grp; n < n_it; n += NGQ) {
-      const uint32_t ph = (n / NGQ) & 1;
-      mbar_wait(&sdp_full[s], ph);
-      tc_fence_after();
-      const int kc = n * 64 + c * 32;
-      uint32_t w = 0xffffffffu;
-      if (p.kbits) { const int wi = kc >> 5; w = (wi < p.kbits_stride) ? __ldg(p.kbits + (size_t)b * p.kbits_stride + wi) : 0u; }
-      const bool all_vis = (w == 0xffffffffu) && (kc + 31 <= limit);
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {             // two passes of 16 key columns keep the live registers low
-        const int k0 = kc + hh * 16;
-        float sv[16], dp[16];
-        tmem_ld_32x32b_x16(tS0 + s * 128 + lane_off + c * 32 + hh * 16, reinterpret_cast<uint32_t*>(sv));
-        tmem_ld_32x32b_x16(tDP0 + s * 128 + lane_off + c * 32 + hh * 16, reinterpret_cast<uint32_t*>(dp));
-        tmem_ld_wait();
-        uint32_t dsk[8];
-        if (all_vis) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float p0 = fast_exp2(fmaf(sv[2 * i], p.scale_log2, -L));
-            const float p1 = fast_exp2(fmaf(sv[2 * i + 1], p.scale_log2, -L));
-            dsk[i] = pack_bf16(p0 * (dp[2 * i] - dl), p1 * (dp[2 * i + 1] - dl));
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const bool v0 = (k0 + 2 * i <= limit) && ((w >> (hh * 16 + 2 * i)) & 1u);
-            const bool v1 = (k0 + 2 * i + 1 <= limit) && ((w >> (hh * 16 + 2 * i + 1)) & 1u);
-            const float p0 = v0 ? fast_exp2(fmaf(sv[2 * i], p.scale_log2, -L)) : 0.f;
-            const float p1 = v1 ? fast_exp2(fmaf(sv[2 * i + 1], p.scale_log2, -L)) : 0.f;
-            dsk[i] = pack_bf16(p0 * (dp[2 * i] - dl), p1 * (dp[2 * i + 1] - dl));
-          }
-        }
-        // packed dS of these 16 keys -> 8 columns inside the fp32 columns this warp has already consumed ([32c, 32c+16))
-        tmem_st_32x32b_x8(tS0 + s * 128 + lane_off + c * 32 + hh * 8, dsk);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&ds_full[s]);
-    }
-    // epilogue: groups 0 and 1 store; each of their warps writes 32 of the 128 head dims of its dQ row (x softmax scale)
-    bf16* dqp = p.dq + (size_t)b * p.dq_sb + (size_t)(row_ok ? qi : 0) * p.dq_ss + (size_t)h * p.dq_sh + grp * 64 + c * 32;
-    if (grp >= 2) {
-      // nothing to store
-    } else if (n_it > 0) {
-      mbar_wait(acc_done, 0);
-      tc_fence_after();
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t ov[16];
-        tmem_ld_32x32b_x16(tDQ + lane_off + grp * 64 + c * 32 + hh * 16, ov);
-        tmem_ld_wait();
-        if (row_ok) {
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            uint4 o4;
-            o4.x = pack_bf16(__uint_as_float(ov[g * 8 + 0]) * p.scale, __uint_as_float(ov[g * 8 + 1]) * p.scale);
-            o4.y = pack_bf16(__uint_as_float(ov[g * 8 + 2]) * p.scale, __uint_as_float(ov[g * 8 + 3]) * p.scale);
-            o4.z = pack_bf16(__uint_as_float(ov[g * 8 + 4]) * p.scale, __uint_as_float(ov[g * 8 + 5]) * p.scale);
-            o4.w = pack_bf16(__uint_as_float(ov[g * 8 + 6]) * p.scale, __uint_as_float(ov[g * 8 + 7]) * p.scale);
-            *reinterpret_cast<uint4*>(dqp + hh * 16 + g * 8) = o4;
-          }
-        }
-      }
-    } else if (row_ok) {
-      const uint4 z = make_uint4(0, 0, 0, 0);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(dqp + i * 8) = z;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem_base, 512); }
-}
-
 // ld[b,h,q] = {lse * log2(e) (+inf if the row is dead or q >= Sq), sum_d dO * O}   (one warp per row of 128, rows padded to Sq_pad)
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, const float* __restrict__ lse,
@@ -944,17 +531,11 @@ int mb200_attn_bwd_bf16(const void* q, const void* k, const void* v, const void*
   constexpr int smem_dq = 2 * FULL_TILE + 2 * QSQ * SUB_TILE + 1024 + 256;
   static const bool cfg_ok =        // thread-safe one-time setup
       cudaFuncSetAttribute(attn_bwd_dkv_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dkv) == cudaSuccess &&
-      cudaFuncSetAttribute(attn_bwd_dkv16_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dkv) == cudaSuccess &&
-      cudaFuncSetAttribute(attn_bwd_dq_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq) == cudaSuccess &&
-      cudaFuncSetAttribute(attn_bwd_dq24_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq) == cudaSuccess;
+      cudaFuncSetAttribute(attn_bwd_dq_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq) == cudaSuccess;
   if (!cfg_ok) { mb200_set_last_error("cudaFuncSetAttribute(attn bwd smem) failed"); return -EIO; }
   dim3 gkv((Sk + 127) / 128, Hkv, B), gq((Sq + 127) / 128, H, B);
-  static const int dkv16 = [] { const char* e = getenv("MB200_ATTN_BWD_DKV16"); return (e && e[0] == '0') ? 0 : 1; }();
-  if (dkv16) attn_bwd_dkv16_sm100_kernel<<<gkv, NTHREADS16, smem_dkv, st>>>(tmQ64, tmDO64, tmK, tmV, p);
-  else       attn_bwd_dkv_sm100_kernel<<<gkv, NTHREADS, smem_dkv, st>>>(tmQ64, tmDO64, tmK, tmV, p);
-  static const int dq24 = [] { const char* e = getenv("MB200_ATTN_BWD_DQ24"); return (e && e[0] == '0') ? 0 : 1; }();
-  if (dq24) attn_bwd_dq24_sm100_kernel<<<gq, DQ_THREADS24, smem_dq, st>>>(tmQ, tmDO, tmK64, tmV64, p);
-  else      attn_bwd_dq_sm100_kernel<<<gq, DQ_THREADS, smem_dq, st>>>(tmQ, tmDO, tmK64, tmV64, p);
+  attn_bwd_dkv_sm100_kernel<<<gkv, NTHREADS, smem_dkv, st>>>(tmQ64, tmDO64, tmK, tmV, p);
+  attn_bwd_dq_sm100_kernel<<<gq, DQ_THREADS, smem_dq, st>>>(tmQ, tmDO, tmK64, tmV64, p);
   MB200_CHECK_LAUNCH();
   return MB200_OK;
 }

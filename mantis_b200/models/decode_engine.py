@@ -59,10 +59,11 @@ class DecodeEngine:
         self._keep = ptrs
         self.layer_tab = (ctypes.c_void_p * len(ptrs))(*[t.data_ptr() if t is not None else None for t in ptrs])
 
-    def step(self, ids, pos, kbits=None):
+    def step(self, ids, pos, kbits=None, next_out=None):
         """ids, pos: int64 [B] on device.  Appends one token per sequence to the cache, returns (logits [B,V], next_ids).
         The returned tensors are VIEWS of the engine's persistent buffers: the next step() overwrites them (callers that keep
-        logits across steps must clone)."""
+        logits across steps must clone).  `next_out`: optional contiguous int64 [B] destination of the arg-max tokens (a row of
+        a time-major token buffer, so a whole generation needs no copy kernels)."""
         ctx = self.cache.get_seq_length()
         self.cache.ensure(ctx + 1)                    # new pages only extend the block table; nothing is copied
         table = self.cache.device_table()
@@ -74,10 +75,40 @@ class DecodeEngine:
         misc = (ctypes.c_void_p * 10)(self.decoder.embed_tokens.weight.data_ptr(), self.decoder.norm.weight.data_ptr(),
                                      self.lm_head_weight.data_ptr(), self.inv_freq.data_ptr(), ids.data_ptr(),
                                      pos.data_ptr(), kbits.data_ptr() if kbits is not None else None,
-                                     self.logits.data_ptr(), self.next_ids.data_ptr(), table.data_ptr())
+                                     self.logits.data_ptr(),
+                                     (next_out if next_out is not None else self.next_ids).data_ptr(), table.data_ptr())
         ops._call("mb200_llama_decode_step", dims, fparm, self.layer_tab, misc, ops._p(self.ws), self.ld_logits, ops._st())
         self.cache.advance(1)
-        return self.logits[:, : self.V], self.next_ids
+        return self.logits[:, : self.V], (next_out if next_out is not None else self.next_ids)
+
+
+def greedy_decode_loop(decoder, lm_head, cache, first_tokens, pos0, n_steps, kbits=None, eos_ids=None, check_every=32):
+    """`n_steps` greedy decode steps after a prefill, ONE C call per token and nothing else: token t+1 is written by the engine's
+    arg-max kernel straight into row t+1 of a time-major buffer, which is also the next step's input; positions are rows of a
+    precomputed table.  Without EOS ids the host never synchronises; with them it looks every `check_every` steps.
+    first_tokens int64 [B] (arg-max of the prefill), pos0 int64 [B] (position id of first_tokens).  Returns [B, <= n_steps + 1]
+    tokens (first_tokens included; trailing steps after every sequence has finished are cut by the caller)."""
+    global native_steps
+    dev = first_tokens.device
+    B = first_tokens.shape[0]
+    eng = getattr(cache, "_engine", None)
+    if eng is None or eng.decoder is not decoder or eng.B != cache.batch or eng.lm_head_weight is not lm_head.weight:
+        eng = DecodeEngine(decoder, lm_head.weight, cache, reserve_tokens=n_steps + 8)
+        cache._engine = eng
+    else:
+        cache.reserve(cache.get_seq_length() + n_steps + 8)
+    toks = torch.empty((n_steps + 1, B), dtype=torch.int64, device=dev)
+    toks[0].copy_(first_tokens)
+    pos = (pos0.to(torch.int64).unsqueeze(0) + torch.arange(n_steps + 1, device=dev, dtype=torch.int64).unsqueeze(1)).contiguous()
+    eos = torch.tensor(sorted(eos_ids), device=dev) if eos_ids else None
+    done_at = n_steps
+    for t in range(n_steps):
+        eng.step(toks[t], pos[t], kbits, next_out=toks[t + 1])
+        native_steps += 1
+        if eos is not None and (t + 1) % check_every == 0 and bool(torch.isin(toks[: t + 2], eos).any(dim=0).all()):
+            done_at = t + 1
+            break
+    return toks[: done_at + 1].t()
 
 
 def native_decode_logits(decoder, lm_head, cache, input_ids, x_dtype, attention_mask, position_ids, labels=None,

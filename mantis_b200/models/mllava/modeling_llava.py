@@ -14,6 +14,7 @@ state-dict keys and error behaviour.  What changes is what runs underneath:
   decode-time K-cache scan + torch.where sync (:480-508) pad slots tracked on the host-free path (mask carried in cache)
 """
 from dataclasses import dataclass
+import os
 from typing import List, Optional, Tuple, Union
 
 import torch
@@ -287,6 +288,89 @@ class LlavaForConditionalGeneration(LlavaPreTrainedModel, GenerationMixin):
     def _reorder_cache(self, past_key_values, beam_idx):
         past_key_values.reorder_cache(beam_idx)
         return past_key_values
+
+    # ---- generate(): greedy decoding without per-token host round trips -------------------------------------------------
+    _FAST_GENERATE_KEYS = {"input_ids", "pixel_values", "attention_mask", "max_new_tokens", "max_length", "min_new_tokens",
+                           "do_sample", "num_beams", "eos_token_id", "pad_token_id", "use_cache", "num_return_sequences"}
+
+    def _fast_greedy_plan(self, inputs, generation_config, kwargs):
+        """-> dict of arguments for the sync-free greedy loop, or None when the call needs anything beyond plain greedy decoding
+        (then transformers' GenerationMixin.generate runs as before)."""
+        if os.environ.get("MB200_FAST_GENERATE", "1") != "1" or inputs is not None or generation_config is not None:
+            return None
+        if not set(kwargs) <= self._FAST_GENERATE_KEYS or kwargs.get("input_ids") is None or kwargs.get("attention_mask") is None:
+            return None
+        gc = self.generation_config
+        ids = kwargs["input_ids"]
+        if (kwargs.get("do_sample", gc.do_sample) or kwargs.get("num_beams", gc.num_beams) != 1
+                or kwargs.get("num_return_sequences", 1) != 1 or kwargs.get("use_cache", True) is False
+                or (gc.repetition_penalty or 1.0) != 1.0 or gc.no_repeat_ngram_size or gc.bad_words_ids
+                or gc.forced_bos_token_id is not None or gc.forced_eos_token_id is not None or gc.suppress_tokens
+                or gc.begin_suppress_tokens or gc.return_dict_in_generate or gc.output_scores or gc.output_logits
+                or getattr(gc, "sequence_bias", None) or getattr(gc, "renormalize_logits", False)):
+            return None
+        if kwargs.get("max_new_tokens", gc.max_new_tokens) is not None:
+            n_new = int(kwargs.get("max_new_tokens", gc.max_new_tokens))
+        elif kwargs.get("max_length") is not None or gc.max_length is not None:
+            n_new = int(kwargs.get("max_length") or gc.max_length) - ids.shape[1]
+        else:
+            return None
+        eos = kwargs.get("eos_token_id", gc.eos_token_id)
+        eos = [] if eos is None else ([int(e) for e in eos] if isinstance(eos, (list, tuple)) else [int(eos)])
+        min_new = kwargs.get("min_new_tokens", gc.min_new_tokens) or 0
+        if n_new < 1 or (eos and min_new):                  # EOS suppression before min_new_tokens needs the logits processor
+            return None
+        pad = kwargs.get("pad_token_id", gc.pad_token_id)
+        if eos and pad is None:
+            pad = eos[0]                                    # GenerationMixin: "Setting pad_token_id to eos_token_id"
+        lm = self.language_model
+        a = lm.model.layers[0].self_attn
+        if (not ids.is_cuda or lm.lm_head.weight.dtype != torch.bfloat16 or a.head_dim != 128 or not 0 < ids.shape[0] <= 16
+                or ops.FORCE_GENERIC):
+            return None
+        return {"n_new": n_new, "eos": eos, "pad": pad}
+
+    @torch.no_grad()
+    def generate(self, inputs=None, generation_config=None, **kwargs):
+        """transformers' `generate()` (ref: the call mantis/models/mllava/utils.py:88 makes).  Plain greedy decoding -- what
+        chat_mllava asks for by default -- takes a loop that issues exactly one C call per token and does not synchronise with
+        the device until the end (or every 32 tokens when EOS ids are set): prefill through forward(), then
+        decode_engine.greedy_decode_loop.  Output conventions are GenerationMixin's (prompt + new tokens, pad after a sequence's
+        EOS, stop when every sequence has finished).  Every other configuration goes through GenerationMixin unchanged."""
+        plan = self._fast_greedy_plan(inputs, generation_config, kwargs)
+        if plan is None:
+            return super().generate(inputs, generation_config=generation_config, **kwargs)
+        from ..decode_engine import DecodeEngine, greedy_decode_loop
+        ids, am = kwargs["input_ids"], kwargs["attention_mask"]
+        cache = B200KVCache()
+        out = self(input_ids=ids, pixel_values=kwargs.get("pixel_values"), attention_mask=am, past_key_values=cache,
+                   use_cache=True, logits_to_keep=1)
+        first = out.logits[:, -1, :].argmax(-1)
+        lm = self.language_model
+        if plan["n_new"] == 1 or not DecodeEngine.eligible(lm.model, cache, lm.lm_head.weight.dtype):
+            if plan["n_new"] > 1:                             # e.g. a peft-wrapped projection: the per-step Python path
+                return super().generate(inputs, generation_config=generation_config, **kwargs)
+            new = first[:, None]
+        else:
+            pm = getattr(cache, "prefill_mask", None)         # merged prompt mask (zero = padded slot), ref :477-508
+            S = cache.get_seq_length()
+            n_steps = plan["n_new"] - 1
+            kbits, pos0 = None, torch.full((ids.shape[0],), S, dtype=torch.int64, device=ids.device)
+            if pm is not None and not bool((pm != 0).all()):
+                full = torch.cat((pm, torch.ones((pm.shape[0], n_steps + 1), dtype=pm.dtype, device=pm.device)), dim=1)
+                kbits = ops.kmask_bits(full)                  # one bitmask for the whole generation: step t reads its first S+t+1 bits
+                pos0 = pm.sum(dim=1).to(torch.int64)          # position id of the first generated token (ref :508)
+            new = greedy_decode_loop(lm.model, lm.lm_head, cache, first, pos0, n_steps, kbits, plan["eos"])
+        if plan["eos"]:
+            eos = torch.tensor(plan["eos"], device=new.device)
+            hit = torch.isin(new, eos)
+            after = (hit.cumsum(dim=1) - hit.long()) > 0       # strictly after a sequence's first EOS
+            new = torch.where(after, torch.full_like(new, plan["pad"]), new)
+            finished = hit.any(dim=1)
+            if bool(finished.all()):
+                last = int((hit.long().argmax(dim=1)).max())  # GenerationMixin stops right after the last sequence finishes
+                new = new[:, : last + 1]
+        return torch.cat((ids, new.to(ids.dtype)), dim=1)
 
     @torch.no_grad()
     def greedy_generate(self, input_ids, pixel_values=None, attention_mask=None, max_new_tokens=32, eos_token_id=None):

@@ -753,20 +753,6 @@ def test_attention_sliding_window(ops, cuda, dtype, hd, Sq, Sk, window):
     assert _rel(q.grad, qr.grad) < tol and _rel(k.grad, kr.grad) < tol and _rel(v.grad, vr.grad) < tol
 
 
-def test_attention_bwd_8_warp_kernels_still_agree(cuda):
-    """the 8/12-softmax-warp backward kernels stay in the library as a switchable fallback (MB200_ATTN_BWD_DKV16=0,
-    MB200_ATTN_BWD_DQ24=0, read once per process): run the backward parity tests against them in a child process"""
-    import os
-    import subprocess
-    import sys
-    env = dict(os.environ, MB200_ATTN_BWD_DKV16="0", MB200_ATTN_BWD_DQ24="0")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-k",
-                        "test_attention_tcgen05_bwd", "-p", "no:cacheprovider"], env=env, capture_output=True, text=True,
-                       timeout=900, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
-    assert " passed" in r.stdout
-
-
 @pytest.mark.parametrize("M,D,I", [(700, 1024, 2816), (7864, 4096, 14336), (513, 256, 1000)])
 @pytest.mark.parametrize("with_res", [False, True])
 def test_fused_swiglu_mlp_matches_the_unfused_kernels(ops, cuda, M, D, I, with_res):

@@ -295,3 +295,56 @@ def test_generate_on_a_worker_thread_matches_the_main_thread(cuda):
     assert decode_engine.native_steps - before >= 2 * 11
     for g in got:
         assert torch.equal(g, main)
+
+
+def _tiny_bf16_llava(cuda, seed=3, scale=4.0):
+    from transformers import LlamaConfig, SiglipVisionConfig
+    from mantis_b200.models.mllava import LlavaConfig, LlavaForConditionalGeneration
+    vc = SiglipVisionConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                            image_size=112, patch_size=14)
+    tc = LlamaConfig(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2,
+                     num_key_value_heads=1, vocab_size=1000, rms_norm_eps=1e-5, rope_theta=500000.0)
+    cfg = LlavaConfig(vision_config=vc, text_config=tc, image_token_index=990, pad_token_id=991, vocab_size=1000,
+                      vision_feature_select_strategy="full")
+    torch.manual_seed(seed)
+    model = LlavaForConditionalGeneration(cfg).to(cuda).to(torch.bfloat16).eval()
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.dim() >= 2:
+                p.mul_(scale)
+    return model
+
+
+@pytest.mark.parametrize("case", ["plain", "left_padded_uneven_images", "eos"])
+def test_fast_greedy_generate_equals_generation_mixin(cuda, case, monkeypatch):
+    """model.generate() takes the sync-free greedy loop for plain greedy decoding; its output (tokens, padding after EOS, length)
+    must equal what transformers' GenerationMixin.generate returns for the same call (MB200_FAST_GENERATE=0)."""
+    from mantis_b200.models import decode_engine
+    model = _tiny_bf16_llava(cuda)
+    g = torch.Generator().manual_seed(7)
+    ids = torch.randint(0, 980, (3, 60), generator=g)
+    ids[:, 5] = 990
+    am = torch.ones_like(ids)
+    n_img = 3
+    if case == "left_padded_uneven_images":
+        ids[0, :9] = 991; am[0, :9] = 0; ids[0, 5] = 991          # row 0: left padding, image moved inside the body
+        ids[0, 20] = 990
+        ids[1, 30] = 990; n_img = 4                               # row 1 carries two images
+    pv = torch.randn(n_img, 3, 112, 112, generator=g).bfloat16()
+    kw = dict(input_ids=ids.to(cuda), pixel_values=pv.to(cuda), attention_mask=am.to(cuda), max_new_tokens=40, do_sample=False,
+              num_beams=1, pad_token_id=991)
+    monkeypatch.setenv("MB200_FAST_GENERATE", "0")
+    ref = model.generate(**kw)
+    if case == "eos":                                             # an EOS id that the greedy continuation actually emits
+        new = ref[:, ids.shape[1]:]
+        kw["eos_token_id"] = [int(new[0, 7]), int(new[1, 19])]
+        ref = model.generate(**kw)
+        assert ref.shape[1] < ids.shape[1] + 40 or bool((ref[:, ids.shape[1]:] == 991).any())
+    monkeypatch.setenv("MB200_FAST_GENERATE", "1")
+    before = decode_engine.native_steps
+    out = model.generate(**kw)
+    assert decode_engine.native_steps > before
+    assert out.shape == ref.shape and torch.equal(out, ref), (out[:, 60:].tolist(), ref[:, 60:].tolist())
+    # anything beyond plain greedy decoding keeps going through GenerationMixin (here: sampling)
+    assert model._fast_greedy_plan(None, None, dict(kw, do_sample=True)) is None
+    assert model._fast_greedy_plan(None, None, dict(kw, streamer=object())) is None

@@ -105,7 +105,12 @@ def test_collator_hints_make_the_step_sync_free_with_identical_results(cuda, nam
     l1, g1 = run(merge_hint=hint)
     ops.check_deferred()                              # nothing to report
     assert torch.equal(l0, l1) and abs(l1.item() - fx["loss"].item()) < 1e-4
-    assert g0.keys() == g1.keys() and all(torch.equal(g0[k], g1[k]) for k in g0)
+    assert g0.keys() == g1.keys()
+    for k in g0:
+        if "embed_tokens" in k:       # scatter-add with repeated tokens (pad ids): fp32 atomics, order-dependent in the last bit
+            assert torch.allclose(g0[k], g1[k], rtol=1e-5, atol=1e-7), k
+        else:
+            assert torch.equal(g0[k], g1[k]), k
     bad = dict(hint, valid_rows=hint["valid_rows"] - 1)
     model.zero_grad(set_to_none=True)
     model(**b, merge_hint=bad)
