@@ -202,6 +202,8 @@ class B200DecoderModel(B200DecoderPreTrainedModel):
         past = cache.get_seq_length() if cache is not None else 0
         if position_ids is None:
             position_ids = torch.arange(past, past + S, device=inputs_embeds.device).unsqueeze(0).expand(B, S)
+        elif position_ids.shape[-1] != S:
+            raise ValueError(f"position_ids cover {position_ids.shape[-1]} positions, the input has {S} tokens")
         key_mask = None
         segs = kwargs.get("cu_segments")
         if attention_mask is not None and attention_mask.dim() == 4:

@@ -271,6 +271,9 @@ class LlavaForConditionalGeneration(LlavaPreTrainedModel, GenerationMixin):
         elif past_key_values is None or not isinstance(past_key_values, B200KVCache):
             past_key_values = B200KVCache()
         position_ids = kwargs.get("position_ids", None)
+        if position_ids is not None and position_ids.shape[-1] > input_ids.shape[1]:
+            # transformers >= 5 may hand over position ids for the WHOLE sequence; the model wants those of the new tokens
+            position_ids = position_ids[..., -input_ids.shape[1]:]
         if attention_mask is not None and position_ids is None:
             position_ids = attention_mask.long().cumsum(-1) - 1
             position_ids.masked_fill_(attention_mask == 0, 1)

@@ -107,8 +107,8 @@ def test_collator_hints_make_the_step_sync_free_with_identical_results(cuda, nam
     assert torch.equal(l0, l1) and abs(l1.item() - fx["loss"].item()) < 1e-4
     assert g0.keys() == g1.keys()
     for k in g0:
-        if "embed_tokens" in k:       # scatter-add with repeated tokens (pad ids): fp32 atomics, order-dependent in the last bit
-            assert torch.allclose(g0[k], g1[k], rtol=1e-5, atol=1e-7), k
+        if "embed" in k:              # scatter-adds with repeated rows (token / position embeddings): fp32 atomics, the last
+            assert torch.allclose(g0[k], g1[k], rtol=1e-5, atol=1e-7), k      # bit depends on the order of arrival
         else:
             assert torch.equal(g0[k], g1[k]), k
     bad = dict(hint, valid_rows=hint["valid_rows"] - 1)
