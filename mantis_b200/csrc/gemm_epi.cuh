@@ -51,34 +51,40 @@ __device__ __forceinline__ void swiglu_store32(const GemmEpi& epi, int row, int 
   const bool vec = (col0 + 32 <= N) && !((epi.ldc | epi.ldc2 | epi.ld_aux) & 7) &&
                    !((reinterpret_cast<uintptr_t>(epi.C) | reinterpret_cast<uintptr_t>(epi.C2) | reinterpret_cast<uintptr_t>(epi.aux0) |
                       reinterpret_cast<uintptr_t>(epi.aux1)) & 15);
+  float g[32], u[32];
+  if (vec) {                                            // every load of the chunk before the first store (see store32)
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    float g[8], u[8], o1[8], o2[8];
-    if (vec) { ld8(g0 + q * 8, g); if (u0) ld8(u0 + q * 8, u); }
-    else {
-      for (int j = 0; j < 8; ++j) {
-        const bool ok = col0 + q * 8 + j < N;
-        g[j] = ok ? __bfloat162float(g0[q * 8 + j]) : 0.f;
-        u[j] = (ok && u0) ? __bfloat162float(u0[q * 8 + j]) : 0.f;
-      }
-    }
+    for (int q = 0; q < 4; ++q) ld8(g0 + q * 8, g + q * 8);
+    if (u0) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float acc = bf16_round(v[q * 8 + j]);          // the value the unfused path would have stored and re-read
-      if (epi.mode == 1) {                                 // acc = up
-        o1[j] = acc;
-        o2[j] = bf16_round(g[j] / (1.f + __expf(-g[j]))) * acc;
-      } else {                                             // acc = d_act
-        const float sg = 1.f / (1.f + __expf(-g[j]));
-        o2[j] = acc * (g[j] * sg);                                          // d_up
-        o1[j] = acc * u[j] * (sg * (1.f + g[j] * (1.f - sg)));              // d_gate
-      }
+      for (int q = 0; q < 4; ++q) ld8(u0 + q * 8, u + q * 8);
     }
-    if (vec) { st8(c1 + q * 8, o1); st8(c2 + q * 8, o2); }
-    else {
-      for (int j = 0; j < 8; ++j)
-        if (col0 + q * 8 + j < N) { c1[q * 8 + j] = __float2bfloat16_rn(o1[j]); c2[q * 8 + j] = __float2bfloat16_rn(o2[j]); }
+  } else {
+    for (int j = 0; j < 32; ++j) {
+      const bool ok = col0 + j < N;
+      g[j] = ok ? __bfloat162float(g0[j]) : 0.f;
+      u[j] = (ok && u0) ? __bfloat162float(u0[j]) : 0.f;
     }
+  }
+  float o1[32], o2[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float acc = bf16_round(v[j]);                  // the value the unfused path would have stored and re-read
+    if (epi.mode == 1) {                                 // acc = up
+      o1[j] = acc;
+      o2[j] = bf16_round(g[j] / (1.f + __expf(-g[j]))) * acc;
+    } else {                                             // acc = d_act
+      const float sg = 1.f / (1.f + __expf(-g[j]));
+      o2[j] = acc * (g[j] * sg);                                          // d_up
+      o1[j] = acc * u[j] * (sg * (1.f + g[j] * (1.f - sg)));              // d_gate
+    }
+  }
+  if (vec) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { st8(c1 + q * 8, o1 + q * 8); st8(c2 + q * 8, o2 + q * 8); }
+  } else {
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j < N) { c1[j] = __float2bfloat16_rn(o1[j]); c2[j] = __float2bfloat16_rn(o2[j]); }
   }
 }
 
@@ -98,12 +104,19 @@ __device__ __forceinline__ void store32(const GemmEpi& epi, int row, int col0, i
     const bool vec = ((epi.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(epi.C) & 15) == 0) && (col0 + 32 <= N) &&
                      (!arow || (((epi.ld_add & 3) == 0) && ((reinterpret_cast<uintptr_t>(epi.addend) & 15) == 0)));
     if (vec) {
+      // all loads of the chunk are issued before the first store: destination and addend may be the same buffer (gradient
+      // accumulation), so the compiler cannot move a load above an earlier store on its own -- eight serialised L2 round trips
+      // per chunk would make the epilogue longer than the tile's mainloop
+      if (arow) {
+        float4 a[8];
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        float4 o = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-        if (arow) { const float4 a = *reinterpret_cast<const float4*>(arow + col0 + 4 * g); o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
-        *reinterpret_cast<float4*>(crow + col0 + 4 * g) = o;
+        for (int g = 0; g < 8; ++g) a[g] = *reinterpret_cast<const float4*>(arow + col0 + 4 * g);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) { v[4 * g] += a[g].x; v[4 * g + 1] += a[g].y; v[4 * g + 2] += a[g].z; v[4 * g + 3] += a[g].w; }
       }
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        *reinterpret_cast<float4*>(crow + col0 + 4 * g) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
     } else {
       for (int j = 0; j < 32; ++j)
         if (col0 + j < N) crow[col0 + j] = v[j] + (arow ? arow[col0 + j] : 0.f);
