@@ -21,6 +21,14 @@ if which in ("gemm", "gemm2cta"):
         ops.gemm(x, w)                                   # fwd  gate/up
         ops.gemm(g, w, trans_a=False, trans_b=False)     # dgrad
         ops.gemm(g, x, trans_a=True, trans_b=False)      # wgrad
+elif which == "swiglu":                                  # the MLP with SwiGLU fused into the GEMM epilogues, fwd + bwd
+    x = (torch.randn(1, M, 4096, device=dev) * 0.5).bfloat16().requires_grad_(True)
+    wg = (torch.randn(14336, 4096, device=dev) * 0.02).bfloat16().requires_grad_(True)
+    wu = (torch.randn(14336, 4096, device=dev) * 0.02).bfloat16().requires_grad_(True)
+    wd = (torch.randn(4096, 14336, device=dev) * 0.02).bfloat16().requires_grad_(True)
+    for _ in range(2):
+        y = ops.swiglu_mlp(x, wg, wu, wd, None)
+        y.backward(torch.randn_like(y))
 elif which == "cublas":                                  # the incumbent at the same shape, for a side-by-side ncu capture
     x = torch.randn(M, 4096, device=dev).bfloat16(); w = (torch.randn(14336, 4096, device=dev) * 0.02).bfloat16()
     for _ in range(4):
