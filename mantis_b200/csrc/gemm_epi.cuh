@@ -6,6 +6,7 @@
 //               mantis/train/zero_configs/zero3.json + scripts/train_mllava.sh:148 `--bf16 True`)
 #pragma once
 #include "common.cuh"
+#include "sm100_ptx.cuh"
 
 namespace gemm_epi {
 
@@ -42,49 +43,93 @@ __device__ __forceinline__ void st8(bf16* p, const float* f) {
   *reinterpret_cast<int4*>(p) = v;
 }
 
+// The operands an epilogue chunk reads from global memory (fp32 / bf16 addend, or gate (+ up) of the SwiGLU modes), fetched one
+// chunk AHEAD of their use: the epilogue warp issues chunk c+1's loads, then converts / stores chunk c, so the L2 round trip
+// (microseconds while the TMA producer keeps L2 busy) is paid under useful work instead of once per chunk.
+struct Prefetch {
+  int4 a[8];          // fp32 addend: 8 x float4 | bf16 addend: a[0..3] | swiglu: gate a[0..3], up a[4..7]
+  bool vec;           // the 32 columns are in range and every pointer / leading dimension allows 16-byte accesses
+};
+
+__device__ __forceinline__ bool chunk_vec(const GemmEpi& epi, int col0, int N) {
+  if (col0 + 32 > N) return false;
+  if (epi.mode)
+    return !((epi.ldc | epi.ldc2 | epi.ld_aux) & 7) &&
+           !((reinterpret_cast<uintptr_t>(epi.C) | reinterpret_cast<uintptr_t>(epi.C2) | reinterpret_cast<uintptr_t>(epi.aux0) |
+              reinterpret_cast<uintptr_t>(epi.aux1)) & 15);
+  if (epi.c_f32)
+    return ((epi.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(epi.C) & 15) == 0) &&
+           (!epi.addend || (((epi.ld_add & 3) == 0) && ((reinterpret_cast<uintptr_t>(epi.addend) & 15) == 0)));
+  return ((epi.ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(epi.C) & 15) == 0) &&
+         (!epi.addend || (((epi.ld_add & 7) == 0) && ((reinterpret_cast<uintptr_t>(epi.addend) & 15) == 0)));
+}
+
+__device__ __forceinline__ void prefetch32(const GemmEpi& epi, int row, int col0, int N, Prefetch& pf) {
+  pf.vec = chunk_vec(epi, col0, N);
+  if (!pf.vec) return;
+  if (epi.mode) {
+    const int4* g = reinterpret_cast<const int4*>(epi.aux0 + (size_t)row * epi.ld_aux + col0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) pf.a[q] = g[q];
+    if (epi.aux1) {
+      const int4* u = reinterpret_cast<const int4*>(epi.aux1 + (size_t)row * epi.ld_aux + col0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) pf.a[4 + q] = u[q];
+    }
+  } else if (epi.addend) {
+    if (epi.c_f32) {
+      const int4* a = reinterpret_cast<const int4*>(reinterpret_cast<const float*>(epi.addend) + (size_t)row * epi.ld_add + col0);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) pf.a[q] = a[q];
+    } else {
+      const int4* a = reinterpret_cast<const int4*>(reinterpret_cast<const bf16*>(epi.addend) + (size_t)row * epi.ld_add + col0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) pf.a[q] = a[q];
+    }
+  }
+}
+
+__device__ __forceinline__ void unpack8(const int4& v, float* f) {
+  const bf162* h = reinterpret_cast<const bf162*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { const float2 t = __bfloat1622float2(h[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+}
+
 // same arithmetic (and the same bf16 rounding points) as swiglu_fwd_kernel / swiglu_bwd_kernel in elementwise.cu
-__device__ __forceinline__ void swiglu_store32(const GemmEpi& epi, int row, int col0, int N, float (&v)[32]) {
+__device__ __forceinline__ void swiglu_one(int mode, float acc_raw, float g, float u, float& o1, float& o2) {
+  const float acc = bf16_round(acc_raw);                 // the value the unfused path would have stored and re-read
+  if (mode == 1) {                                       // acc = up:   o1 = up, o2 = silu(gate) * up
+    o1 = acc;
+    o2 = bf16_round(g / (1.f + __expf(-g))) * acc;
+  } else {                                               // acc = d_act: o1 = d_gate, o2 = d_up
+    const float sg = 1.f / (1.f + __expf(-g));
+    o2 = acc * (g * sg);
+    o1 = acc * u * (sg * (1.f + g * (1.f - sg)));
+  }
+}
+__device__ __forceinline__ void swiglu_store32(const GemmEpi& epi, int row, int col0, int N, float (&v)[32], const Prefetch& pf) {
   bf16* c1 = reinterpret_cast<bf16*>(epi.C) + (size_t)row * epi.ldc + col0;
   bf16* c2 = epi.C2 + (size_t)row * epi.ldc2 + col0;
   const bf16* g0 = epi.aux0 + (size_t)row * epi.ld_aux + col0;
   const bf16* u0 = epi.aux1 ? epi.aux1 + (size_t)row * epi.ld_aux + col0 : nullptr;
-  const bool vec = (col0 + 32 <= N) && !((epi.ldc | epi.ldc2 | epi.ld_aux) & 7) &&
-                   !((reinterpret_cast<uintptr_t>(epi.C) | reinterpret_cast<uintptr_t>(epi.C2) | reinterpret_cast<uintptr_t>(epi.aux0) |
-                      reinterpret_cast<uintptr_t>(epi.aux1)) & 15);
-  float g[32], u[32];
-  if (vec) {                                            // every load of the chunk before the first store (see store32)
+  if (pf.vec) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) ld8(g0 + q * 8, g + q * 8);
-    if (u0) {
+    for (int q = 0; q < 4; ++q) {                        // 8 columns at a time keeps the live registers low
+      float g[8], u[8], o1[8], o2[8];
+      unpack8(pf.a[q], g);
+      if (u0) unpack8(pf.a[4 + q], u);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) ld8(u0 + q * 8, u + q * 8);
+      for (int j = 0; j < 8; ++j) swiglu_one(epi.mode, v[q * 8 + j], g[j], u0 ? u[j] : 0.f, o1[j], o2[j]);
+      st8(c1 + q * 8, o1); st8(c2 + q * 8, o2);
     }
   } else {
     for (int j = 0; j < 32; ++j) {
-      const bool ok = col0 + j < N;
-      g[j] = ok ? __bfloat162float(g0[j]) : 0.f;
-      u[j] = (ok && u0) ? __bfloat162float(u0[j]) : 0.f;
+      if (col0 + j < N) {
+        float o1, o2;
+        swiglu_one(epi.mode, v[j], __bfloat162float(g0[j]), u0 ? __bfloat162float(u0[j]) : 0.f, o1, o2);
+        c1[j] = __float2bfloat16_rn(o1); c2[j] = __float2bfloat16_rn(o2);
+      }
     }
-  }
-  float o1[32], o2[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const float acc = bf16_round(v[j]);                  // the value the unfused path would have stored and re-read
-    if (epi.mode == 1) {                                 // acc = up
-      o1[j] = acc;
-      o2[j] = bf16_round(g[j] / (1.f + __expf(-g[j]))) * acc;
-    } else {                                             // acc = d_act
-      const float sg = 1.f / (1.f + __expf(-g[j]));
-      o2[j] = acc * (g[j] * sg);                                          // d_up
-      o1[j] = acc * u[j] * (sg * (1.f + g[j] * (1.f - sg)));              // d_gate
-    }
-  }
-  if (vec) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) { st8(c1 + q * 8, o1 + q * 8); st8(c2 + q * 8, o2 + q * 8); }
-  } else {
-    for (int j = 0; j < 32; ++j)
-      if (col0 + j < N) { c1[j] = __float2bfloat16_rn(o1[j]); c2[j] = __float2bfloat16_rn(o2[j]); }
   }
 }
 
@@ -95,28 +140,19 @@ __device__ __forceinline__ float epi_act(float x, int kind) {
   return x;
 }
 
-// v[32] = raw accumulators of (row, col0 .. col0+31); caller guarantees row < M and col0 < N
-__device__ __forceinline__ void store32(const GemmEpi& epi, int row, int col0, int N, float (&v)[32]) {
-  if (epi.mode) { swiglu_store32(epi, row, col0, N, v); return; }
+// v[32] = raw accumulators of (row, col0 .. col0+31); pf = prefetch32() of the same chunk; caller guarantees row < M, col0 < N
+__device__ __forceinline__ void store32(const GemmEpi& epi, int row, int col0, int N, float (&v)[32], const Prefetch& pf) {
+  if (epi.mode) { swiglu_store32(epi, row, col0, N, v, pf); return; }
   if (epi.c_f32) {
     float* crow = reinterpret_cast<float*>(epi.C) + (size_t)row * epi.ldc;
     const float* arow = epi.addend ? reinterpret_cast<const float*>(epi.addend) + (size_t)row * epi.ld_add : nullptr;
-    const bool vec = ((epi.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(epi.C) & 15) == 0) && (col0 + 32 <= N) &&
-                     (!arow || (((epi.ld_add & 3) == 0) && ((reinterpret_cast<uintptr_t>(epi.addend) & 15) == 0)));
-    if (vec) {
-      // all loads of the chunk are issued before the first store: destination and addend may be the same buffer (gradient
-      // accumulation), so the compiler cannot move a load above an earlier store on its own -- eight serialised L2 round trips
-      // per chunk would make the epilogue longer than the tile's mainloop
-      if (arow) {
-        float4 a[8];
+    if (pf.vec) {
 #pragma unroll
-        for (int g = 0; g < 8; ++g) a[g] = *reinterpret_cast<const float4*>(arow + col0 + 4 * g);
-#pragma unroll
-        for (int g = 0; g < 8; ++g) { v[4 * g] += a[g].x; v[4 * g + 1] += a[g].y; v[4 * g + 2] += a[g].z; v[4 * g + 3] += a[g].w; }
+      for (int g = 0; g < 8; ++g) {
+        float4 o = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+        if (arow) { const float4 a = *reinterpret_cast<const float4*>(&pf.a[g]); o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+        *reinterpret_cast<float4*>(crow + col0 + 4 * g) = o;
       }
-#pragma unroll
-      for (int g = 0; g < 8; ++g)
-        *reinterpret_cast<float4*>(crow + col0 + 4 * g) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
     } else {
       for (int j = 0; j < 32; ++j)
         if (col0 + j < N) crow[col0 + j] = v[j] + (arow ? arow[col0 + j] : 0.f);
@@ -133,25 +169,18 @@ __device__ __forceinline__ void store32(const GemmEpi& epi, int row, int col0, i
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = epi_act(v[j], epi.act);
   }
-  const bool vec_ok = ((epi.ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(epi.C) & 15) == 0) &&
-                      (!arow || (((epi.ld_add & 7) == 0) && ((reinterpret_cast<uintptr_t>(epi.addend) & 15) == 0)));
-  if (vec_ok && col0 + 32 <= N) {
+  if (pf.vec) {
     if (arow) {
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        int4 a4 = *reinterpret_cast<const int4*>(arow + col0 + g * 8);
-        const bf162* ah = reinterpret_cast<const bf162*>(&a4);
+        float f[8];
+        unpack8(pf.a[g], f);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(ah[j]); v[g * 8 + 2 * j] += f.x; v[g * 8 + 2 * j + 1] += f.y; }
+        for (int j = 0; j < 8; ++j) v[g * 8 + j] += f[j];
       }
     }
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      int4 o4; bf162* oh = reinterpret_cast<bf162*>(&o4);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
-      *reinterpret_cast<int4*>(crow + col0 + g * 8) = o4;
-    }
+    for (int g = 0; g < 4; ++g) st8(crow + col0 + g * 8, v + g * 8);
   } else {
     for (int j = 0; j < 32; ++j) {
       if (col0 + j < N) {
@@ -159,6 +188,30 @@ __device__ __forceinline__ void store32(const GemmEpi& epi, int row, int col0, i
         if (arow) x += __bfloat162float(arow[col0 + j]);
         crow[col0 + j] = __float2bfloat16_rn(x);
       }
+    }
+  }
+}
+
+// One epilogue warp's share of an accumulator tile: NCHUNK chunks of 32 columns starting at TMEM column `tcol` / global column
+// `n0`, for the warp's 32 rows (TMEM lanes 32 * (warp % 4) ...).  Software-pipelined: chunk c+1's global operands are in
+// flight while chunk c is converted and stored.
+template <int NCHUNK>
+__device__ __forceinline__ void epilogue_rows(const GemmEpi& epi, uint32_t taddr, int row, bool row_ok, int n0, int N) {
+  Prefetch pf[2];
+  pf[0].vec = false; pf[1].vec = false;
+  if (row_ok && n0 < N) prefetch32(epi, row, n0, N, pf[0]);
+#pragma unroll
+  for (int c = 0; c < NCHUNK; ++c) {
+    uint32_t r[32];
+    sm100::tmem_ld_32x32b_x32(taddr + c * 32, r);
+    const int col0 = n0 + c * 32;
+    if (c + 1 < NCHUNK && row_ok && col0 + 32 < N) prefetch32(epi, row, col0 + 32, N, pf[(c + 1) & 1]);
+    sm100::tmem_ld_wait();
+    if (row_ok && col0 < N) {
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      store32(epi, row, col0, N, v, pf[c & 1]);
     }
   }
 }

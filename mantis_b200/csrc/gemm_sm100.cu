@@ -41,7 +41,7 @@ __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& mb
 }
 
 template <int BN, int STAGES, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const GemmEpi epi, const int M, const int N, const int K) {
   constexpr int B_STAGE_BYTES = BN * BK * 2;
@@ -64,7 +64,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -129,29 +129,19 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
+    // 8 epilogue warps: two per TMEM lane quarter, each takes one half of the accumulator's BN columns
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       int mb_, nb_; tile_coords(t, num_m, num_n, mb_, nb_);
       const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
       const int row = mb_ * BM + q * 32 + lane;
-      const int n0 = nb_ * BN;
+      const int n0 = nb_ * BN + half * (BN / 2);
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
-      const bool row_ok = row < M;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c * 32, r);
-        tmem_ld_wait();
-        const int col0 = n0 + c * 32;
-        if (row_ok && col0 < N) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          gemm_epi::store32(epi, row, col0, N, v);
-        }
-      }
+      gemm_epi::epilogue_rows<BN / 64>(epi, tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + half * (BN / 2), row, row < M,
+                                       n0, N);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
@@ -174,7 +164,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   if (cfg != cudaSuccess) { mb200_set_last_error("cudaFuncSetAttribute(max dynamic smem) failed"); return -EIO; }
   const int num_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = num_tiles < mb::num_sms() ? num_tiles : mb::num_sms();
-  kern<<<grid, 192, smem, st>>>(tmA, tmB, epi, M, N, K);
+  kern<<<grid, 320, smem, st>>>(tmA, tmB, epi, M, N, K);
   return 0;
 }
 

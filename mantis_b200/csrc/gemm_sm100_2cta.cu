@@ -28,7 +28,7 @@ __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& mb
 }
 
 template <bool A_MN, bool B_MN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const GemmEpi epi, const int M, const int N, const int K) {
   constexpr uint32_t TMEM_COLS = 512;       // 2 accumulator stages x 256 columns
@@ -52,7 +52,7 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 16); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_2cta(tmem_slot, TMEM_COLS);
@@ -113,29 +113,18 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
     }
   } else {
+    // 8 epilogue warps: two per TMEM lane quarter, each takes one 128-column half of the CTA's 128 x 256 accumulator
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     int it = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
       int mb_, nb_; tile_coords(t, num_m, num_n, mb_, nb_);
       const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
       const int row = mb_ * 256 + (int)rank * BM + q * 32 + lane;
-      const int n0 = nb_ * 256;
+      const int n0 = nb_ * 256 + half * 128;
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
-      const bool row_ok = row < M;
-#pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + c * 32, r);
-        tmem_ld_wait();
-        const int col0 = n0 + c * 32;
-        if (row_ok && col0 < N) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          gemm_epi::store32(epi, row, col0, N, v);
-        }
-      }
+      gemm_epi::epilogue_rows<4>(epi, tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + half * 128, row, row < M, n0, N);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);
@@ -159,7 +148,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpi&
   const int num_tiles = ((M + 255) / 256) * ((N + 255) / 256);
   int clusters = mb::num_sms() / 2;
   if (num_tiles < clusters) clusters = num_tiles;
-  kern<<<clusters * 2, 192, smem, st>>>(tmA, tmB, epi, M, N, K);
+  kern<<<clusters * 2, 320, smem, st>>>(tmA, tmB, epi, M, N, K);
   return 0;
 }
 }  // namespace

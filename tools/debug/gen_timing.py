@@ -31,6 +31,16 @@ with torch.no_grad():
             e1.record(); t_issue = time.perf_counter() - t0
             torch.cuda.synchronize(); t_all = time.perf_counter() - t0
         print(f"loop n={n}: device {e0.elapsed_time(e1)/n:.3f} ms/step, host issue {t_issue/n*1e3:.3f} ms/step, wall {t_all/n*1e3:.3f}", flush=True)
+    # phases of generate() itself
+    import mantis_b200.models.decode_engine as de
+    orig = de.greedy_decode_loop
+    def timed_loop(*a, **k):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        r = orig(*a, **k)
+        t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
+        print(f"   inside generate: loop issue {(t1 - t0) * 1e3:.1f} ms, +drain {(t2 - t1) * 1e3:.1f} ms, n_steps {a[5]}", flush=True)
+        return r
+    de.greedy_decode_loop = timed_loop
     for n in (1, 128, 512):
         for rep in range(2):
             torch.cuda.synchronize(); t0 = time.perf_counter()
