@@ -321,7 +321,7 @@ class LlavaForConditionalGeneration(LlavaPreTrainedModel, GenerationMixin):
         eos = kwargs.get("eos_token_id", gc.eos_token_id)
         eos = [] if eos is None else ([int(e) for e in eos] if isinstance(eos, (list, tuple)) else [int(eos)])
         min_new = kwargs.get("min_new_tokens", gc.min_new_tokens) or 0
-        if n_new < 1 or (eos and min_new):                  # EOS suppression before min_new_tokens needs the logits processor
+        if n_new < 1 or min_new > n_new:
             return None
         pad = kwargs.get("pad_token_id", gc.pad_token_id)
         if eos and pad is None:
@@ -331,7 +331,7 @@ class LlavaForConditionalGeneration(LlavaPreTrainedModel, GenerationMixin):
         if (not ids.is_cuda or lm.lm_head.weight.dtype != torch.bfloat16 or a.head_dim != 128 or not 0 < ids.shape[0] <= 16
                 or ops.FORCE_GENERIC):
             return None
-        return {"n_new": n_new, "eos": eos, "pad": pad}
+        return {"n_new": n_new, "eos": eos, "pad": pad, "min_new": int(min_new)}
 
     @torch.no_grad()
     def generate(self, inputs=None, generation_config=None, **kwargs):
@@ -367,6 +367,9 @@ class LlavaForConditionalGeneration(LlavaPreTrainedModel, GenerationMixin):
         if plan["eos"]:
             eos = torch.tensor(plan["eos"], device=new.device)
             hit = torch.isin(new, eos)
+            if plan["min_new"] and bool(hit[:, : plan["min_new"]].any()):
+                # GenerationMixin would have suppressed this EOS (MinNewTokensLengthLogitsProcessor) and continued differently
+                return super().generate(inputs, generation_config=generation_config, **kwargs)
             after = (hit.cumsum(dim=1) - hit.long()) > 0       # strictly after a sequence's first EOS
             new = torch.where(after, torch.full_like(new, plan["pad"]), new)
             finished = hit.any(dim=1)

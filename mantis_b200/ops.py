@@ -138,6 +138,27 @@ def colsum(x2d, out=None, accumulate=False):
     return out
 
 
+WGRAD_SIDE_STREAM = os.environ.get("MB200_WGRAD_STREAM", "0") == "1"
+_side_streams = {}
+
+
+def wgrad_stream(device):
+    """the side stream the weight-gradient GEMMs run on when MB200_WGRAD_STREAM=1 (None otherwise)"""
+    if not WGRAD_SIDE_STREAM:
+        return None
+    key = torch.device(device).index or 0
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
+def join_wgrad_stream(device):
+    """make the current stream wait for every weight-gradient GEMM issued so far (before the gradients are reduced / consumed)"""
+    st = wgrad_stream(device)
+    if st is not None:
+        torch.cuda.current_stream(device).wait_stream(st)
+
+
 def _wgrad_into_main(g2, x2, w):
     """main_grad += g2^T @ x2 for a weight whose gradient lives in a B200Trainer flat buffer (`w._b200_main_grad`, an
     [out, in] view; fp32 by default): accumulation happens in the wgrad epilogue, in the buffer's own precision.  The trainer
@@ -145,7 +166,16 @@ def _wgrad_into_main(g2, x2, w):
     afterwards overwrites (B200Trainer._mark_fresh / _fold_grad)."""
     mg = w._b200_main_grad
     fresh = getattr(w, "_b200_grad_fresh", False)      # first product since the optimizer step: write, do not accumulate
-    gemm(g2, x2, trans_a=True, trans_b=False, addend=None if fresh else mg, out=mg)
+    side = wgrad_stream(mg.device)
+    if side is None:
+        gemm(g2, x2, trans_a=True, trans_b=False, addend=None if fresh else mg, out=mg)
+    else:
+        # The weight gradient is off the critical path of backward (nothing reads it before the optimizer): issued on a side
+        # stream, its persistent CTAs take the SMs that the ragged last wave of the dgrad GEMMs leaves idle, and vice versa.
+        side.wait_stream(torch.cuda.current_stream(mg.device))
+        with torch.cuda.stream(side):
+            gemm(g2, x2, trans_a=True, trans_b=False, addend=None if fresh else mg, out=mg)
+        g2.record_stream(side); x2.record_stream(side)   # autograd frees them on the main stream; the allocator must wait
     w._b200_grad_fresh = False
 
 
@@ -184,9 +214,7 @@ class _LinearFn(torch.autograd.Function):
         if ctx.act is not None:
             g2 = activation_bwd(pre, g2, ctx.act)
         gx = gw = gb = None
-        if ctx.needs_input_grad[0]:
-            gx = gemm(g2, weight, trans_a=False, trans_b=False).reshape(ctx.in_shape)      # dx = dy @ W
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1]:                  # first: it may run on the side stream, next to the dgrad below
             wref = ctx.weight_ref
             if wref is not None:
                 # gradient accumulation fused into the wgrad epilogue: main_grad += dy^T @ x (no temporary, no extra pass;
@@ -194,6 +222,8 @@ class _LinearFn(torch.autograd.Function):
                 _wgrad_into_main(g2, x2, wref)
             else:
                 gw = gemm(g2, x2, trans_a=True, trans_b=False)                             # dW = dy^T @ x
+        if ctx.needs_input_grad[0]:
+            gx = gemm(g2, weight, trans_a=False, trans_b=False).reshape(ctx.in_shape)      # dx = dy @ W
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = colsum(g2)
         return gx, gw, gb, None, gres
@@ -224,11 +254,6 @@ class _MultiLinearFn(torch.autograd.Function):
             g2 = gy.reshape(-1, w.shape[0])
             if g2.stride(1) != 1:
                 g2 = g2.contiguous()
-            if ctx.needs_input_grad[0]:
-                if gx is None:
-                    gx = gemm(g2, w, trans_a=False, trans_b=False)
-                else:
-                    gemm(g2, w, trans_a=False, trans_b=False, addend=gx, out=gx)
             gw = None
             if ctx.needs_input_grad[1 + i]:
                 wref = ctx.wrefs[i]
@@ -237,6 +262,11 @@ class _MultiLinearFn(torch.autograd.Function):
                 else:
                     gw = gemm(g2, x2, trans_a=True, trans_b=False)
             gws.append(gw)
+            if ctx.needs_input_grad[0]:
+                if gx is None:
+                    gx = gemm(g2, w, trans_a=False, trans_b=False)
+                else:
+                    gemm(g2, w, trans_a=False, trans_b=False, addend=gx, out=gx)
         return (gx.reshape(ctx.in_shape) if gx is not None else None, *gws)
 
 
@@ -374,18 +404,19 @@ class _SwigluMLPFn(torch.autograd.Function):
         if g2.stride(1) != 1 or g2.stride(0) % 8 or g2.data_ptr() % 16:
             g2 = g2.contiguous()
         M = g2.shape[0]
+        def wgrad(i, dy_, x_):
+            if not ctx.needs_input_grad[1 + i]:
+                return None
+            if ctx.wrefs[i] is not None:
+                _wgrad_into_main(dy_, x_, ctx.wrefs[i])
+                return None
+            return gemm(dy_, x_, trans_a=True, trans_b=False)
+
+        gwd = wgrad(2, g2, a)                          # needs nothing computed here: may overlap the fused dgrad below
         dg = torch.empty_like(g); du = torch.empty_like(u)
         _call("mb200_gemm_bf16_swiglu_bwd", _p(g2), _p(wd), _p(g), _p(u), _p(dg), _p(du), M, I, Dout, g2.stride(0), wd.stride(0),
               I, _st())
-        grads_w = []
-        for w, wref, (dy_, x_) in zip((wg, wu, wd), ctx.wrefs, ((dg, x2), (du, x2), (g2, a))):
-            gw = None
-            if ctx.needs_input_grad[1 + len(grads_w)]:
-                if wref is not None:
-                    _wgrad_into_main(dy_, x_, wref)
-                else:
-                    gw = gemm(dy_, x_, trans_a=True, trans_b=False)
-            grads_w.append(gw)
+        grads_w = [wgrad(0, dg, x2), wgrad(1, du, x2), gwd]
         gx = None
         if ctx.needs_input_grad[0]:
             gx = gemm(dg, wg, trans_a=False, trans_b=False)

@@ -230,6 +230,8 @@ class B200Trainer:
                 lo = self._layer_starts[i + 1] if i + 1 < n else None
                 if lo is None or self._reduced_from is None or lo >= self._reduced_from:
                     return
+                if self.flat_grad.is_cuda:
+                    ops.join_wgrad_stream(self.flat_grad.device)
                 self._works.append(dist.all_reduce(self.flat_grad[lo:self._reduced_from], op=dist.ReduceOp.SUM, async_op=True))
                 self._reduced_from = lo
             return cb
@@ -354,6 +356,8 @@ class B200Trainer:
 
     def optimizer_step(self):
         self._check_views()
+        if self.flat_grad.is_cuda:
+            ops.join_wgrad_stream(self.flat_grad.device)      # weight-gradient GEMMs issued on the side stream (if enabled)
         self._zero_untouched()
         scale = self.reduce_gradients()
         st = self.state

@@ -346,5 +346,10 @@ def test_fast_greedy_generate_equals_generation_mixin(cuda, case, monkeypatch):
     assert decode_engine.native_steps > before
     assert out.shape == ref.shape and torch.equal(out, ref), (out[:, 60:].tolist(), ref[:, 60:].tolist())
     # anything beyond plain greedy decoding keeps going through GenerationMixin (here: sampling)
+    if case == "eos":                                             # min_new_tokens: fast when no EOS shows up early, else GenerationMixin
+        kw2 = dict(kw, min_new_tokens=12)
+        monkeypatch.setenv("MB200_FAST_GENERATE", "0"); ref2 = model.generate(**kw2)
+        monkeypatch.setenv("MB200_FAST_GENERATE", "1"); out2 = model.generate(**kw2)
+        assert torch.equal(out2, ref2)
     assert model._fast_greedy_plan(None, None, dict(kw, do_sample=True)) is None
     assert model._fast_greedy_plan(None, None, dict(kw, streamer=object())) is None
