@@ -23,6 +23,7 @@ struct GemmEpi {
   int mode;
   const bf16* aux0; const bf16* aux1; long long ld_aux;
   bf16* C2; long long ldc2;
+  int tma_store;                        // plain bf16 output (no addend / fp32 / SwiGLU): written by TMA from a swizzled smem tile
 };
 
 struct SwigluArgs { int mode; const bf16* aux0; const bf16* aux1; long long ld_aux; bf16* C2; long long ldc2; };
@@ -189,6 +190,50 @@ __device__ __forceinline__ void store32(const GemmEpi& epi, int row, int col0, i
         crow[col0 + j] = __float2bfloat16_rn(x);
       }
     }
+  }
+}
+
+// Plain bf16 output through TMA: the warp converts 64 columns of its 32 rows, parks them in its private 4 KB shared-memory tile
+// in the 128B-swizzled layout (16-byte chunk j of row r at r * 128 + ((j ^ (r & 7)) << 4): conflict-free 16-byte stores), and ONE
+// thread hands the tile to the TMA unit, which writes full 128-byte lines and clips rows / columns beyond M / N by itself.
+// Replaces 32 x 16-byte stores per thread that each touch half a sector of 32 different lines.
+template <int NCHUNK64>
+__device__ __forceinline__ void epilogue_rows_tma(const GemmEpi& epi, const CUtensorMap* tmC, uint8_t* stage, uint32_t taddr,
+                                                  int row0, int n0, int N, int lane) {
+#pragma unroll 1
+  for (int cc = 0; cc < NCHUNK64; ++cc) {
+    const int col0 = n0 + cc * 64;
+    if (col0 >= N) break;
+    if (lane == 0) sm100::tma_store_wait_read0();            // the previous store has finished READING the staging tile
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {                            // 32 columns at a time keeps the live registers low
+      uint32_t r[32];
+      sm100::tmem_ld_32x32b_x32(taddr + cc * 64 + h * 32, r);
+      sm100::tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (epi.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (col0 + h * 32 + j < N) v[j] += __bfloat162float(__ldg(epi.bias + col0 + h * 32 + j));
+      }
+      if (epi.act) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = epi_act(v[j], epi.act);
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        int4 o; bf162* oh = reinterpret_cast<bf162*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
+        const int chunk = h * 4 + g;
+        *reinterpret_cast<int4*>(stage + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = o;
+      }
+    }
+    sm100::fence_proxy_async();                              // generic-proxy writes -> visible to the async (TMA) proxy
+    __syncwarp();
+    if (lane == 0) { sm100::tma_store_2d(tmC, stage, col0, row0); sm100::tma_store_commit(); }
   }
 }
 

@@ -3,6 +3,7 @@
 // one third versus the single-CTA 128x256 tile), the even CTA's MMA thread issues tcgen05.mma.cta_group::2 (M = 256,
 // N = 256, K = 16) which reads A from each CTA's shared memory and the two halves of B from both, and accumulates rows
 // 0-127 in CTA0's TMEM and rows 128-255 in CTA1's.  Same epilogue / majorness options as gemm_sm100.cu.
+#include <stdlib.h>
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 #include "tmap.cuh"
@@ -30,7 +31,7 @@ __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& mb
 template <bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                       const GemmEpi epi, const int M, const int N, const int K) {
+                       const __grid_constant__ CUtensorMap tmC, const GemmEpi epi, const int M, const int N, const int K) {
   constexpr uint32_t TMEM_COLS = 512;       // 2 accumulator stages x 256 columns
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -41,6 +42,7 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* sStage = sB + STAGES * B_STAGE + 1024;   // 8 x 4 KB: one 32-row x 64-column staging tile per epilogue warp (TMA store)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();          // 0 = leader
@@ -51,6 +53,7 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmB);
+    if (epi.tma_store) prefetch_tmap(&tmC);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 16); }
     fence_barrier_init();
@@ -124,12 +127,17 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const int n0 = nb_ * 256 + half * 128;
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
-      gemm_epi::epilogue_rows<4>(epi, tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + half * 128, row, row < M, n0, N);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + half * 128;
+      if (epi.tma_store)
+        gemm_epi::epilogue_rows_tma<2>(epi, &tmC, sStage + (warp - 2) * 4096, taddr, row - lane, n0, N, lane);
+      else
+        gemm_epi::epilogue_rows<4>(epi, taddr, row, row < M, n0, N);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);
     }
   }
+  if (warp >= 2 && lane == 0 && epi.tma_store) tma_store_wait_all0();     // outstanding bulk stores complete before the CTA exits
   tc_fence_before();
   cluster_sync_all();
   if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc_2cta(tmem_base, TMEM_COLS); }
@@ -137,8 +145,9 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
 
 template <bool A_MN, bool B_MN>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpi& epi, int M, int N, int K, cudaStream_t st) {
-  constexpr int smem = STAGES * (A_STAGE + B_STAGE) + 1024 + 256;
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmEpi& epi, int M, int N, int K,
+                  cudaStream_t st) {
+  constexpr int smem = STAGES * (A_STAGE + B_STAGE) + 1024 /*barriers*/ + 8 * 4096 /*TMA-store staging*/ + 1024 /*alignment*/;
   auto kern = gemm_sm100_2cta_kernel<A_MN, B_MN>;
   // function-local static with a dynamic initialiser: initialised exactly once even when several host threads race here
   // (generate() on a worker thread, mantis/models/mllava/utils.py:100-186)
@@ -148,7 +157,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpi&
   const int num_tiles = ((M + 255) / 256) * ((N + 255) / 256);
   int clusters = mb::num_sms() / 2;
   if (num_tiles < clusters) clusters = num_tiles;
-  kern<<<clusters * 2, 320, smem, st>>>(tmA, tmB, epi, M, N, K);
+  kern<<<clusters * 2, 320, smem, st>>>(tmA, tmB, tmC, epi, M, N, K);
   return 0;
 }
 }  // namespace
@@ -171,12 +180,20 @@ int mb200_gemm_2cta_impl(const void* A, const void* B, void* C, const void* bias
   epi.C = C; epi.ldc = ldc; epi.bias = (const bf16*)bias; epi.addend = addend; epi.ld_add = ld_add; epi.act = act;
   epi.c_f32 = c_f32; epi.mode = 0; epi.aux0 = nullptr; epi.aux1 = nullptr; epi.ld_aux = 0; epi.C2 = nullptr; epi.ldc2 = 0;
   if (swiglu) { epi.mode = swiglu->mode; epi.aux0 = swiglu->aux0; epi.aux1 = swiglu->aux1; epi.ld_aux = swiglu->ld_aux; epi.C2 = swiglu->C2; epi.ldc2 = swiglu->ldc2; }
+  // TMA-store epilogue for the plain bf16 output (forward projections, first dgrad of a group, LM-head chunks)
+  static const int tma_store_on = [] { const char* e = getenv("MB200_GEMM_TMA_STORE"); return (e && e[0] == '0') ? 0 : 1; }();
+  CUtensorMap tmC = tmA;
+  epi.tma_store = 0;
+  if (tma_store_on && !c_f32 && !swiglu && !addend && !(ldc & 7) && !(reinterpret_cast<uintptr_t>(C) & 15)) {
+    if ((rc = mbtmap::make_2d_store(&tmC, C, M, N, ldc, 64, 32))) return rc;
+    epi.tma_store = 1;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   const bool a_mn = transA != 0, b_mn = transB == 0;
-  if (!a_mn && !b_mn) rc = launch<false, false>(tmA, tmB, epi, M, N, K, st);
-  else if (!a_mn && b_mn) rc = launch<false, true>(tmA, tmB, epi, M, N, K, st);
-  else if (a_mn && b_mn) rc = launch<true, true>(tmA, tmB, epi, M, N, K, st);
-  else rc = launch<true, false>(tmA, tmB, epi, M, N, K, st);
+  if (!a_mn && !b_mn) rc = launch<false, false>(tmA, tmB, tmC, epi, M, N, K, st);
+  else if (!a_mn && b_mn) rc = launch<false, true>(tmA, tmB, tmC, epi, M, N, K, st);
+  else if (a_mn && b_mn) rc = launch<true, true>(tmA, tmB, tmC, epi, M, N, K, st);
+  else rc = launch<true, false>(tmA, tmB, tmC, epi, M, N, K, st);
   if (rc) return rc;
   MB200_CHECK_LAUNCH();
   return MB200_OK;

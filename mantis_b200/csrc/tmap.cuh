@@ -40,6 +40,12 @@ static inline int make_2d(CUtensorMap* tm, const void* base, long long rows, lon
   return 0;
 }
 
+// 2-D bf16 map used as a TMA-STORE destination (no L2 promotion hint needed for stores)
+static inline int make_2d_store(CUtensorMap* tm, void* base, long long rows, long long cols, long long ld, int box_cols,
+                                int box_rows) {
+  return make_2d(tm, base, rows, cols, ld, box_cols, box_rows);
+}
+
 // 4-D bf16 map over x[B, S, H, hd] (element strides sb, ss, sh; hd contiguous): dims (hd, H, S, B), box (64, 1, rows, 1)
 static inline int make_bshd(CUtensorMap* tm, const void* base, int B, int S, int H, int hd, long long sb, long long ss,
                             long long sh, int box_rows) {
