@@ -23,7 +23,7 @@ struct GemmEpi {
   int mode;
   const bf16* aux0; const bf16* aux1; long long ld_aux;
   bf16* C2; long long ldc2;
-  int tma_store;                        // plain bf16 output (no addend / fp32 / SwiGLU): written by TMA from a swizzled smem tile
+  int tma_store;                        // output written (fp32 accumulate: reduce-added) by TMA from a swizzled smem tile
 };
 
 struct SwigluArgs { int mode; const bf16* aux0; const bf16* aux1; long long ld_aux; bf16* C2; long long ldc2; };
@@ -193,47 +193,86 @@ __device__ __forceinline__ void store32(const GemmEpi& epi, int row, int col0, i
   }
 }
 
-// Plain bf16 output through TMA: the warp converts 64 columns of its 32 rows, parks them in its private 4 KB shared-memory tile
-// in the 128B-swizzled layout (16-byte chunk j of row r at r * 128 + ((j ^ (r & 7)) << 4): conflict-free 16-byte stores), and ONE
-// thread hands the tile to the TMA unit, which writes full 128-byte lines and clips rows / columns beyond M / N by itself.
-// Replaces 32 x 16-byte stores per thread that each touch half a sector of 32 different lines.
-template <int NCHUNK64>
+// Output through TMA: the warp converts its 32 rows, parks them in its private 4 KB shared-memory tile in the 128B-swizzled
+// layout (16-byte chunk j of row r at r * 128 + ((j ^ (r & 7)) << 4): conflict-free 16-byte stores), and ONE thread hands the
+// tile to the TMA unit, which writes full 128-byte lines and clips rows / columns beyond M / N by itself.
+//   bf16 C (+ bias / activation / bf16 addend, which is prefetched per thread one chunk ahead): 64-column tiles, TMA store
+//   fp32 C (wgrad into the main gradient): 32-column tiles; accumulation is a TMA REDUCE-ADD -- the previous value of the
+//   gradient is added inside the L2 and never read by the SM
+// Replaces 16-byte stores that each touch half a sector of 32 different lines (and, for fp32, the addend loads).
+template <int NCHUNK>
 __device__ __forceinline__ void epilogue_rows_tma(const GemmEpi& epi, const CUtensorMap* tmC, uint8_t* stage, uint32_t taddr,
-                                                  int row0, int n0, int N, int lane) {
-#pragma unroll 1
-  for (int cc = 0; cc < NCHUNK64; ++cc) {
-    const int col0 = n0 + cc * 64;
-    if (col0 >= N) break;
-    if (lane == 0) sm100::tma_store_wait_read0();            // the previous store has finished READING the staging tile
-    __syncwarp();
+                                                  int row, bool row_ok, int n0, int N, int lane) {
+  const int row0 = row - lane;
+  const bool f32 = epi.c_f32 != 0;
+  const bool pre = !f32 && epi.addend != nullptr;            // bf16 addend: per-thread loads, one chunk ahead
+  Prefetch pf[2];
+  pf[0].vec = false; pf[1].vec = false;
+  if (pre && row_ok && n0 < N) prefetch32(epi, row, n0, N, pf[0]);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {                            // 32 columns at a time keeps the live registers low
+  for (int c = 0; c < NCHUNK; ++c) {
+    const int col0 = n0 + c * 32;
+    if (col0 < N) {                                          // uniform across the warp
       uint32_t r[32];
-      sm100::tmem_ld_32x32b_x32(taddr + cc * 64 + h * 32, r);
+      sm100::tmem_ld_32x32b_x32(taddr + c * 32, r);
+      if (pre && c + 1 < NCHUNK && row_ok && col0 + 32 < N) prefetch32(epi, row, col0 + 32, N, pf[(c + 1) & 1]);
+      if (f32 || (c & 1) == 0) {
+        if (lane == 0) sm100::tma_store_wait_read0();        // the previous bulk operation has finished READING the tile
+        __syncwarp();
+      }
       sm100::tmem_ld_wait();
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      if (epi.bias) {
+      if (f32) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) if (col0 + h * 32 + j < N) v[j] += __bfloat162float(__ldg(epi.bias + col0 + h * 32 + j));
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<float4*>(stage + lane * 128 + ((g ^ (lane & 7)) << 4)) =
+              make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+      } else {
+        if (epi.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (col0 + j < N) v[j] += __bfloat162float(__ldg(epi.bias + col0 + j));
+        }
+        if (epi.act) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = epi_act(v[j], epi.act);
+        }
+        if (pre) {
+          if (pf[c & 1].vec) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float f[8];
+              unpack8(pf[c & 1].a[g], f);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[g * 8 + j] += f[j];
+            }
+          } else if (row_ok) {                               // column tail: scalar addend reads
+            const bf16* arow = reinterpret_cast<const bf16*>(epi.addend) + (size_t)row * epi.ld_add;
+            for (int j = 0; j < 32; ++j) if (col0 + j < N) v[j] += __bfloat162float(arow[col0 + j]);
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          int4 o; bf162* oh = reinterpret_cast<bf162*>(&o);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
+          const int chunk = (c & 1) * 4 + g;
+          *reinterpret_cast<int4*>(stage + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = o;
+        }
       }
-      if (epi.act) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = epi_act(v[j], epi.act);
-      }
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        int4 o; bf162* oh = reinterpret_cast<bf162*>(&o);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
-        const int chunk = h * 4 + g;
-        *reinterpret_cast<int4*>(stage + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = o;
+      const bool flush = f32 || (c & 1) == 1 || c + 1 == NCHUNK || col0 + 32 >= N;
+      if (flush) {
+        sm100::fence_proxy_async();                          // generic-proxy writes -> visible to the async (TMA) proxy
+        __syncwarp();
+        if (lane == 0) {
+          const int tc0 = f32 ? col0 : col0 - (c & 1) * 32;
+          if (f32 && epi.addend) sm100::tma_reduce_add_2d(tmC, stage, tc0, row0);
+          else sm100::tma_store_2d(tmC, stage, tc0, row0);
+          sm100::tma_store_commit();
+        }
       }
     }
-    sm100::fence_proxy_async();                              // generic-proxy writes -> visible to the async (TMA) proxy
-    __syncwarp();
-    if (lane == 0) { sm100::tma_store_2d(tmC, stage, col0, row0); sm100::tma_store_commit(); }
   }
 }
 

@@ -29,7 +29,7 @@ __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& mb
 }
 
 template <bool A_MN, bool B_MN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(200)     // 320 threads x 200 registers = 64000 of the 65536 per SM
 gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmC, const GemmEpi epi, const int M, const int N, const int K) {
   constexpr uint32_t TMEM_COLS = 512;       // 2 accumulator stages x 256 columns
@@ -129,7 +129,7 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + half * 128;
       if (epi.tma_store)
-        gemm_epi::epilogue_rows_tma<2>(epi, &tmC, sStage + (warp - 2) * 4096, taddr, row - lane, n0, N, lane);
+        gemm_epi::epilogue_rows_tma<4>(epi, &tmC, sStage + (warp - 2) * 4096, taddr, row, row < M, n0, N, lane);
       else
         gemm_epi::epilogue_rows<4>(epi, taddr, row, row < M, n0, N);
       tc_fence_before();
@@ -180,13 +180,21 @@ int mb200_gemm_2cta_impl(const void* A, const void* B, void* C, const void* bias
   epi.C = C; epi.ldc = ldc; epi.bias = (const bf16*)bias; epi.addend = addend; epi.ld_add = ld_add; epi.act = act;
   epi.c_f32 = c_f32; epi.mode = 0; epi.aux0 = nullptr; epi.aux1 = nullptr; epi.ld_aux = 0; epi.C2 = nullptr; epi.ldc2 = 0;
   if (swiglu) { epi.mode = swiglu->mode; epi.aux0 = swiglu->aux0; epi.aux1 = swiglu->aux1; epi.ld_aux = swiglu->ld_aux; epi.C2 = swiglu->C2; epi.ldc2 = swiglu->ldc2; }
-  // TMA-store epilogue for the plain bf16 output (forward projections, first dgrad of a group, LM-head chunks)
+  // TMA epilogue (store, or reduce-add for the fp32 gradient accumulation) whenever the alignment rules allow it; the SwiGLU
+  // modes (two outputs) and odd alignments keep the per-thread stores
   static const int tma_store_on = [] { const char* e = getenv("MB200_GEMM_TMA_STORE"); return (e && e[0] == '0') ? 0 : 1; }();
   CUtensorMap tmC = tmA;
   epi.tma_store = 0;
-  if (tma_store_on && !c_f32 && !swiglu && !addend && !(ldc & 7) && !(reinterpret_cast<uintptr_t>(C) & 15)) {
-    if ((rc = mbtmap::make_2d_store(&tmC, C, M, N, ldc, 64, 32))) return rc;
-    epi.tma_store = 1;
+  if (tma_store_on && !swiglu && !(reinterpret_cast<uintptr_t>(C) & 15)) {
+    if (c_f32) {
+      if (!(ldc & 3) && (!addend || addend == C)) {
+        if ((rc = mbtmap::make_2d_store(&tmC, C, M, N, ldc, 32, 32, true))) return rc;
+        epi.tma_store = 1;
+      }
+    } else if (!(ldc & 7) && (!addend || (!(ld_add & 7) && !(reinterpret_cast<uintptr_t>(addend) & 15)))) {
+      if ((rc = mbtmap::make_2d_store(&tmC, C, M, N, ldc, 64, 32))) return rc;
+      epi.tma_store = 1;
+    }
   }
   cudaStream_t st = (cudaStream_t)stream;
   const bool a_mn = transA != 0, b_mn = transB == 0;

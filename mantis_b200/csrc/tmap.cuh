@@ -40,10 +40,20 @@ static inline int make_2d(CUtensorMap* tm, const void* base, long long rows, lon
   return 0;
 }
 
-// 2-D bf16 map used as a TMA-STORE destination (no L2 promotion hint needed for stores)
+// 2-D map used as a TMA-STORE / TMA-REDUCE destination: bf16 (box_cols x box_rows elements) or fp32
 static inline int make_2d_store(CUtensorMap* tm, void* base, long long rows, long long cols, long long ld, int box_cols,
-                                int box_rows) {
-  return make_2d(tm, base, rows, cols, ld, box_cols, box_rows);
+                                int box_rows, bool f32 = false) {
+  if (!f32) return make_2d(tm, base, rows, cols, ld, box_cols, box_rows);
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { mb200_set_last_error("cuTensorMapEncodeTiled unavailable"); return -ENOSYS; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { mb200_set_last_error("cuTensorMapEncodeTiled (fp32 store) failed"); return -EINVAL; }
+  return 0;
 }
 
 // 4-D bf16 map over x[B, S, H, hd] (element strides sb, ss, sh; hd contiguous): dims (hd, H, S, B), box (64, 1, rows, 1)
