@@ -32,7 +32,7 @@ __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int gro
 }
 
 template <bool A_MN, bool B_MN>
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(192)     // 10 warps x (192 x 32 = 12 x 512-register allocation units) = 61440 of the 65536 per SM
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmC, const GemmEpi epi, const int M, const int N, const int K,
                        const int group_m) {
