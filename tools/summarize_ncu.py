@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: per-kernel-family totals and shares for the LAST
-optimizer step in the file (steps are delimited by the runs of adamw_kernel launches)."""
+optimizer step in the file (a step ends with its adamw launch; with fewer than two of them in the capture the whole file --
+model construction included -- is summarised, so capture at least `--warmup 1 --steps 1` completely)."""
 import csv
 import re
 import sys
