@@ -785,21 +785,50 @@ def attention_bwd(q, k, v, o, do, lse, causal, kmask, scale, kbits=None, fast=Fa
     return dq, dk, dv
 
 
+ATTN_PAD_HEAD_DIM = os.environ.get("MB200_ATTN_PAD_HD", "1") == "1"
+attn_padded_calls = 0       # attention calls that took the zero-padded tensor-core route (tests read it)
+
+
+def _pad_hd_ok(q, k, v, Sq):
+    """head_dim 72 (SigLIP), 96 (Idefics2 perceiver), ... fit no tcgen05 tile; zero-padding the head dimension of q, k, v to 128
+    changes neither q.k nor p.v, so the hd-128 tensor-core kernels can serve them (the padded lanes cost 25-44 % extra MMA work,
+    still far ahead of the SIMT kernel).  The frozen ViT does this once at the WEIGHT level (models/vision.py); this is the
+    activation-level version for everything that trains."""
+    hd = q.shape[-1]
+    return (ATTN_PAD_HEAD_DIM and not FORCE_GENERIC and q.is_cuda and q.dtype == torch.bfloat16 and 32 <= hd < 128 and hd % 8 == 0
+            and Sq >= FAST_ATTN_MIN_SQ and k.shape[-1] == hd and v.shape[-1] == hd)
+
+
+def _pad_hd(x):
+    return torch.nn.functional.pad(x, (0, 128 - x.shape[-1]))
+
+
 class _AttentionFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, causal, kmask, scale, window):
+        global attn_padded_calls
         if kmask is not None:
             kmask = kmask.contiguous().to(torch.int64)
+        hd = q.shape[-1]
+        pad = _pad_hd_ok(q, k, v, q.shape[1]) and _window_code(causal, window, k.shape[1]) <= 1
+        if pad:
+            q, k, v = _pad_hd(q), _pad_hd(k), _pad_hd(v)
+            attn_padded_calls += 1
         o, lse, kbits, fast = attention_fwd(q, k, v, causal, kmask, scale, return_kbits=True, window=window)
         ctx.save_for_backward(q, k, v, o, lse, kmask, kbits)
         ctx.causal, ctx.scale, ctx.fast, ctx.window = causal, scale, fast, window
-        return o
+        ctx.hd = hd if pad else None
+        return o[..., :hd].contiguous() if pad else o
 
     @staticmethod
     def backward(ctx, do):
         q, k, v, o, lse, kmask, kbits = ctx.saved_tensors
+        if ctx.hd is not None:
+            do = _pad_hd(do)
         dq, dk, dv = attention_bwd(q, k, v, o, do, lse, ctx.causal, kmask, ctx.scale, kbits=kbits, fast=ctx.fast,
                                    window=ctx.window)
+        if ctx.hd is not None:
+            dq, dk, dv = dq[..., :ctx.hd], dk[..., :ctx.hd], dv[..., :ctx.hd]
         return dq, dk, dv, None, None, None, None
 
 

@@ -787,3 +787,37 @@ def test_fused_swiglu_mlp_matches_the_unfused_kernels(ops, cuda, M, D, I, with_r
     yr = (torch.nn.functional.silu(xf @ gf.t()) * (xf @ uf.t())) @ df.t() + (res.float() if with_res else 0)
     yr.backward(gy.float())
     assert _rel(a[0], yr) < 1e-2 and _rel(a[1], xf.grad) < 2e-2 and _rel(a[2], gf.grad) < 2e-2 and _rel(a[4], df.grad) < 2e-2
+
+
+@pytest.mark.parametrize("hd,H,Hkv,Sq,Sk,causal", [(96, 16, 4, 64, 793, False), (72, 16, 16, 729, 729, False), (96, 8, 2, 300, 300, True)])
+def test_attention_odd_head_dims_run_on_the_tensor_cores(ops, cuda, hd, H, Hkv, Sq, Sk, causal):
+    """head_dim 96 (Idefics2 perceiver, ref modeling_idefics2.py:812-910) and 72 (trainable SigLIP blocks) are zero-padded to 128
+    and served by the tcgen05 kernels, forward and backward; result vs fp32 math and vs the SIMT kernel"""
+    import mantis_b200.ops as om
+    torch.manual_seed(70)
+    B = 2
+    q = torch.randn(B, Sq, H, hd, device=cuda).bfloat16().requires_grad_(True)
+    k = torch.randn(B, Sk, Hkv, hd, device=cuda).bfloat16().requires_grad_(True)
+    v = torch.randn(B, Sk, Hkv, hd, device=cuda).bfloat16().requires_grad_(True)
+    kmask = torch.ones(B, Sk, dtype=torch.int64, device=cuda)
+    if not causal:
+        kmask[1, Sk - 9:] = 0
+    scale = hd ** -0.5
+    before = om.attn_padded_calls
+    o = ops.attention(q, k, v, causal=causal, kmask=kmask, scale=scale)
+    assert om.attn_padded_calls == before + 1 and o.shape == (B, Sq, H, hd)
+    go = torch.randn_like(o)
+    o.backward(go)
+    qr, kr, vr = [t.detach().float().requires_grad_(True) for t in (q, k, v)]
+    ref = _attn_ref(qr, kr, vr, causal, kmask, scale)
+    ref.backward(go.float())
+    assert _rel(o, ref) < 1e-2
+    assert _rel(q.grad, qr.grad) < 1.5e-2 and _rel(k.grad, kr.grad) < 1.5e-2 and _rel(v.grad, vr.grad) < 1.5e-2
+    old = om.ATTN_PAD_HEAD_DIM; om.ATTN_PAD_HEAD_DIM = False
+    try:
+        q2, k2, v2 = [t.detach().clone().requires_grad_(True) for t in (q, k, v)]
+        o2 = ops.attention(q2, k2, v2, causal=causal, kmask=kmask, scale=scale)
+        o2.backward(go)
+    finally:
+        om.ATTN_PAD_HEAD_DIM = old
+    assert _rel(o, o2) < 1e-2 and _rel(q.grad, q2.grad) < 1.5e-2
