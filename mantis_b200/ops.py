@@ -916,12 +916,23 @@ def _merge_ws(B, T, device):
 
 
 _deferred_checks = []       # (pinned host flag, event that marks its arrival, message)
+_flag_pool = None           # pinned ring of host flags (one cudaHostAlloc, not one per check)
+_flag_next = 0
+_FLAG_SLOTS = 512
 
 
 def _defer_check(flag_dev, msg):
     """queue a device-side boolean for a later host-side check WITHOUT synchronising: the flag travels to pinned host memory
     on the current stream and is looked at once its event has completed"""
-    host = torch.empty((1,), dtype=torch.bool).pin_memory()
+    global _flag_pool, _flag_next
+    if _flag_pool is None:
+        _flag_pool = torch.empty((_FLAG_SLOTS,), dtype=torch.bool).pin_memory()
+    if len(_deferred_checks) >= _FLAG_SLOTS // 2:
+        check_deferred(block=False)                       # inference loops never call check_deferred: keep the queue short
+        if len(_deferred_checks) >= _FLAG_SLOTS - 1:
+            check_deferred(block=True)
+    host = _flag_pool[_flag_next:_flag_next + 1]
+    _flag_next = (_flag_next + 1) % _FLAG_SLOTS
     host.copy_(flag_dev.reshape(1), non_blocking=True)
     ev = torch.cuda.Event()
     ev.record()
@@ -1091,6 +1102,9 @@ class _LMHeadCEFn(torch.autograd.Function):
         lab = eff_labels.reshape(-1)
         dev = h2.device
         need_h, need_w = hidden.requires_grad, weight.requires_grad
+        # torch's cross_entropy raises on a target >= the number of classes; the kernels cannot raise, so the check is queued for
+        # the caller's next synchronisation point (ops.check_deferred) instead of silently treating such rows as ignored
+        _defer_check((lab < V).all(), f"cross-entropy target out of range: a label is >= the vocabulary size ({V})")
         idx = None
         if LM_HEAD_SKIP_IGNORED:
             if valid_rows_hint is not None:
@@ -1170,6 +1184,7 @@ class _CEFn(torch.autograd.Function):
         n, V = logits2.shape
         assert logits2.stride(1) == 1
         dev = logits2.device
+        _defer_check((lab < V).all(), f"cross-entropy target out of range: a label is >= the number of classes ({V})")
         loss_rows = torch.empty((n,), dtype=torch.float32, device=dev)
         acc = torch.zeros((2,), dtype=torch.float32, device=dev)
         dl = torch.empty((n, V), dtype=logits2.dtype, device=dev) if logits2.requires_grad else None

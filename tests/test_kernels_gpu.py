@@ -821,3 +821,18 @@ def test_attention_odd_head_dims_run_on_the_tensor_cores(ops, cuda, hd, H, Hkv, 
     finally:
         om.ATTN_PAD_HEAD_DIM = old
     assert _rel(o, o2) < 1e-2 and _rel(q.grad, q2.grad) < 1.5e-2
+
+
+def test_cross_entropy_out_of_range_label_is_reported(ops, cuda):
+    """torch raises on a target >= the number of classes; our kernels queue the check and ops.check_deferred() raises"""
+    torch.manual_seed(80)
+    logits = torch.randn(16, 50, device=cuda, requires_grad=True)
+    lab = torch.randint(0, 50, (16,), device=cuda); lab[3] = 50
+    ops.check_deferred()
+    loss = ops.cross_entropy(logits, lab, torch.tensor([15.0], device=cuda))
+    assert torch.isfinite(loss)
+    with pytest.raises(ValueError, match="out of range"):
+        ops.check_deferred()
+    lab[3] = -100
+    ops.cross_entropy(logits, lab, torch.tensor([15.0], device=cuda))
+    ops.check_deferred()
