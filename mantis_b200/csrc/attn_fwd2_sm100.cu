@@ -188,7 +188,13 @@ attn_fwd2_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       float mx = sv[0];
 #pragma unroll
       for (int i = 1; i < 128; ++i) mx = fmaxf(mx, sv[i]);
-      const float m_new = fmaxf(m, mx * p.scale_log2);
+      // Lazy rescaling: the running maximum only moves when the tile's maximum exceeds it by more than 2^8 (or on a row's first
+      // live tile).  Until then P is formed against the stale maximum (values up to 256: exact in fp32 sums, same relative
+      // precision in bf16) and O needs no correction -- so the 64 KB read-modify-write of O through the 64 B/clk TMEM port,
+      // which with an exact running maximum happens in almost every iteration (some row of the warp always moves), becomes rare.
+      // l, O and lse stay consistent because they are all expressed relative to the same m.
+      const float m_cand = fmaxf(m, mx * p.scale_log2);
+      const float m_new = (m == -INFINITY || m_cand - m > 8.f) ? m_cand : m;
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
       const float alpha = (m == -INFINITY) ? 0.f : fast_exp2(m - m_use);
       float rs = 0.f;
