@@ -206,6 +206,14 @@ int mb200_attn_bwd_bf16(const void* q, const void* k, const void* v, const void*
                         float* delta, void* dq, void* dk, void* dv, int B, int H, int Hkv, int Sq, int Sk, int hd,
                         const long long* strides, float scale, int causal, const int64_t* kmask, long long kmask_sb,
                         const void* kbits, void* stream);
+/* Single-pass backward for self-attention (Sq == Sk): the dK/dV kernel writes dS^T (bf16) once into ds_ws
+ * (mb200_attn_bwd_ds_bytes(B, H, Sq) bytes) and dQ = scale * dS K is a tensor-core GEMM over it -- S and dP are computed and
+ * read back from tensor memory once instead of once per kernel.  ds_ws == NULL or Sq != Sk: same as mb200_attn_bwd_bf16. */
+long long mb200_attn_bwd_ds_bytes(int B, int H, int Sq);
+int mb200_attn_bwd_bf16_sp(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
+                           float* delta, void* dq, void* dk, void* dv, int B, int H, int Hkv, int Sq, int Sk, int hd,
+                           const long long* strides, float scale, int causal, const int64_t* kmask, long long kmask_sb,
+                           const void* kbits, void* ds_ws, void* stream);
 
 /* ---- decode-time kernels of generate() (q_len 1): skinny GEMM (M <= 16 rows, every weight byte read once), KV-cache
  *      append, split-KV attention + combine (hf: llama/modeling_llama.py:269-270; ref modeling_llava.py:477-519) ---- */

@@ -44,6 +44,10 @@ struct BwdParams {
   int B, H, Hkv, Sq, Sk;
   float scale, scale_log2;
   int causal;
+  // single-pass mode: the dK/dV kernel also writes dS^T (bf16) for every (key, query) pair it visits into
+  // ds_t[B*H][Sk_pad][Sq_pad]; the dQ kernel then is a plain GEMM over that buffer (S and dP are computed, and read back from
+  // TMEM, ONCE instead of once per kernel)
+  bf16* ds_t; long long ds_row, ds_head;      // element strides: key row, (batch, head) slab
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -243,6 +247,14 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __gri
         // packed columns [16c, 16c+16) lie inside the fp32 columns this thread has already consumed (lane-private)
         tmem_st_32x32b_x16(tST[s] + lane_off + c * 16, pk);
         tmem_st_32x32b_x16(tDPT[s] + lane_off + c * 16, dk_);
+        if (p.ds_t) {
+          // this key row's dS for 32 queries = 64 contiguous bytes of dS^T; rows / columns beyond Sk / Sq hold exact zeros
+          // (masked above), so the dQ GEMM can read whole padded tiles
+          bf16* dsp = p.ds_t + (size_t)(b * p.H + (hk * G + n / per_head)) * p.ds_head + (size_t)kj * p.ds_row + q0;
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4*>(dsp + g * 8) = make_uint4(dk_[g * 4], dk_[g * 4 + 1], dk_[g * 4 + 2], dk_[g * 4 + 3]);
+        }
       }
       tmem_st_wait();
       tc_fence_before();
@@ -458,6 +470,98 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+// ============================================================================================ dQ from dS^T (single-pass mode)
+// dQ[128 queries x 128] = scale * sum over key sub-tiles of dS[128 q x 64 k] . K[64 k x 128]: a GEMM whose A operand is the
+// dS^T buffer the dK/dV kernel wrote ([keys][queries] => MN-major A, fetched by TMA as two 64-query x 64-key boxes) and whose B
+// operand is the K sub-tile ([keys][hd] => MN-major B).  No S, no dP, no softmax warps, no TMEM reads besides the epilogue.
+constexpr int DQ2_STAGES = 6;
+constexpr int DQ2_THREADS = 64 + 128;
+
+__global__ void __launch_bounds__(DQ2_THREADS, 1)
+attn_bwd_dq2_sm100_kernel(const __grid_constant__ CUtensorMap tmDS, const __grid_constant__ CUtensorMap tmK64, const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                               // DQ2_STAGES x 16 KB: dS^T  [2 x 64 queries][64 keys][128 B]
+  uint8_t* sB = sA + DQ2_STAGES * SUB_TILE;         // DQ2_STAGES x 16 KB: K     [2 x 64 dims   ][64 keys][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + DQ2_STAGES * SUB_TILE);
+  uint64_t* full = bars;                            // [DQ2_STAGES]
+  uint64_t* empty = full + DQ2_STAGES;              // [DQ2_STAGES]
+  uint64_t* acc_done = empty + DQ2_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const mb::LptIdx li = mb::lpt_index();            // heavy (late) query tiles first, across all heads
+  const int qt = (int)gridDim.x - 1 - li.rank;
+  const int h = li.h, b = li.b;
+  const int hk = h / (p.H / p.Hkv);
+  const int q0 = qt * 128;
+  int kv_end = p.Sk;
+  if (p.causal) kv_end = min(p.Sk, q0 + 128);       // single-pass mode is only used for Sq == Sk
+  const int n_it = (kv_end + 63) / 64;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmDS); prefetch_tmap(&tmK64);
+    for (int s = 0; s < DQ2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tDQ = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int bh = b * p.H + h;
+      for (int n = 0; n < n_it; ++n) {
+        const int s = n % DQ2_STAGES; const uint32_t ph = (n / DQ2_STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full[s], 2 * SUB_TILE);
+        tma_load_3d(sA + s * SUB_TILE, &tmDS, &full[s], q0, n * 64, bh);                  // queries q0 .. q0+63
+        tma_load_3d(sA + s * SUB_TILE + SUB_HALF, &tmDS, &full[s], q0 + 64, n * 64, bh);  // queries q0+64 .. q0+127
+        tma_load_4d(sB + s * SUB_TILE, &tmK64, &full[s], 0, hk, n * 64, b);
+        tma_load_4d(sB + s * SUB_TILE + SUB_HALF, &tmK64, &full[s], 64, hk, n * 64, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_it > 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 128, true, true);
+      for (int n = 0; n < n_it; ++n) {
+        const int s = n % DQ2_STAGES; const uint32_t ph = (n / DQ2_STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(sA + s * SUB_TILE), b_addr = smem_u32(sB + s * SUB_TILE);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)     // 16 keys per step: 16 k-rows x 128 B = 2048 B further into both tiles
+          umma_bf16_ss(tDQ, make_smem_desc(a_addr + kk * 2048, SUB_HALF, 1024), make_smem_desc(b_addr + kk * 2048, SUB_HALF, 1024),
+                       idesc, (n | kk) != 0);
+        umma_commit(&empty[s]);
+      }
+      umma_commit(acc_done);
+    }
+  } else {
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;
+    const int qi = q0 + r;
+    const bool row_ok = qi < p.Sq;
+    const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+    bf16* dqp = p.dq + (size_t)b * p.dq_sb + (size_t)(row_ok ? qi : 0) * p.dq_ss + (size_t)h * p.dq_sh;
+    if (n_it > 0) {
+      mbar_wait(acc_done, 0);
+      tc_fence_after();
+      store_acc_row(tDQ + lane_off, dqp, row_ok, p.scale);
+    } else if (row_ok) {
+      const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) *reinterpret_cast<uint4*>(dqp + c * 8) = z;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tDQ, 128); }
+}
+
 // ld[b,h,q] = {lse * log2(e) (+inf if the row is dead or q >= Sq), sum_d dO * O}   (one warp per row of 128, rows padded to Sq_pad)
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, const float* __restrict__ lse,
@@ -492,10 +596,16 @@ extern "C" {
 // delta: fp32 scratch of 2 * B * H * mb200_attn_bwd_sq_pad(Sq) floats (written here: {lse*log2e, rowsum(dO*O)} pairs).
 long long mb200_attn_bwd_sq_pad(int Sq) { return (long long)((Sq + 127) / 128) * 128; }
 
-int mb200_attn_bwd_bf16(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
+// bytes of the dS^T workspace of the single-pass backward (mb200_attn_bwd_bf16_sp): [B*H][Sq_pad][Sq_pad] bf16
+long long mb200_attn_bwd_ds_bytes(int B, int H, int Sq) {
+  const long long Sp = mb200_attn_bwd_sq_pad(Sq);
+  return 2LL * B * H * Sp * Sp;
+}
+
+static int attn_bwd_impl(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
                         float* delta, void* dq, void* dk, void* dv, int B, int H, int Hkv, int Sq, int Sk, int hd,
                         const long long* strides, float scale, int causal, const int64_t* kmask, long long kmask_sb,
-                        const void* kbits, void* stream) {
+                        const void* kbits, void* ds_ws, void* stream) {
   if (B <= 0 || Sq <= 0) return MB200_OK;
   if (hd != HD || H % Hkv != 0 || Sk <= 0) return -ENOTSUP;
   for (int i = 0; i < 12; ++i) if (strides[i] & 7) return -ENOTSUP;
@@ -529,15 +639,44 @@ int mb200_attn_bwd_bf16(const void* q, const void* k, const void* v, const void*
   p.B = B; p.H = H; p.Hkv = Hkv; p.Sq = Sq; p.Sk = Sk; p.scale = scale; p.scale_log2 = scale * LOG2E; p.causal = causal;
   constexpr int smem_dkv = 2 * FULL_TILE + 2 * QS * SUB_TILE + 1024 + 256 + QS * 512;
   constexpr int smem_dq = 2 * FULL_TILE + 2 * QSQ * SUB_TILE + 1024 + 256;
+  constexpr int smem_dq2 = 2 * DQ2_STAGES * SUB_TILE + 1024 + 256;
   static const bool cfg_ok =        // thread-safe one-time setup
       cudaFuncSetAttribute(attn_bwd_dkv_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dkv) == cudaSuccess &&
-      cudaFuncSetAttribute(attn_bwd_dq_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq) == cudaSuccess;
+      cudaFuncSetAttribute(attn_bwd_dq_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq) == cudaSuccess &&
+      cudaFuncSetAttribute(attn_bwd_dq2_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq2) == cudaSuccess;
   if (!cfg_ok) { mb200_set_last_error("cudaFuncSetAttribute(attn bwd smem) failed"); return -EIO; }
   dim3 gkv((Sk + 127) / 128, Hkv, B), gq((Sq + 127) / 128, H, B);
+  p.ds_t = nullptr; p.ds_row = 0; p.ds_head = 0;
+  const bool single_pass = ds_ws != nullptr && Sq == Sk;
+  CUtensorMap tmDS;
+  if (single_pass) {
+    const long long Sp = mb200_attn_bwd_sq_pad(Sq);                  // rows (keys) and columns (queries) padded to 128
+    p.ds_t = (bf16*)ds_ws; p.ds_row = Sp; p.ds_head = Sp * Sp;
+    if ((rc = mbtmap::make_3d(&tmDS, ds_ws, (long long)B * H, Sp, Sp, 64, 64))) return rc;
+  }
   attn_bwd_dkv_sm100_kernel<<<gkv, NTHREADS, smem_dkv, st>>>(tmQ64, tmDO64, tmK, tmV, p);
-  attn_bwd_dq_sm100_kernel<<<gq, DQ_THREADS, smem_dq, st>>>(tmQ, tmDO, tmK64, tmV64, p);
+  if (single_pass) attn_bwd_dq2_sm100_kernel<<<gq, DQ2_THREADS, smem_dq2, st>>>(tmDS, tmK64, p);
+  else             attn_bwd_dq_sm100_kernel<<<gq, DQ_THREADS, smem_dq, st>>>(tmQ, tmDO, tmK64, tmV64, p);
   MB200_CHECK_LAUNCH();
   return MB200_OK;
+}
+
+int mb200_attn_bwd_bf16(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
+                        float* delta, void* dq, void* dk, void* dv, int B, int H, int Hkv, int Sq, int Sk, int hd,
+                        const long long* strides, float scale, int causal, const int64_t* kmask, long long kmask_sb,
+                        const void* kbits, void* stream) {
+  return attn_bwd_impl(q, k, v, o, dout, lse, delta, dq, dk, dv, B, H, Hkv, Sq, Sk, hd, strides, scale, causal, kmask, kmask_sb,
+                       kbits, nullptr, stream);
+}
+// Single-pass variant (self-attention, Sq == Sk): ds_ws = mb200_attn_bwd_ds_bytes(B, H, Sq) bytes of scratch.  The dK/dV kernel
+// writes dS^T there once and dQ = scale * dS K is a tensor-core GEMM over it; with ds_ws == NULL or Sq != Sk it is the
+// two-kernel recompute form above.
+int mb200_attn_bwd_bf16_sp(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
+                           float* delta, void* dq, void* dk, void* dv, int B, int H, int Hkv, int Sq, int Sk, int hd,
+                           const long long* strides, float scale, int causal, const int64_t* kmask, long long kmask_sb,
+                           const void* kbits, void* ds_ws, void* stream) {
+  return attn_bwd_impl(q, k, v, o, dout, lse, delta, dq, dk, dv, B, H, Hkv, Sq, Sk, hd, strides, scale, causal, kmask, kmask_sb,
+                       kbits, ds_ws, stream);
 }
 
 }  // extern "C"

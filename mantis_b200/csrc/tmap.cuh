@@ -56,6 +56,22 @@ static inline int make_2d_store(CUtensorMap* tm, void* base, long long rows, lon
   return 0;
 }
 
+// 3-D bf16 map over x[slabs][rows][cols] (cols contiguous, dense): box (box_cols, box_rows, 1), 128B swizzle
+static inline int make_3d(CUtensorMap* tm, const void* base, long long slabs, long long rows, long long cols, int box_cols,
+                          int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { mb200_set_last_error("cuTensorMapEncodeTiled unavailable"); return -ENOSYS; }
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)slabs};
+  cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)cols * rows * 2};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { mb200_set_last_error("cuTensorMapEncodeTiled (3-D) failed"); return -EINVAL; }
+  return 0;
+}
+
 // 4-D bf16 map over x[B, S, H, hd] (element strides sb, ss, sh; hd contiguous): dims (hd, H, S, B), box (64, 1, rows, 1)
 static inline int make_bshd(CUtensorMap* tm, const void* base, int B, int S, int H, int hd, long long sb, long long ss,
                             long long sh, int box_rows) {

@@ -752,6 +752,26 @@ def decode_attention_paged(q, cache, layer_idx, ctx, kmask, scale, kbits=None):
     return o
 
 
+ATTN_BWD_SINGLE_PASS = os.environ.get("MB200_ATTN_BWD_SINGLE_PASS", "1") == "1"
+ATTN_BWD_WS_MAX = int(os.environ.get("MB200_ATTN_BWD_WS_MAX_GB", "12")) << 30
+_attn_bwd_ws_cache = {}
+
+
+def _attn_bwd_ws(B, H, Sq, device):
+    """dS^T scratch of the single-pass attention backward ([B*H][Sq_pad][Sq_pad] bf16: 4 GB for one config-2 sample), kept and
+    re-used across calls (grow-only, per device and stream); None when it would exceed MB200_ATTN_BWD_WS_MAX_GB."""
+    need = int(_L().mb200_attn_bwd_ds_bytes(B, H, Sq))
+    if need > ATTN_BWD_WS_MAX:
+        return None
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+    ws = _attn_bwd_ws_cache.get(key)
+    if ws is None or ws.numel() < need:
+        _attn_bwd_ws_cache[key] = None
+        ws = torch.empty((need,), dtype=torch.uint8, device=device)
+        _attn_bwd_ws_cache[key] = ws
+    return ws
+
+
 def attention_bwd(q, k, v, o, do, lse, causal, kmask, scale, kbits=None, fast=False, out=None, window=None):
     """`out`: optional (dq, dk, dv) contiguous destinations (slices of packed gradients, see attention_varlen)."""
     B, Sq, H, hd = q.shape
@@ -768,9 +788,10 @@ def attention_bwd(q, k, v, o, do, lse, causal, kmask, scale, kbits=None, fast=Fa
             dv = torch.empty((B, Sk, Hkv, hd), dtype=q.dtype, device=q.device)
         delta = torch.empty((2 * B * H * _L().mb200_attn_bwd_sq_pad(Sq),), dtype=torch.float32, device=q.device)
         st = _strides12(q, k, v, o)
-        _call("mb200_attn_bwd_bf16", _p(q), _p(k), _p(v), _p(o), _p(do), _p(lse), _p(delta), _p(dq), _p(dk), _p(dv),
+        ws = _attn_bwd_ws(B, H, Sq, q.device) if (ATTN_BWD_SINGLE_PASS and Sq == Sk) else None
+        _call("mb200_attn_bwd_bf16_sp", _p(q), _p(k), _p(v), _p(o), _p(do), _p(lse), _p(delta), _p(dq), _p(dk), _p(dv),
               B, H, Hkv, Sq, Sk, hd, st, float(scale), int(causal), _p(kmask), Sk if kmask is not None else 0,
-              _p(kbits), _st())
+              _p(kbits), _p(ws), _st())
         return dq, dk, dv
     qc, kc, vc = q.contiguous(), k.contiguous(), v.contiguous()
     dq = torch.empty_like(qc); dk = torch.empty_like(kc); dv = torch.empty_like(vc)
