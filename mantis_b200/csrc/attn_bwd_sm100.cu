@@ -90,7 +90,7 @@ __device__ __forceinline__ void store_acc_row(uint32_t taddr, bf16* dst, bool ok
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant__ CUtensorMap tmDO64,
                           const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                          const BwdParams p) {
+                          const __grid_constant__ CUtensorMap tmDSst, const BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;                           // 32 KB resident
@@ -99,6 +99,9 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __gri
   uint8_t* sDO = sQ + QS * SUB_TILE;            // QS stages x 16 KB
   float2* sLD = reinterpret_cast<float2*>(sDO + QS * SUB_TILE);   // [QS][64] {lse2, delta}
   uint64_t* bars = reinterpret_cast<uint64_t*>(sLD + QS * 64);
+  // single-pass mode: one 4 KB staging tile per softmax warp ([32 key rows][64 queries] bf16, 128B-swizzled) for the TMA
+  // store of dS^T; placed after the barrier block on the next 1 KB boundary
+  uint8_t* sDS = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bars) + 256 + 1023) & ~uintptr_t(1023));
   uint64_t* kv_full = bars + 0;
   uint64_t* qdo_full = bars + 1;    // [QS]
   uint64_t* qdo_empty = bars + 4;   // [QS]
@@ -248,12 +251,25 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __gri
         tmem_st_32x32b_x16(tST[s] + lane_off + c * 16, pk);
         tmem_st_32x32b_x16(tDPT[s] + lane_off + c * 16, dk_);
         if (p.ds_t) {
-          // this key row's dS for 32 queries = 64 contiguous bytes of dS^T; rows / columns beyond Sk / Sq hold exact zeros
-          // (masked above), so the dQ GEMM can read whole padded tiles
-          bf16* dsp = p.ds_t + (size_t)(b * p.H + (hk * G + n / per_head)) * p.ds_head + (size_t)kj * p.ds_row + q0;
+          // this key row's dS for 32 queries = 64 bytes of its row in the warp's staging tile (chunk j of row r at
+          // r * 128 + ((j ^ (r & 7)) << 4): conflict-free); rows / columns beyond Sk / Sq hold exact zeros (masked above)
+          uint8_t* stg = sDS + (warp - 2) * 4096 + lane * 128;
+          if (c == 0) {
+            if (lane == 0) tma_store_wait_read0();         // the previous sub-tile's store has finished reading the tile
+            __syncwarp();
+          }
 #pragma unroll
           for (int g = 0; g < 4; ++g)
-            *reinterpret_cast<uint4*>(dsp + g * 8) = make_uint4(dk_[g * 4], dk_[g * 4 + 1], dk_[g * 4 + 2], dk_[g * 4 + 3]);
+            *reinterpret_cast<uint4*>(stg + (((c * 4 + g) ^ (lane & 7)) << 4)) =
+                make_uint4(dk_[g * 4], dk_[g * 4 + 1], dk_[g * 4 + 2], dk_[g * 4 + 3]);
+        }
+      }
+      if (p.ds_t) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {                                     // 32 key rows x 64 queries of dS^T, written by the TMA unit
+          tma_store_3d(&tmDSst, sDS + (warp - 2) * 4096, qs * 64, k0 + qd * 32, b * p.H + hk * G + n / per_head);
+          tma_store_commit();
         }
       }
       tmem_st_wait();
@@ -276,6 +292,7 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmQ64, const __gri
       for (int c = 0; c < 16; ++c) *reinterpret_cast<uint4*>(dst + c * 8) = z;
     }
   }
+  if (p.ds_t && warp >= 2 && lane == 0) tma_store_wait_all0();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem_base, 512); }
@@ -637,7 +654,7 @@ static int attn_bwd_impl(const void* q, const void* k, const void* v, const void
   p.dv = (bf16*)dv; p.dv_sb = dk_sb; p.dv_ss = dk_ss; p.dv_sh = hd;
   p.kbits = kmask ? (const uint32_t*)kbits : nullptr; p.kbits_stride = (Sk + 31) / 32;
   p.B = B; p.H = H; p.Hkv = Hkv; p.Sq = Sq; p.Sk = Sk; p.scale = scale; p.scale_log2 = scale * LOG2E; p.causal = causal;
-  constexpr int smem_dkv = 2 * FULL_TILE + 2 * QS * SUB_TILE + 1024 + 256 + QS * 512;
+  constexpr int smem_dkv = 2 * FULL_TILE + 2 * QS * SUB_TILE + 1024 + 256 + QS * 512 + 1024 + 8 * 4096;
   constexpr int smem_dq = 2 * FULL_TILE + 2 * QSQ * SUB_TILE + 1024 + 256;
   constexpr int smem_dq2 = 2 * DQ2_STAGES * SUB_TILE + 1024 + 256;
   static const bool cfg_ok =        // thread-safe one-time setup
@@ -648,13 +665,14 @@ static int attn_bwd_impl(const void* q, const void* k, const void* v, const void
   dim3 gkv((Sk + 127) / 128, Hkv, B), gq((Sq + 127) / 128, H, B);
   p.ds_t = nullptr; p.ds_row = 0; p.ds_head = 0;
   const bool single_pass = ds_ws != nullptr && Sq == Sk;
-  CUtensorMap tmDS;
+  CUtensorMap tmDS, tmDSst = tmK;
   if (single_pass) {
     const long long Sp = mb200_attn_bwd_sq_pad(Sq);                  // rows (keys) and columns (queries) padded to 128
     p.ds_t = (bf16*)ds_ws; p.ds_row = Sp; p.ds_head = Sp * Sp;
-    if ((rc = mbtmap::make_3d(&tmDS, ds_ws, (long long)B * H, Sp, Sp, 64, 64))) return rc;
+    if ((rc = mbtmap::make_3d(&tmDS, ds_ws, (long long)B * H, Sp, Sp, 64, 64))) return rc;      // dQ kernel: loads
+    if ((rc = mbtmap::make_3d(&tmDSst, ds_ws, (long long)B * H, Sp, Sp, 64, 32))) return rc;    // dK/dV kernel: stores
   }
-  attn_bwd_dkv_sm100_kernel<<<gkv, NTHREADS, smem_dkv, st>>>(tmQ64, tmDO64, tmK, tmV, p);
+  attn_bwd_dkv_sm100_kernel<<<gkv, NTHREADS, smem_dkv, st>>>(tmQ64, tmDO64, tmK, tmV, tmDSst, p);
   if (single_pass) attn_bwd_dq2_sm100_kernel<<<gq, DQ2_THREADS, smem_dq2, st>>>(tmDS, tmK64, p);
   else             attn_bwd_dq_sm100_kernel<<<gq, DQ_THREADS, smem_dq, st>>>(tmQ, tmDO, tmK64, tmV64, p);
   MB200_CHECK_LAUNCH();
