@@ -597,6 +597,10 @@ def run_ours(args):
             gen = {f"bs{bs}": generate_record(torch, ops, model, peaks, bs, args.new_tokens) for bs in (1, 16)}
         except Exception as e:  # noqa
             gen = {"error": f"{type(e).__name__}: {e}"}
+    # the per-kernel rooflines are measured on EVERY rank's own GPU (no collective; rank 0's goes into the line) so that
+    # the N > 1 lines of the scaling run carry them too
+    roof = gemm_roofline(torch, ops, peaks) if (full or world == 1) else None
+    scat = scatter_roofline(torch, ops, peaks) if (full or world == 1) else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -613,8 +617,6 @@ def run_ours(args):
     V_ = 32003 if args.workload == "idefics2" else 128258
     skipped = (samples * S_merged - valid_rows) * 6.0 * V_ * 4096 if ops.LM_HEAD_SKIP_IGNORED else 0.0
     step_tflops = world * per_sample_flop * samples * args.steps / (ms * 1e-3) / 1e12
-    roof = gemm_roofline(torch, ops, peaks) if world == 1 else None
-    scat = scatter_roofline(torch, ops, peaks) if world == 1 else None
     line = {
         "metric": ("training tokens/sec Mantis-8B-SigLIP 8-img/2048-tok" if args.workload == "mllava"
                    else "training tokens/sec Mantis-8B-Idefics2 8-img/2048-tok"), "value": value, "unit": "tokens/s",
