@@ -646,6 +646,7 @@ struct DecP {
   float* part;                                  // [B, H, splits, hd + 2]
   int B, H, Hkv, ctx, splits, chunk; float scale;
   const int64_t* table; int table_stride; long long layer_off, v_off;   // paged cache (table != null): k/v unused
+  int hk_fast;                                  // grid = (Hkv, splits, B) instead of (splits, Hkv, B)
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
@@ -799,20 +800,35 @@ decode_attn_kernel(DecP p) {
 // A operand (their register layouts coincide) and V^T fetched with ldmatrix.trans.  ~220 instructions per 32-key tile instead
 // of ~1700 on the FMA pipe, so a warp spends its time waiting for HBM, not issuing (the SIMT kernel reached 3.3 TB/s at
 // batch 16).  fp32 softmax, P rounded to bf16 before P V like the reference (hf: llama/modeling_llama.py:216-218).
-constexpr int DM_ROWB = DHD * 2 + 16;                       // K and V rows padded to 272 B (conflict-free LDS.32 / ldmatrix)
+constexpr int DM_ROWB = DHD * 2 + 16;                       // K and V rows padded to 272 B (conflict-free ldmatrix)
 constexpr int DM_WARP_SMEM = DKT * DM_ROWB * 2;             // 17408 B per warp
-constexpr int DM_QPITCH = DHD + 8;
-constexpr int DM_SMEM = DWARPS * DM_WARP_SMEM + 8 * DM_QPITCH * 2;
+constexpr int DM_SMEM = DWARPS * DM_WARP_SMEM;
+constexpr int DM_RPITCH = DHD + 4;                          // per-warp partial rows (fp32): 16-byte aligned, m and l behind the dims
 
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* row) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(smem_u32(row)));
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(smem_u32(row)));
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   const bf162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&v);
 }
+__device__ __forceinline__ void cp_async16_s(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16_zs(uint32_t smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
 
+// The first version of this kernel spent 55 % of the SM's issue slots (ncu, bs 16: 2100 instructions per warp per 32-key
+// tile, a quarter of them IMAD address arithmetic of the predicated 16-byte copies) -- an HBM stream cannot hide behind that.
+// Now: a lane's 32 copies per tile walk two fixed strides (one 64-bit add each, no predicates on full tiles), Q fragments
+// come straight from global memory (no staging tile, no barrier), K fragments through ldmatrix.x4 (16 instead of 64 shared
+// loads), full tiles skip the mask arithmetic, and the 4 warps' partials meet in each warp's own (dead) tile with ONE barrier.
 __global__ void __launch_bounds__(DWARPS * 32, 3)
 decode_attn_mma_kernel(DecP p, int G) {
   extern __shared__ __align__(16) unsigned char dsm[];
@@ -820,12 +836,20 @@ decode_attn_mma_kernel(DecP p, int G) {
   const int gid = lane >> 2, tid = lane & 3;
   unsigned char* Kt = dsm + w * DM_WARP_SMEM;
   unsigned char* Vt = Kt + DKT * DM_ROWB;
-  bf16* Qs = reinterpret_cast<bf16*>(dsm + DWARPS * DM_WARP_SMEM);        // [8][DM_QPITCH], rows >= G zero
-  const int sp = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
+  // hk_fast: the 8 kv heads of one token range are neighbours in the launch order, so the 256-byte pieces they read out of
+  // the same [token][head][dim] rows are in flight together (whole 2 KB rows per DRAM page visit instead of one eighth)
+  const int sp = p.hk_fast ? blockIdx.y : blockIdx.x, hk = p.hk_fast ? blockIdx.x : blockIdx.y, b = blockIdx.z;
   const int k_begin = sp * p.chunk, k_end = min(p.ctx, k_begin + p.chunk);
   mb::pdl_trigger();
   const bool has_new = (k_end == p.ctx);
   if (has_new) mb::pdl_wait();
+
+  // lane -> rows (lane >> 4) + 2 i, 16-byte chunk (lane & 15) of every row
+  const int r0 = lane >> 4, c16 = lane & 15;
+  const uint32_t kdst = smem_u32(Kt) + r0 * DM_ROWB + c16 * 16;
+  const uint32_t vdst = kdst + DKT * DM_ROWB;
+  const size_t lane_off = (size_t)r0 * p.kv_ss + c16 * 8;
+  const size_t step2 = 2 * (size_t)p.kv_ss;
 
   auto issue_tile = [&](int k0) {
     const bf16* kt; const bf16* vt;
@@ -838,35 +862,53 @@ decode_attn_mma_kernel(DecP p, int G) {
       vt = p.v + (size_t)b * p.kv_sb + (size_t)k0 * p.kv_ss + (size_t)hk * p.kv_sh;
     }
     const int nk = min(DKT, k_end - k0);
+    const bf16* ks = kt + lane_off;
+    const bf16* vs = vt + lane_off;
+    if (nk == DKT) {
+#pragma unroll
+      for (int i = 0; i < DKT / 2; ++i) cp_async16_s(kdst + i * 2 * DM_ROWB, ks + i * step2);
+      cp_async_commit();
+#pragma unroll
+      for (int i = 0; i < DKT / 2; ++i) cp_async16_s(vdst + i * 2 * DM_ROWB, vs + i * step2);
+      cp_async_commit();
+    } else {                                   // the last tile of the context: rows >= nk are zero-filled
 #pragma unroll 4
-    for (int e = lane; e < DKT * 16; e += 32) {
-      const int j = e >> 4, c = e & 15;
-      const bool ok = j < nk;
-      cp_async16(Kt + j * DM_ROWB + c * 16, ok ? (const void*)(kt + (size_t)j * p.kv_ss + c * 8) : (const void*)kt, ok ? 16 : 0);
-    }
-    cp_async_commit();
+      for (int i = 0; i < DKT / 2; ++i) {
+        const bool ok = r0 + 2 * i < nk;
+        cp_async16_zs(kdst + i * 2 * DM_ROWB, ok ? (const void*)(ks + i * step2) : (const void*)kt, ok ? 16 : 0);
+      }
+      cp_async_commit();
 #pragma unroll 4
-    for (int e = lane; e < DKT * 16; e += 32) {
-      const int j = e >> 4, c = e & 15;
-      const bool ok = j < nk;
-      cp_async16(Vt + j * DM_ROWB + c * 16, ok ? (const void*)(vt + (size_t)j * p.kv_ss + c * 8) : (const void*)vt, ok ? 16 : 0);
+      for (int i = 0; i < DKT / 2; ++i) {
+        const bool ok = r0 + 2 * i < nk;
+        cp_async16_zs(vdst + i * 2 * DM_ROWB, ok ? (const void*)(vs + i * step2) : (const void*)vt, ok ? 16 : 0);
+      }
+      cp_async_commit();
     }
-    cp_async_commit();
   };
 
   int k0 = k_begin + w * DKT;
   if (k0 < k_end) issue_tile(k0);
   if (!has_new) mb::pdl_wait();
-  for (int i = threadIdx.x; i < 8 * DHD; i += blockDim.x) {
-    const int g = i / DHD, d = i % DHD;
-    Qs[g * DM_QPITCH + d] = (g < G) ? p.q[(size_t)b * p.q_sb + (size_t)(hk * G + g) * p.q_sh + d] : __float2bfloat16_rn(0.f);
-  }
-  __syncthreads();
+  // A fragments of Q (rows = the GQA group's heads, rows >= G zero): (row gid, dims ks*16 + 2 tid .. +1) and (.. + 8)
   uint32_t qa[8][2];
+  {
+    const bf16* qrow = p.q + (size_t)b * p.q_sb + (size_t)(hk * G + (gid < G ? gid : 0)) * p.q_sh + 2 * tid;
+    const bool q32 = !((p.q_sb | p.q_sh) & 1) && !(reinterpret_cast<uintptr_t>(p.q) & 3);
 #pragma unroll
-  for (int ks = 0; ks < 8; ++ks) {
-    qa[ks][0] = *reinterpret_cast<const uint32_t*>(Qs + gid * DM_QPITCH + ks * 16 + 2 * tid);
-    qa[ks][1] = *reinterpret_cast<const uint32_t*>(Qs + gid * DM_QPITCH + ks * 16 + 8 + 2 * tid);
+    for (int ks = 0; ks < 8; ++ks) {
+      uint32_t lo, hi;
+      if (q32) {
+        lo = *reinterpret_cast<const uint32_t*>(qrow + ks * 16);
+        hi = *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 8);
+      } else {
+        const unsigned short* qs = reinterpret_cast<const unsigned short*>(qrow + ks * 16);
+        lo = (uint32_t)qs[0] | ((uint32_t)qs[1] << 16);
+        hi = (uint32_t)qs[8] | ((uint32_t)qs[9] << 16);
+      }
+      qa[ks][0] = gid < G ? lo : 0u;
+      qa[ks][1] = gid < G ? hi : 0u;
+    }
   }
   float m_run = -INFINITY, l_run = 0.f;          // row gid's running max / sum (replicated over the 4 lanes of a quad)
   float o[16][4];
@@ -880,25 +922,34 @@ decode_attn_mma_kernel(DecP p, int G) {
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
       sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
-      const unsigned char* kr = Kt + (nt * 8 + gid) * DM_ROWB + 4 * tid;
+      // ldmatrix.x4: matrices 0..3 = keys nt*8..+7 x dims kp*32 + {0-7, 8-15, 16-23, 24-31}; lanes 8 i .. 8 i + 7 address matrix i
+      const unsigned char* kr = Kt + (nt * 8 + (lane & 7)) * DM_ROWB + (lane >> 3) * 16;
 #pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + ks * 32);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + ks * 32 + 16);
-        mma_16816(sc[nt], qa[ks][0], 0u, qa[ks][1], 0u, b0, b1);
+      for (int kp = 0; kp < 4; ++kp) {
+        uint32_t b0, b1, b2, b3;
+        ldmatrix_x4(b0, b1, b2, b3, kr + kp * 64);
+        mma_16816(sc[nt], qa[2 * kp][0], 0u, qa[2 * kp][1], 0u, b0, b1);
+        mma_16816(sc[nt], qa[2 * kp + 1][0], 0u, qa[2 * kp + 1][1], 0u, b2, b3);
       }
     }
     float mx = -INFINITY;
+    if (k0 + DKT <= k_end && !p.kbits) {         // a full tile with no key mask: nothing to test
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+      for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int kj = k0 + nt * 8 + 2 * tid + e;
-        bool vis = kj < k_end;
-        if (vis && p.kbits) vis = (p.kbits[(size_t)b * p.kbits_stride + (kj >> 5)] >> (kj & 31)) & 1u;
-        sc[nt][e] = vis ? sc[nt][e] * p.scale : -INFINITY;
-        mx = fmaxf(mx, sc[nt][e]);
-      }
+        for (int e = 0; e < 2; ++e) { sc[nt][e] *= p.scale; mx = fmaxf(mx, sc[nt][e]); }
+    } else {
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int kj = k0 + nt * 8 + 2 * tid + e;
+          bool vis = kj < k_end;
+          if (vis && p.kbits) vis = (p.kbits[(size_t)b * p.kbits_stride + (kj >> 5)] >> (kj & 31)) & 1u;
+          sc[nt][e] = vis ? sc[nt][e] * p.scale : -INFINITY;
+          mx = fmaxf(mx, sc[nt][e]);
+        }
+    }
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
     const float m_new = fmaxf(m_run, mx);
@@ -933,33 +984,40 @@ decode_attn_mma_kernel(DecP p, int G) {
       mma_16816(o[nt], pa[1][0], 0u, pa[1][1], 0u, v2, v3);
     }
     __syncwarp();
-    if (k0 + DWARPS * DKT < k_end) issue_tile(k0 + DWARPS * DKT);
+    if (k0 + DWARPS * DKT < k_end) issue_tile(k0 + DWARPS * DKT);     // only for contexts beyond 64 x 128 keys
   }
-  // combine the 4 warps through shared memory (the tiles are dead by now)
-  float* red = reinterpret_cast<float*>(dsm);            // [DWARPS][G][DHD + 2] floats
-  __syncthreads();
+  // every warp leaves its (unnormalised) partial rows in its OWN tile -- dead by now, so no barrier before the writes
+  float* mine = reinterpret_cast<float*>(Kt);                // [G][DM_RPITCH]: dims, then m, l
   if (gid < G) {
-    float* r = red + ((size_t)w * G + gid) * (DHD + 2);
+    float* r = mine + gid * DM_RPITCH;
 #pragma unroll
-    for (int nt = 0; nt < 16; ++nt) { r[nt * 8 + 2 * tid] = o[nt][0]; r[nt * 8 + 2 * tid + 1] = o[nt][1]; }
+    for (int nt = 0; nt < 16; ++nt) *reinterpret_cast<float2*>(r + nt * 8 + 2 * tid) = make_float2(o[nt][0], o[nt][1]);
     if (tid == 0) { r[DHD] = m_run; r[DHD + 1] = l_run; }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < G * DHD; i += blockDim.x) {
-    const int g = i / DHD, d = i % DHD;
+  for (int g = w; g < G; g += DWARPS) {                      // warp w merges head g: lanes own 4 consecutive dims
+    float mw[DWARPS], lw[DWARPS];
     float M_ = -INFINITY;
 #pragma unroll
-    for (int ww = 0; ww < DWARPS; ++ww) M_ = fmaxf(M_, red[((size_t)ww * G + g) * (DHD + 2) + DHD]);
-    float ov = 0.f, L = 0.f;
+    for (int ww = 0; ww < DWARPS; ++ww) {
+      const float* r = reinterpret_cast<const float*>(dsm + ww * DM_WARP_SMEM) + g * DM_RPITCH;
+      mw[ww] = r[DHD]; lw[ww] = r[DHD + 1];
+      M_ = fmaxf(M_, mw[ww]);
+    }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float L = 0.f;
 #pragma unroll
     for (int ww = 0; ww < DWARPS; ++ww) {
-      const float* r = red + ((size_t)ww * G + g) * (DHD + 2);
-      const float s2 = (r[DHD] == -INFINITY) ? 0.f : __expf(r[DHD] - M_);
-      ov += r[d] * s2; L += r[DHD + 1] * s2;
+      const float* r = reinterpret_cast<const float*>(dsm + ww * DM_WARP_SMEM) + g * DM_RPITCH;
+      const float s2 = (mw[ww] == -INFINITY) ? 0.f : __expf(mw[ww] - M_);
+      const float4 v = *reinterpret_cast<const float4*>(r + lane * 4);
+      acc.x += v.x * s2; acc.y += v.y * s2; acc.z += v.z * s2; acc.w += v.w * s2;
+      L += lw[ww] * s2;
     }
     float* out = p.part + (((size_t)b * p.H + hk * G + g) * p.splits + sp) * (DHD + 2);
-    out[d] = ov;
-    if (d == 0) { out[DHD] = M_; out[DHD + 1] = L; }
+    *reinterpret_cast<float2*>(out + lane * 4) = make_float2(acc.x, acc.y);
+    *reinterpret_cast<float2*>(out + lane * 4 + 2) = make_float2(acc.z, acc.w);
+    if (lane == 0) { out[DHD] = M_; out[DHD + 1] = L; }
   }
 }
 
@@ -1243,7 +1301,6 @@ static int decode_attn_launch(DecP& p, void* o, long long o_sb, long long o_sh, 
   p.splits = mb200_decode_attn_splits(p.ctx);
   p.chunk = ((p.ctx + p.splits - 1) / p.splits + DKT - 1) / DKT * DKT;      // tile-aligned chunks (see the kernel)
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid(p.splits, p.Hkv, p.B);
   static const int use_mma = [] {         // thread-safe one-time setup of every decode-attention variant
     cudaFuncSetAttribute(decode_attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem<1>());
     cudaFuncSetAttribute(decode_attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem<2>());
@@ -1253,8 +1310,13 @@ static int decode_attn_launch(DecP& p, void* o, long long o_sb, long long o_sh, 
     const char* e = getenv("MB200_DECODE_ATTN_MMA");
     return (e && e[0] == '0') ? 0 : 1;
   }();
+  static const int hk_fast = [] { const char* e = getenv("MB200_DECODE_GRID_HK"); return (e && e[0] == '0') ? 0 : 1; }();
   const bool pdl = mb::pdl_mode() != 0;
-  if (use_mma && G <= 8) mb::launch_ex(decode_attn_mma_kernel, grid, dim3(DWARPS * 32), DM_SMEM, st, pdl, p, G);
+  const bool mma = use_mma && G <= 8;
+  p.hk_fast = (mma && hk_fast && p.splits <= 65535) ? 1 : 0;
+  dim3 grid(p.splits, p.Hkv, p.B);
+  if (p.hk_fast) grid = dim3(p.Hkv, p.splits, p.B);
+  if (mma) mb::launch_ex(decode_attn_mma_kernel, grid, dim3(DWARPS * 32), DM_SMEM, st, pdl, p, G);
   else if (G == 1) mb::launch_ex(decode_attn_kernel<1>, grid, dim3(DWARPS * 32), dec_smem<1>(), st, pdl, p);
   else if (G == 2) mb::launch_ex(decode_attn_kernel<2>, grid, dim3(DWARPS * 32), dec_smem<2>(), st, pdl, p);
   else if (G == 4) mb::launch_ex(decode_attn_kernel<4>, grid, dim3(DWARPS * 32), dec_smem<4>(), st, pdl, p);

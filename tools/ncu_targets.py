@@ -39,6 +39,25 @@ elif which == "attn":
     for _ in range(3):
         o, lse = ops.attention_fwd(q, k, v, True, None, 128 ** -0.5)
         ops.attention_bwd(q, k, v, o, torch.randn_like(o), lse, True, None, 128 ** -0.5, fast=True)
+elif which in ("decode1", "decode16"):                   # decode-step kernels at bs 1 / 16 (bench_kernels.py decode shapes)
+    B = 1 if which == "decode1" else 16
+    x = torch.randn(B, 4096, device=dev).bfloat16(); xi = torch.randn(B, 14336, device=dev).bfloat16()
+    wq = (torch.randn(4096, 4096, device=dev) * 0.02).bfloat16(); wk = (torch.randn(1024, 4096, device=dev) * 0.02).bfloat16()
+    wv = (torch.randn(1024, 4096, device=dev) * 0.02).bfloat16()
+    wg = (torch.randn(14336, 4096, device=dev) * 0.02).bfloat16(); wu = (torch.randn(14336, 4096, device=dev) * 0.02).bfloat16()
+    wd = (torch.randn(4096, 14336, device=dev) * 0.02).bfloat16()
+    q = torch.empty(B, 4096, device=dev, dtype=torch.bfloat16); k = torch.empty(B, 1024, device=dev, dtype=torch.bfloat16)
+    v = torch.empty_like(k); act = torch.empty(B, 14336, device=dev, dtype=torch.bfloat16)
+    ctx = 6200
+    qd = torch.randn(B, 1, 32, 128, device=dev).bfloat16()
+    kc = torch.randn(B, ctx, 8, 128, device=dev).bfloat16(); vc = torch.randn(B, ctx, 8, 128, device=dev).bfloat16()
+    for _ in range(2):
+        ops._call("mb200_skinny_gemm3_bf16", ops._p(x), ops._p(wq), ops._p(wk), ops._p(wv), ops._p(q), ops._p(k), ops._p(v), B, 4096,
+                  1024, 1024, 4096, 4096, 4096, ops._st())
+        ops._call("mb200_skinny_swiglu_bf16", ops._p(x), ops._p(wg), ops._p(wu), ops._p(act), B, 14336, 4096, 4096, 4096, 14336, ops._st())
+        ops._call("mb200_skinny_gemm_bf16", ops._p(xi), ops._p(wd), ops._p(q), None, ops._p(q), B, 4096, 14336, 14336, 14336, 4096,
+                  4096, ops._st())
+        ops.decode_attention(qd, kc, vc, ctx, None, 128 ** -0.5)
 elif which == "merge":
     B, T, P, D = 4, 2048, 728, 4096
     ids = torch.randint(0, 128000, (B, T), device=dev)
