@@ -171,6 +171,13 @@ def bench_decode():
         kc = torch.randn(B, ctx, 8, 128, device=dev).bfloat16(); vc = torch.randn(B, ctx, 8, 128, device=dev).bfloat16()
         ms = timeit(lambda i: ops.decode_attention(qd, kc, vc, ctx, None, 128 ** -0.5), reps=20)
         report(f"decode attention ctx={ctx} bs={B}", ms, bytes_=2.0 * B * ctx * 8 * 128 * 2)
+        # same kernel over a head-major cache ([B, Hkv, ctx, hd] storage, passed as a strided view): a tile is one contiguous
+        # 8 KB piece instead of 32 x 256 B at a 2 KB stride -- isolates the DRAM-locality cost of the token-major layout
+        kh = torch.randn(B, 8, ctx, 128, device=dev).bfloat16().permute(0, 2, 1, 3)
+        vh = torch.randn(B, 8, ctx, 128, device=dev).bfloat16().permute(0, 2, 1, 3)
+        ms = timeit(lambda i: ops.decode_attention(qd, kh, vh, ctx, None, 128 ** -0.5), reps=20)
+        report(f"decode attention ctx={ctx} bs={B}, head-major cache view", ms, bytes_=2.0 * B * ctx * 8 * 128 * 2)
+        del kh, vh
         xr = torch.randn(B, 4096, device=dev).bfloat16(); w = torch.ones(4096, device=dev).bfloat16()
         ms = timeit(lambda i: ops.rms_norm(xr, w, 1e-5), reps=50)
         report(f"decode rmsnorm bs={B} (launch-latency bound)", ms, bytes_=2 * B * 4096 * 2)
