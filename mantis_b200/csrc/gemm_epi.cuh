@@ -24,6 +24,7 @@ struct GemmEpi {
   const bf16* aux0; const bf16* aux1; long long ld_aux;
   bf16* C2; long long ldc2;
   int tma_store;                        // output written (fp32 accumulate: reduce-added) by TMA from a swizzled smem tile
+  unsigned long long pol_a, pol_b, pol_c;   // L2 eviction priorities of the A / B loads and the C stores (2-CTA kernel)
 };
 
 struct SwigluArgs { int mode; const bf16* aux0; const bf16* aux1; long long ld_aux; bf16* C2; long long ldc2; };
@@ -267,8 +268,8 @@ __device__ __forceinline__ void epilogue_rows_tma(const GemmEpi& epi, const CUte
         __syncwarp();
         if (lane == 0) {
           const int tc0 = f32 ? col0 : col0 - (c & 1) * 32;
-          if (f32 && epi.addend) sm100::tma_reduce_add_2d(tmC, stage, tc0, row0);
-          else sm100::tma_store_2d(tmC, stage, tc0, row0);
+          if (f32 && epi.addend) sm100::tma_reduce_add_2d_hint(tmC, stage, tc0, row0, epi.pol_c);
+          else sm100::tma_store_2d_hint(tmC, stage, tc0, row0, epi.pol_c);
           sm100::tma_store_commit();
         }
       }

@@ -200,6 +200,7 @@ static int gemm_1cta_impl(const void* A, const void* B, void* C, const void* bia
   else         rc = mbtmap::make_2d(&tmB, B, K, N, ldb, 64, BK);        // [K,N]: box 64(N) x 64(K)
   if (rc) return rc;
   GemmEpi epi;
+  epi.pol_a = epi.pol_b = epi.pol_c = 0;              // (2-CTA kernel only)
   epi.C = C; epi.ldc = ldc; epi.bias = (const bf16*)bias; epi.addend = addend;
   epi.ld_add = ld_add; epi.act = act; epi.c_f32 = c_f32; epi.tma_store = 0; epi.mode = 0; epi.aux0 = nullptr; epi.aux1 = nullptr; epi.ld_aux = 0; epi.C2 = nullptr; epi.ldc2 = 0;
   if (swiglu) { epi.mode = swiglu->mode; epi.aux0 = swiglu->aux0; epi.aux1 = swiglu->aux1; epi.ld_aux = swiglu->ld_aux; epi.C2 = swiglu->C2; epi.ldc2 = swiglu->ldc2; }
