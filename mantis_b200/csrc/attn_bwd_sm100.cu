@@ -579,28 +579,50 @@ attn_bwd_dq2_sm100_kernel(const __grid_constant__ CUtensorMap tmDS, const __grid
   if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tDQ, 128); }
 }
 
-// ld[b,h,q] = {lse * log2(e) (+inf if the row is dead or q >= Sq), sum_d dO * O}   (one warp per row of 128, rows padded to Sq_pad)
+// ld[b,h,q] = {lse * log2(e) (+inf if the row is dead or q >= Sq), sum_d dO * O}, rows padded to Sq_pad.
+// A warp takes 8 heads of ONE token (adjacent warps the next 8): the [token][head][128] rows of O and dO are read as whole
+// contiguous 8 KB pieces with eight 16-byte loads in flight per lane (the one-row-per-warp version, q fastest, touched one
+// 256-byte piece per 8 KB row with two 8-byte loads per lane in flight: 2.2 TB/s).  A half-warp owns one head row.
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, const float* __restrict__ lse,
                   float2* __restrict__ ld, int B, int H, int Sq, int Sq_pad, long long o_sb, long long o_ss, long long o_sh,
                   long long g_sb, long long g_ss, long long g_sh) {
-  const int lane = threadIdx.x & 31;
-  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long total = (long long)B * H * Sq_pad;
-  if (row >= total) return;
-  const int qi = (int)(row % Sq_pad); const int h = (int)((row / Sq_pad) % H); const int b = (int)(row / ((long long)Sq_pad * H));
-  if (qi >= Sq) { if (lane == 0) ld[row] = make_float2(INFINITY, 0.f); return; }
-  const bf16* op = o + (size_t)b * o_sb + (size_t)qi * o_ss + (size_t)h * o_sh + lane * 4;
-  const bf16* gp = dout + (size_t)b * g_sb + (size_t)qi * g_ss + (size_t)h * g_sh + lane * 4;
-  const uint2 a = *reinterpret_cast<const uint2*>(op), g = *reinterpret_cast<const uint2*>(gp);
-  const bf162* ah = reinterpret_cast<const bf162*>(&a); const bf162* gh = reinterpret_cast<const bf162*>(&g);
-  float s = 0.f;
+  const int lane = threadIdx.x & 31, half = lane >> 4, l16 = lane & 15;
+  const int hgroups = (H + 7) / 8;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long tok = wid / hgroups;
+  const int hg = (int)(wid % hgroups);
+  if (tok >= (long long)B * Sq_pad) return;
+  const int b = (int)(tok / Sq_pad), qi = (int)(tok % Sq_pad);
+  const bool live = qi < Sq;
+  int4 a[4], g[4];
 #pragma unroll
-  for (int i = 0; i < 2; ++i) { float2 x = __bfloat1622float2(ah[i]), y = __bfloat1622float2(gh[i]); s += x.x * y.x + x.y * y.y; }
-  s = mb::warp_sum(s);
-  if (lane == 0) {
-    const float L = lse[((size_t)b * H + h) * Sq + qi];
-    ld[row] = make_float2((L == -INFINITY) ? INFINITY : L * LOG2E, s);
+  for (int it = 0; it < 4; ++it) {
+    const int h = hg * 8 + it * 2 + half;
+    if (live && h < H) {
+      a[it] = mb::ld_stream(reinterpret_cast<const int4*>(o + (size_t)b * o_sb + (size_t)qi * o_ss + (size_t)h * o_sh + l16 * 8));
+      g[it] = mb::ld_stream(reinterpret_cast<const int4*>(dout + (size_t)b * g_sb + (size_t)qi * g_ss + (size_t)h * g_sh + l16 * 8));
+    } else {
+      a[it] = make_int4(0, 0, 0, 0); g[it] = make_int4(0, 0, 0, 0);
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int h = hg * 8 + it * 2 + half;
+    const bf162* ah = reinterpret_cast<const bf162*>(&a[it]); const bf162* gh = reinterpret_cast<const bf162*>(&g[it]);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 x = __bfloat1622float2(ah[i]), y = __bfloat1622float2(gh[i]); s += x.x * y.x + x.y * y.y; }
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);      // within the 16-lane half
+    if (l16 == 0 && h < H) {
+      float2 out = make_float2(INFINITY, 0.f);
+      if (live) {
+        const float L = lse[((size_t)b * H + h) * Sq + qi];
+        out = make_float2((L == -INFINITY) ? INFINITY : L * LOG2E, s);
+      }
+      ld[((size_t)b * H + h) * Sq_pad + qi] = out;
+    }
   }
 }
 
@@ -632,8 +654,8 @@ static int attn_bwd_impl(const void* q, const void* k, const void* v, const void
   const long long dk_ss = (long long)Hkv * hd, dk_sb = (long long)Sk * Hkv * hd;
   const int Sq_pad = (int)mb200_attn_bwd_sq_pad(Sq);
   {
-    const long long rows = (long long)B * H * Sq_pad;
-    attn_delta_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>((const bf16*)o, (const bf16*)dout, lse, (float2*)delta,
+    const long long warps = (long long)B * Sq_pad * ((H + 7) / 8);
+    attn_delta_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>((const bf16*)o, (const bf16*)dout, lse, (float2*)delta,
                                                                          B, H, Sq, Sq_pad, strides[9], strides[10], strides[11],
                                                                          dq_sb, dq_ss, hd);
   }

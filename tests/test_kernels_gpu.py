@@ -132,6 +132,30 @@ def test_rmsnorm(ops, cuda, dtype):
         assert (y.detach().float() - hf.float()).abs().max().item() <= 2 * torch.finfo(dtype).eps * hf.abs().max().item()
 
 
+@pytest.mark.parametrize("n,D", [(1, 4096), (3, 1024), (777, 2048), (2500, 4096)])
+def test_rmsnorm_residual_backward_one_pass(ops, cuda, n, D):
+    """rms_norm_res: (norm(x), x) whose backward folds the residual branch's gradient into dx and produces dx and the dw
+    partials in ONE pass over x / dy (rmsnorm_bwd_fused_kernel); row counts around the grid size and the 2-row step."""
+    torch.manual_seed(40 + n)
+    x = torch.randn(n, D, device=cuda).bfloat16().requires_grad_(True)
+    w = (1 + 0.1 * torch.randn(D, device=cuda)).bfloat16().requires_grad_(True)
+    y, r = ops.rms_norm_res(x, w, 1e-5)
+    gy = torch.randn_like(y); gr = torch.randn_like(r)
+    torch.autograd.backward((y, r), (gy, gr))
+    xr = x.detach().float().requires_grad_(True); wr = w.detach().float().requires_grad_(True)
+    yr = wr * (xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + 1e-5))
+    torch.autograd.backward((yr, xr * 1.0), (gy.float(), gr.float()))
+    assert _rel(y, yr) < 8e-3 and torch.equal(r, x)
+    assert _rel(x.grad, xr.grad) < 8e-3 and _rel(w.grad, wr.grad) < 8e-3
+    # the same numbers as the unfused pair norm + autograd's add, to bf16 rounding of the sum
+    x2 = x.detach().clone().requires_grad_(True); w2 = w.detach().clone().requires_grad_(True)
+    y2 = ops.rms_norm(x2, w2, 1e-5)
+    y2.backward(gy)
+    ref_dx = (x2.grad.float() + gr.float())
+    assert (x.grad.float() - ref_dx).abs().max().item() <= 2 ** -6 * ref_dx.abs().max().item()
+    assert _rel(w.grad, w2.grad) < 4e-3
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_layernorm(ops, cuda, dtype):
     torch.manual_seed(5)

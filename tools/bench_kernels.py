@@ -100,6 +100,12 @@ def bench_rowwise():
     x = torch.randn(M, D, device=dev).bfloat16(); w = torch.ones(D, device=dev).bfloat16()
     ms = timeit(lambda i: ops.rms_norm(x, w, 1e-5))
     report("rmsnorm fwd [7864,4096]", ms, bytes_=2 * M * D * 2)
+    xg = x.clone().requires_grad_(True); wg = w.clone().requires_grad_(True)
+    yy, rr = ops.rms_norm_res(xg, wg, 1e-5)
+    gy = torch.randn_like(yy); gr = torch.randn_like(rr)
+    ms = timeit(lambda i: torch.autograd.grad((yy, rr), (xg, wg), (gy, gr), retain_graph=True))
+    report("rmsnorm bwd (dx + dw, residual gradient folded in) [7864,4096]", ms, bytes_=4 * M * D * 2,
+           note="algorithmic = x, dy, dres read + dx written")
     g = torch.randn(M, 14336, device=dev).bfloat16(); u = torch.randn(M, 14336, device=dev).bfloat16()
     ms = timeit(lambda i: ops.swiglu(g, u))
     report("swiglu fwd [7864,14336]", ms, bytes_=3 * M * 14336 * 2)

@@ -10,5 +10,6 @@ python tools/ncu_to_json.py gpurun_out/ncu_gemm2cta_final.ncu-rep gemm_sm100_2ct
 python tools/ncu_to_json.py gpurun_out/ncu_merge_rows_final.ncu-rep merge_rows_kernel profiles/ncu_merge_rows_r02_final.json >> gpurun_out/ncu_to_json.log 2>&1
 cp profiles/ncu_gemm2cta_r02_final.json profiles/ncu_merge_rows_r02_final.json gpurun_out/
 timeout 600 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
-timeout 200 python tools/bench_kernels.py gemm attn decode > gpurun_out/kernel_bench_final.jsonl 2>&1
+timeout 250 python tools/bench_kernels.py gemm attn row decode > gpurun_out/kernel_bench_final.jsonl 2>&1
+MB200_RMSNORM_BWD_PREFETCH=0 timeout 100 python tools/bench_kernels.py row > gpurun_out/kernel_bench_row_noprefetch.jsonl 2>&1
 echo evidence done
